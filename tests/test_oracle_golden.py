@@ -1,0 +1,130 @@
+"""Pins the oracle restatement (oracle/vt_oracle.py) to outputs of the UNMODIFIED reference
+(tests/golden/*.npz, produced by oracle/gen_golden.py).  CPU only."""
+import pytest
+import torch
+
+from oracle import vt_oracle as orc
+from vla_touch_b200 import shapes as shp
+from vla_touch_b200 import synthetic as syn
+import vt_testutil as U
+
+TOL = dict(rtol=0, atol=3e-6)
+
+
+@pytest.mark.parametrize("A", [7, 10])
+def test_normalize_denormalize(A):
+    g = U.golden(f"norm_A{A}")
+    st = syn.synth_stats_varied(A, seed=3)
+    x = syn.det_uniform("norm.x", (3, 16, A), 3, -2.0, 2.0)
+    assert torch.equal(orc.normalize_actions(x, st, "vla"), g["vla_n"])
+    assert torch.equal(orc.normalize_actions(x, st, "expert"), g["exp_n"])
+    assert torch.equal(orc.denormalize_actions(x, st, "expert"), g["exp_dn"])
+    with pytest.raises(ValueError):
+        orc.normalize_actions(x, st, "nope")
+
+
+@pytest.mark.parametrize("case", U.DINO_CASES, ids=[c[0] for c in U.DINO_CASES])
+def test_dinov2(case):
+    tag, hidden, heads, layers, hw, batch, kind, seed = case
+    g = U.golden(tag)
+    sd = {k[len("dino."):]: v for k, v in U.dino_sd(hidden, layers, seed).items()}
+    sd = U.dino_sd(hidden, layers, seed)
+    img = U.images_for(kind, "dino.img", batch, hw, seed)
+    out = orc.dino_encoder_forward(sd, img, heads)
+    torch.testing.assert_close(out, g["cls"], **TOL)
+    if "h_emb" in g:
+        pv = orc.dinov2_preprocess(img)
+        h = orc.dinov2_embeddings(sd, pv[:1])
+        idx = U.TOK_IDX(h.shape[1])
+        torch.testing.assert_close(h[:, idx], g["h_emb"], **TOL)
+        for i in range(layers):
+            h = orc.dinov2_layer(sd, i, h, heads)
+            torch.testing.assert_close(h[:, idx], g[f"h_l{i}"], rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("A,Fd", [(10, 3), (7, 64)])
+def test_state_encoder_and_unet(A, Fd):
+    enc = U.enc_sd(2 * 384 + A + Fd, 21)
+    xin = syn.det_normal("enc.in", (4, 2 * 384 + A + Fd), 21)
+    torch.testing.assert_close(orc.mlp3_gelu(enc, xin), U.golden(f"enc_A{A}_F{Fd}")["out"], **TOL)
+    v_sd, s_sd = U.net_sd(A, 21, "v_net"), U.net_sd(A, 21, "s_net")
+    for T in (16, 32, 48, 64):
+        g = U.golden(f"unet_A{A}_T{T}")
+        x = syn.det_uniform("unet.x", (3, T, A), 22, -1.0, 1.0)
+        cond = syn.det_normal("unet.cond", (3, 256), 22)
+        t = torch.tensor([0.3, 0.001, 0.999])
+        torch.testing.assert_close(orc.unet_forward(v_sd, x, t, cond), g["v"], rtol=0, atol=1e-5)
+        torch.testing.assert_close(orc.unet_forward(s_sd, x, t[:1].expand(3), cond), g["s"], rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("A,T,n", [(10, 16, 10), (7, 64, 10), (7, 64, 50)])
+def test_sde_vs_recorded_noise(A, T, n):
+    g = U.golden(f"sde_A{A}_T{T}_n{n}")
+    v_sd, s_sd = U.net_sd(A, 1021, "v_net"), U.net_sd(A, 1021, "s_net")   # EMA shadow (seed+1000)
+    x0 = syn.det_uniform("sde.x0", (2, T, A), 23, -1.0, 1.0)
+    cond = syn.det_normal("sde.cond", (2, 256), 23)
+    out, traj = orc.sde_vs(v_sd, s_sd, x0, cond, n, 0.03, g["noise"], return_traj=True)
+    torch.testing.assert_close(traj[1], g["x1"], rtol=0, atol=1e-5)
+    torch.testing.assert_close(out, g["out"], rtol=0, atol=5e-5)
+    # live (non-EMA) weights must NOT reproduce it: sample() runs under ema.average_parameters()
+    bad = orc.sde_vs(U.net_sd(A, 21, "v_net"), U.net_sd(A, 21, "s_net"), x0, cond, n, 0.03, g["noise"])
+    assert (bad - g["out"]).abs().max() > 1e-3
+
+
+@pytest.mark.parametrize("A,T", [(10, 16), (7, 64)])
+def test_sde_vs_beta0(A, T):
+    g = U.golden(f"sde_A{A}_T{T}_n10_beta0")
+    x0 = syn.det_uniform("sde.x0", (2, T, A), 23, -1.0, 1.0)
+    cond = syn.det_normal("sde.cond", (2, 256), 23)
+    out = orc.sde_vs(U.net_sd(A, 1021, "v_net"), U.net_sd(A, 1021, "s_net"), x0, cond, 10, 0.0,
+                     torch.zeros(10, 2, T, A))
+    torch.testing.assert_close(out, g["out"], rtol=0, atol=5e-5)
+
+
+def test_sde_schedule_step_count_quirk():
+    # n = int(1/float(1/diffuse_step)) differs from diffuse_step for some values
+    for ds, n in ((10, 10), (50, 50), (93, 92), (99, 98)):
+        assert orc.sde_schedule(ds)[0] == n
+
+
+@pytest.mark.parametrize("A,T", [(10, 16), (7, 64)])
+def test_losses(A, T):
+    g = U.golden(f"loss_A{A}_T{T}")
+    batch = {"obs_cond": syn.det_normal("loss.cond", (3, 256), 24),
+             "expert_act": syn.det_uniform("loss.exp", (3, T, A), 24, -1.0, 1.0),
+             "vla_act": syn.det_uniform("loss.vla", (3, T, A), 24, -1.0, 1.0)}
+    loss, v, s, b = orc.bridge_losses(U.net_sd(A, 21), batch["obs_cond"], batch["expert_act"], batch["vla_act"],
+                                      g["step"], g["z_unit"])
+    for got, key in ((loss, "loss"), (v, "v_loss"), (s, "s_loss"), (b, "b_loss")):
+        torch.testing.assert_close(got, g[key], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("tag", list(U.PREDICT_CASES))
+def test_predict(tag):
+    c = U.predict_case(tag)
+    cond = orc.encode_observation(c["dino"], c["enc"], c["heads"], c["state"], c["img1"], c["img2"], c["forces"])
+    torch.testing.assert_close(cond, c["gold"]["cond"], rtol=0, atol=2e-5)
+    out = orc.predict(c["dino"], c["enc"], c["v_ema"], c["s_ema"], c["stats"], c["heads"], c["state"], c["vla"],
+                      c["img1"], c["img2"], c["forces"], c["steps"], 0.03, c["gold"]["noise"])
+    torch.testing.assert_close(out, c["gold"]["out"], rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("A,Fd,T", [(10, 3, 16), (7, 64, 32)])
+def test_lstm(A, Fd, T):
+    g = U.golden(f"lstm_A{A}_F{Fd}_T{T}")
+    mods = {
+        "force_encoder": syn.synth_state_dict(shp.mlp_shapes([Fd, 128, 128]), 41, "lstm.force_encoder."),
+        "lstm": syn.synth_state_dict(shp.lstm_shapes(128 + A), 41, "lstm.lstm."),
+        "output_head": syn.synth_state_dict(shp.lstm_head_shapes(256, A), 41, "lstm.output_head."),
+    }
+    st = syn.synth_stats_varied(A, 41)
+    vla = syn.det_uniform("lstm.vla", (3, T, A), 41, -1.0, 1.0)
+    forces = syn.det_normal("lstm.forces", (3, T, Fd), 41)
+    cond = syn.det_normal("lstm.cond", (3, 256), 41)
+    expert = syn.det_uniform("lstm.exp", (3, T, A), 41, -1.0, 1.0)
+    vla_n = orc.normalize_actions(vla, st, "vla")
+    fwd = orc.lstm_forward(mods, vla_n, cond, forces)
+    torch.testing.assert_close(fwd, g["fwd"], rtol=0, atol=1e-5)
+    torch.testing.assert_close(torch.nn.functional.mse_loss(fwd, expert), g["loss"], rtol=1e-5, atol=1e-6)
+    # predict_sequence == step-by-step forward + expert de-normalisation (eval mode) :288-319
+    torch.testing.assert_close(orc.denormalize_actions(fwd, st, "expert"), g["seq"], rtol=0, atol=1e-5)
