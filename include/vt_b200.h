@@ -1,0 +1,277 @@
+/*
+ * vt_b200.h -- C ABI of libvt_b200.so: the sm_100a (B200) kernels of the VLA-Touch action-refinement hot path.
+ *
+ * Plain C, no torch types.  Every pointer named `*_dev`/inside a descriptor is a DEVICE pointer owned by the
+ * caller; `stream` is a cudaStream_t passed as void*.  Every function returns 0 on success or a negative
+ * VT_E_* code; vt_last_error() returns a human-readable message for the calling thread.  Nothing throws.
+ *
+ * The library executes PROGRAMS: ordered lists of pre-encoded kernel launches (TMA tensor maps are encoded once
+ * when an op is added).  The Python host (vla_touch_b200/) builds one program per reference function it
+ * replaces -- file:line below are into /root/reference/VLA/residual_controller unless prefixed HF: (transformers
+ * modeling_dinov2.py, the un-vendored dependency holding the DinoV2 arithmetic):
+ *
+ *   DINOv2Encoder.forward                      visual_encoder.py:56-106, HF:97-149,199-235,367-386,473-485
+ *       -> IMGSTATS, PATCHIFY, GEMM(patch-embed), CLS, then per layer LAYERNORM, GEMM(qkv), ATTENTION,
+ *          GEMM(out-proj + LayerScale + residual), LAYERNORM, GEMM(fc1 + GELU), GEMM(fc2 + LayerScale + residual),
+ *          final LAYERNORM on the CLS rows
+ *   DiffusionController.encode_observation     bridge_controller.py:112-134 (state_encoder :42-48)
+ *       -> PACK, 3x GEMM(+GELU)
+ *   normalize_actions / denormalize_actions    controller_dataset.py:303-384             -> AFFINE
+ *   DiffusionConditionalUnet1D.forward         bridge/networks/conditional_unet_1D.py:194-247 (blocks :40-105)
+ *       -> TEMBED, GEMM(time MLP), GEMM(FiLM), 36x GEMM(implicit conv + GroupNorm + Mish + FiLM + residual)
+ *   StochasticInterpolants.sample -> sde_vs    bridge/bridge_model.py:259-279,334-387     -> SDE_STEP per step
+ *   TactileLSTMController.forward / predict    lstm_step_controller.py:170-286            -> GEMM, LSTM_SEQ, HEAD
+ */
+#ifndef VT_B200_H_
+#define VT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VT_ABI_VERSION 1
+
+enum { VT_OK = 0, VT_E_INVALID = -1, VT_E_CUDA = -2, VT_E_UNSUPPORTED = -3, VT_E_NODEVICE = -4 };
+enum { VT_BF16 = 0, VT_F32 = 1, VT_U8 = 2 };
+enum { VT_ACT_NONE = 0, VT_ACT_GELU = 1, VT_ACT_MISH = 2 };
+enum { VT_EPI_LINEAR = 0, VT_EPI_GN = 1 };
+enum { VT_LAYOUT_BHWC = 0, VT_LAYOUT_BCHW = 1 };
+#define VT_MAX_TAPS 8
+
+/* ------------------------------------------------------------------------------------------------------------
+ * GEMM / implicit-GEMM convolution on the tcgen05 tensor cores (replaces nn.Linear, nn.Conv1d, nn.ConvTranspose1d,
+ * nn.Conv2d(k14,s14) + the op that follows them: bias, GELU/Mish, LayerScale+residual, GroupNorm+Mish+FiLM+residual).
+ *
+ *   out[g][row(m)][n] = epilogue( sum_{tap,c} A[g][b][tq + tap_t[tap]][tap_p[tap]][a_c0 + c] * W[g][n][tap*kc + c] )
+ *
+ * A is a channels-last activation viewed as 5-D (channel, phase, tq, sample, group); rows outside [0, a_T) read as
+ * zero (= the convolution's zero padding).  A logical output row m = b * t_out + t  (b sample, t position).
+ * Tiles hold 128 rows: t_box positions x b_box samples (t_box * b_box <= 128); either b_box == 1 and t_box == 128
+ * (plain row-major GEMM over a_T rows of one "sample"), or t_box == t_out (whole samples per tile).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct vt_gemm_desc {
+  /* A operand */
+  const void* a;      /* base of the activation tensor */
+  int32_t in_dtype;   /* VT_BF16 (kind::f16) or VT_F32 (kind::tf32); W has the same dtype */
+  int32_t a_C;        /* channels visible to TMA from `a` (reads beyond are zero) */
+  int32_t a_P;        /* phases: positions are stored as (tq, phase), position = tq * a_P + phase */
+  int32_t a_T;        /* tq extent per sample */
+  int32_t a_B;        /* samples */
+  int32_t a_G;        /* 1: all groups read the same A; else == G */
+  int64_t a_ld;       /* elements between consecutive positions */
+  int64_t a_sB;       /* elements between samples */
+  int64_t a_sG;       /* elements between groups */
+  int32_t a_c0;       /* first channel */
+  int32_t kc;         /* channels per tap, multiple of 64 (bf16) / 32 (f32) */
+  int32_t taps;
+  int32_t tap_p[VT_MAX_TAPS];
+  int32_t tap_t[VT_MAX_TAPS];
+  int32_t t_box, b_box;
+  int32_t passes;     /* 1, or 3 = split-tf32 (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo), in_dtype == VT_F32 only */
+  int32_t a_plane;    /* channel distance from the hi to the lo plane of A (passes == 3) */
+  int32_t w_plane;    /* K distance from the hi to the lo plane of W (passes == 3) */
+  /* W operand: [G][n_pad][w_ld] with K contiguous */
+  const void* w;
+  int32_t n_pad;      /* rows of W per group, multiple of bn */
+  int32_t w_ld;       /* elements per W row (>= taps * kc, multiple of 8) */
+  /* problem */
+  int32_t G;
+  int32_t M;          /* logical rows per group */
+  int32_t N;          /* valid output columns per group */
+  int32_t bn;         /* tile width: 32 or 128 (VT_EPI_GN: 128) */
+  /* output mapping: q = m / row_div, rem = m % row_div, out row = q*out_q + rem*out_r + out_off */
+  void* out;
+  int32_t out_dtype;
+  int32_t ldc;
+  int64_t out_g;      /* elements between groups */
+  int32_t row_div;
+  int64_t out_q, out_r, out_off;
+  int64_t out_plane;  /* >0 (f32 out): also store the tf32 lo plane at +out_plane elements */
+  /* epilogue */
+  int32_t epi;        /* VT_EPI_* */
+  int32_t act;        /* VT_ACT_* (LINEAR only) */
+  const float* bias;      /* [G][n_pad] or null */
+  const float* colscale;  /* [N] (LayerScale) or null, LINEAR only */
+  const void* res;        /* residual added last: f32 for LINEAR, out_dtype for GN; null = none */
+  int32_t ldres;
+  int64_t res_g, res_q, res_r, res_off;
+  int64_t res_plane;      /* >0 (GN, f32): residual stored as tf32 hi|lo planes, both are added */
+  const float* gn_gamma;  /* [G][n_pad] */
+  const float* gn_beta;   /* [G][n_pad] */
+  int32_t gn_group_ch;    /* channels per GroupNorm group: 32 or 64 */
+  float gn_eps;
+  const float* film_c;    /* [G][B][film_ld]: per-sample FiLM (scale at column n, shift at film_C + n) or null */
+  const float* film_t;    /* [G][film_ld]: batch-independent FiLM part added to film_c, or null */
+  int64_t film_g;         /* elements between groups of film_c */
+  int64_t film_tg;        /* elements between groups of film_t */
+  int32_t film_ld, film_C, film_off;
+} vt_gemm_desc;
+
+/* LayerNorm over the last dim (HF:354,359,449; lstm_step_controller.py:76-82).  Row r of the output is computed
+ * from input row r * in_row_stride.  D in {256, 384, 768, 1024}. */
+typedef struct vt_ln_desc {
+  const float* x;
+  int64_t in_ld;          /* elements between input rows that are `in_row_stride` = 1 apart */
+  int64_t in_row_stride;  /* 1 = every row; N_tokens = CLS rows only */
+  int32_t rows, D;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  void* out;
+  int32_t out_dtype;
+  int64_t out_ld;
+  int64_t out_plane;      /* >0 (f32): tf32 hi/lo split */
+  int32_t act;            /* VT_ACT_GELU applies GELU after the affine (LSTM head) */
+} vt_ln_desc;
+
+/* Multi-head softmax(QK^T/sqrt(64))V over packed qkv rows [images*tokens][3*D] (HF:199-235). head_dim == 64. */
+typedef struct vt_attn_desc {
+  const void* qkv;   /* bf16 [images*tokens][3*D]; for in_dtype F32: f32 */
+  void* ctx;         /* [images*tokens][ctx_ld] */
+  int32_t in_dtype;  /* VT_BF16: tcgen05 path; VT_F32: fp32 CUDA-core path (parity mode) */
+  int32_t images, tokens, heads;
+  int64_t ctx_ld;    /* elements between ctx rows (>= D) */
+  int64_t ctx_plane; /* >0 (f32): tf32 hi/lo split of ctx */
+} vt_attn_desc;
+
+/* visual_encoder.py:66-81,95-106: batch-global predicates max>1 and mean<0.5, evaluated on the device. */
+typedef struct vt_imgstats_desc {
+  const void* img;
+  int32_t dtype;     /* VT_U8 or VT_F32 */
+  int64_t count;     /* elements in the whole call tensor */
+  float* partial;    /* scratch, 8-byte aligned: 1024 floats followed by 1024 doubles (12 KiB) */
+  int32_t* flags;    /* out: flags[0] = max > 1 (divide by 255), flags[1] = mean >= 0.5 (ImageNet normalise) */
+} vt_imgstats_desc;
+
+/* layout fix + /255 + ImageNet normalise + 14x14 im2col (visual_encoder.py:70-106, HF:139-149) */
+typedef struct vt_patchify_desc {
+  const void* img;
+  int32_t dtype, layout;
+  int32_t images, H, W, patch;
+  const int32_t* flags;
+  void* out;          /* [images * (H/patch)*(W/patch)][out_ld], k = c*patch*patch + i*patch + j */
+  int32_t out_dtype;
+  int32_t out_cols;   /* logical columns written per row (>= 3*patch*patch, zero padded) */
+  int32_t out_ld;     /* row pitch in elements */
+  int64_t out_plane;
+} vt_patchify_desc;
+
+/* h[b][0][:] = cls + pos[0]  (HF:104-112) */
+typedef struct vt_cls_desc {
+  const float* cls;
+  const float* pos;
+  float* h;
+  int32_t images, tokens, D;
+} vt_cls_desc;
+
+/* Generic row packer: out[r][dst_c0 + c] = cast(act(src[r * src_ld + c])), c < cols; used for torch.cat
+ * (bridge_controller.py:129-132) and Mish(gf) (conditional_unet_1D.py:76-80). */
+typedef struct vt_pack_desc {
+  const float* src;
+  int64_t src_ld;
+  int32_t rows, cols;
+  int32_t act;
+  void* out;
+  int32_t out_dtype;
+  int64_t out_ld;
+  int32_t dst_c0;
+  int64_t out_plane;
+  int32_t zero_to;    /* >cols: also zero-fill columns [dst_c0+cols, dst_c0+zero_to) */
+} vt_pack_desc;
+
+/* normalize_actions / denormalize_actions, controller_dataset.py:303-384 (padding factor 1.4) */
+typedef struct vt_affine_desc {
+  const float* x;     /* [rows][A] */
+  float* out;         /* [rows][A] */
+  const float* mins;  /* [A] */
+  const float* maxs;  /* [A] */
+  int32_t rows, A;
+  int32_t denorm;     /* 0 normalise (with the safe_range guard), 1 de-normalise (without) */
+  float pad;          /* padding factor (reference default 1.4) */
+  void* xpad;         /* optional: also write channel-padded copy [rows][xpad_ld] in xpad_dtype */
+  int32_t xpad_dtype, xpad_ld;
+  int64_t xpad_plane;
+  const float* add;   /* optional [rows][A] added after the map (LSTM: vla + delta) */
+} vt_affine_desc;
+
+/* SinusoidalPosEmb, conditional_unet_1D.py:7-19: out[r] = cat(sin(t_r f_i), cos(t_r f_i)) */
+typedef struct vt_tembed_desc {
+  const float* t;
+  int32_t rows, dim;
+  void* out;
+  int32_t out_dtype;
+  int64_t out_ld;
+  int64_t out_plane;
+} vt_tembed_desc;
+
+/* One Euler-Maruyama step of sde_vs, bridge_model.py:352-385:
+ *   s' = s*ginv;  b = v - dgg*s'*eps;  x += (b + eps*s')*dt + nscale*(d*z)
+ * z = noise[row][a] when noise != null, else Philox4x32-10(seed, step, element). */
+typedef struct vt_sde_desc {
+  float* x;           /* [rows][A] in/out */
+  const float* v;     /* [rows][A] */
+  const float* s;     /* [rows][A] */
+  const float* noise; /* [rows][A] or null */
+  int32_t rows, A;
+  float ginv, dgg, eps, dt, nscale, d;
+  uint64_t seed;
+  const uint64_t* seed_dev; /* optional: seed read from device memory at run time (added to `seed`) */
+  int32_t step;
+  void* xpad;         /* channel-padded copy of the new x for the next U-Net evaluation */
+  int32_t xpad_dtype, xpad_ld;
+  int64_t xpad_plane;
+} vt_sde_desc;
+
+/* nn.LSTM (gate order i,f,g,o), lstm_step_controller.py:66-73,196-204: the input projections xw = W_ih x + b_ih
+ * + b_hh are precomputed by a GEMM; this op runs the recurrence over T steps for one layer. */
+typedef struct vt_lstm_desc {
+  const float* xw;    /* [B][T][4H] */
+  const float* w_hh;  /* W_hh TRANSPOSED: [H][4H] */
+  float* h;           /* [B][H] in/out state */
+  float* c;           /* [B][H] in/out state */
+  void* y;            /* [B][T][y_ld] hidden outputs */
+  int32_t y_dtype;
+  int64_t y_ld;
+  int32_t B, T, H;
+} vt_lstm_desc;
+
+typedef struct vt_program vt_program;
+
+const char* vt_last_error(void);
+int vt_abi_version(void);
+/* sm count / compute capability of the current device; VT_E_NODEVICE without a GPU */
+int vt_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+int vt_program_create(vt_program** out);
+int vt_program_destroy(vt_program* p);
+int vt_program_num_ops(const vt_program* p);
+/* number of kernel launches vt_program_run(p, first, count) performs */
+int vt_program_num_launches(const vt_program* p, int first, int count);
+
+int vt_program_add_gemm(vt_program* p, const vt_gemm_desc* d);
+int vt_program_add_layernorm(vt_program* p, const vt_ln_desc* d);
+int vt_program_add_attention(vt_program* p, const vt_attn_desc* d);
+int vt_program_add_imgstats(vt_program* p, const vt_imgstats_desc* d);
+int vt_program_add_patchify(vt_program* p, const vt_patchify_desc* d);
+int vt_program_add_cls(vt_program* p, const vt_cls_desc* d);
+int vt_program_add_pack(vt_program* p, const vt_pack_desc* d);
+int vt_program_add_affine(vt_program* p, const vt_affine_desc* d);
+int vt_program_add_tembed(vt_program* p, const vt_tembed_desc* d);
+int vt_program_add_sde(vt_program* p, const vt_sde_desc* d);
+int vt_program_add_lstm(vt_program* p, const vt_lstm_desc* d);
+
+/* Launch ops [first, first+count) in order on `stream` (count < 0: to the end). */
+int vt_program_run(vt_program* p, int first, int count, void* stream);
+/* Capture ops [first, first+count) into a CUDA graph (replacing any earlier one); launch it. */
+int vt_program_graph_build(vt_program* p, int first, int count);
+int vt_program_graph_launch(vt_program* p, void* stream);
+
+/* bicubic (A=-0.75, align_corners=False) resize of the patch position embeddings, HF:57-95: src [s*s][D] -> dst [nh*nw][D] */
+int vt_pos_embed_resize(const float* src_dev, int32_t s, float* dst_dev, int32_t nh, int32_t nw, int32_t D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VT_B200_H_ */

@@ -1,0 +1,271 @@
+"""TEST INFRASTRUCTURE ONLY -- a CPU interpreter of plan descriptors.
+
+Interprets the very structs that cross the C ABI (include/vt_b200.h) with plain torch ops on CPU tensors,
+following the documented semantics of each op.  It lets the host-side plan logic (tile boxes, conv taps,
+weight packing, buffer wiring, FiLM offsets ...) be validated against the oracle without a GPU; on the
+B200 the kernels are then checked against the same expectations.  Never imported by the product package.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from vla_touch_b200 import native as nv
+from vla_touch_b200.plan import TORCH_DT, Plan, tf32_round
+
+
+def _flat(plan: Plan, address, dtype):
+    return plan.resolve(address, dtype)
+
+
+def _act(x, act, fast=False):
+    if act == nv.ACT_GELU:
+        return F.gelu(x)
+    if act == nv.ACT_MISH:
+        return F.mish(x)
+    return x
+
+
+def _store(plan, address, dtype_code, idx, vals, plane=0):
+    """scatter vals (float32) to flat element indices idx of the buffer at `address`"""
+    dt = TORCH_DT[dtype_code]
+    flat = _flat(plan, address, dt)
+    if dtype_code == nv.VT_F32 and plane > 0:
+        hi = tf32_round(vals.float().contiguous())
+        flat[idx.reshape(-1)] = hi.reshape(-1)
+        flat[idx.reshape(-1) + plane] = (vals.float() - hi).reshape(-1)
+    else:
+        flat[idx.reshape(-1)] = vals.reshape(-1).to(dt)
+
+
+def emu_gemm(plan: Plan, d: nv.GemmDesc):
+    in_dt = TORCH_DT[d.in_dtype]
+    es_k = 64 if d.in_dtype == nv.VT_BF16 else 32
+    assert d.kc % es_k == 0
+    G, M, N = d.G, d.M, d.N
+    a_flat = _flat(plan, d.a, in_dt)
+    w_flat = _flat(plan, d.w, in_dt)
+    t_out = M // d.a_B
+    m = torch.arange(M)
+    b_idx, t_idx = m // t_out, m % t_out
+    acc = torch.zeros(G, M, N, dtype=torch.float32)
+    passes = [(0, 0)] if d.passes == 1 else [(0, 0), (d.a_plane, 0), (0, d.w_plane)]
+    for g in range(G):
+        ag = g * d.a_sG if d.a_G > 1 else 0
+        w0 = g * d.n_pad * d.w_ld
+        W = w_flat[w0: w0 + N * d.w_ld].reshape(N, d.w_ld).float()
+        for (pa, pw) in passes:
+            cols = []
+            for tp in range(d.taps):
+                p, dt_ = d.tap_p[tp], d.tap_t[tp]
+                tq = t_idx + dt_
+                ok = (tq >= 0) & (tq < d.a_T)
+                base = ag + b_idx * d.a_sB + (tq.clamp(0, d.a_T - 1) * d.a_P + p) * d.a_ld
+                ch = d.a_c0 + pa + torch.arange(d.kc)
+                ch_ok = ch < d.a_C
+                idx = base[:, None] + ch.clamp(max=d.a_C - 1)[None, :]
+                vals = a_flat[idx.reshape(-1)].reshape(M, d.kc).float()
+                vals = vals * (ok[:, None] & ch_ok[None, :])
+                cols.append(vals)
+            A = torch.cat(cols, dim=1)                                  # [M, taps*kc]
+            Wp = W[:, pw: pw + d.taps * d.kc]
+            if d.in_dtype == nv.VT_F32:                                 # the MMA datapath truncates fp32 to tf32
+                A = (A.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+                Wp = (Wp.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+            acc[g] += A @ Wp.t()
+    out_dt = TORCH_DT[d.out_dtype]
+    q, rem = m // d.row_div, m % d.row_div
+    out_rows = q * d.out_q + rem * d.out_r + d.out_off
+    res_rows = q * d.res_q + rem * d.res_r + d.res_off
+    ncol = torch.arange(N)
+    for g in range(G):
+        x = acc[g]
+        if d.bias:
+            x = x + _flat(plan, d.bias, torch.float32)[g * d.n_pad: g * d.n_pad + N]
+        if d.epi == nv.EPI_LINEAR:
+            x = _act(x, d.act)
+            if d.colscale:
+                x = x * _flat(plan, d.colscale, torch.float32)[:N]
+            if d.res:
+                rflat = _flat(plan, d.res, torch.float32)
+                x = x + rflat[(g * d.res_g + res_rows[:, None] * d.ldres + ncol[None, :]).reshape(-1)].reshape(M, N)
+        else:
+            gamma = _flat(plan, d.gn_gamma, torch.float32)[g * d.n_pad: g * d.n_pad + N]
+            beta = _flat(plan, d.gn_beta, torch.float32)[g * d.n_pad: g * d.n_pad + N]
+            assert d.row_div == d.t_box == t_out
+            xs = x.reshape(d.a_B, t_out, N).permute(0, 2, 1)          # [B, C, T]
+            xs = F.group_norm(xs, N // d.gn_group_ch, gamma, beta, d.gn_eps)
+            xs = F.mish(xs).permute(0, 2, 1).reshape(M, N)
+            if d.film_c:
+                fc = _flat(plan, d.film_c, torch.float32)
+                sc_idx = g * d.film_g + q[:, None] * d.film_ld + d.film_off + ncol[None, :]
+                scale = fc[sc_idx.reshape(-1)].reshape(M, N)
+                shift = fc[(sc_idx + d.film_C).reshape(-1)].reshape(M, N)
+                if d.film_t:
+                    ft = _flat(plan, d.film_t, torch.float32)
+                    o = g * d.film_tg + d.film_off
+                    scale = scale + ft[o: o + N]
+                    shift = shift + ft[o + d.film_C: o + d.film_C + N]
+                xs = scale * xs + shift
+            if d.res:
+                rflat = _flat(plan, d.res, out_dt)
+                ridx = (g * d.res_g + res_rows[:, None] * d.ldres + ncol[None, :]).reshape(-1)
+                xs = xs + rflat[ridx].reshape(M, N).float()
+                if d.res_plane > 0:
+                    xs = xs + rflat[ridx + d.res_plane].reshape(M, N).float()
+            x = xs
+        idx = g * d.out_g + out_rows[:, None] * d.ldc + ncol[None, :]
+        _store(plan, d.out, d.out_dtype, idx, x, d.out_plane)
+
+
+def emu_layernorm(plan, d: nv.LnDesc):
+    x = _flat(plan, d.x, torch.float32)
+    rows = torch.arange(d.rows)
+    idx = rows[:, None] * d.in_row_stride * d.in_ld + torch.arange(d.D)[None, :]
+    v = x[idx.reshape(-1)].reshape(d.rows, d.D)
+    y = F.layer_norm(v, (d.D,), _flat(plan, d.gamma, torch.float32)[: d.D], _flat(plan, d.beta, torch.float32)[: d.D], d.eps)
+    if d.act == nv.ACT_GELU:
+        y = F.gelu(y)
+    _store(plan, d.out, d.out_dtype, rows[:, None] * d.out_ld + torch.arange(d.D)[None, :], y, d.out_plane)
+
+
+def emu_attention(plan, d: nv.AttnDesc):
+    dt = TORCH_DT[d.in_dtype]
+    D = d.heads * 64
+    n = d.images * d.tokens
+    qkv = _flat(plan, d.qkv, dt)[: n * 3 * D].reshape(d.images, d.tokens, 3, d.heads, 64).float()
+    q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    att = torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1)
+    if d.in_dtype == nv.VT_BF16:
+        att = att.to(torch.bfloat16).float()   # P is handed to the tensor cores as bf16 (un-normalised in the kernel)
+    ctx = (att @ v).permute(0, 2, 1, 3).reshape(n, D)
+    _store(plan, d.ctx, d.in_dtype, torch.arange(n)[:, None] * d.ctx_ld + torch.arange(D)[None, :], ctx, d.ctx_plane)
+
+
+def emu_imgstats(plan, d: nv.ImgStatsDesc):
+    img = _flat(plan, d.img, TORCH_DT[d.dtype])[: d.count]
+    mx = float(img.max())
+    mean = float(img.double().mean())
+    if mx > 1.0:
+        mean /= 255.0
+    flags = _flat(plan, d.flags, torch.int32)
+    flags[0] = 1 if mx > 1.0 else 0
+    flags[1] = 0 if torch.tensor(mean, dtype=torch.float32) < 0.5 else 1
+
+
+def emu_patchify(plan, d: nv.PatchifyDesc):
+    n = d.images * d.H * d.W * 3
+    img = _flat(plan, d.img, TORCH_DT[d.dtype])[:n]
+    img = img.reshape(d.images, d.H, d.W, 3).permute(0, 3, 1, 2) if d.layout == nv.LAYOUT_BHWC else img.reshape(d.images, 3, d.H, d.W)
+    img = img.float()
+    flags = _flat(plan, d.flags, torch.int32)
+    if int(flags[0]):
+        img = img / 255.0
+    if int(flags[1]):
+        img = (img - torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)) / torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    cols = F.unfold(img, d.patch, stride=d.patch).transpose(1, 2)      # [B, np, 3*p*p], k = c*p*p + i*p + j
+    rows = cols.shape[0] * cols.shape[1]
+    out = torch.zeros(rows, d.out_cols)
+    out[:, : cols.shape[2]] = cols.reshape(rows, -1)
+    _store(plan, d.out, d.out_dtype, torch.arange(rows)[:, None] * d.out_ld + torch.arange(d.out_cols)[None, :], out, d.out_plane)
+
+
+def emu_cls(plan, d: nv.ClsDesc):
+    h = _flat(plan, d.h, torch.float32)
+    row = _flat(plan, d.cls, torch.float32)[: d.D] + _flat(plan, d.pos, torch.float32)[: d.D]
+    for b in range(d.images):
+        h[b * d.tokens * d.D: b * d.tokens * d.D + d.D] = row
+
+
+def emu_pack(plan, d: nv.PackDesc):
+    src = _flat(plan, d.src, torch.float32)
+    rows = torch.arange(d.rows)
+    v = src[(rows[:, None] * d.src_ld + torch.arange(d.cols)[None, :]).reshape(-1)].reshape(d.rows, d.cols)
+    v = _act(v, d.act)
+    width = max(d.cols, d.zero_to)
+    full = torch.zeros(d.rows, width)
+    full[:, : d.cols] = v
+    _store(plan, d.out, d.out_dtype, rows[:, None] * d.out_ld + d.dst_c0 + torch.arange(width)[None, :], full, d.out_plane)
+
+
+def emu_affine(plan, d: nv.AffineDesc):
+    n = d.rows * d.A
+    x = _flat(plan, d.x, torch.float32)[:n].reshape(d.rows, d.A).clone()
+    if d.add:
+        x = x + _flat(plan, d.add, torch.float32)[:n].reshape(d.rows, d.A)
+    mins = _flat(plan, d.mins, torch.float32)[: d.A]
+    maxs = _flat(plan, d.maxs, torch.float32)[: d.A]
+    padded = (maxs - mins) * torch.tensor(d.pad, dtype=torch.float32)
+    center = (mins + maxs) / 2
+    pmin, pmax = center - padded / 2, center + padded / 2
+    rng = pmax - pmin
+    if not d.denorm:
+        rng = torch.where(rng < 1e-6, torch.ones_like(rng), rng)
+        y = 2.0 * (x - pmin) / rng - 1.0
+    else:
+        y = (x + 1.0) / 2.0 * rng + pmin
+    if d.out:
+        _flat(plan, d.out, torch.float32)[:n] = y.reshape(-1)
+    if d.xpad:
+        rows = torch.arange(d.rows)
+        _store(plan, d.xpad, d.xpad_dtype, rows[:, None] * d.xpad_ld + torch.arange(d.A)[None, :], y, d.xpad_plane)
+
+
+def emu_tembed(plan, d: nv.TembedDesc):
+    t = _flat(plan, d.t, torch.float32)[: d.rows]
+    half = d.dim // 2
+    e = math.log(10000) / (half - 1)
+    f = torch.exp(torch.arange(half) * -e)
+    arg = t[:, None] * f[None, :]
+    out = torch.cat((arg.sin(), arg.cos()), dim=-1)
+    rows = torch.arange(d.rows)
+    _store(plan, d.out, d.out_dtype, rows[:, None] * d.out_ld + torch.arange(d.dim)[None, :], out, d.out_plane)
+
+
+def emu_sde(plan, d: nv.SdeDesc):
+    n = d.rows * d.A
+    x = _flat(plan, d.x, torch.float32)[:n]
+    v = _flat(plan, d.v, torch.float32)[:n]
+    s = _flat(plan, d.s, torch.float32)[:n]
+    assert d.noise, "the emulator needs injected noise"
+    z = _flat(plan, d.noise, torch.float32)[:n]
+    f = lambda c: torch.tensor(c, dtype=torch.float32)
+    sv = s * f(d.ginv)
+    b = v - f(d.dgg) * sv * f(d.eps)
+    nx = x + (b + f(d.eps) * sv) * f(d.dt)
+    nx = nx + f(d.nscale) * (f(d.d) * z)
+    x[:] = nx
+    if d.xpad:
+        rows = torch.arange(d.rows)
+        _store(plan, d.xpad, d.xpad_dtype, rows[:, None] * d.xpad_ld + torch.arange(d.A)[None, :], nx.reshape(d.rows, d.A), d.xpad_plane)
+
+
+def emu_lstm(plan, d: nv.LstmDesc):
+    H = d.H
+    xw = _flat(plan, d.xw, torch.float32)[: d.B * d.T * 4 * H].reshape(d.B, d.T, 4 * H)
+    w = _flat(plan, d.w_hh, torch.float32)[: 4 * H * H].reshape(H, 4 * H)     # transposed: [H][4H]
+    h = _flat(plan, d.h, torch.float32)[: d.B * H].reshape(d.B, H)
+    c = _flat(plan, d.c, torch.float32)[: d.B * H].reshape(d.B, H)
+    hh, cc = h.clone(), c.clone()
+    rows = torch.arange(d.B)
+    for t in range(d.T):
+        g = xw[:, t] + hh @ w
+        i_, f_, g_, o_ = g.chunk(4, dim=-1)
+        cc = torch.sigmoid(f_) * cc + torch.sigmoid(i_) * torch.tanh(g_)
+        hh = torch.sigmoid(o_) * torch.tanh(cc)
+        _store(plan, d.y, d.y_dtype, (rows[:, None] * d.T + t) * d.y_ld + torch.arange(H)[None, :], hh)
+    h[:] = hh
+    c[:] = cc
+
+
+_EMU = {nv.GemmDesc: emu_gemm, nv.LnDesc: emu_layernorm, nv.AttnDesc: emu_attention, nv.ImgStatsDesc: emu_imgstats,
+        nv.PatchifyDesc: emu_patchify, nv.ClsDesc: emu_cls, nv.PackDesc: emu_pack, nv.AffineDesc: emu_affine,
+        nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm}
+
+
+@torch.no_grad()
+def run(plan: Plan, first: int = 0, count: int = -1):
+    n = len(plan.descs)
+    last = n if count < 0 else first + count
+    for i in range(first, last):
+        _EMU[type(plan.descs[i])](plan, plan.descs[i])

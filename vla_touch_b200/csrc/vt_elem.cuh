@@ -1,0 +1,386 @@
+// HBM-bound glue kernels of the refinement path: image statistics + patchify (visual_encoder.py:66-106),
+// CLS row, LayerNorm (HF:354,359,449), row packing / Mish(gf), normalise / de-normalise
+// (controller_dataset.py:303-384), sinusoidal step embedding (conditional_unet_1D.py:7-19) and the
+// Euler-Maruyama update of sde_vs (bridge_model.py:352-385).  128-bit accesses and warp-shuffle reductions.
+#pragma once
+#include <curand_kernel.h>
+
+#include "vt_ptx.cuh"
+
+namespace vt {
+
+// Store one value as bf16, as plain f32, or as a tf32 (hi, lo) pair `plane` elements apart.
+__device__ __forceinline__ void store_val(void* out, int dtype, long long idx, long long plane, float v) {
+  if (dtype == 0) {
+    reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16(v);
+  } else if (plane > 0) {
+    const float hi = tf32_hi(v);
+    reinterpret_cast<float*>(out)[idx] = hi;
+    reinterpret_cast<float*>(out)[idx + plane] = v - hi;
+  } else {
+    reinterpret_cast<float*>(out)[idx] = v;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// image statistics: max and mean of the WHOLE call tensor (batch-global predicates)
+// ------------------------------------------------------------------------------------------
+constexpr int STATS_MAX_BLOCKS = 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(256) imgstats_partial_kernel(const T* __restrict__ img, long long count,
+                                                               float* __restrict__ pmax, double* __restrict__ psum) {
+  constexpr int V = 16 / sizeof(T);
+  const long long nvec = count / V;
+  const uint4* p4 = reinterpret_cast<const uint4*>(img);
+  float mx = -INFINITY;
+  double sum = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 q = __ldg(p4 + i);
+    if constexpr (sizeof(T) == 1) {
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+      uint32_t s = 0, m = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const uint32_t v = (w[k] >> (8 * b)) & 0xFFu;
+          s += v;
+          m = max(m, v);
+        }
+      }
+      sum += (double)s;
+      mx = fmaxf(mx, (float)m);
+    } else {
+      const float f[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        sum += (double)f[k];
+        mx = fmaxf(mx, f[k]);
+      }
+    }
+  }
+  if (blockIdx.x == 0) {  // ragged tail
+    for (long long i = nvec * V + threadIdx.x; i < count; i += blockDim.x) {
+      const float v = (float)img[i];
+      sum += (double)v;
+      mx = fmaxf(mx, v);
+    }
+  }
+  __shared__ float smx[8];
+  __shared__ double ssum[8];
+  mx = warp_max(mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    smx[w] = mx;
+    ssum[w] = sum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) {
+      mx = fmaxf(mx, smx[k]);
+      sum += ssum[k];
+    }
+    pmax[blockIdx.x] = mx;
+    psum[blockIdx.x] = sum;
+  }
+}
+
+__global__ void __launch_bounds__(256) imgstats_final_kernel(const float* __restrict__ pmax,
+                                                             const double* __restrict__ psum, int nblk, long long count,
+                                                             int* __restrict__ flags) {
+  float mx = -INFINITY;
+  double sum = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
+    mx = fmaxf(mx, pmax[i]);
+    sum += psum[i];
+  }
+  __shared__ float smx[8];
+  __shared__ double ssum[8];
+  mx = warp_max(mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    smx[w] = mx;
+    ssum[w] = sum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) {
+      mx = fmaxf(mx, smx[k]);
+      sum += ssum[k];
+    }
+    const bool scale255 = mx > 1.0f;                  // visual_encoder.py:78
+    double mean = sum / (double)count;
+    if (scale255) mean /= 255.0;
+    flags[0] = scale255 ? 1 : 0;
+    flags[1] = ((float)mean < 0.5f) ? 0 : 1;          // visual_encoder.py:100 (skip normalisation when mean < 0.5)
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// patchify: layout fix + /255 + ImageNet normalise + im2col for the k14 s14 patch projection
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) patchify_kernel(const T* __restrict__ img, int layout, int images, int H, int W,
+                                                       int patch, const int* __restrict__ flags, void* __restrict__ out,
+                                                       int out_dtype, int out_cols, int out_ld, long long out_plane) {
+  const int gw = W / patch, gh = H / patch;
+  const int kk = 3 * patch * patch;
+  const long long total = (long long)images * gh * gw * out_cols;
+  const bool scale255 = flags[0] != 0, donorm = flags[1] != 0;
+  const float mean[3] = {0.485f, 0.456f, 0.406f};
+  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % out_cols);
+    const long long m = idx / out_cols;
+    float v = 0.f;
+    if (k < kk) {
+      const int p = (int)(m % (gh * gw));
+      const long long b = m / (gh * gw);
+      const int py = p / gw, px = p - py * gw;
+      const int c = k / (patch * patch);
+      const int r = k - c * patch * patch;
+      const int i = r / patch, j = r - i * patch;
+      const int y = py * patch + i, x = px * patch + j;
+      const long long src = (layout == 0) ? (((b * H + y) * W + x) * 3 + c) : (((b * 3 + c) * H + y) * (long long)W + x);
+      v = (float)img[src];
+      if (scale255) v = __fdiv_rn(v, 255.0f);
+      if (donorm) v = __fdiv_rn(__fsub_rn(v, mean[c]), stdv[c]);
+    }
+    store_val(out, out_dtype, m * out_ld + k, out_plane, v);
+  }
+}
+
+__global__ void cls_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ h,
+                           int images, int tokens, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= images * D) return;
+  const int b = i / D, d = i - b * D;
+  h[(long long)b * tokens * D + d] = cls[d] + pos[d];
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, two-pass statistics held in registers
+// ------------------------------------------------------------------------------------------
+template <int VEC>  // D = VEC * 128
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long in_ld,
+                                                        long long in_row_stride, int rows, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, void* __restrict__ out,
+                                                        int out_dtype, long long out_ld, long long out_plane, int act) {
+  constexpr int D = VEC * 128;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * in_row_stride * in_ld);
+  float4 v[VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float4 g = g4[lane + 32 * i], b = b4[lane + 32 * i];
+    float y[4] = {(v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                  (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w};
+    if (act == 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) y[k] = gelu_erf(y[k]);
+    }
+    const long long o = (long long)row * out_ld + 4 * (lane + 32 * i);
+    if (out_dtype == 0) {
+      uint2 pk;
+      pk.x = pack_bf16x2(y[0], y[1]);
+      pk.y = pack_bf16x2(y[2], y[3]);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + o) = pk;
+    } else if (out_plane > 0) {
+      float hi[4], lo[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        hi[k] = tf32_hi(y[k]);
+        lo[k] = y[k] - hi[k];
+      }
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o + out_plane) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    } else {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = make_float4(y[0], y[1], y[2], y[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pack: out[r][dst_c0 + c] = cast(act(src[r][c])), optional zero tail
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src, long long src_ld, int rows, int cols,
+                                                   int act, void* __restrict__ out, int out_dtype, long long out_ld,
+                                                   int dst_c0, long long out_plane, int zero_to) {
+  const int width = zero_to > cols ? zero_to : cols;
+  const long long total = (long long)rows * width;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % width);
+    const long long r = idx / width;
+    float v = 0.f;
+    if (c < cols) {
+      v = src[r * src_ld + c];
+      if (act == 1) v = gelu_erf(v);
+      else if (act == 2) v = mish_precise(v);
+    }
+    store_val(out, out_dtype, r * out_ld + dst_c0 + c, out_plane, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// normalize_actions / denormalize_actions (padding factor 1.4), same operation order as the reference, no FMA
+// contraction, so the fp32 result is bit-identical to the PyTorch CPU path.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) affine_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                     const float* __restrict__ mins, const float* __restrict__ maxs,
+                                                     int rows, int A, int denorm, float pad, void* __restrict__ xpad, int xpad_dtype,
+                                                     int xpad_ld, long long xpad_plane, const float* __restrict__ add) {
+  const long long total = (long long)rows * A;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int a = (int)(idx % A);
+    const long long r = idx / A;
+    const float lo = mins[a], hi = maxs[a];
+    const float orig = __fsub_rn(hi, lo);
+    const float padded = __fmul_rn(orig, pad);
+    const float center = __fdiv_rn(__fadd_rn(lo, hi), 2.0f);
+    const float half = __fdiv_rn(padded, 2.0f);
+    const float pmin = __fsub_rn(center, half);
+    const float pmax = __fadd_rn(center, half);
+    float range = __fsub_rn(pmax, pmin);
+    float v = x[idx];
+    if (add) v = __fadd_rn(v, add[idx]);
+    float y;
+    if (!denorm) {
+      if (range < 1e-6f) range = 1.0f;
+      y = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fsub_rn(v, pmin)), range), 1.0f);
+    } else {
+      y = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(v, 1.0f), 2.0f), range), pmin);
+    }
+    if (out) out[idx] = y;
+    if (xpad) store_val(xpad, xpad_dtype, r * xpad_ld + a, xpad_plane, y);
+  }
+}
+
+// SinusoidalPosEmb: out[r] = cat(sin(t f_i), cos(t f_i)),  f_i = exp(i * -(ln 1e4 / (half - 1)))
+__global__ void __launch_bounds__(256) tembed_kernel(const float* __restrict__ t, int rows, int dim, void* __restrict__ out,
+                                                     int out_dtype, long long out_ld, long long out_plane) {
+  const int half = dim / 2;
+  const float e = (float)(9.210340371976184 / (double)(half - 1));  // math.log(10000) / (half - 1)
+  const int total = rows * half;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int i = idx % half, r = idx / half;
+    const float f = expf(__fmul_rn((float)i, -e));
+    const float arg = __fmul_rn(t[r], f);
+    store_val(out, out_dtype, (long long)r * out_ld + i, out_plane, sinf(arg));
+    store_val(out, out_dtype, (long long)r * out_ld + half + i, out_plane, cosf(arg));
+  }
+}
+
+// One Euler-Maruyama step (bridge_model.py:363-385), reference operation order.
+__global__ void __launch_bounds__(256) sde_step_kernel(float* __restrict__ x, const float* __restrict__ v,
+                                                       const float* __restrict__ s, const float* __restrict__ noise,
+                                                       int rows, int A, float ginv, float dgg, float eps, float dt,
+                                                       float nscale, float d, unsigned long long seed,
+                                                       const unsigned long long* __restrict__ seed_dev, int step,
+                                                       void* __restrict__ xpad, int xpad_dtype, int xpad_ld,
+                                                       long long xpad_plane) {
+  const long long total = (long long)rows * A;
+  if (seed_dev) seed += *seed_dev;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    float z;
+    if (noise) {
+      z = noise[idx];
+    } else {
+      curandStatePhilox4_32_10_t st;
+      curand_init(seed, (unsigned long long)idx, (unsigned long long)step, &st);
+      z = curand_normal(&st);
+    }
+    const float sv = __fmul_rn(s[idx], ginv);                                  // s = s * gamma_inv
+    const float b = __fsub_rn(v[idx], __fmul_rn(__fmul_rn(dgg, sv), eps));     // b = v - (dot_gamma*gamma) * s * eps
+    const float dW = __fmul_rn(d, z);
+    float nx = __fadd_rn(x[idx], __fmul_rn(__fadd_rn(b, __fmul_rn(eps, sv)), dt));   // x + (b + 1.0*eps*s) * dt
+    nx = __fadd_rn(nx, __fmul_rn(nscale, dW));
+    x[idx] = nx;
+    if (xpad) {
+      const int a = (int)(idx % A);
+      const long long r = idx / A;
+      store_val(xpad, xpad_dtype, r * xpad_ld + a, xpad_plane, nx);
+    }
+  }
+}
+
+// bicubic resize (A = -0.75, align_corners = False) of the patch position embeddings, HF:57-95
+__device__ __forceinline__ void cubic_coeffs(float t, float* w) {
+  const float A = -0.75f;
+  float x = t + 1.0f;
+  w[0] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
+  x = t;
+  w[1] = ((A + 2.0f) * x - (A + 3.0f)) * x * x + 1.0f;
+  x = 1.0f - t;
+  w[2] = ((A + 2.0f) * x - (A + 3.0f)) * x * x + 1.0f;
+  x = 2.0f - t;
+  w[3] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
+}
+__global__ void pos_resize_kernel(const float* __restrict__ src, int s, float* __restrict__ dst, int nh, int nw, int D) {
+  const long long total = (long long)nh * nw * D;
+  const float sh = (float)s / (float)nh, sw = (float)s / (float)nw;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(idx % D);
+    const int p = (int)(idx / D);
+    const int oy = p / nw, ox = p - oy * nw;
+    const float ry = sh * ((float)oy + 0.5f) - 0.5f, rx = sw * ((float)ox + 0.5f) - 0.5f;
+    const float fy = floorf(ry), fx = floorf(rx);
+    const int iy = (int)fy, ix = (int)fx;
+    float wy[4], wx[4];
+    cubic_coeffs(ry - fy, wy);
+    cubic_coeffs(rx - fx, wx);
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = min(max(iy - 1 + a, 0), s - 1);
+      float row = 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int xx = min(max(ix - 1 + b, 0), s - 1);
+        row += src[((long long)yy * s + xx) * D + d] * wx[b];
+      }
+      acc += row * wy[a];
+    }
+    dst[idx] = acc;
+  }
+}
+
+}  // namespace vt

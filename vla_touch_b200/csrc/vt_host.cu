@@ -1,0 +1,629 @@
+// Host side of libvt_b200.so: validates op descriptors, encodes TMA tensor maps once, keeps programs (ordered
+// lists of ready-to-launch kernels) and replays them on a stream or as a CUDA graph.  C ABI in include/vt_b200.h.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/vt_b200.h"
+#include "vt_attn.cuh"
+#include "vt_elem.cuh"
+#include "vt_gemm.cuh"
+#include "vt_lstm.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define VT_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess) return fail(VT_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define VT_REQUIRE(cond, ...) \
+  do {                        \
+    if (!(cond)) return fail(VT_E_INVALID, __VA_ARGS__); \
+  } while (0)
+
+// --------------------------------------------------------------------------------------------
+// TMA tensor maps (driver entry point fetched at run time: no link-time dependency on libcuda)
+// --------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap(CUtensorMap* out, int dtype, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(VT_E_CUDA, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+  VT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer %p is not 16-byte aligned", base);
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    VT_REQUIRE(dims[i] >= 1 && dims[i] <= (1ull << 32), "TMA dim %d extent %llu out of range", i, (unsigned long long)dims[i]);
+    VT_REQUIRE(box[i] >= 1 && box[i] <= 256, "TMA box %d extent %u out of range", i, box[i]);
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    gs[i] = strides_bytes[i];
+    VT_REQUIRE((gs[i] & 15) == 0 && gs[i] < (1ull << 40), "TMA stride %d = %llu bytes must be a multiple of 16", i,
+               (unsigned long long)gs[i]);
+  }
+  const CUtensorMapDataType dt = dtype == VT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VT_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return VT_OK;
+}
+
+int grid_for(long long total, int per_block) {
+  long long b = (total + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > 148 * 16) b = 148 * 16;
+  return (int)b;
+}
+
+// --------------------------------------------------------------------------------------------
+// ops
+// --------------------------------------------------------------------------------------------
+struct Op {
+  virtual ~Op() {}
+  virtual int launch(cudaStream_t s) = 0;
+  virtual int launches() const { return 1; }
+};
+
+#define VT_LAUNCH_CHECK(name)                                                                \
+  do {                                                                                       \
+    cudaError_t e__ = cudaGetLastError();                                                    \
+    if (e__ != cudaSuccess) return fail(VT_E_CUDA, "%s launch: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+// ---- GEMM ----
+typedef void (*GemmKernel)(const vt::GemmArgs);
+struct GemmVariant {
+  GemmKernel fn;
+  int smem;
+  bool attr_set;
+};
+
+template <typename TIn, int BN, int MODE, typename TOut, int STAGES>
+GemmVariant make_variant() {
+  GemmVariant v;
+  v.fn = vt::gemm_tc_kernel<TIn, BN, MODE, TOut, STAGES, (sizeof(TIn) == 4)>;
+  v.smem = vt::gemm_smem_bytes<BN, STAGES>();
+  v.attr_set = false;
+  return v;
+}
+
+GemmVariant* gemm_variant(int in_dtype, int bn, int epi, int out_dtype) {
+  using bf = __nv_bfloat16;
+  static GemmVariant v_b_128_l_b = make_variant<bf, 128, vt::EPI_LINEAR, bf, 3>();
+  static GemmVariant v_b_128_l_f = make_variant<bf, 128, vt::EPI_LINEAR, float, 3>();
+  static GemmVariant v_b_32_l_b = make_variant<bf, 32, vt::EPI_LINEAR, bf, 4>();
+  static GemmVariant v_b_32_l_f = make_variant<bf, 32, vt::EPI_LINEAR, float, 4>();
+  static GemmVariant v_b_128_g_b = make_variant<bf, 128, vt::EPI_GN, bf, 3>();
+  static GemmVariant v_f_128_l_f = make_variant<float, 128, vt::EPI_LINEAR, float, 3>();
+  static GemmVariant v_f_32_l_f = make_variant<float, 32, vt::EPI_LINEAR, float, 4>();
+  static GemmVariant v_f_128_g_f = make_variant<float, 128, vt::EPI_GN, float, 3>();
+  if (in_dtype == VT_BF16) {
+    if (epi == VT_EPI_GN) return (bn == 128 && out_dtype == VT_BF16) ? &v_b_128_g_b : nullptr;
+    if (bn == 128) return out_dtype == VT_BF16 ? &v_b_128_l_b : &v_b_128_l_f;
+    if (bn == 32) return out_dtype == VT_BF16 ? &v_b_32_l_b : &v_b_32_l_f;
+    return nullptr;
+  }
+  if (out_dtype != VT_F32) return nullptr;
+  if (epi == VT_EPI_GN) return bn == 128 ? &v_f_128_g_f : nullptr;
+  if (bn == 128) return &v_f_128_l_f;
+  if (bn == 32) return &v_f_32_l_f;
+  return nullptr;
+}
+
+struct GemmOp : Op {
+  vt::GemmArgs args;
+  GemmVariant* var;
+  dim3 grid;
+  int launch(cudaStream_t s) override {
+    if (!var->attr_set) {
+      VT_CUDA(cudaFuncSetAttribute(var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, var->smem));
+      var->attr_set = true;
+    }
+    var->fn<<<grid, vt::GEMM_THREADS, var->smem, s>>>(args);
+    VT_LAUNCH_CHECK("gemm_tc_kernel");
+    return VT_OK;
+  }
+};
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
+  VT_REQUIRE(d.in_dtype == VT_BF16 || d.in_dtype == VT_F32, "gemm: in_dtype %d", d.in_dtype);
+  VT_REQUIRE(d.out_dtype == VT_BF16 || d.out_dtype == VT_F32, "gemm: out_dtype %d", d.out_dtype);
+  const int es = d.in_dtype == VT_BF16 ? 2 : 4;
+  const int KE = 128 / es;
+  VT_REQUIRE(d.a && d.w && d.out, "gemm: null operand pointer");
+  VT_REQUIRE(d.kc > 0 && d.kc % KE == 0, "gemm: kc=%d must be a positive multiple of %d", d.kc, KE);
+  VT_REQUIRE(d.taps >= 1 && d.taps <= VT_MAX_TAPS, "gemm: taps=%d", d.taps);
+  VT_REQUIRE(d.passes == 1 || (d.passes == 3 && d.in_dtype == VT_F32), "gemm: passes=%d", d.passes);
+  VT_REQUIRE(d.t_box >= 1 && d.b_box >= 1 && d.t_box * d.b_box <= 128, "gemm: tile box %dx%d", d.t_box, d.b_box);
+  VT_REQUIRE(d.G >= 1 && (d.a_G == 1 || d.a_G == d.G), "gemm: G=%d a_G=%d", d.G, d.a_G);
+  VT_REQUIRE(d.M >= 1 && d.N >= 1 && d.N <= d.n_pad, "gemm: M=%d N=%d n_pad=%d", d.M, d.N, d.n_pad);
+  VT_REQUIRE(d.bn == 32 || d.bn == 128, "gemm: bn=%d", d.bn);
+  VT_REQUIRE(d.n_pad % d.bn == 0, "gemm: n_pad=%d must be a multiple of bn=%d", d.n_pad, d.bn);
+  VT_REQUIRE(d.w_ld >= d.taps * d.kc, "gemm: w_ld=%d < taps*kc=%d", d.w_ld, d.taps * d.kc);
+  VT_REQUIRE(d.a_P >= 1 && d.a_T >= 1 && d.a_B >= 1 && d.a_C >= 1, "gemm: bad A extents");
+  VT_REQUIRE(d.row_div >= 1, "gemm: row_div=%d", d.row_div);
+  GemmVariant* var = gemm_variant(d.in_dtype, d.bn, d.epi, d.out_dtype);
+  if (!var) return fail(VT_E_UNSUPPORTED, "gemm: no kernel for in=%d bn=%d epi=%d out=%d", d.in_dtype, d.bn, d.epi, d.out_dtype);
+
+  vt::GemmArgs& a = op->args;
+  memset(&a, 0, sizeof(a));
+  op->var = var;
+  const int rows_valid = d.t_box * d.b_box;
+  const int t_out = d.M / d.a_B;
+  if (d.b_box == 1 && d.a_B == 1) {  // one sample: tiles step along its positions
+    a.m_t_step = d.t_box;
+    a.m_b_step = 0;
+  } else {
+    VT_REQUIRE(d.t_box == t_out && d.M == t_out * d.a_B, "gemm: t_box=%d must equal positions per sample %d", d.t_box, t_out);
+    a.m_t_step = 0;
+    a.m_b_step = d.b_box;
+  }
+  {
+    const uint64_t dims[5] = {(uint64_t)d.a_C, (uint64_t)d.a_P, (uint64_t)d.a_T, (uint64_t)d.a_B, (uint64_t)d.a_G};
+    const uint64_t sG = d.a_G > 1 ? (uint64_t)d.a_sG : (uint64_t)d.a_sB * d.a_B;
+    const uint64_t st[4] = {(uint64_t)d.a_ld * es, (uint64_t)d.a_ld * d.a_P * es, (uint64_t)d.a_sB * es, sG * es};
+    const uint32_t box[5] = {(uint32_t)KE, 1u, (uint32_t)d.t_box, (uint32_t)d.b_box, 1u};
+    int rc = make_tmap(&a.tmA, d.in_dtype, 5, d.a, dims, st, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)d.w_ld, (uint64_t)d.G * d.n_pad};
+    const uint64_t st[1] = {(uint64_t)d.w_ld * es};
+    const uint32_t box[2] = {(uint32_t)KE, (uint32_t)d.bn};
+    int rc = make_tmap(&a.tmB, d.in_dtype, 2, d.w, dims, st, box);
+    if (rc) return rc;
+  }
+  a.passes = d.passes;
+  a.taps = d.taps;
+  a.cblocks = d.kc / KE;
+  a.a_c0 = d.a_c0;
+  a.a_plane = d.a_plane;
+  a.b_plane = d.w_plane;
+  a.a_g_mul = d.a_G > 1 ? 1 : 0;
+  for (int i = 0; i < d.taps; ++i) {
+    VT_REQUIRE(d.tap_p[i] >= 0 && d.tap_p[i] < d.a_P, "gemm: tap %d phase %d", i, d.tap_p[i]);
+    a.tap_p[i] = d.tap_p[i];
+    a.tap_t[i] = d.tap_t[i];
+  }
+  a.rows_valid = rows_valid;
+  a.a_box_bytes = rows_valid * 128;
+  a.n_pad = d.n_pad;
+  a.M_total = d.M;
+  a.N = d.N;
+  a.row_div = d.row_div;
+  a.out_q = d.out_q;
+  a.out_r = d.out_r;
+  a.out_off = d.out_off;
+  a.out_g = d.out_g;
+  a.ldc = d.ldc;
+  a.out_plane = d.out_plane;
+  a.out = d.out;
+  a.bias = d.bias;
+  a.act = d.act;
+  a.colscale = d.colscale;
+  a.res = d.res;
+  a.res_q = d.res_q;
+  a.res_r = d.res_r;
+  a.res_off = d.res_off;
+  a.res_g = d.res_g;
+  a.res_plane = d.res_plane;
+  a.ldres = d.ldres;
+  const int oes = d.out_dtype == VT_BF16 ? 2 : 4;
+  const int ov = 16 / oes;
+  bool vec = aligned16(d.out) && d.ldc % ov == 0 && d.out_g % ov == 0 && d.out_plane % ov == 0;
+  if (d.res) {
+    const int res_es = (d.epi == VT_EPI_GN) ? oes : 4;
+    const int rv = 16 / res_es;
+    vec = vec && aligned16(d.res) && d.ldres % rv == 0 && d.res_g % rv == 0;
+  }
+  a.vec = vec ? 1 : 0;
+  if (d.epi == VT_EPI_GN) {
+    VT_REQUIRE(d.gn_gamma && d.gn_beta, "gemm: GroupNorm epilogue needs gamma/beta");
+    VT_REQUIRE(d.gn_group_ch == 32 || d.gn_group_ch == 64, "gemm: gn_group_ch=%d", d.gn_group_ch);
+    VT_REQUIRE(d.N % 128 == 0, "gemm: GroupNorm epilogue needs N %% 128 == 0 (N=%d)", d.N);
+    VT_REQUIRE(d.t_box == t_out, "gemm: GroupNorm epilogue needs whole samples per tile (t_box=%d, positions=%d)", d.t_box, t_out);
+    VT_REQUIRE(d.row_div == d.t_box, "gemm: GroupNorm epilogue needs row_div == t_box");
+    VT_REQUIRE(vec, "gemm: GroupNorm epilogue needs 16-byte aligned rows");
+    VT_REQUIRE(d.b_box <= 32, "gemm: GroupNorm epilogue supports at most 32 samples per tile");
+    if (d.film_c) VT_REQUIRE(d.film_ld % 4 == 0 && d.film_off % 4 == 0 && d.film_C % 4 == 0 && d.film_g % 4 == 0 && aligned16(d.film_c),
+                             "gemm: FiLM table must be 16-byte aligned");
+    a.gn_gamma = d.gn_gamma;
+    a.gn_beta = d.gn_beta;
+    a.gn_gs_log2 = d.gn_group_ch == 32 ? 5 : 6;
+    a.gn_rows = d.t_box;
+    a.gn_eps = d.gn_eps;
+    a.film_c = d.film_c;
+    a.film_t = d.film_t;
+    a.film_g = d.film_g;
+    a.film_tg = d.film_tg;
+    a.film_ld = d.film_ld;
+    a.film_C = d.film_C;
+    a.film_off = d.film_off;
+  }
+  const int m_tiles = (d.M + rows_valid - 1) / rows_valid;
+  const int n_tiles = (d.N + d.bn - 1) / d.bn;
+  VT_REQUIRE(m_tiles <= 65535 && d.G <= 65535, "gemm: grid too large (m_tiles=%d)", m_tiles);
+  op->grid = dim3((unsigned)n_tiles, (unsigned)m_tiles, (unsigned)d.G);
+  return VT_OK;
+}
+
+// ---- attention ----
+struct AttnOp : Op {
+  vt::AttnArgs args;
+  vt_attn_desc d;
+  dim3 grid;
+  static bool attr_set;
+  int launch(cudaStream_t s) override {
+    if (d.in_dtype == VT_BF16) {
+      if (!attr_set) {
+        VT_CUDA(cudaFuncSetAttribute(vt::attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vt::ATT_SMEM_BYTES));
+        attr_set = true;
+      }
+      vt::attn_tc_kernel<<<grid, vt::ATT_THREADS, vt::ATT_SMEM_BYTES, s>>>(args);
+      VT_LAUNCH_CHECK("attn_tc_kernel");
+    } else {
+      const long long warps = (long long)d.images * d.heads * d.tokens;
+      const int blocks = (int)((warps + vt::ATTF_WARPS - 1) / vt::ATTF_WARPS);
+      const size_t smem = (size_t)vt::ATTF_WARPS * d.tokens * sizeof(float);
+      vt::attn_f32_kernel<<<blocks, vt::ATTF_WARPS * 32, smem, s>>>(reinterpret_cast<const float*>(d.qkv),
+                                                                    reinterpret_cast<float*>(d.ctx), d.images, d.tokens,
+                                                                    d.heads, d.heads * 64, d.ctx_ld, d.ctx_plane);
+      VT_LAUNCH_CHECK("attn_f32_kernel");
+    }
+    return VT_OK;
+  }
+};
+bool AttnOp::attr_set = false;
+
+// ---- simple ops ----
+struct LnOp : Op {
+  vt_ln_desc d;
+  int launch(cudaStream_t s) override {
+    const int blocks = (d.rows + 7) / 8;
+#define VT_LN(V)                                                                                                   \
+  vt::layernorm_kernel<V><<<blocks, 256, 0, s>>>(d.x, d.in_ld, d.in_row_stride, d.rows, d.gamma, d.beta, d.eps, d.out, \
+                                                 d.out_dtype, d.out_ld, d.out_plane, d.act)
+    switch (d.D) {
+      case 256: VT_LN(2); break;
+      case 384: VT_LN(3); break;
+      case 768: VT_LN(6); break;
+      case 1024: VT_LN(8); break;
+      default: return fail(VT_E_UNSUPPORTED, "layernorm: D=%d", d.D);
+    }
+#undef VT_LN
+    VT_LAUNCH_CHECK("layernorm_kernel");
+    return VT_OK;
+  }
+};
+
+struct ImgStatsOp : Op {
+  vt_imgstats_desc d;
+  int launches() const override { return 2; }
+  int launch(cudaStream_t s) override {
+    const int es = d.dtype == VT_U8 ? 1 : 4;
+    const long long nvec = d.count / (16 / es);
+    int blocks = (int)((nvec + 256 * 8 - 1) / (256 * 8));
+    blocks = blocks < 1 ? 1 : (blocks > vt::STATS_MAX_BLOCKS ? vt::STATS_MAX_BLOCKS : blocks);
+    float* pmax = d.partial;
+    double* psum = reinterpret_cast<double*>(d.partial + vt::STATS_MAX_BLOCKS);
+    if (d.dtype == VT_U8)
+      vt::imgstats_partial_kernel<uint8_t><<<blocks, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(d.img), d.count, pmax, psum);
+    else
+      vt::imgstats_partial_kernel<float><<<blocks, 256, 0, s>>>(reinterpret_cast<const float*>(d.img), d.count, pmax, psum);
+    VT_LAUNCH_CHECK("imgstats_partial_kernel");
+    vt::imgstats_final_kernel<<<1, 256, 0, s>>>(pmax, psum, blocks, d.count, d.flags);
+    VT_LAUNCH_CHECK("imgstats_final_kernel");
+    return VT_OK;
+  }
+};
+
+struct PatchifyOp : Op {
+  vt_patchify_desc d;
+  int launch(cudaStream_t s) override {
+    const long long total = (long long)d.images * (d.H / d.patch) * (d.W / d.patch) * d.out_cols;
+    const int blocks = grid_for(total, 256 * 4);
+    if (d.dtype == VT_U8)
+      vt::patchify_kernel<uint8_t><<<blocks, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(d.img), d.layout, d.images, d.H,
+                                                          d.W, d.patch, d.flags, d.out, d.out_dtype, d.out_cols, d.out_ld, d.out_plane);
+    else
+      vt::patchify_kernel<float><<<blocks, 256, 0, s>>>(reinterpret_cast<const float*>(d.img), d.layout, d.images, d.H, d.W,
+                                                        d.patch, d.flags, d.out, d.out_dtype, d.out_cols, d.out_ld, d.out_plane);
+    VT_LAUNCH_CHECK("patchify_kernel");
+    return VT_OK;
+  }
+};
+
+struct ClsOp : Op {
+  vt_cls_desc d;
+  int launch(cudaStream_t s) override {
+    vt::cls_kernel<<<(d.images * d.D + 255) / 256, 256, 0, s>>>(d.cls, d.pos, d.h, d.images, d.tokens, d.D);
+    VT_LAUNCH_CHECK("cls_kernel");
+    return VT_OK;
+  }
+};
+
+struct PackOp : Op {
+  vt_pack_desc d;
+  int launch(cudaStream_t s) override {
+    const int width = d.zero_to > d.cols ? d.zero_to : d.cols;
+    vt::pack_kernel<<<grid_for((long long)d.rows * width, 256), 256, 0, s>>>(d.src, d.src_ld, d.rows, d.cols, d.act, d.out,
+                                                                             d.out_dtype, d.out_ld, d.dst_c0, d.out_plane,
+                                                                             d.zero_to);
+    VT_LAUNCH_CHECK("pack_kernel");
+    return VT_OK;
+  }
+};
+
+struct AffineOp : Op {
+  vt_affine_desc d;
+  int launch(cudaStream_t s) override {
+    vt::affine_kernel<<<grid_for((long long)d.rows * d.A, 256), 256, 0, s>>>(d.x, d.out, d.mins, d.maxs, d.rows, d.A, d.denorm,
+                                                                             d.pad, d.xpad, d.xpad_dtype, d.xpad_ld, d.xpad_plane,
+                                                                             d.add);
+    VT_LAUNCH_CHECK("affine_kernel");
+    return VT_OK;
+  }
+};
+
+struct TembedOp : Op {
+  vt_tembed_desc d;
+  int launch(cudaStream_t s) override {
+    vt::tembed_kernel<<<grid_for((long long)d.rows * d.dim / 2, 256), 256, 0, s>>>(d.t, d.rows, d.dim, d.out, d.out_dtype,
+                                                                                   d.out_ld, d.out_plane);
+    VT_LAUNCH_CHECK("tembed_kernel");
+    return VT_OK;
+  }
+};
+
+struct SdeOp : Op {
+  vt_sde_desc d;
+  int launch(cudaStream_t s) override {
+    vt::sde_step_kernel<<<grid_for((long long)d.rows * d.A, 256), 256, 0, s>>>(
+        d.x, d.v, d.s, d.noise, d.rows, d.A, d.ginv, d.dgg, d.eps, d.dt, d.nscale, d.d, (unsigned long long)d.seed,
+        reinterpret_cast<const unsigned long long*>(d.seed_dev), d.step,
+        d.xpad, d.xpad_dtype, d.xpad_ld, d.xpad_plane);
+    VT_LAUNCH_CHECK("sde_step_kernel");
+    return VT_OK;
+  }
+};
+
+struct LstmOp : Op {
+  vt_lstm_desc d;
+  int launch(cudaStream_t s) override {
+    const int blocks = (d.B + vt::LSTM_ROWS - 1) / vt::LSTM_ROWS;
+    if (d.H == 256)
+      vt::lstm_seq_kernel<256><<<blocks, 256, 0, s>>>(d.xw, d.w_hh, d.h, d.c, d.y, d.y_dtype, d.y_ld, d.B, d.T);
+    else
+      return fail(VT_E_UNSUPPORTED, "lstm: H=%d", d.H);
+    VT_LAUNCH_CHECK("lstm_seq_kernel");
+    return VT_OK;
+  }
+};
+
+}  // namespace
+
+struct vt_program {
+  std::vector<std::unique_ptr<Op>> ops;
+  cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t capture_stream = nullptr;
+};
+
+extern "C" {
+
+const char* vt_last_error(void) { return g_err.c_str(); }
+int vt_abi_version(void) { return VT_ABI_VERSION; }
+
+int vt_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(VT_E_NODEVICE, "no CUDA device");
+  }
+  int dev = 0;
+  VT_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  VT_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return VT_OK;
+}
+
+int vt_program_create(vt_program** out) {
+  if (!out) return fail(VT_E_INVALID, "null out");
+  *out = new vt_program();
+  return VT_OK;
+}
+
+int vt_program_destroy(vt_program* p) {
+  if (!p) return VT_OK;
+  if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+  if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
+  delete p;
+  return VT_OK;
+}
+
+int vt_program_num_ops(const vt_program* p) { return p ? (int)p->ops.size() : 0; }
+
+static int clamp_range(const vt_program* p, int first, int* count) {
+  if (!p) return fail(VT_E_INVALID, "null program");
+  const int n = (int)p->ops.size();
+  if (first < 0 || first > n) return fail(VT_E_INVALID, "first=%d out of range (%d ops)", first, n);
+  if (*count < 0 || first + *count > n) *count = n - first;
+  return VT_OK;
+}
+
+int vt_program_num_launches(const vt_program* p, int first, int count) {
+  if (clamp_range(p, first, &count)) return VT_E_INVALID;
+  int k = 0;
+  for (int i = first; i < first + count; ++i) k += p->ops[i]->launches();
+  return k;
+}
+
+int vt_program_add_gemm(vt_program* p, const vt_gemm_desc* d) {
+  if (!p || !d) return fail(VT_E_INVALID, "null argument");
+  std::unique_ptr<GemmOp> op(new GemmOp());
+  int rc = build_gemm(*d, op.get());
+  if (rc) return rc;
+  p->ops.push_back(std::move(op));
+  return VT_OK;
+}
+
+int vt_program_add_attention(vt_program* p, const vt_attn_desc* d) {
+  if (!p || !d) return fail(VT_E_INVALID, "null argument");
+  VT_REQUIRE(d->qkv && d->ctx && d->images >= 1 && d->tokens >= 1 && d->heads >= 1, "attention: bad descriptor");
+  std::unique_ptr<AttnOp> op(new AttnOp());
+  op->d = *d;
+  if (d->in_dtype == VT_BF16) {
+    const int D = d->heads * 64;
+    const uint64_t dims[2] = {(uint64_t)3 * D, (uint64_t)d->images * d->tokens};
+    const uint64_t st[1] = {(uint64_t)3 * D * 2};
+    const uint32_t box[2] = {64u, 128u};
+    int rc = make_tmap(&op->args.tm, VT_BF16, 2, d->qkv, dims, st, box);
+    if (rc) return rc;
+    VT_REQUIRE(aligned16(d->ctx), "attention: ctx must be 16-byte aligned");
+    op->args.ctx = reinterpret_cast<__nv_bfloat16*>(d->ctx);
+    op->args.ctx_ld = d->ctx_ld;
+    VT_REQUIRE(d->ctx_ld >= D && d->ctx_ld % 8 == 0, "attention: ctx_ld=%lld", (long long)d->ctx_ld);
+    op->args.tokens = d->tokens;
+    op->args.heads = d->heads;
+    op->args.D = D;
+    op->args.scale_log2 = 0.125f * 1.4426950408889634f;
+    op->grid = dim3((unsigned)((d->tokens + 127) / 128), (unsigned)d->heads, (unsigned)d->images);
+    VT_REQUIRE(d->images <= 65535, "attention: images=%d exceeds the grid z limit", d->images);
+  } else {
+    VT_REQUIRE(d->in_dtype == VT_F32, "attention: in_dtype %d", d->in_dtype);
+    VT_REQUIRE((size_t)vt::ATTF_WARPS * d->tokens * 4 <= 48 * 1024, "attention(f32): tokens=%d too many", d->tokens);
+  }
+  p->ops.push_back(std::move(op));
+  return VT_OK;
+}
+
+#define VT_SIMPLE_ADD(fname, OpT, DescT, check)                  \
+  int fname(vt_program* p, const DescT* d) {                     \
+    if (!p || !d) return fail(VT_E_INVALID, "null argument");    \
+    check;                                                       \
+    std::unique_ptr<OpT> op(new OpT());                          \
+    op->d = *d;                                                  \
+    p->ops.push_back(std::move(op));                             \
+    return VT_OK;                                                \
+  }
+
+VT_SIMPLE_ADD(vt_program_add_layernorm, LnOp, vt_ln_desc,
+              VT_REQUIRE(d->x && d->out && d->gamma && d->beta && d->rows >= 1 &&
+                             (d->D == 256 || d->D == 384 || d->D == 768 || d->D == 1024) && d->in_ld % 4 == 0 &&
+                             d->out_ld % 4 == 0 && aligned16(d->x) && aligned16(d->out) && d->out_plane % 4 == 0,
+                         "layernorm: bad descriptor (D=%d)", d->D))
+VT_SIMPLE_ADD(vt_program_add_imgstats, ImgStatsOp, vt_imgstats_desc,
+              VT_REQUIRE(d->img && d->partial && d->flags && d->count >= 1 && (d->dtype == VT_U8 || d->dtype == VT_F32) &&
+                             aligned16(d->img) && (reinterpret_cast<uintptr_t>(d->partial) & 7) == 0,
+                         "imgstats: bad descriptor"))
+VT_SIMPLE_ADD(vt_program_add_patchify, PatchifyOp, vt_patchify_desc,
+              VT_REQUIRE(d->img && d->out && d->flags && d->images >= 1 && d->patch >= 1 && d->H % d->patch == 0 &&
+                             d->W % d->patch == 0 && d->out_cols >= 3 * d->patch * d->patch && d->out_ld >= d->out_cols &&
+                             (d->dtype == VT_U8 || d->dtype == VT_F32),
+                         "patchify: bad descriptor"))
+VT_SIMPLE_ADD(vt_program_add_cls, ClsOp, vt_cls_desc, VT_REQUIRE(d->cls && d->pos && d->h, "cls: bad descriptor"))
+VT_SIMPLE_ADD(vt_program_add_pack, PackOp, vt_pack_desc,
+              VT_REQUIRE(d->src && d->out && d->rows >= 1 && d->cols >= 1, "pack: bad descriptor"))
+VT_SIMPLE_ADD(vt_program_add_affine, AffineOp, vt_affine_desc,
+              VT_REQUIRE(d->x && (d->out || d->xpad) && d->mins && d->maxs && d->rows >= 1 && d->A >= 1, "affine: bad descriptor"))
+VT_SIMPLE_ADD(vt_program_add_tembed, TembedOp, vt_tembed_desc,
+              VT_REQUIRE(d->t && d->out && d->rows >= 1 && d->dim >= 4 && d->dim % 2 == 0, "tembed: bad descriptor"))
+VT_SIMPLE_ADD(vt_program_add_sde, SdeOp, vt_sde_desc,
+              VT_REQUIRE(d->x && d->v && d->s && d->rows >= 1 && d->A >= 1, "sde: bad descriptor"))
+VT_SIMPLE_ADD(vt_program_add_lstm, LstmOp, vt_lstm_desc,
+              VT_REQUIRE(d->xw && d->w_hh && d->h && d->c && d->y && d->B >= 1 && d->T >= 1 && d->H == 256, "lstm: bad descriptor"))
+
+int vt_program_run(vt_program* p, int first, int count, void* stream) {
+  int rc = clamp_range(p, first, &count);
+  if (rc) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  for (int i = first; i < first + count; ++i) {
+    rc = p->ops[i]->launch(s);
+    if (rc) return rc;
+  }
+  return VT_OK;
+}
+
+int vt_program_graph_build(vt_program* p, int first, int count) {
+  int rc = clamp_range(p, first, &count);
+  if (rc) return rc;
+  if (!p->capture_stream) VT_CUDA(cudaStreamCreateWithFlags(&p->capture_stream, cudaStreamNonBlocking));
+  if (p->graph_exec) {
+    cudaGraphExecDestroy(p->graph_exec);
+    p->graph_exec = nullptr;
+  }
+  // function attributes cannot be set during capture: run the range once eagerly first
+  rc = vt_program_run(p, first, count, p->capture_stream);
+  if (rc) return rc;
+  VT_CUDA(cudaStreamSynchronize(p->capture_stream));
+  VT_CUDA(cudaStreamBeginCapture(p->capture_stream, cudaStreamCaptureModeThreadLocal));
+  rc = vt_program_run(p, first, count, p->capture_stream);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(p->capture_stream, &graph);
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) return fail(VT_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+  e = cudaGraphInstantiate(&p->graph_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail(VT_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  return VT_OK;
+}
+
+int vt_program_graph_launch(vt_program* p, void* stream) {
+  if (!p || !p->graph_exec) return fail(VT_E_INVALID, "no graph built");
+  VT_CUDA(cudaGraphLaunch(p->graph_exec, reinterpret_cast<cudaStream_t>(stream)));
+  return VT_OK;
+}
+
+int vt_pos_embed_resize(const float* src_dev, int32_t s, float* dst_dev, int32_t nh, int32_t nw, int32_t D, void* stream) {
+  VT_REQUIRE(src_dev && dst_dev && s >= 1 && nh >= 1 && nw >= 1 && D >= 1, "pos_embed_resize: bad arguments");
+  vt::pos_resize_kernel<<<grid_for((long long)nh * nw * D, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src_dev, s, dst_dev, nh, nw, D);
+  VT_LAUNCH_CHECK("pos_resize_kernel");
+  return VT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,199 @@
+"""ctypes binding of libvt_b200.so (C ABI: include/vt_b200.h).
+
+The library is built in-tree by `vla_touch_b200.build.build()` (nvcc, sm_100a).  There is NO fallback:
+if the shared object is missing, or a call is made without a CUDA device, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvt_b200.so")
+
+VT_BF16, VT_F32, VT_U8 = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_MISH = 0, 1, 2
+EPI_LINEAR, EPI_GN = 0, 1
+LAYOUT_BHWC, LAYOUT_BCHW = 0, 1
+MAX_TAPS = 8
+
+i32, i64, f32, u64, vp = C.c_int32, C.c_int64, C.c_float, C.c_uint64, C.c_void_p
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("a", vp), ("in_dtype", i32), ("a_C", i32), ("a_P", i32), ("a_T", i32), ("a_B", i32), ("a_G", i32),
+        ("a_ld", i64), ("a_sB", i64), ("a_sG", i64), ("a_c0", i32), ("kc", i32), ("taps", i32),
+        ("tap_p", i32 * MAX_TAPS), ("tap_t", i32 * MAX_TAPS), ("t_box", i32), ("b_box", i32), ("passes", i32),
+        ("a_plane", i32), ("w_plane", i32),
+        ("w", vp), ("n_pad", i32), ("w_ld", i32),
+        ("G", i32), ("M", i32), ("N", i32), ("bn", i32),
+        ("out", vp), ("out_dtype", i32), ("ldc", i32), ("out_g", i64), ("row_div", i32),
+        ("out_q", i64), ("out_r", i64), ("out_off", i64), ("out_plane", i64),
+        ("epi", i32), ("act", i32), ("bias", vp), ("colscale", vp), ("res", vp), ("ldres", i32),
+        ("res_g", i64), ("res_q", i64), ("res_r", i64), ("res_off", i64), ("res_plane", i64),
+        ("gn_gamma", vp), ("gn_beta", vp), ("gn_group_ch", i32), ("gn_eps", f32),
+        ("film_c", vp), ("film_t", vp), ("film_g", i64), ("film_tg", i64), ("film_ld", i32), ("film_C", i32), ("film_off", i32),
+    ]
+
+
+class LnDesc(C.Structure):
+    _fields_ = [("x", vp), ("in_ld", i64), ("in_row_stride", i64), ("rows", i32), ("D", i32), ("gamma", vp),
+                ("beta", vp), ("eps", f32), ("out", vp), ("out_dtype", i32), ("out_ld", i64), ("out_plane", i64),
+                ("act", i32)]
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [("qkv", vp), ("ctx", vp), ("in_dtype", i32), ("images", i32), ("tokens", i32), ("heads", i32),
+                ("ctx_ld", i64), ("ctx_plane", i64)]
+
+
+class ImgStatsDesc(C.Structure):
+    _fields_ = [("img", vp), ("dtype", i32), ("count", i64), ("partial", vp), ("flags", vp)]
+
+
+class PatchifyDesc(C.Structure):
+    _fields_ = [("img", vp), ("dtype", i32), ("layout", i32), ("images", i32), ("H", i32), ("W", i32), ("patch", i32),
+                ("flags", vp), ("out", vp), ("out_dtype", i32), ("out_cols", i32), ("out_ld", i32), ("out_plane", i64)]
+
+
+class ClsDesc(C.Structure):
+    _fields_ = [("cls", vp), ("pos", vp), ("h", vp), ("images", i32), ("tokens", i32), ("D", i32)]
+
+
+class PackDesc(C.Structure):
+    _fields_ = [("src", vp), ("src_ld", i64), ("rows", i32), ("cols", i32), ("act", i32), ("out", vp),
+                ("out_dtype", i32), ("out_ld", i64), ("dst_c0", i32), ("out_plane", i64), ("zero_to", i32)]
+
+
+class AffineDesc(C.Structure):
+    _fields_ = [("x", vp), ("out", vp), ("mins", vp), ("maxs", vp), ("rows", i32), ("A", i32), ("denorm", i32),
+                ("pad", f32), ("xpad", vp), ("xpad_dtype", i32), ("xpad_ld", i32), ("xpad_plane", i64), ("add", vp)]
+
+
+class TembedDesc(C.Structure):
+    _fields_ = [("t", vp), ("rows", i32), ("dim", i32), ("out", vp), ("out_dtype", i32), ("out_ld", i64),
+                ("out_plane", i64)]
+
+
+class SdeDesc(C.Structure):
+    _fields_ = [("x", vp), ("v", vp), ("s", vp), ("noise", vp), ("rows", i32), ("A", i32), ("ginv", f32),
+                ("dgg", f32), ("eps", f32), ("dt", f32), ("nscale", f32), ("d", f32), ("seed", u64), ("seed_dev", vp), ("step", i32),
+                ("xpad", vp), ("xpad_dtype", i32), ("xpad_ld", i32), ("xpad_plane", i64)]
+
+
+class LstmDesc(C.Structure):
+    _fields_ = [("xw", vp), ("w_hh", vp), ("h", vp), ("c", vp), ("y", vp), ("y_dtype", i32), ("y_ld", i64),
+                ("B", i32), ("T", i32), ("H", i32)]
+
+
+EXPORTS = [
+    "vt_last_error", "vt_abi_version", "vt_device_info", "vt_program_create", "vt_program_destroy",
+    "vt_program_num_ops", "vt_program_num_launches", "vt_program_add_gemm", "vt_program_add_layernorm",
+    "vt_program_add_attention", "vt_program_add_imgstats", "vt_program_add_patchify", "vt_program_add_cls",
+    "vt_program_add_pack", "vt_program_add_affine", "vt_program_add_tembed", "vt_program_add_sde",
+    "vt_program_add_lstm", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
+    "vt_pos_embed_resize",
+]
+
+_ADD = {
+    GemmDesc: "vt_program_add_gemm", LnDesc: "vt_program_add_layernorm", AttnDesc: "vt_program_add_attention",
+    ImgStatsDesc: "vt_program_add_imgstats", PatchifyDesc: "vt_program_add_patchify", ClsDesc: "vt_program_add_cls",
+    PackDesc: "vt_program_add_pack", AffineDesc: "vt_program_add_affine", TembedDesc: "vt_program_add_tembed",
+    SdeDesc: "vt_program_add_sde", LstmDesc: "vt_program_add_lstm",
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load libvt_b200.so (once).  Raises if it has not been built: there is no CPU/PyTorch fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(f"{LIB_PATH} not found: build it with `python -m vla_touch_b200.build` "
+                              "(nvcc, sm_100a). vla_touch_b200 has no fallback path.")
+        L = C.CDLL(LIB_PATH)
+        L.vt_last_error.restype = C.c_char_p
+        L.vt_program_create.argtypes = [C.POINTER(vp)]
+        L.vt_program_destroy.argtypes = [vp]
+        L.vt_program_num_ops.argtypes = [vp]
+        L.vt_program_num_launches.argtypes = [vp, C.c_int, C.c_int]
+        for desc, name in _ADD.items():
+            getattr(L, name).argtypes = [vp, C.POINTER(desc)]
+        L.vt_program_run.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.vt_program_graph_build.argtypes = [vp, C.c_int, C.c_int]
+        L.vt_program_graph_launch.argtypes = [vp, vp]
+        L.vt_device_info.argtypes = [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+        L.vt_pos_embed_resize.argtypes = [vp, i32, vp, i32, i32, i32, vp]
+        if L.vt_abi_version() != 1:
+            raise NativeError("libvt_b200.so ABI version mismatch; rebuild it")
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise NativeError(f"libvt_b200 error {rc}: {lib().vt_last_error().decode()}")
+
+
+def device_info():
+    sm, ma, mi = i32(), i32(), i32()
+    check(lib().vt_device_info(C.byref(sm), C.byref(ma), C.byref(mi)))
+    return sm.value, ma.value, mi.value
+
+
+def require_b200() -> None:
+    """The product path runs on sm_100 only; anything else is an error, never a fallback."""
+    sm, ma, mi = device_info()
+    if ma != 10:
+        raise NativeError(f"vla_touch_b200 needs an sm_100a (B200) device, found compute capability {ma}.{mi}")
+
+
+def current_stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Program:
+    """An ordered list of pre-encoded kernel launches living in the native library."""
+
+    def __init__(self) -> None:
+        h = vp()
+        check(lib().vt_program_create(C.byref(h)))
+        self._h = h
+        self.descs: List[C.Structure] = []   # python-side mirror (kept for inspection and the CPU plan emulator)
+        self.keep: list = []                 # tensors that must outlive the program
+
+    def add(self, desc: C.Structure) -> int:
+        check(getattr(lib(), _ADD[type(desc)])(self._h, C.byref(desc)))
+        self.descs.append(desc)
+        return len(self.descs) - 1
+
+    def __len__(self) -> int:
+        return len(self.descs)
+
+    def num_launches(self, first: int = 0, count: int = -1) -> int:
+        return lib().vt_program_num_launches(self._h, first, count)
+
+    def run(self, first: int = 0, count: int = -1, stream: Optional[int] = None) -> None:
+        check(lib().vt_program_run(self._h, first, count, vp(current_stream_ptr() if stream is None else stream)))
+
+    def graph_build(self, first: int = 0, count: int = -1) -> None:
+        check(lib().vt_program_graph_build(self._h, first, count))
+
+    def graph_launch(self, stream: Optional[int] = None) -> None:
+        check(lib().vt_program_graph_launch(self._h, vp(current_stream_ptr() if stream is None else stream)))
+
+    def __del__(self) -> None:
+        try:
+            if self._h:
+                lib().vt_program_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
