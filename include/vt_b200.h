@@ -179,6 +179,7 @@ typedef struct vt_pack_desc {
   int32_t dst_c0;
   int64_t out_plane;
   int32_t zero_to;    /* >cols: also zero-fill columns [dst_c0+cols, dst_c0+zero_to) */
+  int32_t src_row_div; /* >1: output row r reads source row r / src_row_div (broadcast over time steps) */
 } vt_pack_desc;
 
 /* normalize_actions / denormalize_actions, controller_dataset.py:303-384 (padding factor 1.4) */
@@ -188,7 +189,7 @@ typedef struct vt_affine_desc {
   const float* mins;  /* [A] */
   const float* maxs;  /* [A] */
   int32_t rows, A;
-  int32_t denorm;     /* 0 normalise (with the safe_range guard), 1 de-normalise (without) */
+  int32_t denorm;     /* 0 normalise (with the safe_range guard), 1 de-normalise (without), 2 identity (x + add) */
   float pad;          /* padding factor (reference default 1.4) */
   void* xpad;         /* optional: also write channel-padded copy [rows][xpad_ld] in xpad_dtype */
   int32_t xpad_dtype, xpad_ld;
@@ -234,6 +235,7 @@ typedef struct vt_lstm_desc {
   void* y;            /* [B][T][y_ld] hidden outputs */
   int32_t y_dtype;
   int64_t y_ld;
+  int64_t y_plane;    /* >0 (f32): tf32 hi/lo split of y */
   int32_t B, T, H;
 } vt_lstm_desc;
 

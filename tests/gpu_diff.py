@@ -16,6 +16,10 @@ def _buffer_of(plan: Plan, address: int):
         base = t.data_ptr()
         if base <= address < base + t.numel() * t.element_size():
             return name
+    for i, t in enumerate(plan._reg):          # externally owned tensor: address it by registration index
+        base = t.data_ptr()
+        if base <= address < base + t.numel() * t.element_size():
+            return i
     return None
 
 
@@ -43,8 +47,10 @@ def diff_plans(cpu: Plan, gpu: Plan, first=0, count=-1, sync_inputs=True, report
         prog.run(i, 1)
         torch.cuda.synchronize()
         name = out_buffer_name(cpu, cpu.descs[i])
-        ref = cpu.bufs[name].float()
-        got = gpu.bufs[name].float().cpu()
+        tc = cpu.bufs[name] if isinstance(name, str) else cpu._reg[name]
+        tg = gpu.bufs[name] if isinstance(name, str) else gpu._reg[name]
+        ref = tc.float()
+        got = tg.float().cpu()
         err = (got - ref).abs()
         err = torch.where(torch.isfinite(err), err, torch.full_like(err, float("inf")))
         row = (i, cpu.tags[i], name, float(err.max()), float(ref.abs().max()))
@@ -52,7 +58,7 @@ def diff_plans(cpu: Plan, gpu: Plan, first=0, count=-1, sync_inputs=True, report
         if report:
             report(row)
         if resync:
-            gpu.bufs[name].copy_(cpu.bufs[name])
+            tg.copy_(tc)
     return rows
 
 
@@ -62,5 +68,5 @@ def format_rows(rows, tol_rel=None):
         flag = ""
         if tol_rel is not None and not (err <= tol_rel * max(ref, 1e-6)):
             flag = "  <-- MISMATCH"
-        out.append(f"{i:4d} {tag:48s} {name:16s} err {err:10.3e} ref {ref:10.3e}{flag}")
+        out.append(f"{i:4d} {tag:48s} {str(name):16s} err {err:10.3e} ref {ref:10.3e}{flag}")
     return "\n".join(out)

@@ -157,7 +157,7 @@ def emu_patchify(plan, d: nv.PatchifyDesc):
     n = d.images * d.H * d.W * 3
     img = _flat(plan, d.img, TORCH_DT[d.dtype])[:n]
     img = img.reshape(d.images, d.H, d.W, 3).permute(0, 3, 1, 2) if d.layout == nv.LAYOUT_BHWC else img.reshape(d.images, 3, d.H, d.W)
-    img = img.float()
+    img = img.float()[:, :, : d.H // d.patch * d.patch, : d.W // d.patch * d.patch]
     flags = _flat(plan, d.flags, torch.int32)
     if int(flags[0]):
         img = img / 255.0
@@ -180,7 +180,8 @@ def emu_cls(plan, d: nv.ClsDesc):
 def emu_pack(plan, d: nv.PackDesc):
     src = _flat(plan, d.src, torch.float32)
     rows = torch.arange(d.rows)
-    v = src[(rows[:, None] * d.src_ld + torch.arange(d.cols)[None, :]).reshape(-1)].reshape(d.rows, d.cols)
+    srows = rows // d.src_row_div if d.src_row_div > 1 else rows
+    v = src[(srows[:, None] * d.src_ld + torch.arange(d.cols)[None, :]).reshape(-1)].reshape(d.rows, d.cols)
     v = _act(v, d.act)
     width = max(d.cols, d.zero_to)
     full = torch.zeros(d.rows, width)
@@ -199,7 +200,9 @@ def emu_affine(plan, d: nv.AffineDesc):
     center = (mins + maxs) / 2
     pmin, pmax = center - padded / 2, center + padded / 2
     rng = pmax - pmin
-    if not d.denorm:
+    if d.denorm == 2:
+        y = x
+    elif not d.denorm:
         rng = torch.where(rng < 1e-6, torch.ones_like(rng), rng)
         y = 2.0 * (x - pmin) / rng - 1.0
     else:
@@ -253,7 +256,7 @@ def emu_lstm(plan, d: nv.LstmDesc):
         i_, f_, g_, o_ = g.chunk(4, dim=-1)
         cc = torch.sigmoid(f_) * cc + torch.sigmoid(i_) * torch.tanh(g_)
         hh = torch.sigmoid(o_) * torch.tanh(cc)
-        _store(plan, d.y, d.y_dtype, (rows[:, None] * d.T + t) * d.y_ld + torch.arange(H)[None, :], hh)
+        _store(plan, d.y, d.y_dtype, (rows[:, None] * d.T + t) * d.y_ld + torch.arange(H)[None, :], hh, d.y_plane)
     h[:] = hh
     c[:] = cc
 

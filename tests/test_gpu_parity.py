@@ -1,0 +1,259 @@
+"""GPU parity tests (B200): the public reference-shaped API, running the sm_100a kernels through the C ABI, against
+(a) golden vectors produced by the UNMODIFIED reference (tests/golden, oracle/gen_golden.py) and (b) the CPU oracle.
+
+Tolerances are the north-star gates: bf16 path  max|err| <= 5e-2 * max|ref|   (relative to the tensor scale)
+                                     fp32 path  max|err| <= 1e-3 absolute     (3-pass split-tf32 tensor-core GEMMs)
+"""
+import pytest
+import torch
+
+import vt_testutil as U
+from oracle import vt_oracle as orc
+from vla_touch_b200 import shapes as shp
+from vla_touch_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+MODES = [pytest.param(False, id="bf16"), pytest.param(True, id="f32x3")]
+
+
+def check(got, ref, precise, what=""):
+    got, ref = got.detach().float().cpu(), ref.float()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert torch.isfinite(got).all(), what
+    if precise:
+        assert err <= 1e-3, f"{what}: max|err| {err:.3e} > 1e-3 (scale {scale:.2f})"
+    else:
+        assert err <= 5e-2 * scale, f"{what}: max|err| {err:.3e} > 5e-2 * {scale:.2f}"
+    return err
+
+
+def test_native_library_is_loaded_and_device_is_b200():
+    from vla_touch_b200 import native as nv
+    sm, major, minor = nv.device_info()
+    assert major == 10 and sm >= 100
+    nv.require_b200()
+
+
+@pytest.mark.parametrize("A", [7, 10])
+def test_normalize_denormalize_bit_exact(A):
+    from vla_touch_b200.controller_dataset import denormalize_actions, normalize_actions
+    g = U.golden(f"norm_A{A}")
+    st = {k: v.to(DEV) for k, v in syn.synth_stats_varied(A, seed=3).items()}
+    x = syn.det_uniform("norm.x", (3, 16, A), 3, -2.0, 2.0).to(DEV)
+    assert torch.equal(normalize_actions(x, st, "vla").cpu(), g["vla_n"])
+    assert torch.equal(normalize_actions(x, st, "expert").cpu(), g["exp_n"])
+    assert torch.equal(denormalize_actions(x, st, "expert").cpu(), g["exp_dn"])
+    with pytest.raises(ValueError):
+        normalize_actions(x, st, "nope")
+
+
+@pytest.mark.parametrize("precise", MODES)
+@pytest.mark.parametrize("case", U.DINO_CASES, ids=[c[0] for c in U.DINO_CASES])
+def test_dinov2_encoder_forward(case, precise):
+    from vla_touch_b200.visual_encoder import DINOv2Encoder
+    tag, hidden, heads, layers, hw, batch, kind, seed = case
+    g = U.golden(tag)
+    name = "facebook/dinov2-base" if hidden == 768 else "facebook/dinov2-small"
+    enc = DINOv2Encoder(name, DEV, state_dict=U.dino_sd(hidden, layers, seed), precise=precise)
+    img = U.images_for(kind, "dino.img", batch, hw, seed)
+    out = enc.forward(img)
+    assert out.shape == (batch, hidden) and out.dtype == torch.float32
+    check(out, g["cls"], precise, tag)
+
+
+def test_dinov2_encoder_rejects_bad_channels():
+    from vla_touch_b200.visual_encoder import DINOv2Encoder
+    enc = DINOv2Encoder("facebook/dinov2-small", DEV, state_dict=U.dino_sd(384, 1, 1))
+    with pytest.raises(ValueError):
+        enc.forward(torch.zeros(1, 4, 28, 28))
+
+
+@pytest.mark.parametrize("precise", MODES)
+@pytest.mark.parametrize("A,T", [(10, 16), (10, 48), (7, 32), (7, 64)])
+def test_unet_forward(A, T, precise):
+    from vla_touch_b200.bridge.networks.conditional_unet_1D_si import InterpolantsConditionalUnet1D
+    net = InterpolantsConditionalUnet1D(A, 256, precise=precise)
+    net.load_state_dict(U.net_sd(A, 21))
+    net.to(DEV)
+    g = U.golden(f"unet_A{A}_T{T}")
+    x = syn.det_uniform("unet.x", (3, T, A), 22, -1.0, 1.0).to(DEV)
+    cond = syn.det_normal("unet.cond", (3, 256), 22).to(DEV)
+    t = torch.tensor([0.3, 0.001, 0.999], device=DEV)
+    check(net.v_net(x, t, global_cond=cond), g["v"], precise, "v_net")
+    check(net.s_net(x, t[:1].expand(3), global_cond=cond), g["s"], precise, "s_net")
+
+
+def _interpolant(A, T, precise, beta=0.03):
+    from vla_touch_b200.bridge.bridge_model import StochasticInterpolants
+    args = {'interpolant_type': 'linear', 'gamma_type': '2^0.5*t(t-1)', 'epsilon_type': '1-t', 'prior_policy': 'vla',
+            'beta_max': beta, 'sde_type': 'vs', 'action_dim': A, 'obs_dim': 256, 'obs_horizon': 1, 'net_type': 'unet1D_si',
+            'pretrain': False, 'context_frames': 2, 'horizon': T}
+    si = StochasticInterpolants(precise=precise)
+    si.load_model(args, DEV)
+    si.net.load_state_dict(U.net_sd(A, 21))
+    ema_full = U.net_sd(A, 1021)
+    with torch.no_grad():
+        for (n, _), s in zip(si.net.named_parameters(), si.ema.shadow_params):
+            s.copy_(ema_full[n])
+    si.ema.version += 1
+    return si
+
+
+@pytest.mark.parametrize("precise", MODES)
+@pytest.mark.parametrize("A,T,n", [(10, 16, 10), (7, 64, 10), (7, 64, 50)])
+def test_sample_with_recorded_noise(A, T, n, precise):
+    g = U.golden(f"sde_A{A}_T{T}_n{n}")
+    si = _interpolant(A, T, precise)
+    x0 = syn.det_uniform("sde.x0", (2, T, A), 23, -1.0, 1.0).to(DEV)
+    cond = syn.det_normal("sde.cond", (2, 256), 23).to(DEV)
+    si.noise_override = g["noise"].to(DEV)
+    out, traj = si.sample(x_prior=x0, cond=cond, diffuse_step=n, recod_traj=True)
+    assert len(traj) == n + 1
+    check(traj[1], g["x1"], precise, "first step")
+    check(out, g["out"], precise, "sample")
+    out2 = si.sample(x_prior=x0, cond=cond, diffuse_step=n)
+    assert torch.equal(out2, out)                      # step-by-step == one-shot, and deterministic
+
+
+@pytest.mark.parametrize("A,T", [(10, 16), (7, 64)])
+def test_sample_beta0_is_noise_free(A, T):
+    g = U.golden(f"sde_A{A}_T{T}_n10_beta0")
+    si = _interpolant(A, T, True, beta=0.0)
+    x0 = syn.det_uniform("sde.x0", (2, T, A), 23, -1.0, 1.0).to(DEV)
+    cond = syn.det_normal("sde.cond", (2, 256), 23).to(DEV)
+    out = si.sample(x_prior=x0, cond=cond, diffuse_step=10)       # in-kernel Philox noise, scaled by beta_max = 0
+    check(out, g["out"], True, "beta0")
+
+
+def test_sample_philox_noise_statistics():
+    """Production noise path: in-kernel Philox draws; successive calls differ, and the spread matches dt*sqrt(2 eps)*d."""
+    si = _interpolant(7, 64, False)
+    x0 = syn.det_uniform("sde.x0", (64, 64, 7), 23, -1.0, 1.0).to(DEV)
+    cond = syn.det_normal("sde.cond", (64, 256), 23).to(DEV)
+    a = si.sample(x_prior=x0, cond=cond, diffuse_step=10)
+    b = si.sample(x_prior=x0, cond=cond, diffuse_step=10)
+    assert not torch.equal(a, b)
+    assert (a - b).abs().max() < 0.5 and (a - b).std() > 1e-4
+
+
+@pytest.mark.parametrize("precise", MODES)
+@pytest.mark.parametrize("tag", list(U.PREDICT_CASES))
+def test_predict_against_reference_golden(tag, precise):
+    c = U.predict_case(tag)
+    ctl = U.make_controller(c, DEV, precise=precise)
+    cond = ctl.encode_observation(c["state"].to(DEV), c["img1"], c["img2"], c["forces"].to(DEV))
+    check(cond, c["gold"]["cond"], precise, "encode_observation")
+    ctl.noise_override = c["gold"]["noise"].to(DEV)
+    vla = c["vla"].to(DEV)
+    vla_before = vla.clone()
+    out = ctl.predict(c["state"].to(DEV), vla, c["img1"], c["img2"], c["forces"].to(DEV))
+    assert out.shape == c["gold"]["out"].shape and out.device.type == "cuda"
+    assert torch.equal(vla, vla_before)                 # inputs are not mutated
+    check(out, c["gold"]["out"], precise, tag)
+    out2 = ctl.predict(c["state"].to(DEV), vla, c["img1"], c["img2"], c["forces"].to(DEV))
+    assert torch.equal(out, out2)                       # CUDA-graph replay is deterministic
+
+
+def test_predict_uses_ema_weights():
+    c = U.predict_case("predict_cfg2_B3_dark_varstats")
+    ctl = U.make_controller(c, DEV, precise=True)
+    ctl.noise_override = c["gold"]["noise"].to(DEV)
+    args = (c["state"].to(DEV), c["vla"].to(DEV), c["img1"], c["img2"], c["forces"].to(DEV))
+    good = ctl.predict(*args)
+    ctl.diffusion_model.ema.copy_to()                   # live weights := EMA; then perturb the EMA copy
+    with torch.no_grad():
+        for s in ctl.diffusion_model.ema.shadow_params:
+            s.mul_(1.05)
+    ctl.diffusion_model.ema.version += 1
+    bad = ctl.predict(*args)
+    assert (good.cpu() - c["gold"]["out"]).abs().max() <= 1e-3
+    assert (bad - good).abs().max() > 1e-2              # the engine re-packed the changed EMA weights
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    c = U.predict_case("predict_cfg2_B3_dark_varstats")
+    ctl = U.make_controller(c, DEV, precise=False)
+    ctl.noise_override = c["gold"]["noise"].to(DEV)
+    args = (c["state"].to(DEV), c["vla"].to(DEV), c["img1"], c["img2"], c["forces"].to(DEV))
+    want = ctl.predict(*args)
+    ctl.save(str(tmp_path))
+    ck = torch.load(tmp_path / "controller.pt", weights_only=False)
+    assert set(ck) == {"state_encoder", "model_args", "stats", "force_decoder"}
+    bm = torch.load(tmp_path / "bridge_model.pt", weights_only=False)
+    assert set(bm) == {"net", "ema"} and len(bm["net"]) == 438 and len(bm["ema"]["shadow_params"]) == 438
+    from vla_touch_b200.bridge_controller import DiffusionController
+    c2 = DiffusionController(state_dim=c["A"], device=DEV, model_args=ctl.model_args, force_dim=c["F"],
+                             image_state_dict=c["dino"], diffusion_steps=c["steps"])
+    c2.load(str(tmp_path))
+    c2.noise_override = ctl.noise_override
+    assert torch.equal(c2.predict(*args), want)
+
+
+def test_full_size_batch_properties():
+    """BASELINE configs[1] size (batch 256, 224x224, T=64, A=7, F=64, 10 steps): size-independent properties."""
+    B, T, A, Fd, hw = 256, 64, 7, 64, 224
+    c = dict(A=A, F=Fd, T=T, hidden=384, steps=10, seed=5, dino=U.dino_sd(384, 12, 5), enc=U.enc_sd(2 * 384 + A + Fd, 5),
+             stats=syn.synth_stats_varied(A, 5))
+    ctl = U.make_controller(c, DEV, precise=False)
+    inp = syn.synth_predict_inputs(B, T, A, Fd, hw, 5)
+    noise = syn.det_normal("prop.noise", (10, B, T, A), 5).to(DEV)
+    ctl.noise_override = noise
+    i1, i2 = inp["images_cam1"][:, None], inp["images_cam2"][:, None]
+    big = ctl.predict(inp["state"].to(DEV), inp["vla_actions"].to(DEV), i1, i2, inp["forces"].to(DEV))
+    assert big.shape == (B, T, A) and torch.isfinite(big).all()
+    # rows are independent: the first 3 rows of the batch-256 call equal a batch-3 call on the same rows
+    ctl.noise_override = noise[:, :3].contiguous()
+    small = ctl.predict(inp["state"][:3].to(DEV), inp["vla_actions"][:3].to(DEV), i1[:3], i2[:3], inp["forces"][:3].to(DEV))
+    assert (big[:3] - small).abs().max() <= 1e-5 * max(1.0, float(small.abs().max()))
+    # and they match the CPU oracle on those rows
+    ref = orc.predict(c["dino"], c["enc"], U.net_sd(A, 1005, "v_net"), U.net_sd(A, 1005, "s_net"), c["stats"], 6,
+                      inp["state"][:3], inp["vla_actions"][:3], i1[:3], i2[:3], inp["forces"][:3], 10, 0.03, noise[:, :3].cpu())
+    check(big[:3], ref, False, "batch-256 rows vs oracle")
+
+
+@pytest.mark.parametrize("precise", MODES)
+@pytest.mark.parametrize("A,Fd,T", [(10, 3, 16), (7, 64, 32)])
+def test_lstm_controller(A, Fd, T, precise):
+    from vla_touch_b200.controller_dataset import normalize_actions
+    from vla_touch_b200.lstm_step_controller import TactileLSTMController
+    g = U.golden(f"lstm_A{A}_F{Fd}_T{T}")
+    lc = TactileLSTMController(state_dim=A, hidden_dim=256, num_layers=2, dropout=0.1, device=DEV, force_dim=Fd,
+                               image_state_dict=U.dino_sd(384, 1, 1), precise=precise)
+    for nm, mod in (("obs_encoder", lc.obs_encoder), ("force_encoder", lc.force_encoder), ("lstm", lc.lstm),
+                    ("output_head", lc.output_head)):
+        syn.fill_named_(mod.named_parameters(), 41, prefix=f"lstm.{nm}.")
+    lc.eval()
+    lc.stats = {k: v.to(DEV) for k, v in syn.synth_stats_varied(A, 41).items()}
+    vla = syn.det_uniform("lstm.vla", (3, T, A), 41, -1.0, 1.0).to(DEV)
+    forces = syn.det_normal("lstm.forces", (3, T, Fd), 41).to(DEV)
+    cond = syn.det_normal("lstm.cond", (3, 256), 41).to(DEV)
+    expert = syn.det_uniform("lstm.exp", (3, T, A), 41, -1.0, 1.0).to(DEV)
+    vla_n = normalize_actions(vla, lc.stats, 'vla')
+    batch = {"vla_act": vla_n, "obs_cond": cond, "forces": forces, "expert_act": expert}
+    check(lc.forward(batch), g["fwd"], precise, "forward")
+    assert abs(float(lc.get_loss(batch)) - float(g["loss"])) <= (1e-4 if precise else 5e-2 * float(g["loss"]))
+    check(lc.predict_sequence(cond, vla, forces), g["seq"], precise, "predict_sequence")
+    # stateful single-step deployment path (:232-286): T ticks carrying (h, c)
+    steps = [lc.predict(cond, vla_n[:, t], forces[:, t], initialize=(t == 0)) for t in range(T)]
+    check(torch.stack(steps, dim=1), g["seq"], precise, "predict step-by-step")
+    assert lc.hidden_state.shape == (2, 3, 256)
+
+
+def test_kernels_match_the_descriptor_interpreter_op_by_op():
+    """Every launch of a small U-Net program against the CPU interpretation of the same descriptor (isolated per op)."""
+    import gpu_diff
+    from vla_touch_b200.unet import UnetProgram
+    A, T, B = 10, 16, 3
+    sds = [U.net_sd(A, 21, "v_net"), U.net_sd(A, 21, "s_net")]
+    ups = []
+    for dev in ("cpu", DEV):
+        up = UnetProgram(sds, A, B, T, dev, precise=False)
+        up.x.copy_(syn.det_uniform("unet.x", (B, T, A), 22, -1.0, 1.0))
+        up.t.copy_(torch.tensor([0.3, 0.001, 0.999]))
+        up.cond.copy_(syn.det_normal("unet.cond", (B, 256), 22))
+        ups.append(up)
+    rows = gpu_diff.diff_plans(ups[0].plan, ups[1].plan, resync=True)
+    bad = [r for r in rows if not r[3] <= 2e-2 * max(r[4], 1e-6)]      # one bf16 ulp at the tensor scale is 2^-8
+    assert not bad, gpu_diff.format_rows(bad)

@@ -1,0 +1,206 @@
+"""CPU tests of the host-side logic: the plan descriptors (interpreted by tests/plan_emu.py) reproduce the oracle /
+the reference golden vectors, the C ABI library loads and exports what include/vt_b200.h declares, ctypes mirrors
+match the C structs, and the reference-API helpers behave like the reference."""
+import ctypes
+import os
+import subprocess
+import sys
+import tempfile
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import plan_emu
+import vt_testutil as U
+from oracle import vt_oracle as orc
+from vla_touch_b200 import native as nv
+from vla_touch_b200 import schedule as sch
+from vla_touch_b200 import shapes as shp
+from vla_touch_b200 import synthetic as syn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def cpu_resize(pos, s, nh, nw):
+    D = pos.shape[1]
+    return F.interpolate(pos.reshape(1, s, s, D).permute(0, 3, 1, 2), size=(nh, nw), mode="bicubic",
+                         align_corners=False).permute(0, 2, 3, 1).reshape(-1, D).contiguous()
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = nv.lib()
+    header = open(os.path.join(ROOT, "include", "vt_b200.h")).read()
+    import re
+    declared = set(re.findall(r"\b(vt_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(nv.EXPORTS), declared ^ set(nv.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.vt_abi_version() == 1
+
+
+def test_no_device_is_an_error_not_a_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(nv.NativeError):
+        nv.device_info()
+    from vla_touch_b200.plan import Plan
+    with pytest.raises(nv.NativeError):
+        Plan("cpu").compile()
+    from vla_touch_b200.controller_dataset import normalize_actions
+    with pytest.raises(nv.NativeError):
+        normalize_actions(torch.zeros(1, 2, 3), syn.synth_stats(3), "vla")
+
+
+def test_ctypes_structs_match_the_c_header():
+    descs = {"vt_gemm_desc": nv.GemmDesc, "vt_ln_desc": nv.LnDesc, "vt_attn_desc": nv.AttnDesc,
+             "vt_imgstats_desc": nv.ImgStatsDesc, "vt_patchify_desc": nv.PatchifyDesc, "vt_cls_desc": nv.ClsDesc,
+             "vt_pack_desc": nv.PackDesc, "vt_affine_desc": nv.AffineDesc, "vt_tembed_desc": nv.TembedDesc,
+             "vt_sde_desc": nv.SdeDesc, "vt_lstm_desc": nv.LstmDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/vt_b200.h"', 'int main(void){']
+    probes = []
+    for cname, cls in descs.items():
+        lines.append(f'printf("%zu\\n", sizeof({cname}));')
+        probes.append((cname, None, ctypes.sizeof(cls)))
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("%zu\\n", offsetof({cname}, {fname}));')
+            probes.append((cname, fname, getattr(cls, fname).offset))
+    lines.append('return 0;}')
+    with tempfile.TemporaryDirectory() as td:
+        src, exe = os.path.join(td, "p.c"), os.path.join(td, "p")
+        open(src, "w").write("\n".join(lines))
+        subprocess.run(["gcc", "-o", exe, src], check=True)
+        got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    assert len(got) == len(probes)
+    for (cname, fname, want), g in zip(probes, got):
+        assert g == want, (cname, fname, g, want)
+
+
+def test_schedule_matches_oracle_and_reference_quirks():
+    for ds in (10, 50, 93, 99, 7):
+        n, dt, ts = sch.sde_schedule(ds)
+        n2, dt2, ts2 = orc.sde_schedule(ds)
+        assert n == n2 and dt == dt2 and all(torch.equal(a, b) for a, b in zip(ts, ts2))
+        for t in ts:
+            got = sch.sde_coefficients(t, dt)
+            ref = orc.sde_coefficients(t, dt, 0.03)
+            assert got == tuple(float(x) for x in ref)
+    assert sch.sde_schedule(93)[0] == 92
+    with pytest.raises(NotImplementedError):
+        sch.check_model_args({"gamma_type": "(2t(t-1))^0.5"})
+    with pytest.raises(NotImplementedError):
+        sch.check_model_args({"sde_type": "bs"})
+
+
+@pytest.mark.parametrize("precise,A,T,tol", [(True, 7, 64, 5e-5), (True, 10, 48, 5e-5), (False, 10, 16, 8e-2)])
+def test_unet_plan_reproduces_the_oracle(precise, A, T, tol):
+    from vla_touch_b200.unet import UnetProgram
+    B = 3
+    v_sd, s_sd = U.net_sd(A, 21, "v_net"), U.net_sd(A, 21, "s_net")
+    x = syn.det_uniform("unet.x", (B, T, A), 22, -1.0, 1.0)
+    cond = syn.det_normal("unet.cond", (B, 256), 22)
+    t = torch.tensor([0.3, 0.001, 0.999])
+    up = UnetProgram([v_sd, s_sd], A, B, T, "cpu", precise=precise)
+    up.x.copy_(x); up.t.copy_(t); up.cond.copy_(cond)
+    plan_emu.run(up.plan)
+    if T in (16, 32, 48, 64):
+        g = U.golden(f"unet_A{A}_T{T}")
+        assert (up.bufs.out[0] - g["v"]).abs().max() <= tol          # reference golden vector (v_net, per-sample t)
+    assert (up.bufs.out[0] - orc.unet_forward(v_sd, x, t, cond)).abs().max() <= tol
+    assert (up.bufs.out[1] - orc.unet_forward(s_sd, x, t, cond)).abs().max() <= tol
+    assert len(up.plan) == 43 and sum(isinstance(d, nv.GemmDesc) for d in up.plan.descs) == 39
+
+
+def _engine_for(c, precise):
+    from vla_touch_b200.dino import DinoWeights
+    from vla_touch_b200.engine import BridgeEngine
+    dw = DinoWeights(c["dino"], c["heads"], "cpu", precise)
+    imgs = [c["img1"], c["img2"]]
+    if imgs[0].dim() == 5:
+        imgs = [i[:, 0] for i in imgs]
+    imgs = [i.contiguous() for i in imgs]
+    eng = BridgeEngine(dino=dw, enc_sd=c["enc"], v_sd=c["v_ema"], s_sd=c["s_ema"], action_dim=c["A"], state_dim=c["A"],
+                       force_dim=c["F"], use_force=True, B=c["B"], T=c["T"], H=c["hw"], W=c["hw"], img_dtype=imgs[0].dtype,
+                       layout=nv.LAYOUT_BHWC, diffuse_step=c["steps"], device="cpu", precise=precise, resize=cpu_resize,
+                       inject_noise=True)
+    eng.dino_prog.img[0].copy_(imgs[0]); eng.dino_prog.img[1].copy_(imgs[1])
+    eng.state.copy_(c["state"]); eng.forces.copy_(c["forces"]); eng.vla.copy_(c["vla"]); eng.noise.copy_(c["gold"]["noise"])
+    eng.set_stats(c["stats"])
+    return eng
+
+
+@pytest.mark.parametrize("tag,precise", [("predict_cfg2_B3_dark_varstats", True), ("predict_T48_f32_varstats", True),
+                                         ("predict_cfg2_B3_dark_varstats", False)])
+def test_predict_plan_reproduces_the_reference_golden(tag, precise):
+    c = U.predict_case(tag)
+    eng = _engine_for(c, precise)
+    plan_emu.run(eng.setup)
+    a0, a1 = eng.ranges["dino"][0], eng.ranges["normalize"][1]
+    plan_emu.run(eng.plan, a0, a1 - a0)
+    b0, b1 = eng.step_ranges[0][0], eng.ranges["denormalize"][1]
+    plan_emu.run(eng.plan, b0, b1 - b0)
+    g = c["gold"]
+    scale = float(g["out"].abs().max())
+    if precise:
+        assert (eng.cond - g["cond"]).abs().max() <= 1e-4
+        assert (eng.out - g["out"]).abs().max() <= 1e-3            # north-star fp32 gate: 1e-3 abs
+    else:
+        assert (eng.out - g["out"]).abs().max() <= 5e-2 * scale    # north-star bf16 gate: 5e-2 rel (to the tensor scale)
+    # the two batch-global predicates of visual_encoder.py:78,100, evaluated per camera call
+    want = [1, 0] if "dark" in tag else [0, 1]
+    assert eng.dino_prog.flags[:, :2].tolist() == [want, want]
+
+
+@pytest.mark.parametrize("precise,tol", [(True, 2e-5), (False, 5e-2)])
+def test_lstm_plan_reproduces_the_reference_golden(precise, tol):
+    from vla_touch_b200.lstm_step_controller import LstmEngine
+    A, Fd, T = 10, 3, 16
+    g = U.golden(f"lstm_A{A}_F{Fd}_T{T}")
+    mods = {"force_encoder": syn.synth_state_dict(shp.mlp_shapes([Fd, 128, 128]), 41, "lstm.force_encoder."),
+            "lstm": syn.synth_state_dict(shp.lstm_shapes(128 + A), 41, "lstm.lstm."),
+            "output_head": syn.synth_state_dict(shp.lstm_head_shapes(256, A), 41, "lstm.output_head.")}
+    st = syn.synth_stats_varied(A, 41)
+    vla_n = orc.normalize_actions(syn.det_uniform("lstm.vla", (3, T, A), 41, -1.0, 1.0), st, "vla")
+    for denorm, key in ((False, "fwd"), (True, "seq")):
+        eng = LstmEngine(mods, A, Fd, 256, 2, 3, T, "cpu", precise, denorm)
+        eng.vla.copy_(vla_n); eng.forces.copy_(syn.det_normal("lstm.forces", (3, T, Fd), 41))
+        eng.cond.copy_(syn.det_normal("lstm.cond", (3, 256), 41))
+        eng.stats["action_mins"].copy_(st["action_mins"]); eng.stats["action_maxs"].copy_(st["action_maxs"])
+        plan_emu.run(eng.plan)
+        assert (eng.out - g[key]).abs().max() <= tol * max(1.0, float(g[key].abs().max()))
+
+
+def test_ema_matches_torch_ema_semantics():
+    from vla_touch_b200.ema import ExponentialMovingAverage
+    p = [torch.nn.Parameter(torch.ones(3)), torch.nn.Parameter(torch.zeros(2))]
+    ema = ExponentialMovingAverage(p, decay=0.75)
+    with torch.no_grad():
+        p[0].add_(1.0)
+    ema.update()                                   # decay = min(0.75, 2/11)
+    d = min(0.75, 2 / 11)
+    assert torch.allclose(ema.shadow_params[0], torch.full((3,), 1.0 - (1 - d) * (1.0 - 2.0)))
+    with ema.average_parameters():
+        assert torch.equal(p[0].data, ema.shadow_params[0])
+    assert torch.equal(p[0].data, torch.full((3,), 2.0))
+    sd = ema.state_dict()
+    assert set(sd) == {"decay", "num_updates", "shadow_params", "collected_params"} and sd["num_updates"] == 1
+    ema2 = ExponentialMovingAverage(p, decay=0.5)
+    ema2.load_state_dict(sd)
+    assert ema2.decay == 0.75 and torch.equal(ema2.shadow_params[0], ema.shadow_params[0])
+
+
+def test_parameter_trees_follow_the_reference_key_contract():
+    from vla_touch_b200.bridge.networks.conditional_unet_1D_si import InterpolantsConditionalUnet1D
+    net = InterpolantsConditionalUnet1D(10, 256)
+    keys = [k for k, _ in net.named_parameters()]
+    assert keys == list(shp.si_net_shapes(10, 256).keys())
+    assert len(keys) == 438
+    ref_dir = "/root/reference/VLA/residual_controller"
+    if not os.path.isdir(ref_dir):
+        pytest.skip("reference tree not present (GPU box)")
+    sys.path.insert(0, ROOT)
+    from oracle.ref_shims import import_reference
+    ref = import_reference()
+    rnet = ref.bridge_model.InterpolantsConditionalUnet1D(input_dim=10, global_cond_dim=256)
+    assert [k for k, _ in rnet.named_parameters()] == keys
+    assert [tuple(p.shape) for p in rnet.parameters()] == [tuple(p.shape) for p in net.parameters()]

@@ -83,3 +83,25 @@ def predict_case(tag):
                 dino=dino_sd(hidden, layers, seed), enc=enc_sd(2 * hidden + A + Fd, seed),
                 v_ema=net_sd(A, seed + 1000, "v_net"), s_ema=net_sd(A, seed + 1000, "s_net"),
                 gold=golden(tag))
+
+
+def make_controller(c, device, precise=False):
+    """DiffusionController (public API) holding exactly the weights of a PREDICT_CASES entry: live net = seed, EMA
+    shadow = seed + 1000 (so that a test passes only if sample() really uses the EMA weights, bridge_model.py:267)."""
+    from vla_touch_b200.bridge_controller import DiffusionController
+    model_args = {'interpolant_type': 'linear', 'gamma_type': '2^0.5*t(t-1)', 'epsilon_type': '1-t', 'prior_policy': 'vla',
+                  'beta_max': 0.03, 'sde_type': 'vs', 'action_dim': c["A"], 'obs_dim': 256, 'obs_horizon': 1,
+                  'net_type': 'unet1D_si', 'pretrain': False, 'context_frames': 2, 'horizon': c["T"]}
+    name = "facebook/dinov2-base" if c["hidden"] == 768 else "facebook/dinov2-small"
+    ctl = DiffusionController(state_dim=c["A"], hidden_dim=256, image_model_path=name, diffusion_steps=c["steps"], device=device,
+                              model_args=model_args, use_force=True, force_dim=c["F"], image_state_dict=c["dino"], precise=precise)
+    ctl.state_encoder.load_state_dict(c["enc"])
+    ctl.diffusion_model.net.load_state_dict(net_sd(c["A"], c["seed"]))
+    ema_full = net_sd(c["A"], c["seed"] + 1000)
+    names = [n for n, _ in ctl.diffusion_model.net.named_parameters()]
+    with torch.no_grad():
+        for n, s in zip(names, ctl.diffusion_model.ema.shadow_params):
+            s.copy_(ema_full[n])
+    ctl.diffusion_model.ema.version += 1
+    ctl.stats = {k: v.to(device) for k, v in c["stats"].items()}
+    return ctl

@@ -1,0 +1,121 @@
+"""StochasticInterpolants (reference: bridge/bridge_model.py:28-447) on the B200 engine.
+
+`sample()` runs sde_vs (:334-387) with the EMA weights (:267) as one native program: per-sample FiLM table, then
+n x [36 grouped tcgen05 implicit-GEMM launches for v_net+s_net, Euler-Maruyama update], no host work per step."""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional
+
+import torch
+
+from ..ema import ExponentialMovingAverage
+from ..engine import BridgeEngine
+from ..params import sub_state_dict
+from ..schedule import check_model_args
+from .networks.conditional_unet_1D_si import InterpolantsConditionalUnet1D
+
+
+class StochasticInterpolants:
+    def __init__(self, model_args=None, precise: bool = False):
+        self.precise = precise
+        self.net = None
+        self.ema = None
+        self._engines: Dict[tuple, BridgeEngine] = {}
+        self._engine_version: Dict[tuple, int] = {}
+        self.noise_override: Optional[torch.Tensor] = None    # [n_steps,B,T,A]: injected N(0,1) draws (parity tests)
+        self._seed = 0
+        if model_args:
+            self.load_model_args(model_args)
+
+    def load_model_args(self, model_args):
+        check_model_args(model_args)                    # NotImplementedError for schedules outside App. B
+        self.interpolant_type = model_args['interpolant_type']
+        self.gamma_type = model_args['gamma_type']
+        self.epsilon_type = model_args['epsilon_type']
+        self.prior_policy = model_args['prior_policy']
+        self.d = model_args['beta_max']
+        self.t_min = 0.001
+        self.gamma_inv_max = 200.0
+        self.net = None
+        self.ema = None
+        self.prior_model = None
+        self.sde_type = model_args.get('sde_type', 'vs')
+
+    def load_model(self, model_args, device):
+        self.load_model_args(model_args)
+        if model_args['net_type'] != 'unet1D_si':
+            raise NotImplementedError
+        self.net = InterpolantsConditionalUnet1D(input_dim=model_args['action_dim'],
+                                                 global_cond_dim=model_args['obs_dim'] * model_args['obs_horizon'],
+                                                 precise=self.precise)
+        self.ema = ExponentialMovingAverage(self.net.parameters(), decay=0.75)
+        if model_args['pretrain']:
+            checkpoint = torch.load(os.path.join(model_args['ckpt_path'], "bridge_model.pt"), map_location="cpu",
+                                    weights_only=False)
+            self.net.load_state_dict(checkpoint['net'])
+            self.ema.load_state_dict(checkpoint["ema"])
+        self.net.to(device)
+        self.ema.to(device)
+        self.device = device
+        self._engines.clear()
+
+    def save_model(self, ckpt_path):
+        torch.save({"net": self.net.state_dict(), "ema": self.ema.state_dict()}, os.path.join(ckpt_path, "bridge_model.pt"))
+
+    def train(self):
+        return self
+
+    def eval(self):
+        return self
+
+    # ---- EMA weights as flat state dicts for the engine ----
+    def ema_state_dicts(self):
+        names = [n for n, _ in self.net.named_parameters()]
+        full = {n: s for n, s in zip(names, self.ema.shadow_params)}
+        return sub_state_dict(full, "v_net."), sub_state_dict(full, "s_net.")
+
+    def _engine(self, B: int, T: int, diffuse_step: int, inject: bool) -> BridgeEngine:
+        key = (B, T, diffuse_step, inject)
+        eng = self._engines.get(key)
+        if eng is None:
+            v_sd, s_sd = self.ema_state_dicts()
+            eng = BridgeEngine(dino=None, enc_sd=None, v_sd=v_sd, s_sd=s_sd, action_dim=self.net.input_dim,
+                               state_dim=self.net.input_dim, force_dim=0, use_force=False, B=B, T=T, diffuse_step=diffuse_step,
+                               beta_max=self.d, device=self.device, precise=self.precise, hidden_dim=self.net.global_cond_dim,
+                               inject_noise=inject)
+            self._engines[key] = eng
+            self._engine_version[key] = self.ema.version
+        elif self._engine_version[key] != self.ema.version:
+            eng.refresh_unet(*self.ema_state_dicts())
+            self._engine_version[key] = self.ema.version
+        return eng
+
+    @torch.no_grad()
+    def sample(self, x_prior, cond, diffuse_step=10, recod_traj=False):
+        """x_prior [B,T,A] (normalised), cond [B,obs_dim] -> x_target [B,T,A] (and the trajectory list)."""
+        if self.sde_type != 'vs':
+            raise NotImplementedError
+        B, T, A = x_prior.shape
+        inject = self.noise_override is not None
+        eng = self._engine(B, T, diffuse_step, inject)
+        eng.x.copy_(x_prior)
+        eng.cond.copy_(cond)
+        if inject:
+            eng.noise.copy_(self.noise_override)
+        else:
+            self._seed += 1
+            eng.seed.fill_(self._seed)
+        eng.run_ranges(["film_c", "xprior"])
+        if not recod_traj:
+            eng.run_steps()
+            return eng.x.clone()
+        traj = [eng.x.clone()]
+        for k in range(eng.n_steps):
+            eng.run_steps(k, 1)
+            traj.append(eng.x.clone())
+        return traj[-1], traj
+
+    def get_loss(self, batch_dict, device=None):
+        raise NotImplementedError("StochasticInterpolants.get_loss (training, bridge_model.py:220-246) is not built yet on the "
+                                  "B200 path; see DESIGN.md 'next rows'")

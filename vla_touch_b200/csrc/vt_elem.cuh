@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src, long long src_ld, int rows, int cols,
                                                    int act, void* __restrict__ out, int out_dtype, long long out_ld,
-                                                   int dst_c0, long long out_plane, int zero_to) {
+                                                   int dst_c0, long long out_plane, int zero_to, int src_row_div) {
   const int width = zero_to > cols ? zero_to : cols;
   const long long total = (long long)rows * width;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src
     const long long r = idx / width;
     float v = 0.f;
     if (c < cols) {
-      v = src[r * src_ld + c];
+      v = src[(src_row_div > 1 ? r / src_row_div : r) * src_ld + c];
       if (act == 1) v = gelu_erf(v);
       else if (act == 2) v = mish_precise(v);
     }
@@ -281,7 +281,9 @@ __global__ void __launch_bounds__(256) affine_kernel(const float* __restrict__ x
     float v = x[idx];
     if (add) v = __fadd_rn(v, add[idx]);
     float y;
-    if (!denorm) {
+    if (denorm == 2) {
+      y = v;
+    } else if (!denorm) {
       if (range < 1e-6f) range = 1.0f;
       y = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fsub_rn(v, pmin)), range), 1.0f);
     } else {

@@ -387,7 +387,7 @@ struct PackOp : Op {
     const int width = d.zero_to > d.cols ? d.zero_to : d.cols;
     vt::pack_kernel<<<grid_for((long long)d.rows * width, 256), 256, 0, s>>>(d.src, d.src_ld, d.rows, d.cols, d.act, d.out,
                                                                              d.out_dtype, d.out_ld, d.dst_c0, d.out_plane,
-                                                                             d.zero_to);
+                                                                             d.zero_to, d.src_row_div);
     VT_LAUNCH_CHECK("pack_kernel");
     return VT_OK;
   }
@@ -431,7 +431,7 @@ struct LstmOp : Op {
   int launch(cudaStream_t s) override {
     const int blocks = (d.B + vt::LSTM_ROWS - 1) / vt::LSTM_ROWS;
     if (d.H == 256)
-      vt::lstm_seq_kernel<256><<<blocks, 256, 0, s>>>(d.xw, d.w_hh, d.h, d.c, d.y, d.y_dtype, d.y_ld, d.B, d.T);
+      vt::lstm_seq_kernel<256><<<blocks, 256, 0, s>>>(d.xw, d.w_hh, d.h, d.c, d.y, d.y_dtype, d.y_ld, d.y_plane, d.B, d.T);
     else
       return fail(VT_E_UNSUPPORTED, "lstm: H=%d", d.H);
     VT_LAUNCH_CHECK("lstm_seq_kernel");
@@ -558,8 +558,8 @@ VT_SIMPLE_ADD(vt_program_add_imgstats, ImgStatsOp, vt_imgstats_desc,
                              aligned16(d->img) && (reinterpret_cast<uintptr_t>(d->partial) & 7) == 0,
                          "imgstats: bad descriptor"))
 VT_SIMPLE_ADD(vt_program_add_patchify, PatchifyOp, vt_patchify_desc,
-              VT_REQUIRE(d->img && d->out && d->flags && d->images >= 1 && d->patch >= 1 && d->H % d->patch == 0 &&
-                             d->W % d->patch == 0 && d->out_cols >= 3 * d->patch * d->patch && d->out_ld >= d->out_cols &&
+              VT_REQUIRE(d->img && d->out && d->flags && d->images >= 1 && d->patch >= 1 && d->H >= d->patch &&
+                             d->W >= d->patch && d->out_cols >= 3 * d->patch * d->patch && d->out_ld >= d->out_cols &&
                              (d->dtype == VT_U8 || d->dtype == VT_F32),
                          "patchify: bad descriptor"))
 VT_SIMPLE_ADD(vt_program_add_cls, ClsOp, vt_cls_desc, VT_REQUIRE(d->cls && d->pos && d->h, "cls: bad descriptor"))

@@ -14,7 +14,8 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf
 template <int H>
 __global__ void __launch_bounds__(H) lstm_seq_kernel(const float* __restrict__ xw, const float* __restrict__ w_hh_t,
                                                      float* __restrict__ h_state, float* __restrict__ c_state,
-                                                     void* __restrict__ y, int y_dtype, long long y_ld, int B, int T) {
+                                                     void* __restrict__ y, int y_dtype, long long y_ld, long long y_plane,
+                                                     int B, int T) {
   __shared__ float sh[LSTM_ROWS][H];
   const int j = threadIdx.x;
   const int b0 = blockIdx.x * LSTM_ROWS;
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(H) lstm_seq_kernel(const float* __restrict__ x
       c[r] = fg * c[r] + ig * gg;
       hreg[r] = og * tanhf(c[r]);
       sh[r][j] = hreg[r];
-      if (b0 + r < B) store_val(y, y_dtype, ((long long)(b0 + r) * T + t) * y_ld + j, 0, hreg[r]);
+      if (b0 + r < B) store_val(y, y_dtype, ((long long)(b0 + r) * T + t) * y_ld + j, y_plane, hreg[r]);
     }
     __syncthreads();
   }

@@ -97,8 +97,9 @@ class DinoProgram:
 
     def __init__(self, plan: Plan, W: DinoWeights, n_calls: int, B: int, H: int, Wd: int, img_dtype: torch.dtype,
                  layout: int, resize: Callable = native_pos_resize, tag: str = "dino"):
-        if H % PATCH or Wd % PATCH:
-            raise ValueError(f"image size {H}x{Wd} must be a multiple of the patch size {PATCH}")
+        if H < PATCH or Wd < PATCH:
+            raise ValueError(f"image size {H}x{Wd} is smaller than one {PATCH}x{PATCH} patch")
+        # like Conv2d(k14, s14), trailing rows/columns that do not fill a patch are ignored (384 -> 27 patches)
         if img_dtype not in (torch.uint8, torch.float32):
             raise ValueError(f"images must be uint8 or float32, got {img_dtype}")
         self.plan, self.W = plan, W

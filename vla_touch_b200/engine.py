@@ -128,22 +128,24 @@ class BridgeEngine:
             D = 0
         self.ranges["dino"] = (start, len(p))
         start = len(p)
-        self.enc = MlpWeights(enc_sd, dev, m)
-        self.enc.register(p)
-        obs_dim = 2 * D + state_dim + (force_dim if use_force else 0)
-        if self.enc.dims[0][1] != obs_dim:
-            raise ValueError(f"state_encoder expects {self.enc.dims[0][1]} inputs, controller provides {obs_dim}")
-        kpad = self.enc.dims[0][3]
-        obs = p.buf("enc.obs", (B, m.ld(kpad)), m.tdt)
-        c0 = 0
-        if dino is not None:
-            for c in range(2):
-                p.add(_pack_desc(self.dino_prog.feat[c], D, B, D, obs, 0, m, kpad, c * D), f"enc.cat.cam{c}")
-            c0 = 2 * D
-        p.add(_pack_desc(self.state, state_dim, B, state_dim, obs, 0, m, kpad, c0), "enc.cat.state")
-        if use_force:
-            p.add(_pack_desc(self.forces, force_dim, B, force_dim, obs, 0, m, kpad, c0 + state_dim), "enc.cat.force")
-        build_mlp(p, self.enc, obs, B, self.cond, "enc")
+        self.enc = None
+        if enc_sd is not None:          # None: `cond` is an input (StochasticInterpolants.sample called directly)
+            self.enc = MlpWeights(enc_sd, dev, m)
+            self.enc.register(p)
+            obs_dim = 2 * D + state_dim + (force_dim if use_force else 0)
+            if self.enc.dims[0][1] != obs_dim:
+                raise ValueError(f"state_encoder expects {self.enc.dims[0][1]} inputs, controller provides {obs_dim}")
+            kpad = self.enc.dims[0][3]
+            obs = p.buf("enc.obs", (B, m.ld(kpad)), m.tdt)
+            c0 = 0
+            if dino is not None:
+                for c in range(2):
+                    p.add(_pack_desc(self.dino_prog.feat[c], D, B, D, obs, 0, m, kpad, c * D), f"enc.cat.cam{c}")
+                c0 = 2 * D
+            p.add(_pack_desc(self.state, state_dim, B, state_dim, obs, 0, m, kpad, c0), "enc.cat.state")
+            if use_force:
+                p.add(_pack_desc(self.forces, force_dim, B, force_dim, obs, 0, m, kpad, c0 + state_dim), "enc.cat.force")
+            build_mlp(p, self.enc, obs, B, self.cond, "enc")
         self.ranges["enc"] = (start, len(p))
 
         # ---- sampler ----
@@ -195,6 +197,16 @@ class BridgeEngine:
         self._setup_done = False
         self._graphs: Dict[tuple, object] = {}
         self._noise_mode: Optional[bool] = None
+
+    # ---- weight refresh (same device addresses: programs and graphs stay valid) ----
+    def refresh_unet(self, v_sd: SD, s_sd: SD) -> None:
+        self.unet.refresh([v_sd, s_sd])
+        self._setup_done = False        # the time half of the FiLM tables depends on the weights
+
+    def refresh_enc(self, enc_sd: SD) -> None:
+        new = MlpWeights(enc_sd, self.device, self.mode)
+        for dst, src in zip(self.enc.w + self.enc.b, new.w + new.b):
+            dst.copy_(src)
 
     # ---- execution ----
     def set_stats(self, stats: Dict[str, torch.Tensor]) -> None:

@@ -64,7 +64,8 @@ class ClsDesc(C.Structure):
 
 class PackDesc(C.Structure):
     _fields_ = [("src", vp), ("src_ld", i64), ("rows", i32), ("cols", i32), ("act", i32), ("out", vp),
-                ("out_dtype", i32), ("out_ld", i64), ("dst_c0", i32), ("out_plane", i64), ("zero_to", i32)]
+                ("out_dtype", i32), ("out_ld", i64), ("dst_c0", i32), ("out_plane", i64), ("zero_to", i32),
+                ("src_row_div", i32)]
 
 
 class AffineDesc(C.Structure):
@@ -85,7 +86,7 @@ class SdeDesc(C.Structure):
 
 class LstmDesc(C.Structure):
     _fields_ = [("xw", vp), ("w_hh", vp), ("h", vp), ("c", vp), ("y", vp), ("y_dtype", i32), ("y_ld", i64),
-                ("B", i32), ("T", i32), ("H", i32)]
+                ("y_plane", i64), ("B", i32), ("T", i32), ("H", i32)]
 
 
 EXPORTS = [

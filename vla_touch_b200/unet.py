@@ -94,10 +94,20 @@ class UnetWeights:
         self.mode = m = Mode(precise)
         self.device = torch.device(device)
         self.cin0 = round_up(action_dim, m.ke)            # channel-padded network input
-        dev = lambda t: t.to(self.device)
+        self.film_off = {}
+        self.t = self._pack(sds)
+
+    def refresh(self, sds: Sequence[SD]) -> None:
+        """Re-pack new parameter values into the existing device tensors (addresses unchanged)."""
+        new = self._pack(sds)
+        for k, t in self.t.items():
+            t.copy_(new[k])
+
+    def _pack(self, sds: Sequence[SD]) -> Dict[str, torch.Tensor]:
+        m, action_dim = self.mode, self.A
+        dev = lambda t: t.detach().to(self.device)
         g = lambda k: [dev(sd[k]) for sd in sds]
-        self.t = {}
-        T = self.t
+        T: Dict[str, torch.Tensor] = {}
         # time MLP: Linear(256,1024) Mish Linear(1024,256)
         T["time1.w"] = m.pack_w(torch.stack([w.float() for w in g("diffusion_step_encoder.1.weight")]))
         T["time1.b"] = _pack_vec(g("diffusion_step_encoder.1.bias"), 4 * DSED)
@@ -105,7 +115,6 @@ class UnetWeights:
         T["time2.b"] = _pack_vec(g("diffusion_step_encoder.3.bias"), DSED)
         # FiLM: rows of all blocks stacked in execution order
         names = block_names()
-        self.film_off = {}
         off = 0
         wf = [[] for _ in sds]
         bf = [[] for _ in sds]
@@ -158,6 +167,7 @@ class UnetWeights:
         T["final0.gb"] = _pack_vec(g("final_conv.0.block.1.bias"), c0)
         T["final1.w"] = _pack_conv(g("final_conv.1.weight"), c0, m, n_pad=32)
         T["final1.b"] = _pack_vec(g("final_conv.1.bias"), 32)
+        return T
 
     def register(self, plan: Plan) -> None:
         for t in self.t.values():
