@@ -74,13 +74,13 @@ typedef struct vt_gemm_desc {
   int32_t w_plane;    /* K distance from the hi to the lo plane of W (passes == 3) */
   /* W operand: [G][n_pad][w_ld] with K contiguous */
   const void* w;
-  int32_t n_pad;      /* rows of W per group, multiple of bn */
+  int32_t n_pad;      /* rows of W per group (a multiple of bn when G > 1) */
   int32_t w_ld;       /* elements per W row (>= taps * kc, multiple of 8) */
   /* problem */
   int32_t G;
   int32_t M;          /* logical rows per group */
   int32_t N;          /* valid output columns per group */
-  int32_t bn;         /* tile width: 32 or 128 (VT_EPI_GN: 128) */
+  int32_t bn;         /* tile width: 32, 128, 192 or 256 (VT_EPI_GN: 128 or 256; f32 operands: 32 or 128) */
   /* output mapping: q = m / row_div, rem = m % row_div, out row = q*out_q + rem*out_r + out_off */
   void* out;
   int32_t out_dtype;

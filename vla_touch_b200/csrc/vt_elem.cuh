@@ -139,31 +139,51 @@ template <typename T>
 __global__ void __launch_bounds__(256) patchify_kernel(const T* __restrict__ img, int layout, int images, int H, int W,
                                                        int patch, const int* __restrict__ flags, void* __restrict__ out,
                                                        int out_dtype, int out_cols, int out_ld, long long out_plane) {
+  // one thread = 8 consecutive im2col columns of one patch row (one 16-byte store for bf16 outputs)
   const int gw = W / patch, gh = H / patch;
-  const int kk = 3 * patch * patch;
-  const long long total = (long long)images * gh * gw * out_cols;
+  const int pp = patch * patch;
+  const int kk = 3 * pp;
+  const int k8n = out_cols >> 3;
+  const long long total = (long long)images * gh * gw * k8n;
   const bool scale255 = flags[0] != 0, donorm = flags[1] != 0;
   const float mean[3] = {0.485f, 0.456f, 0.406f};
   const float stdv[3] = {0.229f, 0.224f, 0.225f};
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(idx % out_cols);
-    const long long m = idx / out_cols;
-    float v = 0.f;
-    if (k < kk) {
-      const int p = (int)(m % (gh * gw));
-      const long long b = m / (gh * gw);
-      const int py = p / gw, px = p - py * gw;
-      const int c = k / (patch * patch);
-      const int r = k - c * patch * patch;
-      const int i = r / patch, j = r - i * patch;
-      const int y = py * patch + i, x = px * patch + j;
-      const long long src = (layout == 0) ? (((b * H + y) * W + x) * 3 + c) : (((b * 3 + c) * H + y) * (long long)W + x);
-      v = (float)img[src];
-      if (scale255) v = __fdiv_rn(v, 255.0f);
-      if (donorm) v = __fdiv_rn(__fsub_rn(v, mean[c]), stdv[c]);
+    const int k0 = (int)(idx % k8n) << 3;
+    const long long m = idx / k8n;
+    const int p = (int)(m % (gh * gw));
+    const long long b = m / (gh * gw);
+    const int py = p / gw, px = p - py * gw;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = k0 + e;
+      float x = 0.f;
+      if (k < kk) {
+        const int c = k / pp;
+        const int r = k - c * pp;
+        const int i = r / patch, j = r - i * patch;
+        const int yy = py * patch + i, xx = px * patch + j;
+        const long long src = (layout == 0) ? (((b * H + yy) * W + xx) * 3 + c) : (((b * 3 + c) * H + yy) * (long long)W + xx);
+        x = (float)img[src];
+        if (scale255) x = __fdiv_rn(x, 255.0f);
+        if (donorm) x = __fdiv_rn(__fsub_rn(x, mean[c]), stdv[c]);
+      }
+      v[e] = x;
     }
-    store_val(out, out_dtype, m * out_ld + k, out_plane, v);
+    const long long o = m * out_ld + k0;
+    if (out_dtype == 0) {
+      uint4 w;
+      w.x = pack_bf16x2(v[0], v[1]);
+      w.y = pack_bf16x2(v[2], v[3]);
+      w.z = pack_bf16x2(v[4], v[5]);
+      w.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + o) = w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) store_val(out, out_dtype, o + e, out_plane, v[e]);
+    }
   }
 }
 

@@ -5,11 +5,15 @@
 // with the op that follows fused into the epilogue: bias, GELU/Mish, LayerScale + residual, or
 // GroupNorm(8) + Mish + FiLM / residual (Conv1dBlock + ConditionalResidualBlock1D, :40-105).
 //
-// One CTA computes a 128 x BN output tile.  Warp 0 = TMA producer, warp 1 = TMEM allocator + UMMA issuer,
-// warps 2..5 = epilogue (one TMEM lane quarter each).  A-tiles are fetched with a 5-D tensor map
-// (C, phase, T, B, G): a conv tap is a TMA box whose T coordinate is shifted (out-of-bounds rows are
-// zero-filled by the TMA unit = the conv's zero padding), a stride-2 conv reads the even/odd phase, and
-// v_net / s_net are the G dimension, so no im2col buffer ever exists.
+// PERSISTENT kernel: one CTA per SM walks a static round-robin list of 128 x BN output tiles.
+//   warp 0      TMA producer: A/B k-blocks through a STAGES-deep mbarrier ring that runs ahead across tiles
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer; two accumulators in TMEM (2 x BN columns)
+//   warps 2-5   epilogue warpgroup 0 (accumulator 0: even local tiles)
+//   warps 6-9   epilogue warpgroup 1 (accumulator 1: odd local tiles)
+// so the epilogue of tile i (tcgen05.ld, GroupNorm / activation math, global stores) overlaps the main loop of tile i+1.
+// A-tiles are fetched with a 5-D tensor map (C, phase, T, B, G): a conv tap is a TMA box whose T coordinate is
+// shifted (out-of-bounds rows are zero-filled by the TMA unit = the conv's zero padding), a stride-2 conv reads the
+// even/odd phase, and v_net / s_net are the G dimension, so no im2col buffer ever exists.
 #pragma once
 #include "vt_elem.cuh"
 #include "vt_ptx.cuh"
@@ -17,7 +21,7 @@
 namespace vt {
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * 128;
 constexpr int GEMM_MAX_TAPS = 8;
 
@@ -27,6 +31,8 @@ enum : int { EPI_LINEAR = 0, EPI_GN = 1 };
 struct GemmArgs {
   CUtensorMap tmA;  // 5-D (C, P, T, B, G), box (KE, 1, Tbox, Bbox, 1), SWIZZLE_128B
   CUtensorMap tmB;  // 2-D (Ktot, G*n_pad), box (KE, BN), SWIZZLE_128B
+  // ---- tiles ----
+  int n_tiles, m_tiles, total_tiles;  // tile id = (g * m_tiles + m_tile) * n_tiles + n_tile
   // ---- K loop: k-block i -> (pass, tap, cb) ----
   int passes;   // 1; 3 = split-tf32 (hi*hi, lo*hi, hi*lo)
   int taps;     // conv taps (1 for a plain GEMM)
@@ -83,10 +89,13 @@ struct InTraits<float> {
   static constexpr uint32_t FMT = UMMA_FMT_TF32;
 };
 
+// per epilogue warpgroup: 5 column vectors, GroupNorm row partials [128][BN/32] and sample sums [32][BN/32] (float2)
+__host__ __device__ constexpr int GEMM_WG_SCRATCH_FLOATS(int BN) { return 5 * BN + (128 + 32) * (BN / 32 > 4 ? BN / 32 : 4) * 2; }
+
 template <int BN, int STAGES>
 constexpr int gemm_smem_bytes() {
-  return 1024 /*align slack*/ + STAGES * (GEMM_A_STAGE_BYTES + BN * 128) + 256 /*barriers*/ + 5 * BN * 4 /*col vecs*/ +
-         128 * 4 * 8 /*GN partials*/ + 32 * 4 * 8 /*GN stats*/;
+  return 1024 /*align slack*/ + STAGES * (GEMM_A_STAGE_BYTES + BN * 128) + 256 /*barriers*/ +
+         2 * GEMM_WG_SCRATCH_FLOATS(BN) * 4;
 }
 
 template <typename TOut>
@@ -120,14 +129,268 @@ __device__ __forceinline__ void load_res8(const __nv_bfloat16* p, float* r) {
   }
 }
 
+template <typename TOut>
+__device__ __forceinline__ void store_split8(TOut* outp, long long plane, const float* y) {
+  if constexpr (sizeof(TOut) == 4) {
+    if (plane > 0) {
+      float hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        hi[j] = tf32_hi(y[j]);
+        lo[j] = y[j] - hi[j];
+      }
+      store_chunk8<TOut>(outp, hi);
+      store_chunk8<TOut>(outp + plane, lo);
+      return;
+    }
+  }
+  store_chunk8<TOut>(outp, y);
+}
+
+// Per-tile state shared by the epilogue flavours.
+struct EpiTile {
+  int n0, g, r;            // first column, group, tile row (== TMEM lane)
+  long long grow;          // logical row
+  bool valid;
+  int q, rem;
+  uint32_t taddr;          // TMEM address of this thread's lane, column 0 of the accumulator
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// EPI_LINEAR: bias -> activation -> column scale -> (+ fp32 residual) -> store.  The residual chunk of the NEXT
+// 32 columns is requested before the current chunk is processed, the first one before the accumulator is ready.
+// ------------------------------------------------------------------------------------------------------------
+template <int BN, typename TOut, bool PRECISE>
+__device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile& t, const float* colv, uint64_t* acc_full,
+                                                uint32_t acc_parity) {
+  TOut* outp = reinterpret_cast<TOut*>(a.out) + (long long)t.g * a.out_g +
+               ((long long)t.q * a.out_q + (long long)t.rem * a.out_r + a.out_off) * a.ldc + t.n0;
+  const long long res_row = (long long)t.q * a.res_q + (long long)t.rem * a.res_r + a.res_off;
+  const float* resp = a.res ? reinterpret_cast<const float*>(a.res) + (long long)t.g * a.res_g + res_row * a.ldres + t.n0 : nullptr;
+  const bool vres = resp && a.vec && t.valid;
+  float4 rb[8];
+  auto fetch = [&](int c) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      rb[i] = (vres && t.n0 + c + 4 * i + 4 <= a.N) ? *reinterpret_cast<const float4*>(resp + c + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  fetch(0);
+  mbar_wait(acc_full, acc_parity);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = 0; c < BN; c += 32) {
+    uint32_t v[32];
+    tmem_ld32(t.taddr + c, v);
+    float4 rc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rc[i] = rb[i];
+    if (c + 32 < BN) fetch(c + 32);
+    tmem_ld_wait();
+    if (t.valid) {
+#pragma unroll
+      for (int j8 = 0; j8 < 32; j8 += 8) {
+        const int cc = c + j8;
+        if (t.n0 + cc >= a.N) break;
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float x = __uint_as_float(v[j8 + j]) + colv[cc + j];
+          if (a.act == ACT_GELU) x = PRECISE ? gelu_erf(x) : gelu_fast(x);
+          else if (a.act == ACT_MISH) x = PRECISE ? mish_precise(x) : mish_f(x);
+          y[j] = x * colv[BN + cc + j];
+        }
+        if (a.vec && t.n0 + cc + 8 <= a.N) {
+          const float4 r0 = rc[j8 / 4], r1 = rc[j8 / 4 + 1];
+          y[0] += r0.x; y[1] += r0.y; y[2] += r0.z; y[3] += r0.w;
+          y[4] += r1.x; y[5] += r1.y; y[6] += r1.z; y[7] += r1.w;
+          store_split8<TOut>(outp + cc, a.out_plane, y);
+        } else {  // ragged last columns / unaligned rows: scalar
+          for (int j = 0; j < 8 && t.n0 + cc + j < a.N; ++j) {
+            const float yy = y[j] + (resp ? resp[cc + j] : 0.f);
+            if constexpr (sizeof(TOut) == 4) {
+              if (a.out_plane > 0) {
+                const float hi = tf32_hi(yy);
+                outp[cc + j] = hi;
+                outp[a.out_plane + cc + j] = yy - hi;
+              } else {
+                outp[cc + j] = yy;
+              }
+            } else {
+              outp[cc + j] = __float2bfloat16(yy);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// EPI_GN: GroupNorm(8) + Mish + FiLM | residual.  Tile = all T rows of `rows_valid / gn_rows` samples x 128 channels =
+// whole groups, so the statistics are tile-local.  Pass 1: per-row partial sums per 32-column chunk, reduced over the
+// rows of a sample with warp shuffles (power-of-two T <= 32, or T a multiple of 32) or through shared memory.
+// ------------------------------------------------------------------------------------------------------------
+template <int BN, typename TOut, bool PRECISE>
+__device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t, const float* colv, float2* gn_part,
+                                            float2* gn_stat, int et, int bar_id, uint64_t* acc_full, uint32_t acc_parity) {
+  static_assert(BN == 128 || BN == 256, "GN epilogue: whole 32/64-channel groups per tile");
+  constexpr int NCH = BN / 32;  // 32-column chunks per tile
+  TOut* outp = reinterpret_cast<TOut*>(a.out) + (long long)t.g * a.out_g +
+               ((long long)t.q * a.out_q + (long long)t.rem * a.out_r + a.out_off) * a.ldc + t.n0;
+  const long long res_row = (long long)t.q * a.res_q + (long long)t.rem * a.res_r + a.res_off;
+  const TOut* resp = a.res ? reinterpret_cast<const TOut*>(a.res) + (long long)t.g * a.res_g + res_row * a.ldres + t.n0 : nullptr;
+  const float* filmp = a.film_c ? a.film_c + (long long)t.g * a.film_g + (long long)t.q * a.film_ld + a.film_off + t.n0 : nullptr;
+  const int lane = threadIdx.x & 31;
+
+  mbar_wait(acc_full, acc_parity);
+  tc_fence_after();
+  float s1[NCH], s2[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    uint32_t v[32];
+    tmem_ld32(t.taddr + ch * 32, v);
+    tmem_ld_wait();
+    float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = __uint_as_float(v[j]) + colv[ch * 32 + j];
+      a1 += x;
+      a2 = fmaf(x, x, a2);
+    }
+    s1[ch] = t.valid ? a1 : 0.f;
+    s2[ch] = t.valid ? a2 : 0.f;
+  }
+  const int T = a.gn_rows;
+  const float cnt = (float)(T << a.gn_gs_log2);
+  if (T <= 32 && (T & (T - 1)) == 0) {
+    // samples are aligned groups of T lanes: segmented butterfly, every lane ends with its sample's totals
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      for (int off = T >> 1; off > 0; off >>= 1) {
+        s1[ch] += __shfl_xor_sync(0xffffffffu, s1[ch], off);
+        s2[ch] += __shfl_xor_sync(0xffffffffu, s2[ch], off);
+      }
+    }
+  } else if ((T & 31) == 0) {
+    // a sample spans T/32 whole warps: warp butterfly, then combine the warps through shared memory
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      s1[ch] = warp_sum(s1[ch]);
+      s2[ch] = warp_sum(s2[ch]);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) gn_part[(t.r >> 5) * NCH + ch] = make_float2(s1[ch], s2[ch]);
+    }
+    named_bar_sync(bar_id, 128);
+    const int wpt = T >> 5;
+    const int w0 = ((t.r >> 5) / wpt) * wpt;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      float t1 = 0.f, t2 = 0.f;
+      for (int w = 0; w < wpt; ++w) {
+        const float2 p = gn_part[(w0 + w) * NCH + ch];
+        t1 += p.x;
+        t2 += p.y;
+      }
+      s1[ch] = t1;
+      s2[ch] = t2;
+    }
+  } else {
+    // generic T (e.g. 48, 24, 12): per-row partials through shared memory; thread et sums (sample et / NCH, chunk et % NCH)
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) gn_part[t.r * NCH + ch] = make_float2(s1[ch], s2[ch]);
+    named_bar_sync(bar_id, 128);
+    {
+      const int smp = et / NCH, ch = et % NCH;
+      const int nsamp = a.rows_valid / T;
+      if (smp < nsamp) {
+        float t1 = 0.f, t2 = 0.f;
+        const int r0 = smp * T;
+        for (int i = 0; i < T; ++i) {
+          const float2 p = gn_part[(r0 + i) * NCH + ch];
+          t1 += p.x;
+          t2 += p.y;
+        }
+        gn_stat[smp * NCH + ch] = make_float2(t1, t2);
+      }
+    }
+    named_bar_sync(bar_id, 128);
+    const int smp = t.valid ? (t.r / T) : 0;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const float2 p = gn_stat[smp * NCH + ch];
+      s1[ch] = p.x;
+      s2[ch] = p.y;
+    }
+  }
+  if (a.gn_gs_log2 == 6) {  // 64-channel groups: merge chunk pairs
+#pragma unroll
+    for (int ch = 0; ch < NCH; ch += 2) {
+      const float p1 = s1[ch] + s1[ch + 1], p2 = s2[ch] + s2[ch + 1];
+      s1[ch] = s1[ch + 1] = p1;
+      s2[ch] = s2[ch + 1] = p2;
+    }
+  }
+  float mean[NCH], rstd[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    mean[ch] = s1[ch] / cnt;
+    rstd[ch] = rsqrtf(fmaxf(s2[ch] / cnt - mean[ch] * mean[ch], 0.f) + a.gn_eps);
+  }
+
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    uint32_t v[32];
+    tmem_ld32(t.taddr + ch * 32, v);
+    tmem_ld_wait();
+    if (t.valid) {
+#pragma unroll
+      for (int j8 = 0; j8 < 32; j8 += 8) {
+        const int cc = ch * 32 + j8;
+        float sc[8], sh[8], rr[8], rl[8];
+        if (filmp) {
+          load_res8(filmp + cc, sc);
+          load_res8(filmp + a.film_C + cc, sh);
+        }
+        if (resp) {
+          load_res8(resp + cc, rr);
+          if (a.res_plane > 0) load_res8(resp + a.res_plane + cc, rl);
+        }
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float x = __uint_as_float(v[j8 + j]) + colv[cc + j];
+          x = (x - mean[ch]) * rstd[ch] * colv[BN + cc + j] + colv[2 * BN + cc + j];
+          y[j] = PRECISE ? mish_precise(x) : mish_f(x);
+        }
+        if (filmp) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[j] = (sc[j] + colv[3 * BN + cc + j]) * y[j] + (sh[j] + colv[4 * BN + cc + j]);
+        }
+        if (resp) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[j] += rr[j];
+          if (a.res_plane > 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] += rl[j];
+          }
+        }
+        store_split8<TOut>(outp + cc, a.out_plane, y);
+      }
+    }
+  }
+}
+
 template <typename TIn, int BN, int MODE, typename TOut, int STAGES, bool PRECISE>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_constant__ GemmArgs a) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs a) {
   constexpr int KE = InTraits<TIn>::KE;
   constexpr int B_STAGE_BYTES = BN * 128;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 256 ? 256 : 512);  // power of two
   constexpr uint32_t IDESC = umma_idesc(InTraits<TIn>::FMT, BN);
-  static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN");
-  static_assert(MODE != EPI_GN || BN == 128, "GN epilogue assumes a 128-column tile");
+  static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 192 || BN == 256, "BN");
+  static_assert(MODE != EPI_GN || BN == 128 || BN == 256, "GN epilogue: whole groups per tile");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -136,16 +399,13 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
   uint8_t* sB = smem + STAGES * GEMM_A_STAGE_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
   uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  float* colv = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);  // [5][BN]
-  float2* gn_part = reinterpret_cast<float2*>(colv + 5 * BN);                       // [128][4]
-  float2* gn_stat = gn_part + 128 * 4;                                              // [32][4]
+  uint64_t* acc_full = empty + STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x, m_tile = blockIdx.y, g = blockIdx.z;
   const int nk = a.passes * a.taps * a.cblocks;
-  const int n0 = n_tile * BN;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.tmA);
@@ -157,7 +417,10 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
         mbar_init(&full[s], 1);
         mbar_init(&empty[s], 1);
       }
-      mbar_init(tmem_full, 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&acc_full[s], 1);
+        mbar_init(&acc_empty[s], 128);
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -173,250 +436,108 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       const int per_pass = a.taps * a.cblocks;
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        const int pass = i / per_pass;
-        const int j = i - pass * per_pass;
-        const int tp = j / a.cblocks;
-        const int cb = j - tp * a.cblocks;
-        const int pa = (pass == 1) ? a.a_plane : 0;
-        const int pb = (pass == 2) ? a.b_plane : 0;
-        mbar_arrive_expect_tx(&full[s], a.a_box_bytes + B_STAGE_BYTES);
-        tma_load_5d(sA + s * GEMM_A_STAGE_BYTES, &a.tmA, &full[s], a.a_c0 + pa + cb * KE, a.tap_p[tp],
-                    m_tile * a.m_t_step + a.tap_t[tp], m_tile * a.m_b_step, g * a.a_g_mul);
-        tma_load_2d(sB + s * B_STAGE_BYTES, &a.tmB, &full[s], pb + j * KE, g * a.n_pad + n0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % a.n_tiles;
+        const int rest = tile / a.n_tiles;
+        const int m_tile = rest % a.m_tiles;
+        const int g = rest / a.m_tiles;
+        const int n0 = n_tile * BN;
+        for (int i = 0; i < nk; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          const int pass = i / per_pass;
+          const int j = i - pass * per_pass;
+          const int tp = j / a.cblocks;
+          const int cb = j - tp * a.cblocks;
+          const int pa = (pass == 1) ? a.a_plane : 0;
+          const int pb = (pass == 2) ? a.b_plane : 0;
+          mbar_arrive_expect_tx(&full[s], a.a_box_bytes + B_STAGE_BYTES);
+          tma_load_5d(sA + s * GEMM_A_STAGE_BYTES, &a.tmA, &full[s], a.a_c0 + pa + cb * KE, a.tap_p[tp],
+                      m_tile * a.m_t_step + a.tap_t[tp], m_tile * a.m_b_step, g * a.a_g_mul);
+          tma_load_2d(sB + s * B_STAGE_BYTES, &a.tmB, &full[s], pb + j * KE, g * a.n_pad + n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ UMMA issuer ------------------------------
     if (lane == 0) {
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&full[s], ph);
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t acc = lt & 1;
+        mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint64_t adesc = umma_smem_desc_sw128(smem_u32(sA + s * GEMM_A_STAGE_BYTES));
-        const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sB + s * B_STAGE_BYTES));
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+        for (int i = 0; i < nk; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint64_t adesc = umma_smem_desc_sw128(smem_u32(sA + s * GEMM_A_STAGE_BYTES));
+          const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sB + s * B_STAGE_BYTES));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 4 x (32 bytes of K) per 128-byte swizzle row
-          if constexpr (sizeof(TIn) == 2)
-            umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, IDESC, (i | k) != 0);
-          else
-            umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, IDESC, (i | k) != 0);
+          for (int k = 0; k < 4; ++k) {  // 4 x (32 bytes of K) per 128-byte swizzle row
+            if constexpr (sizeof(TIn) == 2)
+              umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (i | k) != 0);
+            else
+              umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (i | k) != 0);
+          }
+          umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
         }
-        umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+        umma_commit(&acc_full[acc]);
       }
-      umma_commit(tmem_full);
     }
   } else {
-    // ------------------------------ epilogue ------------------------------
-    const int et = threadIdx.x - 64;  // 0..127
-    const int quarter = warp & 3;     // TMEM lane quarter this warp may access
-    const int r = quarter * 32 + lane;
-    // stage per-column vectors while the main loop runs
-    {
-      const long long gcol = (long long)g * a.n_pad + n0;
-      for (int c = et; c < BN; c += 128) {
-        colv[c] = a.bias ? a.bias[gcol + c] : 0.f;
-        if (MODE == EPI_LINEAR) {
-          colv[BN + c] = (a.colscale && (n0 + c) < a.N) ? a.colscale[n0 + c] : 1.f;
-        } else {
-          colv[BN + c] = a.gn_gamma[gcol + c];
-          colv[2 * BN + c] = a.gn_beta[gcol + c];
-          const bool f = a.film_t != nullptr;
-          const long long fo = (long long)g * a.film_tg + a.film_off + n0 + c;
-          colv[3 * BN + c] = f ? a.film_t[fo] : 0.f;
-          colv[4 * BN + c] = f ? a.film_t[fo + a.film_C] : 0.f;
-        }
-      }
-    }
-    named_bar_sync(1, 128);
-
-    const long long grow = (long long)m_tile * a.rows_valid + r;
-    const bool valid = (r < a.rows_valid) && (grow < a.M_total);
-    const int q = (int)(grow / a.row_div);
-    const int rem = (int)(grow - (long long)q * a.row_div);
-    TOut* outp = reinterpret_cast<TOut*>(a.out) + (long long)g * a.out_g +
-                 ((long long)q * a.out_q + (long long)rem * a.out_r + a.out_off) * a.ldc + n0;
-    const long long res_row = (long long)q * a.res_q + (long long)rem * a.res_r + a.res_off;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-
-    if constexpr (MODE == EPI_LINEAR) {
-      const float* resp =
-          a.res ? reinterpret_cast<const float*>(a.res) + (long long)g * a.res_g + res_row * a.ldres + n0 : nullptr;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c, v);
-        tmem_ld_wait();
-        if (valid) {
-#pragma unroll
-          for (int j8 = 0; j8 < 32; j8 += 8) {
-            const int cc = c + j8;
-            if (n0 + cc >= a.N) break;
-            float y[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float x = __uint_as_float(v[j8 + j]) + colv[cc + j];
-              if (a.act == ACT_GELU) x = gelu_erf(x);
-              else if (a.act == ACT_MISH) x = PRECISE ? mish_precise(x) : mish_f(x);
-              y[j] = x * colv[BN + cc + j];
-            }
-            if (a.vec && n0 + cc + 8 <= a.N) {
-              if (resp) {
-                float rr[8];
-                load_res8(resp + cc, rr);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) y[j] += rr[j];
-              }
-              if constexpr (sizeof(TOut) == 4) {
-                if (a.out_plane > 0) {
-                  float hi[8], lo[8];
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    hi[j] = tf32_hi(y[j]);
-                    lo[j] = y[j] - hi[j];
-                  }
-                  store_chunk8<TOut>(outp + cc, hi);
-                  store_chunk8<TOut>(outp + a.out_plane + cc, lo);
-                } else {
-                  store_chunk8<TOut>(outp + cc, y);
-                }
-              } else {
-                store_chunk8<TOut>(outp + cc, y);
-              }
-            } else {  // ragged last columns (N not a multiple of 8): scalar
-              for (int j = 0; j < 8 && n0 + cc + j < a.N; ++j) {
-                float yy = y[j] + (resp ? resp[cc + j] : 0.f);
-                if constexpr (sizeof(TOut) == 4) {
-                  if (a.out_plane > 0) {
-                    const float hi = tf32_hi(yy);
-                    outp[cc + j] = hi;
-                    outp[a.out_plane + cc + j] = yy - hi;
-                  } else {
-                    outp[cc + j] = yy;
-                  }
-                } else {
-                  outp[cc + j] = __float2bfloat16(yy);
-                }
-              }
-            }
-          }
-        }
-      }
-    } else {
-      // ---------------- GroupNorm(8) + Mish + FiLM | residual ----------------
-      // Tile = all T rows of `rows_valid / gn_rows` samples x 128 channels = whole groups, so the
-      // statistics are tile-local.  Pass 1: per-row partial sums per 32-column chunk.
-      float s1[4], s2[4];
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(taddr + ch * 32, v);
-        tmem_ld_wait();
-        float a1 = 0.f, a2 = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]) + colv[ch * 32 + j];
-          a1 += x;
-          a2 = fmaf(x, x, a2);
-        }
-        s1[ch] = valid ? a1 : 0.f;
-        s2[ch] = valid ? a2 : 0.f;
-      }
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) gn_part[r * 4 + ch] = make_float2(s1[ch], s2[ch]);
-      named_bar_sync(1, 128);
+    // ------------------------------ epilogue warpgroups ------------------------------
+    const int wg = (warp - 2) >> 2;               // 0 / 1  <->  accumulator 0 / 1
+    const int et = (threadIdx.x - 64) & 127;      // thread index inside the warpgroup
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int bar_id = 1 + wg;
+    float* colv = scratch + wg * GEMM_WG_SCRATCH_FLOATS(BN);          // [5][BN]
+    float2* gn_part = reinterpret_cast<float2*>(colv + 5 * BN);       // [128][max(BN/32, 4)]
+    float2* gn_stat = gn_part + 128 * (BN / 32 > 4 ? BN / 32 : 4);    // [32][max(BN/32, 4)]
+    EpiTile t;
+    t.r = quarter * 32 + lane;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
+      if ((lt & 1) != (uint32_t)wg) continue;
+      const int n_tile = tile % a.n_tiles;
+      const int rest = tile / a.n_tiles;
+      const int m_tile = rest % a.m_tiles;
+      t.g = rest / a.m_tiles;
+      t.n0 = n_tile * BN;
+      // stage the per-column vectors of this tile (previous tile's readers are done: barrier first)
+      named_bar_sync(bar_id, 128);
       {
-        // thread et -> (sample et/4, chunk et%4); chunks are merged pairwise when a group spans 64 channels
-        const int smp = et >> 2, ch = et & 3;
-        const int nsamp = a.rows_valid / a.gn_rows;
-        float t1 = 0.f, t2 = 0.f;
-        if (smp < nsamp) {
-          const int r0 = smp * a.gn_rows;
-          for (int t = 0; t < a.gn_rows; ++t) {
-            float2 p = gn_part[(r0 + t) * 4 + ch];
-            t1 += p.x;
-            t2 += p.y;
-          }
-        }
-        if (a.gn_gs_log2 == 6) {
-          t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
-          t2 += __shfl_xor_sync(0xffffffffu, t2, 1);
-        }
-        if (smp < nsamp && smp < 32) {
-          const float cnt = (float)(a.gn_rows << a.gn_gs_log2);
-          const float mean = t1 / cnt;
-          const float var = fmaxf(t2 / cnt - mean * mean, 0.f);
-          gn_stat[smp * 4 + ch] = make_float2(mean, rsqrtf(var + a.gn_eps));
-        }
-      }
-      named_bar_sync(1, 128);
-      const int smp = valid ? (r / a.gn_rows) : 0;
-      const float* filmp = a.film_c ? a.film_c + (long long)g * a.film_g + (long long)q * a.film_ld + a.film_off + n0
-                                    : nullptr;
-      const TOut* resp =
-          a.res ? reinterpret_cast<const TOut*>(a.res) + (long long)g * a.res_g + res_row * a.ldres + n0 : nullptr;
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(taddr + ch * 32, v);
-        tmem_ld_wait();
-        if (valid) {
-          const float2 st = gn_stat[smp * 4 + ch];
-#pragma unroll
-          for (int j8 = 0; j8 < 32; j8 += 8) {
-            const int cc = ch * 32 + j8;
-            float y[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float x = __uint_as_float(v[j8 + j]) + colv[cc + j];
-              x = (x - st.x) * st.y * colv[BN + cc + j] + colv[2 * BN + cc + j];
-              y[j] = PRECISE ? mish_precise(x) : mish_f(x);
-            }
-            if (filmp) {
-              float sc[8], sh[8];
-              load_res8(filmp + cc, sc);
-              load_res8(filmp + a.film_C + cc, sh);
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                y[j] = (sc[j] + colv[3 * BN + cc + j]) * y[j] + (sh[j] + colv[4 * BN + cc + j]);
-            }
-            if (resp) {
-              float rr[8];
-              load_res8(resp + cc, rr);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) y[j] += rr[j];
-              if (a.res_plane > 0) {
-                load_res8(resp + a.res_plane + cc, rr);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) y[j] += rr[j];
-              }
-            }
-            if constexpr (sizeof(TOut) == 4) {
-              if (a.out_plane > 0) {
-                float hi[8], lo[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  hi[j] = tf32_hi(y[j]);
-                  lo[j] = y[j] - hi[j];
-                }
-                store_chunk8<TOut>(outp + cc, hi);
-                store_chunk8<TOut>(outp + a.out_plane + cc, lo);
-              } else {
-                store_chunk8<TOut>(outp + cc, y);
-              }
-            } else {
-              store_chunk8<TOut>(outp + cc, y);
-            }
+        const long long gcol = (long long)t.g * a.n_pad + t.n0;
+        for (int c = et; c < BN; c += 128) {
+          colv[c] = a.bias ? a.bias[gcol + c] : 0.f;
+          if (MODE == EPI_LINEAR) {
+            colv[BN + c] = (a.colscale && (t.n0 + c) < a.N) ? a.colscale[t.n0 + c] : 1.f;
+          } else {
+            colv[BN + c] = a.gn_gamma[gcol + c];
+            colv[2 * BN + c] = a.gn_beta[gcol + c];
+            const bool f = a.film_t != nullptr;
+            const long long fo = (long long)t.g * a.film_tg + a.film_off + t.n0 + c;
+            colv[3 * BN + c] = f ? a.film_t[fo] : 0.f;
+            colv[4 * BN + c] = f ? a.film_t[fo + a.film_C] : 0.f;
           }
         }
       }
+      named_bar_sync(bar_id, 128);
+      t.grow = (long long)m_tile * a.rows_valid + t.r;
+      t.valid = (t.r < a.rows_valid) && (t.grow < a.M_total);
+      t.q = (int)(t.grow / a.row_div);
+      t.rem = (int)(t.grow - (long long)t.q * a.row_div);
+      t.taddr = tmem_base + wg * ACC_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
+      const uint32_t parity = (lt >> 1) & 1;
+      if constexpr (MODE == EPI_LINEAR)
+        epilogue_linear<BN, TOut, PRECISE>(a, t, colv, &acc_full[wg], parity);
+      else
+        epilogue_gn<BN, TOut, PRECISE>(a, t, colv, gn_part, gn_stat, et, bar_id, &acc_full[wg], parity);
+      tc_fence_before();
+      mbar_arrive(&acc_empty[wg]);
     }
   }
 

@@ -126,16 +126,26 @@ GemmVariant make_variant() {
 
 GemmVariant* gemm_variant(int in_dtype, int bn, int epi, int out_dtype) {
   using bf = __nv_bfloat16;
-  static GemmVariant v_b_128_l_b = make_variant<bf, 128, vt::EPI_LINEAR, bf, 3>();
-  static GemmVariant v_b_128_l_f = make_variant<bf, 128, vt::EPI_LINEAR, float, 3>();
-  static GemmVariant v_b_32_l_b = make_variant<bf, 32, vt::EPI_LINEAR, bf, 4>();
-  static GemmVariant v_b_32_l_f = make_variant<bf, 32, vt::EPI_LINEAR, float, 4>();
-  static GemmVariant v_b_128_g_b = make_variant<bf, 128, vt::EPI_GN, bf, 3>();
-  static GemmVariant v_f_128_l_f = make_variant<float, 128, vt::EPI_LINEAR, float, 3>();
-  static GemmVariant v_f_32_l_f = make_variant<float, 32, vt::EPI_LINEAR, float, 4>();
-  static GemmVariant v_f_128_g_f = make_variant<float, 128, vt::EPI_GN, float, 3>();
+  static GemmVariant v_b_256_l_b = make_variant<bf, 256, vt::EPI_LINEAR, bf, 4>();
+  static GemmVariant v_b_256_l_f = make_variant<bf, 256, vt::EPI_LINEAR, float, 4>();
+  static GemmVariant v_b_192_l_b = make_variant<bf, 192, vt::EPI_LINEAR, bf, 5>();
+  static GemmVariant v_b_192_l_f = make_variant<bf, 192, vt::EPI_LINEAR, float, 5>();
+  static GemmVariant v_b_128_l_b = make_variant<bf, 128, vt::EPI_LINEAR, bf, 5>();
+  static GemmVariant v_b_128_l_f = make_variant<bf, 128, vt::EPI_LINEAR, float, 5>();
+  static GemmVariant v_b_32_l_b = make_variant<bf, 32, vt::EPI_LINEAR, bf, 6>();
+  static GemmVariant v_b_32_l_f = make_variant<bf, 32, vt::EPI_LINEAR, float, 6>();
+  static GemmVariant v_b_256_g_b = make_variant<bf, 256, vt::EPI_GN, bf, 4>();
+  static GemmVariant v_b_128_g_b = make_variant<bf, 128, vt::EPI_GN, bf, 5>();
+  static GemmVariant v_f_128_l_f = make_variant<float, 128, vt::EPI_LINEAR, float, 5>();
+  static GemmVariant v_f_32_l_f = make_variant<float, 32, vt::EPI_LINEAR, float, 6>();
+  static GemmVariant v_f_128_g_f = make_variant<float, 128, vt::EPI_GN, float, 5>();
   if (in_dtype == VT_BF16) {
-    if (epi == VT_EPI_GN) return (bn == 128 && out_dtype == VT_BF16) ? &v_b_128_g_b : nullptr;
+    if (epi == VT_EPI_GN) {
+      if (out_dtype != VT_BF16) return nullptr;
+      return bn == 256 ? &v_b_256_g_b : (bn == 128 ? &v_b_128_g_b : nullptr);
+    }
+    if (bn == 256) return out_dtype == VT_BF16 ? &v_b_256_l_b : &v_b_256_l_f;
+    if (bn == 192) return out_dtype == VT_BF16 ? &v_b_192_l_b : &v_b_192_l_f;
     if (bn == 128) return out_dtype == VT_BF16 ? &v_b_128_l_b : &v_b_128_l_f;
     if (bn == 32) return out_dtype == VT_BF16 ? &v_b_32_l_b : &v_b_32_l_f;
     return nullptr;
@@ -145,6 +155,16 @@ GemmVariant* gemm_variant(int in_dtype, int bn, int epi, int out_dtype) {
   if (bn == 128) return &v_f_128_l_f;
   if (bn == 32) return &v_f_32_l_f;
   return nullptr;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
 }
 
 struct GemmOp : Op {
@@ -176,8 +196,9 @@ int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
   VT_REQUIRE(d.t_box >= 1 && d.b_box >= 1 && d.t_box * d.b_box <= 128, "gemm: tile box %dx%d", d.t_box, d.b_box);
   VT_REQUIRE(d.G >= 1 && (d.a_G == 1 || d.a_G == d.G), "gemm: G=%d a_G=%d", d.G, d.a_G);
   VT_REQUIRE(d.M >= 1 && d.N >= 1 && d.N <= d.n_pad, "gemm: M=%d N=%d n_pad=%d", d.M, d.N, d.n_pad);
-  VT_REQUIRE(d.bn == 32 || d.bn == 128, "gemm: bn=%d", d.bn);
-  VT_REQUIRE(d.n_pad % d.bn == 0, "gemm: n_pad=%d must be a multiple of bn=%d", d.n_pad, d.bn);
+  VT_REQUIRE(d.bn == 32 || d.bn == 128 || d.bn == 192 || d.bn == 256, "gemm: bn=%d", d.bn);
+  // tiles must not straddle groups; with one group the last tile may be ragged (TMA zero-fills, columns >= N are masked)
+  VT_REQUIRE(d.G == 1 || d.n_pad % d.bn == 0, "gemm: n_pad=%d must be a multiple of bn=%d when G > 1", d.n_pad, d.bn);
   VT_REQUIRE(d.w_ld >= d.taps * d.kc, "gemm: w_ld=%d < taps*kc=%d", d.w_ld, d.taps * d.kc);
   VT_REQUIRE(d.a_P >= 1 && d.a_T >= 1 && d.a_B >= 1 && d.a_C >= 1, "gemm: bad A extents");
   VT_REQUIRE(d.row_div >= 1, "gemm: row_div=%d", d.row_div);
@@ -259,11 +280,11 @@ int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
   if (d.epi == VT_EPI_GN) {
     VT_REQUIRE(d.gn_gamma && d.gn_beta, "gemm: GroupNorm epilogue needs gamma/beta");
     VT_REQUIRE(d.gn_group_ch == 32 || d.gn_group_ch == 64, "gemm: gn_group_ch=%d", d.gn_group_ch);
-    VT_REQUIRE(d.N % 128 == 0, "gemm: GroupNorm epilogue needs N %% 128 == 0 (N=%d)", d.N);
+    VT_REQUIRE(d.N % d.bn == 0, "gemm: GroupNorm epilogue needs N %% bn == 0 (N=%d, bn=%d)", d.N, d.bn);
     VT_REQUIRE(d.t_box == t_out, "gemm: GroupNorm epilogue needs whole samples per tile (t_box=%d, positions=%d)", d.t_box, t_out);
     VT_REQUIRE(d.row_div == d.t_box, "gemm: GroupNorm epilogue needs row_div == t_box");
     VT_REQUIRE(vec, "gemm: GroupNorm epilogue needs 16-byte aligned rows");
-    VT_REQUIRE(d.b_box <= 32, "gemm: GroupNorm epilogue supports at most 32 samples per tile");
+    VT_REQUIRE(d.b_box <= (d.bn == 256 ? 16 : 32), "gemm: GroupNorm epilogue supports at most %d samples per tile", d.bn == 256 ? 16 : 32);
     if (d.film_c) VT_REQUIRE(d.film_ld % 4 == 0 && d.film_off % 4 == 0 && d.film_C % 4 == 0 && d.film_g % 4 == 0 && aligned16(d.film_c),
                              "gemm: FiLM table must be 16-byte aligned");
     a.gn_gamma = d.gn_gamma;
@@ -281,8 +302,13 @@ int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
   }
   const int m_tiles = (d.M + rows_valid - 1) / rows_valid;
   const int n_tiles = (d.N + d.bn - 1) / d.bn;
-  VT_REQUIRE(m_tiles <= 65535 && d.G <= 65535, "gemm: grid too large (m_tiles=%d)", m_tiles);
-  op->grid = dim3((unsigned)n_tiles, (unsigned)m_tiles, (unsigned)d.G);
+  const long long total = (long long)m_tiles * n_tiles * d.G;
+  VT_REQUIRE(total < (1ll << 31), "gemm: too many tiles");
+  a.n_tiles = n_tiles;
+  a.m_tiles = m_tiles;
+  a.total_tiles = (int)total;
+  const int sms = sm_count();
+  op->grid = dim3((unsigned)(total < sms ? total : sms), 1u, 1u);   // persistent: one CTA per SM
   return VT_OK;
 }
 
@@ -359,8 +385,8 @@ struct ImgStatsOp : Op {
 struct PatchifyOp : Op {
   vt_patchify_desc d;
   int launch(cudaStream_t s) override {
-    const long long total = (long long)d.images * (d.H / d.patch) * (d.W / d.patch) * d.out_cols;
-    const int blocks = grid_for(total, 256 * 4);
+    const long long total = (long long)d.images * (d.H / d.patch) * (d.W / d.patch) * (d.out_cols / 8);
+    const int blocks = grid_for(total, 256);
     if (d.dtype == VT_U8)
       vt::patchify_kernel<uint8_t><<<blocks, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(d.img), d.layout, d.images, d.H,
                                                           d.W, d.patch, d.flags, d.out, d.out_dtype, d.out_cols, d.out_ld, d.out_plane);
@@ -560,6 +586,7 @@ VT_SIMPLE_ADD(vt_program_add_imgstats, ImgStatsOp, vt_imgstats_desc,
 VT_SIMPLE_ADD(vt_program_add_patchify, PatchifyOp, vt_patchify_desc,
               VT_REQUIRE(d->img && d->out && d->flags && d->images >= 1 && d->patch >= 1 && d->H >= d->patch &&
                              d->W >= d->patch && d->out_cols >= 3 * d->patch * d->patch && d->out_ld >= d->out_cols &&
+                             d->out_cols % 8 == 0 && d->out_ld % 8 == 0 && aligned16(d->out) &&
                              (d->dtype == VT_U8 || d->dtype == VT_F32),
                          "patchify: bad descriptor"))
 VT_SIMPLE_ADD(vt_program_add_cls, ClsOp, vt_cls_desc, VT_REQUIRE(d->cls && d->pos && d->h, "cls: bad descriptor"))

@@ -13,7 +13,7 @@ from typing import Callable, Dict, List, Optional, Sequence
 import torch
 
 from . import native as nv
-from .plan import Plan, gemm_desc, linear_desc, ptr, round_up
+from .plan import Plan, gemm_desc, linear_desc, pick_bn, ptr, round_up
 from .unet import Mode
 
 SD = Dict[str, torch.Tensor]
@@ -141,7 +141,7 @@ class DinoProgram:
         rows = images * npatch
         plan.add(gemm_desc(
             a=ptr(col), in_dtype=m.dt, a_C=m.ld(W.kp_pad), a_T=rows, a_B=1, a_ld=m.ld(W.kp_pad), kc=W.kp_pad,
-            t_box=min(128, rows), b_box=1, w=ptr(T_["patch.w"]), n_pad=D, w_ld=T_["patch.w"].shape[-1], M=rows, N=D, bn=128,
+            t_box=min(128, rows), b_box=1, w=ptr(T_["patch.w"]), n_pad=D, w_ld=T_["patch.w"].shape[-1], M=rows, N=D, bn=pick_bn(D, D, m.dt),
             out=ptr(h), out_dtype=nv.VT_F32, ldc=D, row_div=npatch, out_q=N, out_r=1, out_off=1, bias=ptr(T_["patch.b"]),
             res=ptr(pos), ldres=D, res_q=0, res_r=1, res_off=1, passes=m.passes, a_plane=m.plane(W.kp_pad),
             w_plane=W.kp_pad if m.precise else 0), f"{tag}.patch_embed+pos")

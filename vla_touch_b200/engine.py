@@ -84,8 +84,8 @@ def build_mlp(plan: Plan, W: MlpWeights, x_op: torch.Tensor, rows: int, out: tor
             ldc, oplane = m.ld(n_pad), m.plane(n_pad)
         plan.add(linear_desc(a=cur, rows=rows, k=k_pad, a_ld=m.ld(k_pad), w=W.w[i], n=n if last else n_pad, n_pad=n_pad,
                              w_ld=W.w[i].shape[-1], out=dst, ldc=ldc, bias=W.b[i], act=acts[i], out_plane=oplane,
-                             passes=m.passes, a_plane=m.plane(k_pad), w_plane=k_pad if m.precise else 0,
-                             bn=128 if n_pad % 128 == 0 else 32), f"{tag}.linear{i}")
+                             passes=m.passes, a_plane=m.plane(k_pad), w_plane=k_pad if m.precise else 0),
+                 f"{tag}.linear{i}")
         cur, cur_k = dst, n_pad
 
 

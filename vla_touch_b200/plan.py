@@ -117,6 +117,19 @@ def gemm_desc(*, a, in_dtype, a_C, a_T, a_B=1, a_P=1, a_G=1, a_ld, a_sB=0, a_sG=
     return d
 
 
+def pick_bn(n: int, n_pad: int, in_dtype: int, G: int = 1) -> int:
+    """Output-tile width.  Wider tiles re-use the A tile for more columns (the kernel is bound by L2 -> SM operand
+    traffic at 128 x 128); 192 divides the ViT widths 384 / 1152 that 256 does not."""
+    if n <= 32:
+        return 32
+    if in_dtype != nv.VT_BF16:
+        return 128
+    for bn in (256, 192):
+        if n % bn == 0 and (G == 1 or n_pad % bn == 0):
+            return bn
+    return 128
+
+
 def linear_desc(*, a: torch.Tensor, a_off: int = 0, rows: int, k: int, a_ld: int, w: torch.Tensor, w_off: int = 0,
                 n: int, n_pad: int, w_ld: int, out: torch.Tensor, out_off: int = 0, ldc: int, bias=None, bias_off: int = 0,
                 act=nv.ACT_NONE, colscale=None, res=None, res_off_elems: int = 0, ldres: int = 0, G: int = 1, a_G: int = 1,
@@ -128,7 +141,7 @@ def linear_desc(*, a: torch.Tensor, a_off: int = 0, rows: int, k: int, a_ld: int
     (default a_ld) bounds what TMA may read, anything beyond reads as zero."""
     in_dtype = VT_DT[a.dtype]
     if bn is None:
-        bn = 128 if n > 32 else 32
+        bn = pick_bn(n, n_pad, in_dtype, G)
     return gemm_desc(
         a=ptr(a, a_off), in_dtype=in_dtype, a_C=a_C if a_C is not None else a_ld, a_T=rows, a_B=1, a_ld=a_ld,
         a_sB=a_ld * rows, a_G=a_G, a_sG=a_sG, kc=k, t_box=min(128, rows), b_box=1, w=ptr(w, w_off), n_pad=n_pad, w_ld=w_ld, G=G,
