@@ -2,14 +2,15 @@
 // qkv rows written by the QKV GEMM.
 //
 // attn_tc_kernel (bf16): one CTA = one (image, head, 128-query tile).  Flash-style loop over 128-key blocks:
-//   warp 4  TMA producer : Q tile once, then K_j / V_j tiles through a 3-slot ring (SWIZZLE_128B boxes of the
+//   warp 8  TMA producer : Q tile once, then K_j / V_j tiles through a 3-slot ring (SWIZZLE_128B boxes of the
 //                          same 2-D tensor map over qkv, different column coordinate)
-//   warp 5  UMMA issuer  : S = Q K_j^T (M128 x N<=128 x K64, accumulator in TMEM columns [0,128)), then
+//   warp 9  UMMA issuer  : S = Q K_j^T (M128 x N<=128 x K64, accumulator in TMEM columns [0,128)), then
 //                          O_j = P_j V_j (M128 x N64 x K<=128; P from shared memory, V as an MN-major operand)
 //                          into TMEM columns [128,192)
-//   warps 0-3 softmax    : one query row per thread; online max / sum in fp32, exp2 with the 1/sqrt(d) scale
-//                          folded in, P written to shared memory as bf16 in the 128B-swizzled K-major layout the
-//                          UMMA descriptor expects, running O kept in registers and rescaled per block.
+//   warps 0-7 softmax    : two threads per query row (64 key columns / 32 output channels each); online max / sum
+//                          in fp32, exp2 with the 1/sqrt(d) scale folded in, P written to shared memory as bf16 in
+//                          the 128B-swizzled K-major layout the UMMA descriptor expects, running O kept in
+//                          registers and rescaled per block.
 // 96 KB of shared memory and 256 TMEM columns per CTA -> two CTAs per SM overlap each other's softmax and MMA.
 //
 // attn_f32_kernel: fp32 CUDA-core variant used by the parity ("precise") mode only.
@@ -19,10 +20,11 @@
 
 namespace vt {
 
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;           // warps 0-7 softmax (two threads per query row), warp 8 TMA, warp 9 MMA
 constexpr int ATT_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
 constexpr int ATT_KV_SLOTS = 3;
-constexpr int ATT_SMEM_BYTES = 1024 + ATT_TILE_BYTES * (1 + ATT_KV_SLOTS + 2) + 256;
+constexpr int ATT_SMEM_BYTES = 1024 + ATT_TILE_BYTES * (1 + ATT_KV_SLOTS + 2) + 256 + 2 * 256 * 4;
+constexpr int ATT_TAIL_MAX = 16;           // a last query tile with <= this many rows goes to attn_tail_kernel
 
 struct AttnArgs {
   CUtensorMap tm;  // 2-D (3*D, images*tokens), box (64, 128), SWIZZLE_128B
@@ -32,7 +34,7 @@ struct AttnArgs {
   float scale_log2;  // log2(e) / sqrt(head_dim)
 };
 
-__global__ void __launch_bounds__(ATT_THREADS) attn_tc_kernel(const __grid_constant__ AttnArgs a) {
+__global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_constant__ AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -47,6 +49,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_tc_kernel(const __grid_const
   uint64_t* p_full = s_full + 1;
   uint64_t* o_full = p_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][256] row max / row sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
@@ -54,7 +57,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_tc_kernel(const __grid_const
   const int nb = (N + 127) >> 7;
   const int row0 = img * N;
 
-  if (warp == 5) {
+  if (warp == 9) {
     if (lane == 0) {
       mbar_init(q_full, 1);
       for (int i = 0; i < ATT_KV_SLOTS; ++i) {
@@ -62,7 +65,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_tc_kernel(const __grid_const
         mbar_init(&kv_empty[i], 1);
       }
       mbar_init(s_full, 1);
-      mbar_init(p_full, 128);
+      mbar_init(p_full, 256);
       mbar_init(o_full, 1);
       fence_barrier_init();
     }
@@ -70,14 +73,14 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_tc_kernel(const __grid_const
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
-  if (warp == 4 && lane == 0) tma_prefetch_desc(&a.tm);
+  if (warp == 8 && lane == 0) tma_prefetch_desc(&a.tm);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
       tma_load_2d(sQ, &a.tm, q_full, head * 64, row0 + qt * 128);
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_tc_kernel(const __grid_const
         tma_load_2d(sKV + slot * ATT_TILE_BYTES, &a.tm, &kv_full[slot], col, row0 + (i >> 1) * 128);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       mbar_wait(q_full, 0);
       const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ));
@@ -132,61 +135,78 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_tc_kernel(const __grid_const
     }
   } else {
     // ------------------------------ softmax + output ------------------------------
-    const int r = threadIdx.x;  // tile row == TMEM lane
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    // Thread (r, half): row r = (warp & 3) * 32 + lane (its TMEM lane), key columns [half*64, half*64+64) of every
+    // 128-key block (= one 64-key chunk of P), output channels [half*32, half*32+32).
+    const int half = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float sl = a.scale_log2;
     float m = -INFINITY, l = 0.f;
-    float o[64];
+    float o[32];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
-    const uint32_t sP_row = smem_u32(sP) + r * 128;
+    for (int i = 0; i < 32; ++i) o[i] = 0.f;
+    const uint32_t sP_row = smem_u32(sP) + half * ATT_TILE_BYTES + r * 128;
     const int sw = r & 7;
+    float* my_x = xch + half * 128 + r;
+    const float* peer_x = xch + (half ^ 1) * 128 + r;
 
     for (int j = 0; j < nb; ++j) {
-      const int valid = min(128, N - j * 128);
-      const int nch = (valid + 31) >> 5;  // 32-column chunks holding valid keys
+      const int valid = min(128, N - j * 128) - half * 64;   // valid keys among this thread's 64 columns (may be <= 0)
       mbar_wait(s_full, j & 1);
       tc_fence_after();
+      // S row in four 16-column chunks, two TMEM loads in flight (register budget: 2 CTAs x 320 threads per SM)
+      const uint32_t s_addr = tmem_S + lane_off + half * 64;
+      uint32_t va[16], vb[16];
       float mx = -INFINITY;
-      for (int ch = 0; ch < nch; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + ch * 32, v);
-        tmem_ld_wait();
+      auto max16 = [&](const uint32_t(&v)[16], int c0) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = (ch * 32 + i < valid) ? __uint_as_float(v[i]) : -INFINITY;
-          mx = fmaxf(mx, s);
-        }
-      }
-      const float m_new = fmaxf(m, mx);
+        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, (c0 + i < valid) ? __uint_as_float(v[i]) : -INFINITY);
+      };
+      tmem_ld16(s_addr, va);
+      tmem_ld_wait();
+      tmem_ld16(s_addr + 16, vb);
+      max16(va, 0);
+      tmem_ld_wait();
+      tmem_ld16(s_addr + 32, va);
+      max16(vb, 16);
+      tmem_ld_wait();
+      tmem_ld16(s_addr + 48, vb);
+      max16(va, 32);
+      tmem_ld_wait();
+      max16(vb, 48);
+      my_x[(j & 1) * 256] = mx;
+      tmem_ld16(s_addr, va);                      // first chunk of the second pass, overlapped with the exchange
+      named_bar_sync(1, 256);
+      const float m_new = fmaxf(m, fmaxf(mx, peer_x[(j & 1) * 256]));
       const float alpha = exp2f((m - m_new) * sl);
       const float msc = m_new * sl;
       float rowsum = 0.f;
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t pk[16];
-        if (ch < nch) {
-          uint32_t v[32];
-          tmem_ld32(tmem_S + lane_off + ch * 32, v);
-          tmem_ld_wait();
+      auto exp16 = [&](const uint32_t(&v)[16], int c0) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = (ch * 32 + i < valid) ? exp2f(fmaf(__uint_as_float(v[i]), sl, -msc)) : 0.f;
-            const float p1 = (ch * 32 + i + 1 < valid) ? exp2f(fmaf(__uint_as_float(v[i + 1]), sl, -msc)) : 0.f;
+        for (int u = 0; u < 2; ++u) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = u * 8 + 2 * e;
+            const float p0 = (c0 + i < valid) ? exp2f(fmaf(__uint_as_float(v[i]), sl, -msc)) : 0.f;
+            const float p1 = (c0 + i + 1 < valid) ? exp2f(fmaf(__uint_as_float(v[i + 1]), sl, -msc)) : 0.f;
             rowsum += p0 + p1;
-            pk[i >> 1] = pack_bf16x2(p0, p1);
+            pk[e] = pack_bf16x2(p0, p1);
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          st_shared_v4(sP_row + ((((c0 >> 3) + u) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
         }
-        // 32 keys = four 16-byte units of this row, in 64-key chunk (ch >> 1), units (ch & 1) * 4 + u
-        const uint32_t base = sP_row + (ch >> 1) * ATT_TILE_BYTES;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int unit = (ch & 1) * 4 + u;
-          st_shared_v4(base + ((unit ^ sw) << 4), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-        }
-      }
+      };
+      tmem_ld_wait();
+      tmem_ld16(s_addr + 16, vb);
+      exp16(va, 0);
+      tmem_ld_wait();
+      tmem_ld16(s_addr + 32, va);
+      exp16(vb, 16);
+      tmem_ld_wait();
+      tmem_ld16(s_addr + 48, vb);
+      exp16(va, 32);
+      tmem_ld_wait();
+      exp16(vb, 48);
       l = l * alpha + rowsum;
       m = m_new;
       fence_proxy_async_smem();
@@ -194,21 +214,23 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_tc_kernel(const __grid_const
       mbar_arrive(p_full);
       mbar_wait(o_full, j & 1);
       tc_fence_after();
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        tmem_ld32(tmem_O + lane_off + h * 32, v);
+      {
+        uint32_t w[32];
+        tmem_ld32(tmem_O + lane_off + half * 32, w);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[h * 32 + i] = fmaf(o[h * 32 + i], alpha, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(w[i]));
       }
     }
+    // combine the two halves' row sums
+    my_x[0] = l;
+    named_bar_sync(1, 256);
+    const float inv = 1.0f / (l + peer_x[0]);
     const int qrow = qt * 128 + r;
     if (qrow < N) {
-      const float inv = 1.0f / l;
-      __nv_bfloat16* dst = a.ctx + (long long)(row0 + qrow) * a.ctx_ld + head * 64;
+      __nv_bfloat16* dst = a.ctx + (long long)(row0 + qrow) * a.ctx_ld + head * 64 + half * 32;
 #pragma unroll
-      for (int i = 0; i < 64; i += 8) {
+      for (int i = 0; i < 32; i += 8) {
         uint4 w;
         w.x = pack_bf16x2(o[i] * inv, o[i + 1] * inv);
         w.y = pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
@@ -221,7 +243,81 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_tc_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, 256);
+  if (warp == 9) tmem_dealloc(tmem_base, 256);
+}
+
+// Last query rows of an image when tokens % 128 <= ATT_TAIL_MAX (e.g. the 257th token at 224x224): one warp per
+// (image, head, row) on the CUDA cores instead of a 128-row tensor-core tile that would be >87% padding.
+constexpr int ATTT_WARPS = 8;
+__global__ void __launch_bounds__(ATTT_WARPS * 32) attn_tail_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                    __nv_bfloat16* __restrict__ ctx, int images, int tokens,
+                                                                    int heads, int D, long long ctx_ld, int first_row,
+                                                                    float scale_log2) {
+  extern __shared__ float sp[];  // [ATTT_WARPS][tokens]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tail = tokens - first_row;
+  const long long gw = (long long)blockIdx.x * ATTT_WARPS + warp;
+  const long long total = (long long)images * heads * tail;
+  if (gw >= total) return;
+  const int qi = first_row + (int)(gw % tail);
+  const int head = (int)((gw / tail) % heads);
+  const int img = (int)(gw / ((long long)tail * heads));
+  const long long ld = 3LL * D;
+  const __nv_bfloat16* base = qkv + (long long)img * tokens * ld;
+  float* p = sp + (long long)warp * tokens;
+  float qr[64];
+  {
+    const uint4* q4 = reinterpret_cast<const uint4*>(base + (long long)qi * ld + head * 64);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 t = q4[i];
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h2[e]);
+        qr[i * 8 + 2 * e] = f.x;
+        qr[i * 8 + 2 * e + 1] = f.y;
+      }
+    }
+  }
+  float mx = -INFINITY;
+  for (int k = lane; k < tokens; k += 32) {
+    const uint4* k4 = reinterpret_cast<const uint4*>(base + (long long)k * ld + D + head * 64);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 t = k4[i];
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h2[e]);
+        acc = fmaf(qr[i * 8 + 2 * e], f.x, acc);
+        acc = fmaf(qr[i * 8 + 2 * e + 1], f.y, acc);
+      }
+    }
+    acc *= scale_log2;
+    p[k] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int k = lane; k < tokens; k += 32) {
+    const float e = exp2f(p[k] - mx);
+    p[k] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  const float inv = 1.0f / sum;
+  float o0 = 0.f, o1 = 0.f;
+  const __nv_bfloat16* vb = base + 2 * D + head * 64 + 2 * lane;
+  for (int k = 0; k < tokens; ++k) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + (long long)k * ld));
+    const float pk = p[k];
+    o0 = fmaf(pk, f.x, o0);
+    o1 = fmaf(pk, f.y, o1);
+  }
+  *reinterpret_cast<uint32_t*>(ctx + ((long long)img * tokens + qi) * ctx_ld + head * 64 + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
 }
 
 // fp32 attention on the CUDA cores (parity mode): one warp per (image, head, query row).

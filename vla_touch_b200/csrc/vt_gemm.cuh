@@ -339,10 +339,16 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
     rstd[ch] = rsqrtf(fmaxf(s2[ch] / cnt - mean[ch] * mean[ch], 0.f) + a.gn_eps);
   }
 
-#pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) {
+#pragma unroll 1
+  for (int ch = 0; ch < NCH; ++ch) {   // rolled: a fully unrolled body (NCH x 4 copies) thrashes the instruction cache
     uint32_t v[32];
     tmem_ld32(t.taddr + ch * 32, v);
+    float mu = mean[0], rs = rstd[0];
+#pragma unroll
+    for (int k = 1; k < NCH; ++k) {
+      mu = (ch == k) ? mean[k] : mu;
+      rs = (ch == k) ? rstd[k] : rs;
+    }
     tmem_ld_wait();
     if (t.valid) {
 #pragma unroll
@@ -361,7 +367,7 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float x = __uint_as_float(v[j8 + j]) + colv[cc + j];
-          x = (x - mean[ch]) * rstd[ch] * colv[BN + cc + j] + colv[2 * BN + cc + j];
+          x = (x - mu) * rs * colv[BN + cc + j] + colv[2 * BN + cc + j];
           y[j] = PRECISE ? mish_precise(x) : mish_f(x);
         }
         if (filmp) {

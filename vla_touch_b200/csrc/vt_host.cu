@@ -317,15 +317,28 @@ struct AttnOp : Op {
   vt::AttnArgs args;
   vt_attn_desc d;
   dim3 grid;
+  int tail_first = -1;   // first query row handled by attn_tail_kernel, or -1
   static bool attr_set;
+  int launches() const override { return (d.in_dtype == VT_BF16 && tail_first >= 0 && grid.x > 0) ? 2 : 1; }
   int launch(cudaStream_t s) override {
     if (d.in_dtype == VT_BF16) {
       if (!attr_set) {
         VT_CUDA(cudaFuncSetAttribute(vt::attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vt::ATT_SMEM_BYTES));
         attr_set = true;
       }
-      vt::attn_tc_kernel<<<grid, vt::ATT_THREADS, vt::ATT_SMEM_BYTES, s>>>(args);
-      VT_LAUNCH_CHECK("attn_tc_kernel");
+      if (grid.x > 0) {
+        vt::attn_tc_kernel<<<grid, vt::ATT_THREADS, vt::ATT_SMEM_BYTES, s>>>(args);
+        VT_LAUNCH_CHECK("attn_tc_kernel");
+      }
+      if (tail_first >= 0) {
+        const long long warps = (long long)d.images * d.heads * (d.tokens - tail_first);
+        const int blocks = (int)((warps + vt::ATTT_WARPS - 1) / vt::ATTT_WARPS);
+        const size_t smem = (size_t)vt::ATTT_WARPS * d.tokens * sizeof(float);
+        vt::attn_tail_kernel<<<blocks, vt::ATTT_WARPS * 32, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(d.qkv),
+                                                                       args.ctx, d.images, d.tokens, d.heads, args.D,
+                                                                       args.ctx_ld, tail_first, args.scale_log2);
+        VT_LAUNCH_CHECK("attn_tail_kernel");
+      }
     } else {
       const long long warps = (long long)d.images * d.heads * d.tokens;
       const int blocks = (int)((warps + vt::ATTF_WARPS - 1) / vt::ATTF_WARPS);
@@ -554,7 +567,13 @@ int vt_program_add_attention(vt_program* p, const vt_attn_desc* d) {
     op->args.heads = d->heads;
     op->args.D = D;
     op->args.scale_log2 = 0.125f * 1.4426950408889634f;
-    op->grid = dim3((unsigned)((d->tokens + 127) / 128), (unsigned)d->heads, (unsigned)d->images);
+    int q_tiles = (d->tokens + 127) / 128;
+    const int rem = d->tokens % 128;
+    if (rem > 0 && rem <= vt::ATT_TAIL_MAX && (size_t)vt::ATTT_WARPS * d->tokens * 4 <= 48 * 1024) {
+      op->tail_first = d->tokens - rem;   // the short last tile runs on the CUDA cores
+      q_tiles -= 1;
+    }
+    op->grid = dim3((unsigned)q_tiles, (unsigned)d->heads, (unsigned)d->images);
     VT_REQUIRE(d->images <= 65535, "attention: images=%d exceeds the grid z limit", d->images);
   } else {
     VT_REQUIRE(d->in_dtype == VT_F32, "attention: in_dtype %d", d->in_dtype);
