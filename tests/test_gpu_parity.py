@@ -245,15 +245,16 @@ def test_kernels_match_the_descriptor_interpreter_op_by_op():
     """Every launch of a small U-Net program against the CPU interpretation of the same descriptor (isolated per op)."""
     import gpu_diff
     from vla_touch_b200.unet import UnetProgram
-    A, T, B = 10, 16, 3
-    sds = [U.net_sd(A, 21, "v_net"), U.net_sd(A, 21, "s_net")]
-    ups = []
-    for dev in ("cpu", DEV):
-        up = UnetProgram(sds, A, B, T, dev, precise=False)
-        up.x.copy_(syn.det_uniform("unet.x", (B, T, A), 22, -1.0, 1.0))
-        up.t.copy_(torch.tensor([0.3, 0.001, 0.999]))
-        up.cond.copy_(syn.det_normal("unet.cond", (B, 256), 22))
-        ups.append(up)
-    rows = gpu_diff.diff_plans(ups[0].plan, ups[1].plan, resync=True)
-    bad = [r for r in rows if not r[3] <= 2e-2 * max(r[4], 1e-6)]      # one bf16 ulp at the tensor scale is 2^-8
-    assert not bad, gpu_diff.format_rows(bad)
+    # (10,16,3): ragged tiles -> direct-store epilogue; (7,32,9): full 128-row tiles -> TMA-store epilogue, M edge clipped
+    for A, T, B in ((10, 16, 3), (7, 32, 9)):
+        sds = [U.net_sd(A, 21, "v_net"), U.net_sd(A, 21, "s_net")]
+        ups = []
+        for dev in ("cpu", DEV):
+            up = UnetProgram(sds, A, B, T, dev, precise=False)
+            up.x.copy_(syn.det_uniform("unet.x", (B, T, A), 22, -1.0, 1.0))
+            up.t.copy_(torch.linspace(0.001, 0.999, B))
+            up.cond.copy_(syn.det_normal("unet.cond", (B, 256), 22))
+            ups.append(up)
+        rows = gpu_diff.diff_plans(ups[0].plan, ups[1].plan, resync=True)
+        bad = [r for r in rows if not r[3] <= 2e-2 * max(r[4], 1e-6)]      # one bf16 ulp at the tensor scale is 2^-8
+        assert not bad, gpu_diff.format_rows(bad)

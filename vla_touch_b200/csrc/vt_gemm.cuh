@@ -31,6 +31,8 @@ enum : int { EPI_LINEAR = 0, EPI_GN = 1 };
 struct GemmArgs {
   CUtensorMap tmA;  // 5-D (C, P, T, B, G), box (KE, 1, Tbox, Bbox, 1), SWIZZLE_128B
   CUtensorMap tmB;  // 2-D (Ktot, G*n_pad), box (KE, BN), SWIZZLE_128B
+  CUtensorMap tmO;  // 3-D (N, M, G) over the output, box (128 B, 32 rows, 1), SWIZZLE_128B; valid when tma_out
+  int tma_out;      // 1: the epilogue stages 32-row x 128-byte boxes in shared memory and drains them with TMA stores
   // ---- tiles ----
   int n_tiles, m_tiles, total_tiles;  // tile id = (g * m_tiles + m_tile) * n_tiles + n_tile
   // ---- K loop: k-block i -> (pass, tap, cb) ----
@@ -90,12 +92,16 @@ struct InTraits<float> {
 };
 
 // per epilogue warpgroup: 5 column vectors, GroupNorm row partials [128][BN/32] and sample sums [32][BN/32] (float2)
-__host__ __device__ constexpr int GEMM_WG_SCRATCH_FLOATS(int BN) { return 5 * BN + (128 + 32) * (BN / 32 > 4 ? BN / 32 : 4) * 2; }
+__host__ __device__ constexpr int GEMM_WG_SCRATCH_FLOATS(int BN, int MODE) {
+  return MODE == 0 ? 2 * BN : 5 * BN + (128 + 32) * (BN / 32 > 4 ? BN / 32 : 4) * 2;
+}
 
-template <int BN, int STAGES>
+constexpr int GEMM_OUT_STAGE_BYTES = 8 * 2 * 4096;  // 8 epilogue warps x 2 boxes of 32 rows x 128 B
+
+template <int BN, int STAGES, int MODE>
 constexpr int gemm_smem_bytes() {
-  return 1024 /*align slack*/ + STAGES * (GEMM_A_STAGE_BYTES + BN * 128) + 256 /*barriers*/ +
-         2 * GEMM_WG_SCRATCH_FLOATS(BN) * 4;
+  return 1024 /*align slack*/ + STAGES * (GEMM_A_STAGE_BYTES + BN * 128) + GEMM_OUT_STAGE_BYTES + 256 /*barriers*/ +
+         2 * GEMM_WG_SCRATCH_FLOATS(BN, MODE) * 4;
 }
 
 template <typename TOut>
@@ -147,6 +153,43 @@ __device__ __forceinline__ void store_split8(TOut* outp, long long plane, const 
   store_chunk8<TOut>(outp, y);
 }
 
+// Per-warp output staging.  Direct epilogue stores (one 16-byte piece of 32 different rows per instruction) keep the
+// L1TEX unit busy for 32 cycles each and were the measured bottleneck of the ViT GEMMs; instead every warp writes its
+// 32 rows x 128 bytes into a swizzled shared-memory box (conflict-free) and one lane issues a TMA store of the box.
+struct OutStage {
+  uint32_t base;   // shared address of this warp's box 0 (box 1 at +4096), 1024-byte aligned
+  uint32_t count;  // boxes staged so far (persists across tiles)
+};
+__device__ __forceinline__ uint32_t stage_begin(OutStage& st, int lane) {
+  if (st.count >= 2) {  // the box used two stores ago must have been read out
+    if (lane == 0) bulk_wait_read<1>();
+    __syncwarp();
+  }
+  return st.base + (st.count & 1) * 4096;
+}
+template <typename TOut>
+__device__ __forceinline__ void stage_put8(uint32_t box, int lane, int col, const float* y) {  // col: multiple of 8 inside the box
+  const uint32_t row = box + lane * 128;
+  const int sw = lane & 7;
+  if constexpr (sizeof(TOut) == 2) {
+    st_shared_v4(row + (((col >> 3) ^ sw) << 4), pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
+                 pack_bf16x2(y[6], y[7]));
+  } else {
+    const int u = col >> 2;
+    st_shared_v4(row + ((u ^ sw) << 4), __float_as_uint(y[0]), __float_as_uint(y[1]), __float_as_uint(y[2]), __float_as_uint(y[3]));
+    st_shared_v4(row + (((u + 1) ^ sw) << 4), __float_as_uint(y[4]), __float_as_uint(y[5]), __float_as_uint(y[6]), __float_as_uint(y[7]));
+  }
+}
+__device__ __forceinline__ void stage_end(OutStage& st, const CUtensorMap* tm, uint32_t box, int lane, int col0, int row0, int g) {
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(tm, box, col0, row0, g);
+    bulk_commit();
+  }
+  st.count++;
+}
+
 // Per-tile state shared by the epilogue flavours.
 struct EpiTile {
   int n0, g, r;            // first column, group, tile row (== TMEM lane)
@@ -162,7 +205,11 @@ struct EpiTile {
 // ------------------------------------------------------------------------------------------------------------
 template <int BN, typename TOut, bool PRECISE>
 __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile& t, const float* colv, uint64_t* acc_full,
-                                                uint32_t acc_parity) {
+                                                uint32_t acc_parity, OutStage& st) {
+  constexpr int CG = 128 / sizeof(TOut);   // columns per staged box
+  const int lane = threadIdx.x & 31;
+  const int row0 = (int)(t.grow - lane);   // first logical row of this warp
+  uint32_t box = 0;
   TOut* outp = reinterpret_cast<TOut*>(a.out) + (long long)t.g * a.out_g +
                ((long long)t.q * a.out_q + (long long)t.rem * a.out_r + a.out_off) * a.ldc + t.n0;
   const long long res_row = (long long)t.q * a.res_q + (long long)t.rem * a.res_r + a.res_off;
@@ -185,6 +232,7 @@ __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile
 #pragma unroll
     for (int i = 0; i < 8; ++i) rc[i] = rb[i];
     if (c + 32 < BN) fetch(c + 32);
+    if (a.tma_out && (c % CG) == 0) box = stage_begin(st, lane);
     tmem_ld_wait();
     if (t.valid) {
 #pragma unroll
@@ -199,7 +247,12 @@ __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile
           else if (a.act == ACT_MISH) x = PRECISE ? mish_precise(x) : mish_f(x);
           y[j] = x * colv[BN + cc + j];
         }
-        if (a.vec && t.n0 + cc + 8 <= a.N) {
+        if (a.tma_out) {
+          const float4 r0 = rc[j8 / 4], r1 = rc[j8 / 4 + 1];
+          y[0] += r0.x; y[1] += r0.y; y[2] += r0.z; y[3] += r0.w;
+          y[4] += r1.x; y[5] += r1.y; y[6] += r1.z; y[7] += r1.w;
+          stage_put8<TOut>(box, lane, cc % CG, y);
+        } else if (a.vec && t.n0 + cc + 8 <= a.N) {
           const float4 r0 = rc[j8 / 4], r1 = rc[j8 / 4 + 1];
           y[0] += r0.x; y[1] += r0.y; y[2] += r0.z; y[3] += r0.w;
           y[4] += r1.x; y[5] += r1.y; y[6] += r1.z; y[7] += r1.w;
@@ -222,6 +275,8 @@ __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile
         }
       }
     }
+    if (a.tma_out && (((c + 32) % CG) == 0 || c + 32 >= BN))
+      stage_end(st, &a.tmO, box, lane, t.n0 + (c / CG) * CG, row0, t.g);
   }
 }
 
@@ -232,9 +287,13 @@ __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile
 // ------------------------------------------------------------------------------------------------------------
 template <int BN, typename TOut, bool PRECISE>
 __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t, const float* colv, float2* gn_part,
-                                            float2* gn_stat, int et, int bar_id, uint64_t* acc_full, uint32_t acc_parity) {
+                                            float2* gn_stat, int et, int bar_id, uint64_t* acc_full, uint32_t acc_parity,
+                                            OutStage& st) {
   static_assert(BN == 128 || BN == 256, "GN epilogue: whole 32/64-channel groups per tile");
   constexpr int NCH = BN / 32;  // 32-column chunks per tile
+  constexpr int CG = 128 / sizeof(TOut);
+  const int row0 = (int)(t.grow - (threadIdx.x & 31));
+  uint32_t box = 0;
   TOut* outp = reinterpret_cast<TOut*>(a.out) + (long long)t.g * a.out_g +
                ((long long)t.q * a.out_q + (long long)t.rem * a.out_r + a.out_off) * a.ldc + t.n0;
   const long long res_row = (long long)t.q * a.res_q + (long long)t.rem * a.res_r + a.res_off;
@@ -349,6 +408,7 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
       mu = (ch == k) ? mean[k] : mu;
       rs = (ch == k) ? rstd[k] : rs;
     }
+    if (a.tma_out && ((ch * 32) % CG) == 0) box = stage_begin(st, lane);
     tmem_ld_wait();
     if (t.valid) {
 #pragma unroll
@@ -382,9 +442,11 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
             for (int j = 0; j < 8; ++j) y[j] += rl[j];
           }
         }
-        store_split8<TOut>(outp + cc, a.out_plane, y);
+        if (a.tma_out) stage_put8<TOut>(box, lane, cc % CG, y);
+        else store_split8<TOut>(outp + cc, a.out_plane, y);
       }
     }
+    if (a.tma_out && (((ch + 1) * 32) % CG) == 0) stage_end(st, &a.tmO, box, lane, t.n0 + ((ch * 32) / CG) * CG, row0, t.g);
   }
 }
 
@@ -403,7 +465,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * GEMM_A_STAGE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
+  uint8_t* sOut = sB + STAGES * B_STAGE_BYTES;   // per-warp output staging boxes (1024-byte aligned)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sOut + GEMM_OUT_STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;   // [2]
   uint64_t* acc_empty = acc_full + 2;    // [2]
@@ -416,6 +479,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.tmA);
     tma_prefetch_desc(&a.tmB);
+    if (a.tma_out) tma_prefetch_desc(&a.tmO);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -500,11 +564,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int et = (threadIdx.x - 64) & 127;      // thread index inside the warpgroup
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int bar_id = 1 + wg;
-    float* colv = scratch + wg * GEMM_WG_SCRATCH_FLOATS(BN);          // [5][BN]
+    float* colv = scratch + wg * GEMM_WG_SCRATCH_FLOATS(BN, MODE);    // [2][BN] (LINEAR) / [5][BN] + GroupNorm partials
     float2* gn_part = reinterpret_cast<float2*>(colv + 5 * BN);       // [128][max(BN/32, 4)]
     float2* gn_stat = gn_part + 128 * (BN / 32 > 4 ? BN / 32 : 4);    // [32][max(BN/32, 4)]
     EpiTile t;
     t.r = quarter * 32 + lane;
+    OutStage st;
+    st.base = smem_u32(sOut) + (warp - 2) * 8192;
+    st.count = 0;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
       if ((lt & 1) != (uint32_t)wg) continue;
@@ -539,12 +606,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       t.taddr = tmem_base + wg * ACC_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
       const uint32_t parity = (lt >> 1) & 1;
       if constexpr (MODE == EPI_LINEAR)
-        epilogue_linear<BN, TOut, PRECISE>(a, t, colv, &acc_full[wg], parity);
+        epilogue_linear<BN, TOut, PRECISE>(a, t, colv, &acc_full[wg], parity, st);
       else
-        epilogue_gn<BN, TOut, PRECISE>(a, t, colv, gn_part, gn_stat, et, bar_id, &acc_full[wg], parity);
+        epilogue_gn<BN, TOut, PRECISE>(a, t, colv, gn_part, gn_stat, et, bar_id, &acc_full[wg], parity, st);
       tc_fence_before();
       mbar_arrive(&acc_empty[wg]);
     }
+    if (a.tma_out && lane == 0) bulk_wait_all();   // staged boxes must be drained before the CTA exits
   }
 
   tc_fence_before();

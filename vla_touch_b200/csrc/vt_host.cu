@@ -119,30 +119,30 @@ template <typename TIn, int BN, int MODE, typename TOut, int STAGES>
 GemmVariant make_variant() {
   GemmVariant v;
   v.fn = vt::gemm_tc_kernel<TIn, BN, MODE, TOut, STAGES, (sizeof(TIn) == 4)>;
-  v.smem = vt::gemm_smem_bytes<BN, STAGES>();
+  v.smem = vt::gemm_smem_bytes<BN, STAGES, MODE>();
+  static_assert(vt::gemm_smem_bytes<BN, STAGES, MODE>() <= 227 * 1024, "shared memory budget");
   v.attr_set = false;
   return v;
 }
 
 GemmVariant* gemm_variant(int in_dtype, int bn, int epi, int out_dtype) {
   using bf = __nv_bfloat16;
-  static GemmVariant v_b_256_l_b = make_variant<bf, 256, vt::EPI_LINEAR, bf, 4>();
-  static GemmVariant v_b_256_l_f = make_variant<bf, 256, vt::EPI_LINEAR, float, 4>();
-  static GemmVariant v_b_192_l_b = make_variant<bf, 192, vt::EPI_LINEAR, bf, 5>();
-  static GemmVariant v_b_192_l_f = make_variant<bf, 192, vt::EPI_LINEAR, float, 5>();
-  static GemmVariant v_b_128_l_b = make_variant<bf, 128, vt::EPI_LINEAR, bf, 5>();
-  static GemmVariant v_b_128_l_f = make_variant<bf, 128, vt::EPI_LINEAR, float, 5>();
+  static GemmVariant v_b_256_l_b = make_variant<bf, 256, vt::EPI_LINEAR, bf, 3>();
+  static GemmVariant v_b_256_l_f = make_variant<bf, 256, vt::EPI_LINEAR, float, 3>();
+  static GemmVariant v_b_192_l_b = make_variant<bf, 192, vt::EPI_LINEAR, bf, 3>();
+  static GemmVariant v_b_192_l_f = make_variant<bf, 192, vt::EPI_LINEAR, float, 3>();
+  static GemmVariant v_b_128_l_b = make_variant<bf, 128, vt::EPI_LINEAR, bf, 4>();
+  static GemmVariant v_b_128_l_f = make_variant<bf, 128, vt::EPI_LINEAR, float, 4>();
   static GemmVariant v_b_32_l_b = make_variant<bf, 32, vt::EPI_LINEAR, bf, 6>();
   static GemmVariant v_b_32_l_f = make_variant<bf, 32, vt::EPI_LINEAR, float, 6>();
-  static GemmVariant v_b_256_g_b = make_variant<bf, 256, vt::EPI_GN, bf, 4>();
-  static GemmVariant v_b_128_g_b = make_variant<bf, 128, vt::EPI_GN, bf, 5>();
-  static GemmVariant v_f_128_l_f = make_variant<float, 128, vt::EPI_LINEAR, float, 5>();
+  static GemmVariant v_b_128_g_b = make_variant<bf, 128, vt::EPI_GN, bf, 4>();
+  static GemmVariant v_f_128_l_f = make_variant<float, 128, vt::EPI_LINEAR, float, 4>();
   static GemmVariant v_f_32_l_f = make_variant<float, 32, vt::EPI_LINEAR, float, 6>();
-  static GemmVariant v_f_128_g_f = make_variant<float, 128, vt::EPI_GN, float, 5>();
+  static GemmVariant v_f_128_g_f = make_variant<float, 128, vt::EPI_GN, float, 4>();
   if (in_dtype == VT_BF16) {
     if (epi == VT_EPI_GN) {
       if (out_dtype != VT_BF16) return nullptr;
-      return bn == 256 ? &v_b_256_g_b : (bn == 128 ? &v_b_128_g_b : nullptr);
+      return bn == 128 ? &v_b_128_g_b : nullptr;
     }
     if (bn == 256) return out_dtype == VT_BF16 ? &v_b_256_l_b : &v_b_256_l_f;
     if (bn == 192) return out_dtype == VT_BF16 ? &v_b_192_l_b : &v_b_192_l_f;
@@ -302,6 +302,24 @@ int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
   }
   const int m_tiles = (d.M + rows_valid - 1) / rows_valid;
   const int n_tiles = (d.N + d.bn - 1) / d.bn;
+  // TMA-store epilogue: full 128-row tiles, output rows linear in the logical row (row = out_r * m + out_off), no hi|lo planes
+  {
+    const int cg = 128 / oes;
+    const bool linear_rows = d.out_q == d.out_r * (int64_t)d.row_div && d.out_r >= 1;
+    if (vec && d.out_plane == 0 && rows_valid == 128 && linear_rows && (d.bn % cg == 0 || n_tiles == 1) && d.N >= 8) {
+      const uint64_t dims[3] = {(uint64_t)d.N, (uint64_t)d.M, (uint64_t)d.G};
+      const uint64_t row_bytes = (uint64_t)d.out_r * d.ldc * oes;
+      const uint64_t g_bytes = d.G > 1 ? (uint64_t)d.out_g * oes : row_bytes * (uint64_t)d.M;
+      const uint64_t st[2] = {row_bytes, g_bytes};
+      const uint32_t box[3] = {(uint32_t)cg, 32u, 1u};
+      const char* base = reinterpret_cast<const char*>(d.out) + (int64_t)d.out_off * d.ldc * oes;
+      if (aligned16(base) && g_bytes < (1ull << 40)) {
+        int rc = make_tmap(&a.tmO, d.out_dtype, 3, base, dims, st, box);
+        if (rc) return rc;
+        a.tma_out = 1;
+      }
+    }
+  }
   const long long total = (long long)m_tiles * n_tiles * d.G;
   VT_REQUIRE(total < (1ll << 31), "gemm: too many tiles");
   a.n_tiles = n_tiles;

@@ -80,6 +80,19 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// TMA store of a shared-memory box (bulk async group completion)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {  // at most N committed groups still reading shared memory
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, fences, MMA, commit, TMEM loads
 // ------------------------------------------------------------------------------------------
@@ -195,19 +208,20 @@ __device__ __forceinline__ float mish_precise(float x) {
   return x * (n / (n + 2.f));
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
-// exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|erf error| < 1.5e-7, far below one bf16 ulp): one MUFU.EX2, one
-// MUFU.RCP and a degree-5 polynomial instead of the ~40-instruction erff
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(t, p, 1.421413741f);
-  p = fmaf(t, p, -0.284496736f);
-  p = fmaf(t, p, 0.254829592f);
-  const float e = 1.f - p * t * __expf(-z * z);
-  return 0.5f * x * (1.f + copysignf(e, x));
+// GELU for the bf16 path.  0.5 x (1 + tanh(x (a + b x^2 + c x^4))) with (a, b, c) fitted to the exact erf GELU on [-6, 6]
+// (max |error| 2.5e-5, i.e. below half a bf16 ulp everywhere; the textbook tanh form is 20x worse) and the hardware
+// tanh.approx: 8 instructions instead of ~40 for erff -- the fc1 epilogue was instruction-issue bound with erff.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float xc = fminf(fmaxf(x, -6.f), 6.f);
+  const float x2 = xc * xc;
+  const float u = xc * fmaf(x2, fmaf(x2, -3.51516795e-4f, 3.70056461e-2f), 7.97507884e-1f);
+  return 0.5f * x * (1.f + tanh_approx(u));
+}
 // round-to-nearest-even onto tf32 (low 13 mantissa bits zero); lo = x - hi is exact in fp32
 __device__ __forceinline__ float tf32_hi(float x) {
   uint32_t u = __float_as_uint(x);
