@@ -154,42 +154,55 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
       const int valid = min(128, N - j * 128) - half * 64;   // valid keys among this thread's 64 columns (may be <= 0)
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // S row in four 16-column chunks, two TMEM loads in flight (register budget: 2 CTAs x 320 threads per SM)
+      // S row in four 16-column chunks, two TMEM loads in flight (register budget: 2 CTAs x 320 threads per SM).
+      // Chunks without valid keys are skipped (the MMA reads only round16(valid) columns of P), full chunks take a
+      // select-free path: the kernel is instruction-issue bound, not MUFU or tensor bound.
       const uint32_t s_addr = tmem_S + lane_off + half * 64;
       uint32_t va[16], vb[16];
       float mx = -INFINITY;
+      const bool act0 = valid > 0, act1 = valid > 16, act2 = valid > 32, act3 = valid > 48;
       auto max16 = [&](const uint32_t(&v)[16], int c0) {
+        if (c0 + 16 <= valid) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, (c0 + i < valid) ? __uint_as_float(v[i]) : -INFINITY);
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, (c0 + i < valid) ? __uint_as_float(v[i]) : -INFINITY);
+        }
       };
-      tmem_ld16(s_addr, va);
+      if (act0) tmem_ld16(s_addr, va);
       tmem_ld_wait();
-      tmem_ld16(s_addr + 16, vb);
-      max16(va, 0);
+      if (act1) tmem_ld16(s_addr + 16, vb);
+      if (act0) max16(va, 0);
       tmem_ld_wait();
-      tmem_ld16(s_addr + 32, va);
-      max16(vb, 16);
+      if (act2) tmem_ld16(s_addr + 32, va);
+      if (act1) max16(vb, 16);
       tmem_ld_wait();
-      tmem_ld16(s_addr + 48, vb);
-      max16(va, 32);
+      if (act3) tmem_ld16(s_addr + 48, vb);
+      if (act2) max16(va, 32);
       tmem_ld_wait();
-      max16(vb, 48);
+      if (act3) max16(vb, 48);
       my_x[(j & 1) * 256] = mx;
-      tmem_ld16(s_addr, va);                      // first chunk of the second pass, overlapped with the exchange
+      if (act0) tmem_ld16(s_addr, va);            // first chunk of the second pass, overlapped with the exchange
       named_bar_sync(1, 256);
       const float m_new = fmaxf(m, fmaxf(mx, peer_x[(j & 1) * 256]));
-      const float alpha = exp2f((m - m_new) * sl);
+      const float alpha = ex2_approx((m - m_new) * sl);
       const float msc = m_new * sl;
       float rowsum = 0.f;
       auto exp16 = [&](const uint32_t(&v)[16], int c0) {
+        const bool full = c0 + 16 <= valid;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           uint32_t pk[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int i = u * 8 + 2 * e;
-            const float p0 = (c0 + i < valid) ? exp2f(fmaf(__uint_as_float(v[i]), sl, -msc)) : 0.f;
-            const float p1 = (c0 + i + 1 < valid) ? exp2f(fmaf(__uint_as_float(v[i + 1]), sl, -msc)) : 0.f;
+            float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl, -msc));
+            float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl, -msc));
+            if (!full) {
+              p0 = (c0 + i < valid) ? p0 : 0.f;
+              p1 = (c0 + i + 1 < valid) ? p1 : 0.f;
+            }
             rowsum += p0 + p1;
             pk[e] = pack_bf16x2(p0, p1);
           }
@@ -197,16 +210,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
         }
       };
       tmem_ld_wait();
-      tmem_ld16(s_addr + 16, vb);
-      exp16(va, 0);
+      if (act1) tmem_ld16(s_addr + 16, vb);
+      if (act0) exp16(va, 0);
       tmem_ld_wait();
-      tmem_ld16(s_addr + 32, va);
-      exp16(vb, 16);
+      if (act2) tmem_ld16(s_addr + 32, va);
+      if (act1) exp16(vb, 16);
       tmem_ld_wait();
-      tmem_ld16(s_addr + 48, vb);
-      exp16(va, 32);
+      if (act3) tmem_ld16(s_addr + 48, vb);
+      if (act2) exp16(va, 32);
       tmem_ld_wait();
-      exp16(vb, 48);
+      if (act3) exp16(vb, 48);
       l = l * alpha + rowsum;
       m = m_new;
       fence_proxy_async_smem();
@@ -246,25 +259,25 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
   if (warp == 9) tmem_dealloc(tmem_base, 256);
 }
 
-// Last query rows of an image when tokens % 128 <= ATT_TAIL_MAX (e.g. the 257th token at 224x224): one warp per
-// (image, head, row) on the CUDA cores instead of a 128-row tensor-core tile that would be >87% padding.
-constexpr int ATTT_WARPS = 8;
-__global__ void __launch_bounds__(ATTT_WARPS * 32) attn_tail_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                                    __nv_bfloat16* __restrict__ ctx, int images, int tokens,
-                                                                    int heads, int D, long long ctx_ld, int first_row,
-                                                                    float scale_log2) {
-  extern __shared__ float sp[];  // [ATTT_WARPS][tokens]
+// Last query rows of an image when tokens % 128 <= ATT_TAIL_MAX (e.g. the 257th token at 224x224): one 128-thread block
+// per (image, head, row) on the CUDA cores instead of a 128-row tensor-core tile that would be >87% padding.
+// Keys are split over the four warps (scores -> shared memory, block-wide max / sum), then thread (w, l) accumulates
+// output channels (2l, 2l+1) over the keys k = w (mod 4) and the four partial sums are combined through shared memory.
+constexpr int ATTT_THREADS = 128;
+__global__ void __launch_bounds__(ATTT_THREADS) attn_tail_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                 __nv_bfloat16* __restrict__ ctx, int images, int tokens,
+                                                                 int heads, int D, long long ctx_ld, int first_row,
+                                                                 float scale_log2) {
+  extern __shared__ float sp[];  // [tokens] scores + [8] reductions + [4][64] partial outputs
+  float* red = sp + tokens;
+  float* part = red + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tail = tokens - first_row;
-  const long long gw = (long long)blockIdx.x * ATTT_WARPS + warp;
-  const long long total = (long long)images * heads * tail;
-  if (gw >= total) return;
-  const int qi = first_row + (int)(gw % tail);
-  const int head = (int)((gw / tail) % heads);
-  const int img = (int)(gw / ((long long)tail * heads));
+  const int qi = first_row + (int)(blockIdx.x % tail);
+  const int head = (int)((blockIdx.x / tail) % heads);
+  const int img = (int)(blockIdx.x / (tail * heads));
   const long long ld = 3LL * D;
   const __nv_bfloat16* base = qkv + (long long)img * tokens * ld;
-  float* p = sp + (long long)warp * tokens;
   float qr[64];
   {
     const uint4* q4 = reinterpret_cast<const uint4*>(base + (long long)qi * ld + head * 64);
@@ -281,13 +294,15 @@ __global__ void __launch_bounds__(ATTT_WARPS * 32) attn_tail_kernel(const __nv_b
     }
   }
   float mx = -INFINITY;
-  for (int k = lane; k < tokens; k += 32) {
+  for (int k = threadIdx.x; k < tokens; k += ATTT_THREADS) {
     const uint4* k4 = reinterpret_cast<const uint4*>(base + (long long)k * ld + D + head * 64);
+    uint4 kv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) kv[i] = k4[i];
     float acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const uint4 t = k4[i];
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&t);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kv[i]);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 f = __bfloat1622float2(h2[e]);
@@ -296,28 +311,39 @@ __global__ void __launch_bounds__(ATTT_WARPS * 32) attn_tail_kernel(const __nv_b
       }
     }
     acc *= scale_log2;
-    p[k] = acc;
+    sp[k] = acc;
     mx = fmaxf(mx, acc);
   }
   mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
   float sum = 0.f;
-  for (int k = lane; k < tokens; k += 32) {
-    const float e = exp2f(p[k] - mx);
-    p[k] = e;
+  for (int k = threadIdx.x; k < tokens; k += ATTT_THREADS) {
+    const float e = ex2_approx(sp[k] - mx);
+    sp[k] = e;
     sum += e;
   }
   sum = warp_sum(sum);
-  __syncwarp();
-  const float inv = 1.0f / sum;
+  if (lane == 0) red[4 + warp] = sum;
+  __syncthreads();
+  const float inv = 1.0f / (red[4] + red[5] + red[6] + red[7]);
   float o0 = 0.f, o1 = 0.f;
   const __nv_bfloat16* vb = base + 2 * D + head * 64 + 2 * lane;
-  for (int k = 0; k < tokens; ++k) {
+  for (int k = warp; k < tokens; k += 4) {
     const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + (long long)k * ld));
-    const float pk = p[k];
+    const float pk = sp[k];
     o0 = fmaf(pk, f.x, o0);
     o1 = fmaf(pk, f.y, o1);
   }
-  *reinterpret_cast<uint32_t*>(ctx + ((long long)img * tokens + qi) * ctx_ld + head * 64 + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
+  part[warp * 64 + 2 * lane] = o0;
+  part[warp * 64 + 2 * lane + 1] = o1;
+  __syncthreads();
+  if (warp == 0) {
+    o0 = part[2 * lane] + part[64 + 2 * lane] + part[128 + 2 * lane] + part[192 + 2 * lane];
+    o1 = part[2 * lane + 1] + part[64 + 2 * lane + 1] + part[128 + 2 * lane + 1] + part[192 + 2 * lane + 1];
+    *reinterpret_cast<uint32_t*>(ctx + ((long long)img * tokens + qi) * ctx_ld + head * 64 + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
+  }
 }
 
 // fp32 attention on the CUDA cores (parity mode): one warp per (image, head, query row).

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <memory>
 #include <string>
@@ -233,6 +234,10 @@ int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
     int rc = make_tmap(&a.tmB, d.in_dtype, 2, d.w, dims, st, box);
     if (rc) return rc;
   }
+  {
+    const char* dbg = getenv("VT_GEMM_DEBUG");
+    a.debug = dbg ? atoi(dbg) : 0;
+  }
   a.passes = d.passes;
   a.taps = d.taps;
   a.cblocks = d.kc / KE;
@@ -349,12 +354,11 @@ struct AttnOp : Op {
         VT_LAUNCH_CHECK("attn_tc_kernel");
       }
       if (tail_first >= 0) {
-        const long long warps = (long long)d.images * d.heads * (d.tokens - tail_first);
-        const int blocks = (int)((warps + vt::ATTT_WARPS - 1) / vt::ATTT_WARPS);
-        const size_t smem = (size_t)vt::ATTT_WARPS * d.tokens * sizeof(float);
-        vt::attn_tail_kernel<<<blocks, vt::ATTT_WARPS * 32, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(d.qkv),
-                                                                       args.ctx, d.images, d.tokens, d.heads, args.D,
-                                                                       args.ctx_ld, tail_first, args.scale_log2);
+        const long long blocks = (long long)d.images * d.heads * (d.tokens - tail_first);
+        const size_t smem = (size_t)(d.tokens + 8 + 256) * sizeof(float);
+        vt::attn_tail_kernel<<<(unsigned)blocks, vt::ATTT_THREADS, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(d.qkv),
+                                                                            args.ctx, d.images, d.tokens, d.heads, args.D,
+                                                                            args.ctx_ld, tail_first, args.scale_log2);
         VT_LAUNCH_CHECK("attn_tail_kernel");
       }
     } else {
@@ -587,7 +591,7 @@ int vt_program_add_attention(vt_program* p, const vt_attn_desc* d) {
     op->args.scale_log2 = 0.125f * 1.4426950408889634f;
     int q_tiles = (d->tokens + 127) / 128;
     const int rem = d->tokens % 128;
-    if (rem > 0 && rem <= vt::ATT_TAIL_MAX && (size_t)vt::ATTT_WARPS * d->tokens * 4 <= 48 * 1024) {
+    if (rem > 0 && rem <= vt::ATT_TAIL_MAX && (size_t)(d->tokens + 264) * 4 <= 48 * 1024) {
       op->tail_first = d->tokens - rem;   // the short last tile runs on the CUDA cores
       q_tiles -= 1;
     }

@@ -211,6 +211,11 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + er
 // GELU for the bf16 path.  0.5 x (1 + tanh(x (a + b x^2 + c x^4))) with (a, b, c) fitted to the exact erf GELU on [-6, 6]
 // (max |error| 2.5e-5, i.e. below half a bf16 ulp everywhere; the textbook tanh form is 20x worse) and the hardware
 // tanh.approx: 8 instructions instead of ~40 for erff -- the fc1 epilogue was instruction-issue bound with erff.
+__device__ __forceinline__ float ex2_approx(float x) {   // 2^x, one MUFU.EX2 (ex2(-inf) = 0)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
