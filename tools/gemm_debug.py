@@ -15,8 +15,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         print(f"  op {i:4d} {eng.plan.tags[i]:44s} {sorted(ts)[1]:8.1f} us", flush=True)
 else:
     ops = sys.argv[1:] or ["7", "9", "11", "12", "105", "111", "115", "123"]
-    for dbg in ("0", "1", "2", "3"):
-        print(f"VT_GEMM_DEBUG={dbg}  (bit0: no TMA/MMA, bit1: no epilogue)", flush=True)
+    for dbg in os.environ.get("VT_DEBUG_SET", "0 1 2 3 6 10").split():
+        print(f"VT_GEMM_DEBUG={dbg}  (1: no TMA+MMA, 2: no epilogue, 4: no TMA, 8: no MMA)", flush=True)
         env = dict(os.environ, VT_GEMM_DEBUG=dbg)
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"] + ops, env=env, capture_output=True, text=True, timeout=600)
         print(r.stdout + r.stderr[-800:], flush=True)

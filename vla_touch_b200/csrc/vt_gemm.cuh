@@ -32,7 +32,8 @@ struct GemmArgs {
   CUtensorMap tmA;  // 5-D (C, P, T, B, G), box (KE, 1, Tbox, Bbox, 1), SWIZZLE_128B
   CUtensorMap tmB;  // 2-D (Ktot, G*n_pad), box (KE, BN), SWIZZLE_128B
   CUtensorMap tmO;  // 3-D (N, M, G) over the output, box (128 B, 32 rows, 1), SWIZZLE_128B; valid when tma_out
-  int debug;        // developer knob (env VT_GEMM_DEBUG): bit0 skip TMA loads + MMAs, bit1 skip the epilogue body
+  int debug;        // developer knob (env VT_GEMM_DEBUG): 1 skip TMA loads + MMAs, 2 skip the epilogue body, 4 skip TMA
+                    // loads only, 8 skip MMAs only
   int tma_out;      // 1: the epilogue stages 32-row x 128-byte boxes in shared memory and drains them with TMA stores
   // ---- tiles ----
   int n_tiles, m_tiles, total_tiles;  // tile id = (g * m_tiles + m_tile) * n_tiles + n_tile
@@ -92,9 +93,9 @@ struct InTraits<float> {
   static constexpr uint32_t FMT = UMMA_FMT_TF32;
 };
 
-// per epilogue warpgroup (GroupNorm only): row partials [128][BN/32] and sample sums [32][BN/32] (float2)
+// per epilogue warpgroup: 5 column vectors, GroupNorm row partials [128][BN/32] and sample sums [32][BN/32] (float2)
 __host__ __device__ constexpr int GEMM_WG_SCRATCH_FLOATS(int BN, int MODE) {
-  return MODE == 0 ? 0 : (128 + 32) * (BN / 32 > 4 ? BN / 32 : 4) * 2;
+  return MODE == 0 ? 2 * BN : 5 * BN + (128 + 32) * (BN / 32 > 4 ? BN / 32 : 4) * 2;
 }
 
 constexpr int GEMM_OUT_STAGE_BYTES = 8 * 2 * 4096;  // 8 epilogue warps x 2 boxes of 32 rows x 128 B
@@ -191,21 +192,6 @@ __device__ __forceinline__ void stage_end(OutStage& st, const CUtensorMap* tm, u
   st.count++;
 }
 
-// 8 consecutive entries of a per-column vector (bias, LayerScale, GroupNorm affine, FiLM time part).  Every lane reads the
-// same address, so these are broadcast L1 hits; `avail` guards ragged ends, a null vector yields `dflt`.
-__device__ __forceinline__ void ld_col8(const float* __restrict__ p, int avail, float dflt, float* out) {
-  if (p == nullptr) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) out[j] = dflt;
-  } else if (avail >= 8) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) out[j] = j < avail ? __ldg(p + j) : dflt;
-  }
-}
-
 // Per-tile state shared by the epilogue flavours.
 struct EpiTile {
   int n0, g, r;            // first column, group, tile row (== TMEM lane)
@@ -220,10 +206,14 @@ struct EpiTile {
 // 32 columns is requested before the current chunk is processed, the first one before the accumulator is ready.
 // ------------------------------------------------------------------------------------------------------------
 template <int BN, typename TOut, bool PRECISE>
-__device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile& t, uint64_t* acc_full,
+__device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile& t, const float* colv, uint64_t* acc_full,
                                                 uint32_t acc_parity, OutStage& st) {
-  const float* biasp = a.bias ? a.bias + (long long)t.g * a.n_pad + t.n0 : nullptr;
-  const float* scalep = a.colscale ? a.colscale + t.n0 : nullptr;
+  // kernel parameters used inside the column loops, pinned in registers (the struct lives in the constant bank and is
+  // otherwise re-read after every asm "memory" clobber)
+  const int N = a.N, act = a.act, dbg = a.debug;
+  const bool tma = a.tma_out != 0, vec = a.vec != 0;
+  const long long oplane = a.out_plane;
+
   constexpr int CG = 128 / sizeof(TOut);   // columns per staged box
   const int lane = threadIdx.x & 31;
   const int row0 = (int)(t.grow - lane);   // first logical row of this warp
@@ -232,12 +222,12 @@ __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile
                ((long long)t.q * a.out_q + (long long)t.rem * a.out_r + a.out_off) * a.ldc + t.n0;
   const long long res_row = (long long)t.q * a.res_q + (long long)t.rem * a.res_r + a.res_off;
   const float* resp = a.res ? reinterpret_cast<const float*>(a.res) + (long long)t.g * a.res_g + res_row * a.ldres + t.n0 : nullptr;
-  const bool vres = resp && a.vec && t.valid;
+  const bool vres = resp && vec && t.valid;
   float4 rb[8];
   auto fetch = [&](int c) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      rb[i] = (vres && t.n0 + c + 4 * i + 4 <= a.N) ? *reinterpret_cast<const float4*>(resp + c + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[i] = (vres && t.n0 + c + 4 * i + 4 <= N) ? *reinterpret_cast<const float4*>(resp + c + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
   };
   fetch(0);
   mbar_wait(acc_full, acc_parity);
@@ -245,47 +235,58 @@ __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile
 #pragma unroll 1
   for (int c = 0; c < BN; c += 32) {
     uint32_t v[32];
-    tmem_ld32(t.taddr + c, v);
+    if (dbg & 32) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0u;
+    } else {
+      tmem_ld32(t.taddr + c, v);
+    }
     float4 rc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) rc[i] = rb[i];
     if (c + 32 < BN) fetch(c + 32);
-    if (a.tma_out && (c % CG) == 0) box = stage_begin(st, lane);
+    if (tma && (c % CG) == 0 && !(dbg & 16)) box = stage_begin(st, lane);
     tmem_ld_wait();
     if (t.valid) {
 #pragma unroll
       for (int j8 = 0; j8 < 32; j8 += 8) {
         const int cc = c + j8;
-        if (t.n0 + cc >= a.N) break;
-        float y[8], bs[8], cs[8];
-        const int avail = a.N - (t.n0 + cc);
-        ld_col8(biasp ? biasp + cc : nullptr, avail, 0.f, bs);
-        ld_col8(scalep ? scalep + cc : nullptr, avail, 1.f, cs);
+        if (t.n0 + cc >= N) break;
+        float y[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float x = __uint_as_float(v[j8 + j]) + bs[j];
-          if (a.act == ACT_GELU) x = PRECISE ? gelu_erf(x) : gelu_fast(x);
-          else if (a.act == ACT_MISH) x = PRECISE ? mish_precise(x) : mish_f(x);
-          y[j] = x * cs[j];
+        for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(v[j8 + j]) + colv[cc + j];
+        if (act == ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[j] = PRECISE ? gelu_erf(y[j]) : gelu_fast(y[j]);
+        } else if (act == ACT_MISH) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[j] = PRECISE ? mish_precise(y[j]) : mish_f(y[j]);
         }
-        if (a.tma_out) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] *= colv[BN + cc + j];
+        if (dbg & 16) {
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc += y[j];
+          if (acc == 123.456f) outp[cc] = TOut(acc);   // keeps the math alive without producing output traffic
+        } else if (tma) {
           const float4 r0 = rc[j8 / 4], r1 = rc[j8 / 4 + 1];
           y[0] += r0.x; y[1] += r0.y; y[2] += r0.z; y[3] += r0.w;
           y[4] += r1.x; y[5] += r1.y; y[6] += r1.z; y[7] += r1.w;
           stage_put8<TOut>(box, lane, cc % CG, y);
-        } else if (a.vec && t.n0 + cc + 8 <= a.N) {
+        } else if (vec && t.n0 + cc + 8 <= N) {
           const float4 r0 = rc[j8 / 4], r1 = rc[j8 / 4 + 1];
           y[0] += r0.x; y[1] += r0.y; y[2] += r0.z; y[3] += r0.w;
           y[4] += r1.x; y[5] += r1.y; y[6] += r1.z; y[7] += r1.w;
-          store_split8<TOut>(outp + cc, a.out_plane, y);
+          store_split8<TOut>(outp + cc, oplane, y);
         } else {  // ragged last columns / unaligned rows: scalar
-          for (int j = 0; j < 8 && t.n0 + cc + j < a.N; ++j) {
+          for (int j = 0; j < 8 && t.n0 + cc + j < N; ++j) {
             const float yy = y[j] + (resp ? resp[cc + j] : 0.f);
             if constexpr (sizeof(TOut) == 4) {
-              if (a.out_plane > 0) {
+              if (oplane > 0) {
                 const float hi = tf32_hi(yy);
                 outp[cc + j] = hi;
-                outp[a.out_plane + cc + j] = yy - hi;
+                outp[oplane + cc + j] = yy - hi;
               } else {
                 outp[cc + j] = yy;
               }
@@ -296,7 +297,7 @@ __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile
         }
       }
     }
-    if (a.tma_out && (((c + 32) % CG) == 0 || c + 32 >= BN))
+    if (tma && !(dbg & 16) && (((c + 32) % CG) == 0 || c + 32 >= BN))
       stage_end(st, &a.tmO, box, lane, t.n0 + (c / CG) * CG, row0, t.g);
   }
 }
@@ -307,14 +308,13 @@ __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile
 // rows of a sample with warp shuffles (power-of-two T <= 32, or T a multiple of 32) or through shared memory.
 // ------------------------------------------------------------------------------------------------------------
 template <int BN, typename TOut, bool PRECISE>
-__device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t, float2* gn_part,
+__device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t, const float* colv, float2* gn_part,
                                             float2* gn_stat, int et, int bar_id, uint64_t* acc_full, uint32_t acc_parity,
                                             OutStage& st) {
-  const long long gcol = (long long)t.g * a.n_pad + t.n0;
-  const float* biasp = a.bias ? a.bias + gcol : nullptr;
-  const float* gammap = a.gn_gamma + gcol;
-  const float* betap = a.gn_beta + gcol;
-  const float* filmtp = a.film_t ? a.film_t + (long long)t.g * a.film_tg + a.film_off + t.n0 : nullptr;
+  const bool tma = a.tma_out != 0;
+  const long long oplane = a.out_plane, rplane = a.res_plane;
+  const int filmC = a.film_C;
+
   static_assert(BN == 128 || BN == 256, "GN epilogue: whole 32/64-channel groups per tile");
   constexpr int NCH = BN / 32;  // 32-column chunks per tile
   constexpr int CG = 128 / sizeof(TOut);
@@ -337,15 +337,10 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
     tmem_ld_wait();
     float a1 = 0.f, a2 = 0.f;
 #pragma unroll
-    for (int j8 = 0; j8 < 32; j8 += 8) {
-      float bs[8];
-      ld_col8(biasp ? biasp + ch * 32 + j8 : nullptr, 8, 0.f, bs);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float x = __uint_as_float(v[j8 + j]) + bs[j];
-        a1 += x;
-        a2 = fmaf(x, x, a2);
-      }
+    for (int j = 0; j < 32; ++j) {
+      float x = __uint_as_float(v[j]) + colv[ch * 32 + j];
+      a1 += x;
+      a2 = fmaf(x, x, a2);
     }
     s1[ch] = t.valid ? a1 : 0.f;
     s2[ch] = t.valid ? a2 : 0.f;
@@ -368,7 +363,6 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
       s1[ch] = warp_sum(s1[ch]);
       s2[ch] = warp_sum(s2[ch]);
     }
-    named_bar_sync(bar_id, 128);   // every thread is done reading the previous tile's partials
     if (lane == 0) {
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) gn_part[(t.r >> 5) * NCH + ch] = make_float2(s1[ch], s2[ch]);
@@ -389,7 +383,6 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
     }
   } else {
     // generic T (e.g. 48, 24, 12): per-row partials through shared memory; thread et sums (sample et / NCH, chunk et % NCH)
-    named_bar_sync(bar_id, 128);   // every thread is done reading the previous tile's partials
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) gn_part[t.r * NCH + ch] = make_float2(s1[ch], s2[ch]);
     named_bar_sync(bar_id, 128);
@@ -441,7 +434,7 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
       mu = (ch == k) ? mean[k] : mu;
       rs = (ch == k) ? rstd[k] : rs;
     }
-    if (a.tma_out && ((ch * 32) % CG) == 0) box = stage_begin(st, lane);
+    if (tma && ((ch * 32) % CG) == 0) box = stage_begin(st, lane);
     tmem_ld_wait();
     if (t.valid) {
 #pragma unroll
@@ -450,42 +443,36 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
         float sc[8], sh[8], rr[8], rl[8];
         if (filmp) {
           load_res8(filmp + cc, sc);
-          load_res8(filmp + a.film_C + cc, sh);
+          load_res8(filmp + filmC + cc, sh);
         }
         if (resp) {
           load_res8(resp + cc, rr);
-          if (a.res_plane > 0) load_res8(resp + a.res_plane + cc, rl);
+          if (rplane > 0) load_res8(resp + rplane + cc, rl);
         }
-        float y[8], bs[8], ga[8], be[8];
-        ld_col8(biasp ? biasp + cc : nullptr, 8, 0.f, bs);
-        ld_col8(gammap + cc, 8, 1.f, ga);
-        ld_col8(betap + cc, 8, 0.f, be);
+        float y[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float x = __uint_as_float(v[j8 + j]) + bs[j];
-          x = (x - mu) * rs * ga[j] + be[j];
+          float x = __uint_as_float(v[j8 + j]) + colv[cc + j];
+          x = (x - mu) * rs * colv[BN + cc + j] + colv[2 * BN + cc + j];
           y[j] = PRECISE ? mish_precise(x) : mish_f(x);
         }
         if (filmp) {
-          float ts[8], th[8];
-          ld_col8(filmtp ? filmtp + cc : nullptr, 8, 0.f, ts);
-          ld_col8(filmtp ? filmtp + a.film_C + cc : nullptr, 8, 0.f, th);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) y[j] = (sc[j] + ts[j]) * y[j] + (sh[j] + th[j]);
+          for (int j = 0; j < 8; ++j) y[j] = (sc[j] + colv[3 * BN + cc + j]) * y[j] + (sh[j] + colv[4 * BN + cc + j]);
         }
         if (resp) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) y[j] += rr[j];
-          if (a.res_plane > 0) {
+          if (rplane > 0) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) y[j] += rl[j];
           }
         }
-        if (a.tma_out) stage_put8<TOut>(box, lane, cc % CG, y);
-        else store_split8<TOut>(outp + cc, a.out_plane, y);
+        if (tma) stage_put8<TOut>(box, lane, cc % CG, y);
+        else store_split8<TOut>(outp + cc, oplane, y);
       }
     }
-    if (a.tma_out && (((ch + 1) * 32) % CG) == 0) stage_end(st, &a.tmO, box, lane, t.n0 + ((ch * 32) / CG) * CG, row0, t.g);
+    if (tma && (((ch + 1) * 32) % CG) == 0) stage_end(st, &a.tmO, box, lane, t.n0 + ((ch * 32) / CG) * CG, row0, t.g);
   }
 }
 
@@ -545,9 +532,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int s = 0;
-      uint32_t ph = 0;   // ring position: no divisions in this loop (a k-block of MMA work is only a few hundred cycles)
+      uint32_t ph = 0;   // ring position kept incrementally: no divisions in this loop
       int n_tile = blockIdx.x % a.n_tiles, rest = blockIdx.x / a.n_tiles;
       const int dn = gridDim.x % a.n_tiles, dr = gridDim.x / a.n_tiles;
+      const bool no_tma = (a.debug & 5) != 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         const int m_tile = rest % a.m_tiles;
         const int g = rest / a.m_tiles;
@@ -560,7 +548,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             const int tap_p = a.tap_p[tp], tap_t = t_base + a.tap_t[tp];
             for (int cb = 0; cb < a.cblocks; ++cb, kb += KE) {
               mbar_wait(&empty[s], ph ^ 1);
-              if (a.debug & 1) {
+              if (no_tma) {
                 mbar_arrive(&full[s]);
               } else {
                 mbar_arrive_expect_tx(&full[s], a.a_box_bytes + B_STAGE_BYTES);
@@ -587,6 +575,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     if (lane == 0) {
       uint32_t lt = 0, ph = 0;
       int s = 0;
+      const bool no_mma = (a.debug & 9) != 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
         const uint32_t acc = lt & 1;
         mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
@@ -599,7 +588,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sB + s * B_STAGE_BYTES));
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 4 x (32 bytes of K) per 128-byte swizzle row
-            if (a.debug & 1) break;
+            if (no_mma) break;
             if constexpr (sizeof(TIn) == 2)
               umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (i | k) != 0);
             else
@@ -620,7 +609,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int et = (threadIdx.x - 64) & 127;      // thread index inside the warpgroup
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int bar_id = 1 + wg;
-    float2* gn_part = reinterpret_cast<float2*>(scratch + wg * GEMM_WG_SCRATCH_FLOATS(BN, MODE));   // [128][max(BN/32, 4)]
+    float* colv = scratch + wg * GEMM_WG_SCRATCH_FLOATS(BN, MODE);    // [2][BN] (LINEAR) / [5][BN] + GroupNorm partials
+    float2* gn_part = reinterpret_cast<float2*>(colv + 5 * BN);       // [128][max(BN/32, 4)]
     float2* gn_stat = gn_part + 128 * (BN / 32 > 4 ? BN / 32 : 4);    // [32][max(BN/32, 4)]
     EpiTile t;
     t.r = quarter * 32 + lane;
@@ -635,6 +625,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       const int m_tile = rest % a.m_tiles;
       t.g = rest / a.m_tiles;
       t.n0 = n_tile * BN;
+      // stage the per-column vectors of this tile (previous tile's readers are done: barrier first)
+      if (!(a.debug & 64)) named_bar_sync(bar_id, 128);
+      if (!(a.debug & 64)) {
+        const long long gcol = (long long)t.g * a.n_pad + t.n0;
+        for (int c = et; c < BN; c += 128) {
+          colv[c] = a.bias ? a.bias[gcol + c] : 0.f;
+          if (MODE == EPI_LINEAR) {
+            colv[BN + c] = (a.colscale && (t.n0 + c) < a.N) ? a.colscale[t.n0 + c] : 1.f;
+          } else {
+            colv[BN + c] = a.gn_gamma[gcol + c];
+            colv[2 * BN + c] = a.gn_beta[gcol + c];
+            const bool f = a.film_t != nullptr;
+            const long long fo = (long long)t.g * a.film_tg + a.film_off + t.n0 + c;
+            colv[3 * BN + c] = f ? a.film_t[fo] : 0.f;
+            colv[4 * BN + c] = f ? a.film_t[fo + a.film_C] : 0.f;
+          }
+        }
+      }
+      if (!(a.debug & 64)) named_bar_sync(bar_id, 128);
       t.grow = (long long)m_tile * a.rows_valid + t.r;
       t.valid = (t.r < a.rows_valid) && (t.grow < a.M_total);
       t.q = (int)(t.grow / a.row_div);
@@ -645,9 +654,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         mbar_wait(&acc_full[wg], parity);
         tc_fence_after();
       } else if constexpr (MODE == EPI_LINEAR)
-        epilogue_linear<BN, TOut, PRECISE>(a, t, &acc_full[wg], parity, st);
+        epilogue_linear<BN, TOut, PRECISE>(a, t, colv, &acc_full[wg], parity, st);
       else
-        epilogue_gn<BN, TOut, PRECISE>(a, t, gn_part, gn_stat, et, bar_id, &acc_full[wg], parity, st);
+        epilogue_gn<BN, TOut, PRECISE>(a, t, colv, gn_part, gn_stat, et, bar_id, &acc_full[wg], parity, st);
       tc_fence_before();
       mbar_arrive(&acc_empty[wg]);
     }
