@@ -225,6 +225,37 @@ typedef struct vt_sde_desc {
   int64_t xpad_plane;
 } vt_sde_desc;
 
+/* q_sample of the stochastic interpolant, bridge_model.py:103-107,248-257:
+ *   t = clip(step, 1e-3, 1-1e-3);  gamma = 1.4142 t (1-t);  z = d * z_unit;  xt = (1-t) x0 + t x1 + gamma z */
+typedef struct vt_qsample_desc {
+  const float* x0;      /* [B][n] prior (vla) actions, n = T*A */
+  const float* x1;      /* [B][n] target (expert) actions */
+  const float* step;    /* [B] raw U(0,1) draws */
+  const float* z_unit;  /* [B][n] N(0,1) draws */
+  float d;              /* beta_max */
+  int32_t B, n, A;
+  float* xt;            /* [B][n] */
+  float* tclip;         /* [B] */
+  void* xpad;           /* channel-padded operand copy of xt: [B*T][xpad_ld] */
+  int32_t xpad_dtype, xpad_ld;
+  int64_t xpad_plane;
+} vt_qsample_desc;
+
+/* velocity / score / b losses, bridge_model.py:183-218,240-246, for nets stacked as [b_net, v_net, s_net]:
+ *   L_v = mean_b(0.5|v|^2 - <x1-x0, v>),  L_s = mean_b(0.5|s|^2 + <z, s>),  L_b = mean_b(0.5|b|^2 - <x1-x0 + gdot z, b>)
+ * with z = d*z_unit, gdot = 1.4142 (1 - 2 t).  out[4] = (L_v + L_s + L_b, L_v, L_s, L_b). */
+typedef struct vt_siloss_desc {
+  const float* bvs;     /* [3][B][n] outputs of b_net, v_net, s_net */
+  const float* x0;
+  const float* x1;
+  const float* z_unit;
+  const float* tclip;   /* [B] */
+  float d;
+  int32_t B, n;
+  float* per_sample;    /* scratch [3][B] */
+  float* out;           /* [4] */
+} vt_siloss_desc;
+
 /* nn.LSTM (gate order i,f,g,o), lstm_step_controller.py:66-73,196-204: the input projections xw = W_ih x + b_ih
  * + b_hh are precomputed by a GEMM; this op runs the recurrence over T steps for one layer. */
 typedef struct vt_lstm_desc {
@@ -263,6 +294,8 @@ int vt_program_add_affine(vt_program* p, const vt_affine_desc* d);
 int vt_program_add_tembed(vt_program* p, const vt_tembed_desc* d);
 int vt_program_add_sde(vt_program* p, const vt_sde_desc* d);
 int vt_program_add_lstm(vt_program* p, const vt_lstm_desc* d);
+int vt_program_add_qsample(vt_program* p, const vt_qsample_desc* d);
+int vt_program_add_siloss(vt_program* p, const vt_siloss_desc* d);
 
 /* Launch ops [first, first+count) in order on `stream` (count < 0: to the end). */
 int vt_program_run(vt_program* p, int first, int count, void* stream);

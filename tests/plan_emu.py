@@ -261,7 +261,40 @@ def emu_lstm(plan, d: nv.LstmDesc):
     c[:] = cc
 
 
-_EMU = {nv.GemmDesc: emu_gemm, nv.LnDesc: emu_layernorm, nv.AttnDesc: emu_attention, nv.ImgStatsDesc: emu_imgstats,
+def emu_qsample(plan, d: nv.QsampleDesc):
+    N = d.B * d.n
+    x0 = _flat(plan, d.x0, torch.float32)[:N].reshape(d.B, d.n)
+    x1 = _flat(plan, d.x1, torch.float32)[:N].reshape(d.B, d.n)
+    z = _flat(plan, d.z_unit, torch.float32)[:N].reshape(d.B, d.n) * torch.tensor(d.d, dtype=torch.float32)
+    t = torch.clip(_flat(plan, d.step, torch.float32)[: d.B], 0.001, 1.0 - 0.001)
+    tb = t[:, None]
+    gamma = 1.4142 * tb * (1 - tb)
+    xt = (1 - tb) * x0 + tb * x1 + gamma * z
+    _flat(plan, d.xt, torch.float32)[:N] = xt.reshape(-1)
+    _flat(plan, d.tclip, torch.float32)[: d.B] = t
+    if d.xpad:
+        rows = torch.arange(N // d.A)
+        _store(plan, d.xpad, d.xpad_dtype, rows[:, None] * d.xpad_ld + torch.arange(d.A)[None, :], xt.reshape(-1, d.A), d.xpad_plane)
+
+
+def emu_siloss(plan, d: nv.SilossDesc):
+    N = d.B * d.n
+    bvs = _flat(plan, d.bvs, torch.float32)[: 3 * N].reshape(3, d.B, d.n)
+    x0 = _flat(plan, d.x0, torch.float32)[:N].reshape(d.B, d.n)
+    x1 = _flat(plan, d.x1, torch.float32)[:N].reshape(d.B, d.n)
+    z = _flat(plan, d.z_unit, torch.float32)[:N].reshape(d.B, d.n) * torch.tensor(d.d, dtype=torch.float32)
+    t = _flat(plan, d.tclip, torch.float32)[: d.B]
+    gd = (1.4142 * (1 - 2 * t))[:, None]
+    pt = x1 - x0
+    b, v, s = bvs[0], bvs[1], bvs[2]
+    lv = (0.5 * (v * v).sum(-1) - (pt * v).sum(-1)).mean()
+    ls = (0.5 * (s * s).sum(-1) + (z * s).sum(-1)).mean()
+    lb = (0.5 * (b * b).sum(-1) - ((pt + gd * z) * b).sum(-1)).mean()
+    out = _flat(plan, d.out, torch.float32)
+    out[0], out[1], out[2], out[3] = lv + ls + lb, lv, ls, lb
+
+
+_EMU = {nv.QsampleDesc: emu_qsample, nv.SilossDesc: emu_siloss, nv.GemmDesc: emu_gemm, nv.LnDesc: emu_layernorm, nv.AttnDesc: emu_attention, nv.ImgStatsDesc: emu_imgstats,
         nv.PatchifyDesc: emu_patchify, nv.ClsDesc: emu_cls, nv.PackDesc: emu_pack, nv.AffineDesc: emu_affine,
         nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm}
 

@@ -258,3 +258,17 @@ def test_kernels_match_the_descriptor_interpreter_op_by_op():
         rows = gpu_diff.diff_plans(ups[0].plan, ups[1].plan, resync=True)
         bad = [r for r in rows if not r[3] <= 2e-2 * max(r[4], 1e-6)]      # one bf16 ulp at the tensor scale is 2^-8
         assert not bad, gpu_diff.format_rows(bad)
+
+
+@pytest.mark.parametrize("precise", MODES)
+@pytest.mark.parametrize("A,T", [(10, 16), (7, 64)])
+def test_get_loss_value(A, T, precise):
+    g = U.golden(f"loss_A{A}_T{T}")
+    si = _interpolant(A, T, precise)
+    si.step_override, si.z_override = g["step"].to(DEV), g["z_unit"].to(DEV)
+    batch = {"obs_cond": syn.det_normal("loss.cond", (3, 256), 24), "expert_act": syn.det_uniform("loss.exp", (3, T, A), 24, -1.0, 1.0),
+             "vla_act": syn.det_uniform("loss.vla", (3, T, A), 24, -1.0, 1.0)}
+    loss, info = si.get_loss(batch, DEV)
+    tol = 2e-3 if precise else 5e-2
+    for got, key in ((loss, "loss"), (info["v_loss"], "v_loss"), (info["s_loss"], "s_loss"), (info["b_loss"], "b_loss")):
+        assert abs(float(got) - float(g[key])) <= tol * max(1.0, abs(float(g[key]))), (key, float(got), float(g[key]))

@@ -56,7 +56,8 @@ def test_ctypes_structs_match_the_c_header():
     descs = {"vt_gemm_desc": nv.GemmDesc, "vt_ln_desc": nv.LnDesc, "vt_attn_desc": nv.AttnDesc,
              "vt_imgstats_desc": nv.ImgStatsDesc, "vt_patchify_desc": nv.PatchifyDesc, "vt_cls_desc": nv.ClsDesc,
              "vt_pack_desc": nv.PackDesc, "vt_affine_desc": nv.AffineDesc, "vt_tembed_desc": nv.TembedDesc,
-             "vt_sde_desc": nv.SdeDesc, "vt_lstm_desc": nv.LstmDesc}
+             "vt_sde_desc": nv.SdeDesc, "vt_lstm_desc": nv.LstmDesc, "vt_qsample_desc": nv.QsampleDesc,
+             "vt_siloss_desc": nv.SilossDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/vt_b200.h"', 'int main(void){']
     probes = []
     for cname, cls in descs.items():
@@ -204,3 +205,17 @@ def test_parameter_trees_follow_the_reference_key_contract():
     rnet = ref.bridge_model.InterpolantsConditionalUnet1D(input_dim=10, global_cond_dim=256)
     assert [k for k, _ in rnet.named_parameters()] == keys
     assert [tuple(p.shape) for p in rnet.parameters()] == [tuple(p.shape) for p in net.parameters()]
+
+
+@pytest.mark.parametrize("A,T", [(10, 16), (7, 64)])
+def test_loss_plan_reproduces_the_reference_golden(A, T):
+    from vla_touch_b200.unet import LossProgram
+    g = U.golden(f"loss_A{A}_T{T}")
+    full = U.net_sd(A, 21)
+    sub = lambda n: {k[len(n):]: v for k, v in full.items() if k.startswith(n)}
+    lp = LossProgram([sub("b_net."), sub("v_net."), sub("s_net.")], A, 3, T, 0.03, "cpu", precise=True)
+    lp.x0.copy_(syn.det_uniform("loss.vla", (3, T, A), 24, -1.0, 1.0)); lp.x1.copy_(syn.det_uniform("loss.exp", (3, T, A), 24, -1.0, 1.0))
+    lp.cond.copy_(syn.det_normal("loss.cond", (3, 256), 24)); lp.step.copy_(g["step"]); lp.z.copy_(g["z_unit"])
+    plan_emu.run(lp.plan)
+    for i, key in enumerate(("loss", "v_loss", "s_loss", "b_loss")):
+        assert abs(float(lp.out[i]) - float(g[key])) <= 1e-3 * max(1.0, abs(float(g[key]))), key

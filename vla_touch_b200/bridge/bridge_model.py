@@ -13,6 +13,7 @@ from ..ema import ExponentialMovingAverage
 from ..engine import BridgeEngine
 from ..params import sub_state_dict
 from ..schedule import check_model_args
+from ..unet import LossProgram
 from .networks.conditional_unet_1D_si import InterpolantsConditionalUnet1D
 
 
@@ -24,6 +25,9 @@ class StochasticInterpolants:
         self._engines: Dict[tuple, BridgeEngine] = {}
         self._engine_version: Dict[tuple, int] = {}
         self.noise_override: Optional[torch.Tensor] = None    # [n_steps,B,T,A]: injected N(0,1) draws (parity tests)
+        self.step_override: Optional[torch.Tensor] = None     # get_loss: injected U(0,1) draws [B]
+        self.z_override: Optional[torch.Tensor] = None        # get_loss: injected N(0,1) draws [B,T,A]
+        self._loss_programs: Dict[tuple, list] = {}
         self._seed = 0
         if model_args:
             self.load_model_args(model_args)
@@ -116,6 +120,31 @@ class StochasticInterpolants:
             traj.append(eng.x.clone())
         return traj[-1], traj
 
+    @torch.no_grad()
     def get_loss(self, batch_dict, device=None):
-        raise NotImplementedError("StochasticInterpolants.get_loss (training, bridge_model.py:220-246) is not built yet on the "
-                                  "B200 path; see DESIGN.md 'next rows'")
+        """Loss VALUE of bridge_model.py:220-246 (v + s + b losses on the live b_net / v_net / s_net weights), computed by
+        one native program.  Forward only: the returned tensors carry no autograd graph (the backward kernels are the next
+        row), so this serves validation / monitoring (`_validate`, bridge_train.py:380-438)."""
+        device = device or self.device
+        nobs = batch_dict['obs_cond'].to(device).float().flatten(1)
+        naction = batch_dict['expert_act'].to(device).float()
+        if 'vla_act' in batch_dict:
+            prior_action = batch_dict['vla_act'].to(device).float()
+        else:
+            prior_action = torch.randn(naction.shape).float().to(naction.device)
+        B, T, A = naction.shape
+        step = self.step_override if self.step_override is not None else torch.rand(B, device=device)
+        z = self.z_override if self.z_override is not None else torch.randn_like(naction)
+        key = (B, T)
+        version = sum(p._version for p in self.net.parameters())
+        ent = self._loss_programs.get(key)
+        sd = self.net.state_dict()
+        sds = [sub_state_dict(sd, "b_net."), sub_state_dict(sd, "v_net."), sub_state_dict(sd, "s_net.")]
+        if ent is None:
+            ent = [LossProgram(sds, A, B, T, float(self.d), device, self.precise), version]
+            self._loss_programs[key] = ent
+        elif ent[1] != version:
+            ent[0].refresh(sds)
+            ent[1] = version
+        out = ent[0](prior_action, naction, nobs, step, z).clone()
+        return out[0], {'v_loss': out[1], 's_loss': out[2], 'b_loss': out[3]}

@@ -363,6 +363,71 @@ __global__ void __launch_bounds__(256) sde_step_kernel(float* __restrict__ x, co
   }
 }
 
+// q_sample (bridge_model.py:103-107,248-257), reference operation order
+__global__ void __launch_bounds__(256) qsample_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
+                                                      const float* __restrict__ step, const float* __restrict__ z_unit, float d,
+                                                      int B, int n, int A, float* __restrict__ xt, float* __restrict__ tclip,
+                                                      void* __restrict__ xpad, int xpad_dtype, int xpad_ld, long long xpad_plane) {
+  const long long total = (long long)B * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / n);
+    const int e = (int)(idx - (long long)b * n);
+    const float t = fminf(fmaxf(step[b], 0.001f), 1.0f - 0.001f);
+    if (e == 0) tclip[b] = t;
+    const float gamma = __fmul_rn(__fmul_rn(1.4142f, t), __fsub_rn(1.0f, t));
+    const float z = __fmul_rn(d, z_unit[idx]);
+    float v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, t), x0[idx]), __fmul_rn(t, x1[idx]));
+    v = __fadd_rn(v, __fmul_rn(gamma, z));
+    xt[idx] = v;
+    if (xpad) store_val(xpad, xpad_dtype, (idx / A) * xpad_ld + (idx % A), xpad_plane, v);
+  }
+}
+
+// per-sample loss terms (one block per sample), then the batch mean
+__global__ void __launch_bounds__(128) siloss_sample_kernel(const float* __restrict__ bvs, const float* __restrict__ x0,
+                                                            const float* __restrict__ x1, const float* __restrict__ z_unit,
+                                                            const float* __restrict__ tclip, float d, int B, int n,
+                                                            float* __restrict__ per_sample) {
+  const int b = blockIdx.x;
+  const float t = tclip[b];
+  const float gd = 1.4142f * (1.0f - 2.0f * t);
+  const float* pb = bvs + (long long)b * n;
+  const float* pv = pb + (long long)B * n;
+  const float* ps = pv + (long long)B * n;
+  float lv = 0.f, ls = 0.f, lb = 0.f;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const long long i = (long long)b * n + e;
+    const float pt = x1[i] - x0[i];
+    const float z = d * z_unit[i];
+    const float v = pv[e], s = ps[e], bb = pb[e];
+    lv += 0.5f * v * v - pt * v;
+    ls += 0.5f * s * s + z * s;
+    lb += 0.5f * bb * bb - (pt + gd * z) * bb;
+  }
+  __shared__ float red[3][4];
+  lv = warp_sum(lv); ls = warp_sum(ls); lb = warp_sum(lb);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[0][w] = lv; red[1][w] = ls; red[2][w] = lb; }
+  __syncthreads();
+  if (threadIdx.x < 3) per_sample[threadIdx.x * B + b] = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
+}
+__global__ void __launch_bounds__(96) siloss_mean_kernel(const float* __restrict__ per_sample, int B, float* __restrict__ out) {
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;   // k: 0 = b, 1 = v, 2 = s
+  float acc = 0.f;
+  for (int i = lane; i < B; i += 32) acc += per_sample[k * B + i];
+  acc = warp_sum(acc) / (float)B;
+  __shared__ float m[3];
+  if (lane == 0) m[k] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    out[1] = m[1];
+    out[2] = m[2];
+    out[3] = m[0];
+    out[0] = m[1] + m[2] + m[0];
+  }
+}
+
 // bicubic resize (A = -0.75, align_corners = False) of the patch position embeddings, HF:57-95
 __device__ __forceinline__ void cubic_coeffs(float t, float* w) {
   const float A = -0.75f;

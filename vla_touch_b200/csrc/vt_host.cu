@@ -487,6 +487,28 @@ struct SdeOp : Op {
   }
 };
 
+struct QsampleOp : Op {
+  vt_qsample_desc d;
+  int launch(cudaStream_t s) override {
+    vt::qsample_kernel<<<grid_for((long long)d.B * d.n, 256), 256, 0, s>>>(d.x0, d.x1, d.step, d.z_unit, d.d, d.B, d.n, d.A, d.xt,
+                                                                           d.tclip, d.xpad, d.xpad_dtype, d.xpad_ld, d.xpad_plane);
+    VT_LAUNCH_CHECK("qsample_kernel");
+    return VT_OK;
+  }
+};
+
+struct SilossOp : Op {
+  vt_siloss_desc d;
+  int launches() const override { return 2; }
+  int launch(cudaStream_t s) override {
+    vt::siloss_sample_kernel<<<d.B, 128, 0, s>>>(d.bvs, d.x0, d.x1, d.z_unit, d.tclip, d.d, d.B, d.n, d.per_sample);
+    VT_LAUNCH_CHECK("siloss_sample_kernel");
+    vt::siloss_mean_kernel<<<1, 96, 0, s>>>(d.per_sample, d.B, d.out);
+    VT_LAUNCH_CHECK("siloss_mean_kernel");
+    return VT_OK;
+  }
+};
+
 struct LstmOp : Op {
   vt_lstm_desc d;
   int launch(cudaStream_t s) override {
@@ -641,6 +663,13 @@ VT_SIMPLE_ADD(vt_program_add_sde, SdeOp, vt_sde_desc,
               VT_REQUIRE(d->x && d->v && d->s && d->rows >= 1 && d->A >= 1, "sde: bad descriptor"))
 VT_SIMPLE_ADD(vt_program_add_lstm, LstmOp, vt_lstm_desc,
               VT_REQUIRE(d->xw && d->w_hh && d->h && d->c && d->y && d->B >= 1 && d->T >= 1 && d->H == 256, "lstm: bad descriptor"))
+
+VT_SIMPLE_ADD(vt_program_add_qsample, QsampleOp, vt_qsample_desc,
+              VT_REQUIRE(d->x0 && d->x1 && d->step && d->z_unit && d->xt && d->tclip && d->B >= 1 && d->n >= 1 && d->A >= 1 &&
+                             d->n % d->A == 0, "qsample: bad descriptor"))
+VT_SIMPLE_ADD(vt_program_add_siloss, SilossOp, vt_siloss_desc,
+              VT_REQUIRE(d->bvs && d->x0 && d->x1 && d->z_unit && d->tclip && d->per_sample && d->out && d->B >= 1 && d->n >= 1,
+                         "siloss: bad descriptor"))
 
 int vt_program_run(vt_program* p, int first, int count, void* stream) {
   int rc = clamp_range(p, first, &count);

@@ -89,12 +89,22 @@ class LstmDesc(C.Structure):
                 ("y_plane", i64), ("B", i32), ("T", i32), ("H", i32)]
 
 
+class QsampleDesc(C.Structure):
+    _fields_ = [("x0", vp), ("x1", vp), ("step", vp), ("z_unit", vp), ("d", f32), ("B", i32), ("n", i32), ("A", i32),
+                ("xt", vp), ("tclip", vp), ("xpad", vp), ("xpad_dtype", i32), ("xpad_ld", i32), ("xpad_plane", i64)]
+
+
+class SilossDesc(C.Structure):
+    _fields_ = [("bvs", vp), ("x0", vp), ("x1", vp), ("z_unit", vp), ("tclip", vp), ("d", f32), ("B", i32), ("n", i32),
+                ("per_sample", vp), ("out", vp)]
+
+
 EXPORTS = [
     "vt_last_error", "vt_abi_version", "vt_device_info", "vt_program_create", "vt_program_destroy",
     "vt_program_num_ops", "vt_program_num_launches", "vt_program_add_gemm", "vt_program_add_layernorm",
     "vt_program_add_attention", "vt_program_add_imgstats", "vt_program_add_patchify", "vt_program_add_cls",
     "vt_program_add_pack", "vt_program_add_affine", "vt_program_add_tembed", "vt_program_add_sde",
-    "vt_program_add_lstm", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
+    "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
     "vt_pos_embed_resize",
 ]
 
@@ -102,7 +112,8 @@ _ADD = {
     GemmDesc: "vt_program_add_gemm", LnDesc: "vt_program_add_layernorm", AttnDesc: "vt_program_add_attention",
     ImgStatsDesc: "vt_program_add_imgstats", PatchifyDesc: "vt_program_add_patchify", ClsDesc: "vt_program_add_cls",
     PackDesc: "vt_program_add_pack", AffineDesc: "vt_program_add_affine", TembedDesc: "vt_program_add_tembed",
-    SdeDesc: "vt_program_add_sde", LstmDesc: "vt_program_add_lstm",
+    SdeDesc: "vt_program_add_sde", LstmDesc: "vt_program_add_lstm", QsampleDesc: "vt_program_add_qsample",
+    SilossDesc: "vt_program_add_siloss",
 }
 
 _lib: Optional[C.CDLL] = None

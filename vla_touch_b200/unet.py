@@ -407,3 +407,48 @@ class UnetProgram:
         self.cond.copy_(global_cond)
         self.plan.compile().run()
         return self.bufs.out
+
+
+class LossProgram:
+    """StochasticInterpolants.get_loss forward value (bridge_model.py:220-257,183-218): q_sample, then b_net / v_net / s_net
+    evaluated as one grouped program (G = 3) on the same (x_t, t, cond), then the three loss reductions.
+    Inputs: x0 (vla_act), x1 (expert_act) [B,T,A], cond [B,cond], step [B] ~ U(0,1), z_unit [B,T,A] ~ N(0,1)."""
+
+    def __init__(self, sds_bvs: Sequence[SD], action_dim: int, B: int, T: int, beta_max: float, device, precise: bool = False):
+        assert len(sds_bvs) == 3, "expects [b_net, v_net, s_net]"
+        self.W = UnetWeights(sds_bvs, action_dim, device, precise)
+        self.plan = p = Plan(device)
+        self.W.register(p)
+        m, A = self.W.mode, action_dim
+        self.B, self.T, self.A = B, T, A
+        f32 = torch.float32
+        self.x0 = p.buf("in.x0", (B, T, A), f32)
+        self.x1 = p.buf("in.x1", (B, T, A), f32)
+        self.cond = p.buf("in.cond", (B, self.W.cond_dim), f32)
+        self.step = p.buf("in.step", (B,), f32)
+        self.z = p.buf("in.z_unit", (B, T, A), f32)
+        self.xt = p.buf("xt", (B, T, A), f32)
+        self.tclip = p.buf("tclip", (B,), f32)
+        self.film = p.buf("film", (3, B, FILM_ROWS), f32)
+        self.bufs = UnetBuffers(p, self.W, B, T)
+        self.per_sample = p.buf("loss.per_sample", (3, B), f32)
+        self.out = p.buf("loss.out", (4,), f32)
+        d = nv.QsampleDesc()
+        d.x0, d.x1, d.step, d.z_unit, d.d = ptr(self.x0), ptr(self.x1), ptr(self.step), ptr(self.z), beta_max
+        d.B, d.n, d.A, d.xt, d.tclip = B, T * A, A, ptr(self.xt), ptr(self.tclip)
+        d.xpad, d.xpad_dtype, d.xpad_ld, d.xpad_plane = ptr(self.bufs.xpad), m.dt, m.ld(self.W.cin0), m.plane(self.W.cin0)
+        p.add(d, "q_sample")
+        build_time_film(p, self.W, self.tclip, B, self.cond, self.film)
+        build_unet_eval(p, self.W, self.bufs, self.film, None)
+        d = nv.SilossDesc()
+        d.bvs, d.x0, d.x1, d.z_unit, d.tclip, d.d = ptr(self.bufs.out), ptr(self.x0), ptr(self.x1), ptr(self.z), ptr(self.tclip), beta_max
+        d.B, d.n, d.per_sample, d.out = B, T * A, ptr(self.per_sample), ptr(self.out)
+        p.add(d, "si_losses")
+
+    def refresh(self, sds_bvs: Sequence[SD]) -> None:
+        self.W.refresh(sds_bvs)
+
+    def __call__(self, x0, x1, cond, step, z_unit) -> torch.Tensor:
+        self.x0.copy_(x0); self.x1.copy_(x1); self.cond.copy_(cond); self.step.copy_(step); self.z.copy_(z_unit)
+        self.plan.compile().run()
+        return self.out
