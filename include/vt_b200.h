@@ -270,6 +270,29 @@ typedef struct vt_lstm_desc {
   int32_t B, T, H;
 } vt_lstm_desc;
 
+/* Fused multi-tensor optimizer step of the bridge trainer (bridge_train.py:330-337 + torch_ema update):
+ *   g *= grad_scale (1/world after the gradient all-reduce);  AdamW (torch.optim.AdamW semantics, decoupled weight decay,
+ *   bias correction with step t);  EMA shadow s -= (1 - ema_decay) (s - p)  when ema != null.
+ * `tensors` is a DEVICE array of n records, `chunks` a DEVICE array of n_chunks (tensor index, element offset) pairs, one
+ * per thread block (chunk_elems elements each). */
+typedef struct vt_opt_tensor {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  float* ema;       /* may be null */
+  int64_t numel;
+} vt_opt_tensor;
+typedef struct vt_adamw_desc {
+  const vt_opt_tensor* tensors;
+  const int64_t* chunks;       /* [n_chunks][2] */
+  int32_t n_chunks, chunk_elems;
+  float lr, beta1, beta2, eps, weight_decay;
+  float bias_corr1, bias_corr2; /* 1 - beta1^t, 1 - beta2^t */
+  float ema_decay;              /* min(decay, (1+n)/(10+n)) */
+  float grad_scale;
+} vt_adamw_desc;
+
 typedef struct vt_program vt_program;
 
 const char* vt_last_error(void);
@@ -302,6 +325,9 @@ int vt_program_run(vt_program* p, int first, int count, void* stream);
 /* Capture ops [first, first+count) into a CUDA graph (replacing any earlier one); launch it. */
 int vt_program_graph_build(vt_program* p, int first, int count);
 int vt_program_graph_launch(vt_program* p, void* stream);
+
+/* immediate launch of the fused AdamW + EMA step */
+int vt_adamw_ema_step(const vt_adamw_desc* d, void* stream);
 
 /* bicubic (A=-0.75, align_corners=False) resize of the patch position embeddings, HF:57-95: src [s*s][D] -> dst [nh*nw][D] */
 int vt_pos_embed_resize(const float* src_dev, int32_t s, float* dst_dev, int32_t nh, int32_t nw, int32_t D, void* stream);

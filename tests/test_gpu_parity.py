@@ -272,3 +272,31 @@ def test_get_loss_value(A, T, precise):
     tol = 2e-3 if precise else 5e-2
     for got, key in ((loss, "loss"), (info["v_loss"], "v_loss"), (info["s_loss"], "s_loss"), (info["b_loss"], "b_loss")):
         assert abs(float(got) - float(g[key])) <= tol * max(1.0, abs(float(g[key]))), (key, float(got), float(g[key]))
+
+
+def test_fused_adamw_ema_matches_torch():
+    """One multi-tensor launch == torch.optim.AdamW + CosineAnnealingLR + torch_ema update (bridge_train.py:330-337)."""
+    from vla_touch_b200.ema import ExponentialMovingAverage
+    from vla_touch_b200.optim import FusedAdamWEMA
+    torch.manual_seed(0)
+    shapes = [(300, 70), (513,), (4, 5, 6), (70000,)]
+    p_ref = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in shapes]
+    p_new = [torch.nn.Parameter(p.detach().clone()) for p in p_ref]
+    opt_ref = torch.optim.AdamW(p_ref, lr=1e-2, weight_decay=1e-2)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt_ref, T_max=10, eta_min=1e-3)
+    ema_ref = ExponentialMovingAverage(p_ref[:2], decay=0.75)
+    ema_new = ExponentialMovingAverage(p_new[:2], decay=0.75)
+    opt = FusedAdamWEMA(p_new, lr=1e-2, weight_decay=1e-2, ema=ema_new, ema_params=p_new[:2], t_max=10, eta_min=1e-3)
+    for it in range(5):
+        grads = [torch.randn(s, device=DEV) for s in shapes]
+        for p, g in zip(p_ref, grads):
+            p.grad = g.clone() * 0.5                     # reference sees the already averaged gradient
+        opt_ref.step(); ema_ref.update(); sched.step()
+        for p, g in zip(p_new, grads):
+            p.grad.copy_(g)
+        opt.step(grad_scale=0.5)                          # 1/world folded into the kernel
+        for a, b in zip(p_new, p_ref):
+            torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-6)
+        for a, b in zip(ema_new.shadow_params, ema_ref.shadow_params):
+            torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-6)
+    assert ema_new.num_updates == 5

@@ -57,7 +57,7 @@ def test_ctypes_structs_match_the_c_header():
              "vt_imgstats_desc": nv.ImgStatsDesc, "vt_patchify_desc": nv.PatchifyDesc, "vt_cls_desc": nv.ClsDesc,
              "vt_pack_desc": nv.PackDesc, "vt_affine_desc": nv.AffineDesc, "vt_tembed_desc": nv.TembedDesc,
              "vt_sde_desc": nv.SdeDesc, "vt_lstm_desc": nv.LstmDesc, "vt_qsample_desc": nv.QsampleDesc,
-             "vt_siloss_desc": nv.SilossDesc}
+             "vt_siloss_desc": nv.SilossDesc, "vt_opt_tensor": nv.OptTensor, "vt_adamw_desc": nv.AdamwDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/vt_b200.h"', 'int main(void){']
     probes = []
     for cname, cls in descs.items():

@@ -428,6 +428,41 @@ __global__ void __launch_bounds__(96) siloss_mean_kernel(const float* __restrict
   }
 }
 
+// fused multi-tensor AdamW + EMA (one thread block per chunk of one tensor, 128-bit accesses when aligned)
+struct OptTensor {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  float* ema;
+  long long numel;
+};
+__global__ void __launch_bounds__(256) adamw_ema_kernel(const OptTensor* __restrict__ tensors, const long long* __restrict__ chunks,
+                                                        int chunk_elems, float lr, float beta1, float beta2, float eps, float wd,
+                                                        float bc1, float bc2, float ema_decay, float grad_scale) {
+  const OptTensor t = tensors[chunks[2 * blockIdx.x]];
+  const long long off = chunks[2 * blockIdx.x + 1];
+  const long long end = min(off + (long long)chunk_elems, t.numel);
+  const float step_size = lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  const float one_minus_decay = 1.0f - ema_decay;
+  for (long long i = off + threadIdx.x; i < end; i += blockDim.x) {
+    const float g = t.g[i] * grad_scale;
+    float p = t.p[i] * (1.0f - lr * wd);
+    const float m = beta1 * t.m[i] + (1.0f - beta1) * g;
+    const float v = beta2 * t.v[i] + (1.0f - beta2) * g * g;
+    const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
+    p -= step_size * (m / denom);
+    t.p[i] = p;
+    t.m[i] = m;
+    t.v[i] = v;
+    if (t.ema) {
+      const float s = t.ema[i];
+      t.ema[i] = s - one_minus_decay * (s - p);
+    }
+  }
+}
+
 // bicubic resize (A = -0.75, align_corners = False) of the patch position embeddings, HF:57-95
 __device__ __forceinline__ void cubic_coeffs(float t, float* w) {
   const float A = -0.75f;

@@ -715,6 +715,16 @@ int vt_program_graph_launch(vt_program* p, void* stream) {
   return VT_OK;
 }
 
+int vt_adamw_ema_step(const vt_adamw_desc* d, void* stream) {
+  VT_REQUIRE(d && d->tensors && d->chunks && d->n_chunks >= 1 && d->chunk_elems >= 1, "adamw: bad descriptor");
+  static_assert(sizeof(vt_opt_tensor) == sizeof(vt::OptTensor), "record layout");
+  vt::adamw_ema_kernel<<<d->n_chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const vt::OptTensor*>(d->tensors), reinterpret_cast<const long long*>(d->chunks), d->chunk_elems, d->lr,
+      d->beta1, d->beta2, d->eps, d->weight_decay, d->bias_corr1, d->bias_corr2, d->ema_decay, d->grad_scale);
+  VT_LAUNCH_CHECK("adamw_ema_kernel");
+  return VT_OK;
+}
+
 int vt_pos_embed_resize(const float* src_dev, int32_t s, float* dst_dev, int32_t nh, int32_t nw, int32_t D, void* stream) {
   VT_REQUIRE(src_dev && dst_dev && s >= 1 && nh >= 1 && nw >= 1 && D >= 1, "pos_embed_resize: bad arguments");
   vt::pos_resize_kernel<<<grid_for((long long)nh * nw * D, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(

@@ -99,13 +99,23 @@ class SilossDesc(C.Structure):
                 ("per_sample", vp), ("out", vp)]
 
 
+class OptTensor(C.Structure):
+    _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("ema", vp), ("numel", i64)]
+
+
+class AdamwDesc(C.Structure):
+    _fields_ = [("tensors", vp), ("chunks", vp), ("n_chunks", i32), ("chunk_elems", i32), ("lr", f32), ("beta1", f32),
+                ("beta2", f32), ("eps", f32), ("weight_decay", f32), ("bias_corr1", f32), ("bias_corr2", f32),
+                ("ema_decay", f32), ("grad_scale", f32)]
+
+
 EXPORTS = [
     "vt_last_error", "vt_abi_version", "vt_device_info", "vt_program_create", "vt_program_destroy",
     "vt_program_num_ops", "vt_program_num_launches", "vt_program_add_gemm", "vt_program_add_layernorm",
     "vt_program_add_attention", "vt_program_add_imgstats", "vt_program_add_patchify", "vt_program_add_cls",
     "vt_program_add_pack", "vt_program_add_affine", "vt_program_add_tembed", "vt_program_add_sde",
     "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
-    "vt_pos_embed_resize",
+    "vt_pos_embed_resize", "vt_adamw_ema_step",
 ]
 
 _ADD = {
@@ -143,6 +153,7 @@ def lib() -> C.CDLL:
         L.vt_program_graph_launch.argtypes = [vp, vp]
         L.vt_device_info.argtypes = [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
         L.vt_pos_embed_resize.argtypes = [vp, i32, vp, i32, i32, i32, vp]
+        L.vt_adamw_ema_step.argtypes = [C.POINTER(AdamwDesc), vp]
         if L.vt_abi_version() != 1:
             raise NativeError("libvt_b200.so ABI version mismatch; rebuild it")
         _lib = L
