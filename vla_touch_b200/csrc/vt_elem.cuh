@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(128) siloss_sample_kernel(const float* __restr
   if (threadIdx.x < 3) per_sample[threadIdx.x * B + b] = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
 }
 __global__ void __launch_bounds__(96) siloss_mean_kernel(const float* __restrict__ per_sample, int B, float* __restrict__ out) {
-  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;   // k: 0 = b, 1 = v, 2 = s
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;   // k: 0 = v, 1 = s, 2 = b (rows of per_sample)
   float acc = 0.f;
   for (int i = lane; i < B; i += 32) acc += per_sample[k * B + i];
   acc = warp_sum(acc) / (float)B;
@@ -421,10 +421,10 @@ __global__ void __launch_bounds__(96) siloss_mean_kernel(const float* __restrict
   if (lane == 0) m[k] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
-    out[1] = m[1];
-    out[2] = m[2];
-    out[3] = m[0];
-    out[0] = m[1] + m[2] + m[0];
+    out[1] = m[0];
+    out[2] = m[1];
+    out[3] = m[2];
+    out[0] = m[0] + m[1] + m[2];
   }
 }
 
