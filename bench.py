@@ -164,6 +164,8 @@ def main():
         args.steps = min(args.steps, 5)
         return run_reference(args, wl)
 
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # the version banner goes to stdout and would precede the JSON line
     import torch
     import torch.distributed as dist
     from vla_touch_b200 import native as nv

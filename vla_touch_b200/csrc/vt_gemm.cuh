@@ -98,7 +98,13 @@ __host__ __device__ constexpr int GEMM_WG_SCRATCH_FLOATS(int BN, int MODE) {
   return MODE == 0 ? 2 * BN : 5 * BN + (128 + 32) * (BN / 32 > 4 ? BN / 32 : 4) * 2;
 }
 
-constexpr int GEMM_OUT_STAGE_BYTES = 8 * 2 * 4096;  // 8 epilogue warps x 2 boxes of 32 rows x 128 B
+// 8 epilogue warps x 2 boxes of 32 rows x 128 B when the TMA-store epilogue is compiled in.  Measured on B200: the
+// main loop is bound by the TMA -> MMA -> commit round trip divided by the ring depth, so the 64 KB buy more as two
+// extra operand stages than as output staging; the direct-store epilogue is kept as the default.
+#ifndef VT_GEMM_TMA_STORE
+#define VT_GEMM_TMA_STORE 0
+#endif
+constexpr int GEMM_OUT_STAGE_BYTES = VT_GEMM_TMA_STORE ? 8 * 2 * 4096 : 0;
 
 template <int BN, int STAGES, int MODE>
 constexpr int gemm_smem_bytes() {

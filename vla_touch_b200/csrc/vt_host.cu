@@ -128,18 +128,18 @@ GemmVariant make_variant() {
 
 GemmVariant* gemm_variant(int in_dtype, int bn, int epi, int out_dtype) {
   using bf = __nv_bfloat16;
-  static GemmVariant v_b_256_l_b = make_variant<bf, 256, vt::EPI_LINEAR, bf, 3>();
-  static GemmVariant v_b_256_l_f = make_variant<bf, 256, vt::EPI_LINEAR, float, 3>();
-  static GemmVariant v_b_192_l_b = make_variant<bf, 192, vt::EPI_LINEAR, bf, 3>();
-  static GemmVariant v_b_192_l_f = make_variant<bf, 192, vt::EPI_LINEAR, float, 3>();
-  static GemmVariant v_b_128_l_b = make_variant<bf, 128, vt::EPI_LINEAR, bf, 4>();
-  static GemmVariant v_b_128_l_f = make_variant<bf, 128, vt::EPI_LINEAR, float, 4>();
+  static GemmVariant v_b_256_l_b = make_variant<bf, 256, vt::EPI_LINEAR, bf, VT_GEMM_TMA_STORE ? 3 : 4>();
+  static GemmVariant v_b_256_l_f = make_variant<bf, 256, vt::EPI_LINEAR, float, VT_GEMM_TMA_STORE ? 3 : 4>();
+  static GemmVariant v_b_192_l_b = make_variant<bf, 192, vt::EPI_LINEAR, bf, VT_GEMM_TMA_STORE ? 3 : 5>();
+  static GemmVariant v_b_192_l_f = make_variant<bf, 192, vt::EPI_LINEAR, float, VT_GEMM_TMA_STORE ? 3 : 5>();
+  static GemmVariant v_b_128_l_b = make_variant<bf, 128, vt::EPI_LINEAR, bf, VT_GEMM_TMA_STORE ? 4 : 6>();
+  static GemmVariant v_b_128_l_f = make_variant<bf, 128, vt::EPI_LINEAR, float, VT_GEMM_TMA_STORE ? 4 : 6>();
   static GemmVariant v_b_32_l_b = make_variant<bf, 32, vt::EPI_LINEAR, bf, 6>();
   static GemmVariant v_b_32_l_f = make_variant<bf, 32, vt::EPI_LINEAR, float, 6>();
-  static GemmVariant v_b_128_g_b = make_variant<bf, 128, vt::EPI_GN, bf, 4>();
-  static GemmVariant v_f_128_l_f = make_variant<float, 128, vt::EPI_LINEAR, float, 4>();
+  static GemmVariant v_b_128_g_b = make_variant<bf, 128, vt::EPI_GN, bf, VT_GEMM_TMA_STORE ? 4 : 6>();
+  static GemmVariant v_f_128_l_f = make_variant<float, 128, vt::EPI_LINEAR, float, VT_GEMM_TMA_STORE ? 4 : 6>();
   static GemmVariant v_f_32_l_f = make_variant<float, 32, vt::EPI_LINEAR, float, 6>();
-  static GemmVariant v_f_128_g_f = make_variant<float, 128, vt::EPI_GN, float, 4>();
+  static GemmVariant v_f_128_g_f = make_variant<float, 128, vt::EPI_GN, float, VT_GEMM_TMA_STORE ? 4 : 6>();
   if (in_dtype == VT_BF16) {
     if (epi == VT_EPI_GN) {
       if (out_dtype != VT_BF16) return nullptr;
@@ -311,7 +311,7 @@ int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
   {
     const int cg = 128 / oes;
     const bool linear_rows = d.out_q == d.out_r * (int64_t)d.row_div && d.out_r >= 1;
-    if (vec && d.out_plane == 0 && rows_valid == 128 && linear_rows && (d.bn % cg == 0 || n_tiles == 1) && d.N >= 8) {
+    if (VT_GEMM_TMA_STORE && vec && d.out_plane == 0 && rows_valid == 128 && linear_rows && (d.bn % cg == 0 || n_tiles == 1) && d.N >= 8) {
       const uint64_t dims[3] = {(uint64_t)d.N, (uint64_t)d.M, (uint64_t)d.G};
       const uint64_t row_bytes = (uint64_t)d.out_r * d.ldc * oes;
       const uint64_t g_bytes = d.G > 1 ? (uint64_t)d.out_g * oes : row_bytes * (uint64_t)d.M;
