@@ -106,9 +106,12 @@ __host__ __device__ constexpr int GEMM_WG_SCRATCH_FLOATS(int BN, int MODE) {
 #endif
 constexpr int GEMM_OUT_STAGE_BYTES = VT_GEMM_TMA_STORE ? 8 * 2 * 4096 : 0;
 
-template <int BN, int STAGES, int MODE>
+// KA = number of 128-byte-wide K atoms (64 bf16 / 32 tf32 elements of K each) per pipeline stage.
+// One mbarrier wait + tcgen05.commit per stage costs the single issuing thread ~450 cycles (measured), more than the MMA
+// time of one atom at BN=128, so a stage carries KA atoms (2 x 4 UMMA instructions per barrier round).
+template <int BN, int STAGES, int MODE, int KA>
 constexpr int gemm_smem_bytes() {
-  return 1024 /*align slack*/ + STAGES * (GEMM_A_STAGE_BYTES + BN * 128) + GEMM_OUT_STAGE_BYTES + 256 /*barriers*/ +
+  return 1024 /*align slack*/ + STAGES * KA * (GEMM_A_STAGE_BYTES + BN * 128) + GEMM_OUT_STAGE_BYTES + 256 /*barriers*/ +
          2 * GEMM_WG_SCRATCH_FLOATS(BN, MODE) * 4;
 }
 
@@ -482,10 +485,13 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
   }
 }
 
-template <typename TIn, int BN, int MODE, typename TOut, int STAGES, bool PRECISE>
+template <typename TIn, int BN, int MODE, typename TOut, int STAGES, bool PRECISE, int KA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs a) {
   constexpr int KE = InTraits<TIn>::KE;
-  constexpr int B_STAGE_BYTES = BN * 128;
+  constexpr int A_ATOM_BYTES = GEMM_A_STAGE_BYTES;   // one K atom of A: 128 rows x 128 B
+  constexpr int B_ATOM_BYTES = BN * 128;
+  constexpr int A_STAGE_BYTES = KA * A_ATOM_BYTES;
+  constexpr int B_STAGE_BYTES = KA * B_ATOM_BYTES;
   constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 256 ? 256 : 512);  // power of two
   constexpr uint32_t IDESC = umma_idesc(InTraits<TIn>::FMT, BN);
@@ -496,7 +502,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * GEMM_A_STAGE_BYTES;
+  uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
   uint8_t* sOut = sB + STAGES * B_STAGE_BYTES;   // per-warp output staging boxes (1024-byte aligned)
   uint64_t* full = reinterpret_cast<uint64_t*>(sOut + GEMM_OUT_STAGE_BYTES);
   uint64_t* empty = full + STAGES;
@@ -542,7 +548,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       int n_tile = blockIdx.x % a.n_tiles, rest = blockIdx.x / a.n_tiles;
       const int dn = gridDim.x % a.n_tiles, dr = gridDim.x / a.n_tiles;
       const bool no_tma = (a.debug & 5) != 0;
+      int at = 0, n_at = 0;   // atoms issued into / planned for the current stage
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        int left = nk;
         const int m_tile = rest % a.m_tiles;
         const int g = rest / a.m_tiles;
         const int n0 = n_tile * BN;
@@ -553,17 +561,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           for (int tp = 0; tp < a.taps; ++tp) {
             const int tap_p = a.tap_p[tp], tap_t = t_base + a.tap_t[tp];
             for (int cb = 0; cb < a.cblocks; ++cb, kb += KE) {
-              mbar_wait(&empty[s], ph ^ 1);
-              if (no_tma) {
-                mbar_arrive(&full[s]);
-              } else {
-                mbar_arrive_expect_tx(&full[s], a.a_box_bytes + B_STAGE_BYTES);
-                tma_load_5d(sA + s * GEMM_A_STAGE_BYTES, &a.tmA, &full[s], pa + cb * KE, tap_p, tap_t, b_base, g_a);
-                tma_load_2d(sB + s * B_STAGE_BYTES, &a.tmB, &full[s], kb, g_b);
+              if (at == 0) {   // open a stage: it will receive min(KA, k-blocks left in this tile) atoms
+                n_at = left < KA ? left : KA;
+                mbar_wait(&empty[s], ph ^ 1);
+                if (no_tma) mbar_arrive(&full[s]);
+                else mbar_arrive_expect_tx(&full[s], n_at * (a.a_box_bytes + B_ATOM_BYTES));
               }
-              if (++s == STAGES) {
-                s = 0;
-                ph ^= 1;
+              if (!no_tma) {
+                tma_load_5d(sA + s * A_STAGE_BYTES + at * A_ATOM_BYTES, &a.tmA, &full[s], pa + cb * KE, tap_p, tap_t, b_base, g_a);
+                tma_load_2d(sB + s * B_STAGE_BYTES + at * B_ATOM_BYTES, &a.tmB, &full[s], kb, g_b);
+              }
+              --left;
+              if (++at == n_at) {
+                at = 0;
+                if (++s == STAGES) {
+                  s = 0;
+                  ph ^= 1;
+                }
               }
             }
           }
@@ -587,18 +601,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-        for (int i = 0; i < nk; ++i) {
+        for (int i = 0; i < nk; i += KA) {
+          const int n_at = (nk - i) < KA ? (nk - i) : KA;
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint64_t adesc = umma_smem_desc_sw128(smem_u32(sA + s * GEMM_A_STAGE_BYTES));
-          const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sB + s * B_STAGE_BYTES));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 x (32 bytes of K) per 128-byte swizzle row
-            if (no_mma) break;
-            if constexpr (sizeof(TIn) == 2)
-              umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (i | k) != 0);
-            else
-              umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (i | k) != 0);
+          for (int at = 0; at < KA; ++at) {
+            if (at >= n_at || no_mma) break;
+            const uint64_t adesc = umma_smem_desc_sw128(smem_u32(sA + s * A_STAGE_BYTES + at * A_ATOM_BYTES));
+            const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sB + s * B_STAGE_BYTES + at * B_ATOM_BYTES));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // 4 x (32 bytes of K) per 128-byte swizzle row
+              if constexpr (sizeof(TIn) == 2)
+                umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (i | at | k) != 0);
+              else
+                umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (i | at | k) != 0);
+            }
           }
           umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
           if (++s == STAGES) {

@@ -116,30 +116,31 @@ struct GemmVariant {
   bool attr_set;
 };
 
-template <typename TIn, int BN, int MODE, typename TOut, int STAGES>
+template <typename TIn, int BN, int MODE, typename TOut, int STAGES, int KA>
 GemmVariant make_variant() {
   GemmVariant v;
-  v.fn = vt::gemm_tc_kernel<TIn, BN, MODE, TOut, STAGES, (sizeof(TIn) == 4)>;
-  v.smem = vt::gemm_smem_bytes<BN, STAGES, MODE>();
-  static_assert(vt::gemm_smem_bytes<BN, STAGES, MODE>() <= 227 * 1024, "shared memory budget");
+  v.fn = vt::gemm_tc_kernel<TIn, BN, MODE, TOut, STAGES, (sizeof(TIn) == 4), KA>;
+  v.smem = vt::gemm_smem_bytes<BN, STAGES, MODE, KA>();
+  static_assert(vt::gemm_smem_bytes<BN, STAGES, MODE, KA>() <= 227 * 1024, "shared memory budget");
   v.attr_set = false;
   return v;
 }
 
+// (stages x K atoms per stage) per tile width: ~190 KB of operand ring, two atoms per barrier round
 GemmVariant* gemm_variant(int in_dtype, int bn, int epi, int out_dtype) {
   using bf = __nv_bfloat16;
-  static GemmVariant v_b_256_l_b = make_variant<bf, 256, vt::EPI_LINEAR, bf, VT_GEMM_TMA_STORE ? 3 : 4>();
-  static GemmVariant v_b_256_l_f = make_variant<bf, 256, vt::EPI_LINEAR, float, VT_GEMM_TMA_STORE ? 3 : 4>();
-  static GemmVariant v_b_192_l_b = make_variant<bf, 192, vt::EPI_LINEAR, bf, VT_GEMM_TMA_STORE ? 3 : 5>();
-  static GemmVariant v_b_192_l_f = make_variant<bf, 192, vt::EPI_LINEAR, float, VT_GEMM_TMA_STORE ? 3 : 5>();
-  static GemmVariant v_b_128_l_b = make_variant<bf, 128, vt::EPI_LINEAR, bf, VT_GEMM_TMA_STORE ? 4 : 6>();
-  static GemmVariant v_b_128_l_f = make_variant<bf, 128, vt::EPI_LINEAR, float, VT_GEMM_TMA_STORE ? 4 : 6>();
-  static GemmVariant v_b_32_l_b = make_variant<bf, 32, vt::EPI_LINEAR, bf, 6>();
-  static GemmVariant v_b_32_l_f = make_variant<bf, 32, vt::EPI_LINEAR, float, 6>();
-  static GemmVariant v_b_128_g_b = make_variant<bf, 128, vt::EPI_GN, bf, VT_GEMM_TMA_STORE ? 4 : 6>();
-  static GemmVariant v_f_128_l_f = make_variant<float, 128, vt::EPI_LINEAR, float, VT_GEMM_TMA_STORE ? 4 : 6>();
-  static GemmVariant v_f_32_l_f = make_variant<float, 32, vt::EPI_LINEAR, float, 6>();
-  static GemmVariant v_f_128_g_f = make_variant<float, 128, vt::EPI_GN, float, VT_GEMM_TMA_STORE ? 4 : 6>();
+  static GemmVariant v_b_256_l_b = make_variant<bf, 256, vt::EPI_LINEAR, bf, 2, 2>();
+  static GemmVariant v_b_256_l_f = make_variant<bf, 256, vt::EPI_LINEAR, float, 2, 2>();
+  static GemmVariant v_b_192_l_b = make_variant<bf, 192, vt::EPI_LINEAR, bf, 2, 2>();
+  static GemmVariant v_b_192_l_f = make_variant<bf, 192, vt::EPI_LINEAR, float, 2, 2>();
+  static GemmVariant v_b_128_l_b = make_variant<bf, 128, vt::EPI_LINEAR, bf, 3, 2>();
+  static GemmVariant v_b_128_l_f = make_variant<bf, 128, vt::EPI_LINEAR, float, 3, 2>();
+  static GemmVariant v_b_32_l_b = make_variant<bf, 32, vt::EPI_LINEAR, bf, 4, 2>();
+  static GemmVariant v_b_32_l_f = make_variant<bf, 32, vt::EPI_LINEAR, float, 4, 2>();
+  static GemmVariant v_b_128_g_b = make_variant<bf, 128, vt::EPI_GN, bf, 3, 2>();
+  static GemmVariant v_f_128_l_f = make_variant<float, 128, vt::EPI_LINEAR, float, 3, 2>();
+  static GemmVariant v_f_32_l_f = make_variant<float, 32, vt::EPI_LINEAR, float, 4, 2>();
+  static GemmVariant v_f_128_g_f = make_variant<float, 128, vt::EPI_GN, float, 3, 2>();
   if (in_dtype == VT_BF16) {
     if (epi == VT_EPI_GN) {
       if (out_dtype != VT_BF16) return nullptr;
