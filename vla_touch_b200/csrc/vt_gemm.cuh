@@ -59,6 +59,7 @@ struct GemmArgs {
   int ldc;
   long long out_plane;  // >0: also store the tf32 lo-plane at +out_plane (TOut=float split mode)
   int vec;              // 1: rows are 16-byte aligned (ldc/ldres/pointers), 128-bit epilogue accesses allowed
+  int fast;             // 1: every tile is full width, no hi|lo planes, 32-bit row offsets: the transposing epilogue applies
   void* out;
   const float* bias;  // [G][n_pad] or null
   int act;
@@ -105,13 +106,16 @@ __host__ __device__ constexpr int GEMM_WG_SCRATCH_FLOATS(int BN, int MODE) {
 #define VT_GEMM_TMA_STORE 0
 #endif
 constexpr int GEMM_OUT_STAGE_BYTES = VT_GEMM_TMA_STORE ? 8 * 2 * 4096 : 0;
+// Per-warp 32 x 32 fp32 transposition buffer of the coalescing epilogue (8 epilogue warps x 4 KB).
+__host__ __device__ constexpr int GEMM_XPOSE_BYTES(int BN, int MODE) { return (MODE == 0 && BN >= 128) ? 8 * 4096 : 0; }
 
 // KA = number of 128-byte-wide K atoms (64 bf16 / 32 tf32 elements of K each) per pipeline stage.
 // One mbarrier wait + tcgen05.commit per stage costs the single issuing thread ~450 cycles (measured), more than the MMA
 // time of one atom at BN=128, so a stage carries KA atoms (2 x 4 UMMA instructions per barrier round).
-template <int BN, int STAGES, int MODE, int KA>
+template <int BN, int STAGES, int MODE, int KA, int CTAS = 1>
 constexpr int gemm_smem_bytes() {
-  return 1024 /*align slack*/ + STAGES * KA * (GEMM_A_STAGE_BYTES + BN * 128) + GEMM_OUT_STAGE_BYTES + 256 /*barriers*/ +
+  return 1024 /*align slack*/ + STAGES * KA * (GEMM_A_STAGE_BYTES + (BN / CTAS) * 128) + GEMM_OUT_STAGE_BYTES +
+         GEMM_XPOSE_BYTES(BN, MODE) + 256 /*barriers*/ +
          2 * GEMM_WG_SCRATCH_FLOATS(BN, MODE) * 4;
 }
 
@@ -312,6 +316,123 @@ __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// EPI_LINEAR, coalescing variant (a.fast): the accumulator arrives one ROW per lane (tcgen05.ld 32x32b), which makes
+// every direct global access touch 32 different lines.  Each warp therefore transposes its 32 x 32 chunk through a
+// swizzled 4 KB shared-memory buffer; afterwards a lane owns NC = 16 / sizeof(TOut) consecutive columns of 32 / NC rows,
+// so that one warp-wide load / store covers whole 128-byte (fp32) or 64-byte (bf16) row segments, the per-column
+// parameters sit in registers, and the math is packed f32x2:  y = act(acc + bias) * colscale + residual.
+// The residual rows of the next chunk are in flight while the current one is processed; the first chunk's are
+// requested before the accumulator is ready.
+// ------------------------------------------------------------------------------------------------------------
+template <int BN, typename TOut, bool PRECISE>
+__device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTile& t, const float* colv, uint32_t xbuf,
+                                                  uint64_t* acc_full, uint32_t acc_parity) {
+  constexpr int NC = 16 / sizeof(TOut);   // columns per lane after the transpose
+  constexpr int LPR = 32 / NC;            // lanes per row segment (8 / 4)
+  constexpr int RPI = 32 / LPR;           // rows per warp-wide access (4 / 8)
+  constexpr int R = 32 / RPI;             // rows per lane (8 / 4)
+  constexpr int NV = NC / 4;              // float4 pieces per lane row
+  const int lane = threadIdx.x & 31;
+  const int sr = lane / LPR, cg = lane % LPR;
+  const int act = a.act;
+  const long long wrow0 = t.grow - lane;            // first logical row of this warp
+  const int trow0 = t.r - lane;                     // ... and its row inside the tile
+  TOut* outp = reinterpret_cast<TOut*>(a.out) + (long long)t.g * a.out_g + t.n0 + cg * NC;
+  const float* resp = a.res ? reinterpret_cast<const float*>(a.res) + (long long)t.g * a.res_g + t.n0 + cg * NC : nullptr;
+  int ooff[R], roff[R];
+  uint32_t rd[R], vmask = 0;
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const int row = i * RPI + sr;
+    const long long grow = wrow0 + row;
+    const bool ok = (trow0 + row < a.rows_valid) && (grow < a.M_total);
+    const long long q = grow / a.row_div, rem = grow - q * a.row_div;
+    ooff[i] = ok ? (int)((q * a.out_q + rem * a.out_r + a.out_off) * a.ldc) : 0;
+    roff[i] = ok ? (int)((q * a.res_q + rem * a.res_r + a.res_off) * a.ldres) : 0;
+    vmask |= ok ? (1u << i) : 0u;
+    rd[i] = xbuf + row * 128 + (((NV * cg) ^ (row & 7)) << 4);
+  }
+  const uint32_t wr = xbuf + lane * 128;
+  const int sw = lane & 7;
+  float4 rb[R * NV];
+  auto fetch = [&](int c) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+#pragma unroll
+      for (int h = 0; h < NV; ++h)
+        rb[i * NV + h] = (resp && ((vmask >> i) & 1)) ? *reinterpret_cast<const float4*>(resp + roff[i] + c + 4 * h)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  fetch(0);
+  mbar_wait(acc_full, acc_parity);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = 0; c < BN; c += 32) {
+    uint32_t v[32];
+    tmem_ld32(t.taddr + c, v);
+    float4 bs[NV], sc[NV];
+#pragma unroll
+    for (int h = 0; h < NV; ++h) {
+      bs[h] = *reinterpret_cast<const float4*>(colv + c + cg * NC + 4 * h);
+      sc[h] = *reinterpret_cast<const float4*>(colv + BN + c + cg * NC + 4 * h);
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) st_shared_v4(wr + ((j ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+    float4 x[R * NV];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      x[i * NV] = ld_shared_v4f(rd[i]);
+      if constexpr (NV == 2) x[i * NV + 1] = ld_shared_v4f(rd[i] ^ 16u);   // piece 2cg+1: same row, the neighbouring 16 bytes
+    }
+    __syncwarp();
+    float4 rc[R * NV];
+#pragma unroll
+    for (int i = 0; i < R * NV; ++i) rc[i] = rb[i];
+    if (c + 32 < BN) fetch(c + 32);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      float4 y[NV];
+#pragma unroll
+      for (int h = 0; h < NV; ++h) {
+        const float4 xv = x[i * NV + h];
+        float2 z0 = fadd2(make_float2(xv.x, xv.y), make_float2(bs[h].x, bs[h].y));
+        float2 z1 = fadd2(make_float2(xv.z, xv.w), make_float2(bs[h].z, bs[h].w));
+        if (act == ACT_GELU) {
+          z0.x = PRECISE ? gelu_erf(z0.x) : gelu_fast(z0.x);
+          z0.y = PRECISE ? gelu_erf(z0.y) : gelu_fast(z0.y);
+          z1.x = PRECISE ? gelu_erf(z1.x) : gelu_fast(z1.x);
+          z1.y = PRECISE ? gelu_erf(z1.y) : gelu_fast(z1.y);
+        } else if (act == ACT_MISH) {
+          z0.x = PRECISE ? mish_precise(z0.x) : mish_f(z0.x);
+          z0.y = PRECISE ? mish_precise(z0.y) : mish_f(z0.y);
+          z1.x = PRECISE ? mish_precise(z1.x) : mish_f(z1.x);
+          z1.y = PRECISE ? mish_precise(z1.y) : mish_f(z1.y);
+        }
+        const float4 r = rc[i * NV + h];
+        const float2 y0 = ffma2(z0, make_float2(sc[h].x, sc[h].y), make_float2(r.x, r.y));
+        const float2 y1 = ffma2(z1, make_float2(sc[h].z, sc[h].w), make_float2(r.z, r.w));
+        y[h] = make_float4(y0.x, y0.y, y1.x, y1.y);
+      }
+      if ((vmask >> i) & 1) {
+        if constexpr (sizeof(TOut) == 4) {
+          *reinterpret_cast<float4*>(outp + ooff[i] + c) = y[0];
+        } else {
+          uint4 w;
+          w.x = pack_bf16x2(y[0].x, y[0].y);
+          w.y = pack_bf16x2(y[0].z, y[0].w);
+          w.z = pack_bf16x2(y[1].x, y[1].y);
+          w.w = pack_bf16x2(y[1].z, y[1].w);
+          *reinterpret_cast<uint4*>(outp + ooff[i] + c) = w;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // EPI_GN: GroupNorm(8) + Mish + FiLM | residual.  Tile = all T rows of `rows_valid / gn_rows` samples x 128 channels =
 // whole groups, so the statistics are tile-local.  Pass 1: per-row partial sums per 32-column chunk, reduced over the
 // rows of a sample with warp shuffles (power-of-two T <= 32, or T a multiple of 32) or through shared memory.
@@ -485,18 +606,20 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
   }
 }
 
-template <typename TIn, int BN, int MODE, typename TOut, int STAGES, bool PRECISE, int KA>
+template <typename TIn, int BN, int MODE, typename TOut, int STAGES, bool PRECISE, int KA, int CTAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs a) {
   constexpr int KE = InTraits<TIn>::KE;
   constexpr int A_ATOM_BYTES = GEMM_A_STAGE_BYTES;   // one K atom of A: 128 rows x 128 B
-  constexpr int B_ATOM_BYTES = BN * 128;
+  constexpr int B_ROWS = BN / CTAS;                  // rows of B this CTA holds (a pair splits the tile's N)
+  constexpr int B_ATOM_BYTES = B_ROWS * 128;
   constexpr int A_STAGE_BYTES = KA * A_ATOM_BYTES;
   constexpr int B_STAGE_BYTES = KA * B_ATOM_BYTES;
   constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 256 ? 256 : 512);  // power of two
-  constexpr uint32_t IDESC = umma_idesc(InTraits<TIn>::FMT, BN);
+  constexpr uint32_t IDESC = umma_idesc(InTraits<TIn>::FMT, BN, 0, 0, 128 * CTAS);
   static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 192 || BN == 256, "BN");
   static_assert(MODE != EPI_GN || BN == 128 || BN == 256, "GN epilogue: whole groups per tile");
+  static_assert(CTAS == 1 || (CTAS == 2 && sizeof(TIn) == 2 && BN % 32 == 0), "CTA pairs: bf16 operands");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -504,7 +627,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
   uint8_t* sOut = sB + STAGES * B_STAGE_BYTES;   // per-warp output staging boxes (1024-byte aligned)
-  uint64_t* full = reinterpret_cast<uint64_t*>(sOut + GEMM_OUT_STAGE_BYTES);
+  uint8_t* sX = sOut + GEMM_OUT_STAGE_BYTES;      // per-warp transposition buffers of the coalescing epilogue
+  uint64_t* full = reinterpret_cast<uint64_t*>(sX + GEMM_XPOSE_BYTES(BN, MODE));
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;   // [2]
   uint64_t* acc_empty = acc_full + 2;    // [2]
@@ -513,6 +637,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = a.passes * a.taps * a.cblocks;
+  // A pair (cluster of two CTAs, CTAS == 2) works on two vertically adjacent 128-row tiles as ONE M = 256 MMA:
+  // rank 0 (the leader) issues the MMAs and owns the `full` barriers, both CTAs load their own operand halves.
+  const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
+  const int worker = blockIdx.x / CTAS, n_workers = gridDim.x / CTAS;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.tmA);
@@ -527,16 +655,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&acc_full[s], 1);
-        mbar_init(&acc_empty[s], 128);
+        mbar_init(&acc_empty[s], 4 * CTAS);   // one arrival per epilogue warp of every CTA of the pair
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CTAS == 2) {
+      tmem_alloc_pair(tmem_slot, TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -545,16 +678,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;   // ring position kept incrementally: no divisions in this loop
-      int n_tile = blockIdx.x % a.n_tiles, rest = blockIdx.x / a.n_tiles;
-      const int dn = gridDim.x % a.n_tiles, dr = gridDim.x / a.n_tiles;
+      int n_tile = worker % a.n_tiles, rest = worker / a.n_tiles;
+      const int dn = n_workers % a.n_tiles, dr = n_workers / a.n_tiles;
       const bool no_tma = (a.debug & 5) != 0;
       int at = 0, n_at = 0;   // atoms issued into / planned for the current stage
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < a.total_tiles; tile += n_workers) {
         int left = nk;
-        const int m_tile = rest % a.m_tiles;
+        const int m_tile = (rest % a.m_tiles) * CTAS + rank;
         const int g = rest / a.m_tiles;
         const int n0 = n_tile * BN;
-        const int t_base = m_tile * a.m_t_step, b_base = m_tile * a.m_b_step, g_a = g * a.a_g_mul, g_b = g * a.n_pad + n0;
+        const int t_base = m_tile * a.m_t_step, b_base = m_tile * a.m_b_step, g_a = g * a.a_g_mul;
+        const int g_b = g * a.n_pad + n0 + rank * B_ROWS;
         for (int pass = 0; pass < a.passes; ++pass) {
           const int pa = a.a_c0 + ((pass == 1) ? a.a_plane : 0);
           int kb = (pass == 2) ? a.b_plane : 0;
@@ -564,12 +698,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               if (at == 0) {   // open a stage: it will receive min(KA, k-blocks left in this tile) atoms
                 n_at = left < KA ? left : KA;
                 mbar_wait(&empty[s], ph ^ 1);
-                if (no_tma) mbar_arrive(&full[s]);
-                else mbar_arrive_expect_tx(&full[s], n_at * (a.a_box_bytes + B_ATOM_BYTES));
+                if (rank == 0) {   // the leader's barrier counts the bytes of both CTAs
+                  if (no_tma) mbar_arrive(&full[s]);
+                  else mbar_arrive_expect_tx(&full[s], n_at * CTAS * (a.a_box_bytes + B_ATOM_BYTES));
+                }
               }
               if (!no_tma) {
-                tma_load_5d(sA + s * A_STAGE_BYTES + at * A_ATOM_BYTES, &a.tmA, &full[s], pa + cb * KE, tap_p, tap_t, b_base, g_a);
-                tma_load_2d(sB + s * B_STAGE_BYTES + at * B_ATOM_BYTES, &a.tmB, &full[s], kb, g_b);
+                if constexpr (CTAS == 2) {
+                  const uint32_t fb = mapa_shared(smem_u32(&full[s]), 0);
+                  tma_load_5d_pair(sA + s * A_STAGE_BYTES + at * A_ATOM_BYTES, &a.tmA, fb, pa + cb * KE, tap_p, tap_t, b_base, g_a);
+                  tma_load_2d_pair(sB + s * B_STAGE_BYTES + at * B_ATOM_BYTES, &a.tmB, fb, kb, g_b);
+                } else {
+                  tma_load_5d(sA + s * A_STAGE_BYTES + at * A_ATOM_BYTES, &a.tmA, &full[s], pa + cb * KE, tap_p, tap_t, b_base, g_a);
+                  tma_load_2d(sB + s * B_STAGE_BYTES + at * B_ATOM_BYTES, &a.tmB, &full[s], kb, g_b);
+                }
               }
               --left;
               if (++at == n_at) {
@@ -591,14 +733,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ UMMA issuer ------------------------------
-    if (lane == 0) {
+    // ------------------------------ UMMA issuer (leader CTA only) ------------------------------
+    if (lane == 0 && rank == 0) {
       uint32_t lt = 0, ph = 0;
       int s = 0;
       const bool no_mma = (a.debug & 9) != 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
+      for (int tile = worker; tile < a.total_tiles; tile += n_workers, ++lt) {
         const uint32_t acc = lt & 1;
-        mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+        mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);  // the epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
         for (int i = 0; i < nk; i += KA) {
@@ -612,19 +754,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sB + s * B_STAGE_BYTES + at * B_ATOM_BYTES));
 #pragma unroll
             for (int k = 0; k < 4; ++k) {  // 4 x (32 bytes of K) per 128-byte swizzle row
-              if constexpr (sizeof(TIn) == 2)
+              if constexpr (CTAS == 2)
+                umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (i | at | k) != 0);
+              else if constexpr (sizeof(TIn) == 2)
                 umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (i | at | k) != 0);
               else
                 umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (i | at | k) != 0);
             }
           }
-          umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+          // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+          if constexpr (CTAS == 2) umma_commit_pair(&empty[s], 3); else umma_commit(&empty[s]);
           if (++s == STAGES) {
             s = 0;
             ph ^= 1;
           }
         }
-        umma_commit(&acc_full[acc]);
+        if constexpr (CTAS == 2) umma_commit_pair(&acc_full[acc], 3); else umma_commit(&acc_full[acc]);
       }
     }
   } else {
@@ -642,11 +787,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     st.base = smem_u32(sOut) + (warp - 2) * 8192;
     st.count = 0;
     uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
+    const uint32_t acc_empty_leader = CTAS == 2 ? mapa_shared(smem_u32(&acc_empty[wg]), 0) : 0u;
+    for (int tile = worker; tile < a.total_tiles; tile += n_workers, ++lt) {
       if ((lt & 1) != (uint32_t)wg) continue;
       const int n_tile = tile % a.n_tiles;
       const int rest = tile / a.n_tiles;
-      const int m_tile = rest % a.m_tiles;
+      const int m_tile = (rest % a.m_tiles) * CTAS + rank;
       t.g = rest / a.m_tiles;
       t.n0 = n_tile * BN;
       // stage the per-column vectors of this tile (previous tile's readers are done: barrier first)
@@ -677,19 +823,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       if (a.debug & 2) {
         mbar_wait(&acc_full[wg], parity);
         tc_fence_after();
-      } else if constexpr (MODE == EPI_LINEAR)
-        epilogue_linear<BN, TOut, PRECISE>(a, t, colv, &acc_full[wg], parity, st);
-      else
+      } else if constexpr (MODE == EPI_LINEAR) {
+        if (GEMM_XPOSE_BYTES(BN, MODE) > 0 && a.fast)
+          epilogue_linear_t<BN, TOut, PRECISE>(a, t, colv, smem_u32(sX) + (warp - 2) * 4096, &acc_full[wg], parity);
+        else
+          epilogue_linear<BN, TOut, PRECISE>(a, t, colv, &acc_full[wg], parity, st);
+      } else
         epilogue_gn<BN, TOut, PRECISE>(a, t, colv, gn_part, gn_stat, et, bar_id, &acc_full[wg], parity, st);
       tc_fence_before();
-      mbar_arrive(&acc_empty[wg]);
+      __syncwarp();
+      if (lane == 0) {   // this warp's quarter of the accumulator has been read out
+        if constexpr (CTAS == 2) mbar_arrive_cluster(acc_empty_leader); else mbar_arrive(&acc_empty[wg]);
+      }
     }
     if (a.tma_out && lane == 0) bulk_wait_all();   // staged boxes must be drained before the CTA exits
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();   // the peer may still signal / read this CTA
+  if (warp == 1) {
+    if constexpr (CTAS == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 }  // namespace vt

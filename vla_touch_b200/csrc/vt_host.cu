@@ -113,39 +113,51 @@ typedef void (*GemmKernel)(const vt::GemmArgs);
 struct GemmVariant {
   GemmKernel fn;
   int smem;
+  int ctas;   // 1, or 2 = CTA pairs (cluster of two, tcgen05 cta_group::2, M = 256 per MMA)
   bool attr_set;
 };
 
-template <typename TIn, int BN, int MODE, typename TOut, int STAGES, int KA>
+template <typename TIn, int BN, int MODE, typename TOut, int STAGES, int KA, int CTAS = 1>
 GemmVariant make_variant() {
   GemmVariant v;
-  v.fn = vt::gemm_tc_kernel<TIn, BN, MODE, TOut, STAGES, (sizeof(TIn) == 4), KA>;
-  v.smem = vt::gemm_smem_bytes<BN, STAGES, MODE, KA>();
-  static_assert(vt::gemm_smem_bytes<BN, STAGES, MODE, KA>() <= 227 * 1024, "shared memory budget");
+  v.fn = vt::gemm_tc_kernel<TIn, BN, MODE, TOut, STAGES, (sizeof(TIn) == 4), KA, CTAS>;
+  v.smem = vt::gemm_smem_bytes<BN, STAGES, MODE, KA, CTAS>();
+  static_assert(vt::gemm_smem_bytes<BN, STAGES, MODE, KA, CTAS>() <= 227 * 1024, "shared memory budget");
+  v.ctas = CTAS;
   v.attr_set = false;
   return v;
 }
 
-// (stages x K atoms per stage) per tile width: ~190 KB of operand ring, two atoms per barrier round
-GemmVariant* gemm_variant(int in_dtype, int bn, int epi, int out_dtype) {
+// (stages x K atoms per stage) per tile width: ~190 KB of operand ring, two atoms per barrier round.
+// `pair` selects the CTA-pair kernels (bf16, bn 192 / 256): each CTA stages its 128 rows of A and HALF of the B tile, so
+// the operand bytes per MMA cycle that cross L2 -> shared memory halve against the single-CTA 128 x bn tile.
+GemmVariant* gemm_variant(int in_dtype, int bn, int epi, int out_dtype, bool pair) {
   using bf = __nv_bfloat16;
-  static GemmVariant v_b_256_l_b = make_variant<bf, 256, vt::EPI_LINEAR, bf, 2, 2>();
-  static GemmVariant v_b_256_l_f = make_variant<bf, 256, vt::EPI_LINEAR, float, 2, 2>();
+  static GemmVariant v_b_256_l_b = make_variant<bf, 256, vt::EPI_LINEAR, bf, 3, 1>();
+  static GemmVariant v_b_256_l_f = make_variant<bf, 256, vt::EPI_LINEAR, float, 3, 1>();
   static GemmVariant v_b_192_l_b = make_variant<bf, 192, vt::EPI_LINEAR, bf, 2, 2>();
   static GemmVariant v_b_192_l_f = make_variant<bf, 192, vt::EPI_LINEAR, float, 2, 2>();
-  static GemmVariant v_b_128_l_b = make_variant<bf, 128, vt::EPI_LINEAR, bf, 3, 2>();
-  static GemmVariant v_b_128_l_f = make_variant<bf, 128, vt::EPI_LINEAR, float, 3, 2>();
+  static GemmVariant v_b_128_l_b = make_variant<bf, 128, vt::EPI_LINEAR, bf, 5, 1>();
+  static GemmVariant v_b_128_l_f = make_variant<bf, 128, vt::EPI_LINEAR, float, 5, 1>();
   static GemmVariant v_b_32_l_b = make_variant<bf, 32, vt::EPI_LINEAR, bf, 4, 2>();
   static GemmVariant v_b_32_l_f = make_variant<bf, 32, vt::EPI_LINEAR, float, 4, 2>();
   static GemmVariant v_b_128_g_b = make_variant<bf, 128, vt::EPI_GN, bf, 3, 2>();
-  static GemmVariant v_f_128_l_f = make_variant<float, 128, vt::EPI_LINEAR, float, 3, 2>();
+  static GemmVariant v_f_128_l_f = make_variant<float, 128, vt::EPI_LINEAR, float, 5, 1>();
   static GemmVariant v_f_32_l_f = make_variant<float, 32, vt::EPI_LINEAR, float, 4, 2>();
   static GemmVariant v_f_128_g_f = make_variant<float, 128, vt::EPI_GN, float, 3, 2>();
+  static GemmVariant p_b_256_l_b = make_variant<bf, 256, vt::EPI_LINEAR, bf, 5, 1, 2>();
+  static GemmVariant p_b_256_l_f = make_variant<bf, 256, vt::EPI_LINEAR, float, 5, 1, 2>();
+  static GemmVariant p_b_192_l_b = make_variant<bf, 192, vt::EPI_LINEAR, bf, 3, 2, 2>();
+  static GemmVariant p_b_192_l_f = make_variant<bf, 192, vt::EPI_LINEAR, float, 3, 2, 2>();
+  static GemmVariant p_b_256_g_b = make_variant<bf, 256, vt::EPI_GN, bf, 3, 2, 2>();
   if (in_dtype == VT_BF16) {
     if (epi == VT_EPI_GN) {
       if (out_dtype != VT_BF16) return nullptr;
+      if (bn == 256) return pair ? &p_b_256_g_b : nullptr;
       return bn == 128 ? &v_b_128_g_b : nullptr;
     }
+    if (pair && bn == 256) return out_dtype == VT_BF16 ? &p_b_256_l_b : &p_b_256_l_f;
+    if (pair && bn == 192) return out_dtype == VT_BF16 ? &p_b_192_l_b : &p_b_192_l_f;
     if (bn == 256) return out_dtype == VT_BF16 ? &v_b_256_l_b : &v_b_256_l_f;
     if (bn == 192) return out_dtype == VT_BF16 ? &v_b_192_l_b : &v_b_192_l_f;
     if (bn == 128) return out_dtype == VT_BF16 ? &v_b_128_l_b : &v_b_128_l_f;
@@ -178,7 +190,25 @@ struct GemmOp : Op {
       VT_CUDA(cudaFuncSetAttribute(var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, var->smem));
       var->attr_set = true;
     }
-    var->fn<<<grid, vt::GEMM_THREADS, var->smem, s>>>(args);
+    if (var->ctas == 2) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = grid;
+      cfg.blockDim = dim3(vt::GEMM_THREADS, 1, 1);
+      cfg.dynamicSmemBytes = (size_t)var->smem;
+      cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, var->fn, args);
+      if (e != cudaSuccess) return fail(VT_E_CUDA, "gemm_tc_kernel (CTA pairs) launch: %s", cudaGetErrorString(e));
+    } else {
+      var->fn<<<grid, vt::GEMM_THREADS, var->smem, s>>>(args);
+    }
     VT_LAUNCH_CHECK("gemm_tc_kernel");
     return VT_OK;
   }
@@ -204,7 +234,12 @@ int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
   VT_REQUIRE(d.w_ld >= d.taps * d.kc, "gemm: w_ld=%d < taps*kc=%d", d.w_ld, d.taps * d.kc);
   VT_REQUIRE(d.a_P >= 1 && d.a_T >= 1 && d.a_B >= 1 && d.a_C >= 1, "gemm: bad A extents");
   VT_REQUIRE(d.row_div >= 1, "gemm: row_div=%d", d.row_div);
-  GemmVariant* var = gemm_variant(d.in_dtype, d.bn, d.epi, d.out_dtype);
+  // CTA pairs whenever the shape has at least two row tiles (env VT_GEMM_PAIR=0 keeps the single-CTA kernels: A/B runs)
+  const int m_tiles_1 = (d.M + d.t_box * d.b_box - 1) / (d.t_box * d.b_box);
+  static const bool pair_enabled = !(getenv("VT_GEMM_PAIR") && atoi(getenv("VT_GEMM_PAIR")) == 0);
+  bool pair = pair_enabled && d.in_dtype == VT_BF16 && (d.bn == 256 || d.bn == 192) && m_tiles_1 >= 2 && d.passes == 1;
+  if (d.epi == VT_EPI_GN && d.bn == 256) pair = true;   // the 256-wide GroupNorm epilogue exists as a pair kernel only
+  GemmVariant* var = gemm_variant(d.in_dtype, d.bn, d.epi, d.out_dtype, pair);
   if (!var) return fail(VT_E_UNSUPPORTED, "gemm: no kernel for in=%d bn=%d epi=%d out=%d", d.in_dtype, d.bn, d.epi, d.out_dtype);
 
   vt::GemmArgs& a = op->args;
@@ -231,7 +266,7 @@ int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
   {
     const uint64_t dims[2] = {(uint64_t)d.w_ld, (uint64_t)d.G * d.n_pad};
     const uint64_t st[1] = {(uint64_t)d.w_ld * es};
-    const uint32_t box[2] = {(uint32_t)KE, (uint32_t)d.bn};
+    const uint32_t box[2] = {(uint32_t)KE, (uint32_t)(d.bn / var->ctas)};   // a pair splits the tile's N rows of B
     int rc = make_tmap(&a.tmB, d.in_dtype, 2, d.w, dims, st, box);
     if (rc) return rc;
   }
@@ -283,6 +318,17 @@ int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
     vec = vec && aligned16(d.res) && d.ldres % rv == 0 && d.res_g % rv == 0;
   }
   a.vec = vec ? 1 : 0;
+  {  // coalescing epilogue: full-width tiles, plain (no hi|lo plane) output, row offsets that fit 32 bits
+    auto span = [&](long long q, long long r, long long off, long long ld) {
+      return (((long long)d.M / d.row_div + 1) * (q < 0 ? -q : q) + (long long)d.row_div * (r < 0 ? -r : r) + off + 1) * ld;
+    };
+    bool fast = vec && d.epi == VT_EPI_LINEAR && d.bn >= 128 && d.N % d.bn == 0 && d.out_plane == 0 && d.res_plane == 0 &&
+                d.out_q >= 0 && d.out_r >= 0 && d.out_off >= 0 && span(d.out_q, d.out_r, d.out_off, d.ldc) < (1ll << 31);
+    if (d.res) fast = fast && d.res_q >= 0 && d.res_r >= 0 && d.res_off >= 0 && span(d.res_q, d.res_r, d.res_off, d.ldres) < (1ll << 31);
+    const char* nf = getenv("VT_GEMM_FAST");
+    if (nf && atoi(nf) == 0) fast = false;
+    a.fast = fast ? 1 : 0;
+  }
   if (d.epi == VT_EPI_GN) {
     VT_REQUIRE(d.gn_gamma && d.gn_beta, "gemm: GroupNorm epilogue needs gamma/beta");
     VT_REQUIRE(d.gn_group_ch == 32 || d.gn_group_ch == 64, "gemm: gn_group_ch=%d", d.gn_group_ch);
@@ -326,13 +372,16 @@ int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
       }
     }
   }
-  const long long total = (long long)m_tiles * n_tiles * d.G;
+  // work units: one 128-row tile per CTA, or two vertically adjacent tiles per CTA pair (a missing second tile is all
+  // out-of-bounds: zero-filled by TMA, masked in the epilogue)
+  const int m_units = (m_tiles + var->ctas - 1) / var->ctas;
+  const long long total = (long long)m_units * n_tiles * d.G;
   VT_REQUIRE(total < (1ll << 31), "gemm: too many tiles");
   a.n_tiles = n_tiles;
-  a.m_tiles = m_tiles;
+  a.m_tiles = m_units;
   a.total_tiles = (int)total;
-  const int sms = sm_count();
-  op->grid = dim3((unsigned)(total < sms ? total : sms), 1u, 1u);   // persistent: one CTA per SM
+  const int workers = sm_count() / var->ctas;
+  op->grid = dim3((unsigned)(total < workers ? total : workers) * var->ctas, 1u, 1u);   // persistent: one CTA per SM
   return VT_OK;
 }
 

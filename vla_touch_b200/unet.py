@@ -213,8 +213,8 @@ def _conv(plan: Plan, W: UnetWeights, B: int, src: _View, dst: _View, w: torch.T
     """One grouped implicit-GEMM convolution.  src/dst are channel windows of [G][B][T][ld] buffers."""
     m, G = W.mode, W.G
     t_in_q = src.T // phases
-    if bn == 128 and gn is None and not m.precise and n % 256 == 0:
-        bn = 256                                  # wider tile: less A-operand traffic per MAC (GroupNorm tiles stay at 128)
+    if bn == 128 and not m.precise and n % 256 == 0:
+        bn = 256                                  # 256-wide tiles run as CTA pairs (M = 256 MMAs): half the operand bytes per MAC
     b_box = max(1, min(128 // t_out, B, 32 if bn == 128 else 16))
     a_sB = src.T * src.ld
     n_pad = w.shape[1]
