@@ -94,9 +94,11 @@ struct InTraits<float> {
   static constexpr uint32_t FMT = UMMA_FMT_TF32;
 };
 
-// per epilogue warpgroup: 5 column vectors, GroupNorm row partials [128][BN/32] and sample sums [32][BN/32] (float2)
+// two column-vector sets (one per accumulator: 2 x BN LINEAR / 5 x BN GroupNorm), and per epilogue warpgroup the GroupNorm
+// row partials [128][4] and sample sums [64][4] (float2)
+__host__ __device__ constexpr int GEMM_COLV_FLOATS(int BN, int MODE) { return MODE == 0 ? 2 * BN : 5 * BN; }
 __host__ __device__ constexpr int GEMM_WG_SCRATCH_FLOATS(int BN, int MODE) {
-  return MODE == 0 ? 2 * BN : 5 * BN + (128 + 32) * (BN / 32 > 4 ? BN / 32 : 4) * 2;
+  return GEMM_COLV_FLOATS(BN, MODE) + (MODE == 0 ? 0 : (128 + 64) * 4 * 2);
 }
 
 // 8 epilogue warps x 2 boxes of 32 rows x 128 B when the TMA-store epilogue is compiled in.  Measured on B200: the
@@ -220,7 +222,7 @@ struct EpiTile {
 // ------------------------------------------------------------------------------------------------------------
 template <int BN, typename TOut, bool PRECISE>
 __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile& t, const float* colv, uint64_t* acc_full,
-                                                uint32_t acc_parity, OutStage& st) {
+                                                uint32_t acc_parity, OutStage& st, int c_begin, int c_end) {
   // kernel parameters used inside the column loops, pinned in registers (the struct lives in the constant bank and is
   // otherwise re-read after every asm "memory" clobber)
   const int N = a.N, act = a.act, dbg = a.debug;
@@ -242,11 +244,11 @@ __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile
     for (int i = 0; i < 8; ++i)
       rb[i] = (vres && t.n0 + c + 4 * i + 4 <= N) ? *reinterpret_cast<const float4*>(resp + c + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
   };
-  fetch(0);
+  fetch(c_begin);
   mbar_wait(acc_full, acc_parity);
   tc_fence_after();
 #pragma unroll 1
-  for (int c = 0; c < BN; c += 32) {
+  for (int c = c_begin; c < c_end; c += 32) {
     uint32_t v[32];
     if (dbg & 32) {
 #pragma unroll
@@ -257,7 +259,7 @@ __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile
     float4 rc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) rc[i] = rb[i];
-    if (c + 32 < BN) fetch(c + 32);
+    if (c + 32 < c_end) fetch(c + 32);
     if (tma && (c % CG) == 0 && !(dbg & 16)) box = stage_begin(st, lane);
     tmem_ld_wait();
     if (t.valid) {
@@ -310,7 +312,7 @@ __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile
         }
       }
     }
-    if (tma && !(dbg & 16) && (((c + 32) % CG) == 0 || c + 32 >= BN))
+    if (tma && !(dbg & 16) && (((c + 32) % CG) == 0 || c + 32 >= c_end))
       stage_end(st, &a.tmO, box, lane, t.n0 + (c / CG) * CG, row0, t.g);
   }
 }
@@ -320,13 +322,26 @@ __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile
 // every direct global access touch 32 different lines.  Each warp therefore transposes its 32 x 32 chunk through a
 // swizzled 4 KB shared-memory buffer; afterwards a lane owns NC = 16 / sizeof(TOut) consecutive columns of 32 / NC rows,
 // so that one warp-wide load / store covers whole 128-byte (fp32) or 64-byte (bf16) row segments, the per-column
-// parameters sit in registers, and the math is packed f32x2:  y = act(acc + bias) * colscale + residual.
-// The residual rows of the next chunk are in flight while the current one is processed; the first chunk's are
-// requested before the accumulator is ready.
+// parameters are plain (L1-resident) vector loads into registers, and the math is packed f32x2:
+//   y = act(acc + bias) * colscale + residual.
+// Activation and residual are compile-time so the chunk loop is branch-free.  The residual rows of the next chunk are in
+// flight while the current one is processed; the first chunk's are requested before the accumulator is ready.
 // ------------------------------------------------------------------------------------------------------------
-template <int BN, typename TOut, bool PRECISE>
-__device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTile& t, const float* colv, uint32_t xbuf,
-                                                  uint64_t* acc_full, uint32_t acc_parity) {
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {   // same fit as gelu_fast, two lanes per instruction
+  float2 x2 = fmul2(x, x);
+  x2.x = fminf(x2.x, 36.f);
+  x2.y = fminf(x2.y, 36.f);
+  float2 p = ffma2(x2, make_float2(-3.51516795e-4f, -3.51516795e-4f), make_float2(3.70056461e-2f, 3.70056461e-2f));
+  p = ffma2(x2, p, make_float2(7.97507884e-1f, 7.97507884e-1f));
+  const float2 u = fmul2(x, p);
+  const float2 th = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+  const float2 hx = fmul2(x, make_float2(0.5f, 0.5f));
+  return ffma2(hx, th, hx);
+}
+
+template <int BN, typename TOut, bool PRECISE, int ACT, bool HAS_RES>
+__device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTile& t, uint32_t xbuf, uint64_t* acc_full,
+                                                  uint32_t acc_parity, int c_begin, int c_end) {
   constexpr int NC = 16 / sizeof(TOut);   // columns per lane after the transpose
   constexpr int LPR = 32 / NC;            // lanes per row segment (8 / 4)
   constexpr int RPI = 32 / LPR;           // rows per warp-wide access (4 / 8)
@@ -334,11 +349,12 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTi
   constexpr int NV = NC / 4;              // float4 pieces per lane row
   const int lane = threadIdx.x & 31;
   const int sr = lane / LPR, cg = lane % LPR;
-  const int act = a.act;
   const long long wrow0 = t.grow - lane;            // first logical row of this warp
   const int trow0 = t.r - lane;                     // ... and its row inside the tile
   TOut* outp = reinterpret_cast<TOut*>(a.out) + (long long)t.g * a.out_g + t.n0 + cg * NC;
-  const float* resp = a.res ? reinterpret_cast<const float*>(a.res) + (long long)t.g * a.res_g + t.n0 + cg * NC : nullptr;
+  const float* resp = HAS_RES ? reinterpret_cast<const float*>(a.res) + (long long)t.g * a.res_g + t.n0 + cg * NC : nullptr;
+  const float* biasp = a.bias ? a.bias + (long long)t.g * a.n_pad + t.n0 + cg * NC : nullptr;
+  const float* scalep = a.colscale ? a.colscale + t.n0 + cg * NC : nullptr;
   int ooff[R], roff[R];
   uint32_t rd[R], vmask = 0;
 #pragma unroll
@@ -348,34 +364,35 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTi
     const bool ok = (trow0 + row < a.rows_valid) && (grow < a.M_total);
     const long long q = grow / a.row_div, rem = grow - q * a.row_div;
     ooff[i] = ok ? (int)((q * a.out_q + rem * a.out_r + a.out_off) * a.ldc) : 0;
-    roff[i] = ok ? (int)((q * a.res_q + rem * a.res_r + a.res_off) * a.ldres) : 0;
+    roff[i] = (ok && HAS_RES) ? (int)((q * a.res_q + rem * a.res_r + a.res_off) * a.ldres) : 0;
     vmask |= ok ? (1u << i) : 0u;
     rd[i] = xbuf + row * 128 + (((NV * cg) ^ (row & 7)) << 4);
   }
   const uint32_t wr = xbuf + lane * 128;
   const int sw = lane & 7;
-  float4 rb[R * NV];
+  float4 rb[HAS_RES ? R * NV : 1];
   auto fetch = [&](int c) {
+    if constexpr (HAS_RES) {
 #pragma unroll
-    for (int i = 0; i < R; ++i) {
+      for (int i = 0; i < R; ++i) {
 #pragma unroll
-      for (int h = 0; h < NV; ++h)
-        rb[i * NV + h] = (resp && ((vmask >> i) & 1)) ? *reinterpret_cast<const float4*>(resp + roff[i] + c + 4 * h)
-                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int h = 0; h < NV; ++h)   // rows that do not exist read row 0 of the tile's column range (valid memory), never stored
+          rb[i * NV + h] = *reinterpret_cast<const float4*>(resp + roff[i] + c + 4 * h);
+      }
     }
   };
-  fetch(0);
+  fetch(c_begin);
   mbar_wait(acc_full, acc_parity);
   tc_fence_after();
 #pragma unroll 1
-  for (int c = 0; c < BN; c += 32) {
+  for (int c = c_begin; c < c_end; c += 32) {
     uint32_t v[32];
     tmem_ld32(t.taddr + c, v);
     float4 bs[NV], sc[NV];
 #pragma unroll
     for (int h = 0; h < NV; ++h) {
-      bs[h] = *reinterpret_cast<const float4*>(colv + c + cg * NC + 4 * h);
-      sc[h] = *reinterpret_cast<const float4*>(colv + BN + c + cg * NC + 4 * h);
+      bs[h] = biasp ? *reinterpret_cast<const float4*>(biasp + c + 4 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
+      sc[h] = scalep ? *reinterpret_cast<const float4*>(scalep + c + 4 * h) : make_float4(1.f, 1.f, 1.f, 1.f);
     }
     tmem_ld_wait();
 #pragma unroll
@@ -388,10 +405,6 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTi
       if constexpr (NV == 2) x[i * NV + 1] = ld_shared_v4f(rd[i] ^ 16u);   // piece 2cg+1: same row, the neighbouring 16 bytes
     }
     __syncwarp();
-    float4 rc[R * NV];
-#pragma unroll
-    for (int i = 0; i < R * NV; ++i) rc[i] = rb[i];
-    if (c + 32 < BN) fetch(c + 32);
 #pragma unroll
     for (int i = 0; i < R; ++i) {
       float4 y[NV];
@@ -400,20 +413,27 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTi
         const float4 xv = x[i * NV + h];
         float2 z0 = fadd2(make_float2(xv.x, xv.y), make_float2(bs[h].x, bs[h].y));
         float2 z1 = fadd2(make_float2(xv.z, xv.w), make_float2(bs[h].z, bs[h].w));
-        if (act == ACT_GELU) {
-          z0.x = PRECISE ? gelu_erf(z0.x) : gelu_fast(z0.x);
-          z0.y = PRECISE ? gelu_erf(z0.y) : gelu_fast(z0.y);
-          z1.x = PRECISE ? gelu_erf(z1.x) : gelu_fast(z1.x);
-          z1.y = PRECISE ? gelu_erf(z1.y) : gelu_fast(z1.y);
-        } else if (act == ACT_MISH) {
-          z0.x = PRECISE ? mish_precise(z0.x) : mish_f(z0.x);
-          z0.y = PRECISE ? mish_precise(z0.y) : mish_f(z0.y);
-          z1.x = PRECISE ? mish_precise(z1.x) : mish_f(z1.x);
-          z1.y = PRECISE ? mish_precise(z1.y) : mish_f(z1.y);
+        if constexpr (ACT == ACT_GELU) {
+          if constexpr (PRECISE) {
+            z0 = make_float2(gelu_erf(z0.x), gelu_erf(z0.y));
+            z1 = make_float2(gelu_erf(z1.x), gelu_erf(z1.y));
+          } else {
+            z0 = gelu_fast2(z0);
+            z1 = gelu_fast2(z1);
+          }
+        } else if constexpr (ACT == ACT_MISH) {
+          z0 = make_float2(PRECISE ? mish_precise(z0.x) : mish_f(z0.x), PRECISE ? mish_precise(z0.y) : mish_f(z0.y));
+          z1 = make_float2(PRECISE ? mish_precise(z1.x) : mish_f(z1.x), PRECISE ? mish_precise(z1.y) : mish_f(z1.y));
         }
-        const float4 r = rc[i * NV + h];
-        const float2 y0 = ffma2(z0, make_float2(sc[h].x, sc[h].y), make_float2(r.x, r.y));
-        const float2 y1 = ffma2(z1, make_float2(sc[h].z, sc[h].w), make_float2(r.z, r.w));
+        float2 y0, y1;
+        if constexpr (HAS_RES) {
+          const float4 r = rb[i * NV + h];
+          y0 = ffma2(z0, make_float2(sc[h].x, sc[h].y), make_float2(r.x, r.y));
+          y1 = ffma2(z1, make_float2(sc[h].z, sc[h].w), make_float2(r.z, r.w));
+        } else {
+          y0 = fmul2(z0, make_float2(sc[h].x, sc[h].y));
+          y1 = fmul2(z1, make_float2(sc[h].z, sc[h].w));
+        }
         y[h] = make_float4(y0.x, y0.y, y1.x, y1.y);
       }
       if ((vmask >> i) & 1) {
@@ -423,12 +443,30 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTi
           uint4 w;
           w.x = pack_bf16x2(y[0].x, y[0].y);
           w.y = pack_bf16x2(y[0].z, y[0].w);
-          w.z = pack_bf16x2(y[1].x, y[1].y);
-          w.w = pack_bf16x2(y[1].z, y[1].w);
+          w.z = pack_bf16x2(y[NV - 1].x, y[NV - 1].y);
+          w.w = pack_bf16x2(y[NV - 1].z, y[NV - 1].w);
           *reinterpret_cast<uint4*>(outp + ooff[i] + c) = w;
         }
       }
     }
+    if (HAS_RES && c + 32 < c_end) fetch(c + 32);   // in flight during the next chunk's TMEM load + transpose
+  }
+}
+
+// runtime (activation, residual) -> compile-time instantiation of the coalescing epilogue
+template <int BN, typename TOut, bool PRECISE>
+__device__ __forceinline__ void epilogue_linear_fast(const GemmArgs& a, const EpiTile& t, uint32_t xbuf, uint64_t* acc_full,
+                                                     uint32_t parity, int c0, int c1) {
+  const bool res = a.res != nullptr;
+  if (a.act == ACT_GELU) {
+    if (res) epilogue_linear_t<BN, TOut, PRECISE, ACT_GELU, true>(a, t, xbuf, acc_full, parity, c0, c1);
+    else epilogue_linear_t<BN, TOut, PRECISE, ACT_GELU, false>(a, t, xbuf, acc_full, parity, c0, c1);
+  } else if (a.act == ACT_MISH) {
+    if (res) epilogue_linear_t<BN, TOut, PRECISE, ACT_MISH, true>(a, t, xbuf, acc_full, parity, c0, c1);
+    else epilogue_linear_t<BN, TOut, PRECISE, ACT_MISH, false>(a, t, xbuf, acc_full, parity, c0, c1);
+  } else {
+    if (res) epilogue_linear_t<BN, TOut, PRECISE, ACT_NONE, true>(a, t, xbuf, acc_full, parity, c0, c1);
+    else epilogue_linear_t<BN, TOut, PRECISE, ACT_NONE, false>(a, t, xbuf, acc_full, parity, c0, c1);
   }
 }
 
@@ -440,21 +478,22 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTi
 template <int BN, typename TOut, bool PRECISE>
 __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t, const float* colv, float2* gn_part,
                                             float2* gn_stat, int et, int bar_id, uint64_t* acc_full, uint32_t acc_parity,
-                                            OutStage& st) {
+                                            OutStage& st, int cb) {
+  // `cb`: first tile column of the half this warpgroup handles (0 or BN / 2); colv / TMEM / output columns are tile-relative
   const bool tma = a.tma_out != 0;
   const long long oplane = a.out_plane, rplane = a.res_plane;
   const int filmC = a.film_C;
 
   static_assert(BN == 128 || BN == 256, "GN epilogue: whole 32/64-channel groups per tile");
-  constexpr int NCH = BN / 32;  // 32-column chunks per tile
+  constexpr int NCH = BN / 64;  // 32-column chunks per half tile (2 or 4): whole 32- / 64-channel groups
   constexpr int CG = 128 / sizeof(TOut);
   const int row0 = (int)(t.grow - (threadIdx.x & 31));
   uint32_t box = 0;
   TOut* outp = reinterpret_cast<TOut*>(a.out) + (long long)t.g * a.out_g +
-               ((long long)t.q * a.out_q + (long long)t.rem * a.out_r + a.out_off) * a.ldc + t.n0;
+               ((long long)t.q * a.out_q + (long long)t.rem * a.out_r + a.out_off) * a.ldc + t.n0 + cb;
   const long long res_row = (long long)t.q * a.res_q + (long long)t.rem * a.res_r + a.res_off;
-  const TOut* resp = a.res ? reinterpret_cast<const TOut*>(a.res) + (long long)t.g * a.res_g + res_row * a.ldres + t.n0 : nullptr;
-  const float* filmp = a.film_c ? a.film_c + (long long)t.g * a.film_g + (long long)t.q * a.film_ld + a.film_off + t.n0 : nullptr;
+  const TOut* resp = a.res ? reinterpret_cast<const TOut*>(a.res) + (long long)t.g * a.res_g + res_row * a.ldres + t.n0 + cb : nullptr;
+  const float* filmp = a.film_c ? a.film_c + (long long)t.g * a.film_g + (long long)t.q * a.film_ld + a.film_off + t.n0 + cb : nullptr;
   const int lane = threadIdx.x & 31;
 
   mbar_wait(acc_full, acc_parity);
@@ -463,12 +502,12 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
     uint32_t v[32];
-    tmem_ld32(t.taddr + ch * 32, v);
+    tmem_ld32(t.taddr + cb + ch * 32, v);
     tmem_ld_wait();
     float a1 = 0.f, a2 = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      float x = __uint_as_float(v[j]) + colv[ch * 32 + j];
+      float x = __uint_as_float(v[j]) + colv[cb + ch * 32 + j];
       a1 += x;
       a2 = fmaf(x, x, a2);
     }
@@ -557,7 +596,7 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
 #pragma unroll 1
   for (int ch = 0; ch < NCH; ++ch) {   // rolled: a fully unrolled body (NCH x 4 copies) thrashes the instruction cache
     uint32_t v[32];
-    tmem_ld32(t.taddr + ch * 32, v);
+    tmem_ld32(t.taddr + cb + ch * 32, v);
     float mu = mean[0], rs = rstd[0];
 #pragma unroll
     for (int k = 1; k < NCH; ++k) {
@@ -582,13 +621,13 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
         float y[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float x = __uint_as_float(v[j8 + j]) + colv[cc + j];
-          x = (x - mu) * rs * colv[BN + cc + j] + colv[2 * BN + cc + j];
+          float x = __uint_as_float(v[j8 + j]) + colv[cb + cc + j];
+          x = (x - mu) * rs * colv[BN + cb + cc + j] + colv[2 * BN + cb + cc + j];
           y[j] = PRECISE ? mish_precise(x) : mish_f(x);
         }
         if (filmp) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) y[j] = (sc[j] + colv[3 * BN + cc + j]) * y[j] + (sh[j] + colv[4 * BN + cc + j]);
+          for (int j = 0; j < 8; ++j) y[j] = (sc[j] + colv[3 * BN + cb + cc + j]) * y[j] + (sh[j] + colv[4 * BN + cb + cc + j]);
         }
         if (resp) {
 #pragma unroll
@@ -602,7 +641,7 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
         else store_split8<TOut>(outp + cc, oplane, y);
       }
     }
-    if (tma && (((ch + 1) * 32) % CG) == 0) stage_end(st, &a.tmO, box, lane, t.n0 + ((ch * 32) / CG) * CG, row0, t.g);
+    if (tma && (((ch + 1) * 32) % CG) == 0) stage_end(st, &a.tmO, box, lane, t.n0 + cb + ((ch * 32) / CG) * CG, row0, t.g);
   }
 }
 
@@ -655,7 +694,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&acc_full[s], 1);
-        mbar_init(&acc_empty[s], 4 * CTAS);   // one arrival per epilogue warp of every CTA of the pair
+        mbar_init(&acc_empty[s], 8 * CTAS);   // one arrival per epilogue warp of every CTA of the pair
       }
       fence_barrier_init();
     }
@@ -774,32 +813,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
   } else {
     // ------------------------------ epilogue warpgroups ------------------------------
-    const int wg = (warp - 2) >> 2;               // 0 / 1  <->  accumulator 0 / 1
+    // Both warpgroups work on EVERY tile: warpgroup h takes the tile's columns [h * BN/2, (h+1) * BN/2), so a CTA with
+    // one or two tiles (the U-Net layers at batch 256) still uses all eight epilogue warps; accumulator lt & 1.
+    const int half = (warp - 2) >> 2;
     const int et = (threadIdx.x - 64) & 127;      // thread index inside the warpgroup
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int bar_id = 1 + wg;
-    float* colv = scratch + wg * GEMM_WG_SCRATCH_FLOATS(BN, MODE);    // [2][BN] (LINEAR) / [5][BN] + GroupNorm partials
-    float2* gn_part = reinterpret_cast<float2*>(colv + 5 * BN);       // [128][max(BN/32, 4)]
-    float2* gn_stat = gn_part + 128 * (BN / 32 > 4 ? BN / 32 : 4);    // [32][max(BN/32, 4)]
+    constexpr int HB = BN >= 64 ? BN / 2 : BN;    // columns per warpgroup (BN = 32: warpgroup 1 only signals)
+    const int c_begin = half * HB, c_end = (BN >= 64 || half == 0) ? c_begin + HB : c_begin;
+    constexpr int CV = GEMM_COLV_FLOATS(BN, MODE);
+    float2* gn_part = reinterpret_cast<float2*>(scratch + 2 * CV) + half * (128 + 64) * 4;   // [128][4]
+    float2* gn_stat = gn_part + 128 * 4;                                                      // [64][4]
     EpiTile t;
     t.r = quarter * 32 + lane;
     OutStage st;
     st.base = smem_u32(sOut) + (warp - 2) * 8192;
     st.count = 0;
     uint32_t lt = 0;
-    const uint32_t acc_empty_leader = CTAS == 2 ? mapa_shared(smem_u32(&acc_empty[wg]), 0) : 0u;
+    const bool fast = GEMM_XPOSE_BYTES(BN, MODE) > 0 && a.fast != 0;
     for (int tile = worker; tile < a.total_tiles; tile += n_workers, ++lt) {
-      if ((lt & 1) != (uint32_t)wg) continue;
+      const uint32_t acc = lt & 1;
       const int n_tile = tile % a.n_tiles;
       const int rest = tile / a.n_tiles;
       const int m_tile = (rest % a.m_tiles) * CTAS + rank;
       t.g = rest / a.m_tiles;
       t.n0 = n_tile * BN;
-      // stage the per-column vectors of this tile (previous tile's readers are done: barrier first)
-      if (!(a.debug & 64)) named_bar_sync(bar_id, 128);
-      if (!(a.debug & 64)) {
+      float* colv = scratch + acc * CV;    // [2][BN] (LINEAR) / [5][BN] (GroupNorm) column vectors of this tile
+      if (!fast) {
+        // stage the per-column vectors.  Set `acc` was last read two tiles ago and every warp has passed the barrier of
+        // the tile in between, so only the write -> read edge needs a barrier.
         const long long gcol = (long long)t.g * a.n_pad + t.n0;
-        for (int c = et; c < BN; c += 128) {
+        for (int c = threadIdx.x - 64; c < BN; c += 256) {
           colv[c] = a.bias ? a.bias[gcol + c] : 0.f;
           if (MODE == EPI_LINEAR) {
             colv[BN + c] = (a.colscale && (t.n0 + c) < a.N) ? a.colscale[t.n0 + c] : 1.f;
@@ -812,28 +855,33 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             colv[4 * BN + c] = f ? a.film_t[fo + a.film_C] : 0.f;
           }
         }
+        named_bar_sync(1, 256);
       }
-      if (!(a.debug & 64)) named_bar_sync(bar_id, 128);
       t.grow = (long long)m_tile * a.rows_valid + t.r;
       t.valid = (t.r < a.rows_valid) && (t.grow < a.M_total);
       t.q = (int)(t.grow / a.row_div);
       t.rem = (int)(t.grow - (long long)t.q * a.row_div);
-      t.taddr = tmem_base + wg * ACC_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
+      t.taddr = tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
       const uint32_t parity = (lt >> 1) & 1;
-      if (a.debug & 2) {
-        mbar_wait(&acc_full[wg], parity);
-        tc_fence_after();
-      } else if constexpr (MODE == EPI_LINEAR) {
-        if (GEMM_XPOSE_BYTES(BN, MODE) > 0 && a.fast)
-          epilogue_linear_t<BN, TOut, PRECISE>(a, t, colv, smem_u32(sX) + (warp - 2) * 4096, &acc_full[wg], parity);
-        else
-          epilogue_linear<BN, TOut, PRECISE>(a, t, colv, &acc_full[wg], parity, st);
-      } else
-        epilogue_gn<BN, TOut, PRECISE>(a, t, colv, gn_part, gn_stat, et, bar_id, &acc_full[wg], parity, st);
+      if (c_begin < c_end) {
+        if (a.debug & 2) {
+          mbar_wait(&acc_full[acc], parity);
+          tc_fence_after();
+        } else if constexpr (MODE == EPI_LINEAR) {
+          if constexpr (GEMM_XPOSE_BYTES(BN, MODE) > 0) {
+            if (fast) epilogue_linear_fast<BN, TOut, PRECISE>(a, t, smem_u32(sX) + (warp - 2) * 4096, &acc_full[acc], parity, c_begin, c_end);
+            else epilogue_linear<BN, TOut, PRECISE>(a, t, colv, &acc_full[acc], parity, st, c_begin, c_end);
+          } else {
+            epilogue_linear<BN, TOut, PRECISE>(a, t, colv, &acc_full[acc], parity, st, c_begin, c_end);
+          }
+        } else {
+          epilogue_gn<BN, TOut, PRECISE>(a, t, colv, gn_part, gn_stat, et, 2 + half, &acc_full[acc], parity, st, c_begin);
+        }
+      }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {   // this warp's quarter of the accumulator has been read out
-        if constexpr (CTAS == 2) mbar_arrive_cluster(acc_empty_leader); else mbar_arrive(&acc_empty[wg]);
+      if (lane == 0) {   // this warp's share of the accumulator has been read out
+        if constexpr (CTAS == 2) mbar_arrive_remote(mapa_shared(smem_u32(&acc_empty[acc]), 0)); else mbar_arrive(&acc_empty[acc]);
       }
     }
     if (a.tma_out && lane == 0) bulk_wait_all();   // staged boxes must be drained before the CTA exits

@@ -336,7 +336,7 @@ int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
     VT_REQUIRE(d.t_box == t_out, "gemm: GroupNorm epilogue needs whole samples per tile (t_box=%d, positions=%d)", d.t_box, t_out);
     VT_REQUIRE(d.row_div == d.t_box, "gemm: GroupNorm epilogue needs row_div == t_box");
     VT_REQUIRE(vec, "gemm: GroupNorm epilogue needs 16-byte aligned rows");
-    VT_REQUIRE(d.b_box <= (d.bn == 256 ? 16 : 32), "gemm: GroupNorm epilogue supports at most %d samples per tile", d.bn == 256 ? 16 : 32);
+    VT_REQUIRE(d.b_box <= 32, "gemm: GroupNorm epilogue supports at most 32 samples per tile");
     if (d.film_c) VT_REQUIRE(d.film_ld % 4 == 0 && d.film_off % 4 == 0 && d.film_C % 4 == 0 && d.film_g % 4 == 0 && aligned16(d.film_c),
                              "gemm: FiLM table must be 16-byte aligned");
     a.gn_gamma = d.gn_gamma;
