@@ -259,6 +259,423 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
   if (warp == 9) tmem_dealloc(tmem_base, 256);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// attn_row_kernel (bf16, 256 <= tokens <= 272, e.g. the 257 tokens of a 224 x 224 image): PERSISTENT, one CTA per SM,
+// work unit = one (image, head).  The whole key range fits TMEM, so there is no online-softmax rescaling:
+//   warp 8   TMA producer: K tiles (2 x 128 rows + a 16-row tail box; double-buffered across units), V tiles (single
+//            buffer: free again one query tile before the next unit needs it), Q tiles (2-deep ring)
+//   warp 9   UMMA issuer : S = Q K^T for ALL keys into TMEM columns [0, 272); then O = P V per 64-key chunk as soon
+//            as the softmax warps have published that chunk of P
+//   warps 0-7  softmax   : two threads per query row (keys [0,128) / [128, 272)); pass 1 row max, pass 2
+//            p = 2^(s*c - m*c) -> bf16 P chunk tiles in shared memory (128B-swizzled K-major UMMA operand) + row sums;
+//            O is read once per query tile, scaled by 1/sum, staged in the (dead) Q tile and written by ONE TMA store
+//   warps 10-11  tail rows: the 1..16 query rows behind the last full tile (the CLS-shifted 257th token) on the CUDA
+//            cores, straight from the K / V tiles that are already in shared memory - no 128-row tile that is 99 %
+//            padding, no second pass over K and V in HBM.
+// Per full query tile the MUFU pipe (128 x 257 exponentials, 16 / clock / SM) is the floor: ~2100 of ~3400 cycles.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int ATR_THREADS = 384;
+constexpr int ATR_KBUF = 2 * ATT_TILE_BYTES + 2048;           // two 128-row tiles + one 16-row tail tile
+constexpr int ATR_SMEM_K = 0;                                 // [2][ATR_KBUF]
+constexpr int ATR_SMEM_V = 2 * ATR_KBUF;                      // [ATR_KBUF]
+constexpr int ATR_SMEM_Q = 3 * ATR_KBUF;                      // [2][16 KB]   (also the O staging tile)
+constexpr int ATR_SMEM_P = ATR_SMEM_Q + 2 * ATT_TILE_BYTES;   // [5][16 KB]   64-key chunks of P (chunk 4: 16 keys)
+constexpr int ATR_SMEM_BAR = ATR_SMEM_P + 5 * ATT_TILE_BYTES; // 32 mbarriers
+constexpr int ATR_SMEM_XCH = ATR_SMEM_BAR + 256;              // [2][2][128] floats: row max / row sum exchange
+constexpr int ATR_SMEM_TAIL = ATR_SMEM_XCH + 4096;            // tail warps: q[64], p[272], red[8], part[2][64] floats
+constexpr int ATR_SMEM_BYTES = 1024 + ATR_SMEM_TAIL + (64 + 272 + 8 + 128) * 4 + 16;
+static_assert(ATR_SMEM_BYTES <= 227 * 1024, "attn_row_kernel shared memory");
+
+struct AttnRowArgs {
+  CUtensorMap tm;    // 2-D (3*D, images*tokens) over qkv, box (64, 128), SWIZZLE_128B
+  CUtensorMap tm16;  // same tensor, box (64, 16): the K / V tail rows
+  CUtensorMap tmO;   // 2-D (D, images*tokens) over ctx (row stride ctx_ld), box (64, 128), SWIZZLE_128B
+  const __nv_bfloat16* qkv;
+  __nv_bfloat16* ctx;
+  long long ctx_ld;
+  int tokens, heads, D, units;   // units = images * heads
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(ATR_THREADS, 1) attn_row_kernel(const __grid_constant__ AttnRowArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sK = smem + ATR_SMEM_K;
+  uint8_t* sV = smem + ATR_SMEM_V;
+  uint8_t* sQ = smem + ATR_SMEM_Q;
+  uint8_t* sP = smem + ATR_SMEM_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATR_SMEM_BAR);
+  uint64_t* k_full = bars;            // [2]
+  uint64_t* k_empty = bars + 2;       // [2]
+  uint64_t* v_full = bars + 4;
+  uint64_t* v_empty = bars + 5;
+  uint64_t* q_full = bars + 6;        // [2]
+  uint64_t* q_empty = bars + 8;       // [2]
+  uint64_t* s_full = bars + 10;
+  uint64_t* s_empty = bars + 11;
+  uint64_t* p_full = bars + 12;       // [5]
+  uint64_t* o_full = bars + 17;
+  uint64_t* o_empty = bars + 18;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  float* xch = reinterpret_cast<float*>(smem + ATR_SMEM_XCH);
+  float* tq = reinterpret_cast<float*>(smem + ATR_SMEM_TAIL);   // [64]
+  float* tp = tq + 64;                                           // [272]
+  float* tred = tp + 272;                                        // [8]
+  float* tpart = tred + 8;                                       // [2][64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = a.tokens;
+  const int n_tail = N - 256;              // 0..16 keys / query rows behind the two full tiles
+  const bool has_tail = n_tail > 0;
+
+  if (warp == 9) {
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&k_full[i], 1);
+        mbar_init(&k_empty[i], has_tail ? 3 : 1);   // MMA commit + the two tail warps
+        mbar_init(&q_full[i], 1);
+        mbar_init(&q_empty[i], 1);
+      }
+      mbar_init(v_full, 1);
+      mbar_init(v_empty, has_tail ? 3 : 1);
+      mbar_init(s_full, 1);
+      mbar_init(s_empty, 256);
+      for (int i = 0; i < 5; ++i) mbar_init(&p_full[i], 128);
+      mbar_init(o_full, 1);
+      mbar_init(o_empty, 256);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&a.tm);
+    tma_prefetch_desc(&a.tm16);
+    tma_prefetch_desc(&a.tmO);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 288;
+
+  if (warp == 8) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      uint32_t us = 0, qs = 0;
+      for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x, ++us) {
+        const int img = unit / a.heads, head = unit - img * a.heads;
+        const int row0 = img * N;
+        const uint32_t kb = us & 1;
+        uint8_t* kbuf = sK + kb * ATR_KBUF;
+        mbar_wait(&k_empty[kb], ((us >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[kb], 2 * ATT_TILE_BYTES + (has_tail ? 2048 : 0));
+        tma_load_2d(kbuf, &a.tm, &k_full[kb], a.D + head * 64, row0);
+        tma_load_2d(kbuf + ATT_TILE_BYTES, &a.tm, &k_full[kb], a.D + head * 64, row0 + 128);
+        if (has_tail) tma_load_2d(kbuf + 2 * ATT_TILE_BYTES, &a.tm16, &k_full[kb], a.D + head * 64, row0 + 256);
+        {   // first Q tile before V: it is needed first
+          const uint32_t qb = qs & 1;
+          mbar_wait(&q_empty[qb], ((qs >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&q_full[qb], ATT_TILE_BYTES);
+          tma_load_2d(sQ + qb * ATT_TILE_BYTES, &a.tm, &q_full[qb], head * 64, row0);
+          ++qs;
+        }
+        mbar_wait(v_empty, (us & 1) ^ 1);
+        mbar_arrive_expect_tx(v_full, 2 * ATT_TILE_BYTES + (has_tail ? 2048 : 0));
+        tma_load_2d(sV, &a.tm, v_full, 2 * a.D + head * 64, row0);
+        tma_load_2d(sV + ATT_TILE_BYTES, &a.tm, v_full, 2 * a.D + head * 64, row0 + 128);
+        if (has_tail) tma_load_2d(sV + 2 * ATT_TILE_BYTES, &a.tm16, v_full, 2 * a.D + head * 64, row0 + 256);
+        {
+          const uint32_t qb = qs & 1;
+          mbar_wait(&q_empty[qb], ((qs >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&q_full[qb], ATT_TILE_BYTES);
+          tma_load_2d(sQ + qb * ATT_TILE_BYTES, &a.tm, &q_full[qb], head * 64, row0 + 128);
+          ++qs;
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------ UMMA issuer ------------------------------
+    if (lane == 0) {
+      uint32_t us = 0, qs = 0;
+      const uint32_t idesc_s = umma_idesc(UMMA_FMT_BF16, 128);
+      const uint32_t idesc_st = umma_idesc(UMMA_FMT_BF16, 16);
+      const uint32_t idesc_o = umma_idesc(UMMA_FMT_BF16, 64, 0, 1);
+      const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(sV));
+      const uint64_t pdesc = umma_smem_desc_sw128(smem_u32(sP));
+      for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x, ++us) {
+        const uint32_t kb = us & 1;
+        const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sK + kb * ATR_KBUF));
+        mbar_wait(&k_full[kb], (us >> 1) & 1);
+        for (int qt = 0; qt < 2; ++qt, ++qs) {
+          const uint32_t qb = qs & 1;
+          const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ + qb * ATT_TILE_BYTES));
+          mbar_wait(&q_full[qb], (qs >> 1) & 1);
+          mbar_wait(s_empty, (qs & 1) ^ 1);       // every softmax thread has finished reading the previous S
+          tc_fence_after();
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tmem_S + j * 128, qdesc + 2 * k, kdesc + (uint64_t)(j * (ATT_TILE_BYTES >> 4)) + 2 * k, idesc_s, k != 0);
+          }
+          if (has_tail) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tmem_S + 256, qdesc + 2 * k, kdesc + (uint64_t)(2 * (ATT_TILE_BYTES >> 4)) + 2 * k, idesc_st, k != 0);
+          }
+          umma_commit(s_full);
+          if (qt == 1) umma_commit(&k_empty[kb]);   // last use of this unit's K tiles
+          if (qt == 0) mbar_wait(v_full, us & 1);
+          mbar_wait(o_empty, (qs & 1) ^ 1);         // the previous query tile's O has been read out
+          tc_fence_after();
+          for (int c = 0; c < 4; ++c) {             // 64-key chunks of P, published one by one
+            mbar_wait(&p_full[c], qs & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16(tmem_O, pdesc + (uint64_t)(c * (ATT_TILE_BYTES >> 4)) + 2 * kk,
+                       vdesc + (uint64_t)((c * 64 + kk * 16) * 128 >> 4), idesc_o, (c | kk) != 0);
+          }
+          if (has_tail) {
+            mbar_wait(&p_full[4], qs & 1);
+            tc_fence_after();
+            umma_f16(tmem_O, pdesc + (uint64_t)(4 * (ATT_TILE_BYTES >> 4)), vdesc + (uint64_t)(256 * 128 >> 4), idesc_o, 1);
+          }
+          umma_commit(o_full);
+          if (qt == 1) umma_commit(v_empty);
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ------------------------------ softmax + output ------------------------------
+    const int half = warp >> 2, quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const float sl = a.scale_log2;
+    const int sw = r & 7;
+    const uint32_t sP_row = smem_u32(sP) + half * 2 * ATT_TILE_BYTES + r * 128;   // this half's first chunk tile
+    const int my_tail = half ? n_tail : 0;                                        // valid tail keys of this thread
+    uint32_t qs = 0;
+    for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x) {
+      const int img = unit / a.heads, head = unit - img * a.heads;
+      for (int qt = 0; qt < 2; ++qt, ++qs) {
+        float* my_x = xch + (qs & 1) * 512 + half * 128 + r;
+        const float* peer_x = xch + (qs & 1) * 512 + (half ^ 1) * 128 + r;
+        mbar_wait(s_full, qs & 1);
+        tc_fence_after();
+        const uint32_t s_addr = tmem_S + lane_off + half * 128;
+        uint32_t va[16], vb[16];
+        // ---- pass 1: row max over this thread's 128 (+ tail) columns, two TMEM loads in flight ----
+        float mx = -INFINITY;
+        tmem_ld16(s_addr, va);
+#pragma unroll
+        for (int g = 0; g < 8; g += 2) {
+          tmem_ld_wait();
+          tmem_ld16(s_addr + (g + 1) * 16, vb);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(va[i]));
+          tmem_ld_wait();
+          if (g + 2 < 8) tmem_ld16(s_addr + (g + 2) * 16, va);
+          else if (my_tail > 0) tmem_ld16(s_addr + 128, va);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(vb[i]));
+        }
+        if (my_tail > 0) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, i < my_tail ? __uint_as_float(va[i]) : -INFINITY);
+        }
+        my_x[0] = mx;
+        tmem_ld16(s_addr, va);                        // first chunk of pass 2, overlapped with the exchange
+        named_bar_sync(1 + quarter, 64);              // the two warps that share these 32 rows
+        const float m = fmaxf(mx, peer_x[0]);
+        const float2 msc = make_float2(-m * sl, -m * sl), sl2 = make_float2(sl, sl);
+        // ---- pass 2: p = 2^(s*sl - m*sl) -> bf16 P (two 64-key chunk tiles per half) + row sum ----
+        float2 rsum = make_float2(0.f, 0.f);
+        auto exp16 = [&](const uint32_t(&v)[16], uint32_t row_addr, int piece0) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = u * 8 + 2 * e;
+              const float2 x = ffma2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sl2, msc);
+              const float2 pp = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+              rsum = fadd2(rsum, pp);
+              pk[e] = pack_bf16x2(pp.x, pp.y);
+            }
+            st_shared_v4(row_addr + (((piece0 + u) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+          }
+        };
+#pragma unroll
+        for (int g = 0; g < 8; g += 2) {
+          tmem_ld_wait();
+          tmem_ld16(s_addr + (g + 1) * 16, vb);
+          exp16(va, sP_row + (g >> 2) * ATT_TILE_BYTES, (g & 3) * 2);
+          tmem_ld_wait();
+          if (g + 2 < 8) tmem_ld16(s_addr + (g + 2) * 16, va);
+          else if (my_tail > 0) tmem_ld16(s_addr + 128, va);
+          exp16(vb, sP_row + (g >> 2) * ATT_TILE_BYTES, (g & 3) * 2 + 2);
+          if ((g & 3) == 2) {                         // a 64-key chunk of P is complete for this row
+            fence_proxy_async_smem();
+            mbar_arrive(&p_full[half * 2 + (g >> 2)]);
+          }
+        }
+        if (has_tail && half == 1) {
+          tmem_ld_wait();
+          uint32_t pk[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int i = 2 * e;
+            const float2 x = ffma2(make_float2(__uint_as_float(va[i]), __uint_as_float(va[i + 1])), sl2, msc);
+            float2 pp = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+            pp.x = i < my_tail ? pp.x : 0.f;
+            pp.y = i + 1 < my_tail ? pp.y : 0.f;
+            rsum = fadd2(rsum, pp);
+            pk[e] = pack_bf16x2(pp.x, pp.y);
+          }
+          const uint32_t row_addr = smem_u32(sP) + 4 * ATT_TILE_BYTES + r * 128;
+          st_shared_v4(row_addr + ((0 ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+          st_shared_v4(row_addr + ((1 ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
+          fence_proxy_async_smem();
+        }
+        if (has_tail && half == 1) mbar_arrive(&p_full[4]);   // the tail chunk belongs to the upper half's 128 threads
+        tc_fence_before();
+        mbar_arrive(s_empty);                         // S may be overwritten by the next query tile
+        // ---- row sum exchange, O read-out ----
+        my_x[256] = rsum.x + rsum.y;
+        named_bar_sync(1 + quarter, 64);
+        const float inv = 1.0f / (rsum.x + rsum.y + peer_x[256]);
+        mbar_wait(o_full, qs & 1);
+        tc_fence_after();
+        uint32_t w[32];
+        tmem_ld32(tmem_O + lane_off + half * 32, w);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(o_empty);
+        // stage this row's 32 channels (64 bytes) in the dead Q tile, 128B-swizzled as the TMA store expects
+        const uint32_t qb = qs & 1;
+        const uint32_t o_row = smem_u32(sQ) + qb * ATT_TILE_BYTES + r * 128;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = u * 8;
+          st_shared_v4(o_row + (((half * 4 + u) ^ sw) << 4),
+                       pack_bf16x2(__uint_as_float(w[i]) * inv, __uint_as_float(w[i + 1]) * inv),
+                       pack_bf16x2(__uint_as_float(w[i + 2]) * inv, __uint_as_float(w[i + 3]) * inv),
+                       pack_bf16x2(__uint_as_float(w[i + 4]) * inv, __uint_as_float(w[i + 5]) * inv),
+                       pack_bf16x2(__uint_as_float(w[i + 6]) * inv, __uint_as_float(w[i + 7]) * inv));
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(5, 256);
+        if (threadIdx.x == 0) {
+          tma_store_2d(&a.tmO, o_row - r * 128, head * 64, img * N + qt * 128);
+          bulk_commit();
+          bulk_wait_read<0>();                        // the tile has been read: the producer may load the next Q into it
+          mbar_arrive(&q_empty[qb]);
+        }
+      }
+    }
+    if (threadIdx.x == 0) bulk_wait_all();
+  } else if (has_tail) {
+    // ------------------------------ tail query rows on the CUDA cores (warps 10, 11) ------------------------------
+    const int tw = warp - 10;                 // 0 / 1
+    const int tid = tw * 32 + lane;           // 0..63
+    uint32_t us = 0;
+    for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x, ++us) {
+      const int img = unit / a.heads, head = unit - img * a.heads;
+      const uint32_t kb = us & 1;
+      const uint32_t kbase = smem_u32(sK + kb * ATR_KBUF), vbase = smem_u32(sV);
+      mbar_wait(&k_full[kb], (us >> 1) & 1);
+      for (int tr = 0; tr < n_tail; ++tr) {
+        const long long qrow = (long long)img * N + 256 + tr;
+        named_bar_sync(6, 64);                // previous row's readers of tq / tp / tpart are done
+        tq[tid] = __bfloat162float(a.qkv[qrow * (3LL * a.D) + head * 64 + tid]);
+        named_bar_sync(6, 64);
+        float q[64];
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          const float4 t4 = *reinterpret_cast<const float4*>(tq + i);
+          q[i] = t4.x; q[i + 1] = t4.y; q[i + 2] = t4.z; q[i + 3] = t4.w;
+        }
+        // scores of keys tid, tid + 64, ... (5 per thread)
+        float sc[5];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const int k = tid + 64 * j;
+          float acc = -INFINITY;
+          if (k < N) {
+            const uint32_t row = kbase + k * 128;   // tiles are contiguous: key k lives at row k of the 128-byte rows
+            acc = 0.f;
+#pragma unroll
+            for (int pc = 0; pc < 8; ++pc) {
+              const float4 raw = ld_shared_v4f(row + ((pc ^ (k & 7)) << 4));
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h2[e]);
+                acc = fmaf(q[pc * 8 + 2 * e], f.x, acc);
+                acc = fmaf(q[pc * 8 + 2 * e + 1], f.y, acc);
+              }
+            }
+            acc *= a.scale_log2;
+          }
+          sc[j] = acc;
+          mx = fmaxf(mx, acc);
+        }
+        mx = warp_max(mx);
+        if (lane == 0) tred[tw] = mx;
+        named_bar_sync(6, 64);
+        mx = fmaxf(tred[0], tred[1]);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const int k = tid + 64 * j;
+          const float e = k < N ? ex2_approx(sc[j] - mx) : 0.f;
+          if (k < 272) tp[k] = e;
+          sum += e;
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) tred[2 + tw] = sum;
+        mbar_wait(v_full, us & 1);
+        named_bar_sync(6, 64);
+        const float inv = 1.0f / (tred[2] + tred[3]);
+        // O[c] = sum_k p[k] V[k][c]: lane -> channel pair (2 lane, 2 lane + 1), warp tw -> keys k = tw (mod 2)
+        float o0 = 0.f, o1 = 0.f;
+        for (int k = tw; k < N; k += 2) {
+          uint32_t raw;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(raw) : "r"(vbase + k * 128 + (((lane >> 2) ^ (k & 7)) << 4) + (lane & 3) * 4));
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw));
+          const float pk = tp[k];
+          o0 = fmaf(pk, f.x, o0);
+          o1 = fmaf(pk, f.y, o1);
+        }
+        tpart[tw * 64 + 2 * lane] = o0;
+        tpart[tw * 64 + 2 * lane + 1] = o1;
+        named_bar_sync(6, 64);
+        if (tw == 0) {
+          o0 = (tpart[2 * lane] + tpart[64 + 2 * lane]) * inv;
+          o1 = (tpart[2 * lane + 1] + tpart[64 + 2 * lane + 1]) * inv;
+          *reinterpret_cast<uint32_t*>(a.ctx + qrow * a.ctx_ld + head * 64 + 2 * lane) = pack_bf16x2(o0, o1);
+        }
+      }
+      // this warp is done with the unit's K and V tiles
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&k_empty[kb]);
+        mbar_arrive(v_empty);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem_base, 512);
+}
+
 // Last query rows of an image when tokens % 128 <= ATT_TAIL_MAX (e.g. the 257th token at 224x224): one 128-thread block
 // per (image, head, row) on the CUDA cores instead of a 128-row tensor-core tile that would be >87% padding.
 // Keys are split over the four warps (scores -> shared memory, block-wide max / sum), then thread (w, l) accumulates

@@ -388,13 +388,23 @@ int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
 // ---- attention ----
 struct AttnOp : Op {
   vt::AttnArgs args;
+  vt::AttnRowArgs rargs;
+  bool row_kernel = false;   // whole key range resident in TMEM (256..272 tokens): attn_row_kernel
   vt_attn_desc d;
   dim3 grid;
   int tail_first = -1;   // first query row handled by attn_tail_kernel, or -1
   static bool attr_set;
-  int launches() const override { return (d.in_dtype == VT_BF16 && tail_first >= 0 && grid.x > 0) ? 2 : 1; }
+  int launches() const override { return (d.in_dtype == VT_BF16 && !row_kernel && tail_first >= 0 && grid.x > 0) ? 2 : 1; }
   int launch(cudaStream_t s) override {
-    if (d.in_dtype == VT_BF16) {
+    if (d.in_dtype == VT_BF16 && row_kernel) {
+      static bool row_attr_set = false;
+      if (!row_attr_set) {
+        VT_CUDA(cudaFuncSetAttribute(vt::attn_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vt::ATR_SMEM_BYTES));
+        row_attr_set = true;
+      }
+      vt::attn_row_kernel<<<grid, vt::ATR_THREADS, vt::ATR_SMEM_BYTES, s>>>(rargs);
+      VT_LAUNCH_CHECK("attn_row_kernel");
+    } else if (d.in_dtype == VT_BF16) {
       if (!attr_set) {
         VT_CUDA(cudaFuncSetAttribute(vt::attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vt::ATT_SMEM_BYTES));
         attr_set = true;
@@ -669,6 +679,29 @@ int vt_program_add_attention(vt_program* p, const vt_attn_desc* d) {
     }
     op->grid = dim3((unsigned)q_tiles, (unsigned)d->heads, (unsigned)d->images);
     VT_REQUIRE(d->images <= 65535, "attention: images=%d exceeds the grid z limit", d->images);
+    const char* rk = getenv("VT_ATTN_ROW");
+    if (d->tokens >= 256 && d->tokens <= 272 && !(rk && atoi(rk) == 0) && (long long)d->images * d->tokens < (1ll << 31)) {
+      vt::AttnRowArgs& r = op->rargs;
+      r.tm = op->args.tm;
+      const uint32_t box16[2] = {64u, 16u};
+      rc = make_tmap(&r.tm16, VT_BF16, 2, d->qkv, dims, st, box16);
+      if (rc) return rc;
+      const uint64_t odims[2] = {(uint64_t)D, (uint64_t)d->images * d->tokens};
+      const uint64_t ost[1] = {(uint64_t)d->ctx_ld * 2};
+      rc = make_tmap(&r.tmO, VT_BF16, 2, d->ctx, odims, ost, box);
+      if (rc) return rc;
+      r.qkv = reinterpret_cast<const __nv_bfloat16*>(d->qkv);
+      r.ctx = op->args.ctx;
+      r.ctx_ld = d->ctx_ld;
+      r.tokens = d->tokens;
+      r.heads = d->heads;
+      r.D = D;
+      r.units = d->images * d->heads;
+      r.scale_log2 = op->args.scale_log2;
+      op->row_kernel = true;
+      const int sms = sm_count();
+      op->grid = dim3((unsigned)(r.units < sms ? r.units : sms), 1u, 1u);
+    }
   } else {
     VT_REQUIRE(d->in_dtype == VT_F32, "attention: in_dtype %d", d->in_dtype);
     VT_REQUIRE((size_t)vt::ATTF_WARPS * d->tokens * 4 <= 48 * 1024, "attention(f32): tokens=%d too many", d->tokens);
