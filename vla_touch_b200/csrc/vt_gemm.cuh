@@ -94,11 +94,14 @@ struct InTraits<float> {
   static constexpr uint32_t FMT = UMMA_FMT_TF32;
 };
 
-// two column-vector sets (one per accumulator: 2 x BN LINEAR / 5 x BN GroupNorm), and per epilogue warpgroup the GroupNorm
-// row partials [128][4] and sample sums [64][4] (float2)
+// Epilogue scratch.  LINEAR: two column-vector sets (one per accumulator) of [2][BN].  GroupNorm: one set of [5][BN]
+// (bias, gamma, beta, FiLM time scale / shift), per warpgroup the row partials [128][4] and sample sums [64][4] (float2),
+// and the staged per-sample FiLM table [GEMM_FILM_SAMPLES][2][BN].
+constexpr int GEMM_FILM_SAMPLES = 8;
 __host__ __device__ constexpr int GEMM_COLV_FLOATS(int BN, int MODE) { return MODE == 0 ? 2 * BN : 5 * BN; }
-__host__ __device__ constexpr int GEMM_WG_SCRATCH_FLOATS(int BN, int MODE) {
-  return GEMM_COLV_FLOATS(BN, MODE) + (MODE == 0 ? 0 : (128 + 64) * 4 * 2);
+__host__ __device__ constexpr int GEMM_SCRATCH_FLOATS(int BN, int MODE) {
+  return MODE == 0 ? 2 * GEMM_COLV_FLOATS(BN, MODE)
+                   : GEMM_COLV_FLOATS(BN, MODE) + 2 * (128 + 64) * 4 * 2 + GEMM_FILM_SAMPLES * 2 * BN;
 }
 
 // 8 epilogue warps x 2 boxes of 32 rows x 128 B when the TMA-store epilogue is compiled in.  Measured on B200: the
@@ -117,8 +120,7 @@ __host__ __device__ constexpr int GEMM_XPOSE_BYTES(int BN, int MODE) { return (M
 template <int BN, int STAGES, int MODE, int KA, int CTAS = 1>
 constexpr int gemm_smem_bytes() {
   return 1024 /*align slack*/ + STAGES * KA * (GEMM_A_STAGE_BYTES + (BN / CTAS) * 128) + GEMM_OUT_STAGE_BYTES +
-         GEMM_XPOSE_BYTES(BN, MODE) + 256 /*barriers*/ +
-         2 * GEMM_WG_SCRATCH_FLOATS(BN, MODE) * 4;
+         GEMM_XPOSE_BYTES(BN, MODE) + 256 /*barriers*/ + GEMM_SCRATCH_FLOATS(BN, MODE) * 4;
 }
 
 template <typename TOut>
@@ -475,47 +477,14 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmArgs& a, const Ep
 // whole groups, so the statistics are tile-local.  Pass 1: per-row partial sums per 32-column chunk, reduced over the
 // rows of a sample with warp shuffles (power-of-two T <= 32, or T a multiple of 32) or through shared memory.
 // ------------------------------------------------------------------------------------------------------------
-template <int BN, typename TOut, bool PRECISE>
-__device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t, const float* colv, float2* gn_part,
-                                            float2* gn_stat, int et, int bar_id, uint64_t* acc_full, uint32_t acc_parity,
-                                            OutStage& st, int cb) {
-  // `cb`: first tile column of the half this warpgroup handles (0 or BN / 2); colv / TMEM / output columns are tile-relative
-  const bool tma = a.tma_out != 0;
-  const long long oplane = a.out_plane, rplane = a.res_plane;
-  const int filmC = a.film_C;
-
-  static_assert(BN == 128 || BN == 256, "GN epilogue: whole 32/64-channel groups per tile");
-  constexpr int NCH = BN / 64;  // 32-column chunks per half tile (2 or 4): whole 32- / 64-channel groups
-  constexpr int CG = 128 / sizeof(TOut);
-  const int row0 = (int)(t.grow - (threadIdx.x & 31));
-  uint32_t box = 0;
-  TOut* outp = reinterpret_cast<TOut*>(a.out) + (long long)t.g * a.out_g +
-               ((long long)t.q * a.out_q + (long long)t.rem * a.out_r + a.out_off) * a.ldc + t.n0 + cb;
-  const long long res_row = (long long)t.q * a.res_q + (long long)t.rem * a.res_r + a.res_off;
-  const TOut* resp = a.res ? reinterpret_cast<const TOut*>(a.res) + (long long)t.g * a.res_g + res_row * a.ldres + t.n0 + cb : nullptr;
-  const float* filmp = a.film_c ? a.film_c + (long long)t.g * a.film_g + (long long)t.q * a.film_ld + a.film_off + t.n0 + cb : nullptr;
-  const int lane = threadIdx.x & 31;
-
-  mbar_wait(acc_full, acc_parity);
-  tc_fence_after();
-  float s1[NCH], s2[NCH];
-#pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) {
-    uint32_t v[32];
-    tmem_ld32(t.taddr + cb + ch * 32, v);
-    tmem_ld_wait();
-    float a1 = 0.f, a2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float x = __uint_as_float(v[j]) + colv[cb + ch * 32 + j];
-      a1 += x;
-      a2 = fmaf(x, x, a2);
-    }
-    s1[ch] = t.valid ? a1 : 0.f;
-    s2[ch] = t.valid ? a2 : 0.f;
-  }
+// Row partials (s1 = sum, s2 = sum of squares per 32-column chunk) -> totals of the row's sample and GroupNorm group,
+// left in every thread of the sample.  Power-of-two T <= 32: segmented warp butterfly; T a multiple of 32: warp butterfly +
+// shared memory across the sample's warps; any other T: per-row partials through shared memory.
+template <int NCH>
+__device__ __forceinline__ void gn_sample_totals(const GemmArgs& a, const EpiTile& t, float (&s1)[NCH], float (&s2)[NCH],
+                                                 float2* gn_part, float2* gn_stat, int et, int bar_id) {
   const int T = a.gn_rows;
-  const float cnt = (float)(T << a.gn_gs_log2);
+  const int lane = threadIdx.x & 31;
   if (T <= 32 && (T & (T - 1)) == 0) {
     // samples are aligned groups of T lanes: segmented butterfly, every lane ends with its sample's totals
 #pragma unroll
@@ -586,6 +555,187 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
       s2[ch] = s2[ch + 1] = p2;
     }
   }
+}
+
+// Mish on two lanes: x * n / (n + 2), n = e^x (e^x + 2); two MUFU (ex2, rcp) per element, the rest packed f32x2.
+__device__ __forceinline__ float2 mish2(float2 x) {
+  const float2 xe = fmul2(make_float2(fminf(x.x, 20.f), fminf(x.y, 20.f)), make_float2(1.4426950408889634f, 1.4426950408889634f));
+  const float2 e = make_float2(ex2_approx(xe.x), ex2_approx(xe.y));
+  const float2 n = ffma2(e, e, fadd2(e, e));
+  const float2 d = fadd2(n, make_float2(2.f, 2.f));
+  float2 r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
+  return fmul2(x, fmul2(n, r));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// EPI_GN, bf16 production variant.  Everything that does not depend on the accumulator is fetched while the main loop
+// still runs: the per-(sample, column) FiLM scale / shift (cond part + time part) is staged in shared memory by the
+// caller (`films`, [samples][2][BN], null = no FiLM or too many samples) and the residual rows of the first chunk are
+// already in registers when the accumulator arrives; the residual of chunk c+1 is in flight while chunk c is computed.
+// ------------------------------------------------------------------------------------------------------------
+template <int BN>
+__device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, const EpiTile& t, const float* colv, const float* films,
+                                                 float2* gn_part, float2* gn_stat, int et, int bar_id, uint64_t* acc_full,
+                                                 uint32_t acc_parity, int cb) {
+  constexpr int NCH = BN / 64;  // 32-column chunks per half tile
+  using bf = __nv_bfloat16;
+  bf* outp = reinterpret_cast<bf*>(a.out) + (long long)t.g * a.out_g +
+             ((long long)t.q * a.out_q + (long long)t.rem * a.out_r + a.out_off) * a.ldc + t.n0 + cb;
+  const long long res_row = (long long)t.q * a.res_q + (long long)t.rem * a.res_r + a.res_off;
+  const bf* resp = (a.res && t.valid) ? reinterpret_cast<const bf*>(a.res) + (long long)t.g * a.res_g + res_row * a.ldres + t.n0 + cb : nullptr;
+  const float* filmp = (a.film_c && !films) ? a.film_c + (long long)t.g * a.film_g + (long long)t.q * a.film_ld + a.film_off + t.n0 + cb : nullptr;
+  const float* fs = films ? films + (t.valid ? (t.r / a.gn_rows) : 0) * 2 * BN + cb : nullptr;   // this row's sample
+  uint4 rr[4];
+  auto fetch_res = [&](int ch) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rr[i] = resp ? *reinterpret_cast<const uint4*>(resp + ch * 32 + i * 8) : make_uint4(0u, 0u, 0u, 0u);
+  };
+  fetch_res(0);
+
+  mbar_wait(acc_full, acc_parity);
+  tc_fence_after();
+  // ---- pass 1: per-row sums of (acc + bias) over every 32-column chunk ----
+  float s1[NCH], s2[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    uint32_t v[32];
+    tmem_ld32(t.taddr + cb + ch * 32, v);
+    tmem_ld_wait();
+    float2 a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(colv + cb + ch * 32 + j);
+      const float2 x0 = fadd2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(b4.x, b4.y));
+      const float2 x1 = fadd2(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), make_float2(b4.z, b4.w));
+      a1 = fadd2(a1, fadd2(x0, x1));
+      a2 = ffma2(x0, x0, a2);
+      a2 = ffma2(x1, x1, a2);
+    }
+    s1[ch] = t.valid ? a1.x + a1.y : 0.f;
+    s2[ch] = t.valid ? a2.x + a2.y : 0.f;
+  }
+  gn_sample_totals<NCH>(a, t, s1, s2, gn_part, gn_stat, et, bar_id);
+  const float cnt = (float)(a.gn_rows << a.gn_gs_log2);
+  float rstd[NCH], nmr[NCH];   // 1/std and -mean/std of the row's sample, per chunk (group)
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const float mean = s1[ch] / cnt;
+    rstd[ch] = rsqrtf(fmaxf(s2[ch] / cnt - mean * mean, 0.f) + a.gn_eps);
+    nmr[ch] = -mean * rstd[ch];
+  }
+  // ---- pass 2: normalise, affine, Mish, FiLM, residual, store ----
+#pragma unroll 1
+  for (int ch = 0; ch < NCH; ++ch) {
+    uint32_t v[32];
+    tmem_ld32(t.taddr + cb + ch * 32, v);
+    float rs = rstd[0], nm = nmr[0];
+#pragma unroll
+    for (int k = 1; k < NCH; ++k) {
+      rs = (ch == k) ? rstd[k] : rs;
+      nm = (ch == k) ? nmr[k] : nm;
+    }
+    const float2 rs2 = make_float2(rs, rs), nm2 = make_float2(nm, nm);
+    uint4 rc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rc[i] = rr[i];
+    if (ch + 1 < NCH) fetch_res(ch + 1);
+    tmem_ld_wait();
+    if (t.valid) {
+#pragma unroll
+      for (int j8 = 0; j8 < 32; j8 += 8) {
+        const int cc = ch * 32 + j8;
+        float2 y[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float4 b4 = *reinterpret_cast<const float4*>(colv + cb + cc + 4 * h);
+          const float4 g4 = *reinterpret_cast<const float4*>(colv + BN + cb + cc + 4 * h);
+          const float4 e4 = *reinterpret_cast<const float4*>(colv + 2 * BN + cb + cc + 4 * h);
+          float2 x0 = fadd2(make_float2(__uint_as_float(v[j8 + 4 * h]), __uint_as_float(v[j8 + 4 * h + 1])), make_float2(b4.x, b4.y));
+          float2 x1 = fadd2(make_float2(__uint_as_float(v[j8 + 4 * h + 2]), __uint_as_float(v[j8 + 4 * h + 3])), make_float2(b4.z, b4.w));
+          x0 = ffma2(ffma2(x0, rs2, nm2), make_float2(g4.x, g4.y), make_float2(e4.x, e4.y));
+          x1 = ffma2(ffma2(x1, rs2, nm2), make_float2(g4.z, g4.w), make_float2(e4.z, e4.w));
+          y[2 * h] = mish2(x0);
+          y[2 * h + 1] = mish2(x1);
+        }
+        if (fs) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float4 sc = *reinterpret_cast<const float4*>(fs + cc + 4 * h);
+            const float4 sh = *reinterpret_cast<const float4*>(fs + BN + cc + 4 * h);
+            y[2 * h] = ffma2(y[2 * h], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
+            y[2 * h + 1] = ffma2(y[2 * h + 1], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
+          }
+        } else if (filmp) {   // more samples per tile than the staging buffer holds: straight from global memory
+          float sc[8], sh[8];
+          load_res8(filmp + cc, sc);
+          load_res8(filmp + a.film_C + cc, sh);
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const float2 s2v = fadd2(make_float2(sc[2 * h], sc[2 * h + 1]), make_float2(colv[3 * BN + cb + cc + 2 * h], colv[3 * BN + cb + cc + 2 * h + 1]));
+            const float2 h2v = fadd2(make_float2(sh[2 * h], sh[2 * h + 1]), make_float2(colv[4 * BN + cb + cc + 2 * h], colv[4 * BN + cb + cc + 2 * h + 1]));
+            y[h] = ffma2(y[h], s2v, h2v);
+          }
+        }
+        if (resp) {
+          const uint4 rv = rc[j8 >> 3];
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+          for (int h = 0; h < 4; ++h) y[h] = fadd2(y[h], __bfloat1622float2(h2[h]));
+        }
+        uint4 w;
+        w.x = pack_bf16x2(y[0].x, y[0].y);
+        w.y = pack_bf16x2(y[1].x, y[1].y);
+        w.z = pack_bf16x2(y[2].x, y[2].y);
+        w.w = pack_bf16x2(y[3].x, y[3].y);
+        *reinterpret_cast<uint4*>(outp + cc) = w;
+      }
+    }
+  }
+}
+
+template <int BN, typename TOut, bool PRECISE>
+__device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t, const float* colv, float2* gn_part,
+                                            float2* gn_stat, int et, int bar_id, uint64_t* acc_full, uint32_t acc_parity,
+                                            OutStage& st, int cb) {
+  // `cb`: first tile column of the half this warpgroup handles (0 or BN / 2); colv / TMEM / output columns are tile-relative
+  const bool tma = a.tma_out != 0;
+  const long long oplane = a.out_plane, rplane = a.res_plane;
+  const int filmC = a.film_C;
+
+  static_assert(BN == 128 || BN == 256, "GN epilogue: whole 32/64-channel groups per tile");
+  constexpr int NCH = BN / 64;  // 32-column chunks per half tile (2 or 4): whole 32- / 64-channel groups
+  constexpr int CG = 128 / sizeof(TOut);
+  const int row0 = (int)(t.grow - (threadIdx.x & 31));
+  uint32_t box = 0;
+  TOut* outp = reinterpret_cast<TOut*>(a.out) + (long long)t.g * a.out_g +
+               ((long long)t.q * a.out_q + (long long)t.rem * a.out_r + a.out_off) * a.ldc + t.n0 + cb;
+  const long long res_row = (long long)t.q * a.res_q + (long long)t.rem * a.res_r + a.res_off;
+  const TOut* resp = a.res ? reinterpret_cast<const TOut*>(a.res) + (long long)t.g * a.res_g + res_row * a.ldres + t.n0 + cb : nullptr;
+  const float* filmp = a.film_c ? a.film_c + (long long)t.g * a.film_g + (long long)t.q * a.film_ld + a.film_off + t.n0 + cb : nullptr;
+  const int lane = threadIdx.x & 31;
+
+  mbar_wait(acc_full, acc_parity);
+  tc_fence_after();
+  float s1[NCH], s2[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    uint32_t v[32];
+    tmem_ld32(t.taddr + cb + ch * 32, v);
+    tmem_ld_wait();
+    float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = __uint_as_float(v[j]) + colv[cb + ch * 32 + j];
+      a1 += x;
+      a2 = fmaf(x, x, a2);
+    }
+    s1[ch] = t.valid ? a1 : 0.f;
+    s2[ch] = t.valid ? a2 : 0.f;
+  }
+  gn_sample_totals<NCH>(a, t, s1, s2, gn_part, gn_stat, et, bar_id);
+  const float cnt = (float)(a.gn_rows << a.gn_gs_log2);
   float mean[NCH], rstd[NCH];
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
@@ -821,8 +971,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     constexpr int HB = BN >= 64 ? BN / 2 : BN;    // columns per warpgroup (BN = 32: warpgroup 1 only signals)
     const int c_begin = half * HB, c_end = (BN >= 64 || half == 0) ? c_begin + HB : c_begin;
     constexpr int CV = GEMM_COLV_FLOATS(BN, MODE);
-    float2* gn_part = reinterpret_cast<float2*>(scratch + 2 * CV) + half * (128 + 64) * 4;   // [128][4]
-    float2* gn_stat = gn_part + 128 * 4;                                                      // [64][4]
+    constexpr bool GN_FAST = MODE == EPI_GN && sizeof(TOut) == 2 && !PRECISE;
+    float2* gn_part = reinterpret_cast<float2*>(scratch + CV) + half * (128 + 64) * 4;   // [128][4]   (GroupNorm only)
+    float2* gn_stat = gn_part + 128 * 4;                                                  // [64][4]
+    float* films = scratch + CV + 2 * (128 + 64) * 4 * 2;                                 // [8][2][BN] (GroupNorm only)
     EpiTile t;
     t.r = quarter * 32 + lane;
     OutStage st;
@@ -830,6 +982,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     st.count = 0;
     uint32_t lt = 0;
     const bool fast = GEMM_XPOSE_BYTES(BN, MODE) > 0 && a.fast != 0;
+    const int et256 = threadIdx.x - 64;
     for (int tile = worker; tile < a.total_tiles; tile += n_workers, ++lt) {
       const uint32_t acc = lt & 1;
       const int n_tile = tile % a.n_tiles;
@@ -837,12 +990,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       const int m_tile = (rest % a.m_tiles) * CTAS + rank;
       t.g = rest / a.m_tiles;
       t.n0 = n_tile * BN;
-      float* colv = scratch + acc * CV;    // [2][BN] (LINEAR) / [5][BN] (GroupNorm) column vectors of this tile
+      float* colv = scratch + (MODE == EPI_LINEAR ? acc * CV : 0);   // column vectors of this tile
+      bool film_staged = false;
       if (!fast) {
-        // stage the per-column vectors.  Set `acc` was last read two tiles ago and every warp has passed the barrier of
-        // the tile in between, so only the write -> read edge needs a barrier.
+        // Stage the per-column vectors.  LINEAR: set `acc` was last read two tiles ago and every warp has passed the
+        // barrier of the tile in between, so only the write -> read edge needs a barrier.  GroupNorm (one set): all
+        // readers of the previous tile must be done first.
+        if (MODE == EPI_GN) named_bar_sync(1, 256);
         const long long gcol = (long long)t.g * a.n_pad + t.n0;
-        for (int c = threadIdx.x - 64; c < BN; c += 256) {
+        for (int c = et256; c < BN; c += 256) {
           colv[c] = a.bias ? a.bias[gcol + c] : 0.f;
           if (MODE == EPI_LINEAR) {
             colv[BN + c] = (a.colscale && (t.n0 + c) < a.N) ? a.colscale[t.n0 + c] : 1.f;
@@ -853,6 +1009,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             const long long fo = (long long)t.g * a.film_tg + a.film_off + t.n0 + c;
             colv[3 * BN + c] = f ? a.film_t[fo] : 0.f;
             colv[4 * BN + c] = f ? a.film_t[fo + a.film_C] : 0.f;
+          }
+        }
+        if constexpr (GN_FAST) {
+          // FiLM scale / shift of every sample of the tile (cond part + time part), while the main loop runs
+          const int nsamp = a.rows_valid / a.gn_rows;
+          if (a.film_c && nsamp <= GEMM_FILM_SAMPLES) {
+            film_staged = true;
+            const long long smp0 = (long long)m_tile * nsamp;
+            const long long n_samples = a.M_total / a.gn_rows;
+            const float* fc = a.film_c + (long long)t.g * a.film_g + a.film_off + t.n0;
+            const float* ft = a.film_t ? a.film_t + (long long)t.g * a.film_tg + a.film_off + t.n0 : nullptr;
+            for (int i = et256; i < nsamp * 2 * BN; i += 256) {
+              const int c = i % BN, which = (i / BN) & 1, smp = i / (2 * BN);
+              float v = 0.f;
+              if (smp0 + smp < n_samples) {
+                v = fc[(smp0 + smp) * a.film_ld + which * a.film_C + c];
+                if (ft) v += ft[which * a.film_C + c];
+              }
+              films[i] = v;
+            }
           }
         }
         named_bar_sync(1, 256);
@@ -874,6 +1050,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           } else {
             epilogue_linear<BN, TOut, PRECISE>(a, t, colv, &acc_full[acc], parity, st, c_begin, c_end);
           }
+        } else if constexpr (GN_FAST) {
+          if (a.out_plane == 0 && a.res_plane == 0 && !a.tma_out)
+            epilogue_gn_fast<BN>(a, t, colv, film_staged ? films : nullptr, gn_part, gn_stat, et, 2 + half, &acc_full[acc], parity, c_begin);
+          else
+            epilogue_gn<BN, TOut, PRECISE>(a, t, colv, gn_part, gn_stat, et, 2 + half, &acc_full[acc], parity, st, c_begin);
         } else {
           epilogue_gn<BN, TOut, PRECISE>(a, t, colv, gn_part, gn_stat, et, 2 + half, &acc_full[acc], parity, st, c_begin);
         }
