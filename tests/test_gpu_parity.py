@@ -246,7 +246,9 @@ def test_kernels_match_the_descriptor_interpreter_op_by_op():
     import gpu_diff
     from vla_touch_b200.unet import UnetProgram
     # (10,16,3): ragged tiles -> direct-store epilogue; (7,32,9): full 128-row tiles -> TMA-store epilogue, M edge clipped
-    for A, T, B in ((10, 16, 3), (7, 32, 9)):
+    # (10,16,40): 5 / 3 / 2 row tiles per net -> CTA pairs with a missing second tile, 8 / 16 / 32 samples per tile (FiLM table
+    # staged in shared memory / read from global memory); (7,64,5): two samples per tile, odd tile count
+    for A, T, B in ((10, 16, 3), (7, 32, 9), (10, 16, 40), (7, 64, 5)):
         sds = [U.net_sd(A, 21, "v_net"), U.net_sd(A, 21, "s_net")]
         ups = []
         for dev in ("cpu", DEV):
@@ -300,3 +302,76 @@ def test_fused_adamw_ema_matches_torch():
         for a, b in zip(ema_new.shadow_params, ema_ref.shadow_params):
             torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-6)
     assert ema_new.num_updates == 5
+
+
+@pytest.mark.parametrize("tokens", [256, 257, 264, 272, 130, 730])
+def test_attention_kernels_against_fp32_softmax(tokens):
+    """attn_row_kernel (256..272 tokens: whole key range in TMEM, tail query rows on the CUDA cores) and the flash-style
+    attn_tc_kernel (any other count) against softmax(Q K^T / 8) V computed in fp32 from the same bf16 qkv rows (HF:199-235)."""
+    from vla_touch_b200 import native as nv
+    from vla_touch_b200.plan import Plan, ptr
+    images, heads = 3, 6
+    D = heads * 64
+    g = torch.Generator().manual_seed(tokens)
+    qkv32 = torch.randn(images * tokens, 3 * D, generator=g) * 1.5
+    plan = Plan(torch.device(DEV))
+    qkv = plan.buf("qkv", (images * tokens, 3 * D), torch.bfloat16)
+    ctx = plan.buf("ctx", (images * tokens, D), torch.bfloat16)
+    qkv.copy_(qkv32)
+    ctx.fill_(float("nan"))
+    d = nv.AttnDesc()
+    d.qkv, d.ctx, d.in_dtype, d.images, d.tokens, d.heads = ptr(qkv), ptr(ctx), nv.VT_BF16, images, tokens, heads
+    d.ctx_ld, d.ctx_plane = D, 0
+    plan.add(d, "attention")
+    plan.compile().run(0, 1)
+    torch.cuda.synchronize()
+    x = qkv.float().cpu().view(images, tokens, 3, heads, 64).permute(2, 0, 3, 1, 4)      # [3][img][head][tok][64]
+    ref = torch.softmax(x[0] @ x[1].transpose(-1, -2) / 8.0, dim=-1) @ x[2]
+    ref = ref.permute(0, 2, 1, 3).reshape(images * tokens, D)
+    got = ctx.float().cpu()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item(), (tokens, err, ref.abs().max().item())   # P and the output are bf16
+
+
+@pytest.mark.parametrize("shape", [(1300, 384, 1152, "none"), (700, 1536, 384, "res"), (515, 384, 1536, "gelu")])
+def test_cta_pair_gemm_matches_single_cta_gemm(shape, monkeypatch):
+    """The cta_group::2 kernels (M = 256 MMAs, operands split over a CTA pair) and the coalescing epilogue against the
+    single-CTA kernels with the generic epilogue, on ragged row counts (odd tile counts, a pair with one tile missing)."""
+    from vla_touch_b200 import native as nv
+    from vla_touch_b200.plan import Plan, linear_desc, pack_linear_weight
+    M, K, N, kind = shape
+    g = torch.Generator().manual_seed(M)
+    a32 = torch.randn(M, K, generator=g)
+    w32 = torch.randn(N, K, generator=g) / K ** 0.5
+    b32 = torch.randn(N, generator=g)
+    outs = []
+    for pair, fast in (("1", "1"), ("0", "0")):
+        monkeypatch.setenv("VT_GEMM_PAIR", pair)
+        monkeypatch.setenv("VT_GEMM_FAST", fast)
+        plan = Plan(torch.device(DEV))
+        a = plan.buf("a", (M, K), torch.bfloat16)
+        a.copy_(a32)
+        wp, n_pad, k_pad = pack_linear_weight(w32, torch.bfloat16)
+        w = plan.reg(wp.to(DEV))
+        bias = plan.reg(b32.to(DEV))
+        kw = {}
+        if kind == "res":
+            out = plan.buf("out", (M, N), torch.float32)
+            out.copy_(torch.arange(M * N, dtype=torch.float32).view(M, N) % 7 - 3)
+            scale = plan.reg((torch.arange(N, dtype=torch.float32) % 5 * 0.25 + 0.5).to(DEV))
+            kw = dict(colscale=scale, res=out, ldres=N)
+        else:
+            out = plan.buf("out", (M, N), torch.bfloat16)
+            if kind == "gelu":
+                kw = dict(act=nv.ACT_GELU)
+        plan.add(linear_desc(a=a, rows=M, k=k_pad, a_ld=K, w=w, n=N, n_pad=n_pad, w_ld=k_pad, out=out, ldc=N, bias=bias, **kw),
+                 "gemm")
+        plan.compile().run(0, 1)
+        torch.cuda.synchronize()
+        outs.append(out.float().cpu())
+    ref = a32.bfloat16().float() @ w32.bfloat16().float().t() + b32
+    tol = 2e-2 * ref.abs().max().item()
+    assert (outs[0] - outs[1]).abs().max().item() <= tol
+    if kind == "none":
+        assert (outs[0] - ref).abs().max().item() <= tol

@@ -21,7 +21,7 @@
 namespace vt {
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_THREADS = 320;
+constexpr int GEMM_THREADS = 320;   // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * 128;
 constexpr int GEMM_MAX_TAPS = 8;
 

@@ -236,7 +236,7 @@ int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
   VT_REQUIRE(d.row_div >= 1, "gemm: row_div=%d", d.row_div);
   // CTA pairs whenever the shape has at least two row tiles (env VT_GEMM_PAIR=0 keeps the single-CTA kernels: A/B runs)
   const int m_tiles_1 = (d.M + d.t_box * d.b_box - 1) / (d.t_box * d.b_box);
-  static const bool pair_enabled = !(getenv("VT_GEMM_PAIR") && atoi(getenv("VT_GEMM_PAIR")) == 0);
+  const bool pair_enabled = !(getenv("VT_GEMM_PAIR") && atoi(getenv("VT_GEMM_PAIR")) == 0);
   bool pair = pair_enabled && d.in_dtype == VT_BF16 && (d.bn == 256 || d.bn == 192) && m_tiles_1 >= 2 && d.passes == 1;
   if (d.epi == VT_EPI_GN && d.bn == 256) pair = true;   // the 256-wide GroupNorm epilogue exists as a pair kernel only
   GemmVariant* var = gemm_variant(d.in_dtype, d.bn, d.epi, d.out_dtype, pair);
