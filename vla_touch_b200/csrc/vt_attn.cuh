@@ -355,11 +355,13 @@ __global__ void __launch_bounds__(ATR_THREADS, 1) attn_row_kernel(const __grid_c
     tma_prefetch_desc(&a.tm16);
     tma_prefetch_desc(&a.tmO);
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 288;
+  pdl_wait();
 
   if (warp == 8) {
     // ------------------------------ TMA producer ------------------------------

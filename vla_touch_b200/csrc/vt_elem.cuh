@@ -203,6 +203,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         long long in_row_stride, int rows, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, void* __restrict__ out,
                                                         int out_dtype, long long out_ld, long long out_plane, int act) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int D = VEC * 128;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -337,6 +339,8 @@ __global__ void __launch_bounds__(256) sde_step_kernel(float* __restrict__ x, co
                                                        const unsigned long long* __restrict__ seed_dev, int step,
                                                        void* __restrict__ xpad, int xpad_dtype, int xpad_ld,
                                                        long long xpad_plane) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)rows * A;
   if (seed_dev) seed += *seed_dev;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;

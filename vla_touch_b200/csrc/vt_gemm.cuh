@@ -351,8 +351,10 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTi
   constexpr int NV = NC / 4;              // float4 pieces per lane row
   const int lane = threadIdx.x & 31;
   const int sr = lane / LPR, cg = lane % LPR;
-  const long long wrow0 = t.grow - lane;            // first logical row of this warp
+  const int wrow0 = (int)t.grow - lane;             // first logical row of this warp
   const int trow0 = t.r - lane;                     // ... and its row inside the tile
+  const int rdiv = a.row_div, oq = (int)a.out_q, orr = (int)a.out_r, ooff0 = (int)a.out_off;
+  const int rq = (int)a.res_q, rr_ = (int)a.res_r, roff0 = (int)a.res_off;
   TOut* outp = reinterpret_cast<TOut*>(a.out) + (long long)t.g * a.out_g + t.n0 + cg * NC;
   const float* resp = HAS_RES ? reinterpret_cast<const float*>(a.res) + (long long)t.g * a.res_g + t.n0 + cg * NC : nullptr;
   const float* biasp = a.bias ? a.bias + (long long)t.g * a.n_pad + t.n0 + cg * NC : nullptr;
@@ -362,11 +364,12 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTi
 #pragma unroll
   for (int i = 0; i < R; ++i) {
     const int row = i * RPI + sr;
-    const long long grow = wrow0 + row;
+    const int grow = wrow0 + row;
     const bool ok = (trow0 + row < a.rows_valid) && (grow < a.M_total);
-    const long long q = grow / a.row_div, rem = grow - q * a.row_div;
-    ooff[i] = ok ? (int)((q * a.out_q + rem * a.out_r + a.out_off) * a.ldc) : 0;
-    roff[i] = (ok && HAS_RES) ? (int)((q * a.res_q + rem * a.res_r + a.res_off) * a.ldres) : 0;
+    // a.fast guarantees that rows and element offsets fit 32 bits: no 64-bit divisions / multiplies per tile
+    const int q = rdiv == 1 ? grow : (int)((unsigned)grow / (unsigned)rdiv), rem = grow - q * rdiv;
+    ooff[i] = ok ? (q * oq + rem * orr + ooff0) * a.ldc : 0;
+    roff[i] = (ok && HAS_RES) ? (q * rq + rem * rr_ + roff0) * a.ldres : 0;
     vmask |= ok ? (1u << i) : 0u;
     rd[i] = xbuf + row * 128 + (((NV * cg) ^ (row & 7)) << 4);
   }
@@ -857,10 +860,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       tmem_relinquish();
     }
   }
+  pdl_launch_dependents();   // the next kernel may set itself up on SMs this grid has already left
   tc_fence_before();
   if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                // barriers, TMEM and descriptors are ready; now the producing kernel must have finished
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -1035,7 +1040,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
       t.grow = (long long)m_tile * a.rows_valid + t.r;
       t.valid = (t.r < a.rows_valid) && (t.grow < a.M_total);
-      t.q = (int)(t.grow / a.row_div);
+      t.q = a.row_div == 1 ? (int)t.grow : (int)((unsigned)t.grow / (unsigned)a.row_div);   // rows fit 32 bits (M is an int)
       t.rem = (int)(t.grow - (long long)t.q * a.row_div);
       t.taddr = tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
       const uint32_t parity = (lt >> 1) & 1;

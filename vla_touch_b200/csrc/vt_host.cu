@@ -108,6 +108,44 @@ struct Op {
     if (e__ != cudaSuccess) return fail(VT_E_CUDA, "%s launch: %s", name, cudaGetErrorString(e__)); \
   } while (0)
 
+// Launch with optional cluster-of-two and programmatic-dependent-launch attributes.  PDL (env VT_PDL=0 disables it): the
+// kernel may be scheduled while its stream predecessor drains; every kernel launched this way calls griddepcontrol.wait
+// before it touches global memory, so the data dependences are unchanged -- only launch latency and prologue are hidden.
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VT_PDL");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_ex(void (*fn)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool cluster2, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (cluster2) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = 2;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl && pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = (unsigned)n;
+  return cudaLaunchKernelEx(&cfg, fn, KArgs(args)...);
+}
+
 // ---- GEMM ----
 typedef void (*GemmKernel)(const vt::GemmArgs);
 struct GemmVariant {
@@ -190,24 +228,9 @@ struct GemmOp : Op {
       VT_CUDA(cudaFuncSetAttribute(var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, var->smem));
       var->attr_set = true;
     }
-    if (var->ctas == 2) {
-      cudaLaunchConfig_t cfg;
-      memset(&cfg, 0, sizeof(cfg));
-      cfg.gridDim = grid;
-      cfg.blockDim = dim3(vt::GEMM_THREADS, 1, 1);
-      cfg.dynamicSmemBytes = (size_t)var->smem;
-      cfg.stream = s;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = 2;
-      at[0].val.clusterDim.y = 1;
-      at[0].val.clusterDim.z = 1;
-      cfg.attrs = at;
-      cfg.numAttrs = 1;
-      cudaError_t e = cudaLaunchKernelEx(&cfg, var->fn, args);
-      if (e != cudaSuccess) return fail(VT_E_CUDA, "gemm_tc_kernel (CTA pairs) launch: %s", cudaGetErrorString(e));
-    } else {
-      var->fn<<<grid, vt::GEMM_THREADS, var->smem, s>>>(args);
+    {
+      cudaError_t e = launch_ex(var->fn, grid, dim3(vt::GEMM_THREADS, 1, 1), (size_t)var->smem, s, var->ctas == 2, true, args);
+      if (e != cudaSuccess) return fail(VT_E_CUDA, "gemm_tc_kernel launch: %s", cudaGetErrorString(e));
     }
     VT_LAUNCH_CHECK("gemm_tc_kernel");
     return VT_OK;
@@ -402,7 +425,10 @@ struct AttnOp : Op {
         VT_CUDA(cudaFuncSetAttribute(vt::attn_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vt::ATR_SMEM_BYTES));
         row_attr_set = true;
       }
-      vt::attn_row_kernel<<<grid, vt::ATR_THREADS, vt::ATR_SMEM_BYTES, s>>>(rargs);
+      {
+        cudaError_t e = launch_ex(vt::attn_row_kernel, grid, dim3(vt::ATR_THREADS, 1, 1), (size_t)vt::ATR_SMEM_BYTES, s, false, true, rargs);
+        if (e != cudaSuccess) return fail(VT_E_CUDA, "attn_row_kernel launch: %s", cudaGetErrorString(e));
+      }
       VT_LAUNCH_CHECK("attn_row_kernel");
     } else if (d.in_dtype == VT_BF16) {
       if (!attr_set) {
@@ -441,8 +467,8 @@ struct LnOp : Op {
   int launch(cudaStream_t s) override {
     const int blocks = (d.rows + 7) / 8;
 #define VT_LN(V)                                                                                                   \
-  vt::layernorm_kernel<V><<<blocks, 256, 0, s>>>(d.x, d.in_ld, d.in_row_stride, d.rows, d.gamma, d.beta, d.eps, d.out, \
-                                                 d.out_dtype, d.out_ld, d.out_plane, d.act)
+  launch_ex(vt::layernorm_kernel<V>, dim3(blocks), dim3(256), 0, s, false, true, d.x, d.in_ld, d.in_row_stride, d.rows, d.gamma, \
+            d.beta, d.eps, d.out, d.out_dtype, d.out_ld, d.out_plane, d.act)
     switch (d.D) {
       case 256: VT_LN(2); break;
       case 384: VT_LN(3); break;
@@ -538,7 +564,7 @@ struct TembedOp : Op {
 struct SdeOp : Op {
   vt_sde_desc d;
   int launch(cudaStream_t s) override {
-    vt::sde_step_kernel<<<grid_for((long long)d.rows * d.A, 256), 256, 0, s>>>(
+    launch_ex(vt::sde_step_kernel, dim3(grid_for((long long)d.rows * d.A, 256)), dim3(256), 0, s, false, true,
         d.x, d.v, d.s, d.noise, d.rows, d.A, d.ginv, d.dgg, d.eps, d.dt, d.nscale, d.d, (unsigned long long)d.seed,
         reinterpret_cast<const unsigned long long*>(d.seed_dev), d.step,
         d.xpad, d.xpad_dtype, d.xpad_ld, d.xpad_plane);
