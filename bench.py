@@ -273,11 +273,42 @@ def main():
     torch.cuda.synchronize()
     k_ms = ev0.elapsed_time(ev1) / reps
     achieved = fl / (k_ms * 1e-3) / 1e12
+    # DRAM traffic of that launch from the committed ncu --set full capture (profiles/ncu_traffic.json, bytes per launch)
+    traffic, traffic_src = None, None
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        for key, rec in table.get(args.workload, {}).items():
+            if eng.plan.tags[idx].endswith(key):
+                traffic, traffic_src = rec["dram_bytes"], rec["source"]
+    except Exception:
+        pass
+    # the attention kernel of one ViT layer, timed the same way (BASELINE metric: DinoV2 attention TFLOP/s vs peak)
+    attn = None
+    att_ops = [i for i, d in enumerate(eng.plan.descs) if isinstance(d, nv.AttnDesc) and a0 <= i < b1]
+    if att_ops:
+        ai = att_ops[-1]
+        d = eng.plan.descs[ai]
+        for _ in range(5):
+            prog.run(ai, 1)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(reps):
+            prog.run(ai, 1)
+        ev1.record()
+        torch.cuda.synchronize()
+        a_ms = ev0.elapsed_time(ev1) / reps
+        a_fl = 4.0 * d.tokens * d.tokens * 64 * d.heads * d.images
+        a_exp = float(d.tokens) * d.tokens * d.heads * d.images
+        attn = {"kernel": f"attention [{eng.plan.tags[ai]}]", "ms_per_launch": a_ms, "flops_per_launch": a_fl,
+                "achieved": a_fl / (a_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "frac_of_tensor_peak": a_fl / (a_ms * 1e-3) / 1e12 / peak_tf,
+                "exp_per_launch": a_exp,
+                "note": "head_dim 64: one exponential per 256 tensor FLOPs; at 16 MUFU ex2 / clock / SM the softmax alone "
+                        "needs 2x the cycles of the two MMAs, so the tensor pipe cannot exceed ~50 % in this kernel"}
     f_chunk = flops_per_chunk(hidden, layers, hw, T, A, F, eng.n_steps)
     step_tf = value / world * f_chunk / 1e12
     roofline = {"bound": "tensor", "kernel": f"gemm_tc_kernel [{eng.plan.tags[idx]}]", "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
-                "flops_per_launch": fl, "ms_per_launch": k_ms,
+                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src, "flops_per_launch": fl, "ms_per_launch": k_ms, "attention": attn,
                 "whole_step": {"algorithmic_tflops_per_gpu": step_tf, "frac_of_sustained": step_tf / peaks.get("bf16_tflops_sustained", 1400.0),
                                "gflop_per_chunk": f_chunk / 1e9, "executed_gemm_gflop_per_chunk": total_gemm_flops / batch / 1e9}}
     line = {

@@ -39,9 +39,10 @@ def _load_local_state_dict(model_name: str) -> Optional[Dict[str, torch.Tensor]]
         return None
 
 
-def prepare_images(images, device):
+def prepare_images(images, device, keep_pinned_host: bool = False):
     """Host-side part of visual_encoder.py:66-75: numpy -> float/255, [B,T,H,W,C] -> [B*T,H,W,C]; returns
-    (contiguous tensor on `device`, layout)."""
+    (contiguous tensor on `device`, layout).  keep_pinned_host: a contiguous pinned host tensor is returned as it is, for
+    the caller's own asynchronous upload."""
     if isinstance(images, np.ndarray):
         images = torch.from_numpy(images).float() / 255.0
     if images.dim() == 5:
@@ -59,6 +60,8 @@ def prepare_images(images, device):
     if layout == nv.LAYOUT_BCHW and images.shape[1] != 3:
         raise ValueError("Make sure that the channel dimension of the pixel values match with the one set in the "
                          f"configuration. Expected 3 but got {images.shape[1]}.")
+    if keep_pinned_host and images.device.type == "cpu" and images.is_pinned() and images.is_contiguous():
+        return images, layout
     return images.to(device, non_blocking=True).contiguous(), layout
 
 
