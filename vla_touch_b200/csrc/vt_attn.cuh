@@ -313,11 +313,10 @@ __global__ void __launch_bounds__(ATR_THREADS, 1) attn_row_kernel(const __grid_c
   uint64_t* q_full = bars + 6;        // [2]
   uint64_t* q_empty = bars + 8;       // [2]
   uint64_t* s_full = bars + 10;
-  uint64_t* s_empty = bars + 11;
   uint64_t* p_full = bars + 12;       // [5]
-  uint64_t* o_full = bars + 17;
-  uint64_t* o_empty = bars + 18;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* o_full = bars + 17;       // [2]  (O accumulators alternate per query tile)
+  uint64_t* o_empty = bars + 19;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
   float* xch = reinterpret_cast<float*>(smem + ATR_SMEM_XCH);
   float* tq = reinterpret_cast<float*>(smem + ATR_SMEM_TAIL);   // [64]
   float* tp = tq + 64;                                           // [272]
@@ -340,10 +339,11 @@ __global__ void __launch_bounds__(ATR_THREADS, 1) attn_row_kernel(const __grid_c
       mbar_init(v_full, 1);
       mbar_init(v_empty, has_tail ? 3 : 1);
       mbar_init(s_full, 1);
-      mbar_init(s_empty, 256);
       for (int i = 0; i < 5; ++i) mbar_init(&p_full[i], 128);
-      mbar_init(o_full, 1);
-      mbar_init(o_empty, 256);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&o_full[i], 1);
+        mbar_init(&o_empty[i], 256);
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(ATR_THREADS, 1) attn_row_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 288;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 288;   // O accumulators at columns 288 and 352
   pdl_wait();
 
   if (warp == 8) {
@@ -400,55 +400,62 @@ __global__ void __launch_bounds__(ATR_THREADS, 1) attn_row_kernel(const __grid_c
     }
   } else if (warp == 9) {
     // ------------------------------ UMMA issuer ------------------------------
-    if (lane == 0) {
-      uint32_t us = 0, qs = 0;
-      const uint32_t idesc_s = umma_idesc(UMMA_FMT_BF16, 128);
+    // S of query tile t+1 is issued in 64-key slices INTERLEAVED with the P V slices of tile t: slice c of S may be
+    // overwritten as soon as p_full[c] of tile t has completed (every row has read that slice and published its P), so
+    // the next tile's scores are ready when the softmax warps come back from the O read-out instead of one S MMA later.
+    if (lane == 0 && blockIdx.x < a.units) {
+      const uint32_t idesc_s = umma_idesc(UMMA_FMT_BF16, 64);
       const uint32_t idesc_st = umma_idesc(UMMA_FMT_BF16, 16);
       const uint32_t idesc_o = umma_idesc(UMMA_FMT_BF16, 64, 0, 1);
       const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(sV));
       const uint64_t pdesc = umma_smem_desc_sw128(smem_u32(sP));
-      for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x, ++us) {
-        const uint32_t kb = us & 1;
-        const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sK + kb * ATR_KBUF));
-        mbar_wait(&k_full[kb], (us >> 1) & 1);
-        for (int qt = 0; qt < 2; ++qt, ++qs) {
-          const uint32_t qb = qs & 1;
-          const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ + qb * ATT_TILE_BYTES));
-          mbar_wait(&q_full[qb], (qs >> 1) & 1);
-          mbar_wait(s_empty, (qs & 1) ^ 1);       // every softmax thread has finished reading the previous S
+      const uint32_t n_tiles = 2u * (uint32_t)((a.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
+      // S slice c (c = 4: the 16-key tail) of tile t: keys [64 c, 64 c + 64) are rows of the unit's contiguous K tiles
+      auto issue_s = [&](uint32_t t, int c) {
+        const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ + (t & 1) * ATT_TILE_BYTES));
+        const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sK + ((t >> 1) & 1) * ATR_KBUF)) + (uint64_t)(c * 64 * 128 >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_S + c * 64, qdesc + 2 * k, kdesc + 2 * k, c < 4 ? idesc_s : idesc_st, k != 0);
+      };
+      auto wait_inputs = [&](uint32_t t) {   // K tiles (first tile of a unit) and Q tile of tile t
+        if ((t & 1) == 0) mbar_wait(&k_full[(t >> 1) & 1], (t >> 2) & 1);
+        mbar_wait(&q_full[t & 1], (t >> 1) & 1);
+        tc_fence_after();
+      };
+      wait_inputs(0);
+      for (int c = 0; c < 4; ++c) issue_s(0, c);
+      if (has_tail) issue_s(0, 4);
+      umma_commit(s_full);
+      umma_commit(&q_empty[0]);
+      for (uint32_t t = 0; t < n_tiles; ++t) {
+        const bool more = t + 1 < n_tiles;
+        if ((t & 1) == 0) mbar_wait(v_full, (t >> 1) & 1);
+        const uint32_t o_tmem = tmem_O + (t & 1) * 64;
+        mbar_wait(&o_empty[t & 1], ((t >> 1) & 1) ^ 1);   // the O accumulator of two tiles ago has been read out
+        if (more) wait_inputs(t + 1);
+        tc_fence_after();
+        for (int c = 0; c < 4; ++c) {             // 64-key chunks of P, published one by one
+          mbar_wait(&p_full[c], t & 1);
           tc_fence_after();
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16(tmem_S + j * 128, qdesc + 2 * k, kdesc + (uint64_t)(j * (ATT_TILE_BYTES >> 4)) + 2 * k, idesc_s, k != 0);
-          }
-          if (has_tail) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16(tmem_S + 256, qdesc + 2 * k, kdesc + (uint64_t)(2 * (ATT_TILE_BYTES >> 4)) + 2 * k, idesc_st, k != 0);
-          }
-          umma_commit(s_full);
-          if (qt == 1) umma_commit(&k_empty[kb]);   // last use of this unit's K tiles
-          if (qt == 0) mbar_wait(v_full, us & 1);
-          mbar_wait(o_empty, (qs & 1) ^ 1);         // the previous query tile's O has been read out
-          tc_fence_after();
-          for (int c = 0; c < 4; ++c) {             // 64-key chunks of P, published one by one
-            mbar_wait(&p_full[c], qs & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_f16(tmem_O, pdesc + (uint64_t)(c * (ATT_TILE_BYTES >> 4)) + 2 * kk,
-                       vdesc + (uint64_t)((c * 64 + kk * 16) * 128 >> 4), idesc_o, (c | kk) != 0);
-          }
-          if (has_tail) {
-            mbar_wait(&p_full[4], qs & 1);
-            tc_fence_after();
-            umma_f16(tmem_O, pdesc + (uint64_t)(4 * (ATT_TILE_BYTES >> 4)), vdesc + (uint64_t)(256 * 128 >> 4), idesc_o, 1);
-          }
-          umma_commit(o_full);
-          if (qt == 1) umma_commit(v_empty);
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16(o_tmem, pdesc + (uint64_t)(c * (ATT_TILE_BYTES >> 4)) + 2 * kk,
+                     vdesc + (uint64_t)((c * 64 + kk * 16) * 128 >> 4), idesc_o, (c | kk) != 0);
+          if (more) issue_s(t + 1, c);
         }
+        if (has_tail) {
+          mbar_wait(&p_full[4], t & 1);
+          tc_fence_after();
+          umma_f16(o_tmem, pdesc + (uint64_t)(4 * (ATT_TILE_BYTES >> 4)), vdesc + (uint64_t)(256 * 128 >> 4), idesc_o, 1);
+          if (more) issue_s(t + 1, 4);
+        }
+        umma_commit(&o_full[t & 1]);
+        if (more) {
+          umma_commit(s_full);
+          umma_commit(&q_empty[(t + 1) & 1]);     // S of tile t+1 was the only reader of its Q tile
+        }
+        if ((t & 1) == 0) umma_commit(&k_empty[(t >> 1) & 1]);   // S of the unit's second tile (just issued) was the last use of K
+        else umma_commit(v_empty);                               // last P V of the unit
       }
     }
   } else if (warp < 8) {
@@ -461,6 +468,28 @@ __global__ void __launch_bounds__(ATR_THREADS, 1) attn_row_kernel(const __grid_c
     const uint32_t sP_row = smem_u32(sP) + half * 2 * ATT_TILE_BYTES + r * 128;   // this half's first chunk tile
     const int my_tail = half ? n_tail : 0;                                        // valid tail keys of this thread
     uint32_t qs = 0;
+    float inv_prev = 0.f;
+    __nv_bfloat16* dst_prev = nullptr;
+    // O accumulator of tile `t` (columns 288 + 64 (t & 1)): this thread's 32 channels, scaled by 1 / row sum, straight to
+    // global memory (64 contiguous bytes per row); frees the accumulator for tile t + 2.
+    auto read_out = [&](uint32_t t, float inv, __nv_bfloat16* dst) {
+      mbar_wait(&o_full[t & 1], (t >> 1) & 1);
+      tc_fence_after();
+      uint32_t w[32];
+      tmem_ld32(tmem_O + (t & 1) * 64 + lane_off + half * 32, w);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&o_empty[t & 1]);
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 o4;
+        o4.x = pack_bf16x2(__uint_as_float(w[i]) * inv, __uint_as_float(w[i + 1]) * inv);
+        o4.y = pack_bf16x2(__uint_as_float(w[i + 2]) * inv, __uint_as_float(w[i + 3]) * inv);
+        o4.z = pack_bf16x2(__uint_as_float(w[i + 4]) * inv, __uint_as_float(w[i + 5]) * inv);
+        o4.w = pack_bf16x2(__uint_as_float(w[i + 6]) * inv, __uint_as_float(w[i + 7]) * inv);
+        *reinterpret_cast<uint4*>(dst + i) = o4;
+      }
+    };
     for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x) {
       const int img = unit / a.heads, head = unit - img * a.heads;
       for (int qt = 0; qt < 2; ++qt, ++qs) {
@@ -469,70 +498,64 @@ __global__ void __launch_bounds__(ATR_THREADS, 1) attn_row_kernel(const __grid_c
         mbar_wait(s_full, qs & 1);
         tc_fence_after();
         const uint32_t s_addr = tmem_S + lane_off + half * 128;
-        uint32_t va[16], vb[16];
-        // ---- pass 1: row max over this thread's 128 (+ tail) columns, two TMEM loads in flight ----
-        float mx = -INFINITY;
-        tmem_ld16(s_addr, va);
+        // ---- the thread's 128 scores in ONE TMEM round trip (two x64 loads in flight), kept in registers for both
+        //      passes; only the 16 tail columns are read a second time ----
+        uint32_t v0[64], v1[64], vt[16];
+        tmem_ld64(s_addr, v0);
+        tmem_ld64(s_addr + 64, v1);
+        if (my_tail > 0) tmem_ld16(s_addr + 128, vt);
+        tmem_ld_wait();
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-        for (int g = 0; g < 8; g += 2) {
-          tmem_ld_wait();
-          tmem_ld16(s_addr + (g + 1) * 16, vb);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(va[i]));
-          tmem_ld_wait();
-          if (g + 2 < 8) tmem_ld16(s_addr + (g + 2) * 16, va);
-          else if (my_tail > 0) tmem_ld16(s_addr + 128, va);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(vb[i]));
+        for (int i = 0; i < 64; i += 2) {
+          m0 = fmaxf(m0, __uint_as_float(v0[i]));
+          m1 = fmaxf(m1, __uint_as_float(v0[i + 1]));
+          m2 = fmaxf(m2, __uint_as_float(v1[i]));
+          m3 = fmaxf(m3, __uint_as_float(v1[i + 1]));
         }
+        float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         if (my_tail > 0) {
-          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, i < my_tail ? __uint_as_float(va[i]) : -INFINITY);
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, i < my_tail ? __uint_as_float(vt[i]) : -INFINITY);
         }
         my_x[0] = mx;
-        tmem_ld16(s_addr, va);                        // first chunk of pass 2, overlapped with the exchange
         named_bar_sync(1 + quarter, 64);              // the two warps that share these 32 rows
         const float m = fmaxf(mx, peer_x[0]);
         const float2 msc = make_float2(-m * sl, -m * sl), sl2 = make_float2(sl, sl);
         // ---- pass 2: p = 2^(s*sl - m*sl) -> bf16 P (two 64-key chunk tiles per half) + row sum ----
-        float2 rsum = make_float2(0.f, 0.f);
-        auto exp16 = [&](const uint32_t(&v)[16], uint32_t row_addr, int piece0) {
+        float2 rsum = make_float2(0.f, 0.f), rsum2 = make_float2(0.f, 0.f);
+        auto exp64 = [&](const uint32_t(&v)[64], uint32_t row_addr) {
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
+          for (int u = 0; u < 8; ++u) {               // 8 keys = one 16-byte piece of the 128-byte P row
             uint32_t pk[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int i = u * 8 + 2 * e;
               const float2 x = ffma2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sl2, msc);
               const float2 pp = make_float2(ex2_approx(x.x), ex2_approx(x.y));
-              rsum = fadd2(rsum, pp);
+              if (e & 1) rsum2 = fadd2(rsum2, pp); else rsum = fadd2(rsum, pp);
               pk[e] = pack_bf16x2(pp.x, pp.y);
             }
-            st_shared_v4(row_addr + (((piece0 + u) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+            st_shared_v4(row_addr + ((u ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
           }
         };
-#pragma unroll
-        for (int g = 0; g < 8; g += 2) {
-          tmem_ld_wait();
-          tmem_ld16(s_addr + (g + 1) * 16, vb);
-          exp16(va, sP_row + (g >> 2) * ATT_TILE_BYTES, (g & 3) * 2);
-          tmem_ld_wait();
-          if (g + 2 < 8) tmem_ld16(s_addr + (g + 2) * 16, va);
-          else if (my_tail > 0) tmem_ld16(s_addr + 128, va);
-          exp16(vb, sP_row + (g >> 2) * ATT_TILE_BYTES, (g & 3) * 2 + 2);
-          if ((g & 3) == 2) {                         // a 64-key chunk of P is complete for this row
-            fence_proxy_async_smem();
-            mbar_arrive(&p_full[half * 2 + (g >> 2)]);
-          }
-        }
+        exp64(v0, sP_row);
+        fence_proxy_async_smem();                     // chunk complete for this row; its S slice is dead
+        tc_fence_before();
+        mbar_arrive(&p_full[half * 2]);
+        exp64(v1, sP_row + ATT_TILE_BYTES);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&p_full[half * 2 + 1]);
+        rsum = fadd2(rsum, rsum2);
         if (has_tail && half == 1) {
+          tmem_ld16(s_addr + 128, vt);
           tmem_ld_wait();
           uint32_t pk[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int i = 2 * e;
-            const float2 x = ffma2(make_float2(__uint_as_float(va[i]), __uint_as_float(va[i + 1])), sl2, msc);
+            const float2 x = ffma2(make_float2(__uint_as_float(vt[i]), __uint_as_float(vt[i + 1])), sl2, msc);
             float2 pp = make_float2(ex2_approx(x.x), ex2_approx(x.y));
             pp.x = i < my_tail ? pp.x : 0.f;
             pp.y = i + 1 < my_tail ? pp.y : 0.f;
@@ -544,43 +567,21 @@ __global__ void __launch_bounds__(ATR_THREADS, 1) attn_row_kernel(const __grid_c
           st_shared_v4(row_addr + ((1 ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
           fence_proxy_async_smem();
         }
-        if (has_tail && half == 1) mbar_arrive(&p_full[4]);   // the tail chunk belongs to the upper half's 128 threads
-        tc_fence_before();
-        mbar_arrive(s_empty);                         // S may be overwritten by the next query tile
-        // ---- row sum exchange, O read-out ----
+        if (has_tail && half == 1) {                  // the tail chunk belongs to the upper half's 128 threads
+          tc_fence_before();
+          mbar_arrive(&p_full[4]);
+        }
+        // ---- row sum exchange; O of the PREVIOUS tile is read out now, while this tile's P V (and the next tile's S)
+        //      drain through the tensor pipe ----
         my_x[256] = rsum.x + rsum.y;
         named_bar_sync(1 + quarter, 64);
         const float inv = 1.0f / (rsum.x + rsum.y + peer_x[256]);
-        mbar_wait(o_full, qs & 1);
-        tc_fence_after();
-        uint32_t w[32];
-        tmem_ld32(tmem_O + lane_off + half * 32, w);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(o_empty);
-        // stage this row's 32 channels (64 bytes) in the dead Q tile, 128B-swizzled as the TMA store expects
-        const uint32_t qb = qs & 1;
-        const uint32_t o_row = smem_u32(sQ) + qb * ATT_TILE_BYTES + r * 128;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = u * 8;
-          st_shared_v4(o_row + (((half * 4 + u) ^ sw) << 4),
-                       pack_bf16x2(__uint_as_float(w[i]) * inv, __uint_as_float(w[i + 1]) * inv),
-                       pack_bf16x2(__uint_as_float(w[i + 2]) * inv, __uint_as_float(w[i + 3]) * inv),
-                       pack_bf16x2(__uint_as_float(w[i + 4]) * inv, __uint_as_float(w[i + 5]) * inv),
-                       pack_bf16x2(__uint_as_float(w[i + 6]) * inv, __uint_as_float(w[i + 7]) * inv));
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(5, 256);
-        if (threadIdx.x == 0) {
-          tma_store_2d(&a.tmO, o_row - r * 128, head * 64, img * N + qt * 128);
-          bulk_commit();
-          bulk_wait_read<0>();                        // the tile has been read: the producer may load the next Q into it
-          mbar_arrive(&q_empty[qb]);
-        }
+        if (qs > 0) read_out(qs - 1, inv_prev, dst_prev);
+        inv_prev = inv;
+        dst_prev = a.ctx + ((long long)img * N + qt * 128 + r) * a.ctx_ld + head * 64 + half * 32;
       }
     }
-    if (threadIdx.x == 0) bulk_wait_all();
+    if (qs > 0) read_out(qs - 1, inv_prev, dst_prev);
   } else if (has_tail) {
     // ------------------------------ tail query rows on the CUDA cores (warps 10, 11) ------------------------------
     const int tw = warp - 10;                 // 0 / 1
@@ -590,19 +591,26 @@ __global__ void __launch_bounds__(ATR_THREADS, 1) attn_row_kernel(const __grid_c
       const int img = unit / a.heads, head = unit - img * a.heads;
       const uint32_t kb = us & 1;
       const uint32_t kbase = smem_u32(sK + kb * ATR_KBUF), vbase = smem_u32(sV);
-      mbar_wait(&k_full[kb], (us >> 1) & 1);
       for (int tr = 0; tr < n_tail; ++tr) {
         const long long qrow = (long long)img * N + 256 + tr;
-        named_bar_sync(6, 64);                // previous row's readers of tq / tp / tpart are done
-        tq[tid] = __bfloat162float(a.qkv[qrow * (3LL * a.D) + head * 64 + tid]);
-        named_bar_sync(6, 64);
+        // the query row straight into registers (every lane reads the same 128 bytes: one L1 line, broadcast)
         float q[64];
+        {
+          const uint4* q4 = reinterpret_cast<const uint4*>(a.qkv + qrow * (3LL * a.D) + head * 64);
 #pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(tq + i);
-          q[i] = t4.x; q[i + 1] = t4.y; q[i + 2] = t4.z; q[i + 3] = t4.w;
+          for (int i = 0; i < 8; ++i) {
+            const uint4 raw = q4[i];
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(h2[e]);
+              q[i * 8 + 2 * e] = f.x * a.scale_log2;     // fold log2(e) / sqrt(d) into the query
+              q[i * 8 + 2 * e + 1] = f.y * a.scale_log2;
+            }
+          }
         }
-        // scores of keys tid, tid + 64, ... (5 per thread)
+        if (tr == 0) mbar_wait(&k_full[kb], (us >> 1) & 1);
+        // scores of keys tid, tid + 64, ... (5 per thread), two independent accumulators per key
         float sc[5];
         float mx = -INFINITY;
 #pragma unroll
@@ -611,7 +619,7 @@ __global__ void __launch_bounds__(ATR_THREADS, 1) attn_row_kernel(const __grid_c
           float acc = -INFINITY;
           if (k < N) {
             const uint32_t row = kbase + k * 128;   // tiles are contiguous: key k lives at row k of the 128-byte rows
-            acc = 0.f;
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
             for (int pc = 0; pc < 8; ++pc) {
               const float4 raw = ld_shared_v4f(row + ((pc ^ (k & 7)) << 4));
@@ -619,16 +627,17 @@ __global__ void __launch_bounds__(ATR_THREADS, 1) attn_row_kernel(const __grid_c
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 f = __bfloat1622float2(h2[e]);
-                acc = fmaf(q[pc * 8 + 2 * e], f.x, acc);
-                acc = fmaf(q[pc * 8 + 2 * e + 1], f.y, acc);
+                a0 = fmaf(q[pc * 8 + 2 * e], f.x, a0);
+                a1 = fmaf(q[pc * 8 + 2 * e + 1], f.y, a1);
               }
             }
-            acc *= a.scale_log2;
+            acc = a0 + a1;
           }
           sc[j] = acc;
           mx = fmaxf(mx, acc);
         }
         mx = warp_max(mx);
+        named_bar_sync(6, 64);                // the previous row's readers of tred / tp / tpart are done
         if (lane == 0) tred[tw] = mx;
         named_bar_sync(6, 64);
         mx = fmaxf(tred[0], tred[1]);
@@ -642,26 +651,41 @@ __global__ void __launch_bounds__(ATR_THREADS, 1) attn_row_kernel(const __grid_c
         }
         sum = warp_sum(sum);
         if (lane == 0) tred[2 + tw] = sum;
-        mbar_wait(v_full, us & 1);
+        if (tr == 0) mbar_wait(v_full, us & 1);
         named_bar_sync(6, 64);
         const float inv = 1.0f / (tred[2] + tred[3]);
-        // O[c] = sum_k p[k] V[k][c]: lane -> channel pair (2 lane, 2 lane + 1), warp tw -> keys k = tw (mod 2)
-        float o0 = 0.f, o1 = 0.f;
-        for (int k = tw; k < N; k += 2) {
+        // O[c] = sum_k p[k] V[k][c]: lane -> channel pair (2 lane, 2 lane + 1), warp tw -> keys k = tw (mod 2);
+        // four independent accumulator pairs keep the FMA chains short
+        float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t vcol = ((lane & 3) << 2), vpc = lane >> 2;
+        int k = tw;
+        for (; k + 6 < N; k += 8) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int kk = k + 2 * u;
+            uint32_t raw;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(raw) : "r"(vbase + kk * 128 + ((vpc ^ (kk & 7)) << 4) + vcol));
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw));
+            const float pk = tp[kk];
+            o0[u] = fmaf(pk, f.x, o0[u]);
+            o1[u] = fmaf(pk, f.y, o1[u]);
+          }
+        }
+        for (; k < N; k += 2) {
           uint32_t raw;
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(raw) : "r"(vbase + k * 128 + (((lane >> 2) ^ (k & 7)) << 4) + (lane & 3) * 4));
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(raw) : "r"(vbase + k * 128 + ((vpc ^ (k & 7)) << 4) + vcol));
           const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw));
           const float pk = tp[k];
-          o0 = fmaf(pk, f.x, o0);
-          o1 = fmaf(pk, f.y, o1);
+          o0[0] = fmaf(pk, f.x, o0[0]);
+          o1[0] = fmaf(pk, f.y, o1[0]);
         }
-        tpart[tw * 64 + 2 * lane] = o0;
-        tpart[tw * 64 + 2 * lane + 1] = o1;
+        tpart[tw * 64 + 2 * lane] = (o0[0] + o0[1]) + (o0[2] + o0[3]);
+        tpart[tw * 64 + 2 * lane + 1] = (o1[0] + o1[1]) + (o1[2] + o1[3]);
         named_bar_sync(6, 64);
         if (tw == 0) {
-          o0 = (tpart[2 * lane] + tpart[64 + 2 * lane]) * inv;
-          o1 = (tpart[2 * lane + 1] + tpart[64 + 2 * lane + 1]) * inv;
-          *reinterpret_cast<uint32_t*>(a.ctx + qrow * a.ctx_ld + head * 64 + 2 * lane) = pack_bf16x2(o0, o1);
+          const float r0 = (tpart[2 * lane] + tpart[64 + 2 * lane]) * inv;
+          const float r1 = (tpart[2 * lane + 1] + tpart[64 + 2 * lane + 1]) * inv;
+          *reinterpret_cast<uint32_t*>(a.ctx + qrow * a.ctx_ld + head * 64 + 2 * lane) = pack_bf16x2(r0, r1);
         }
       }
       // this warp is done with the unit's K and V tiles

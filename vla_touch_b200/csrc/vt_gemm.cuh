@@ -865,7 +865,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();                // barriers, TMEM and descriptors are ready; now the producing kernel must have finished
+  // Barriers, TMEM and descriptors are ready; from here on the producing kernel must have finished (programmatic
+  // dependent launch).  Only the producer thread runs ahead: the WEIGHT tiles of its first stages do not depend on the
+  // predecessor, so their HBM round trip is started before the wait.
+  int pre_atoms = 0;
+  if (warp == 0 && lane == 0 && a.passes == 1 && (a.debug & 5) == 0 && worker < a.total_tiles) {
+    const int per_pass = a.taps * a.cblocks;          // == nk
+    const int pre_stages = (per_pass + KA - 1) / KA < STAGES ? (per_pass + KA - 1) / KA : STAGES;
+    const int n_tile0 = worker % a.n_tiles, g0 = (worker / a.n_tiles) / a.m_tiles;
+    const int g_b0 = g0 * a.n_pad + n_tile0 * BN + rank * B_ROWS;
+    for (int st = 0; st < pre_stages; ++st) {
+      const int left = per_pass - st * KA;
+      const int n_at = left < KA ? left : KA;
+      if (rank == 0) mbar_arrive_expect_tx(&full[st], n_at * CTAS * (a.a_box_bytes + B_ATOM_BYTES));   // ring is empty: no wait
+      for (int at = 0; at < n_at; ++at) {
+        const int kb = (st * KA + at) * KE;
+        if constexpr (CTAS == 2)
+          tma_load_2d_pair(sB + st * B_STAGE_BYTES + at * B_ATOM_BYTES, &a.tmB, mapa_shared(smem_u32(&full[st]), 0), kb, g_b0);
+        else
+          tma_load_2d(sB + st * B_STAGE_BYTES + at * B_ATOM_BYTES, &a.tmB, &full[st], kb, g_b0);
+        ++pre_atoms;
+      }
+    }
+  }
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -876,6 +899,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       const int dn = n_workers % a.n_tiles, dr = n_workers / a.n_tiles;
       const bool no_tma = (a.debug & 5) != 0;
       int at = 0, n_at = 0;   // atoms issued into / planned for the current stage
+      int atom_seq = 0;       // atoms handled so far (the first pre_atoms already have their stage opened and B in flight)
       for (int tile = worker; tile < a.total_tiles; tile += n_workers) {
         int left = nk;
         const int m_tile = (rest % a.m_tiles) * CTAS + rank;
@@ -889,22 +913,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           for (int tp = 0; tp < a.taps; ++tp) {
             const int tap_p = a.tap_p[tp], tap_t = t_base + a.tap_t[tp];
             for (int cb = 0; cb < a.cblocks; ++cb, kb += KE) {
+              const bool pre = atom_seq < pre_atoms;   // stage opened and weight tile requested before pdl_wait
+              ++atom_seq;
               if (at == 0) {   // open a stage: it will receive min(KA, k-blocks left in this tile) atoms
                 n_at = left < KA ? left : KA;
-                mbar_wait(&empty[s], ph ^ 1);
-                if (rank == 0) {   // the leader's barrier counts the bytes of both CTAs
-                  if (no_tma) mbar_arrive(&full[s]);
-                  else mbar_arrive_expect_tx(&full[s], n_at * CTAS * (a.a_box_bytes + B_ATOM_BYTES));
+                if (!pre) {
+                  mbar_wait(&empty[s], ph ^ 1);
+                  if (rank == 0) {   // the leader's barrier counts the bytes of both CTAs
+                    if (no_tma) mbar_arrive(&full[s]);
+                    else mbar_arrive_expect_tx(&full[s], n_at * CTAS * (a.a_box_bytes + B_ATOM_BYTES));
+                  }
                 }
               }
               if (!no_tma) {
                 if constexpr (CTAS == 2) {
                   const uint32_t fb = mapa_shared(smem_u32(&full[s]), 0);
                   tma_load_5d_pair(sA + s * A_STAGE_BYTES + at * A_ATOM_BYTES, &a.tmA, fb, pa + cb * KE, tap_p, tap_t, b_base, g_a);
-                  tma_load_2d_pair(sB + s * B_STAGE_BYTES + at * B_ATOM_BYTES, &a.tmB, fb, kb, g_b);
+                  if (!pre) tma_load_2d_pair(sB + s * B_STAGE_BYTES + at * B_ATOM_BYTES, &a.tmB, fb, kb, g_b);
                 } else {
                   tma_load_5d(sA + s * A_STAGE_BYTES + at * A_ATOM_BYTES, &a.tmA, &full[s], pa + cb * KE, tap_p, tap_t, b_base, g_a);
-                  tma_load_2d(sB + s * B_STAGE_BYTES + at * B_ATOM_BYTES, &a.tmB, &full[s], kb, g_b);
+                  if (!pre) tma_load_2d(sB + s * B_STAGE_BYTES + at * B_ATOM_BYTES, &a.tmB, &full[s], kb, g_b);
                 }
               }
               --left;
