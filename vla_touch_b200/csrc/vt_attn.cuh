@@ -264,11 +264,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc_kernel(const __grid_co
 // work unit = one (image, head).  The whole key range fits TMEM, so there is no online-softmax rescaling:
 //   warp 8   TMA producer: K tiles (2 x 128 rows + a 16-row tail box; double-buffered across units), V tiles (single
 //            buffer: free again one query tile before the next unit needs it), Q tiles (2-deep ring)
-//   warp 9   UMMA issuer : S = Q K^T for ALL keys into TMEM columns [0, 272); then O = P V per 64-key chunk as soon
-//            as the softmax warps have published that chunk of P
-//   warps 0-7  softmax   : two threads per query row (keys [0,128) / [128, 272)); pass 1 row max, pass 2
+//   warp 9   UMMA issuer : S = Q K^T for ALL keys into TMEM columns [0, 272), issued in 64-key slices interleaved with
+//            the previous tile's O = P V slices (a slice of S may be overwritten once the p_full barrier of the chunk
+//            it holds has completed); two O accumulators (columns 288 / 352) alternate per query tile
+//   warps 0-7  softmax   : two threads per query row (keys [0,128) / [128, 272)); the 128 scores are read from TMEM
+//            once (two x64 loads in flight) and stay in registers for the max pass and the exp pass;
 //            p = 2^(s*c - m*c) -> bf16 P chunk tiles in shared memory (128B-swizzled K-major UMMA operand) + row sums;
-//            O is read once per query tile, scaled by 1/sum, staged in the (dead) Q tile and written by ONE TMA store
+//            O of tile t-1 is read out (scaled by 1/sum, 64 contiguous bytes per row) while tile t's MMAs drain
 //   warps 10-11  tail rows: the 1..16 query rows behind the last full tile (the CLS-shifted 257th token) on the CUDA
 //            cores, straight from the K / V tiles that are already in shared memory - no 128-row tile that is 99 %
 //            padding, no second pass over K and V in HBM.

@@ -5,12 +5,13 @@
 // with the op that follows fused into the epilogue: bias, GELU/Mish, LayerScale + residual, or
 // GroupNorm(8) + Mish + FiLM / residual (Conv1dBlock + ConditionalResidualBlock1D, :40-105).
 //
-// PERSISTENT kernel: one CTA per SM walks a static round-robin list of 128 x BN output tiles.
+// PERSISTENT kernel: one CTA per SM (or one CTA PAIR per TPC, CTAS = 2) walks a static round-robin list of output tiles.
 //   warp 0      TMA producer: A/B k-blocks through a STAGES-deep mbarrier ring that runs ahead across tiles
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer; two accumulators in TMEM (2 x BN columns)
-//   warps 2-5   epilogue warpgroup 0 (accumulator 0: even local tiles)
-//   warps 6-9   epilogue warpgroup 1 (accumulator 1: odd local tiles)
+//   warps 2-9   epilogue: both warpgroups work on every tile (column halves), accumulator = local tile index & 1,
 // so the epilogue of tile i (tcgen05.ld, GroupNorm / activation math, global stores) overlaps the main loop of tile i+1.
+// CTA pairs: tcgen05 cta_group::2, M = 256 per MMA; each CTA stages its own 128 rows of A and half of the B tile, the
+// leader CTA issues the MMAs and owns the `full` barriers, commits are multicast to both CTAs.
 // A-tiles are fetched with a 5-D tensor map (C, phase, T, B, G): a conv tap is a TMA box whose T coordinate is
 // shifted (out-of-bounds rows are zero-filled by the TMA unit = the conv's zero padding), a stride-2 conv reads the
 // even/odd phase, and v_net / s_net are the G dimension, so no im2col buffer ever exists.
