@@ -22,7 +22,8 @@
 namespace vt {
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_THREADS = 320;   // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue
+// warp 0 TMA producer, warp 1 MMA issuer, then EW = 8 or 12 epilogue warps (two or three per TMEM lane quarter)
+__host__ __device__ constexpr int GEMM_THREADS(int EW) { return 64 + 32 * EW; }
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * 128;
 constexpr int GEMM_MAX_TAPS = 8;
 
@@ -113,15 +114,15 @@ __host__ __device__ constexpr int GEMM_SCRATCH_FLOATS(int BN, int MODE) {
 #endif
 constexpr int GEMM_OUT_STAGE_BYTES = VT_GEMM_TMA_STORE ? 8 * 2 * 4096 : 0;
 // Per-warp 32 x 32 fp32 transposition buffer of the coalescing epilogue (8 epilogue warps x 4 KB).
-__host__ __device__ constexpr int GEMM_XPOSE_BYTES(int BN, int MODE) { return (MODE == 0 && BN >= 128) ? 8 * 4096 : 0; }
+__host__ __device__ constexpr int GEMM_XPOSE_BYTES(int BN, int MODE, int EW = 8) { return (MODE == 0 && BN >= 128) ? EW * 4096 : 0; }
 
 // KA = number of 128-byte-wide K atoms (64 bf16 / 32 tf32 elements of K each) per pipeline stage.
 // One mbarrier wait + tcgen05.commit per stage costs the single issuing thread ~450 cycles (measured), more than the MMA
 // time of one atom at BN=128, so a stage carries KA atoms (2 x 4 UMMA instructions per barrier round).
-template <int BN, int STAGES, int MODE, int KA, int CTAS = 1>
+template <int BN, int STAGES, int MODE, int KA, int CTAS = 1, int EW = 8>
 constexpr int gemm_smem_bytes() {
   return 1024 /*align slack*/ + STAGES * KA * (GEMM_A_STAGE_BYTES + (BN / CTAS) * 128) + GEMM_OUT_STAGE_BYTES +
-         GEMM_XPOSE_BYTES(BN, MODE) + 256 /*barriers*/ + GEMM_SCRATCH_FLOATS(BN, MODE) * 4;
+         GEMM_XPOSE_BYTES(BN, MODE, EW) + 256 /*barriers*/ + GEMM_SCRATCH_FLOATS(BN, MODE) * 4;
 }
 
 template <typename TOut>
@@ -352,6 +353,7 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTi
   constexpr int NV = NC / 4;              // float4 pieces per lane row
   const int lane = threadIdx.x & 31;
   const int sr = lane / LPR, cg = lane % LPR;
+  const int dbg = a.debug;
   const int wrow0 = (int)t.grow - lane;             // first logical row of this warp
   const int trow0 = t.r - lane;                     // ... and its row inside the tile
   const int rdiv = a.row_div, oq = (int)a.out_q, orr = (int)a.out_r, ooff0 = (int)a.out_off;
@@ -401,16 +403,22 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTi
       sc[h] = scalep ? *reinterpret_cast<const float4*>(scalep + c + 4 * h) : make_float4(1.f, 1.f, 1.f, 1.f);
     }
     tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) st_shared_v4(wr + ((j ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    __syncwarp();
     float4 x[R * NV];
+    if (dbg & 32) {   // developer knob: no transposition through shared memory (results are wrong, timing only)
 #pragma unroll
-    for (int i = 0; i < R; ++i) {
-      x[i * NV] = ld_shared_v4f(rd[i]);
-      if constexpr (NV == 2) x[i * NV + 1] = ld_shared_v4f(rd[i] ^ 16u);   // piece 2cg+1: same row, the neighbouring 16 bytes
+      for (int i = 0; i < R * NV; ++i)
+        x[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) st_shared_v4(wr + ((j ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        x[i * NV] = ld_shared_v4f(rd[i]);
+        if constexpr (NV == 2) x[i * NV + 1] = ld_shared_v4f(rd[i] ^ 16u);   // piece 2cg+1: same row, the neighbouring 16 bytes
+      }
+      __syncwarp();
     }
-    __syncwarp();
 #pragma unroll
     for (int i = 0; i < R; ++i) {
       float4 y[NV];
@@ -442,7 +450,9 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTi
         }
         y[h] = make_float4(y0.x, y0.y, y1.x, y1.y);
       }
-      if ((vmask >> i) & 1) {
+      if (dbg & 16) {   // developer knob: keep the math alive, produce no store traffic
+        if (y[0].x == 123.456f) outp[ooff[i] + c] = TOut(y[0].y);
+      } else if ((vmask >> i) & 1) {
         if constexpr (sizeof(TOut) == 4) {
           *reinterpret_cast<float4*>(outp + ooff[i] + c) = y[0];
         } else {
@@ -463,17 +473,11 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTi
 template <int BN, typename TOut, bool PRECISE>
 __device__ __forceinline__ void epilogue_linear_fast(const GemmArgs& a, const EpiTile& t, uint32_t xbuf, uint64_t* acc_full,
                                                      uint32_t parity, int c0, int c1) {
-  const bool res = a.res != nullptr;
-  if (a.act == ACT_GELU) {
-    if (res) epilogue_linear_t<BN, TOut, PRECISE, ACT_GELU, true>(a, t, xbuf, acc_full, parity, c0, c1);
-    else epilogue_linear_t<BN, TOut, PRECISE, ACT_GELU, false>(a, t, xbuf, acc_full, parity, c0, c1);
-  } else if (a.act == ACT_MISH) {
-    if (res) epilogue_linear_t<BN, TOut, PRECISE, ACT_MISH, true>(a, t, xbuf, acc_full, parity, c0, c1);
-    else epilogue_linear_t<BN, TOut, PRECISE, ACT_MISH, false>(a, t, xbuf, acc_full, parity, c0, c1);
-  } else {
-    if (res) epilogue_linear_t<BN, TOut, PRECISE, ACT_NONE, true>(a, t, xbuf, acc_full, parity, c0, c1);
-    else epilogue_linear_t<BN, TOut, PRECISE, ACT_NONE, false>(a, t, xbuf, acc_full, parity, c0, c1);
-  }
+  // the three combinations the path uses (host sets a.fast only for these): GELU without residual (fc1), plain (qkv,
+  // patch embed, U-Net linear convs), plain + residual (attention out-projection, fc2)
+  if (a.act == ACT_GELU) epilogue_linear_t<BN, TOut, PRECISE, ACT_GELU, false>(a, t, xbuf, acc_full, parity, c0, c1);
+  else if (a.res != nullptr) epilogue_linear_t<BN, TOut, PRECISE, ACT_NONE, true>(a, t, xbuf, acc_full, parity, c0, c1);
+  else epilogue_linear_t<BN, TOut, PRECISE, ACT_NONE, false>(a, t, xbuf, acc_full, parity, c0, c1);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -799,8 +803,9 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
   }
 }
 
-template <typename TIn, int BN, int MODE, typename TOut, int STAGES, bool PRECISE, int KA, int CTAS>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs a) {
+template <typename TIn, int BN, int MODE, typename TOut, int STAGES, bool PRECISE, int KA, int CTAS, int EW>
+__global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __grid_constant__ GemmArgs a) {
+  static_assert(EW == 8 || (EW == 12 && MODE == EPI_LINEAR), "epilogue warps: 8, or 12 for the LINEAR epilogue");
   constexpr int KE = InTraits<TIn>::KE;
   constexpr int A_ATOM_BYTES = GEMM_A_STAGE_BYTES;   // one K atom of A: 128 rows x 128 B
   constexpr int B_ROWS = BN / CTAS;                  // rows of B this CTA holds (a pair splits the tile's N)
@@ -821,7 +826,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
   uint8_t* sOut = sB + STAGES * B_STAGE_BYTES;   // per-warp output staging boxes (1024-byte aligned)
   uint8_t* sX = sOut + GEMM_OUT_STAGE_BYTES;      // per-warp transposition buffers of the coalescing epilogue
-  uint64_t* full = reinterpret_cast<uint64_t*>(sX + GEMM_XPOSE_BYTES(BN, MODE));
+  uint64_t* full = reinterpret_cast<uint64_t*>(sX + GEMM_XPOSE_BYTES(BN, MODE, EW));
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;   // [2]
   uint64_t* acc_empty = acc_full + 2;    // [2]
@@ -848,7 +853,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&acc_full[s], 1);
-        mbar_init(&acc_empty[s], 8 * CTAS);   // one arrival per epilogue warp of every CTA of the pair
+        mbar_init(&acc_empty[s], EW * CTAS);   // one arrival per epilogue warp of every CTA of the pair
       }
       fence_barrier_init();
     }
@@ -1002,8 +1007,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int half = (warp - 2) >> 2;
     const int et = (threadIdx.x - 64) & 127;      // thread index inside the warpgroup
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    constexpr int HB = BN >= 64 ? BN / 2 : BN;    // columns per warpgroup (BN = 32: warpgroup 1 only signals)
-    const int c_begin = half * HB, c_end = (BN >= 64 || half == 0) ? c_begin + HB : c_begin;
+    // 32-column chunks of the tile are dealt to the EW / 4 warpgroups (a warpgroup without columns only signals)
+    constexpr int NPARTS = EW / 4, CHUNKS = (BN + 31) / 32;
+    const int my_chunks = CHUNKS / NPARTS + (half < CHUNKS % NPARTS ? 1 : 0);
+    const int c_begin = 32 * (half * (CHUNKS / NPARTS) + (half < CHUNKS % NPARTS ? half : CHUNKS % NPARTS));
+    const int c_end = c_begin + 32 * my_chunks;
     constexpr int CV = GEMM_COLV_FLOATS(BN, MODE);
     constexpr bool GN_FAST = MODE == EPI_GN && sizeof(TOut) == 2 && !PRECISE;
     float2* gn_part = reinterpret_cast<float2*>(scratch + CV) + half * (128 + 64) * 4;   // [128][4]   (GroupNorm only)
@@ -1015,7 +1023,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     st.base = smem_u32(sOut) + (warp - 2) * 8192;
     st.count = 0;
     uint32_t lt = 0;
-    const bool fast = GEMM_XPOSE_BYTES(BN, MODE) > 0 && a.fast != 0;
+    const bool fast = GEMM_XPOSE_BYTES(BN, MODE, EW) > 0 && a.fast != 0;
     const int et256 = threadIdx.x - 64;
     for (int tile = worker; tile < a.total_tiles; tile += n_workers, ++lt) {
       const uint32_t acc = lt & 1;
@@ -1030,9 +1038,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         // Stage the per-column vectors.  LINEAR: set `acc` was last read two tiles ago and every warp has passed the
         // barrier of the tile in between, so only the write -> read edge needs a barrier.  GroupNorm (one set): all
         // readers of the previous tile must be done first.
-        if (MODE == EPI_GN) named_bar_sync(1, 256);
+        if (MODE == EPI_GN) named_bar_sync(1, 32 * EW);
         const long long gcol = (long long)t.g * a.n_pad + t.n0;
-        for (int c = et256; c < BN; c += 256) {
+        for (int c = et256; c < BN; c += 32 * EW) {
           colv[c] = a.bias ? a.bias[gcol + c] : 0.f;
           if (MODE == EPI_LINEAR) {
             colv[BN + c] = (a.colscale && (t.n0 + c) < a.N) ? a.colscale[t.n0 + c] : 1.f;
@@ -1054,7 +1062,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             const long long n_samples = a.M_total / a.gn_rows;
             const float* fc = a.film_c + (long long)t.g * a.film_g + a.film_off + t.n0;
             const float* ft = a.film_t ? a.film_t + (long long)t.g * a.film_tg + a.film_off + t.n0 : nullptr;
-            for (int i = et256; i < nsamp * 2 * BN; i += 256) {
+            for (int i = et256; i < nsamp * 2 * BN; i += 32 * EW) {
               const int c = i % BN, which = (i / BN) & 1, smp = i / (2 * BN);
               float v = 0.f;
               if (smp0 + smp < n_samples) {
@@ -1065,7 +1073,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             }
           }
         }
-        named_bar_sync(1, 256);
+        named_bar_sync(1, 32 * EW);
       }
       t.grow = (long long)m_tile * a.rows_valid + t.r;
       t.valid = (t.r < a.rows_valid) && (t.grow < a.M_total);
@@ -1078,7 +1086,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           mbar_wait(&acc_full[acc], parity);
           tc_fence_after();
         } else if constexpr (MODE == EPI_LINEAR) {
-          if constexpr (GEMM_XPOSE_BYTES(BN, MODE) > 0) {
+          if constexpr (GEMM_XPOSE_BYTES(BN, MODE, EW) > 0) {
             if (fast) epilogue_linear_fast<BN, TOut, PRECISE>(a, t, smem_u32(sX) + (warp - 2) * 4096, &acc_full[acc], parity, c_begin, c_end);
             else epilogue_linear<BN, TOut, PRECISE>(a, t, colv, &acc_full[acc], parity, st, c_begin, c_end);
           } else {

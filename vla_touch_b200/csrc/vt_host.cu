@@ -152,16 +152,18 @@ struct GemmVariant {
   GemmKernel fn;
   int smem;
   int ctas;   // 1, or 2 = CTA pairs (cluster of two, tcgen05 cta_group::2, M = 256 per MMA)
+  int threads;
   bool attr_set;
 };
 
-template <typename TIn, int BN, int MODE, typename TOut, int STAGES, int KA, int CTAS = 1>
+template <typename TIn, int BN, int MODE, typename TOut, int STAGES, int KA, int CTAS = 1, int EW = 8>
 GemmVariant make_variant() {
   GemmVariant v;
-  v.fn = vt::gemm_tc_kernel<TIn, BN, MODE, TOut, STAGES, (sizeof(TIn) == 4), KA, CTAS>;
-  v.smem = vt::gemm_smem_bytes<BN, STAGES, MODE, KA, CTAS>();
-  static_assert(vt::gemm_smem_bytes<BN, STAGES, MODE, KA, CTAS>() <= 227 * 1024, "shared memory budget");
+  v.fn = vt::gemm_tc_kernel<TIn, BN, MODE, TOut, STAGES, (sizeof(TIn) == 4), KA, CTAS, EW>;
+  v.smem = vt::gemm_smem_bytes<BN, STAGES, MODE, KA, CTAS, EW>();
+  static_assert(vt::gemm_smem_bytes<BN, STAGES, MODE, KA, CTAS, EW>() <= 227 * 1024, "shared memory budget");
   v.ctas = CTAS;
+  v.threads = vt::GEMM_THREADS(EW);
   v.attr_set = false;
   return v;
 }
@@ -229,7 +231,7 @@ struct GemmOp : Op {
       var->attr_set = true;
     }
     {
-      cudaError_t e = launch_ex(var->fn, grid, dim3(vt::GEMM_THREADS, 1, 1), (size_t)var->smem, s, var->ctas == 2, true, args);
+      cudaError_t e = launch_ex(var->fn, grid, dim3((unsigned)var->threads, 1, 1), (size_t)var->smem, s, var->ctas == 2, true, args);
       if (e != cudaSuccess) return fail(VT_E_CUDA, "gemm_tc_kernel launch: %s", cudaGetErrorString(e));
     }
     VT_LAUNCH_CHECK("gemm_tc_kernel");
@@ -345,7 +347,8 @@ int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
     auto span = [&](long long q, long long r, long long off, long long ld) {
       return (((long long)d.M / d.row_div + 1) * (q < 0 ? -q : q) + (long long)d.row_div * (r < 0 ? -r : r) + off + 1) * ld;
     };
-    bool fast = vec && d.epi == VT_EPI_LINEAR && d.bn >= 128 && d.N % d.bn == 0 && d.out_plane == 0 && d.res_plane == 0 &&
+    const bool combo = d.act == VT_ACT_NONE || (d.act == VT_ACT_GELU && !d.res);   // instantiated (activation, residual) pairs
+    bool fast = vec && combo && d.epi == VT_EPI_LINEAR && d.bn >= 128 && d.N % d.bn == 0 && d.out_plane == 0 && d.res_plane == 0 &&
                 d.out_q >= 0 && d.out_r >= 0 && d.out_off >= 0 && span(d.out_q, d.out_r, d.out_off, d.ldc) < (1ll << 31);
     if (d.res) fast = fast && d.res_q >= 0 && d.res_r >= 0 && d.res_off >= 0 && span(d.res_q, d.res_r, d.res_off, d.ldres) < (1ll << 31);
     const char* nf = getenv("VT_GEMM_FAST");
