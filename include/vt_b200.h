@@ -136,6 +136,23 @@ typedef struct vt_attn_desc {
   int64_t ctx_plane; /* >0 (f32): tf32 hi/lo split of ctx */
 } vt_attn_desc;
 
+/* Fused ViT MLP block of DinoV2-S (HF Dinov2MLP + layer_scale2 + residual, HF:312-328,380-386):
+ *   h += ls2 * (GELU(xn W1^T + b1) W2^T + b2)   with the [rows, 4D] hidden activation kept on chip.  D must be 384. */
+typedef struct vt_mlp_desc {
+  const void* xn;   /* bf16 [rows][ld_x]: LayerNorm2(h) */
+  int64_t ld_x;
+  const void* w1;   /* bf16 [4D][w1_ld], K contiguous */
+  int64_t w1_ld;
+  const float* b1;  /* [4D] */
+  const void* w2;   /* bf16 [D][w2_ld], K contiguous */
+  int64_t w2_ld;
+  const float* b2;  /* [D] */
+  const float* ls2; /* [D] LayerScale, or NULL */
+  float* h;         /* fp32 [rows][ld_h] residual stream, updated in place */
+  int64_t ld_h;
+  int32_t rows, D;
+} vt_mlp_desc;
+
 /* visual_encoder.py:66-81,95-106: batch-global predicates max>1 and mean<0.5, evaluated on the device. */
 typedef struct vt_imgstats_desc {
   const void* img;
@@ -309,6 +326,9 @@ int vt_program_num_launches(const vt_program* p, int first, int count);
 int vt_program_add_gemm(vt_program* p, const vt_gemm_desc* d);
 int vt_program_add_layernorm(vt_program* p, const vt_ln_desc* d);
 int vt_program_add_attention(vt_program* p, const vt_attn_desc* d);
+int vt_program_add_mlp(vt_program* p, const vt_mlp_desc* d);
+/* developer instrumentation (VT_GEMM_DEBUG bit 128): (tag, clock64) pairs of one epilogue warp; returns the entry count */
+int vt_debug_timestamps(long long* out, int max_entries);
 int vt_program_add_imgstats(vt_program* p, const vt_imgstats_desc* d);
 int vt_program_add_patchify(vt_program* p, const vt_patchify_desc* d);
 int vt_program_add_cls(vt_program* p, const vt_cls_desc* d);

@@ -375,3 +375,38 @@ def test_cta_pair_gemm_matches_single_cta_gemm(shape, monkeypatch):
     assert (outs[0] - outs[1]).abs().max().item() <= tol
     if kind == "none":
         assert (outs[0] - ref).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("rows", [515, 1300, 128])
+def test_fused_mlp_matches_reference_math(rows):
+    """mlp_fused_kernel (fc1 + GELU + fc2 + LayerScale + residual in one CTA-pair kernel, hidden activation on chip) against
+    the same math in fp32 on the bf16-rounded operands (HF Dinov2MLP, HF:312-328; layer_scale2 + residual HF:380-386)."""
+    from vla_touch_b200 import native as nv
+    from vla_touch_b200.plan import Plan, ptr
+    D = 384
+    g = torch.Generator().manual_seed(rows)
+    xn32 = torch.randn(rows, D, generator=g)
+    w1 = (torch.randn(4 * D, D, generator=g) / D ** 0.5).bfloat16()
+    w2 = (torch.randn(D, 4 * D, generator=g) / (4 * D) ** 0.5).bfloat16()
+    b1, b2 = torch.randn(4 * D, generator=g) * 0.1, torch.randn(D, generator=g) * 0.1
+    ls2 = torch.rand(D, generator=g) + 0.5
+    h0 = torch.randn(rows, D, generator=g)
+    plan = Plan(torch.device(DEV))
+    xn = plan.buf("xn", (rows, D), torch.bfloat16)
+    h = plan.buf("h", (rows, D), torch.float32)
+    xn.copy_(xn32)
+    h.copy_(h0)
+    t = {k: plan.reg(v.to(DEV).contiguous()) for k, v in dict(w1=w1, w2=w2, b1=b1, b2=b2, ls2=ls2).items()}
+    d = nv.MlpDesc()
+    d.xn, d.ld_x, d.w1, d.w1_ld, d.b1 = ptr(xn), D, ptr(t["w1"]), D, ptr(t["b1"])
+    d.w2, d.w2_ld, d.b2, d.ls2 = ptr(t["w2"]), 4 * D, ptr(t["b2"]), ptr(t["ls2"])
+    d.h, d.ld_h, d.rows, d.D = ptr(h), D, rows, D
+    plan.add(d, "mlp")
+    plan.compile().run(0, 1)
+    torch.cuda.synchronize()
+    hid = torch.nn.functional.gelu(xn.float().cpu() @ w1.float().t() + b1).bfloat16().float()     # the kernel feeds bf16 H to MMA2
+    ref = h0 + ls2 * (hid @ w2.float().t() + b2)
+    got = h.cpu()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item(), (rows, err, ref.abs().max().item())

@@ -28,6 +28,22 @@ constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * 128;
 constexpr int GEMM_MAX_TAPS = 8;
 
 enum : int { ACT_NONE = 0, ACT_GELU = 1, ACT_MISH = 2 };
+
+// Developer instrumentation (VT_GEMM_DEBUG bit 128): warp 2 of CTA 0 records clock64() at the phase boundaries of its
+// epilogue into this buffer (read back with vt_debug_timestamps).
+constexpr int VT_DBG_TS = 2048;
+__device__ long long vt_dbg_ts[VT_DBG_TS];
+__device__ int vt_dbg_n;
+// The entry counter lives in a register of the recording thread (`n`): a stamp is two fire-and-forget stores.
+__device__ __forceinline__ void dbg_stamp(bool on, int& n, int tag) {
+  if (on && n + 1 < VT_DBG_TS) {
+    vt_dbg_ts[n] = tag;
+    vt_dbg_ts[n + 1] = clock64();
+    n += 2;
+    vt_dbg_n = n;
+  }
+}
+
 enum : int { EPI_LINEAR = 0, EPI_GN = 1 };
 
 struct GemmArgs {
@@ -216,6 +232,7 @@ struct EpiTile {
   int n0, g, r;            // first column, group, tile row (== TMEM lane)
   long long grow;          // logical row
   bool valid;
+  int dbg_n;               // developer instrumentation: timestamps recorded so far (see dbg_stamp)
   int q, rem;
   uint32_t taddr;          // TMEM address of this thread's lane, column 0 of the accumulator
 };
@@ -344,7 +361,7 @@ __device__ __forceinline__ float2 gelu_fast2(float2 x) {   // same fit as gelu_f
 }
 
 template <int BN, typename TOut, bool PRECISE, int ACT, bool HAS_RES>
-__device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTile& t, uint32_t xbuf, uint64_t* acc_full,
+__device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, EpiTile& t, uint32_t xbuf, uint64_t* acc_full,
                                                   uint32_t acc_parity, int c_begin, int c_end) {
   constexpr int NC = 16 / sizeof(TOut);   // columns per lane after the transpose
   constexpr int LPR = 32 / NC;            // lanes per row segment (8 / 4)
@@ -389,9 +406,12 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTi
       }
     }
   };
+  const bool ts_on = (dbg & 128) && blockIdx.x == 0 && threadIdx.x == 64;
+  dbg_stamp(ts_on, t.dbg_n, 1);
   fetch(c_begin);
   mbar_wait(acc_full, acc_parity);
   tc_fence_after();
+  dbg_stamp(ts_on, t.dbg_n, 2);
 #pragma unroll 1
   for (int c = c_begin; c < c_end; c += 32) {
     uint32_t v[32];
@@ -403,6 +423,7 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTi
       sc[h] = scalep ? *reinterpret_cast<const float4*>(scalep + c + 4 * h) : make_float4(1.f, 1.f, 1.f, 1.f);
     }
     tmem_ld_wait();
+    dbg_stamp(ts_on, t.dbg_n, 3);
     float4 x[R * NV];
     if (dbg & 32) {   // developer knob: no transposition through shared memory (results are wrong, timing only)
 #pragma unroll
@@ -419,6 +440,7 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTi
       }
       __syncwarp();
     }
+    dbg_stamp(ts_on, t.dbg_n, 4);
 #pragma unroll
     for (int i = 0; i < R; ++i) {
       float4 y[NV];
@@ -465,13 +487,15 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, const EpiTi
         }
       }
     }
+    dbg_stamp(ts_on, t.dbg_n, 5);
     if (HAS_RES && c + 32 < c_end) fetch(c + 32);   // in flight during the next chunk's TMEM load + transpose
   }
+  dbg_stamp(ts_on, t.dbg_n, 6);
 }
 
 // runtime (activation, residual) -> compile-time instantiation of the coalescing epilogue
 template <int BN, typename TOut, bool PRECISE>
-__device__ __forceinline__ void epilogue_linear_fast(const GemmArgs& a, const EpiTile& t, uint32_t xbuf, uint64_t* acc_full,
+__device__ __forceinline__ void epilogue_linear_fast(const GemmArgs& a, EpiTile& t, uint32_t xbuf, uint64_t* acc_full,
                                                      uint32_t parity, int c0, int c1) {
   // the three combinations the path uses (host sets a.fast only for these): GELU without residual (fc1), plain (qkv,
   // patch embed, U-Net linear convs), plain + residual (attention out-projection, fc2)
@@ -1019,6 +1043,7 @@ __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __gr
     float* films = scratch + CV + 2 * (128 + 64) * 4 * 2;                                 // [8][2][BN] (GroupNorm only)
     EpiTile t;
     t.r = quarter * 32 + lane;
+    t.dbg_n = 0;
     OutStage st;
     st.base = smem_u32(sOut) + (warp - 2) * 8192;
     st.count = 0;

@@ -12,6 +12,7 @@
 
 #include "../../include/vt_b200.h"
 #include "vt_attn.cuh"
+#include "vt_mlp.cuh"
 #include "vt_elem.cuh"
 #include "vt_gemm.cuh"
 #include "vt_lstm.cuh"
@@ -190,11 +191,13 @@ GemmVariant* gemm_variant(int in_dtype, int bn, int epi, int out_dtype, bool pai
   static GemmVariant p_b_192_l_b = make_variant<bf, 192, vt::EPI_LINEAR, bf, 3, 2, 2>();
   static GemmVariant p_b_192_l_f = make_variant<bf, 192, vt::EPI_LINEAR, float, 3, 2, 2>();
   static GemmVariant p_b_256_g_b = make_variant<bf, 256, vt::EPI_GN, bf, 3, 2, 2>();
+  static GemmVariant p_b_128_g_b = make_variant<bf, 128, vt::EPI_GN, bf, 4, 2, 2>();
   if (in_dtype == VT_BF16) {
     if (epi == VT_EPI_GN) {
       if (out_dtype != VT_BF16) return nullptr;
       if (bn == 256) return pair ? &p_b_256_g_b : nullptr;
-      return bn == 128 ? &v_b_128_g_b : nullptr;
+      if (bn == 128) return pair ? &p_b_128_g_b : &v_b_128_g_b;
+      return nullptr;
     }
     if (pair && bn == 256) return out_dtype == VT_BF16 ? &p_b_256_l_b : &p_b_256_l_f;
     if (pair && bn == 192) return out_dtype == VT_BF16 ? &p_b_192_l_b : &p_b_192_l_f;
@@ -262,7 +265,8 @@ int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
   // CTA pairs whenever the shape has at least two row tiles (env VT_GEMM_PAIR=0 keeps the single-CTA kernels: A/B runs)
   const int m_tiles_1 = (d.M + d.t_box * d.b_box - 1) / (d.t_box * d.b_box);
   const bool pair_enabled = !(getenv("VT_GEMM_PAIR") && atoi(getenv("VT_GEMM_PAIR")) == 0);
-  bool pair = pair_enabled && d.in_dtype == VT_BF16 && (d.bn == 256 || d.bn == 192) && m_tiles_1 >= 2 && d.passes == 1;
+  bool pair = pair_enabled && d.in_dtype == VT_BF16 && (d.bn == 256 || d.bn == 192 || (d.bn == 128 && d.epi == VT_EPI_GN)) &&
+              m_tiles_1 >= 2 && d.passes == 1;
   if (d.epi == VT_EPI_GN && d.bn == 256) pair = true;   // the 256-wide GroupNorm epilogue exists as a pair kernel only
   GemmVariant* var = gemm_variant(d.in_dtype, d.bn, d.epi, d.out_dtype, pair);
   if (!var) return fail(VT_E_UNSUPPORTED, "gemm: no kernel for in=%d bn=%d epi=%d out=%d", d.in_dtype, d.bn, d.epi, d.out_dtype);
@@ -463,6 +467,23 @@ struct AttnOp : Op {
   }
 };
 bool AttnOp::attr_set = false;
+
+// ---- fused ViT MLP ----
+struct MlpOp : Op {
+  vt::MlpArgs args;
+  dim3 grid;
+  int launch(cudaStream_t s) override {
+    static bool attr_set = false;
+    if (!attr_set) {
+      VT_CUDA(cudaFuncSetAttribute(vt::mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vt::MLP_SMEM_BYTES));
+      attr_set = true;
+    }
+    cudaError_t e = launch_ex(vt::mlp_fused_kernel, grid, dim3(vt::MLP_THREADS, 1, 1), (size_t)vt::MLP_SMEM_BYTES, s, true, true, args);
+    if (e != cudaSuccess) return fail(VT_E_CUDA, "mlp_fused_kernel launch: %s", cudaGetErrorString(e));
+    VT_LAUNCH_CHECK("mlp_fused_kernel");
+    return VT_OK;
+  }
+};
 
 // ---- simple ops ----
 struct LnOp : Op {
@@ -676,6 +697,80 @@ int vt_program_add_gemm(vt_program* p, const vt_gemm_desc* d) {
   std::unique_ptr<GemmOp> op(new GemmOp());
   int rc = build_gemm(*d, op.get());
   if (rc) return rc;
+  p->ops.push_back(std::move(op));
+  return VT_OK;
+}
+
+// developer instrumentation: copy out (and reset) the epilogue timestamps recorded under VT_GEMM_DEBUG bit 128
+int vt_debug_timestamps(long long* out, int max_entries) {
+  int n = 0;
+  if (cudaMemcpyFromSymbol(&n, vt::vt_dbg_n, sizeof(int)) != cudaSuccess) return -1;
+  if (n > max_entries) n = max_entries;
+  if (n > 0 && cudaMemcpyFromSymbol(out, vt::vt_dbg_ts, sizeof(long long) * n) != cudaSuccess) return -1;
+  const int zero = 0;
+  cudaMemcpyToSymbol(vt::vt_dbg_n, &zero, sizeof(int));
+  return n;
+}
+
+int vt_program_add_mlp(vt_program* p, const vt_mlp_desc* d) {
+  if (!p || !d) return fail(VT_E_INVALID, "null argument");
+  VT_REQUIRE(d->xn && d->w1 && d->b1 && d->w2 && d->b2 && d->h && d->rows >= 1, "mlp: bad descriptor");
+  VT_REQUIRE(d->D == vt::MLP_D, "mlp: the fused kernel is built for D = %d (got %d)", vt::MLP_D, d->D);
+  VT_REQUIRE(d->ld_x >= d->D && d->ld_x % 8 == 0 && d->w1_ld >= d->D && d->w1_ld % 8 == 0 && d->w2_ld >= 4 * d->D && d->w2_ld % 8 == 0,
+             "mlp: leading dimensions");
+  VT_REQUIRE(d->ld_h >= d->D && d->ld_h % 4 == 0 && aligned16(d->h) && aligned16(d->b1) && aligned16(d->b2) && (!d->ls2 || aligned16(d->ls2)),
+             "mlp: fp32 operands must be 16-byte aligned");
+  VT_REQUIRE((long long)d->rows * d->ld_h < (1ll << 31), "mlp: residual stream too large for 32-bit offsets");
+  std::unique_ptr<MlpOp> op(new MlpOp());
+  vt::MlpArgs& a = op->args;
+  memset(&a, 0, sizeof(a));
+  {
+    const uint64_t dims[2] = {(uint64_t)d->D, (uint64_t)d->rows};
+    const uint64_t st[1] = {(uint64_t)d->ld_x * 2};
+    const uint32_t box[2] = {64u, 128u};
+    int rc = make_tmap(&a.tmX, VT_BF16, 2, d->xn, dims, st, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)d->D, (uint64_t)4 * d->D};
+    const uint64_t st[1] = {(uint64_t)d->w1_ld * 2};
+    const uint32_t box[2] = {64u, 64u};
+    int rc = make_tmap(&a.tmW1, VT_BF16, 2, d->w1, dims, st, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)4 * d->D, (uint64_t)d->D};
+    const uint64_t st[1] = {(uint64_t)d->w2_ld * 2};
+    const uint32_t box[2] = {64u, 96u};
+    int rc = make_tmap(&a.tmW2, VT_BF16, 2, d->w2, dims, st, box);
+    if (rc) return rc;
+  }
+  a.b1 = d->b1;
+  vt::GemmArgs& e = a.epi;
+  e.M_total = d->rows;
+  e.N = d->D;
+  e.n_pad = d->D;
+  e.rows_valid = 128;
+  e.row_div = 1;
+  e.out_q = 1;
+  e.res_q = 1;
+  e.ldc = (int)d->ld_h;
+  e.ldres = (int)d->ld_h;
+  e.out = d->h;
+  e.res = d->h;
+  e.bias = d->b2;
+  e.colscale = d->ls2;
+  e.act = VT_ACT_NONE;
+  e.vec = 1;
+  e.fast = 1;
+  {
+    const char* dbg = getenv("VT_GEMM_DEBUG");
+    e.debug = dbg ? (atoi(dbg) & 128) : 0;
+  }
+  a.m_tiles = (d->rows + 127) / 128;
+  a.n_pairs = (a.m_tiles + 1) / 2;
+  const int workers = sm_count() / 2;
+  op->grid = dim3((unsigned)(a.n_pairs < workers ? a.n_pairs : workers) * 2u, 1u, 1u);
   p->ops.push_back(std::move(op));
   return VT_OK;
 }

@@ -8,6 +8,8 @@ predicates (`max > 1`, `mean < 0.5`) separate per camera and evaluating them on 
 """
 from __future__ import annotations
 
+import os
+
 from typing import Callable, Dict, List, Optional, Sequence
 
 import torch
@@ -157,6 +159,8 @@ class DinoProgram:
             plan.add(d, name)
 
         lin = dict(rows=M, passes=m.passes)
+        # DinoV2-S in bf16 on the GPU: fc1 + GELU + fc2 + LayerScale + residual as ONE kernel (hidden activation stays on chip)
+        fused_mlp = (not m.precise and D == 384 and plan.device.type == "cuda" and os.environ.get("VT_FUSED_MLP", "1") != "0")
         for i in range(W.layers):
             L = f"{tag}.l{i}."
             ln(0, M, 1, T_[f"{i}.ln1.w"], T_[f"{i}.ln1.b"], xn, m.dt, m.ld(D), m.plane(D), 0, L + "norm1")
@@ -171,6 +175,14 @@ class DinoProgram:
                                  out=h, ldc=D, bias=T_[f"{i}.o.b"], colscale=T_[f"{i}.ls1"], res=h, ldres=D,
                                  a_plane=m.plane(D), w_plane=D if m.precise else 0, **lin), L + "attn_out+ls1+res")
             ln(0, M, 1, T_[f"{i}.ln2.w"], T_[f"{i}.ln2.b"], xn, m.dt, m.ld(D), m.plane(D), 0, L + "norm2")
+            if fused_mlp:
+                d = nv.MlpDesc()
+                d.xn, d.ld_x = ptr(xn), m.ld(D)
+                d.w1, d.w1_ld, d.b1 = ptr(T_[f"{i}.fc1.w"]), T_[f"{i}.fc1.w"].shape[-1], ptr(T_[f"{i}.fc1.b"])
+                d.w2, d.w2_ld, d.b2 = ptr(T_[f"{i}.fc2.w"]), T_[f"{i}.fc2.w"].shape[-1], ptr(T_[f"{i}.fc2.b"])
+                d.ls2, d.h, d.ld_h, d.rows, d.D = ptr(T_[f"{i}.ls2"]), ptr(h), D, M, D
+                plan.add(d, L + "mlp(fc1+gelu+fc2+ls2+res)")
+                continue
             plan.add(linear_desc(a=xn, k=D, a_ld=m.ld(D), w=T_[f"{i}.fc1.w"], n=4 * D, n_pad=4 * D,
                                  w_ld=T_[f"{i}.fc1.w"].shape[-1], out=hid, ldc=m.ld(4 * D), bias=T_[f"{i}.fc1.b"],
                                  act=nv.ACT_GELU, out_plane=m.plane(4 * D), a_plane=m.plane(D), w_plane=D if m.precise else 0,

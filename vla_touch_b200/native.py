@@ -49,6 +49,11 @@ class AttnDesc(C.Structure):
                 ("ctx_ld", i64), ("ctx_plane", i64)]
 
 
+class MlpDesc(C.Structure):
+    _fields_ = [("xn", vp), ("ld_x", i64), ("w1", vp), ("w1_ld", i64), ("b1", vp), ("w2", vp), ("w2_ld", i64), ("b2", vp),
+                ("ls2", vp), ("h", vp), ("ld_h", i64), ("rows", i32), ("D", i32)]
+
+
 class ImgStatsDesc(C.Structure):
     _fields_ = [("img", vp), ("dtype", i32), ("count", i64), ("partial", vp), ("flags", vp)]
 
@@ -112,14 +117,14 @@ class AdamwDesc(C.Structure):
 EXPORTS = [
     "vt_last_error", "vt_abi_version", "vt_device_info", "vt_program_create", "vt_program_destroy",
     "vt_program_num_ops", "vt_program_num_launches", "vt_program_add_gemm", "vt_program_add_layernorm",
-    "vt_program_add_attention", "vt_program_add_imgstats", "vt_program_add_patchify", "vt_program_add_cls",
+    "vt_program_add_attention", "vt_program_add_mlp", "vt_debug_timestamps", "vt_program_add_imgstats", "vt_program_add_patchify", "vt_program_add_cls",
     "vt_program_add_pack", "vt_program_add_affine", "vt_program_add_tembed", "vt_program_add_sde",
     "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
     "vt_pos_embed_resize", "vt_adamw_ema_step",
 ]
 
 _ADD = {
-    GemmDesc: "vt_program_add_gemm", LnDesc: "vt_program_add_layernorm", AttnDesc: "vt_program_add_attention",
+    GemmDesc: "vt_program_add_gemm", LnDesc: "vt_program_add_layernorm", AttnDesc: "vt_program_add_attention", MlpDesc: "vt_program_add_mlp",
     ImgStatsDesc: "vt_program_add_imgstats", PatchifyDesc: "vt_program_add_patchify", ClsDesc: "vt_program_add_cls",
     PackDesc: "vt_program_add_pack", AffineDesc: "vt_program_add_affine", TembedDesc: "vt_program_add_tembed",
     SdeDesc: "vt_program_add_sde", LstmDesc: "vt_program_add_lstm", QsampleDesc: "vt_program_add_qsample",

@@ -13,6 +13,8 @@ sampler the time half is batch-independent and pre-computed for all steps (`film
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -213,7 +215,7 @@ def _conv(plan: Plan, W: UnetWeights, B: int, src: _View, dst: _View, w: torch.T
     """One grouped implicit-GEMM convolution.  src/dst are channel windows of [G][B][T][ld] buffers."""
     m, G = W.mode, W.G
     t_in_q = src.T // phases
-    if bn == 128 and not m.precise and n % 256 == 0:
+    if bn == 128 and not m.precise and n % 256 == 0 and not (gn is not None and os.environ.get("VT_GN_BN") == "128"):
         bn = 256                                  # 256-wide tiles run as CTA pairs (M = 256 MMAs): half the operand bytes per MAC
     b_box = max(1, min(128 // t_out, B, 32 if bn == 128 else 16))
     a_sB = src.T * src.ld
