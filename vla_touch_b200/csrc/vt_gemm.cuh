@@ -408,6 +408,16 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, EpiTile& t,
   };
   const bool ts_on = (dbg & 128) && blockIdx.x == 0 && threadIdx.x == 64;
   dbg_stamp(ts_on, t.dbg_n, 1);
+  if constexpr (HAS_RES) {
+    // Row `lane` of this warp's 32 rows: ask for its residual columns in L2 now (one bulk prefetch per lane), so that the
+    // per-chunk loads below are L2 hits; the first chunk's loads are issued before the accumulator is ready.
+    const int grow = wrow0 + lane;
+    if (trow0 + lane < a.rows_valid && grow < a.M_total) {
+      const int q = rdiv == 1 ? grow : (int)((unsigned)grow / (unsigned)rdiv), rem = grow - q * rdiv;
+      bulk_prefetch_l2(reinterpret_cast<const float*>(a.res) + (long long)t.g * a.res_g + (long long)(q * rq + rem * rr_ + roff0) * a.ldres +
+                           t.n0 + c_begin, (uint32_t)(c_end - c_begin) * 4u);
+    }
+  }
   fetch(c_begin);
   mbar_wait(acc_full, acc_parity);
   tc_fence_after();
@@ -423,6 +433,10 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, EpiTile& t,
       sc[h] = scalep ? *reinterpret_cast<const float4*>(scalep + c + 4 * h) : make_float4(1.f, 1.f, 1.f, 1.f);
     }
     tmem_ld_wait();
+    // tcgen05.wait::ld is a scoreboard wait that also covers global loads issued before it (measured: the wait took a full
+    // residual-load latency), so this chunk's residual rows are requested only now; they are L2 hits (prefetch above) and
+    // overlap the transposition.
+    if (HAS_RES && c != c_begin) fetch(c);
     dbg_stamp(ts_on, t.dbg_n, 3);
     float4 x[R * NV];
     if (dbg & 32) {   // developer knob: no transposition through shared memory (results are wrong, timing only)
@@ -488,7 +502,6 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, EpiTile& t,
       }
     }
     dbg_stamp(ts_on, t.dbg_n, 5);
-    if (HAS_RES && c + 32 < c_end) fetch(c + 32);   // in flight during the next chunk's TMEM load + transpose
   }
   dbg_stamp(ts_on, t.dbg_n, 6);
 }
@@ -672,8 +685,8 @@ __device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, const EpiTil
     uint4 rc[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) rc[i] = rr[i];
-    if (ch + 1 < NCH) fetch_res(ch + 1);
     tmem_ld_wait();
+    if (ch + 1 < NCH) fetch_res(ch + 1);   // after the wait: tcgen05.wait::ld also waits for global loads issued before it
     if (t.valid) {
 #pragma unroll
       for (int j8 = 0; j8 < 32; j8 += 8) {
