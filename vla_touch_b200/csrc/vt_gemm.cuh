@@ -426,13 +426,13 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, EpiTile& t,
   for (int c = c_begin; c < c_end; c += 32) {
     uint32_t v[32];
     tmem_ld32(t.taddr + c, v);
-    float4 bs[NV], sc[NV];
+    tmem_ld_wait();
+    float4 bs[NV], sc[NV];   // requested after the TMEM wait (see below), used after the transposition
 #pragma unroll
     for (int h = 0; h < NV; ++h) {
       bs[h] = biasp ? *reinterpret_cast<const float4*>(biasp + c + 4 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
       sc[h] = scalep ? *reinterpret_cast<const float4*>(scalep + c + 4 * h) : make_float4(1.f, 1.f, 1.f, 1.f);
     }
-    tmem_ld_wait();
     // tcgen05.wait::ld is a scoreboard wait that also covers global loads issued before it (measured: the wait took a full
     // residual-load latency), so this chunk's residual rows are requested only now; they are L2 hits (prefetch above) and
     // overlap the transposition.
