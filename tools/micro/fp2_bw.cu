@@ -4,7 +4,7 @@
 #include "vt_gemm.cuh"
 using namespace vt;
 
-template <int MODE>
+template <int MODE, int CH = 16>
 __global__ void __launch_bounds__(256, 1) k(int iters, long long* cycles, float* sink, float seed) {
   float2 x[16];
 #pragma unroll
@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(256, 1) k(int iters, long long* cycles, float*
   const long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < CH; ++i) {
       if (MODE == 0) x[i] = ffma2(x[i], s, b);                                                   // packed FMA, 16 independent chains
       else if (MODE == 1) { x[i].x = fmaf(x[i].x, s.x, b.x); x[i].y = fmaf(x[i].y, s.y, b.y); }  // scalar FMA, 32 chains
       else if (MODE == 2) x[i] = gelu_fast2(fadd2(x[i], b));                                      // packed GELU
@@ -31,17 +31,17 @@ __global__ void __launch_bounds__(256, 1) k(int iters, long long* cycles, float*
   if (acc == 123.456f) sink[0] = acc;
 }
 
-template <int MODE>
+template <int MODE, int CH = 16>
 void run(const char* name) {
   long long* cyc; float* sink;
   cudaMalloc(&cyc, 148 * 8); cudaMalloc(&sink, 4);
   const int iters = 2000;
-  k<MODE><<<148, 256>>>(iters, cyc, sink, 0.3f);
+  k<MODE, CH><<<148, 256>>>(iters, cyc, sink, 0.3f);
   cudaDeviceSynchronize();
-  k<MODE><<<148, 256>>>(iters, cyc, sink, 0.3f);
+  k<MODE, CH><<<148, 256>>>(iters, cyc, sink, 0.3f);
   cudaError_t e = cudaDeviceSynchronize();
   long long h[148]; cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
-  const double elems = (double)iters * 32 * 256;   // elements per SM
+  const double elems = (double)iters * 2 * CH * 256;   // elements per SM
   printf("%-14s %9lld cycles  %6.2f elements/cycle/SM   %6.1f cycles per 32-element step per warp (%s)\n", name, h[0], elems / h[0],
          (double)h[0] / iters, cudaGetErrorString(e));
 }
@@ -53,5 +53,10 @@ int main() {
   run<3>("GELU scalar");
   run<4>("Mish packed");
   run<5>("Mish scalar");
+  run<4, 8>("Mish packed, 8 chains");
+  run<4, 4>("Mish packed, 4 chains");
+  run<4, 2>("Mish packed, 2 chains");
+  run<2, 4>("GELU packed, 4 chains");
+  run<2, 2>("GELU packed, 2 chains");
   return 0;
 }

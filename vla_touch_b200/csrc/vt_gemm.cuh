@@ -621,7 +621,7 @@ __device__ __forceinline__ float2 mish2(float2 x) {
 // already in registers when the accumulator arrives; the residual of chunk c+1 is in flight while chunk c is computed.
 // ------------------------------------------------------------------------------------------------------------
 template <int BN>
-__device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, const EpiTile& t, const float* colv, const float* films,
+__device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, EpiTile& t, const float* colv, const float* films,
                                                  float2* gn_part, float2* gn_stat, int et, int bar_id, uint64_t* acc_full,
                                                  uint32_t acc_parity, int cb) {
   constexpr int NCH = BN / 64;  // 32-column chunks per half tile
@@ -638,9 +638,12 @@ __device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, const EpiTil
     for (int i = 0; i < 4; ++i) rr[i] = resp ? *reinterpret_cast<const uint4*>(resp + ch * 32 + i * 8) : make_uint4(0u, 0u, 0u, 0u);
   };
   fetch_res(0);
+  const bool ts_on = (a.debug & 128) && blockIdx.x == 0 && threadIdx.x == 64;
+  dbg_stamp(ts_on, t.dbg_n, 20);
 
   mbar_wait(acc_full, acc_parity);
   tc_fence_after();
+  dbg_stamp(ts_on, t.dbg_n, 21);
   // ---- pass 1: per-row sums of (acc + bias) over every 32-column chunk ----
   float s1[NCH], s2[NCH];
 #pragma unroll
@@ -661,7 +664,9 @@ __device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, const EpiTil
     s1[ch] = t.valid ? a1.x + a1.y : 0.f;
     s2[ch] = t.valid ? a2.x + a2.y : 0.f;
   }
+  dbg_stamp(ts_on, t.dbg_n, 22);
   gn_sample_totals<NCH>(a, t, s1, s2, gn_part, gn_stat, et, bar_id);
+  dbg_stamp(ts_on, t.dbg_n, 23);
   const float cnt = (float)(a.gn_rows << a.gn_gs_log2);
   float rstd[NCH], nmr[NCH];   // 1/std and -mean/std of the row's sample, per chunk (group)
 #pragma unroll
@@ -688,55 +693,66 @@ __device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, const EpiTil
     tmem_ld_wait();
     if (ch + 1 < NCH) fetch_res(ch + 1);   // after the wait: tcgen05.wait::ld also waits for global loads issued before it
     if (t.valid) {
+      // The whole 32-column chunk moves through the phases together (16 independent pairs per phase): the Mish chain
+      // (ex2 -> fma -> add -> rcp -> mul) has ~150 cycles of latency and only two warps share a scheduler.
+      const int c0 = ch * 32;
+      float2 y[16];
 #pragma unroll
-      for (int j8 = 0; j8 < 32; j8 += 8) {
-        const int cc = ch * 32 + j8;
-        float2 y[4];
+      for (int h = 0; h < 8; ++h) {
+        const float4 b4 = *reinterpret_cast<const float4*>(colv + cb + c0 + 4 * h);
+        const float4 g4 = *reinterpret_cast<const float4*>(colv + BN + cb + c0 + 4 * h);
+        const float4 e4 = *reinterpret_cast<const float4*>(colv + 2 * BN + cb + c0 + 4 * h);
+        const float2 x0 = fadd2(make_float2(__uint_as_float(v[4 * h]), __uint_as_float(v[4 * h + 1])), make_float2(b4.x, b4.y));
+        const float2 x1 = fadd2(make_float2(__uint_as_float(v[4 * h + 2]), __uint_as_float(v[4 * h + 3])), make_float2(b4.z, b4.w));
+        y[2 * h] = ffma2(ffma2(x0, rs2, nm2), make_float2(g4.x, g4.y), make_float2(e4.x, e4.y));
+        y[2 * h + 1] = ffma2(ffma2(x1, rs2, nm2), make_float2(g4.z, g4.w), make_float2(e4.z, e4.w));
+      }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float4 b4 = *reinterpret_cast<const float4*>(colv + cb + cc + 4 * h);
-          const float4 g4 = *reinterpret_cast<const float4*>(colv + BN + cb + cc + 4 * h);
-          const float4 e4 = *reinterpret_cast<const float4*>(colv + 2 * BN + cb + cc + 4 * h);
-          float2 x0 = fadd2(make_float2(__uint_as_float(v[j8 + 4 * h]), __uint_as_float(v[j8 + 4 * h + 1])), make_float2(b4.x, b4.y));
-          float2 x1 = fadd2(make_float2(__uint_as_float(v[j8 + 4 * h + 2]), __uint_as_float(v[j8 + 4 * h + 3])), make_float2(b4.z, b4.w));
-          x0 = ffma2(ffma2(x0, rs2, nm2), make_float2(g4.x, g4.y), make_float2(e4.x, e4.y));
-          x1 = ffma2(ffma2(x1, rs2, nm2), make_float2(g4.z, g4.w), make_float2(e4.z, e4.w));
-          y[2 * h] = mish2(x0);
-          y[2 * h + 1] = mish2(x1);
+      for (int p = 0; p < 16; ++p) y[p] = mish2(y[p]);
+      if (fs) {
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          const float4 sc = *reinterpret_cast<const float4*>(fs + c0 + 4 * h);
+          const float4 sh = *reinterpret_cast<const float4*>(fs + BN + c0 + 4 * h);
+          y[2 * h] = ffma2(y[2 * h], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
+          y[2 * h + 1] = ffma2(y[2 * h + 1], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
         }
-        if (fs) {
+      } else if (filmp) {   // more samples per tile than the staging buffer holds: straight from global memory
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const float4 sc = *reinterpret_cast<const float4*>(fs + cc + 4 * h);
-            const float4 sh = *reinterpret_cast<const float4*>(fs + BN + cc + 4 * h);
-            y[2 * h] = ffma2(y[2 * h], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
-            y[2 * h + 1] = ffma2(y[2 * h + 1], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
-          }
-        } else if (filmp) {   // more samples per tile than the staging buffer holds: straight from global memory
+        for (int j8 = 0; j8 < 32; j8 += 8) {
           float sc[8], sh[8];
-          load_res8(filmp + cc, sc);
-          load_res8(filmp + a.film_C + cc, sh);
+          load_res8(filmp + c0 + j8, sc);
+          load_res8(filmp + a.film_C + c0 + j8, sh);
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
-            const float2 s2v = fadd2(make_float2(sc[2 * h], sc[2 * h + 1]), make_float2(colv[3 * BN + cb + cc + 2 * h], colv[3 * BN + cb + cc + 2 * h + 1]));
-            const float2 h2v = fadd2(make_float2(sh[2 * h], sh[2 * h + 1]), make_float2(colv[4 * BN + cb + cc + 2 * h], colv[4 * BN + cb + cc + 2 * h + 1]));
-            y[h] = ffma2(y[h], s2v, h2v);
+            const float2 s2v = fadd2(make_float2(sc[2 * h], sc[2 * h + 1]),
+                                     make_float2(colv[3 * BN + cb + c0 + j8 + 2 * h], colv[3 * BN + cb + c0 + j8 + 2 * h + 1]));
+            const float2 h2v = fadd2(make_float2(sh[2 * h], sh[2 * h + 1]),
+                                     make_float2(colv[4 * BN + cb + c0 + j8 + 2 * h], colv[4 * BN + cb + c0 + j8 + 2 * h + 1]));
+            y[j8 / 2 + h] = ffma2(y[j8 / 2 + h], s2v, h2v);
           }
         }
-        if (resp) {
-          const uint4 rv = rc[j8 >> 3];
+      }
+      if (resp) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 rv = rc[q];
           const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
-          for (int h = 0; h < 4; ++h) y[h] = fadd2(y[h], __bfloat1622float2(h2[h]));
+          for (int h = 0; h < 4; ++h) y[4 * q + h] = fadd2(y[4 * q + h], __bfloat1622float2(h2[h]));
         }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
         uint4 w;
-        w.x = pack_bf16x2(y[0].x, y[0].y);
-        w.y = pack_bf16x2(y[1].x, y[1].y);
-        w.z = pack_bf16x2(y[2].x, y[2].y);
-        w.w = pack_bf16x2(y[3].x, y[3].y);
-        *reinterpret_cast<uint4*>(outp + cc) = w;
+        w.x = pack_bf16x2(y[4 * q].x, y[4 * q].y);
+        w.y = pack_bf16x2(y[4 * q + 1].x, y[4 * q + 1].y);
+        w.z = pack_bf16x2(y[4 * q + 2].x, y[4 * q + 2].y);
+        w.w = pack_bf16x2(y[4 * q + 3].x, y[4 * q + 3].y);
+        *reinterpret_cast<uint4*>(outp + c0 + 8 * q) = w;
       }
     }
+    dbg_stamp(ts_on, t.dbg_n, 24);
   }
 }
 
@@ -1065,6 +1081,7 @@ __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __gr
     const int et256 = threadIdx.x - 64;
     for (int tile = worker; tile < a.total_tiles; tile += n_workers, ++lt) {
       const uint32_t acc = lt & 1;
+      dbg_stamp((a.debug & 128) && blockIdx.x == 0 && threadIdx.x == 64, t.dbg_n, 19);
       const int n_tile = tile % a.n_tiles;
       const int rest = tile / a.n_tiles;
       const int m_tile = (rest % a.m_tiles) * CTAS + rank;
