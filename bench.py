@@ -144,6 +144,9 @@ def cpu_baseline(wl, seconds=15.0):
 
 
 def gemm_flops(d):
+    """FLOPs of one tensor-core launch: an implicit GEMM, or the fused ViT MLP (two GEMMs rows x D x 4D)."""
+    if hasattr(d, "w2"):                       # MlpDesc
+        return 2.0 * 2.0 * d.rows * d.D * 4 * d.D
     return 2.0 * d.G * d.M * d.N * d.taps * d.kc * d.passes
 
 
@@ -263,7 +266,7 @@ def main():
     peak_src = "MEASURED_PEAKS.json bf16_tflops (burst, kernel timed alone)" if peaks else "fallback 1590 (B200_PROFILING.md)"
     prog = eng.plan.compile()
     a0, b1 = eng.predict_range()
-    gemms = [(gemm_flops(d), i) for i, d in enumerate(eng.plan.descs) if isinstance(d, nv.GemmDesc) and a0 <= i < b1]
+    gemms = [(gemm_flops(d), i) for i, d in enumerate(eng.plan.descs) if isinstance(d, (nv.GemmDesc, nv.MlpDesc)) and a0 <= i < b1]
     total_gemm_flops = sum(f for f, _ in gemms)
     fl, idx = max(gemms)
     for _ in range(5):
@@ -311,7 +314,8 @@ def main():
                         "needs 2x the cycles of the two MMAs, so the tensor pipe cannot exceed ~50 % in this kernel"}
     f_chunk = flops_per_chunk(hidden, layers, hw, T, A, F, eng.n_steps)
     step_tf = value / world * f_chunk / 1e12
-    roofline = {"bound": "tensor", "kernel": f"gemm_tc_kernel [{eng.plan.tags[idx]}]", "achieved": achieved, "peak": peak_tf,
+    roofline = {"bound": "tensor",
+                "kernel": f"{'mlp_fused_kernel' if isinstance(eng.plan.descs[idx], nv.MlpDesc) else 'gemm_tc_kernel'} [{eng.plan.tags[idx]}]", "achieved": achieved, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "flops_per_launch": fl, "ms_per_launch": k_ms, "attention": attn,
                 "whole_step": {"algorithmic_tflops_per_gpu": step_tf, "frac_of_sustained": step_tf / peaks.get("bf16_tflops_sustained", 1400.0),
