@@ -1,6 +1,6 @@
 """Developer tool (GPU box): VT_GEMM_DEBUG=128 timestamps of one epilogue warp (CTA 0, warp 2) for selected GEMM ops."""
 import os, sys, ctypes as C
-os.environ["VT_GEMM_DEBUG"] = "128"
+os.environ["VT_GEMM_DEBUG"] = os.environ.get("VT_TRACE_BITS", "128")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
 import torch, ncu_ops
@@ -11,7 +11,7 @@ L = nv.lib()
 L.vt_debug_timestamps.argtypes = [C.POINTER(C.c_longlong), C.c_int]
 L.vt_debug_timestamps.restype = C.c_int
 buf = (C.c_longlong * 2048)()
-names = {1: "enter", 2: "acc_full", 3: "tmem_ld", 4: "transpose", 5: "math+store", 6: "exit", 10: "chunk", 11: "h_full", 12: "tmem_ld64", 13: "gelu", 14: "h_sfree", 15: "sts+arrive", 19: "tile", 20: "gn enter", 21: "gn acc_full", 22: "gn pass1", 23: "gn stats", 24: "gn chunk"}
+names = {1: "enter", 2: "acc_full", 3: "tmem_ld", 4: "transpose", 5: "math+store", 6: "exit", 10: "chunk", 11: "h_full", 12: "tmem_ld64", 13: "gelu", 14: "h_sfree", 15: "sts+arrive", 19: "tile", 20: "gn enter", 21: "gn acc_full", 22: "gn pass1", 23: "gn stats", 24: "gn chunk", 30: "kernel entry", 31: "prologue done", 32: "pdl_wait done", 33: "first operands", 34: "tile MMAs issued", 35: "roles done", 36: "final sync"}
 for i in [int(x) for x in sys.argv[1:]]:
     prog.run(i, 1); torch.cuda.synchronize()
     L.vt_debug_timestamps(buf, 2048)          # reset

@@ -873,6 +873,9 @@ __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __gr
   static_assert(CTAS == 1 || (CTAS == 2 && sizeof(TIn) == 2 && BN % 32 == 0), "CTA pairs: bf16 operands");
 
   extern __shared__ uint8_t smem_raw[];
+  const bool ts_mma = (a.debug & 256) && blockIdx.x == 0 && threadIdx.x == 32;   // developer instrumentation: MMA thread of CTA 0
+  int ts_n = 0;
+  dbg_stamp(ts_mma, ts_n, 30);
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sA = smem;
@@ -924,6 +927,7 @@ __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __gr
   if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  dbg_stamp(ts_mma, ts_n, 31);
   // Barriers, TMEM and descriptors are ready; from here on the producing kernel must have finished (programmatic
   // dependent launch).  Only the producer thread runs ahead: the WEIGHT tiles of its first stages do not depend on the
   // predecessor, so their HBM round trip is started before the wait.
@@ -948,6 +952,7 @@ __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __gr
     }
   }
   pdl_wait();
+  dbg_stamp(ts_mma, ts_n, 32);
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -1028,6 +1033,7 @@ __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __gr
           const int n_at = (nk - i) < KA ? (nk - i) : KA;
           mbar_wait(&full[s], ph);
           tc_fence_after();
+          if (lt == 0 && i == 0) dbg_stamp(ts_mma, ts_n, 33);
 #pragma unroll
           for (int at = 0; at < KA; ++at) {
             if (at >= n_at || no_mma) break;
@@ -1051,6 +1057,7 @@ __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __gr
           }
         }
         if constexpr (CTAS == 2) umma_commit_pair(&acc_full[acc], 3); else umma_commit(&acc_full[acc]);
+        dbg_stamp(ts_mma, ts_n, 34);
       }
     }
   } else {
@@ -1165,8 +1172,10 @@ __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __gr
     if (a.tma_out && lane == 0) bulk_wait_all();   // staged boxes must be drained before the CTA exits
   }
 
+  dbg_stamp(ts_mma, ts_n, 35);
   tc_fence_before();
   if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();   // the peer may still signal / read this CTA
+  dbg_stamp(ts_mma, ts_n, 36);
   if (warp == 1) {
     if constexpr (CTAS == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
