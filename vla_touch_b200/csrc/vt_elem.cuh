@@ -148,6 +148,19 @@ __global__ void __launch_bounds__(256) patchify_kernel(const T* __restrict__ img
   const bool scale255 = flags[0] != 0, donorm = flags[1] != 0;
   const float mean[3] = {0.485f, 0.456f, 0.406f};
   const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  // uint8 pixels: the normalised value of every (channel, pixel value) is computed ONCE per block with exactly the
+  // reference's operations (x / 255, (x - mean) / std in IEEE fp32, visual_encoder.py:78,95-106) and looked up afterwards.
+  __shared__ float lut[sizeof(T) == 1 ? 3 * 256 : 1];
+  if constexpr (sizeof(T) == 1) {
+    for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
+      const int c = i >> 8;
+      float x = (float)(i & 255);
+      if (scale255) x = __fdiv_rn(x, 255.0f);
+      if (donorm) x = __fdiv_rn(__fsub_rn(x, mean[c]), stdv[c]);
+      lut[i] = x;
+    }
+    __syncthreads();
+  }
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int k0 = (int)(idx % k8n) << 3;
@@ -155,22 +168,33 @@ __global__ void __launch_bounds__(256) patchify_kernel(const T* __restrict__ img
     const int p = (int)(m % (gh * gw));
     const long long b = m / (gh * gw);
     const int py = p / gw, px = p - py * gw;
+    // (channel, row, column) of column k0 inside the patch, advanced incrementally: two divisions per 8 elements
+    int c = k0 / pp;
+    int r = k0 - c * pp;
+    int i = r / patch, j = r - i * patch;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int k = k0 + e;
       float x = 0.f;
-      if (k < kk) {
-        const int c = k / pp;
-        const int r = k - c * pp;
-        const int i = r / patch, j = r - i * patch;
+      if (k0 + e < kk) {
         const int yy = py * patch + i, xx = px * patch + j;
         const long long src = (layout == 0) ? (((b * H + yy) * W + xx) * 3 + c) : (((b * 3 + c) * H + yy) * (long long)W + xx);
-        x = (float)img[src];
-        if (scale255) x = __fdiv_rn(x, 255.0f);
-        if (donorm) x = __fdiv_rn(__fsub_rn(x, mean[c]), stdv[c]);
+        if constexpr (sizeof(T) == 1) {
+          x = lut[(c << 8) | (int)img[src]];
+        } else {
+          x = (float)img[src];
+          if (scale255) x = __fdiv_rn(x, 255.0f);
+          if (donorm) x = __fdiv_rn(__fsub_rn(x, mean[c]), stdv[c]);
+        }
       }
       v[e] = x;
+      if (++j == patch) {
+        j = 0;
+        if (++i == patch) {
+          i = 0;
+          ++c;
+        }
+      }
     }
     const long long o = m * out_ld + k0;
     if (out_dtype == 0) {
