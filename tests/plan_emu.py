@@ -142,6 +142,23 @@ def emu_attention(plan, d: nv.AttnDesc):
     _store(plan, d.ctx, d.in_dtype, torch.arange(n)[:, None] * d.ctx_ld + torch.arange(D)[None, :], ctx, d.ctx_plane)
 
 
+def emu_mlp(plan, d: nv.MlpDesc):
+    """h += ls2 * (bf16(GELU(xn W1^T + b1)) W2^T + b2): the hidden activation is handed to the second MMA as bf16."""
+    D, H = d.D, 4 * d.D
+    r = torch.arange(d.rows)
+    xn = _flat(plan, d.xn, torch.bfloat16)[(r[:, None] * d.ld_x + torch.arange(D)[None, :]).reshape(-1)].reshape(d.rows, D).float()
+    w1 = _flat(plan, d.w1, torch.bfloat16)[(torch.arange(H)[:, None] * d.w1_ld + torch.arange(D)[None, :]).reshape(-1)].reshape(H, D).float()
+    w2 = _flat(plan, d.w2, torch.bfloat16)[(torch.arange(D)[:, None] * d.w2_ld + torch.arange(H)[None, :]).reshape(-1)].reshape(D, H).float()
+    b1, b2 = _flat(plan, d.b1, torch.float32)[:H], _flat(plan, d.b2, torch.float32)[:D]
+    hid = F.gelu(xn @ w1.t() + b1).to(torch.bfloat16).float()
+    y = hid @ w2.t() + b2
+    if d.ls2:
+        y = y * _flat(plan, d.ls2, torch.float32)[:D]
+    hf = _flat(plan, d.h, torch.float32)
+    idx = (r[:, None] * d.ld_h + torch.arange(D)[None, :]).reshape(-1)
+    hf[idx] = (y + hf[idx].reshape(d.rows, D)).reshape(-1)
+
+
 def emu_imgstats(plan, d: nv.ImgStatsDesc):
     img = _flat(plan, d.img, TORCH_DT[d.dtype])[: d.count]
     mx = float(img.max())
@@ -296,7 +313,7 @@ def emu_siloss(plan, d: nv.SilossDesc):
 
 _EMU = {nv.QsampleDesc: emu_qsample, nv.SilossDesc: emu_siloss, nv.GemmDesc: emu_gemm, nv.LnDesc: emu_layernorm, nv.AttnDesc: emu_attention, nv.ImgStatsDesc: emu_imgstats,
         nv.PatchifyDesc: emu_patchify, nv.ClsDesc: emu_cls, nv.PackDesc: emu_pack, nv.AffineDesc: emu_affine,
-        nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm}
+        nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm, nv.MlpDesc: emu_mlp}
 
 
 @torch.no_grad()

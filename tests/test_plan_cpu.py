@@ -57,7 +57,8 @@ def test_ctypes_structs_match_the_c_header():
              "vt_imgstats_desc": nv.ImgStatsDesc, "vt_patchify_desc": nv.PatchifyDesc, "vt_cls_desc": nv.ClsDesc,
              "vt_pack_desc": nv.PackDesc, "vt_affine_desc": nv.AffineDesc, "vt_tembed_desc": nv.TembedDesc,
              "vt_sde_desc": nv.SdeDesc, "vt_lstm_desc": nv.LstmDesc, "vt_qsample_desc": nv.QsampleDesc,
-             "vt_siloss_desc": nv.SilossDesc, "vt_opt_tensor": nv.OptTensor, "vt_adamw_desc": nv.AdamwDesc}
+             "vt_siloss_desc": nv.SilossDesc, "vt_opt_tensor": nv.OptTensor, "vt_adamw_desc": nv.AdamwDesc,
+             "vt_mlp_desc": nv.MlpDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/vt_b200.h"', 'int main(void){']
     probes = []
     for cname, cls in descs.items():
@@ -219,3 +220,39 @@ def test_loss_plan_reproduces_the_reference_golden(A, T):
     plan_emu.run(lp.plan)
     for i, key in enumerate(("loss", "v_loss", "s_loss", "b_loss")):
         assert abs(float(lp.out[i]) - float(g[key])) <= 1e-3 * max(1.0, abs(float(g[key]))), key
+
+
+def test_fused_mlp_descriptor_equals_the_two_gemm_descriptors():
+    """vt_mlp_desc (one fused kernel on the GPU) means exactly what the fc1+GELU and fc2+LayerScale+residual GEMM descriptors of
+    the unfused plan mean (HF Dinov2MLP, HF:312-328,380-386): both interpreted on the CPU from the same buffers."""
+    from vla_touch_b200.plan import Plan, linear_desc, pack_linear_weight, ptr
+    D, rows = 384, 150
+    g = torch.Generator().manual_seed(5)
+    w1, w2 = torch.randn(4 * D, D, generator=g) / D ** 0.5, torch.randn(D, 4 * D, generator=g) / (4 * D) ** 0.5
+    outs = []
+    for fused in (True, False):
+        plan = Plan(torch.device("cpu"))
+        xn = plan.buf("xn", (rows, D), torch.bfloat16)
+        hid = plan.buf("hid", (rows, 4 * D), torch.bfloat16)
+        h = plan.buf("h", (rows, D), torch.float32)
+        gg = torch.Generator().manual_seed(6)
+        xn.copy_(torch.randn(rows, D, generator=gg))
+        h.copy_(torch.randn(rows, D, generator=gg))
+        w1p, n1, k1 = pack_linear_weight(w1, torch.bfloat16)
+        w2p, n2, k2 = pack_linear_weight(w2, torch.bfloat16)
+        t = {k: plan.reg(v) for k, v in dict(w1=w1p, w2=w2p, b1=torch.linspace(-1, 1, 4 * D), b2=torch.linspace(1, -1, D),
+                                             ls2=torch.linspace(0.5, 1.5, D)).items()}
+        if fused:
+            d = nv.MlpDesc()
+            d.xn, d.ld_x, d.w1, d.w1_ld, d.b1 = ptr(xn), D, ptr(t["w1"]), k1, ptr(t["b1"])
+            d.w2, d.w2_ld, d.b2, d.ls2 = ptr(t["w2"]), k2, ptr(t["b2"]), ptr(t["ls2"])
+            d.h, d.ld_h, d.rows, d.D = ptr(h), D, rows, D
+            plan.add(d, "mlp")
+        else:
+            plan.add(linear_desc(a=xn, rows=rows, k=k1, a_ld=D, w=t["w1"], n=4 * D, n_pad=n1, w_ld=k1, out=hid, ldc=4 * D,
+                                 bias=t["b1"], act=nv.ACT_GELU), "fc1")
+            plan.add(linear_desc(a=hid, rows=rows, k=k2, a_ld=4 * D, w=t["w2"], n=D, n_pad=n2, w_ld=k2, out=h, ldc=D, bias=t["b2"],
+                                 colscale=t["ls2"], res=h, ldres=D), "fc2")
+        plan_emu.run(plan)
+        outs.append(h.clone())
+    assert torch.equal(outs[0], outs[1])
