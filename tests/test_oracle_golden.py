@@ -99,6 +99,29 @@ def test_losses(A, T):
         torch.testing.assert_close(got, g[key], rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("A,T", [(10, 16), (7, 64)])
+def test_loss_gradients(A, T):
+    """Autograd through the oracle's bridge_losses against the reference's loss.backward() (oracle/gen_golden_grads.py):
+    d loss / d obs_cond in full, and norm / sum / first elements of every parameter gradient of net.{b,v,s}_net.  This is the
+    parity gate the backward kernels will be held to."""
+    g, gg = U.golden(f"loss_A{A}_T{T}"), U.golden(f"loss_grads_A{A}_T{T}")
+    sd = {k: v.clone().requires_grad_(True) for k, v in U.net_sd(A, 21).items()}
+    cond = syn.det_normal("loss.cond", (3, 256), 24).requires_grad_(True)
+    loss, *_ = orc.bridge_losses(sd, cond, syn.det_uniform("loss.exp", (3, T, A), 24, -1.0, 1.0),
+                                 syn.det_uniform("loss.vla", (3, T, A), 24, -1.0, 1.0), g["step"], g["z_unit"])
+    loss.backward()
+    torch.testing.assert_close(cond.grad, gg["d_cond"], rtol=1e-4, atol=1e-5 * float(gg["d_cond"].abs().max()))
+    names = [str(n) for n in gg["names"]]
+    assert sorted(names) == sorted(sd.keys())
+    for i, n in enumerate(names):
+        gr = sd[n].grad.flatten().double()
+        scale = max(float(gg["norm"][i]), 1e-12)
+        assert abs(float(gr.norm()) - float(gg["norm"][i])) <= 1e-4 * scale, n
+        assert abs(float(gr.sum()) - float(gg["sum"][i])) <= 1e-3 * scale, n
+        k = min(8, gr.numel())
+        assert float((gr[:k] - gg["head"][i][:k].double()).abs().max()) <= 1e-4 * scale, n
+
+
 @pytest.mark.parametrize("tag", list(U.PREDICT_CASES))
 def test_predict(tag):
     c = U.predict_case(tag)
@@ -128,3 +151,33 @@ def test_lstm(A, Fd, T):
     torch.testing.assert_close(torch.nn.functional.mse_loss(fwd, expert), g["loss"], rtol=1e-5, atol=1e-6)
     # predict_sequence == step-by-step forward + expert de-normalisation (eval mode) :288-319
     torch.testing.assert_close(orc.denormalize_actions(fwd, st, "expert"), g["seq"], rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("A,Fd,T", [(10, 3, 16), (7, 64, 32)])
+def test_lstm_loss_gradients(A, Fd, T):
+    """Autograd through the oracle's lstm_forward + MSE against the reference's get_loss(...).backward() in eval mode
+    (oracle/gen_golden_grads.py; lstm_step_controller.py:321-337): the parity gate of the LSTM BPTT kernel (row a12)."""
+    gg = U.golden(f"lstm_grads_A{A}_F{Fd}_T{T}")
+    mods = {
+        "force_encoder": syn.synth_state_dict(shp.mlp_shapes([Fd, 128, 128]), 41, "lstm.force_encoder."),
+        "lstm": syn.synth_state_dict(shp.lstm_shapes(128 + A), 41, "lstm.lstm."),
+        "output_head": syn.synth_state_dict(shp.lstm_head_shapes(256, A), 41, "lstm.output_head."),
+    }
+    mods = {m: {k: v.clone().requires_grad_(True) for k, v in sd.items()} for m, sd in mods.items()}
+    st = syn.synth_stats_varied(A, 41)
+    vla_n = orc.normalize_actions(syn.det_uniform("lstm.vla", (3, T, A), 41, -1.0, 1.0), st, "vla")
+    forces = syn.det_normal("lstm.forces", (3, T, Fd), 41)
+    cond = syn.det_normal("lstm.cond", (3, 256), 41).requires_grad_(True)
+    expert = syn.det_uniform("lstm.exp", (3, T, A), 41, -1.0, 1.0)
+    loss = torch.nn.functional.mse_loss(orc.lstm_forward(mods, vla_n, cond, forces), expert)
+    torch.testing.assert_close(loss.detach(), gg["loss"], rtol=1e-5, atol=1e-6)
+    loss.backward()
+    torch.testing.assert_close(cond.grad, gg["d_cond"], rtol=1e-4, atol=1e-6)
+    for i, n in enumerate(str(x) for x in gg["names"]):
+        m, key = n.split(".", 1)
+        gr = mods[m][key].grad.flatten().double()
+        scale = max(float(gg["norm"][i]), 1e-12)
+        assert abs(float(gr.norm()) - float(gg["norm"][i])) <= 1e-4 * scale, n
+        assert abs(float(gr.sum()) - float(gg["sum"][i])) <= 1e-3 * scale, n
+        k = min(8, gr.numel())
+        assert float((gr[:k] - gg["head"][i][:k].double()).abs().max()) <= 1e-4 * scale, n

@@ -14,7 +14,7 @@ TOK_IDX = lambda n: list(range(8)) + list(range(n - 4, n))
 
 def golden(name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
-    return {k: torch.from_numpy(np.asarray(z[k])) for k in z.files}
+    return {k: (torch.from_numpy(np.asarray(z[k])) if z[k].dtype.kind in "fiub" else z[k]) for k in z.files}   # names stay numpy
 
 
 def dino_sd(hidden, layers, seed):
