@@ -181,3 +181,45 @@ def test_lstm_loss_gradients(A, Fd, T):
         assert abs(float(gr.sum()) - float(gg["sum"][i])) <= 1e-3 * scale, n
         k = min(8, gr.numel())
         assert float((gr[:k] - gg["head"][i][:k].double()).abs().max()) <= 1e-4 * scale, n
+
+
+def test_explicit_unet_backward_matches_autograd():
+    """oracle/vt_oracle_bwd.py (per-tap dgrad / wgrad, fused GroupNorm+Mish backward, FiLM, skips: the op decomposition of the
+    round-2 kernels) against autograd through the forward oracle, every parameter, the condition and the input."""
+    from oracle import vt_oracle_bwd as ob
+    A, T, B = 7, 16, 2
+    sd = {k: v.double().requires_grad_(True) for k, v in U.net_sd(A, 21, "v_net").items()}
+    x = syn.det_uniform("bwd.x", (B, T, A), 5, -1.0, 1.0).double().requires_grad_(True)
+    cond = syn.det_normal("bwd.cond", (B, 256), 5).double().requires_grad_(True)
+    t = torch.tensor([0.3, 0.9], dtype=torch.float64)
+    dout = syn.det_normal("bwd.dout", (B, T, A), 5).double()
+    out = orc.unet_forward(sd, x, t, cond)
+    out.backward(dout)
+    with torch.no_grad():
+        out2, cache = ob.unet_forward_cached({k: v.detach() for k, v in sd.items()}, x.detach(), t, cond.detach())
+        grads, dcond, dx = ob.unet_backward({k: v.detach() for k, v in sd.items()}, cache, dout)
+    torch.testing.assert_close(out2, out.detach(), rtol=1e-9, atol=1e-9)
+    torch.testing.assert_close(dcond, cond.grad, rtol=1e-7, atol=1e-9)
+    torch.testing.assert_close(dx, x.grad, rtol=1e-7, atol=1e-9)
+    assert sorted(grads) == sorted(sd)
+    for k in sd:
+        torch.testing.assert_close(grads[k], sd[k].grad, rtol=1e-7, atol=1e-8, msg=k)
+
+
+@pytest.mark.parametrize("A,T", [(10, 16), (7, 64)])
+def test_explicit_loss_backward_matches_reference_digests(A, T):
+    """The explicit backward of get_loss (three nets, v / s / b targets) against the reference's loss.backward() fixtures."""
+    from oracle import vt_oracle_bwd as ob
+    g, gg = U.golden(f"loss_A{A}_T{T}"), U.golden(f"loss_grads_A{A}_T{T}")
+    with torch.no_grad():
+        loss, grads, dcond = ob.bridge_loss_backward(U.net_sd(A, 21), syn.det_normal("loss.cond", (3, 256), 24),
+                                                     syn.det_uniform("loss.exp", (3, T, A), 24, -1.0, 1.0),
+                                                     syn.det_uniform("loss.vla", (3, T, A), 24, -1.0, 1.0), g["step"], g["z_unit"])
+    assert abs(float(loss) - float(g["loss"])) <= 1e-4 * max(1.0, abs(float(g["loss"])))
+    torch.testing.assert_close(dcond, gg["d_cond"], rtol=1e-3, atol=1e-4 * float(gg["d_cond"].abs().max()))
+    for i, n in enumerate(str(x) for x in gg["names"]):
+        gr = grads[n].flatten().double()
+        scale = max(float(gg["norm"][i]), 1e-12)
+        assert abs(float(gr.norm()) - float(gg["norm"][i])) <= 1e-3 * scale, n
+        k = min(8, gr.numel())
+        assert float((gr[:k] - gg["head"][i][:k].double()).abs().max()) <= 1e-3 * scale, n
