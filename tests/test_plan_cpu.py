@@ -256,3 +256,47 @@ def test_fused_mlp_descriptor_equals_the_two_gemm_descriptors():
         plan_emu.run(plan)
         outs.append(h.clone())
     assert torch.equal(outs[0], outs[1])
+
+
+def test_dgrad_descriptors_reproduce_the_explicit_backward():
+    """unet_bwd.py: the data gradients of Conv1d(k5) / Conv1d(k3, stride 2) / ConvTranspose1d(k4, stride 2) expressed as forward
+    implicit-GEMM descriptors (shifted taps, transposed weight slices, phase-interleaved rows), interpreted on the CPU, against
+    oracle/vt_oracle_bwd.py (which is pinned to autograd and to the reference's gradients)."""
+    from oracle import vt_oracle_bwd as ob
+    from vla_touch_b200 import unet_bwd as ub
+    from vla_touch_b200.plan import Plan
+    from vla_touch_b200.unet import _View
+    G, B, C = 2, 3, 256
+    g = torch.Generator().manual_seed(9)
+    bf = lambda t: t.to(torch.bfloat16).float()
+
+    def run(kind, T_dy, T_dx, ws):
+        plan = Plan(torch.device("cpu"))
+        dy = plan.buf("dy", (G, B, T_dy, C), torch.bfloat16)
+        dx = plan.buf("dx", (G, B, T_dx, C), torch.bfloat16)
+        dy.copy_(torch.randn(G, B, T_dy, C, generator=g))
+        ctx = ub.DgradCtx(G, precise=False)
+        vy, vx = _View(dy, T_dy, C), _View(dx, T_dx, C)
+        if kind == "k5":
+            ub.conv_dgrad(plan, ctx, B, vy, vx, ws, pad=2)
+        elif kind == "down":
+            ub.downsample_dgrad(plan, ctx, B, vy, vx, ws)
+        else:
+            ub.upsample_dgrad(plan, ctx, B, vy, vx, ws)
+        plan_emu.run(plan)
+        for n in range(G):
+            dyn = dy[n].float().permute(0, 2, 1)                      # [B, C, T]
+            w = bf(ws[n])
+            if kind == "k5":
+                ref = ob.conv1d_bwd(torch.zeros(B, C, T_dx), w, dyn, padding=2)[0]
+            elif kind == "down":
+                ref = ob.conv1d_bwd(torch.zeros(B, C, T_dx), w, dyn, stride=2, padding=1)[0]
+            else:
+                ref = ob.convT1d_bwd(torch.zeros(B, C, T_dx), w, dyn)[0]
+            got = dx[n].float().permute(0, 2, 1)
+            err = (got - ref).abs().max().item()
+            assert err <= 1e-2 * ref.abs().max().item(), (kind, n, err, ref.abs().max().item())
+
+    run("k5", 16, 16, [torch.randn(C, C, 5, generator=g) / (5 * C) ** 0.5 for _ in range(G)])
+    run("down", 8, 16, [torch.randn(C, C, 3, generator=g) / (3 * C) ** 0.5 for _ in range(G)])
+    run("up", 32, 16, [torch.randn(C, C, 4, generator=g) / (2 * C) ** 0.5 for _ in range(G)])
