@@ -268,3 +268,97 @@ def bridge_loss_backward(net_sd: SD, obs_cond, expert_act, vla_act, step, z_unit
         grads.update({n + k: v for k, v in g.items()})
         dcond = dcond + dc
     return loss, grads, dcond
+
+
+# ---------------------------------------------------------------------------------------------- LSTM controller (row a12)
+def lstm_loss_backward(mods: Dict[str, SD], vla_act_n, obs_cond, forces, expert_act):
+    """TactileLSTMController.get_loss (lstm_step_controller.py:321-337, eval mode: dropout off) forward + explicit
+    back-propagation through time, in the decomposition of the planned kernels: the input / head linear maps of ALL time steps
+    are batched GEMMs (their weight gradients one GEMM each over B*T rows), only the recurrence itself is sequential
+    (per step: gate derivatives, dh_{t-1} = W_hh^T dgates, W_hh gradient accumulated as an outer product).
+    -> (loss, grads {module.param}, d obs_cond)."""
+    fe, lstm, head = mods["force_encoder"], mods["lstm"], mods["output_head"]
+    B, T, A = vla_act_n.shape
+    L = 0
+    while f"weight_ih_l{L}" in lstm:
+        L += 1
+    H = lstm["weight_hh_l0"].shape[1]
+    # ---- forward, keeping what BPTT needs ----
+    f0 = forces.reshape(B * T, -1)
+    a1 = F.linear(f0, fe["0.weight"], fe["0.bias"])
+    g1 = F.gelu(a1)
+    fenc = F.linear(g1, fe["2.weight"], fe["2.bias"]).reshape(B, T, -1)
+    x = torch.cat([fenc, vla_act_n], dim=-1)
+    inps = [x]
+    gates, cs, hs = [], [], []
+    for l in range(L):
+        xin = inps[l]
+        pre_x = F.linear(xin.reshape(B * T, -1), lstm[f"weight_ih_l{l}"], lstm[f"bias_ih_l{l}"]).reshape(B, T, 4 * H)   # batched
+        h, c = torch.zeros(B, H), torch.zeros(B, H)
+        gl, cl, hl = [], [], []
+        for t in range(T):
+            g = pre_x[:, t] + F.linear(h, lstm[f"weight_hh_l{l}"], lstm[f"bias_hh_l{l}"])
+            i_, f_, g_, o_ = g.chunk(4, dim=-1)
+            i_, f_, g_, o_ = torch.sigmoid(i_), torch.sigmoid(f_), torch.tanh(g_), torch.sigmoid(o_)
+            c_prev = c
+            c = f_ * c + i_ * g_
+            h = o_ * torch.tanh(c)
+            gl.append((i_, f_, g_, o_, c_prev))
+            cl.append(c)
+            hl.append(h)
+        gates.append(gl)
+        cs.append(cl)
+        hs.append(torch.stack(hl, dim=1))
+        inps.append(hs[-1])
+    y = hs[-1]
+    comb = torch.cat([y, obs_cond.unsqueeze(1).expand(B, T, obs_cond.shape[-1])], dim=-1).reshape(B * T, -1)
+    z0 = F.linear(comb, head["0.weight"], head["0.bias"])
+    mu = z0.mean(dim=-1, keepdim=True)
+    rstd = torch.rsqrt(z0.var(dim=-1, unbiased=False, keepdim=True) + 1e-5)
+    zh = (z0 - mu) * rstd
+    z1 = zh * head["1.weight"] + head["1.bias"]
+    g2 = F.gelu(z1)
+    delta = F.linear(g2, head["4.weight"], head["4.bias"]).reshape(B, T, A)
+    out = vla_act_n + delta
+    loss = torch.mean((out - expert_act) ** 2)
+    # ---- backward ----
+    grads: Dict[str, torch.Tensor] = {}
+    dout = (2.0 / out.numel()) * (out - expert_act)
+    ddelta = dout.reshape(B * T, A)
+    dg2, grads["output_head.4.weight"], grads["output_head.4.bias"] = linear_bwd(g2, head["4.weight"], ddelta)
+    gelu_grad = lambda v: 0.5 * (1 + torch.erf(v / 2 ** 0.5)) + v * torch.exp(-0.5 * v * v) / (2 * torch.pi) ** 0.5
+    dz1 = dg2 * gelu_grad(z1)
+    grads["output_head.1.weight"] = (dz1 * zh).sum(dim=0)
+    grads["output_head.1.bias"] = dz1.sum(dim=0)
+    dzh = dz1 * head["1.weight"]
+    dz0 = rstd * (dzh - dzh.mean(dim=-1, keepdim=True) - zh * (dzh * zh).mean(dim=-1, keepdim=True))
+    dcomb, grads["output_head.0.weight"], grads["output_head.0.bias"] = linear_bwd(comb, head["0.weight"], dz0)
+    dcomb = dcomb.reshape(B, T, -1)
+    dcond = dcomb[:, :, H:].sum(dim=1)
+    dy = dcomb[:, :, :H]
+    for l in reversed(range(L)):
+        w_hh = lstm[f"weight_hh_l{l}"]
+        dgates_all = torch.zeros(B, T, 4 * H)
+        dh_next, dc_next = torch.zeros(B, H), torch.zeros(B, H)
+        dw_hh = torch.zeros_like(w_hh)
+        for t in reversed(range(T)):
+            i_, f_, g_, o_, c_prev = gates[l][t]
+            tc = torch.tanh(cs[l][t])
+            dh = dy[:, t] + dh_next
+            dc = dc_next + dh * o_ * (1 - tc * tc)
+            dg = torch.cat([dc * g_ * i_ * (1 - i_), dc * c_prev * f_ * (1 - f_), dc * i_ * (1 - g_ * g_), dh * tc * o_ * (1 - o_)], dim=-1)
+            dgates_all[:, t] = dg
+            h_prev = hs[l][:, t - 1] if t > 0 else torch.zeros(B, H)
+            dw_hh += dg.t() @ h_prev
+            dh_next = dg @ w_hh
+            dc_next = dc * f_
+        grads[f"lstm.weight_hh_l{l}"] = dw_hh
+        grads[f"lstm.bias_hh_l{l}"] = dgates_all.sum(dim=(0, 1))
+        grads[f"lstm.bias_ih_l{l}"] = grads[f"lstm.bias_hh_l{l}"].clone()
+        dxin, grads[f"lstm.weight_ih_l{l}"], _ = linear_bwd(inps[l].reshape(B * T, -1), lstm[f"weight_ih_l{l}"],
+                                                            dgates_all.reshape(B * T, 4 * H))
+        dy = dxin.reshape(B, T, -1)
+    dfenc = dy[:, :, : fenc.shape[-1]].reshape(B * T, -1)
+    dg1, grads["force_encoder.2.weight"], grads["force_encoder.2.bias"] = linear_bwd(g1, fe["2.weight"], dfenc)
+    _, grads["force_encoder.0.weight"], grads["force_encoder.0.bias"] = linear_bwd(f0, fe["0.weight"], dg1 * gelu_grad(a1))
+    return loss, grads, dcond

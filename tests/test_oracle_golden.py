@@ -223,3 +223,30 @@ def test_explicit_loss_backward_matches_reference_digests(A, T):
         assert abs(float(gr.norm()) - float(gg["norm"][i])) <= 1e-3 * scale, n
         k = min(8, gr.numel())
         assert float((gr[:k] - gg["head"][i][:k].double()).abs().max()) <= 1e-3 * scale, n
+
+
+@pytest.mark.parametrize("A,Fd,T", [(10, 3, 16), (7, 64, 32)])
+def test_explicit_lstm_bptt_matches_reference_digests(A, Fd, T):
+    """oracle/vt_oracle_bwd.lstm_loss_backward (batched input / head GEMMs + sequential recurrence backward) against the
+    reference's get_loss().backward() fixtures (lstm_step_controller.py:321-337, eval mode)."""
+    from oracle import vt_oracle_bwd as ob
+    gg = U.golden(f"lstm_grads_A{A}_F{Fd}_T{T}")
+    mods = {
+        "force_encoder": syn.synth_state_dict(shp.mlp_shapes([Fd, 128, 128]), 41, "lstm.force_encoder."),
+        "lstm": syn.synth_state_dict(shp.lstm_shapes(128 + A), 41, "lstm.lstm."),
+        "output_head": syn.synth_state_dict(shp.lstm_head_shapes(256, A), 41, "lstm.output_head."),
+    }
+    st = syn.synth_stats_varied(A, 41)
+    vla_n = orc.normalize_actions(syn.det_uniform("lstm.vla", (3, T, A), 41, -1.0, 1.0), st, "vla")
+    with torch.no_grad():
+        loss, grads, dcond = ob.lstm_loss_backward(mods, vla_n, syn.det_normal("lstm.cond", (3, 256), 41),
+                                                   syn.det_normal("lstm.forces", (3, T, Fd), 41),
+                                                   syn.det_uniform("lstm.exp", (3, T, A), 41, -1.0, 1.0))
+    torch.testing.assert_close(loss, gg["loss"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(dcond, gg["d_cond"], rtol=1e-3, atol=1e-6)
+    for i, n in enumerate(str(x) for x in gg["names"]):
+        gr = grads[n].flatten().double()
+        scale = max(float(gg["norm"][i]), 1e-12)
+        assert abs(float(gr.norm()) - float(gg["norm"][i])) <= 1e-3 * scale, n
+        k = min(8, gr.numel())
+        assert float((gr[:k] - gg["head"][i][:k].double()).abs().max()) <= 1e-3 * scale, n
