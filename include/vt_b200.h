@@ -273,6 +273,69 @@ typedef struct vt_siloss_desc {
   float* out;           /* [4] */
 } vt_siloss_desc;
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Backward of the U-Net's Conv1dBlock = Conv1d -> GroupNorm(8) -> Mish (conditional_unet_1D.py:40-55) and of the FiLM
+ * modulation that follows blocks[0] (:97-102).  The data gradients of the convolutions run on vt_gemm_desc unchanged
+ * (transposed weight slices, shifted taps); the WEIGHT gradients are plain row-major GEMMs over transposed operand copies
+ * (K = B*T rows) made by vt_tcol_desc; everything elementwise is vt_gnbwd_desc.
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* Transposed im2col copy (bf16):  out[g][tap * c_pad + c][b * t_out + t] = src[g][b][t * stride + tap_off[tap]][c],
+ * zero where the position falls outside [0, T_src).  Rows c in [C, c_pad) and columns >= B * t_out are never written
+ * (the caller zero-initialises the buffer once).
+ *   wgrad Conv1d(k, s, p):        dW[co][k][ci] = dY^T (taps = 1, off 0)  x  X^T (tap_off[k] = k - p, stride s)
+ *   wgrad ConvTranspose1d(4,2,1): dW[ci][k][co] = X^T                     x  dY^T (tap_off[k] = k - 1, stride 2) */
+typedef struct vt_tcol_desc {
+  const void* src;      /* channels-last activation, first channel of the window */
+  int32_t src_dtype;    /* VT_BF16 or VT_F32 */
+  int64_t ld;           /* elements between positions */
+  int64_t sB, sG;       /* elements between samples / groups */
+  int32_t G, B, T_src, C;
+  int32_t taps;
+  int32_t tap_off[VT_MAX_TAPS];
+  int32_t stride;
+  int32_t t_out;        /* positions per sample in the K index */
+  void* out;            /* bf16 [G][taps * c_pad][k_ld] */
+  int32_t c_pad;
+  int64_t k_ld;         /* >= B * t_out, multiple of 64 */
+  int64_t out_g;        /* elements between groups of out */
+} vt_tcol_desc;
+
+/* GroupNorm + Mish (+ FiLM) backward from the raw conv output (bias included), per net g and sample b:
+ *   xh = (raw - mean) * rstd over each (sample, group);  y = xh * gamma + beta;  m = mish(y)
+ *   film != null (forward out = scale * m + shift):  dm = dout * scale,  dfilm[b][film_off + c] = sum_t dout * m,
+ *                                                    dfilm[b][film_off + C + c] = sum_t dout;   else dm = dout
+ *   da = dm * mish'(y);  dgamma[c] = sum_{b,t} da * xh;  dbeta[c] = sum_{b,t} da;  dxh = da * gamma
+ *   draw = rstd * (dxh - mean_g(dxh) - xh * mean_g(dxh * xh));  dbias[c] = sum_{b,t} draw       (two launches) */
+typedef struct vt_gnbwd_desc {
+  const float* raw;     /* [G][B][T][C] */
+  const float* dout;    /* [G][B][T][dout_ld] */
+  int64_t dout_ld, dout_g;
+  const float* gamma;   /* [G][p_ld] */
+  const float* beta;    /* [G][p_ld] */
+  int32_t p_ld;
+  const float* film;    /* [G][B][film_ld] or null */
+  float* dfilm;         /* [G][B][film_ld] or null (same geometry as film) */
+  int64_t film_g;
+  int32_t film_ld, film_off;
+  void* draw;           /* bf16 [G][B][T][C]: the A operand of the conv's dgrad / wgrad */
+  float* part;          /* scratch [G][B][3][C] */
+  float* dgamma;        /* [G][p_ld] */
+  float* dbeta;         /* [G][p_ld] */
+  float* dbias;         /* [G][p_ld] */
+  int32_t G, B, T, C, groups;
+  float eps;
+} vt_gnbwd_desc;
+
+/* out[g][c] = sum_r x[g][r][c]: bias gradient of a convolution that has no GroupNorm (down / up-sampling, 1x1 convs). */
+typedef struct vt_colsum_desc {
+  const float* x;
+  int64_t ld, x_g;
+  int32_t G, rows, C;
+  float* out;           /* [G][out_ld] */
+  int32_t out_ld;
+} vt_colsum_desc;
+
 /* nn.LSTM (gate order i,f,g,o), lstm_step_controller.py:66-73,196-204: the input projections xw = W_ih x + b_ih
  * + b_hh are precomputed by a GEMM; this op runs the recurrence over T steps for one layer. */
 typedef struct vt_lstm_desc {
@@ -339,6 +402,9 @@ int vt_program_add_sde(vt_program* p, const vt_sde_desc* d);
 int vt_program_add_lstm(vt_program* p, const vt_lstm_desc* d);
 int vt_program_add_qsample(vt_program* p, const vt_qsample_desc* d);
 int vt_program_add_siloss(vt_program* p, const vt_siloss_desc* d);
+int vt_program_add_tcol(vt_program* p, const vt_tcol_desc* d);
+int vt_program_add_gnbwd(vt_program* p, const vt_gnbwd_desc* d);
+int vt_program_add_colsum(vt_program* p, const vt_colsum_desc* d);
 
 /* Launch ops [first, first+count) in order on `stream` (count < 0: to the end). */
 int vt_program_run(vt_program* p, int first, int count, void* stream);

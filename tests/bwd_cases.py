@@ -1,0 +1,168 @@
+"""TEST INFRASTRUCTURE ONLY -- the backward-plan cases shared by the CPU (descriptor interpreter) and the GPU (native kernels)
+tests: each builder returns (plan, check) where check() compares the plan's output buffers with oracle/vt_oracle_bwd.py."""
+import torch
+
+from oracle import vt_oracle_bwd as ob
+from vla_touch_b200 import unet_bwd as ub
+from vla_touch_b200.plan import Plan
+from vla_touch_b200.unet import _View
+
+bf = lambda t: t.to(torch.bfloat16).float()
+
+
+def _rel(got, ref):
+    return (got - ref).abs().max().item() / max(ref.abs().max().item(), 1e-12)
+
+
+def wgrad_case(kind: str, device, G=2, B=3, C=256, seed=11):
+    """conv_wgrad for 'k5' (Conv1d k5 p2), 'down' (Conv1d k3 s2 p1), 'up' (ConvTranspose1d k4 s2 p1), 'k1in' (1x1 conv on a
+    64-channel padded 7-channel input shared by all nets: the first block's residual_conv)."""
+    g = torch.Generator().manual_seed(seed)
+    plan = Plan(device)
+    ctx = ub.DgradCtx(G, precise=False)
+    T = 16
+    if kind == "k1in":
+        Cx, Tx, Ty, shared = 64, T, T, True
+        x = plan.buf("x", (B, Tx, Cx), torch.bfloat16)
+        x[:, :, :7] = torch.randn(B, Tx, 7, generator=g).to(device)
+    else:
+        Cx, Tx, shared = C, T, False
+        Ty = {"k5": T, "down": T // 2, "up": 2 * T}[kind]
+        x = plan.buf("x", (G, B, Tx, Cx), torch.bfloat16)
+        x.copy_(torch.randn(G, B, Tx, Cx, generator=g))
+    dy = plan.buf("dy", (G, B, Ty, C), torch.bfloat16)
+    dy.copy_(torch.randn(G, B, Ty, C, generator=g))
+    vx, vy = _View(x, Tx, Cx, shared=shared), _View(dy, Ty, C)
+    if kind == "k5":
+        dw = ub.conv_wgrad(plan, ctx, B, vy, vx, tap_off=[k - 2 for k in range(5)], t_out=T)
+    elif kind == "k1in":
+        dw = ub.conv_wgrad(plan, ctx, B, vy, vx, tap_off=[0], t_out=T)
+    elif kind == "down":
+        dw = ub.conv_wgrad(plan, ctx, B, vy, vx, tap_off=[k - 1 for k in range(3)], stride=2, t_out=Ty)
+    else:
+        dw = ub.conv_wgrad(plan, ctx, B, vx, vy, tap_off=[k - 1 for k in range(4)], stride=2, t_out=Tx)
+
+    def check(tol=1e-2):
+        for n in range(G):
+            xn = (x if shared else x[n]).float().cpu().permute(0, 2, 1)
+            dyn = dy[n].float().cpu().permute(0, 2, 1)
+            if kind == "k5":
+                ref = ob.conv1d_bwd(xn, torch.zeros(C, Cx, 5), dyn, padding=2)[1]
+                got = ub.unpack_wgrad(dw, Cx, 5)[n]
+            elif kind == "k1in":
+                ref = ob.conv1d_bwd(xn[:, :7], torch.zeros(C, 7, 1), dyn)[1]
+                got = ub.unpack_wgrad(dw, 7, 1)[n]
+            elif kind == "down":
+                ref = ob.conv1d_bwd(xn, torch.zeros(C, Cx, 3), dyn, stride=2, padding=1)[1]
+                got = ub.unpack_wgrad(dw, Cx, 3)[n]
+            else:
+                ref = ob.convT1d_bwd(xn, torch.zeros(Cx, C, 4), dyn)[1]
+                got = ub.unpack_wgrad(dw, C, 4)[n]
+            e = _rel(got.float().cpu(), ref)
+            assert e <= tol, (kind, n, e)
+    return plan, check
+
+
+def block_case(device, film: bool, G=2, B=3, T=16, Ci=256, Co=256, seed=5):
+    """conv_block_backward of Conv1d(k5) -> GroupNorm(8) -> Mish [-> FiLM] against gn_mish_bwd + conv1d_bwd of the oracle."""
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g)
+    plan = Plan(device)
+    ctx = ub.DgradCtx(G, precise=False)
+    ws = [r(Co, Ci, 5) / (5 * Ci) ** 0.5 for _ in range(G)]
+    bs = [0.1 * r(Co) for _ in range(G)]
+    gam = [1 + 0.2 * r(Co) for _ in range(G)]
+    bet = [0.2 * r(Co) for _ in range(G)]
+    x = plan.buf("x", (G, B, T, Ci), torch.bfloat16)
+    x.copy_(r(G, B, T, Ci))
+    dout = plan.buf("dout", (G, B, T, Co), torch.float32)
+    dout.copy_(r(G, B, T, Co))
+    dx = plan.buf("dx", (G, B, T, Ci), torch.bfloat16)
+    fl = None
+    if film:
+        LD, OFF = 4 * Co, Co          # a table wider than the block's slice, like the stacked FiLM table of the 12 blocks
+        ft = plan.buf("film", (G, B, LD), torch.float32)
+        ft.copy_(1 + 0.3 * r(G, B, LD))
+        dft = plan.buf("dfilm", (G, B, LD), torch.float32)
+        fl = (ft, dft, OFF)
+    out = ub.conv_block_backward(plan, ctx, B, _View(x, T, Ci), ws, bs, gam, bet, dout, _View(dx, T, Ci), film=fl, tag="blk")
+
+    def check(tol=2e-2):
+        errs = {}
+        for n in range(G):
+            xn = x[n].float().cpu().permute(0, 2, 1)
+            w = bf(ws[n])
+            raw = ob.conv1d_fwd(xn, w, bs[n], padding=2)
+            do = dout[n].float().cpu().permute(0, 2, 1)
+            if film:
+                scale = ft[n, :, OFF: OFF + Co].float().cpu()[:, :, None]
+                y0 = ob.gn_mish_fwd(raw, gam[n], bet[n])
+                demb = torch.cat([(do * y0).sum(-1), do.sum(-1)], dim=1)
+                errs["dfilm"] = _rel(dft[n, :, OFF: OFF + 2 * Co].float().cpu(), demb)
+                assert float(dft[n, :, :OFF].abs().max()) == 0 and float(dft[n, :, OFF + 2 * Co:].abs().max()) == 0
+                do = do * scale
+            draw, dgam, dbet = ob.gn_mish_bwd(raw, gam[n], bet[n], do)
+            dxr, dwr, dbr = ob.conv1d_bwd(xn, w, draw, padding=2)
+            errs["raw"] = _rel(out["raw"][n].float().cpu().permute(0, 2, 1), raw)
+            errs["draw"] = _rel(out["draw"][n].float().cpu().permute(0, 2, 1), draw)
+            errs["dgamma"] = _rel(out["dgamma"][n].float().cpu(), dgam)
+            errs["dbeta"] = _rel(out["dbeta"][n].float().cpu(), dbet)
+            errs["dbias"] = _rel(out["dbias"][n].float().cpu(), dbr)
+            errs["dw"] = _rel(ub.unpack_wgrad(out["dw"], Ci, 5)[n].float().cpu(), dwr)
+            errs["dx"] = _rel(dx[n].float().cpu().permute(0, 2, 1), dxr)
+            bad = {k: v for k, v in errs.items() if not v <= tol}
+            assert not bad, (n, bad, errs)
+        return errs
+    return plan, check
+
+
+def colsum_case(device, G=2, rows=100, C=70, ld=96):
+    from vla_touch_b200 import native as nv
+    from vla_touch_b200.plan import ptr
+    plan = Plan(device)
+    x = plan.buf("x", (G, rows, ld), torch.float32)
+    x.copy_(torch.randn(G, rows, ld, generator=torch.Generator().manual_seed(3)))
+    out = plan.buf("out", (G, 128), torch.float32)
+    d = nv.ColsumDesc()
+    d.x, d.ld, d.x_g, d.G, d.rows, d.C, d.out, d.out_ld = ptr(x), ld, rows * ld, G, rows, C, ptr(out), 128
+    plan.add(d, "colsum")
+
+    def check(tol=1e-5):
+        ref = x[:, :, :C].float().cpu().sum(dim=1)
+        assert _rel(out[:, :C].float().cpu(), ref) <= tol
+        assert float(out[:, C:].abs().max()) == 0
+    return plan, check
+
+
+def dgrad_case(kind: str, device, G=2, B=3, C=256, seed=9):
+    """conv_dgrad / downsample_dgrad / upsample_dgrad (forward implicit-GEMM descriptors) against the oracle's dX."""
+    g = torch.Generator().manual_seed(seed)
+    T_dy, T_dx, K = {"k5": (16, 16, 5), "down": (8, 16, 3), "up": (32, 16, 4)}[kind]
+    ws = [torch.randn(C, C, K, generator=g) / (K * C) ** 0.5 for _ in range(G)]
+    plan = Plan(device)
+    dy = plan.buf("dy", (G, B, T_dy, C), torch.bfloat16)
+    dx = plan.buf("dx", (G, B, T_dx, C), torch.bfloat16)
+    dy.copy_(torch.randn(G, B, T_dy, C, generator=g))
+    ctx = ub.DgradCtx(G, precise=False)
+    vy, vx = _View(dy, T_dy, C), _View(dx, T_dx, C)
+    if kind == "k5":
+        ub.conv_dgrad(plan, ctx, B, vy, vx, ws, pad=2)
+    elif kind == "down":
+        ub.downsample_dgrad(plan, ctx, B, vy, vx, ws)
+    else:
+        ub.upsample_dgrad(plan, ctx, B, vy, vx, ws)
+
+    def check(tol=1e-2):
+        for n in range(G):
+            dyn = dy[n].float().cpu().permute(0, 2, 1)
+            w = bf(ws[n])
+            z = torch.zeros(B, C, T_dx)
+            if kind == "k5":
+                ref = ob.conv1d_bwd(z, w, dyn, padding=2)[0]
+            elif kind == "down":
+                ref = ob.conv1d_bwd(z, w, dyn, stride=2, padding=1)[0]
+            else:
+                ref = ob.convT1d_bwd(z, w, dyn)[0]
+            e = _rel(dx[n].float().cpu().permute(0, 2, 1), ref)
+            assert e <= tol, (kind, n, e)
+    return plan, check

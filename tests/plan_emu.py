@@ -311,9 +311,78 @@ def emu_siloss(plan, d: nv.SilossDesc):
     out[0], out[1], out[2], out[3] = lv + ls + lb, lv, ls, lb
 
 
+def emu_tcol(plan, d: nv.TcolDesc):
+    src = _flat(plan, d.src, TORCH_DT[d.src_dtype])
+    out = _flat(plan, d.out, torch.bfloat16)
+    K = d.B * d.t_out
+    k = torch.arange(K)
+    b, t = k // d.t_out, k % d.t_out
+    c = torch.arange(d.C)
+    for g in range(d.G):
+        for tap in range(d.taps):
+            pos = t * d.stride + d.tap_off[tap]
+            ok = (pos >= 0) & (pos < d.T_src)
+            idx = g * d.sG + b * d.sB + pos.clamp(0, d.T_src - 1) * d.ld                       # [K]
+            vals = src[(idx[None, :] + c[:, None]).reshape(-1)].reshape(d.C, K).float() * ok[None, :]
+            oidx = g * d.out_g + (tap * d.c_pad + c[:, None]) * d.k_ld + k[None, :]
+            out[oidx.reshape(-1)] = vals.reshape(-1).to(torch.bfloat16)
+
+
+def _mish_grad(y):
+    tsp = torch.tanh(F.softplus(y))
+    return tsp + y * (1 - tsp * tsp) * torch.sigmoid(y)
+
+
+def emu_gnbwd(plan, d: nv.GnbwdDesc):
+    G, B, T, C = d.G, d.B, d.T, d.C
+    raw = _flat(plan, d.raw, torch.float32)[: G * B * T * C].reshape(G, B, T, C)
+    doutf = _flat(plan, d.dout, torch.float32)
+    draw = _flat(plan, d.draw, torch.bfloat16)
+    cc = torch.arange(C)
+    rows = torch.arange(B * T)
+    for g in range(G):
+        go = doutf[(g * d.dout_g + rows[:, None] * d.dout_ld + cc[None, :]).reshape(-1)].reshape(B, T, C)
+        gamma = _flat(plan, d.gamma, torch.float32)[g * d.p_ld: g * d.p_ld + C]
+        beta = _flat(plan, d.beta, torch.float32)[g * d.p_ld: g * d.p_ld + C]
+        r = raw[g].permute(0, 2, 1).reshape(B, d.groups, -1)                                 # [B, groups, Cg*T]
+        mean = r.mean(dim=-1, keepdim=True)
+        rstd = torch.rsqrt(r.var(dim=-1, unbiased=False, keepdim=True) + d.eps)
+        xh = ((r - mean) * rstd).reshape(B, C, T).permute(0, 2, 1)                           # [B, T, C]
+        y = xh * gamma + beta
+        m = F.mish(y)
+        dm = go
+        if d.film:
+            film = _flat(plan, d.film, torch.float32)
+            fidx = g * d.film_g + torch.arange(B)[:, None] * d.film_ld + d.film_off + cc[None, :]
+            scale = film[fidx.reshape(-1)].reshape(B, 1, C)
+            dm = go * scale
+            if d.dfilm:
+                df = _flat(plan, d.dfilm, torch.float32)
+                df[fidx.reshape(-1)] = (go * m).sum(dim=1).reshape(-1)
+                df[(fidx + C).reshape(-1)] = go.sum(dim=1).reshape(-1)
+        da = dm * _mish_grad(y)
+        dxh = (da * gamma).permute(0, 2, 1).reshape(B, d.groups, -1)
+        xg = xh.permute(0, 2, 1).reshape(B, d.groups, -1)
+        dr = rstd * (dxh - dxh.mean(dim=-1, keepdim=True) - xg * (dxh * xg).mean(dim=-1, keepdim=True))
+        dr = dr.reshape(B, C, T).permute(0, 2, 1)                                            # [B, T, C]
+        draw[g * B * T * C: (g + 1) * B * T * C] = dr.reshape(-1).to(torch.bfloat16)
+        for ptr_, val in ((d.dgamma, (da * xh).sum(dim=(0, 1))), (d.dbeta, da.sum(dim=(0, 1))), (d.dbias, dr.sum(dim=(0, 1)))):
+            if ptr_:
+                _flat(plan, ptr_, torch.float32)[g * d.p_ld: g * d.p_ld + C] = val
+
+
+def emu_colsum(plan, d: nv.ColsumDesc):
+    x = _flat(plan, d.x, torch.float32)
+    out = _flat(plan, d.out, torch.float32)
+    rows, cc = torch.arange(d.rows), torch.arange(d.C)
+    for g in range(d.G):
+        v = x[(g * d.x_g + rows[:, None] * d.ld + cc[None, :]).reshape(-1)].reshape(d.rows, d.C)
+        out[g * d.out_ld: g * d.out_ld + d.C] = v.sum(dim=0)
+
+
 _EMU = {nv.QsampleDesc: emu_qsample, nv.SilossDesc: emu_siloss, nv.GemmDesc: emu_gemm, nv.LnDesc: emu_layernorm, nv.AttnDesc: emu_attention, nv.ImgStatsDesc: emu_imgstats,
         nv.PatchifyDesc: emu_patchify, nv.ClsDesc: emu_cls, nv.PackDesc: emu_pack, nv.AffineDesc: emu_affine,
-        nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm, nv.MlpDesc: emu_mlp}
+        nv.TcolDesc: emu_tcol, nv.GnbwdDesc: emu_gnbwd, nv.ColsumDesc: emu_colsum, nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm, nv.MlpDesc: emu_mlp}
 
 
 @torch.no_grad()

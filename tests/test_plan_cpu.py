@@ -58,7 +58,8 @@ def test_ctypes_structs_match_the_c_header():
              "vt_pack_desc": nv.PackDesc, "vt_affine_desc": nv.AffineDesc, "vt_tembed_desc": nv.TembedDesc,
              "vt_sde_desc": nv.SdeDesc, "vt_lstm_desc": nv.LstmDesc, "vt_qsample_desc": nv.QsampleDesc,
              "vt_siloss_desc": nv.SilossDesc, "vt_opt_tensor": nv.OptTensor, "vt_adamw_desc": nv.AdamwDesc,
-             "vt_mlp_desc": nv.MlpDesc}
+             "vt_mlp_desc": nv.MlpDesc, "vt_tcol_desc": nv.TcolDesc, "vt_gnbwd_desc": nv.GnbwdDesc,
+             "vt_colsum_desc": nv.ColsumDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/vt_b200.h"', 'int main(void){']
     probes = []
     for cname, cls in descs.items():
@@ -300,3 +301,26 @@ def test_dgrad_descriptors_reproduce_the_explicit_backward():
     run("k5", 16, 16, [torch.randn(C, C, 5, generator=g) / (5 * C) ** 0.5 for _ in range(G)])
     run("down", 8, 16, [torch.randn(C, C, 3, generator=g) / (3 * C) ** 0.5 for _ in range(G)])
     run("up", 32, 16, [torch.randn(C, C, 4, generator=g) / (2 * C) ** 0.5 for _ in range(G)])
+
+
+@pytest.mark.parametrize("kind", ["k5", "down", "up", "k1in"])
+def test_wgrad_descriptors_reproduce_the_explicit_backward(kind):
+    """unet_bwd.conv_wgrad: weight gradients as tcol (transposed im2col) + one plain GEMM descriptor, interpreted on the CPU,
+    against conv1d_bwd / convT1d_bwd of oracle/vt_oracle_bwd.py."""
+    import bwd_cases
+    plan, check = bwd_cases.wgrad_case(kind, torch.device("cpu"))
+    plan_emu.run(plan)
+    check()
+
+
+@pytest.mark.parametrize("film", [False, True])
+def test_conv_block_backward_plan_reproduces_the_explicit_backward(film):
+    """unet_bwd.conv_block_backward (recomputed raw conv -> GroupNorm+Mish(+FiLM) backward -> wgrad -> dgrad) interpreted on the
+    CPU against gn_mish_bwd + conv1d_bwd (+ the FiLM reductions of _res_block_bwd) of the oracle."""
+    import bwd_cases
+    plan, check = bwd_cases.block_case(torch.device("cpu"), film)
+    plan_emu.run(plan)
+    check()
+    plan, check = bwd_cases.colsum_case(torch.device("cpu"))
+    plan_emu.run(plan)
+    check()

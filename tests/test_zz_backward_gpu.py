@@ -1,0 +1,54 @@
+"""GPU parity of the backward building blocks (row a10 of SURVEY 8, first slice): the dgrad / wgrad plans of unet_bwd.py and
+the GroupNorm + Mish (+ FiLM) backward kernel run through the C ABI on the B200 and are held to oracle/vt_oracle_bwd.py
+(which is pinned to autograd and to the reference's own loss.backward() digests).  bf16 operands, fp32 accumulation: the
+gate is 2e-2 of the gradient's scale per tensor (north_star: 5e-2 relative on bf16).  Named test_zz_* so that it runs last."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import bwd_cases  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+
+
+def _run(plan):
+    plan.compile().run()
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("kind", ["k5", "down", "up", "k1in"])
+def test_wgrad_on_the_tensor_cores(kind):
+    plan, check = bwd_cases.wgrad_case(kind, DEV)
+    _run(plan)
+    check()
+
+
+@pytest.mark.parametrize("film", [False, True])
+def test_conv_block_backward(film):
+    plan, check = bwd_cases.block_case(DEV, film)
+    _run(plan)
+    check()
+
+
+def test_conv_block_backward_wide_and_long():
+    """512 channels (two channels per thread in gn_mish_bwd_kernel, 64-channel groups) and T = 64 (the BASELINE horizon)."""
+    plan, check = bwd_cases.block_case(DEV, True, G=3, B=4, T=64, Ci=256, Co=512, seed=6)
+    _run(plan)
+    check()
+
+
+def test_colsum():
+    plan, check = bwd_cases.colsum_case(DEV)
+    _run(plan)
+    check()
+
+
+@pytest.mark.parametrize("kind", ["k5", "down", "up"])
+def test_dgrad_on_the_tensor_cores(kind):
+    plan, check = bwd_cases.dgrad_case(kind, DEV)
+    _run(plan)
+    check()

@@ -1,0 +1,236 @@
+// Backward-pass kernels of the interpolant U-Net's Conv1dBlock (conditional_unet_1D.py:40-55, 86-105):
+//   tcol_kernel        transposed (im2col-T) operand copies for the weight-gradient GEMMs (K = B*T rows)
+//   gn_mish_bwd_kernel GroupNorm(8) + Mish (+ FiLM) backward from the raw conv output, one CTA per (net, sample)
+//   colsum_kernel      per-channel parameter gradients = sum over samples of the per-sample partials
+// CUDA-core kernels: HBM / L2 bound elementwise + reduction work (the contractions run on gemm_tc_kernel).
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "vt_ptx.cuh"
+
+namespace vt {
+
+struct TcolArgs {
+  const void* src;
+  int src_dtype;                 // 0 bf16, 1 f32
+  long long ld, sB, sG;
+  int G, B, T_src, C;
+  int taps;
+  int tap_off[8];
+  int stride, t_out;
+  __nv_bfloat16* out;
+  int c_pad;
+  long long k_ld, out_g;
+};
+
+// out[g][tap * c_pad + c][b * t_out + t] = src[g][b][t * stride + tap_off[tap]][c]  (zero outside [0, T_src)).
+// 32 x 32 tiles through shared memory: reads coalesced along channels, writes coalesced along the K index.
+// grid = (ceil(B * t_out / 32), ceil(C / 32), G * taps), block = (32, 8).
+__global__ void __launch_bounds__(256) tcol_kernel(const TcolArgs a) {
+  __shared__ float tile[32][33];
+  const int g = blockIdx.z / a.taps, tap = blockIdx.z % a.taps;
+  const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int K = a.B * a.t_out;
+  const int off = a.tap_off[tap];
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int k = k0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (k < K && c < a.C) {
+      const int b = k / a.t_out, t = k % a.t_out;
+      const int pos = t * a.stride + off;
+      if (pos >= 0 && pos < a.T_src) {
+        const long long idx = (long long)g * a.sG + (long long)b * a.sB + (long long)pos * a.ld + c;
+        v = a.src_dtype == 0 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.src)[idx])
+                             : reinterpret_cast<const float*>(a.src)[idx];
+      }
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, k = k0 + threadIdx.x;
+    if (c < a.C && k < K)
+      a.out[(long long)g * a.out_g + ((long long)tap * a.c_pad + c) * a.k_ld + k] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+
+// d mish(x) / dx and mish(x) from one exponential: tanh(softplus(x)) = n / (n + 2), n = e (e + 2), e = exp(x)
+__device__ __forceinline__ void mish_and_grad(float x, float& m, float& dm) {
+  const float e = expf(fminf(x, 20.f));
+  const float n = e * (e + 2.f);
+  const float tsp = n / (n + 2.f);
+  const float sig = e / (1.f + e);
+  m = x * tsp;
+  dm = tsp + x * (1.f - tsp * tsp) * sig;
+}
+
+struct GnBwdArgs {
+  const float* raw;      // [G][B][T][C]
+  const float* dout;     // [G][B][T][dout_ld]
+  long long dout_ld, dout_g;
+  const float* gamma;    // [G][p_ld]
+  const float* beta;
+  int p_ld;
+  const float* film;     // [G][B][film_ld] or null: scale at film_off + c
+  long long film_g;
+  int film_ld, film_off;
+  float* dfilm;          // [G][B][film_ld]: d scale at film_off + c, d shift at film_off + C + c
+  __nv_bfloat16* draw;   // [G][B][T][C]
+  float* part;           // [G][B][3][C]: per-sample (d gamma, d beta, d bias)
+  int G, B, T, C, groups;
+  float eps;
+};
+
+constexpr int GNB_MAX_CPT = 2;   // channels per thread: C <= 512 with 256 threads
+
+// One CTA (256 threads) per (net g, sample b).  Thread owns channels tid, tid + 256; loops over the T positions, so global
+// accesses are coalesced along channels.  Four sweeps over the sample's raw tile (<= 128 KB: L1 / L2 resident):
+//   1 mean  2 variance (two-pass, like torch)  3 per-channel gradient sums  4 d raw
+__global__ void __launch_bounds__(256) gn_mish_bwd_kernel(const GnBwdArgs a) {
+  __shared__ float s_ch[2][512];
+  __shared__ float s_mean[64], s_rstd[64], s_m1[64], s_m2[64];
+  const int g = blockIdx.x / a.B, b = blockIdx.x % a.B;
+  const int tid = threadIdx.x;
+  const int C = a.C, T = a.T, Cg = C / a.groups;
+  const long long sample = ((long long)g * a.B + b) * T;
+  const float* raw = a.raw + sample * C;
+  const float* dout = a.dout + (long long)g * a.dout_g + (long long)b * T * a.dout_ld;
+  const float inv_n = 1.f / (float)(Cg * T);
+
+  // sweep 1: per-channel sums -> group means
+  for (int j = 0; j < GNB_MAX_CPT; ++j) {
+    const int c = tid + j * 256;
+    if (c < C) {
+      float s = 0.f;
+      for (int t = 0; t < T; ++t) s += raw[(long long)t * C + c];
+      s_ch[0][c] = s;
+    }
+  }
+  __syncthreads();
+  if (tid < a.groups) {
+    float s = 0.f;
+    for (int i = 0; i < Cg; ++i) s += s_ch[0][tid * Cg + i];
+    s_mean[tid] = s * inv_n;
+  }
+  __syncthreads();
+  // sweep 2: centred second moment -> rstd
+  for (int j = 0; j < GNB_MAX_CPT; ++j) {
+    const int c = tid + j * 256;
+    if (c < C) {
+      const float mu = s_mean[c / Cg];
+      float s = 0.f;
+      for (int t = 0; t < T; ++t) {
+        const float d = raw[(long long)t * C + c] - mu;
+        s += d * d;
+      }
+      s_ch[1][c] = s;
+    }
+  }
+  __syncthreads();
+  if (tid < a.groups) {
+    float s = 0.f;
+    for (int i = 0; i < Cg; ++i) s += s_ch[1][tid * Cg + i];
+    s_rstd[tid] = rsqrtf(s * inv_n + a.eps);
+  }
+  __syncthreads();
+  // sweep 3: da = dm * mish'(y);  per-channel sums of da, da * xh (and the FiLM gradients)
+  float gam[GNB_MAX_CPT], bet[GNB_MAX_CPT], scl[GNB_MAX_CPT], s_da[GNB_MAX_CPT], s_dax[GNB_MAX_CPT];
+  for (int j = 0; j < GNB_MAX_CPT; ++j) {
+    const int c = tid + j * 256;
+    gam[j] = bet[j] = 0.f;
+    scl[j] = 1.f;
+    s_da[j] = s_dax[j] = 0.f;
+    if (c < C) {
+      gam[j] = a.gamma[(long long)g * a.p_ld + c];
+      bet[j] = a.beta[(long long)g * a.p_ld + c];
+      const float mu = s_mean[c / Cg], rs = s_rstd[c / Cg];
+      if (a.film) scl[j] = a.film[(long long)g * a.film_g + (long long)b * a.film_ld + a.film_off + c];
+      float f_sc = 0.f, f_sh = 0.f;
+      for (int t = 0; t < T; ++t) {
+        const float xh = (raw[(long long)t * C + c] - mu) * rs;
+        const float go = dout[(long long)t * a.dout_ld + c];
+        float m, dm;
+        mish_and_grad(xh * gam[j] + bet[j], m, dm);
+        const float da = go * scl[j] * dm;
+        s_da[j] += da;
+        s_dax[j] += da * xh;
+        f_sc += go * m;
+        f_sh += go;
+      }
+      if (a.dfilm) {
+        float* df = a.dfilm + (long long)g * a.film_g + (long long)b * a.film_ld + a.film_off;
+        df[c] = f_sc;
+        df[C + c] = f_sh;
+      }
+      s_ch[0][c] = gam[j] * s_da[j];
+      s_ch[1][c] = gam[j] * s_dax[j];
+    }
+  }
+  __syncthreads();
+  if (tid < a.groups) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = 0; i < Cg; ++i) {
+      s1 += s_ch[0][tid * Cg + i];
+      s2 += s_ch[1][tid * Cg + i];
+    }
+    s_m1[tid] = s1 * inv_n;
+    s_m2[tid] = s2 * inv_n;
+  }
+  __syncthreads();
+  // sweep 4: d raw = rstd * (da * gamma - mean_g(dxh) - xh * mean_g(dxh * xh));  d bias = sum_t d raw
+  for (int j = 0; j < GNB_MAX_CPT; ++j) {
+    const int c = tid + j * 256;
+    if (c < C) {
+      const int gi = c / Cg;
+      const float mu = s_mean[gi], rs = s_rstd[gi], m1 = s_m1[gi], m2 = s_m2[gi];
+      float s_dr = 0.f;
+      for (int t = 0; t < T; ++t) {
+        const float xh = (raw[(long long)t * C + c] - mu) * rs;
+        const float go = dout[(long long)t * a.dout_ld + c];
+        float m, dm;
+        mish_and_grad(xh * gam[j] + bet[j], m, dm);
+        const float dr = rs * (go * scl[j] * dm * gam[j] - m1 - xh * m2);
+        s_dr += dr;
+        a.draw[(sample + t) * C + c] = __float2bfloat16(dr);
+      }
+      float* p = a.part + ((long long)g * a.B + b) * 3 * C;
+      p[c] = s_dax[j];
+      p[C + c] = s_da[j];
+      p[2 * C + c] = s_dr;
+    }
+  }
+}
+
+// out_k[g][c] = sum_b part[g][b][k][c], k = 0..2 -> (d gamma, d beta, d bias), each [G][p_ld]
+__global__ void __launch_bounds__(256) gn_colsum_kernel(const float* __restrict__ part, int G, int B, int C, float* dgamma,
+                                                        float* dbeta, float* dbias, int p_ld) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= G * 3 * C) return;
+  const int c = idx % C, k = (idx / C) % 3, g = idx / (3 * C);
+  const float* p = part + (long long)g * B * 3 * C + (long long)k * C + c;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += p[(long long)b * 3 * C];
+  float* o = k == 0 ? dgamma : (k == 1 ? dbeta : dbias);
+  if (o) o[(long long)g * p_ld + c] = s;
+}
+
+// out[g][c] = sum_r x[g][r][c] : bias gradient of a convolution without GroupNorm (conv1d_bwd's `dy.sum(dim=(0, 2))`).
+// grid = (ceil(C / 32), G), block = (32, 8)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long ld, long long x_g, int rows, int C,
+                                                     float* __restrict__ out, int out_ld) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, g = blockIdx.y;
+  float s = 0.f;
+  if (c < C)
+    for (int r = threadIdx.y; r < rows; r += 8) s += x[(long long)g * x_g + (long long)r * ld + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    out[(long long)g * out_ld + c] = t;
+  }
+}
+
+}  // namespace vt

@@ -16,6 +16,7 @@
 #include "vt_elem.cuh"
 #include "vt_gemm.cuh"
 #include "vt_lstm.cuh"
+#include "vt_bwd.cuh"
 
 namespace {
 
@@ -619,6 +620,52 @@ struct SilossOp : Op {
   }
 };
 
+struct TcolOp : Op {
+  vt_tcol_desc d;
+  int launch(cudaStream_t s) override {
+    vt::TcolArgs a;
+    a.src = d.src; a.src_dtype = d.src_dtype == VT_BF16 ? 0 : 1;
+    a.ld = d.ld; a.sB = d.sB; a.sG = d.sG;
+    a.G = d.G; a.B = d.B; a.T_src = d.T_src; a.C = d.C; a.taps = d.taps;
+    for (int i = 0; i < 8; ++i) a.tap_off[i] = i < d.taps ? d.tap_off[i] : 0;
+    a.stride = d.stride; a.t_out = d.t_out;
+    a.out = reinterpret_cast<__nv_bfloat16*>(d.out);
+    a.c_pad = d.c_pad; a.k_ld = d.k_ld; a.out_g = d.out_g;
+    const dim3 grid((unsigned)((d.B * d.t_out + 31) / 32), (unsigned)((d.C + 31) / 32), (unsigned)(d.G * d.taps));
+    vt::tcol_kernel<<<grid, dim3(32, 8, 1), 0, s>>>(a);
+    VT_LAUNCH_CHECK("tcol_kernel");
+    return VT_OK;
+  }
+};
+
+struct GnbwdOp : Op {
+  vt_gnbwd_desc d;
+  int launches() const override { return 2; }
+  int launch(cudaStream_t s) override {
+    vt::GnBwdArgs a;
+    a.raw = d.raw; a.dout = d.dout; a.dout_ld = d.dout_ld; a.dout_g = d.dout_g;
+    a.gamma = d.gamma; a.beta = d.beta; a.p_ld = d.p_ld;
+    a.film = d.film; a.film_g = d.film_g; a.film_ld = d.film_ld; a.film_off = d.film_off; a.dfilm = d.dfilm;
+    a.draw = reinterpret_cast<__nv_bfloat16*>(d.draw); a.part = d.part;
+    a.G = d.G; a.B = d.B; a.T = d.T; a.C = d.C; a.groups = d.groups; a.eps = d.eps;
+    vt::gn_mish_bwd_kernel<<<d.G * d.B, 256, 0, s>>>(a);
+    VT_LAUNCH_CHECK("gn_mish_bwd_kernel");
+    vt::gn_colsum_kernel<<<(d.G * 3 * d.C + 255) / 256, 256, 0, s>>>(d.part, d.G, d.B, d.C, d.dgamma, d.dbeta, d.dbias, d.p_ld);
+    VT_LAUNCH_CHECK("gn_colsum_kernel");
+    return VT_OK;
+  }
+};
+
+struct ColsumOp : Op {
+  vt_colsum_desc d;
+  int launch(cudaStream_t s) override {
+    vt::colsum_kernel<<<dim3((unsigned)((d.C + 31) / 32), (unsigned)d.G, 1), dim3(32, 8, 1), 0, s>>>(d.x, d.ld, d.x_g, d.rows, d.C,
+                                                                                                  d.out, d.out_ld);
+    VT_LAUNCH_CHECK("colsum_kernel");
+    return VT_OK;
+  }
+};
+
 struct LstmOp : Op {
   vt_lstm_desc d;
   int launch(cudaStream_t s) override {
@@ -870,6 +917,21 @@ VT_SIMPLE_ADD(vt_program_add_sde, SdeOp, vt_sde_desc,
               VT_REQUIRE(d->x && d->v && d->s && d->rows >= 1 && d->A >= 1, "sde: bad descriptor"))
 VT_SIMPLE_ADD(vt_program_add_lstm, LstmOp, vt_lstm_desc,
               VT_REQUIRE(d->xw && d->w_hh && d->h && d->c && d->y && d->B >= 1 && d->T >= 1 && d->H == 256, "lstm: bad descriptor"))
+
+VT_SIMPLE_ADD(vt_program_add_tcol, TcolOp, vt_tcol_desc,
+              VT_REQUIRE(d->src && d->out && (d->src_dtype == VT_BF16 || d->src_dtype == VT_F32) && d->G >= 1 && d->B >= 1 &&
+                             d->T_src >= 1 && d->C >= 1 && d->taps >= 1 && d->taps <= VT_MAX_TAPS && d->stride >= 1 &&
+                             d->t_out >= 1 && d->c_pad >= d->C && d->k_ld >= (int64_t)d->B * d->t_out && d->k_ld % 64 == 0 &&
+                             (int64_t)d->G * d->taps <= 65535,
+                         "tcol: bad descriptor"))
+VT_SIMPLE_ADD(vt_program_add_gnbwd, GnbwdOp, vt_gnbwd_desc,
+              VT_REQUIRE(d->raw && d->dout && d->gamma && d->beta && d->draw && d->part && d->G >= 1 && d->B >= 1 && d->T >= 1 &&
+                             d->C >= 1 && d->C <= 256 * vt::GNB_MAX_CPT && d->groups >= 1 && d->groups <= 64 &&
+                             d->C % d->groups == 0 && d->dout_ld >= d->C && (!d->dfilm || d->film),
+                         "gnbwd: bad descriptor (C=%d groups=%d)", d->C, d->groups))
+VT_SIMPLE_ADD(vt_program_add_colsum, ColsumOp, vt_colsum_desc,
+              VT_REQUIRE(d->x && d->out && d->G >= 1 && d->G <= 65535 && d->rows >= 1 && d->C >= 1 && d->ld >= d->C,
+                         "colsum: bad descriptor"))
 
 VT_SIMPLE_ADD(vt_program_add_qsample, QsampleOp, vt_qsample_desc,
               VT_REQUIRE(d->x0 && d->x1 && d->step && d->z_unit && d->xt && d->tclip && d->B >= 1 && d->n >= 1 && d->A >= 1 &&

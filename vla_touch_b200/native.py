@@ -104,6 +104,23 @@ class SilossDesc(C.Structure):
                 ("per_sample", vp), ("out", vp)]
 
 
+class TcolDesc(C.Structure):
+    _fields_ = [("src", vp), ("src_dtype", i32), ("ld", i64), ("sB", i64), ("sG", i64), ("G", i32), ("B", i32), ("T_src", i32),
+                ("C", i32), ("taps", i32), ("tap_off", i32 * 8), ("stride", i32), ("t_out", i32), ("out", vp), ("c_pad", i32),
+                ("k_ld", i64), ("out_g", i64)]
+
+
+class GnbwdDesc(C.Structure):
+    _fields_ = [("raw", vp), ("dout", vp), ("dout_ld", i64), ("dout_g", i64), ("gamma", vp), ("beta", vp), ("p_ld", i32),
+                ("film", vp), ("dfilm", vp), ("film_g", i64), ("film_ld", i32), ("film_off", i32), ("draw", vp), ("part", vp),
+                ("dgamma", vp), ("dbeta", vp), ("dbias", vp), ("G", i32), ("B", i32), ("T", i32), ("C", i32), ("groups", i32),
+                ("eps", f32)]
+
+
+class ColsumDesc(C.Structure):
+    _fields_ = [("x", vp), ("ld", i64), ("x_g", i64), ("G", i32), ("rows", i32), ("C", i32), ("out", vp), ("out_ld", i32)]
+
+
 class OptTensor(C.Structure):
     _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("ema", vp), ("numel", i64)]
 
@@ -119,7 +136,7 @@ EXPORTS = [
     "vt_program_num_ops", "vt_program_num_launches", "vt_program_add_gemm", "vt_program_add_layernorm",
     "vt_program_add_attention", "vt_program_add_mlp", "vt_debug_timestamps", "vt_program_add_imgstats", "vt_program_add_patchify", "vt_program_add_cls",
     "vt_program_add_pack", "vt_program_add_affine", "vt_program_add_tembed", "vt_program_add_sde",
-    "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
+    "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_add_tcol", "vt_program_add_gnbwd", "vt_program_add_colsum", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
     "vt_pos_embed_resize", "vt_adamw_ema_step",
 ]
 
@@ -128,7 +145,8 @@ _ADD = {
     ImgStatsDesc: "vt_program_add_imgstats", PatchifyDesc: "vt_program_add_patchify", ClsDesc: "vt_program_add_cls",
     PackDesc: "vt_program_add_pack", AffineDesc: "vt_program_add_affine", TembedDesc: "vt_program_add_tembed",
     SdeDesc: "vt_program_add_sde", LstmDesc: "vt_program_add_lstm", QsampleDesc: "vt_program_add_qsample",
-    SilossDesc: "vt_program_add_siloss",
+    SilossDesc: "vt_program_add_siloss", TcolDesc: "vt_program_add_tcol", GnbwdDesc: "vt_program_add_gnbwd",
+    ColsumDesc: "vt_program_add_colsum",
 }
 
 _lib: Optional[C.CDLL] = None

@@ -1,5 +1,6 @@
-"""Backward of the interpolant U-Net, part 1: the DATA gradients (dgrad) of every convolution as implicit GEMMs that run on
-the forward kernel unchanged (`gemm_tc_kernel`, LINEAR epilogue) -- only the tap tables and the weight packing differ.
+"""Backward of the interpolant U-Net's convolution blocks (row a10 of SURVEY 8: get_loss().backward()).
+
+Part 1: the DATA gradients (dgrad) of every convolution as implicit GEMMs that run on the forward kernel unchanged (`gemm_tc_kernel`, LINEAR epilogue) -- only the tap tables and the weight packing differ.
 
     Conv1d(k, s=1, p)            dX[u]    = sum_k W_k^T dY[u + p - k]                 one GEMM, taps shifted by (p - k)
     Conv1d(k3, s=2, p=1)         dX[2v]   = W_1^T dY[v]                               one GEMM per output phase, rows interleaved
@@ -7,10 +8,15 @@ the forward kernel unchanged (`gemm_tc_kernel`, LINEAR epilogue) -- only the tap
     ConvTranspose1d(k4, s2, p1)  dX[t]    = sum_k W_k dY[2t + k - 1]                  a stride-2 conv over dY: even / odd phase taps
     (Upsample1d :31-37)
 
-(conditional_unet_1D.py:22-55).  W_k is the [C_out, C_in] slice of tap k (ConvTranspose: [C_in, C_out]).  The weight
-gradients (wgrad: K = rows, MN-major operands), the fused GroupNorm+Mish+FiLM backward and the training-mode forward that keeps
-the raw conv outputs are the round-2 kernels; `oracle/vt_oracle_bwd.py` is the checker all of them are held to.  These plan
-builders are host logic: verified on the CPU by interpreting the descriptors (tests/test_plan_cpu.py) against that oracle.
+(conditional_unet_1D.py:22-55).  W_k is the [C_out, C_in] slice of tap k (ConvTranspose: [C_in, C_out]).
+
+Part 2: the WEIGHT gradients as plain row-major GEMMs on the same kernel (K = B*T positions) over K-major operand copies made
+by `tcol_kernel` (transposed im2col), the fused GroupNorm + Mish (+ FiLM) backward `gn_mish_bwd_kernel` working from the raw
+conv output (which is recomputed with the LINEAR epilogue instead of being saved by the forward pass), bias gradients as
+column sums, and `conv_block_backward`, the backward of one whole Conv1dBlock.  Assembling the 12 residual blocks, the FiLM /
+time-MLP linears and the loss derivatives into the full get_loss backward is the next step; `oracle/vt_oracle_bwd.py` is the
+checker all of it is held to.  The plan builders are host logic: verified on the CPU by interpreting the descriptors
+(tests/test_plan_cpu.py) against that oracle; tests/test_zz_backward_gpu.py runs the same plans on the B200.
 """
 from __future__ import annotations
 
@@ -18,7 +24,9 @@ from typing import List, Sequence
 
 import torch
 
-from .unet import Mode, _View, _conv, _pack_conv
+from . import native as nv
+from .plan import VT_DT, linear_desc, ptr, round_up
+from .unet import N_GROUPS, Mode, _View, _conv, _pack_conv, _pack_vec
 
 
 class DgradCtx:
@@ -77,3 +85,102 @@ def upsample_dgrad(plan, ctx: DgradCtx, B: int, dy: _View, dx: _View, ws: Sequen
     _conv(plan, ctx, B, dy, dx, wd, zb, taps=[(1, -1), (0, 0), (1, 0), (0, 1)], cin_pad=dy.C, n=ci, t_out=dx.T, phases=2,
           tag=tag or "upsample.dgrad")
     return [wd, zb]
+
+
+# ------------------------------------------------------------------------------------------------
+# part 2: weight gradients and the fused GroupNorm + Mish (+ FiLM) backward
+# ------------------------------------------------------------------------------------------------
+def _tcol(src: _View, B: int, G: int, out: torch.Tensor, *, tap_off: Sequence[int], stride: int, t_out: int, c_pad: int) -> nv.TcolDesc:
+    d = nv.TcolDesc()
+    d.src, d.src_dtype = ptr(src.t, src.c0), VT_DT[src.t.dtype]
+    d.ld, d.sB, d.sG = src.ld, src.T * src.ld, 0 if src.shared else B * src.T * src.ld
+    d.G, d.B, d.T_src, d.C, d.taps = G, B, src.T, src.C, len(tap_off)
+    for i, o in enumerate(tap_off):
+        d.tap_off[i] = o
+    d.stride, d.t_out, d.out, d.c_pad = stride, t_out, ptr(out), c_pad
+    d.k_ld, d.out_g = out.shape[-1], out.shape[1] * out.shape[2]
+    return d
+
+
+def conv_wgrad(plan, ctx: DgradCtx, B: int, rows_src: _View, cols_src: _View, *, tap_off: Sequence[int], stride: int = 1,
+               t_out: int, tag: str = "conv.wgrad") -> torch.Tensor:
+    """Weight gradient of a convolution as ONE plain row-major GEMM on the forward kernel (K = B * t_out positions):
+
+        dW[g][r][tap * c_pad + c] = sum_{b, t < t_out} rows_src[g][b][t][r] * cols_src[g][b][t * stride + tap_off[tap]][c]
+
+    Conv1d(k, s, p):         rows_src = dY (one tap, offset 0), cols_src = X  (tap_off[k] = k - p, stride s)  -> [C_out][k][C_in]
+    ConvTranspose1d(4,2,1):  rows_src = X,                      cols_src = dY (tap_off[k] = k - 1, stride 2)  -> [C_in][k][C_out]
+    (conv1d_bwd / convT1d_bwd of oracle/vt_oracle_bwd.py; conditional_unet_1D.py:22-55).  Both operands are first copied
+    into K-major (transposed) bf16 buffers by tcol_kernel.  Returns dW fp32 [G][rows][taps * c_pad]: the forward packing of
+    the weight (`_pack_conv`), so `unpack_wgrad` is a view."""
+    G = ctx.G
+    assert not ctx.mode.precise, "training runs in the bf16 mode"
+    kp = round_up(B * t_out, 64)
+    R, c_pad, taps = rows_src.C, cols_src.C, len(tap_off)
+    n = taps * c_pad
+    bn = 256 if n % 256 == 0 else 128
+    n_pad = round_up(n, bn)
+    nm = tag + f"#{len(plan)}"
+    rT = plan.buf(nm + ".rowsT", (G, round_up(R, 128), kp), torch.bfloat16)
+    cT = plan.buf(nm + ".colsT", (G, n_pad, kp), torch.bfloat16)
+    dw = plan.buf(nm + ".dw", (G, R, n), torch.float32)
+    plan.add(_tcol(rows_src, B, G, rT, tap_off=[0], stride=1, t_out=t_out, c_pad=R), tag + ".rowsT")
+    plan.add(_tcol(cols_src, B, G, cT, tap_off=list(tap_off), stride=stride, t_out=t_out, c_pad=c_pad), tag + ".colsT")
+    plan.add(linear_desc(a=rT, rows=R, k=kp, a_ld=kp, w=cT, n=n, n_pad=n_pad, w_ld=kp, out=dw, ldc=n, G=G, a_G=G,
+                         a_sG=rT.shape[1] * kp, out_g=R * n, bn=bn), tag + ".gemm")
+    return dw
+
+
+def unpack_wgrad(dw: torch.Tensor, c_valid: int, taps: int) -> torch.Tensor:
+    """[G][R][taps * c_pad] -> the nn.Module layout: Conv1d [G][C_out][C_in][k]; ConvTranspose1d [G][C_in][C_out][k]
+    (both are [rows][channels][k] in the respective layer's own weight order)."""
+    G, R, n = dw.shape
+    return dw.view(G, R, taps, n // taps)[:, :, :, :c_valid].permute(0, 1, 3, 2)
+
+
+def gn_mish_backward(plan, ctx: DgradCtx, B: int, T: int, C: int, raw: torch.Tensor, dout: torch.Tensor, gamma: torch.Tensor,
+                     beta: torch.Tensor, *, film=None, tag: str = "gn.bwd"):
+    """GroupNorm(8) + Mish (+ FiLM) backward of one Conv1dBlock for G nets (gn_mish_bwd + the FiLM lines of _res_block_bwd in
+    oracle/vt_oracle_bwd.py).  raw / dout fp32 [G][B][T][C]; gamma / beta fp32 [G][C];
+    film = (film table [G][B][ld], d film table [G][B][ld], column offset) or None.
+    Returns (draw bf16 [G][B][T][C], dgamma, dbeta, dbias fp32 [G][C])."""
+    G = ctx.G
+    nm = tag + f"#{len(plan)}"
+    draw = plan.buf(nm + ".draw", (G, B, T, C), torch.bfloat16)
+    part = plan.buf(nm + ".part", (G, B, 3, C), torch.float32)
+    dg, db, dbias = (plan.buf(nm + "." + k, (G, C), torch.float32) for k in ("dgamma", "dbeta", "dbias"))
+    d = nv.GnbwdDesc()
+    d.raw, d.dout, d.dout_ld, d.dout_g = ptr(raw), ptr(dout), dout.shape[-1], B * T * dout.shape[-1]
+    d.gamma, d.beta, d.p_ld = ptr(gamma), ptr(beta), gamma.shape[-1]
+    if film is not None:
+        ft, dft, off = film
+        d.film, d.dfilm, d.film_g, d.film_ld, d.film_off = ptr(ft), ptr(dft), B * ft.shape[-1], ft.shape[-1], off
+    d.draw, d.part, d.dgamma, d.dbeta, d.dbias = ptr(draw), ptr(part), ptr(dg), ptr(db), ptr(dbias)
+    d.G, d.B, d.T, d.C, d.groups, d.eps = G, B, T, C, N_GROUPS, 1e-5
+    plan.add(d, tag)
+    return draw, dg, db, dbias
+
+
+def conv_block_backward(plan, ctx: DgradCtx, B: int, x: _View, ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor],
+                        gammas: Sequence[torch.Tensor], betas: Sequence[torch.Tensor], dout: torch.Tensor, dx: _View, *,
+                        film=None, tag: str = "block"):
+    """Backward of Conv1dBlock = Conv1d(k, padding k//2) -> GroupNorm(8) -> Mish [-> FiLM] (conditional_unet_1D.py:40-55,
+    97-102) for G nets: the raw conv output is RECOMPUTED with the forward kernel (LINEAR epilogue, fp32) instead of being
+    saved by the forward pass, then  gn_mish_backward -> conv_wgrad -> conv_dgrad.
+    x: bf16 [G][B][T][C_in] view (block input), dout fp32 [G][B][T][C_out], dx: bf16 view receiving d x.
+    Returns dict(dw [G][C_out][k * cin_pad], dbias, dgamma, dbeta [G][C_out])."""
+    co, ci, K = ws[0].shape
+    m, T = ctx.mode, x.T
+    dev = plan.device
+    wf = plan.reg(_pack_conv([w.to(dev) for w in ws], x.C, m))
+    bf = plan.reg(_pack_vec([b.to(dev) for b in bs], wf.shape[1]))
+    gm = plan.reg(_pack_vec([g.to(dev) for g in gammas], co))
+    bt = plan.reg(_pack_vec([b.to(dev) for b in betas], co))
+    raw = plan.buf(tag + f"#{len(plan)}.raw", (ctx.G, B, T, co), torch.float32)
+    _conv(plan, ctx, B, x, None, wf, bf, taps=[(0, k - K // 2) for k in range(K)], cin_pad=x.C, n=co, t_out=T, out_f32=raw,
+          tag=tag + ".conv_raw(recompute)")
+    draw, dg, db, dbias = gn_mish_backward(plan, ctx, B, T, co, raw, dout, gm, bt, film=film, tag=tag + ".gn+mish.bwd")
+    vy = _View(draw, T, co)
+    dw = conv_wgrad(plan, ctx, B, vy, x, tap_off=[k - K // 2 for k in range(K)], t_out=T, tag=tag + ".wgrad")
+    conv_dgrad(plan, ctx, B, vy, dx, [w.to(dev) for w in ws], pad=K // 2, tag=tag + ".dgrad")
+    return dict(dw=dw, dbias=dbias, dgamma=dg, dbeta=db, raw=raw, draw=draw)
