@@ -166,3 +166,75 @@ def dgrad_case(kind: str, device, G=2, B=3, C=256, seed=9):
             e = _rel(dx[n].float().cpu().permute(0, 2, 1), ref)
             assert e <= tol, (kind, n, e)
     return plan, check
+
+
+def res_block_case(device, Ci: int, Co: int, G=2, B=3, T=16, seed=21, need_dx=True):
+    """res_block_backward against _res_block_bwd of the oracle.  Ci != Co -> the block has a 1x1 residual_conv.
+    Ci == 7: the network's first block (64-channel padded input shared by all nets, no input gradient)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g)
+    p = "blk."
+    first = Ci == 7
+    sds = []
+    for _ in range(G):
+        sd = {p + "blocks.0.block.0.weight": bf(r(Co, Ci, 5) / (5 * Ci) ** 0.5), p + "blocks.0.block.0.bias": 0.1 * r(Co),
+              p + "blocks.0.block.1.weight": 1 + 0.2 * r(Co), p + "blocks.0.block.1.bias": 0.2 * r(Co),
+              p + "blocks.1.block.0.weight": bf(r(Co, Co, 5) / (5 * Co) ** 0.5), p + "blocks.1.block.0.bias": 0.1 * r(Co),
+              p + "blocks.1.block.1.weight": 1 + 0.2 * r(Co), p + "blocks.1.block.1.bias": 0.2 * r(Co),
+              p + "cond_encoder.1.weight": r(2 * Co, 512) / 512 ** 0.5, p + "cond_encoder.1.bias": 1 + 0.1 * r(2 * Co)}
+        if Ci != Co:
+            sd[p + "residual_conv.weight"] = bf(r(Co, Ci, 1) / Ci ** 0.5)
+            sd[p + "residual_conv.bias"] = 0.1 * r(Co)
+        sds.append(sd)
+    mgf = r(B, 512)
+    xs = bf(r(B, Ci, T)) if first else bf(r(G, B, Ci, T))                       # oracle layout [B, C, T]
+    douts = r(G, B, Co, T)
+    caches, embs = [], []
+    for n in range(G):
+        cache = {}
+        ob._res_block_fwd(sds[n], p, xs if first else xs[n], mgf, cache)
+        caches.append(cache)
+        embs.append(F.linear(mgf, sds[n][p + "cond_encoder.1.weight"], sds[n][p + "cond_encoder.1.bias"]))
+    plan = Plan(device)
+    ctx = ub.DgradCtx(G, precise=False)
+    Cx = 64 if first else Ci
+    if first:
+        x = plan.buf("x", (B, T, Cx), torch.bfloat16)
+        x[:, :, :Ci] = xs.permute(0, 2, 1).to(device)
+    else:
+        x = plan.buf("x", (G, B, T, Cx), torch.bfloat16)
+        x.copy_(xs.permute(0, 1, 3, 2))
+    y1 = plan.buf("y1", (G, B, T, Co), torch.bfloat16)
+    y1.copy_(torch.stack([c[p + "blocks.1."][0] for c in caches]).permute(0, 1, 3, 2))
+    dout = plan.buf("dout", (G, B, T, Co), torch.float32)
+    dout.copy_(douts.permute(0, 1, 3, 2))
+    ft = plan.buf("film", (G, B, 2 * Co), torch.float32)
+    ft.copy_(torch.stack(embs))
+    dft = plan.buf("dfilm", (G, B, 2 * Co), torch.float32)
+    dx = None if first or not need_dx else plan.buf("dx", (G, B, T, Cx), torch.float32)
+    out = ub.res_block_backward(plan, ctx, B, sds, p, _View(x, T, Cx, shared=first), _View(y1, T, Co), dout,
+                                None if dx is None else _View(dx, T, Cx), (ft, dft, 0))
+
+    def check(tol=2e-2):
+        errs = {}
+        for n in range(G):
+            grads = {}
+            dxr, dmgf = ob._res_block_bwd(sds[n], p, douts[n], mgf, caches[n], grads)
+            for k, v in out.items():
+                ref = grads[p + k]
+                if isinstance(v, tuple):
+                    got = ub.unpack_wgrad(v[0], ref.shape[1], v[1])[n].float().cpu()
+                else:
+                    got = v[n].float().cpu()
+                errs[k] = max(errs.get(k, 0.0), _rel(got, ref))
+            demb = dft[n].float().cpu()
+            errs["cond_encoder.1.bias"] = max(errs.get("cond_encoder.1.bias", 0.0), _rel(demb.sum(0), grads[p + "cond_encoder.1.bias"]))
+            errs["cond_encoder.1.weight"] = max(errs.get("cond_encoder.1.weight", 0.0),
+                                                _rel(demb.t() @ mgf, grads[p + "cond_encoder.1.weight"]))
+            if dx is not None:
+                errs["dx"] = max(errs.get("dx", 0.0), _rel(dx[n].float().cpu().permute(0, 2, 1), dxr))
+        bad = {k: v for k, v in errs.items() if not v <= tol}
+        assert not bad, (bad, errs)
+        return errs
+    return plan, check

@@ -324,3 +324,13 @@ def test_conv_block_backward_plan_reproduces_the_explicit_backward(film):
     plan, check = bwd_cases.colsum_case(torch.device("cpu"))
     plan_emu.run(plan)
     check()
+
+
+@pytest.mark.parametrize("ci,co", [(256, 256), (256, 512), (1024, 512), (7, 256)])
+def test_res_block_backward_plan_reproduces_the_explicit_backward(ci, co):
+    """unet_bwd.res_block_backward (ConditionalResidualBlock1D: both Conv1dBlocks, FiLM, identity / 1x1-conv residual, the
+    first block's shared padded input) interpreted on the CPU against _res_block_bwd of oracle/vt_oracle_bwd.py."""
+    import bwd_cases
+    plan, check = bwd_cases.res_block_case(torch.device("cpu"), ci, co)
+    plan_emu.run(plan)
+    check()

@@ -52,3 +52,12 @@ def test_dgrad_on_the_tensor_cores(kind):
     plan, check = bwd_cases.dgrad_case(kind, DEV)
     _run(plan)
     check()
+
+
+@pytest.mark.parametrize("ci,co", [(256, 256), (256, 512), (1024, 512), (7, 256)])
+def test_res_block_backward(ci, co):
+    """ConditionalResidualBlock1D backward (conditional_unet_1D.py:58-105): identity and 1x1-conv residual, concatenated
+    (1024-channel) input, the network's first block."""
+    plan, check = bwd_cases.res_block_case(DEV, ci, co)
+    _run(plan)
+    check()

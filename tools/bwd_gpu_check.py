@@ -20,6 +20,10 @@ cases += [("colsum", bwd_cases.colsum_case),
           ("block", lambda d: bwd_cases.block_case(d, False)),
           ("block.film", lambda d: bwd_cases.block_case(d, True)),
           ("block.film.512ch.T64", lambda d: bwd_cases.block_case(d, True, G=3, B=4, T=64, Ci=256, Co=512, seed=6))]
+cases += [(f"res_block.{ci}->{co}", lambda d, ci=ci, co=co: bwd_cases.res_block_case(d, ci, co))
+          for ci, co in ((256, 256), (256, 512), (1024, 512), (7, 256))]
+if len(sys.argv) > 1:
+    cases = [c for c in cases if any(a in c[0] for a in sys.argv[1:])]
 ok = True
 for name, fn in cases:
     t0 = time.time()

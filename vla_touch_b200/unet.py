@@ -232,8 +232,12 @@ def _conv(plan: Plan, W: UnetWeights, B: int, src: _View, dst: _View, w: torch.T
                   row_div=1, out_q=1, out_r=0, out_off=0)
     else:
         oq, orr, ooff, t_dst = out_rows if out_rows else (t_out, 1, 0, t_out)
-        kw.update(out=ptr(dst.t, dst.c0), out_dtype=m.dt, ldc=dst.ld, out_g=B * dst.T * dst.ld, row_div=t_out, out_q=oq,
-                  out_r=orr, out_off=ooff, out_plane=m.plane(dst.ctot))
+        f32_dst = dst.t.dtype == torch.float32 and not m.precise      # backward plans: fp32 gradient buffers in the bf16 mode
+        kw.update(out=ptr(dst.t, dst.c0), out_dtype=nv.VT_F32 if f32_dst else m.dt, ldc=dst.ld, out_g=B * dst.T * dst.ld,
+                  row_div=t_out, out_q=oq, out_r=orr, out_off=ooff, out_plane=0 if f32_dst else m.plane(dst.ctot))
+        if gn is None and res is not None:                             # LINEAR epilogue: fp32 rows added last (same row mapping)
+            assert res.t.dtype == torch.float32
+            kw.update(res=ptr(res.t, res.c0), ldres=res.ld, res_g=B * res.T * res.ld, res_q=oq, res_r=orr, res_off=ooff)
     if gn is not None:
         gamma, beta = gn
         kw.update(epi=nv.EPI_GN, gn_gamma=ptr(gamma), gn_beta=ptr(beta), gn_group_ch=n // N_GROUPS, gn_eps=1e-5)

@@ -20,7 +20,7 @@ checker all of it is held to.  The plan builders are host logic: verified on the
 """
 from __future__ import annotations
 
-from typing import List, Sequence
+from typing import List, Optional, Sequence
 
 import torch
 
@@ -48,19 +48,22 @@ def pack_dgrad_convT(ws: Sequence[torch.Tensor], taps_k: Sequence[int], cout_pad
     return _pack_conv([w[:, :, list(taps_k)] for w in ws], cout_pad, mode)
 
 
-def conv_dgrad(plan, ctx: DgradCtx, B: int, dy: _View, dx: _View, ws: Sequence[torch.Tensor], pad: int, tag: str = "") -> List[torch.Tensor]:
-    """dX of a stride-1 Conv1d(k, padding=pad).  dy: [G][B][T][C_out] view, dx: [G][B][T][C_in] view.  Returns the tensors the
-    plan must keep alive (packed weights, zero bias)."""
+def conv_dgrad(plan, ctx: DgradCtx, B: int, dy: _View, dx: _View, ws: Sequence[torch.Tensor], pad: int, tag: str = "",
+               res: Optional[_View] = None) -> List[torch.Tensor]:
+    """dX of a stride-1 Conv1d(k, padding=pad).  dy: [G][B][T][C_out] view, dx: [G][B][T][C_in] view (bf16, or fp32 when the
+    gradient feeds an elementwise backward); res: fp32 view added to the result (gradient fan-in: residual / skip paths).
+    Returns the tensors the plan must keep alive (packed weights, zero bias)."""
     co, ci, K = ws[0].shape
     m = ctx.mode
     wd = plan.reg(pack_dgrad_conv(ws, range(K), dy.C, m).to(plan.device))
     zb = plan.reg(torch.zeros(ctx.G, wd.shape[1], dtype=torch.float32, device=plan.device))
-    _conv(plan, ctx, B, dy, dx, wd, zb, taps=[(0, pad - k) for k in range(K)], cin_pad=dy.C, n=ci, t_out=dy.T,
+    _conv(plan, ctx, B, dy, dx, wd, zb, taps=[(0, pad - k) for k in range(K)], cin_pad=dy.C, n=ci, t_out=dy.T, res=res,
           tag=tag or "conv.dgrad")
     return [wd, zb]
 
 
-def downsample_dgrad(plan, ctx: DgradCtx, B: int, dy: _View, dx: _View, ws: Sequence[torch.Tensor], tag: str = "") -> List[torch.Tensor]:
+def downsample_dgrad(plan, ctx: DgradCtx, B: int, dy: _View, dx: _View, ws: Sequence[torch.Tensor], tag: str = "",
+                     res: Optional[_View] = None) -> List[torch.Tensor]:
     """dX of Conv1d(k3, stride 2, padding 1): dy has T/2 positions, dx T; one GEMM per parity of the dX position."""
     co, ci, K = ws[0].shape
     assert K == 3 and dx.T == 2 * dy.T
@@ -68,13 +71,14 @@ def downsample_dgrad(plan, ctx: DgradCtx, B: int, dy: _View, dx: _View, ws: Sequ
     for ph, taps_k, taps in ((0, (1,), [(0, 0)]), (1, (0, 2), [(0, 1), (0, 0)])):
         wd = plan.reg(pack_dgrad_conv(ws, taps_k, dy.C, m).to(plan.device))
         zb = plan.reg(torch.zeros(ctx.G, wd.shape[1], dtype=torch.float32, device=plan.device))
-        _conv(plan, ctx, B, dy, dx, wd, zb, taps=taps, cin_pad=dy.C, n=ci, t_out=dy.T, out_rows=(dx.T, 2, ph, dx.T),
+        _conv(plan, ctx, B, dy, dx, wd, zb, taps=taps, cin_pad=dy.C, n=ci, t_out=dy.T, out_rows=(dx.T, 2, ph, dx.T), res=res,
               tag=(tag or "downsample.dgrad") + f".phase{ph}")
         keep += [wd, zb]
     return keep
 
 
-def upsample_dgrad(plan, ctx: DgradCtx, B: int, dy: _View, dx: _View, ws: Sequence[torch.Tensor], tag: str = "") -> List[torch.Tensor]:
+def upsample_dgrad(plan, ctx: DgradCtx, B: int, dy: _View, dx: _View, ws: Sequence[torch.Tensor], tag: str = "",
+                   res: Optional[_View] = None) -> List[torch.Tensor]:
     """dX of ConvTranspose1d(k4, stride 2, padding 1): dy has 2T positions (read as even / odd phases), dx T."""
     ci, co, K = ws[0].shape
     assert K == 4 and dy.T == 2 * dx.T
@@ -82,7 +86,7 @@ def upsample_dgrad(plan, ctx: DgradCtx, B: int, dy: _View, dx: _View, ws: Sequen
     wd = plan.reg(pack_dgrad_convT(ws, range(K), dy.C, m).to(plan.device))
     zb = plan.reg(torch.zeros(ctx.G, wd.shape[1], dtype=torch.float32, device=plan.device))
     # dY[2t + k - 1]: k = 0 -> odd phase, index t-1;  k = 1 -> even, t;  k = 2 -> odd, t;  k = 3 -> even, t+1
-    _conv(plan, ctx, B, dy, dx, wd, zb, taps=[(1, -1), (0, 0), (1, 0), (0, 1)], cin_pad=dy.C, n=ci, t_out=dx.T, phases=2,
+    _conv(plan, ctx, B, dy, dx, wd, zb, taps=[(1, -1), (0, 0), (1, 0), (0, 1)], cin_pad=dy.C, n=ci, t_out=dx.T, phases=2, res=res,
           tag=tag or "upsample.dgrad")
     return [wd, zb]
 
@@ -163,11 +167,11 @@ def gn_mish_backward(plan, ctx: DgradCtx, B: int, T: int, C: int, raw: torch.Ten
 
 def conv_block_backward(plan, ctx: DgradCtx, B: int, x: _View, ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor],
                         gammas: Sequence[torch.Tensor], betas: Sequence[torch.Tensor], dout: torch.Tensor, dx: _View, *,
-                        film=None, tag: str = "block"):
+                        film=None, res: Optional[_View] = None, tag: str = "block"):
     """Backward of Conv1dBlock = Conv1d(k, padding k//2) -> GroupNorm(8) -> Mish [-> FiLM] (conditional_unet_1D.py:40-55,
     97-102) for G nets: the raw conv output is RECOMPUTED with the forward kernel (LINEAR epilogue, fp32) instead of being
     saved by the forward pass, then  gn_mish_backward -> conv_wgrad -> conv_dgrad.
-    x: bf16 [G][B][T][C_in] view (block input), dout fp32 [G][B][T][C_out], dx: bf16 view receiving d x.
+    x: bf16 [G][B][T][C_in] view (block input), dout fp32 [G][B][T][C_out], dx: bf16 or fp32 view receiving d x (+ res).
     Returns dict(dw [G][C_out][k * cin_pad], dbias, dgamma, dbeta [G][C_out])."""
     co, ci, K = ws[0].shape
     m, T = ctx.mode, x.T
@@ -182,5 +186,67 @@ def conv_block_backward(plan, ctx: DgradCtx, B: int, x: _View, ws: Sequence[torc
     draw, dg, db, dbias = gn_mish_backward(plan, ctx, B, T, co, raw, dout, gm, bt, film=film, tag=tag + ".gn+mish.bwd")
     vy = _View(draw, T, co)
     dw = conv_wgrad(plan, ctx, B, vy, x, tap_off=[k - K // 2 for k in range(K)], t_out=T, tag=tag + ".wgrad")
-    conv_dgrad(plan, ctx, B, vy, dx, [w.to(dev) for w in ws], pad=K // 2, tag=tag + ".dgrad")
+    if dx is not None:                     # the first block's input gradient (d sample) is not needed by training
+        conv_dgrad(plan, ctx, B, vy, dx, [w.to(dev) for w in ws], pad=K // 2, tag=tag + ".dgrad", res=res)
     return dict(dw=dw, dbias=dbias, dgamma=dg, dbeta=db, raw=raw, draw=draw)
+
+
+def cast_bf16(plan, src: torch.Tensor, tag: str) -> torch.Tensor:
+    """fp32 gradient [.., C] -> bf16 copy of the same shape (the GEMM operand of the dgrad / wgrad that consume it)."""
+    out = plan.buf(tag + f"#{len(plan)}.bf16", tuple(src.shape), torch.bfloat16)
+    d = nv.PackDesc()
+    C = src.shape[-1]
+    d.src, d.src_ld, d.rows, d.cols, d.act = ptr(src), C, src.numel() // C, C, nv.ACT_NONE
+    d.out, d.out_dtype, d.out_ld, d.dst_c0, d.out_plane, d.zero_to = ptr(out), nv.VT_BF16, C, 0, 0, 0
+    plan.add(d, tag)
+    return out
+
+
+def colsum(plan, G: int, x: torch.Tensor, rows: int, tag: str) -> torch.Tensor:
+    """[G][rows][C] fp32 -> [G][C]: the bias gradient of a convolution without GroupNorm."""
+    C = x.shape[-1]
+    out = plan.buf(tag + f"#{len(plan)}.out", (G, C), torch.float32)
+    d = nv.ColsumDesc()
+    d.x, d.ld, d.x_g, d.G, d.rows, d.C, d.out, d.out_ld = ptr(x), C, rows * C, G, rows, C, ptr(out), C
+    plan.add(d, tag)
+    return out
+
+
+def res_block_backward(plan, ctx: DgradCtx, B: int, sds: Sequence[dict], pfx: str, x: _View, y1: _View, dout: torch.Tensor,
+                       dx: _View, film, tag: str = "") -> dict:
+    """Backward of ConditionalResidualBlock1D (conditional_unet_1D.py:58-105; `_res_block_bwd` of the oracle) for G nets.
+
+    sds: the nets' state dicts, pfx the block's key prefix; x: bf16 view of the block input, y1: bf16 view of the FiLM output
+    (= input of blocks[1], kept by the training forward), dout fp32 [G][B][T][C_out], dx: fp32 view receiving d x (None: skip),
+    film = (FiLM table, d FiLM table, column offset of this block).  The gradient of the cond_encoder Linear is taken from the
+    d FiLM table for all 12 blocks at once by the caller.  Returns {reference parameter key suffix: gradient buffer}."""
+    tag = tag or pfx
+    g = lambda k: [sd[pfx + k] for sd in sds]
+    T = x.T
+    co = dout.shape[-1]
+    out = {}
+    # blocks[1]: Conv1d -> GN -> Mish, no FiLM; its d x is d y1 (fp32: it is the d out of blocks[0]'s elementwise backward)
+    dy1 = plan.buf(tag + f"#{len(plan)}.dy1", (ctx.G, B, T, co), torch.float32)
+    b1 = conv_block_backward(plan, ctx, B, y1, g("blocks.1.block.0.weight"), g("blocks.1.block.0.bias"),
+                             g("blocks.1.block.1.weight"), g("blocks.1.block.1.bias"), dout, _View(dy1, T, co), tag=tag + "blocks.1")
+    # residual path: d x += dout (identity) or W_r^T dout (1x1 conv)
+    res = _View(dout, T, co)
+    if pfx + "residual_conv.weight" in sds[0]:
+        wr = g("residual_conv.weight")
+        dob = _View(cast_bf16(plan, dout, tag + "dout.bf16"), T, co)
+        if dx is not None:
+            dxr = plan.buf(tag + f"#{len(plan)}.dxr", (ctx.G, B, T, dx.C), torch.float32)
+            conv_dgrad(plan, ctx, B, dob, _View(dxr, T, dx.C), [w.to(plan.device) for w in wr], pad=0, tag=tag + "residual_conv.dgrad")
+            res = _View(dxr, T, dx.C)
+        out["residual_conv.weight"] = (conv_wgrad(plan, ctx, B, dob, x, tap_off=[0], t_out=T, tag=tag + "residual_conv.wgrad"), 1)
+        out["residual_conv.bias"] = colsum(plan, ctx.G, dout, B * T, tag + "residual_conv.dbias")
+    b0 = conv_block_backward(plan, ctx, B, x, g("blocks.0.block.0.weight"), g("blocks.0.block.0.bias"),
+                             g("blocks.0.block.1.weight"), g("blocks.0.block.1.bias"), dy1, dx, film=film, res=res,
+                             tag=tag + "blocks.0")
+    for i, b in ((0, b0), (1, b1)):
+        K = sds[0][pfx + f"blocks.{i}.block.0.weight"].shape[-1]
+        out[f"blocks.{i}.block.0.weight"] = (b["dw"], K)
+        out[f"blocks.{i}.block.0.bias"] = b["dbias"]
+        out[f"blocks.{i}.block.1.weight"] = b["dgamma"]
+        out[f"blocks.{i}.block.1.bias"] = b["dbeta"]
+    return out
