@@ -336,6 +336,22 @@ typedef struct vt_colsum_desc {
   int32_t out_ld;
 } vt_colsum_desc;
 
+/* Strided fp32 elementwise combine over [rows][cols] windows: VT_EW_ADD out = a + b (gradient fan-in where a skip connection
+ * and the main path meet, conditional_unet_1D.py:226-240); VT_EW_MISH_BWD out = a * mish'(b) (backward of the Mish in front of
+ * the cond_encoder / diffusion_step_encoder linears, :76-80,186-191). */
+enum { VT_EW_ADD = 0, VT_EW_MISH_BWD = 1 };
+typedef struct vt_ewise_desc {
+  const float* a;
+  int64_t a_ld;
+  const float* b;
+  int64_t b_ld;
+  float* out;
+  int64_t out_ld;
+  int64_t rows;
+  int32_t cols;
+  int32_t op;
+} vt_ewise_desc;
+
 /* nn.LSTM (gate order i,f,g,o), lstm_step_controller.py:66-73,196-204: the input projections xw = W_ih x + b_ih
  * + b_hh are precomputed by a GEMM; this op runs the recurrence over T steps for one layer. */
 typedef struct vt_lstm_desc {
@@ -405,6 +421,7 @@ int vt_program_add_siloss(vt_program* p, const vt_siloss_desc* d);
 int vt_program_add_tcol(vt_program* p, const vt_tcol_desc* d);
 int vt_program_add_gnbwd(vt_program* p, const vt_gnbwd_desc* d);
 int vt_program_add_colsum(vt_program* p, const vt_colsum_desc* d);
+int vt_program_add_ewise(vt_program* p, const vt_ewise_desc* d);
 
 /* Launch ops [first, first+count) in order on `stream` (count < 0: to the end). */
 int vt_program_run(vt_program* p, int first, int count, void* stream);

@@ -238,3 +238,50 @@ def res_block_case(device, Ci: int, Co: int, G=2, B=3, T=16, seed=21, need_dx=Tr
         assert not bad, (bad, errs)
         return errs
     return plan, check
+
+
+def unet_case(device, A=7, T=16, B=2, G=2, seed=31):
+    """Training forward + build_unet_backward of G whole U-Nets against unet_forward_cached / unet_backward of the oracle:
+    every parameter gradient the plan produces, per net."""
+    import vt_testutil as U
+    from vla_touch_b200 import synthetic as syn
+    from vla_touch_b200 import unet_train as ut
+    from vla_touch_b200.unet import FILM_ROWS, UnetWeights, build_time_film, xpad_desc
+    names = ["b_net", "v_net", "s_net"][:G]
+    sds = [{k: (bf(v) if v.dim() >= 2 else v.clone()) for k, v in U.net_sd(A, seed, n).items()} for n in names]
+    x = syn.det_uniform("bwd.x", (B, T, A), seed, -1.0, 1.0)
+    cond = syn.det_normal("bwd.cond", (B, 256), seed)
+    t = torch.linspace(0.2, 0.9, B)
+    dout = syn.det_normal("bwd.dout", (G, B, T, A), seed)
+    plan = Plan(device)
+    W = UnetWeights(sds, A, device, precise=False)
+    W.register(plan)
+    xb = plan.buf("in.x", (B, T, A), torch.float32); xb.copy_(x)
+    tbuf = plan.buf("in.t", (B,), torch.float32); tbuf.copy_(t)
+    cb = plan.buf("in.cond", (B, 256), torch.float32); cb.copy_(cond)
+    dvs = plan.buf("in.dvs", (G, B, T, A), torch.float32); dvs.copy_(dout)
+    film = plan.buf("film", (G, B, FILM_ROWS), torch.float32)
+    dfilm = plan.buf("dfilm", (G, B, FILM_ROWS), torch.float32)
+    tb = ut.UnetTrainBuffers(plan, W, B, T)
+    plan.add(xpad_desc(W, xb, B * T, tb), "xpad")
+    tf = ut.build_time_film_train(plan, W, tbuf, B, cb, film) if hasattr(ut, "build_time_film_train") else build_time_film(plan, W, tbuf, B, cb, film)
+    ut.build_unet_train_forward(plan, W, tb, film)
+    grads = ut.build_unet_backward(plan, W, sds, tb, dvs, film, dfilm)
+    extra = ut.build_film_time_backward(plan, W, sds, tf, B, film, dfilm, grads) if hasattr(ut, "build_film_time_backward") else None
+
+    def check(tol=4e-2):
+        errs = {}
+        for n in range(G):
+            out_ref, cache = ob.unet_forward_cached(sds[n], x, t, cond)
+            ref, dcond, _ = ob.unet_backward(sds[n], cache, dout[n])
+            errs["forward"] = max(errs.get("forward", 0.0), _rel(tb.out[n].float().cpu(), out_ref))
+            for k, v in grads.items():
+                got = ut.grad_tensor(v, ref[k].shape)[n].float().cpu()
+                errs[k] = max(errs.get(k, 0.0), _rel(got.reshape(ref[k].shape), ref[k]))
+            if extra is not None:
+                errs["d_cond"] = max(errs.get("d_cond", 0.0), _rel(extra["dcond"][n].float().cpu(), dcond))
+        missing = set(ref) - set(grads)
+        bad = {k: v for k, v in errs.items() if not v <= tol}
+        assert not bad, (bad,)
+        return dict(worst=max(errs.values()), n=len(errs), missing=sorted(missing))
+    return plan, check

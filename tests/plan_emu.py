@@ -380,9 +380,16 @@ def emu_colsum(plan, d: nv.ColsumDesc):
         out[g * d.out_ld: g * d.out_ld + d.C] = v.sum(dim=0)
 
 
+def emu_ewise(plan, d: nv.EwiseDesc):
+    a, b, out = (_flat(plan, x, torch.float32) for x in (d.a, d.b, d.out))
+    r, c = torch.arange(d.rows)[:, None], torch.arange(d.cols)[None, :]
+    x, y = a[(r * d.a_ld + c).reshape(-1)], b[(r * d.b_ld + c).reshape(-1)]
+    out[(r * d.out_ld + c).reshape(-1)] = x + y if d.op == nv.EW_ADD else x * _mish_grad(y)
+
+
 _EMU = {nv.QsampleDesc: emu_qsample, nv.SilossDesc: emu_siloss, nv.GemmDesc: emu_gemm, nv.LnDesc: emu_layernorm, nv.AttnDesc: emu_attention, nv.ImgStatsDesc: emu_imgstats,
         nv.PatchifyDesc: emu_patchify, nv.ClsDesc: emu_cls, nv.PackDesc: emu_pack, nv.AffineDesc: emu_affine,
-        nv.TcolDesc: emu_tcol, nv.GnbwdDesc: emu_gnbwd, nv.ColsumDesc: emu_colsum, nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm, nv.MlpDesc: emu_mlp}
+        nv.TcolDesc: emu_tcol, nv.GnbwdDesc: emu_gnbwd, nv.ColsumDesc: emu_colsum, nv.EwiseDesc: emu_ewise, nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm, nv.MlpDesc: emu_mlp}
 
 
 @torch.no_grad()

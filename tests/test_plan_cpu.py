@@ -59,7 +59,7 @@ def test_ctypes_structs_match_the_c_header():
              "vt_sde_desc": nv.SdeDesc, "vt_lstm_desc": nv.LstmDesc, "vt_qsample_desc": nv.QsampleDesc,
              "vt_siloss_desc": nv.SilossDesc, "vt_opt_tensor": nv.OptTensor, "vt_adamw_desc": nv.AdamwDesc,
              "vt_mlp_desc": nv.MlpDesc, "vt_tcol_desc": nv.TcolDesc, "vt_gnbwd_desc": nv.GnbwdDesc,
-             "vt_colsum_desc": nv.ColsumDesc}
+             "vt_colsum_desc": nv.ColsumDesc, "vt_ewise_desc": nv.EwiseDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/vt_b200.h"', 'int main(void){']
     probes = []
     for cname, cls in descs.items():

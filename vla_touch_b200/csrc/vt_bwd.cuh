@@ -233,4 +233,26 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
   }
 }
 
+// Strided fp32 elementwise combine over [rows][cols] windows:  op 0: out = a + b (gradient fan-in at a skip connection),
+// op 1: out = a * mish'(b) (backward of the Mish in front of the FiLM / time-embedding linears).
+__global__ void __launch_bounds__(256) ewise_kernel(const float* __restrict__ a, long long a_ld, const float* __restrict__ b,
+                                                    long long b_ld, float* __restrict__ out, long long out_ld, long long rows,
+                                                    int cols, int op) {
+  const long long total = rows * cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cols);
+    const long long r = idx / cols;
+    const float x = a[r * a_ld + c], y = b[r * b_ld + c];
+    float v;
+    if (op == 0) {
+      v = x + y;
+    } else {
+      float m, dm;
+      mish_and_grad(y, m, dm);
+      v = x * dm;
+    }
+    out[r * out_ld + c] = v;
+  }
+}
+
 }  // namespace vt

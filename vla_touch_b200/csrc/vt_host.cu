@@ -666,6 +666,15 @@ struct ColsumOp : Op {
   }
 };
 
+struct EwiseOp : Op {
+  vt_ewise_desc d;
+  int launch(cudaStream_t s) override {
+    vt::ewise_kernel<<<grid_for(d.rows * d.cols, 256), 256, 0, s>>>(d.a, d.a_ld, d.b, d.b_ld, d.out, d.out_ld, d.rows, d.cols, d.op);
+    VT_LAUNCH_CHECK("ewise_kernel");
+    return VT_OK;
+  }
+};
+
 struct LstmOp : Op {
   vt_lstm_desc d;
   int launch(cudaStream_t s) override {
@@ -932,6 +941,11 @@ VT_SIMPLE_ADD(vt_program_add_gnbwd, GnbwdOp, vt_gnbwd_desc,
 VT_SIMPLE_ADD(vt_program_add_colsum, ColsumOp, vt_colsum_desc,
               VT_REQUIRE(d->x && d->out && d->G >= 1 && d->G <= 65535 && d->rows >= 1 && d->C >= 1 && d->ld >= d->C,
                          "colsum: bad descriptor"))
+
+VT_SIMPLE_ADD(vt_program_add_ewise, EwiseOp, vt_ewise_desc,
+              VT_REQUIRE(d->a && d->b && d->out && d->rows >= 1 && d->cols >= 1 && d->a_ld >= d->cols && d->b_ld >= d->cols &&
+                             d->out_ld >= d->cols && (d->op == VT_EW_ADD || d->op == VT_EW_MISH_BWD),
+                         "ewise: bad descriptor"))
 
 VT_SIMPLE_ADD(vt_program_add_qsample, QsampleOp, vt_qsample_desc,
               VT_REQUIRE(d->x0 && d->x1 && d->step && d->z_unit && d->xt && d->tclip && d->B >= 1 && d->n >= 1 && d->A >= 1 &&

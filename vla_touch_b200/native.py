@@ -121,6 +121,14 @@ class ColsumDesc(C.Structure):
     _fields_ = [("x", vp), ("ld", i64), ("x_g", i64), ("G", i32), ("rows", i32), ("C", i32), ("out", vp), ("out_ld", i32)]
 
 
+class EwiseDesc(C.Structure):
+    _fields_ = [("a", vp), ("a_ld", i64), ("b", vp), ("b_ld", i64), ("out", vp), ("out_ld", i64), ("rows", i64), ("cols", i32),
+                ("op", i32)]
+
+
+EW_ADD, EW_MISH_BWD = 0, 1
+
+
 class OptTensor(C.Structure):
     _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("ema", vp), ("numel", i64)]
 
@@ -136,7 +144,7 @@ EXPORTS = [
     "vt_program_num_ops", "vt_program_num_launches", "vt_program_add_gemm", "vt_program_add_layernorm",
     "vt_program_add_attention", "vt_program_add_mlp", "vt_debug_timestamps", "vt_program_add_imgstats", "vt_program_add_patchify", "vt_program_add_cls",
     "vt_program_add_pack", "vt_program_add_affine", "vt_program_add_tembed", "vt_program_add_sde",
-    "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_add_tcol", "vt_program_add_gnbwd", "vt_program_add_colsum", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
+    "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_add_tcol", "vt_program_add_gnbwd", "vt_program_add_colsum", "vt_program_add_ewise", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
     "vt_pos_embed_resize", "vt_adamw_ema_step",
 ]
 
@@ -146,7 +154,7 @@ _ADD = {
     PackDesc: "vt_program_add_pack", AffineDesc: "vt_program_add_affine", TembedDesc: "vt_program_add_tembed",
     SdeDesc: "vt_program_add_sde", LstmDesc: "vt_program_add_lstm", QsampleDesc: "vt_program_add_qsample",
     SilossDesc: "vt_program_add_siloss", TcolDesc: "vt_program_add_tcol", GnbwdDesc: "vt_program_add_gnbwd",
-    ColsumDesc: "vt_program_add_colsum",
+    ColsumDesc: "vt_program_add_colsum", EwiseDesc: "vt_program_add_ewise",
 }
 
 _lib: Optional[C.CDLL] = None

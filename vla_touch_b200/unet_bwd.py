@@ -142,10 +142,15 @@ def unpack_wgrad(dw: torch.Tensor, c_valid: int, taps: int) -> torch.Tensor:
     return dw.view(G, R, taps, n // taps)[:, :, :, :c_valid].permute(0, 1, 3, 2)
 
 
+def as_view(t, T: int) -> _View:
+    """fp32 gradient given as a compact [G][B][T][C] tensor or as a channel window (_View) of a wider buffer."""
+    return t if isinstance(t, _View) else _View(t, T, t.shape[-1])
+
+
 def gn_mish_backward(plan, ctx: DgradCtx, B: int, T: int, C: int, raw: torch.Tensor, dout: torch.Tensor, gamma: torch.Tensor,
                      beta: torch.Tensor, *, film=None, tag: str = "gn.bwd"):
     """GroupNorm(8) + Mish (+ FiLM) backward of one Conv1dBlock for G nets (gn_mish_bwd + the FiLM lines of _res_block_bwd in
-    oracle/vt_oracle_bwd.py).  raw / dout fp32 [G][B][T][C]; gamma / beta fp32 [G][C];
+    oracle/vt_oracle_bwd.py).  raw fp32 [G][B][T][C], dout fp32 tensor or channel window of the same extent; gamma / beta fp32 [G][C];
     film = (film table [G][B][ld], d film table [G][B][ld], column offset) or None.
     Returns (draw bf16 [G][B][T][C], dgamma, dbeta, dbias fp32 [G][C])."""
     G = ctx.G
@@ -154,7 +159,8 @@ def gn_mish_backward(plan, ctx: DgradCtx, B: int, T: int, C: int, raw: torch.Ten
     part = plan.buf(nm + ".part", (G, B, 3, C), torch.float32)
     dg, db, dbias = (plan.buf(nm + "." + k, (G, C), torch.float32) for k in ("dgamma", "dbeta", "dbias"))
     d = nv.GnbwdDesc()
-    d.raw, d.dout, d.dout_ld, d.dout_g = ptr(raw), ptr(dout), dout.shape[-1], B * T * dout.shape[-1]
+    dv = as_view(dout, T)
+    d.raw, d.dout, d.dout_ld, d.dout_g = ptr(raw), ptr(dv.t, dv.c0), dv.ld, B * T * dv.ld
     d.gamma, d.beta, d.p_ld = ptr(gamma), ptr(beta), gamma.shape[-1]
     if film is not None:
         ft, dft, off = film
@@ -191,23 +197,25 @@ def conv_block_backward(plan, ctx: DgradCtx, B: int, x: _View, ws: Sequence[torc
     return dict(dw=dw, dbias=dbias, dgamma=dg, dbeta=db, raw=raw, draw=draw)
 
 
-def cast_bf16(plan, src: torch.Tensor, tag: str) -> torch.Tensor:
-    """fp32 gradient [.., C] -> bf16 copy of the same shape (the GEMM operand of the dgrad / wgrad that consume it)."""
-    out = plan.buf(tag + f"#{len(plan)}.bf16", tuple(src.shape), torch.bfloat16)
+def cast_bf16(plan, G: int, B: int, src, T: int, tag: str, c_pad: Optional[int] = None) -> _View:
+    """fp32 gradient (tensor or channel window) -> compact bf16 copy [G][B][T][c_pad] (zero-filled beyond C): the GEMM operand
+    of the dgrad / wgrad that consume it."""
+    v = as_view(src, T)
+    cp = c_pad or v.C
+    out = plan.buf(tag + f"#{len(plan)}.bf16", (G, B, T, cp), torch.bfloat16)
     d = nv.PackDesc()
-    C = src.shape[-1]
-    d.src, d.src_ld, d.rows, d.cols, d.act = ptr(src), C, src.numel() // C, C, nv.ACT_NONE
-    d.out, d.out_dtype, d.out_ld, d.dst_c0, d.out_plane, d.zero_to = ptr(out), nv.VT_BF16, C, 0, 0, 0
+    d.src, d.src_ld, d.rows, d.cols, d.act = ptr(v.t, v.c0), v.ld, G * B * T, v.C, nv.ACT_NONE
+    d.out, d.out_dtype, d.out_ld, d.dst_c0, d.out_plane, d.zero_to = ptr(out), nv.VT_BF16, cp, 0, 0, cp if cp > v.C else 0
     plan.add(d, tag)
-    return out
+    return _View(out, T, cp)
 
 
-def colsum(plan, G: int, x: torch.Tensor, rows: int, tag: str) -> torch.Tensor:
-    """[G][rows][C] fp32 -> [G][C]: the bias gradient of a convolution without GroupNorm."""
-    C = x.shape[-1]
-    out = plan.buf(tag + f"#{len(plan)}.out", (G, C), torch.float32)
+def colsum(plan, G: int, B: int, x, T: int, tag: str) -> torch.Tensor:
+    """fp32 [G][B*T][C] (tensor or channel window) -> [G][C]: the bias gradient of a convolution without GroupNorm."""
+    v = as_view(x, T)
+    out = plan.buf(tag + f"#{len(plan)}.out", (G, v.C), torch.float32)
     d = nv.ColsumDesc()
-    d.x, d.ld, d.x_g, d.G, d.rows, d.C, d.out, d.out_ld = ptr(x), C, rows * C, G, rows, C, ptr(out), C
+    d.x, d.ld, d.x_g, d.G, d.rows, d.C, d.out, d.out_ld = ptr(v.t, v.c0), v.ld, B * T * v.ld, G, B * T, v.C, ptr(out), v.C
     plan.add(d, tag)
     return out
 
@@ -223,23 +231,24 @@ def res_block_backward(plan, ctx: DgradCtx, B: int, sds: Sequence[dict], pfx: st
     tag = tag or pfx
     g = lambda k: [sd[pfx + k] for sd in sds]
     T = x.T
-    co = dout.shape[-1]
+    dout = as_view(dout, T)
+    co = dout.C
     out = {}
     # blocks[1]: Conv1d -> GN -> Mish, no FiLM; its d x is d y1 (fp32: it is the d out of blocks[0]'s elementwise backward)
     dy1 = plan.buf(tag + f"#{len(plan)}.dy1", (ctx.G, B, T, co), torch.float32)
     b1 = conv_block_backward(plan, ctx, B, y1, g("blocks.1.block.0.weight"), g("blocks.1.block.0.bias"),
                              g("blocks.1.block.1.weight"), g("blocks.1.block.1.bias"), dout, _View(dy1, T, co), tag=tag + "blocks.1")
     # residual path: d x += dout (identity) or W_r^T dout (1x1 conv)
-    res = _View(dout, T, co)
+    res = dout
     if pfx + "residual_conv.weight" in sds[0]:
         wr = g("residual_conv.weight")
-        dob = _View(cast_bf16(plan, dout, tag + "dout.bf16"), T, co)
+        dob = cast_bf16(plan, ctx.G, B, dout, T, tag + "dout.bf16")
         if dx is not None:
             dxr = plan.buf(tag + f"#{len(plan)}.dxr", (ctx.G, B, T, dx.C), torch.float32)
             conv_dgrad(plan, ctx, B, dob, _View(dxr, T, dx.C), [w.to(plan.device) for w in wr], pad=0, tag=tag + "residual_conv.dgrad")
             res = _View(dxr, T, dx.C)
         out["residual_conv.weight"] = (conv_wgrad(plan, ctx, B, dob, x, tap_off=[0], t_out=T, tag=tag + "residual_conv.wgrad"), 1)
-        out["residual_conv.bias"] = colsum(plan, ctx.G, dout, B * T, tag + "residual_conv.dbias")
+        out["residual_conv.bias"] = colsum(plan, ctx.G, B, dout, T, tag + "residual_conv.dbias")
     b0 = conv_block_backward(plan, ctx, B, x, g("blocks.0.block.0.weight"), g("blocks.0.block.0.bias"),
                              g("blocks.0.block.1.weight"), g("blocks.0.block.1.bias"), dy1, dx, film=film, res=res,
                              tag=tag + "blocks.0")

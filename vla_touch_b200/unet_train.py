@@ -1,0 +1,208 @@
+"""Training-mode forward and the explicit backward of the interpolant U-Nets (row a10 of SURVEY 8:
+StochasticInterpolants.get_loss(...).backward(), bridge_model.py:220-246, through DiffusionConditionalUnet1D.forward,
+bridge/networks/conditional_unet_1D.py:194-247) as ONE plan for the G = 3 nets (b_net, v_net, s_net).
+
+Forward: the same fused kernels as inference (implicit-GEMM conv + GroupNorm + Mish + FiLM + residual in the epilogue), but
+every block writes its own buffers, because the backward reads each block's input and FiLM output again.  The raw conv outputs
+are NOT stored: the backward recomputes them (unet_bwd.conv_block_backward).
+
+Backward, in reverse execution order (`unet_backward` of oracle/vt_oracle_bwd.py is the checker):
+  final 1x1 conv, final Conv1dBlock, then per level: ConvTranspose1d (up) / 12 x ConditionalResidualBlock1D / Conv1d stride 2
+  (down); torch.cat splits the gradient into channel windows (free: consumers read windows of the fp32 gradient buffer), the
+  skip connections sum gradients through the dgrad GEMM's residual input or one `ewise` add; the unused level-0 skip
+   gets no gradient.  Then the FiLM Linear of all 12 blocks at once (their d scale / d shift rows are columns
+  of one [B][11264] table), Mish'(gf), the time-embedding MLP, and d global_cond.
+Gradient activations are fp32 where an elementwise backward consumes them and are cast to bf16 copies where a GEMM does.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import native as nv
+from . import unet_bwd as ub
+from .plan import Plan, linear_desc, ptr
+from .unet import DOWN_DIMS, DSED, FILM_ROWS, UnetWeights, _View, _conv, _tembed, block_names
+
+SD = Dict[str, torch.Tensor]
+K5 = [(0, dt) for dt in (-2, -1, 0, 1, 2)]
+K1 = [(0, 0)]
+
+
+class _Block:
+    def __init__(self, pfx: str, x: _View, y1: _View, out: _View, r: Optional[_View]):
+        self.pfx, self.x, self.y1, self.out, self.r = pfx, x, y1, out, r
+
+
+class UnetTrainBuffers:
+    """Activations of one training forward of G nets on (B, T): one buffer per block output / FiLM output."""
+
+    def __init__(self, plan: Plan, W: UnetWeights, B: int, T: int, tag: str = "tr"):
+        if T % 4 != 0 or T > 128 or T < 4:
+            raise ValueError(f"horizon T={T} must be a multiple of 4 in [4, 128]")
+        if W.mode.precise:
+            raise ValueError("the training plans run in the bf16 mode")
+        G = W.G
+        self.B, self.T, self.G = B, T, G
+        T0, T1, T2 = self.Ts = (T, T // 2, T // 4)
+        d0, d1, d2 = DOWN_DIMS
+        bf = torch.bfloat16
+        mk = lambda name, t, c: plan.buf(f"{tag}.{name}", (G, B, t, c), bf)
+        self.xpad = plan.buf(f"{tag}.xpad", (B, T0, W.cin0), bf)
+        self.out = plan.buf(f"{tag}.vs", (G, B, T0, W.A), torch.float32)
+        A0, A1, D1, A2 = mk("A0", T0, d0), mk("A1", T0, d0), mk("D1", T1, d0), mk("A2", T1, d1)
+        cat1, D2, A4, cat0 = mk("cat1", T1, 2 * d1), mk("D2", T2, d1), mk("A4", T2, d2), mk("cat0", T2, 2 * d2)
+        A6, A8, A9 = mk("A6", T2, d2), mk("A8", T2, d1), mk("A9", T2, d1)
+        A10, A11, F0, F1 = mk("A10", T1, d0), mk("A11", T1, d0), mk("F0", T0, d0), mk("F1", T0, d0)
+        V = _View
+        self.xin = V(self.xpad, T0, W.cin0, shared=True)
+        self.A1, self.A9, self.A11, self.F0, self.F1 = V(A1, T0, d0), V(A9, T2, d1), V(A11, T1, d0), V(F0, T0, d0), V(F1, T0, d0)
+        self.D1, self.D2 = V(D1, T1, d0), V(D2, T2, d1)
+        self.h1 = V(cat1, T1, d1, c0=d1, ctot=2 * d1)            # skip of level 1 = second half of up_modules.1's input
+        self.h2 = V(cat0, T2, d2, c0=d2, ctot=2 * d2)            # skip of level 2 = second half of up_modules.0's input
+        self.cat0, self.cat1 = V(cat0, T2, 2 * d2), V(cat1, T1, 2 * d1)
+        self.up0_out = V(cat1, T1, d1, c0=0, ctot=2 * d1)
+        mid_out = V(cat0, T2, d2, c0=0, ctot=2 * d2)
+        chain = [(self.xin, V(A0, T0, d0)), (V(A0, T0, d0), self.A1), (self.D1, V(A2, T1, d1)), (V(A2, T1, d1), self.h1),
+                 (self.D2, V(A4, T2, d2)), (V(A4, T2, d2), self.h2), (self.h2, V(A6, T2, d2)), (V(A6, T2, d2), mid_out),
+                 (self.cat0, V(A8, T2, d1)), (V(A8, T2, d1), self.A9), (self.cat1, V(A10, T1, d0)), (V(A10, T1, d0), self.A11)]
+        self.blocks: List[_Block] = []
+        for i, ((pfx, _, co), (x, out)) in enumerate(zip(block_names(), chain)):
+            y1 = V(mk(f"U{i}", out.T, co), out.T, co)
+            r = V(mk(f"R{i}", out.T, co), out.T, co) if pfx + "r.w" in W.t else None
+            self.blocks.append(_Block(pfx, x, y1, out, r))
+
+
+def build_unet_train_forward(plan: Plan, W: UnetWeights, tb: UnetTrainBuffers, film: torch.Tensor, tag: str = "fwd") -> None:
+    """tb.xpad (+ the per-sample FiLM table film fp32 [G][B][11264]) -> tb.out [G][B][T][A]; 42 GEMM launches."""
+    T_, B = W.t, tb.B
+    T0, T1, T2 = tb.Ts
+    d0, d1, d2 = DOWN_DIMS
+    ds_taps = [(1, -1), (0, 0), (1, 0)]
+
+    def crb(k: int) -> None:
+        b = tb.blocks[k]
+        pfx, co, t = b.pfx, b.out.C, b.out.T
+        _conv(plan, W, B, b.x, b.y1, T_[pfx + "c0.w"], T_[pfx + "c0.b"], taps=K5, cin_pad=b.x.C, n=co, t_out=t,
+              gn=(T_[pfx + "g0.w"], T_[pfx + "g0.b"]), film=(film, None, 0, W.film_off[pfx]), tag=f"{tag}.{pfx}conv0+gn+mish+film")
+        res = b.x
+        if b.r is not None:
+            _conv(plan, W, B, b.x, b.r, T_[pfx + "r.w"], T_[pfx + "r.b"], taps=K1, cin_pad=b.x.C, n=co, t_out=t,
+                  tag=f"{tag}.{pfx}residual_conv")
+            res = b.r
+        _conv(plan, W, B, b.y1, b.out, T_[pfx + "c1.w"], T_[pfx + "c1.b"], taps=K5, cin_pad=co, n=co, t_out=t,
+              gn=(T_[pfx + "g1.w"], T_[pfx + "g1.b"]), res=res, tag=f"{tag}.{pfx}conv1+gn+mish+res")
+
+    def up(U: int, src: _View, dst: _View, t_in: int, c: int) -> None:
+        for ph, taps in ((0, [(0, 0), (0, -1)]), (1, [(0, 1), (0, 0)])):
+            _conv(plan, W, B, src, dst, T_[f"us{U}.w{ph}"], T_[f"us{U}.b"], taps=taps, cin_pad=c, n=c, t_out=t_in,
+                  out_rows=(2 * t_in, 2, ph, 2 * t_in), tag=f"{tag}.up{U}.upsample.phase{ph}")
+
+    crb(0); crb(1)
+    _conv(plan, W, B, tb.A1, tb.D1, T_["ds0.w"], T_["ds0.b"], taps=ds_taps, cin_pad=d0, n=d0, t_out=T1, phases=2, tag=f"{tag}.down0.downsample")
+    crb(2); crb(3)
+    _conv(plan, W, B, tb.h1, tb.D2, T_["ds1.w"], T_["ds1.b"], taps=ds_taps, cin_pad=d1, n=d1, t_out=T2, phases=2, tag=f"{tag}.down1.downsample")
+    for k in (4, 5, 6, 7, 8, 9):
+        crb(k)
+    up(0, tb.A9, tb.up0_out, T2, d1)
+    crb(10); crb(11)
+    up(1, tb.A11, tb.F0, T1, d0)
+    _conv(plan, W, B, tb.F0, tb.F1, T_["final0.w"], T_["final0.b"], taps=K5, cin_pad=d0, n=d0, t_out=T0,
+          gn=(T_["final0.gw"], T_["final0.gb"]), tag=f"{tag}.final_conv.0+gn+mish")
+    _conv(plan, W, B, tb.F1, None, T_["final1.w"], T_["final1.b"], taps=K1, cin_pad=d0, n=W.A, t_out=T0, bn=32,
+          out_f32=tb.out, tag=f"{tag}.final_conv.1")
+
+
+Grad = Tuple[torch.Tensor, int]     # (buffer, taps): taps > 0 -> packed conv weight gradient (unet_bwd.unpack_wgrad), 0 -> as is
+
+
+def build_unet_backward(plan: Plan, W: UnetWeights, sds: Sequence[SD], tb: UnetTrainBuffers, dvs: torch.Tensor,
+                        film: torch.Tensor, dfilm: torch.Tensor, tag: str = "bwd") -> Dict[str, Grad]:
+    """Gradients of every convolution / GroupNorm parameter of the G nets from dvs = d loss / d tb.out (fp32 [G][B][T][A]);
+    fills dfilm (fp32 [G][B][11264]: d scale | d shift of every block).  Returns {reference state-dict key: (buffer, taps)}."""
+    G, B = W.G, tb.B
+    T0, T1, T2 = tb.Ts
+    d0, d1, d2 = DOWN_DIMS
+    dev = plan.device
+    grads: Dict[str, Grad] = {}
+    g = lambda k: [sd[k].to(dev) for sd in sds]
+    f32 = lambda name, t, c: plan.buf(f"{tag}.{name}", (G, B, t, c), torch.float32)
+    V = _View
+
+    # final_conv.1: Conv1d(d0 -> A, k1)
+    dvb = ub.cast_bf16(plan, G, B, dvs, T0, f"{tag}.dvs.bf16", c_pad=W.mode.ke)
+    grads["final_conv.1.weight"] = (ub.conv_wgrad(plan, W, B, dvb, tb.F1, tap_off=[0], t_out=T0, tag=f"{tag}.final_conv.1.wgrad"), 1)
+    grads["final_conv.1.bias"] = (ub.colsum(plan, G, B, dvs, T0, f"{tag}.final_conv.1.dbias"), 0)
+    dF1 = f32("dF1", T0, d0)
+    ub.conv_dgrad(plan, W, B, dvb, V(dF1, T0, d0), g("final_conv.1.weight"), pad=0, tag=f"{tag}.final_conv.1.dgrad")
+    # final_conv.0: Conv1dBlock
+    dF0 = f32("dF0", T0, d0)
+    b = ub.conv_block_backward(plan, W, B, tb.F0, g("final_conv.0.block.0.weight"), g("final_conv.0.block.0.bias"),
+                               g("final_conv.0.block.1.weight"), g("final_conv.0.block.1.bias"), dF1, V(dF0, T0, d0),
+                               tag=f"{tag}.final_conv.0")
+    grads.update({"final_conv.0.block.0.weight": (b["dw"], 5), "final_conv.0.block.0.bias": (b["dbias"], 0),
+                  "final_conv.0.block.1.weight": (b["dgamma"], 0), "final_conv.0.block.1.bias": (b["dbeta"], 0)})
+
+    def up_bwd(U: int, x: _View, dy, t_in: int, c: int, dx: torch.Tensor) -> None:
+        """ConvTranspose1d(k4, s2, p1): x [t_in] -> y [2 t_in]; dy fp32 (tensor / window over 2 t_in positions)"""
+        key = f"up_modules.{U}.2.conv."
+        dyb = ub.cast_bf16(plan, G, B, dy, 2 * t_in, f"{tag}.{key}dy.bf16")
+        grads[key + "weight"] = (ub.conv_wgrad(plan, W, B, x, dyb, tap_off=[-1, 0, 1, 2], stride=2, t_out=t_in, tag=f"{tag}.{key}wgrad"), 4)
+        grads[key + "bias"] = (ub.colsum(plan, G, B, dy, 2 * t_in, f"{tag}.{key}dbias"), 0)
+        ub.upsample_dgrad(plan, W, B, dyb, V(dx, t_in, c), g(key + "weight"), tag=f"{tag}.{key}dgrad")
+
+    def down_bwd(L: int, x: _View, dy: torch.Tensor, t_out: int, c: int, dx: torch.Tensor, res: Optional[_View]) -> None:
+        """Conv1d(k3, s2, p1): x [2 t_out] -> y [t_out]"""
+        key = f"down_modules.{L}.2.conv."
+        dyb = ub.cast_bf16(plan, G, B, dy, t_out, f"{tag}.{key}dy.bf16")
+        grads[key + "weight"] = (ub.conv_wgrad(plan, W, B, dyb, x, tap_off=[-1, 0, 1], stride=2, t_out=t_out, tag=f"{tag}.{key}wgrad"), 3)
+        grads[key + "bias"] = (ub.colsum(plan, G, B, dy, t_out, f"{tag}.{key}dbias"), 0)
+        ub.downsample_dgrad(plan, W, B, dyb, V(dx, 2 * t_out, c), g(key + "weight"), tag=f"{tag}.{key}dgrad", res=res)
+
+    def crb_bwd(k: int, dout, dx: Optional[_View]) -> None:
+        blk = tb.blocks[k]
+        pfx = blk.pfx
+        out = ub.res_block_backward(plan, W, B, sds, pfx, blk.x, blk.y1, dout, dx, (film, dfilm, W.film_off[pfx]), tag=f"{tag}.{pfx}")
+        for key, v in out.items():
+            grads[pfx + key] = v if isinstance(v, tuple) else (v, 0)
+
+    dA11 = f32("dA11", T1, d0)
+    up_bwd(1, tb.A11, dF0, T1, d0, dA11)
+    dA10, dcat1 = f32("dA10", T1, d0), f32("dcat1", T1, 2 * d1)
+    crb_bwd(11, dA11, V(dA10, T1, d0))
+    crb_bwd(10, dA10, V(dcat1, T1, 2 * d1))
+    dA9 = f32("dA9", T2, d1)
+    up_bwd(0, tb.A9, V(dcat1, T1, d1, c0=0), T2, d1, dA9)
+    dA8, dcat0 = f32("dA8", T2, d1), f32("dcat0", T2, 2 * d2)
+    crb_bwd(9, dA9, V(dA8, T2, d1))
+    crb_bwd(8, dA8, V(dcat0, T2, 2 * d2))
+    dA6, dh2a, dh2 = f32("dA6", T2, d2), f32("dh2a", T2, d2), f32("dh2", T2, d2)
+    crb_bwd(7, V(dcat0, T2, d2, c0=0), V(dA6, T2, d2))
+    crb_bwd(6, dA6, V(dh2a, T2, d2))
+    e = nv.EwiseDesc()                                           # level-2 skip: d h2 = (through mid / up path) + (cat half)
+    e.a, e.a_ld, e.b, e.b_ld, e.out, e.out_ld = ptr(dh2a), d2, ptr(dcat0, d2), 2 * d2, ptr(dh2), d2
+    e.rows, e.cols, e.op = G * B * T2, d2, nv.EW_ADD
+    plan.add(e, f"{tag}.skip2.add")
+    dA4, dD2 = f32("dA4", T2, d2), f32("dD2", T2, d1)
+    crb_bwd(5, dh2, V(dA4, T2, d2))
+    crb_bwd(4, dA4, V(dD2, T2, d1))
+    dh1 = f32("dh1", T1, d1)
+    down_bwd(1, tb.h1, dD2, T2, d1, dh1, res=V(dcat1, T1, d1, c0=d1))          # level-1 skip summed in the dgrad epilogue
+    dA2, dD1 = f32("dA2", T1, d1), f32("dD1", T1, d0)
+    crb_bwd(3, dh1, V(dA2, T1, d1))
+    crb_bwd(2, dA2, V(dD1, T1, d0))
+    dA1 = f32("dA1", T0, d0)
+    down_bwd(0, tb.A1, dD1, T1, d0, dA1, res=None)                              # the level-0 skip is never consumed
+    dA0 = f32("dA0", T0, d0)
+    crb_bwd(1, dA1, V(dA0, T0, d0))
+    crb_bwd(0, dA0, None)                                                       # d sample is not needed
+    return grads
+
+
+def grad_tensor(v: Grad, ref_shape) -> torch.Tensor:
+    """-> [G, *ref_shape] view/copy of a gradient buffer in the reference parameter's own layout."""
+    buf, taps = v
+    if taps:
+        return ub.unpack_wgrad(buf, ref_shape[1], taps)[:, : ref_shape[0]]
+    return buf[:, : ref_shape[0]] if buf.dim() == 2 else buf
