@@ -352,6 +352,19 @@ typedef struct vt_ewise_desc {
   int32_t op;
 } vt_ewise_desc;
 
+/* Derivative of the summed loss of vt_siloss_desc with respect to the stacked net outputs (the seed of the backward pass):
+ *   dvs[0] = (b - (x1 - x0 + gdot z)) / B,  dvs[1] = (v - (x1 - x0)) / B,  dvs[2] = (s + z) / B     (bridge_model.py:183-246) */
+typedef struct vt_silossbwd_desc {
+  const float* bvs;     /* [3][B][n] */
+  const float* x0;
+  const float* x1;
+  const float* z_unit;
+  const float* tclip;   /* [B] */
+  float d;
+  int32_t B, n;
+  float* dvs;           /* [3][B][n] */
+} vt_silossbwd_desc;
+
 /* nn.LSTM (gate order i,f,g,o), lstm_step_controller.py:66-73,196-204: the input projections xw = W_ih x + b_ih
  * + b_hh are precomputed by a GEMM; this op runs the recurrence over T steps for one layer. */
 typedef struct vt_lstm_desc {
@@ -422,6 +435,7 @@ int vt_program_add_tcol(vt_program* p, const vt_tcol_desc* d);
 int vt_program_add_gnbwd(vt_program* p, const vt_gnbwd_desc* d);
 int vt_program_add_colsum(vt_program* p, const vt_colsum_desc* d);
 int vt_program_add_ewise(vt_program* p, const vt_ewise_desc* d);
+int vt_program_add_silossbwd(vt_program* p, const vt_silossbwd_desc* d);
 
 /* Launch ops [first, first+count) in order on `stream` (count < 0: to the end). */
 int vt_program_run(vt_program* p, int first, int count, void* stream);

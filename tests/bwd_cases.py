@@ -285,3 +285,48 @@ def unet_case(device, A=7, T=16, B=2, G=2, seed=31):
         assert not bad, (bad,)
         return dict(worst=max(errs.values()), n=len(errs), missing=sorted(missing))
     return plan, check
+
+
+def loss_case(device, A=7, T=64):
+    """LossBackwardProgram against the REFERENCE's own get_loss(...).backward() digests (tests/golden/loss_grads_*.npz, made by
+    oracle/gen_golden_grads.py from the unmodified reference): loss values, d loss / d obs_cond in full, and norm / sum / first
+    elements of all 438 parameter gradients.  bf16 operands: 3e-2 of each tensor's scale."""
+    import vt_testutil as U
+    from vla_touch_b200 import synthetic as syn
+    from vla_touch_b200.unet_train import LossBackwardProgram
+    g, gg = U.golden(f"loss_A{A}_T{T}"), U.golden(f"loss_grads_A{A}_T{T}")
+    full = U.net_sd(A, 21)
+    sub = lambda n: {k[len(n):]: v for k, v in full.items() if k.startswith(n)}
+    lp = LossBackwardProgram([sub("b_net."), sub("v_net."), sub("s_net.")], A, 3, T, 0.03, device)
+    lp.set_inputs(syn.det_uniform("loss.vla", (3, T, A), 24, -1.0, 1.0), syn.det_uniform("loss.exp", (3, T, A), 24, -1.0, 1.0),
+                  syn.det_normal("loss.cond", (3, 256), 24), torch.as_tensor(g["step"]), torch.as_tensor(g["z_unit"]))
+
+    def check(tol=3e-2):
+        """(1) reference digests: loss values, d_cond in full, norm and leading elements of all 438 gradients (the `sum` digest
+        is not used at bf16: for gradients with a coherent factor, e.g. dW = d_emb^T Mish(gf) with mean(Mish) > 0, it amplifies
+        the operand rounding by sqrt(numel)); (2) every gradient tensor IN FULL against autograd through the forward oracle,
+        which tests/test_oracle_golden.py::test_loss_gradients holds to all three reference digests at 1e-4."""
+        from oracle import vt_oracle as orc
+        for i, key in enumerate(("loss", "v_loss", "s_loss", "b_loss")):
+            assert abs(float(lp.out[i]) - float(g[key])) <= 2e-2 * max(1.0, abs(float(g[key]))), (key, float(lp.out[i]), float(g[key]))
+        dc = torch.as_tensor(gg["d_cond"])
+        worst = {"d_cond": _rel(lp.d_cond.float().cpu(), dc)}
+        grads = lp.grads
+        names = [str(n) for n in gg["names"]]
+        assert sorted(names) == sorted(grads), "every reference parameter has a gradient"
+        sd = {k: v.clone().requires_grad_(True) for k, v in full.items()}
+        loss, *_ = orc.bridge_losses(sd, syn.det_normal("loss.cond", (3, 256), 24), syn.det_uniform("loss.exp", (3, T, A), 24, -1.0, 1.0),
+                                     syn.det_uniform("loss.vla", (3, T, A), 24, -1.0, 1.0), torch.as_tensor(g["step"]), torch.as_tensor(g["z_unit"]))
+        loss.backward()
+        for i, n in enumerate(names):
+            got = grads[n].float().cpu()
+            gr = got.flatten().double()
+            scale = max(float(gg["norm"][i]), 1e-12)
+            k = min(8, gr.numel())
+            worst[n] = max(abs(float(gr.norm()) - float(gg["norm"][i])) / scale,
+                           float((gr[:k] - torch.as_tensor(gg["head"][i][:k]).double()).abs().max()) / scale,
+                           _rel(got, sd[n].grad))
+        bad = {k: v for k, v in worst.items() if not v <= tol}
+        assert not bad, bad
+        return dict(worst=max(worst.values()), tensors=len(worst))
+    return lp.plan, check

@@ -387,9 +387,21 @@ def emu_ewise(plan, d: nv.EwiseDesc):
     out[(r * d.out_ld + c).reshape(-1)] = x + y if d.op == nv.EW_ADD else x * _mish_grad(y)
 
 
+def emu_silossbwd(plan, d: nv.SilossBwdDesc):
+    N = d.B * d.n
+    bvs = _flat(plan, d.bvs, torch.float32)[: 3 * N].reshape(3, d.B, d.n)
+    x0 = _flat(plan, d.x0, torch.float32)[:N].reshape(d.B, d.n)
+    x1 = _flat(plan, d.x1, torch.float32)[:N].reshape(d.B, d.n)
+    z = _flat(plan, d.z_unit, torch.float32)[:N].reshape(d.B, d.n) * torch.tensor(d.d, dtype=torch.float32)
+    gd = (1.4142 * (1 - 2 * _flat(plan, d.tclip, torch.float32)[: d.B]))[:, None]
+    pt = x1 - x0
+    tgt = torch.stack([pt + gd * z, pt, -z])
+    _flat(plan, d.dvs, torch.float32)[: 3 * N] = ((bvs - tgt) / d.B).reshape(-1)
+
+
 _EMU = {nv.QsampleDesc: emu_qsample, nv.SilossDesc: emu_siloss, nv.GemmDesc: emu_gemm, nv.LnDesc: emu_layernorm, nv.AttnDesc: emu_attention, nv.ImgStatsDesc: emu_imgstats,
         nv.PatchifyDesc: emu_patchify, nv.ClsDesc: emu_cls, nv.PackDesc: emu_pack, nv.AffineDesc: emu_affine,
-        nv.TcolDesc: emu_tcol, nv.GnbwdDesc: emu_gnbwd, nv.ColsumDesc: emu_colsum, nv.EwiseDesc: emu_ewise, nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm, nv.MlpDesc: emu_mlp}
+        nv.TcolDesc: emu_tcol, nv.GnbwdDesc: emu_gnbwd, nv.ColsumDesc: emu_colsum, nv.EwiseDesc: emu_ewise, nv.SilossBwdDesc: emu_silossbwd, nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm, nv.MlpDesc: emu_mlp}
 
 
 @torch.no_grad()

@@ -59,7 +59,7 @@ def test_ctypes_structs_match_the_c_header():
              "vt_sde_desc": nv.SdeDesc, "vt_lstm_desc": nv.LstmDesc, "vt_qsample_desc": nv.QsampleDesc,
              "vt_siloss_desc": nv.SilossDesc, "vt_opt_tensor": nv.OptTensor, "vt_adamw_desc": nv.AdamwDesc,
              "vt_mlp_desc": nv.MlpDesc, "vt_tcol_desc": nv.TcolDesc, "vt_gnbwd_desc": nv.GnbwdDesc,
-             "vt_colsum_desc": nv.ColsumDesc, "vt_ewise_desc": nv.EwiseDesc}
+             "vt_colsum_desc": nv.ColsumDesc, "vt_ewise_desc": nv.EwiseDesc, "vt_silossbwd_desc": nv.SilossBwdDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/vt_b200.h"', 'int main(void){']
     probes = []
     for cname, cls in descs.items():
@@ -334,3 +334,23 @@ def test_res_block_backward_plan_reproduces_the_explicit_backward(ci, co):
     plan, check = bwd_cases.res_block_case(torch.device("cpu"), ci, co)
     plan_emu.run(plan)
     check()
+
+
+def test_unet_backward_plan_reproduces_the_explicit_backward():
+    """unet_train: training forward + build_unet_backward + build_film_time_backward of whole U-Nets (146 parameter gradients
+    per net + d global_cond), interpreted on the CPU, against unet_forward_cached / unet_backward of oracle/vt_oracle_bwd.py."""
+    import bwd_cases
+    plan, check = bwd_cases.unet_case(torch.device("cpu"))
+    plan_emu.run(plan)
+    res = check()
+    assert res["missing"] == [] and res["n"] == 148
+
+
+@pytest.mark.parametrize("A,T", [(10, 16), (7, 64)])
+def test_loss_backward_program_reproduces_the_reference_gradients(A, T):
+    """LossBackwardProgram = get_loss(...).backward() of the reference (bridge_model.py:220-246) as one plan, interpreted on the
+    CPU: the reference's own gradient digests (tests/golden/loss_grads_*.npz) and every gradient tensor in full."""
+    import bwd_cases
+    plan, check = bwd_cases.loss_case(torch.device("cpu"), A, T)
+    plan_emu.run(plan)
+    assert check()["tensors"] == 439

@@ -61,3 +61,20 @@ def test_res_block_backward(ci, co):
     plan, check = bwd_cases.res_block_case(DEV, ci, co)
     _run(plan)
     check()
+
+
+def test_unet_backward():
+    """Whole U-Nets: training forward + explicit backward (146 parameter gradients per net, d global_cond) on the B200."""
+    plan, check = bwd_cases.unet_case(DEV)
+    _run(plan)
+    res = check()
+    assert res["missing"] == []
+
+
+@pytest.mark.parametrize("A,T", [(10, 16), (7, 64)])
+def test_get_loss_backward_against_the_reference_gradients(A, T):
+    """get_loss(...).backward() of the reference (bridge_model.py:220-246) as one program on the B200: loss values, d obs_cond,
+    and all 438 parameter gradients of b_net / v_net / s_net against the reference's own digests and in full."""
+    plan, check = bwd_cases.loss_case(DEV, A, T)
+    _run(plan)
+    assert check()["tensors"] == 439

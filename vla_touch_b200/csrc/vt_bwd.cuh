@@ -255,4 +255,24 @@ __global__ void __launch_bounds__(256) ewise_kernel(const float* __restrict__ a,
   }
 }
 
+// d (L_v + L_s + L_b) / d (net outputs), bridge_model.py:183-218 with the batch mean of get_loss (:240-246), nets stacked as
+// [b_net, v_net, s_net]:  d/db = (b - (x1 - x0 + gdot z)) / B,  d/dv = (v - (x1 - x0)) / B,  d/ds = (s + z) / B,  z = d z_unit
+__global__ void __launch_bounds__(256) siloss_bwd_kernel(const float* __restrict__ bvs, const float* __restrict__ x0,
+                                                         const float* __restrict__ x1, const float* __restrict__ z_unit,
+                                                         const float* __restrict__ tclip, float d, int B, int n,
+                                                         float* __restrict__ dvs) {
+  const long long per = (long long)B * n, total = 3 * per;
+  const float inv_b = 1.f / (float)B;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx / per);
+    const long long i = idx - (long long)g * per;
+    const int b = (int)(i / n);
+    const float pt = x1[i] - x0[i];
+    const float z = d * z_unit[i];
+    const float gd = 1.4142f * (1.0f - 2.0f * tclip[b]);
+    const float tgt = g == 0 ? pt + gd * z : (g == 1 ? pt : -z);
+    dvs[idx] = (bvs[idx] - tgt) * inv_b;
+  }
+}
+
 }  // namespace vt

@@ -675,6 +675,15 @@ struct EwiseOp : Op {
   }
 };
 
+struct SilossBwdOp : Op {
+  vt_silossbwd_desc d;
+  int launch(cudaStream_t s) override {
+    vt::siloss_bwd_kernel<<<grid_for(3ll * d.B * d.n, 256), 256, 0, s>>>(d.bvs, d.x0, d.x1, d.z_unit, d.tclip, d.d, d.B, d.n, d.dvs);
+    VT_LAUNCH_CHECK("siloss_bwd_kernel");
+    return VT_OK;
+  }
+};
+
 struct LstmOp : Op {
   vt_lstm_desc d;
   int launch(cudaStream_t s) override {
@@ -946,6 +955,10 @@ VT_SIMPLE_ADD(vt_program_add_ewise, EwiseOp, vt_ewise_desc,
               VT_REQUIRE(d->a && d->b && d->out && d->rows >= 1 && d->cols >= 1 && d->a_ld >= d->cols && d->b_ld >= d->cols &&
                              d->out_ld >= d->cols && (d->op == VT_EW_ADD || d->op == VT_EW_MISH_BWD),
                          "ewise: bad descriptor"))
+
+VT_SIMPLE_ADD(vt_program_add_silossbwd, SilossBwdOp, vt_silossbwd_desc,
+              VT_REQUIRE(d->bvs && d->x0 && d->x1 && d->z_unit && d->tclip && d->dvs && d->B >= 1 && d->n >= 1,
+                         "silossbwd: bad descriptor"))
 
 VT_SIMPLE_ADD(vt_program_add_qsample, QsampleOp, vt_qsample_desc,
               VT_REQUIRE(d->x0 && d->x1 && d->step && d->z_unit && d->xt && d->tclip && d->B >= 1 && d->n >= 1 && d->A >= 1 &&

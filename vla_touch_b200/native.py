@@ -129,6 +129,11 @@ class EwiseDesc(C.Structure):
 EW_ADD, EW_MISH_BWD = 0, 1
 
 
+class SilossBwdDesc(C.Structure):
+    _fields_ = [("bvs", vp), ("x0", vp), ("x1", vp), ("z_unit", vp), ("tclip", vp), ("d", f32), ("B", i32), ("n", i32),
+                ("dvs", vp)]
+
+
 class OptTensor(C.Structure):
     _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("ema", vp), ("numel", i64)]
 
@@ -144,7 +149,7 @@ EXPORTS = [
     "vt_program_num_ops", "vt_program_num_launches", "vt_program_add_gemm", "vt_program_add_layernorm",
     "vt_program_add_attention", "vt_program_add_mlp", "vt_debug_timestamps", "vt_program_add_imgstats", "vt_program_add_patchify", "vt_program_add_cls",
     "vt_program_add_pack", "vt_program_add_affine", "vt_program_add_tembed", "vt_program_add_sde",
-    "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_add_tcol", "vt_program_add_gnbwd", "vt_program_add_colsum", "vt_program_add_ewise", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
+    "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_add_tcol", "vt_program_add_gnbwd", "vt_program_add_colsum", "vt_program_add_ewise", "vt_program_add_silossbwd", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
     "vt_pos_embed_resize", "vt_adamw_ema_step",
 ]
 
@@ -155,6 +160,7 @@ _ADD = {
     SdeDesc: "vt_program_add_sde", LstmDesc: "vt_program_add_lstm", QsampleDesc: "vt_program_add_qsample",
     SilossDesc: "vt_program_add_siloss", TcolDesc: "vt_program_add_tcol", GnbwdDesc: "vt_program_add_gnbwd",
     ColsumDesc: "vt_program_add_colsum", EwiseDesc: "vt_program_add_ewise",
+    SilossBwdDesc: "vt_program_add_silossbwd",
 }
 
 _lib: Optional[C.CDLL] = None

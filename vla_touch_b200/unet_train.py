@@ -206,3 +206,157 @@ def grad_tensor(v: Grad, ref_shape) -> torch.Tensor:
     if taps:
         return ub.unpack_wgrad(buf, ref_shape[1], taps)[:, : ref_shape[0]]
     return buf[:, : ref_shape[0]] if buf.dim() == 2 else buf
+
+
+# ------------------------------------------------------------------------------------------------
+# time embedding + FiLM (diffusion_step_encoder, cond_encoder): training forward keeps the pre-activations
+# ------------------------------------------------------------------------------------------------
+def _pack_rows(plan: Plan, src: torch.Tensor, src_ld: int, rows: int, cols: int, out: torch.Tensor, out_ld: int, dst_c0: int,
+               act: int, tag: str, out_off: int = 0) -> None:
+    d = nv.PackDesc()
+    d.src, d.src_ld, d.rows, d.cols, d.act = ptr(src), src_ld, rows, cols, act
+    d.out, d.out_dtype, d.out_ld, d.dst_c0 = ptr(out, out_off), nv.VT_BF16 if out.dtype == torch.bfloat16 else nv.VT_F32, out_ld, dst_c0
+    d.out_plane, d.zero_to = 0, 0
+    plan.add(d, tag)
+
+
+def build_time_film_train(plan: Plan, W: UnetWeights, t_rows: torch.Tensor, B: int, cond: torch.Tensor, film: torch.Tensor,
+                          tag: str = "film") -> Dict[str, torch.Tensor]:
+    """film[G][B][11264] = cond_encoder(Mish(cat(diffusion_step_encoder(t), cond))) for G nets like unet.build_time_film, but
+    with the Mish inputs t1 = Linear(256 -> 1024)(pe) and gf = cat(temb, cond) kept in fp32 for the backward
+    (conditional_unet_1D.py:186-191, 209-213, 76-80)."""
+    m, G, T_ = W.mode, W.G, W.t
+    kd = DSED + W.cond_dim
+    emb = plan.buf(f"{tag}.emb", (B, DSED), m.tdt)
+    t1 = plan.buf(f"{tag}.t1", (G, B, 4 * DSED), torch.float32)
+    hid = plan.buf(f"{tag}.hid", (G, B, 4 * DSED), m.tdt)
+    gf = plan.buf(f"{tag}.gf", (G, B, kd), torch.float32)
+    mgf = plan.buf(f"{tag}.mgf", (G, B, kd), m.tdt)
+    plan.add(_tembed(t_rows, B, emb, m), f"{tag}.sinusoid")
+    plan.add(linear_desc(a=emb, rows=B, k=DSED, a_ld=DSED, w=T_["time1.w"], n=4 * DSED, n_pad=4 * DSED, w_ld=DSED, out=t1,
+                         ldc=4 * DSED, bias=T_["time1.b"], G=G, a_G=1, out_g=B * 4 * DSED), f"{tag}.time_mlp.0")
+    _pack_rows(plan, t1, 4 * DSED, G * B, 4 * DSED, hid, 4 * DSED, 0, nv.ACT_MISH, f"{tag}.mish(t1)")
+    plan.add(linear_desc(a=hid, rows=B, k=4 * DSED, a_ld=4 * DSED, w=T_["time2.w"], n=DSED, n_pad=DSED, w_ld=4 * DSED, out=gf,
+                         ldc=kd, bias=T_["time2.b"], G=G, a_G=G, a_sG=B * 4 * DSED, out_g=B * kd), f"{tag}.time_mlp.1")
+    for g in range(G):
+        _pack_rows(plan, cond, cond.shape[-1], B, W.cond_dim, gf, kd, DSED, nv.ACT_NONE, f"{tag}.cat(cond).g{g}", out_off=g * B * kd)
+    _pack_rows(plan, gf, kd, G * B, kd, mgf, kd, 0, nv.ACT_MISH, f"{tag}.mish(gf)")
+    plan.add(linear_desc(a=mgf, rows=B, k=kd, a_ld=kd, w=T_["film.w_full"], n=FILM_ROWS, n_pad=FILM_ROWS, w_ld=kd, out=film,
+                         ldc=FILM_ROWS, bias=T_["film.b"], G=G, a_G=G, a_sG=B * kd, out_g=B * FILM_ROWS), f"{tag}.film_gemm")
+    return dict(emb=emb, t1=t1, hid=hid, gf=gf, mgf=mgf)
+
+
+def _ewise(plan: Plan, a, a_ld: int, b, b_ld: int, out: torch.Tensor, rows: int, cols: int, op: int, tag: str) -> None:
+    e = nv.EwiseDesc()
+    e.a, e.a_ld, e.b, e.b_ld, e.out, e.out_ld, e.rows, e.cols, e.op = a, a_ld, b, b_ld, ptr(out), out.shape[-1], rows, cols, op
+    plan.add(e, tag)
+
+
+def build_film_time_backward(plan: Plan, W: UnetWeights, sds: Sequence[SD], tf: Dict[str, torch.Tensor], B: int,
+                             film: torch.Tensor, dfilm: torch.Tensor, grads: Dict[str, Grad], tag: str = "bwd.film") -> Dict[str, torch.Tensor]:
+    """From the d FiLM table of all 12 blocks: gradients of every cond_encoder Linear (one wgrad GEMM for the stacked
+    [11264 x 512] matrix), d Mish(gf) -> d gf, the diffusion_step_encoder MLP, and d global_cond per net
+    (tail of `unet_backward` in oracle/vt_oracle_bwd.py).  Adds the parameter gradients to `grads`; returns {"dcond": [G][B][cond]}."""
+    G, dev = W.G, plan.device
+    kd = DSED + W.cond_dim
+    V = _View
+    # cond_encoder.1 of all blocks: rows [off, off + 2 C) of the stacked matrix
+    dwf = ub.conv_wgrad(plan, W, B, V(dfilm, 1, FILM_ROWS), V(tf["mgf"], 1, kd), tap_off=[0], t_out=1, tag=f"{tag}.cond_encoder.wgrad")
+    dbf = ub.colsum(plan, G, B, dfilm, 1, f"{tag}.cond_encoder.dbias")
+    for pfx, _, co in block_names():
+        off = W.film_off[pfx]
+        grads[pfx + "cond_encoder.1.weight"] = (dwf[:, off: off + 2 * co], 0)
+        grads[pfx + "cond_encoder.1.bias"] = (dbf[:, off: off + 2 * co], 0)
+    # d Mish(gf) = d film @ W_full
+    wt = plan.reg(torch.stack([torch.cat([sd[pfx + "cond_encoder.1.weight"].to(dev).float() for pfx, _, _ in block_names()]).t()
+                               for sd in sds]).to(torch.bfloat16).contiguous())                       # [G][512][11264]
+    dfb = ub.cast_bf16(plan, G, B, dfilm, 1, f"{tag}.dfilm.bf16")
+    dmgf = plan.buf(f"{tag}.dmgf", (G, B, kd), torch.float32)
+    plan.add(linear_desc(a=dfb.t, rows=B, k=FILM_ROWS, a_ld=FILM_ROWS, w=wt, n=kd, n_pad=kd, w_ld=FILM_ROWS, out=dmgf, ldc=kd,
+                         G=G, a_G=G, a_sG=B * FILM_ROWS, out_g=B * kd), f"{tag}.cond_encoder.dgrad")
+    dgf = plan.buf(f"{tag}.dgf", (G, B, kd), torch.float32)
+    _ewise(plan, ptr(dmgf), kd, ptr(tf["gf"]), kd, dgf, G * B, kd, nv.EW_MISH_BWD, f"{tag}.mish'(gf)")
+    dtemb = V(dgf, 1, DSED, c0=0)
+    # diffusion_step_encoder.3: Linear(1024 -> 256)
+    grads["diffusion_step_encoder.3.weight"] = (ub.conv_wgrad(plan, W, B, dtemb, V(tf["hid"], 1, 4 * DSED), tap_off=[0], t_out=1,
+                                                              tag=f"{tag}.time_mlp.1.wgrad"), 0)
+    grads["diffusion_step_encoder.3.bias"] = (ub.colsum(plan, G, B, dtemb, 1, f"{tag}.time_mlp.1.dbias"), 0)
+    w3t = plan.reg(torch.stack([sd["diffusion_step_encoder.3.weight"].to(dev).float().t() for sd in sds]).to(torch.bfloat16).contiguous())
+    dtb = ub.cast_bf16(plan, G, B, dtemb, 1, f"{tag}.dtemb.bf16")
+    dhid = plan.buf(f"{tag}.dhid", (G, B, 4 * DSED), torch.float32)
+    plan.add(linear_desc(a=dtb.t, rows=B, k=DSED, a_ld=DSED, w=w3t, n=4 * DSED, n_pad=4 * DSED, w_ld=DSED, out=dhid, ldc=4 * DSED,
+                         G=G, a_G=G, a_sG=B * DSED, out_g=B * 4 * DSED), f"{tag}.time_mlp.1.dgrad")
+    dt1 = plan.buf(f"{tag}.dt1", (G, B, 4 * DSED), torch.float32)
+    _ewise(plan, ptr(dhid), 4 * DSED, ptr(tf["t1"]), 4 * DSED, dt1, G * B, 4 * DSED, nv.EW_MISH_BWD, f"{tag}.mish'(t1)")
+    # diffusion_step_encoder.1: Linear(256 -> 1024) on the sinusoidal embedding (shared by the nets)
+    grads["diffusion_step_encoder.1.weight"] = (ub.conv_wgrad(plan, W, B, V(dt1, 1, 4 * DSED), V(tf["emb"], 1, DSED, shared=True),
+                                                              tap_off=[0], t_out=1, tag=f"{tag}.time_mlp.0.wgrad"), 0)
+    grads["diffusion_step_encoder.1.bias"] = (ub.colsum(plan, G, B, dt1, 1, f"{tag}.time_mlp.0.dbias"), 0)
+    return dict(dcond=dgf[:, :, DSED:], dgf=dgf)
+
+
+class LossBackwardProgram:
+    """StochasticInterpolants.get_loss(...) and its backward (bridge_model.py:220-257, 183-218; bridge_train.py:315-334) as one
+    program for [b_net, v_net, s_net]:  q_sample -> time embedding / FiLM -> training forward of the three U-Nets -> the three
+    losses -> their derivative -> the explicit backward (build_unet_backward, build_film_time_backward).
+
+    Inputs: x0 (vla_act), x1 (expert_act) [B,T,A], cond [B,cond] (obs_cond), step [B] ~ U(0,1), z_unit [B,T,A] ~ N(0,1).
+    Outputs: .out fp32 [4] = (loss, v_loss, s_loss, b_loss); .grads {'b_net.'/'v_net.'/'s_net.' + reference key: tensor in the
+    reference parameter's layout}; .d_cond [B,cond] = d loss / d obs_cond (summed over the nets: the gradient that trains the
+    state encoder)."""
+    NETS = ("b_net.", "v_net.", "s_net.")
+
+    def __init__(self, sds_bvs: Sequence[SD], action_dim: int, B: int, T: int, beta_max: float, device):
+        assert len(sds_bvs) == 3, "expects [b_net, v_net, s_net]"
+        self.sds = [dict(sd) for sd in sds_bvs]
+        self.W = W = UnetWeights(sds_bvs, action_dim, device, precise=False)
+        self.plan = p = Plan(device)
+        W.register(p)
+        m, A, f32 = W.mode, action_dim, torch.float32
+        self.B, self.T, self.A = B, T, A
+        self.x0, self.x1 = p.buf("in.x0", (B, T, A), f32), p.buf("in.x1", (B, T, A), f32)
+        self.cond = p.buf("in.cond", (B, W.cond_dim), f32)
+        self.step, self.z = p.buf("in.step", (B,), f32), p.buf("in.z_unit", (B, T, A), f32)
+        self.xt, self.tclip = p.buf("xt", (B, T, A), f32), p.buf("tclip", (B,), f32)
+        self.film, self.dfilm = p.buf("film", (3, B, FILM_ROWS), f32), p.buf("dfilm", (3, B, FILM_ROWS), f32)
+        self.tb = tb = UnetTrainBuffers(p, W, B, T)
+        self.per_sample, self.out = p.buf("loss.per_sample", (3, B), f32), p.buf("loss.out", (4,), f32)
+        self.dvs = p.buf("loss.dvs", (3, B, T, A), f32)
+        d = nv.QsampleDesc()
+        d.x0, d.x1, d.step, d.z_unit, d.d = ptr(self.x0), ptr(self.x1), ptr(self.step), ptr(self.z), beta_max
+        d.B, d.n, d.A, d.xt, d.tclip = B, T * A, A, ptr(self.xt), ptr(self.tclip)
+        d.xpad, d.xpad_dtype, d.xpad_ld, d.xpad_plane = ptr(tb.xpad), m.dt, W.cin0, 0
+        p.add(d, "q_sample")
+        self.tf = build_time_film_train(p, W, self.tclip, B, self.cond, self.film)
+        build_unet_train_forward(p, W, tb, self.film)
+        d = nv.SilossDesc()
+        d.bvs, d.x0, d.x1, d.z_unit, d.tclip, d.d = ptr(tb.out), ptr(self.x0), ptr(self.x1), ptr(self.z), ptr(self.tclip), beta_max
+        d.B, d.n, d.per_sample, d.out = B, T * A, ptr(self.per_sample), ptr(self.out)
+        p.add(d, "si_losses")
+        self.n_forward_ops = len(p)
+        d = nv.SilossBwdDesc()
+        d.bvs, d.x0, d.x1, d.z_unit, d.tclip, d.d = ptr(tb.out), ptr(self.x0), ptr(self.x1), ptr(self.z), ptr(self.tclip), beta_max
+        d.B, d.n, d.dvs = B, T * A, ptr(self.dvs)
+        p.add(d, "si_losses.bwd")
+        self._g = build_unet_backward(p, W, self.sds, tb, self.dvs, self.film, self.dfilm)
+        self._x = build_film_time_backward(p, W, self.sds, self.tf, B, self.film, self.dfilm, self._g)
+
+    def set_inputs(self, x0, x1, cond, step, z_unit) -> None:
+        self.x0.copy_(x0); self.x1.copy_(x1); self.cond.copy_(cond); self.step.copy_(step); self.z.copy_(z_unit)
+
+    def run(self) -> torch.Tensor:
+        self.plan.compile().run()
+        return self.out
+
+    @property
+    def grads(self) -> Dict[str, torch.Tensor]:
+        out = {}
+        for key, v in self._g.items():
+            full = grad_tensor(v, self.sds[0][key].shape)
+            for n, pfx in enumerate(self.NETS):
+                out[pfx + key] = full[n].reshape(self.sds[0][key].shape)
+        return out
+
+    @property
+    def d_cond(self) -> torch.Tensor:
+        return self._x["dcond"].sum(dim=0)
