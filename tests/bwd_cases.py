@@ -330,3 +330,61 @@ def loss_case(device, A=7, T=64):
         assert not bad, bad
         return dict(worst=max(worst.values()), tensors=len(worst))
     return lp.plan, check
+
+
+def interpolant(A, T, device, precise=False, beta=0.03):
+    """vla_touch_b200's StochasticInterpolants with the fixture weights (the model the reference gradient digests were made on)."""
+    import vt_testutil as U
+    from vla_touch_b200.bridge.bridge_model import StochasticInterpolants
+    args = {'interpolant_type': 'linear', 'gamma_type': '2^0.5*t(t-1)', 'epsilon_type': '1-t', 'prior_policy': 'vla',
+            'beta_max': beta, 'sde_type': 'vs', 'action_dim': A, 'obs_dim': 256, 'obs_horizon': 1, 'net_type': 'unet1D_si',
+            'pretrain': False, 'context_frames': 2, 'horizon': T}
+    si = StochasticInterpolants(precise=precise)
+    si.load_model(args, device)
+    si.net.load_state_dict(U.net_sd(A, 21))
+    return si
+
+
+def training_step_case(device, A=10, T=16):
+    """The reference training step's autograd contract (bridge_train.py:315-334): loss, info = get_loss(batch);
+    loss.backward() fills .grad of every net parameter and back-propagates into obs_cond; after an in-place parameter update the
+    next call uses the new weights (operand copies are re-packed).  Checked against autograd through the forward oracle."""
+    import vt_testutil as U
+    from oracle import vt_oracle as orc
+    from vla_touch_b200 import synthetic as syn
+    g = U.golden(f"loss_A{A}_T{T}")
+    si = interpolant(A, T, device)
+    si.step_override, si.z_override = torch.as_tensor(g["step"]).to(device), torch.as_tensor(g["z_unit"]).to(device)
+    cond0 = syn.det_normal("loss.cond", (3, 256), 24)
+    exp, vla = syn.det_uniform("loss.exp", (3, T, A), 24, -1.0, 1.0), syn.det_uniform("loss.vla", (3, T, A), 24, -1.0, 1.0)
+
+    def one_step(tol=3e-2):
+        pre = torch.nn.Linear(256, 256, bias=False).to(device)          # stands for the state encoder in front of obs_cond
+        with torch.no_grad():
+            pre.weight.copy_(torch.eye(256))
+        for p in si.net.parameters():
+            p.grad = None
+        loss, info = si.get_loss({"obs_cond": pre(cond0.to(device)), "expert_act": exp.to(device), "vla_act": vla.to(device)}, device)
+        assert loss.requires_grad and not info["v_loss"].requires_grad
+        (2.0 * loss).backward()                                          # a scaled loss: gradients scale with it
+        sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in si.net.state_dict().items()}
+        c = cond0.clone().requires_grad_(True)
+        ref, *_ = orc.bridge_losses(sd, c, exp, vla, torch.as_tensor(g["step"]), torch.as_tensor(g["z_unit"]))
+        (2.0 * ref).backward()
+        assert abs(float(loss) - float(ref)) <= 2e-2 * max(1.0, abs(float(ref)))
+        worst = {"d_cond(through the producer of obs_cond)": _rel(pre.weight.grad.float().cpu(), c.grad.t() @ cond0)}
+        for n, p in si.net.named_parameters():
+            assert p.grad is not None and p.grad.shape == p.shape, n
+            worst[n] = _rel(p.grad.float().cpu(), sd[n].grad)
+        bad = {k: v for k, v in worst.items() if not v <= tol}
+        assert not bad, bad
+        return max(worst.values())
+
+    def check():
+        w1 = one_step()
+        with torch.no_grad():                                            # an "optimizer step": in-place update of every parameter
+            for i, p in enumerate(si.net.parameters()):
+                p.mul_(1.0 + 0.05 * ((i % 3) - 1)).add_(0.01 if p.dim() == 1 else 0.0)
+        w2 = one_step()
+        return dict(first=w1, after_update=w2)
+    return check

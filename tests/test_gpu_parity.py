@@ -270,7 +270,9 @@ def test_get_loss_value(A, T, precise):
     si.step_override, si.z_override = g["step"].to(DEV), g["z_unit"].to(DEV)
     batch = {"obs_cond": syn.det_normal("loss.cond", (3, 256), 24), "expert_act": syn.det_uniform("loss.exp", (3, T, A), 24, -1.0, 1.0),
              "vla_act": syn.det_uniform("loss.vla", (3, T, A), 24, -1.0, 1.0)}
-    loss, info = si.get_loss(batch, DEV)
+    with torch.no_grad():                      # the validation path (_validate, bridge_train.py:380-438): forward program only
+        loss, info = si.get_loss(batch, DEV)
+    assert not loss.requires_grad
     tol = 2e-3 if precise else 5e-2
     for got, key in ((loss, "loss"), (info["v_loss"], "v_loss"), (info["s_loss"], "s_loss"), (info["b_loss"], "b_loss")):
         assert abs(float(got) - float(g[key])) <= tol * max(1.0, abs(float(g[key]))), (key, float(got), float(g[key]))

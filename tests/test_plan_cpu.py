@@ -354,3 +354,22 @@ def test_loss_backward_program_reproduces_the_reference_gradients(A, T):
     plan, check = bwd_cases.loss_case(torch.device("cpu"), A, T)
     plan_emu.run(plan)
     assert check()["tensors"] == 439
+
+
+def test_get_loss_backward_through_autograd(monkeypatch):
+    """StochasticInterpolants.get_loss -> loss.backward() (the reference training step, bridge_train.py:315-334) with the
+    native program replaced by the CPU descriptor interpreter: .grad of all 438 parameters and the gradient reaching the
+    producer of obs_cond, before and after an in-place parameter update (re-packed operand copies)."""
+    import bwd_cases
+    from vla_touch_b200.plan import Plan
+
+    class _Interp:
+        def __init__(self, plan):
+            self.plan = plan
+
+        def run(self, first=0, count=-1):
+            plan_emu.run(self.plan, first, count)
+
+    monkeypatch.setattr(Plan, "compile", lambda self: _Interp(self))
+    res = bwd_cases.training_step_case(torch.device("cpu"))()
+    assert res["first"] <= 3e-2 and res["after_update"] <= 3e-2

@@ -78,3 +78,10 @@ def test_get_loss_backward_against_the_reference_gradients(A, T):
     plan, check = bwd_cases.loss_case(DEV, A, T)
     _run(plan)
     assert check()["tensors"] == 439
+
+
+def test_training_step_autograd_contract():
+    """loss, info = get_loss(batch); loss.backward() on the B200: .grad of all 438 net parameters, the gradient flowing into the
+    producer of obs_cond, and the re-packed operand copies after an in-place parameter update."""
+    res = bwd_cases.training_step_case(DEV)()
+    assert res["first"] <= 3e-2 and res["after_update"] <= 3e-2

@@ -14,6 +14,7 @@ from ..engine import BridgeEngine
 from ..params import sub_state_dict
 from ..schedule import check_model_args
 from ..unet import LossProgram
+from ..unet_train import LossBackwardProgram
 from .networks.conditional_unet_1D_si import InterpolantsConditionalUnet1D
 
 
@@ -120,13 +121,17 @@ class StochasticInterpolants:
             traj.append(eng.x.clone())
         return traj[-1], traj
 
-    @torch.no_grad()
     def get_loss(self, batch_dict, device=None):
-        """Loss VALUE of bridge_model.py:220-246 (v + s + b losses on the live b_net / v_net / s_net weights), computed by
-        one native program.  Forward only: the returned tensors carry no autograd graph (the backward kernels are the next
-        row), so this serves validation / monitoring (`_validate`, bridge_train.py:380-438)."""
+        """bridge_model.py:220-246: (loss, {'v_loss', 's_loss', 'b_loss'}) on the live b_net / v_net / s_net weights.
+
+        With autograd enabled and trainable nets (the training loop, bridge_train.py:315-334) the returned loss is
+        differentiable: one native program computes the three losses AND their gradients (unet_train.LossBackwardProgram:
+        training forward of the three U-Nets, explicit backward on the same tcgen05 GEMM kernel), and `loss.backward()`
+        hands them to the nets' nn.Parameters and, through d loss / d obs_cond, to whatever produced `obs_cond` (the state
+        encoder).  Under torch.no_grad() (`_validate`, bridge_train.py:380-438) only the forward program runs.  bf16 operands
+        in training; `precise=True` controllers train in bf16 as well (the fp32 split-tf32 mode is inference only)."""
         device = device or self.device
-        nobs = batch_dict['obs_cond'].to(device).float().flatten(1)
+        obs = batch_dict['obs_cond'].to(device)
         naction = batch_dict['expert_act'].to(device).float()
         if 'vla_act' in batch_dict:
             prior_action = batch_dict['vla_act'].to(device).float()
@@ -135,11 +140,38 @@ class StochasticInterpolants:
         B, T, A = naction.shape
         step = self.step_override if self.step_override is not None else torch.rand(B, device=device)
         z = self.z_override if self.z_override is not None else torch.randn_like(naction)
+        params = list(self.net.parameters())
+        if torch.is_grad_enabled() and (obs.requires_grad or any(p.requires_grad for p in params)):
+            return self._get_loss_with_grad(obs, prior_action, naction, step, z, params)
+        with torch.no_grad():
+            return self._get_loss_value(obs.float().flatten(1), prior_action, naction, step, z)
+
+    def _net_state_dicts(self):
+        sd = {k: v.detach() for k, v in self.net.state_dict().items()}
+        return [sub_state_dict(sd, "b_net."), sub_state_dict(sd, "v_net."), sub_state_dict(sd, "s_net.")]
+
+    def _get_loss_with_grad(self, obs, x0, x1, step, z, params):
+        B, T, A = x1.shape
+        key = (B, T, "bwd")
+        version = sum(p._version for p in params)
+        ent = self._loss_programs.get(key)
+        if ent is None:
+            ent = [LossBackwardProgram(self._net_state_dicts(), A, B, T, float(self.d), self.device), version]
+            self._loss_programs[key] = ent
+        elif ent[1] != version:
+            ent[0].refresh(self._net_state_dicts())
+            ent[1] = version
+        names = [n for n, _ in self.net.named_parameters()]
+        out = _BridgeLossFn.apply(ent[0], names, x0, x1, step, z, obs.float().flatten(1), *params)
+        return out[0], {'v_loss': out[1].detach(), 's_loss': out[2].detach(), 'b_loss': out[3].detach()}
+
+    def _get_loss_value(self, nobs, prior_action, naction, step, z):
+        device = self.device
+        B, T, A = naction.shape
         key = (B, T)
         version = sum(p._version for p in self.net.parameters())
         ent = self._loss_programs.get(key)
-        sd = self.net.state_dict()
-        sds = [sub_state_dict(sd, "b_net."), sub_state_dict(sd, "v_net."), sub_state_dict(sd, "s_net.")]
+        sds = self._net_state_dicts()
         if ent is None:
             ent = [LossProgram(sds, A, B, T, float(self.d), device, self.precise), version]
             self._loss_programs[key] = ent
@@ -148,3 +180,23 @@ class StochasticInterpolants:
             ent[1] = version
         out = ent[0](prior_action, naction, nobs, step, z).clone()
         return out[0], {'v_loss': out[1], 's_loss': out[2], 'b_loss': out[3]}
+
+
+class _BridgeLossFn(torch.autograd.Function):
+    """loss[4] = (total, v, s, b) with the gradients of the TOTAL computed eagerly by the native program in forward();
+    backward() scales them by the incoming gradient of loss[0] (the three partial losses are reported for logging only,
+    bridge_train.py:318-327, and are returned detached by get_loss)."""
+
+    @staticmethod
+    def forward(ctx, prog, names, x0, x1, step, z, obs, *params):
+        prog.set_inputs(x0, x1, obs, step, z)
+        out = prog.run().clone()
+        g = prog.grads
+        ctx.save_for_backward(prog.d_cond.clone(), *[g[n].clone() for n in names])
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        d_cond, *grads = ctx.saved_tensors
+        s = gout[0]
+        return (None, None, None, None, None, None, s * d_cond) + tuple(s * g for g in grads)

@@ -37,6 +37,31 @@ class DgradCtx:
         self.mode = Mode(precise)
 
 
+class Ws(list):
+    """The same parameter of the G nets (a list of tensors) that remembers its state-dict key, so that the operand copies
+    packed from it at plan-build time can be re-packed after an optimizer step (`repack_all`)."""
+
+    def __init__(self, sds: Sequence[dict], key: str, device):
+        super().__init__(sd[key].detach().to(device) for sd in sds)
+        self.key, self.device = key, device
+
+
+def track(ctx, dest: torch.Tensor, ws, pack) -> torch.Tensor:
+    """Remember how `dest` was packed from the parameter list `ws` (only when the parameters carry their key)."""
+    key = getattr(ws, "key", None)
+    if key is not None:
+        if not hasattr(ctx, "repack"):
+            ctx.repack = []
+        ctx.repack.append((dest, lambda sds, key=key, dev=ws.device: pack(Ws(sds, key, dev))))
+    return dest
+
+
+def repack_all(ctx, sds: Sequence[dict]) -> None:
+    """Re-pack every tracked operand copy from new parameter values into the same device tensors (addresses unchanged)."""
+    for dest, fn in getattr(ctx, "repack", []):
+        dest.copy_(fn(sds))
+
+
 def pack_dgrad_conv(ws: Sequence[torch.Tensor], taps_k: Sequence[int], cout_pad: int, mode: Mode) -> torch.Tensor:
     """Forward Conv1d weights [C_out, C_in, K] of G nets -> dgrad B operand [G][round128(C_in)][len(taps_k) * cout_pad]:
     row ci holds, tap by tap (in the order of taps_k), W[:, ci, k] over the output channels (the GEMM's K dimension)."""
@@ -55,7 +80,8 @@ def conv_dgrad(plan, ctx: DgradCtx, B: int, dy: _View, dx: _View, ws: Sequence[t
     Returns the tensors the plan must keep alive (packed weights, zero bias)."""
     co, ci, K = ws[0].shape
     m = ctx.mode
-    wd = plan.reg(pack_dgrad_conv(ws, range(K), dy.C, m).to(plan.device))
+    pk = lambda w: pack_dgrad_conv(w, range(K), dy.C, m).to(plan.device)
+    wd = track(ctx, plan.reg(pk(ws)), ws, pk)
     zb = plan.reg(torch.zeros(ctx.G, wd.shape[1], dtype=torch.float32, device=plan.device))
     _conv(plan, ctx, B, dy, dx, wd, zb, taps=[(0, pad - k) for k in range(K)], cin_pad=dy.C, n=ci, t_out=dy.T, res=res,
           tag=tag or "conv.dgrad")
@@ -69,7 +95,8 @@ def downsample_dgrad(plan, ctx: DgradCtx, B: int, dy: _View, dx: _View, ws: Sequ
     assert K == 3 and dx.T == 2 * dy.T
     m, keep = ctx.mode, []
     for ph, taps_k, taps in ((0, (1,), [(0, 0)]), (1, (0, 2), [(0, 1), (0, 0)])):
-        wd = plan.reg(pack_dgrad_conv(ws, taps_k, dy.C, m).to(plan.device))
+        pk = lambda w, taps_k=taps_k: pack_dgrad_conv(w, taps_k, dy.C, m).to(plan.device)
+        wd = track(ctx, plan.reg(pk(ws)), ws, pk)
         zb = plan.reg(torch.zeros(ctx.G, wd.shape[1], dtype=torch.float32, device=plan.device))
         _conv(plan, ctx, B, dy, dx, wd, zb, taps=taps, cin_pad=dy.C, n=ci, t_out=dy.T, out_rows=(dx.T, 2, ph, dx.T), res=res,
               tag=(tag or "downsample.dgrad") + f".phase{ph}")
@@ -83,7 +110,8 @@ def upsample_dgrad(plan, ctx: DgradCtx, B: int, dy: _View, dx: _View, ws: Sequen
     ci, co, K = ws[0].shape
     assert K == 4 and dy.T == 2 * dx.T
     m = ctx.mode
-    wd = plan.reg(pack_dgrad_convT(ws, range(K), dy.C, m).to(plan.device))
+    pk = lambda w: pack_dgrad_convT(w, range(K), dy.C, m).to(plan.device)
+    wd = track(ctx, plan.reg(pk(ws)), ws, pk)
     zb = plan.reg(torch.zeros(ctx.G, wd.shape[1], dtype=torch.float32, device=plan.device))
     # dY[2t + k - 1]: k = 0 -> odd phase, index t-1;  k = 1 -> even, t;  k = 2 -> odd, t;  k = 3 -> even, t+1
     _conv(plan, ctx, B, dy, dx, wd, zb, taps=[(1, -1), (0, 0), (1, 0), (0, 1)], cin_pad=dy.C, n=ci, t_out=dx.T, phases=2, res=res,
@@ -182,10 +210,13 @@ def conv_block_backward(plan, ctx: DgradCtx, B: int, x: _View, ws: Sequence[torc
     co, ci, K = ws[0].shape
     m, T = ctx.mode, x.T
     dev = plan.device
-    wf = plan.reg(_pack_conv([w.to(dev) for w in ws], x.C, m))
-    bf = plan.reg(_pack_vec([b.to(dev) for b in bs], wf.shape[1]))
-    gm = plan.reg(_pack_vec([g.to(dev) for g in gammas], co))
-    bt = plan.reg(_pack_vec([b.to(dev) for b in betas], co))
+    pw = lambda w: _pack_conv([t.to(dev) for t in w], x.C, m)
+    wf = track(ctx, plan.reg(pw(ws)), ws, pw)
+    pb = lambda v: _pack_vec([t.to(dev) for t in v], wf.shape[1])
+    pc = lambda v: _pack_vec([t.to(dev) for t in v], co)
+    bf = track(ctx, plan.reg(pb(bs)), bs, pb)
+    gm = track(ctx, plan.reg(pc(gammas)), gammas, pc)
+    bt = track(ctx, plan.reg(pc(betas)), betas, pc)
     raw = plan.buf(tag + f"#{len(plan)}.raw", (ctx.G, B, T, co), torch.float32)
     _conv(plan, ctx, B, x, None, wf, bf, taps=[(0, k - K // 2) for k in range(K)], cin_pad=x.C, n=co, t_out=T, out_f32=raw,
           tag=tag + ".conv_raw(recompute)")
@@ -193,7 +224,7 @@ def conv_block_backward(plan, ctx: DgradCtx, B: int, x: _View, ws: Sequence[torc
     vy = _View(draw, T, co)
     dw = conv_wgrad(plan, ctx, B, vy, x, tap_off=[k - K // 2 for k in range(K)], t_out=T, tag=tag + ".wgrad")
     if dx is not None:                     # the first block's input gradient (d sample) is not needed by training
-        conv_dgrad(plan, ctx, B, vy, dx, [w.to(dev) for w in ws], pad=K // 2, tag=tag + ".dgrad", res=res)
+        conv_dgrad(plan, ctx, B, vy, dx, ws, pad=K // 2, tag=tag + ".dgrad", res=res)
     return dict(dw=dw, dbias=dbias, dgamma=dg, dbeta=db, raw=raw, draw=draw)
 
 
@@ -229,7 +260,7 @@ def res_block_backward(plan, ctx: DgradCtx, B: int, sds: Sequence[dict], pfx: st
     film = (FiLM table, d FiLM table, column offset of this block).  The gradient of the cond_encoder Linear is taken from the
     d FiLM table for all 12 blocks at once by the caller.  Returns {reference parameter key suffix: gradient buffer}."""
     tag = tag or pfx
-    g = lambda k: [sd[pfx + k] for sd in sds]
+    g = lambda k: Ws(sds, pfx + k, plan.device)
     T = x.T
     dout = as_view(dout, T)
     co = dout.C
@@ -245,7 +276,7 @@ def res_block_backward(plan, ctx: DgradCtx, B: int, sds: Sequence[dict], pfx: st
         dob = cast_bf16(plan, ctx.G, B, dout, T, tag + "dout.bf16")
         if dx is not None:
             dxr = plan.buf(tag + f"#{len(plan)}.dxr", (ctx.G, B, T, dx.C), torch.float32)
-            conv_dgrad(plan, ctx, B, dob, _View(dxr, T, dx.C), [w.to(plan.device) for w in wr], pad=0, tag=tag + "residual_conv.dgrad")
+            conv_dgrad(plan, ctx, B, dob, _View(dxr, T, dx.C), wr, pad=0, tag=tag + "residual_conv.dgrad")
             res = _View(dxr, T, dx.C)
         out["residual_conv.weight"] = (conv_wgrad(plan, ctx, B, dob, x, tap_off=[0], t_out=T, tag=tag + "residual_conv.wgrad"), 1)
         out["residual_conv.bias"] = colsum(plan, ctx.G, B, dout, T, tag + "residual_conv.dbias")

@@ -126,7 +126,7 @@ def build_unet_backward(plan: Plan, W: UnetWeights, sds: Sequence[SD], tb: UnetT
     d0, d1, d2 = DOWN_DIMS
     dev = plan.device
     grads: Dict[str, Grad] = {}
-    g = lambda k: [sd[k].to(dev) for sd in sds]
+    g = lambda k: ub.Ws(sds, k, dev)
     f32 = lambda name, t, c: plan.buf(f"{tag}.{name}", (G, B, t, c), torch.float32)
     V = _View
 
@@ -268,8 +268,9 @@ def build_film_time_backward(plan: Plan, W: UnetWeights, sds: Sequence[SD], tf: 
         grads[pfx + "cond_encoder.1.weight"] = (dwf[:, off: off + 2 * co], 0)
         grads[pfx + "cond_encoder.1.bias"] = (dbf[:, off: off + 2 * co], 0)
     # d Mish(gf) = d film @ W_full
-    wt = plan.reg(torch.stack([torch.cat([sd[pfx + "cond_encoder.1.weight"].to(dev).float() for pfx, _, _ in block_names()]).t()
-                               for sd in sds]).to(torch.bfloat16).contiguous())                       # [G][512][11264]
+    pack_wt = lambda sds_: torch.stack([torch.cat([sd[pfx + "cond_encoder.1.weight"].detach().to(dev).float()
+                                                   for pfx, _, _ in block_names()]).t() for sd in sds_]).to(torch.bfloat16).contiguous()
+    wt = plan.reg(pack_wt(sds))                                                                       # [G][512][11264]
     dfb = ub.cast_bf16(plan, G, B, dfilm, 1, f"{tag}.dfilm.bf16")
     dmgf = plan.buf(f"{tag}.dmgf", (G, B, kd), torch.float32)
     plan.add(linear_desc(a=dfb.t, rows=B, k=FILM_ROWS, a_ld=FILM_ROWS, w=wt, n=kd, n_pad=kd, w_ld=FILM_ROWS, out=dmgf, ldc=kd,
@@ -281,7 +282,12 @@ def build_film_time_backward(plan: Plan, W: UnetWeights, sds: Sequence[SD], tf: 
     grads["diffusion_step_encoder.3.weight"] = (ub.conv_wgrad(plan, W, B, dtemb, V(tf["hid"], 1, 4 * DSED), tap_off=[0], t_out=1,
                                                               tag=f"{tag}.time_mlp.1.wgrad"), 0)
     grads["diffusion_step_encoder.3.bias"] = (ub.colsum(plan, G, B, dtemb, 1, f"{tag}.time_mlp.1.dbias"), 0)
-    w3t = plan.reg(torch.stack([sd["diffusion_step_encoder.3.weight"].to(dev).float().t() for sd in sds]).to(torch.bfloat16).contiguous())
+    pack_w3t = lambda sds_: torch.stack([sd["diffusion_step_encoder.3.weight"].detach().to(dev).float().t()
+                                         for sd in sds_]).to(torch.bfloat16).contiguous()
+    w3t = plan.reg(pack_w3t(sds))
+    if not hasattr(W, "repack"):
+        W.repack = []
+    W.repack += [(wt, pack_wt), (w3t, pack_w3t)]
     dtb = ub.cast_bf16(plan, G, B, dtemb, 1, f"{tag}.dtemb.bf16")
     dhid = plan.buf(f"{tag}.dhid", (G, B, 4 * DSED), torch.float32)
     plan.add(linear_desc(a=dtb.t, rows=B, k=DSED, a_ld=DSED, w=w3t, n=4 * DSED, n_pad=4 * DSED, w_ld=DSED, out=dhid, ldc=4 * DSED,
@@ -340,6 +346,13 @@ class LossBackwardProgram:
         p.add(d, "si_losses.bwd")
         self._g = build_unet_backward(p, W, self.sds, tb, self.dvs, self.film, self.dfilm)
         self._x = build_film_time_backward(p, W, self.sds, self.tf, B, self.film, self.dfilm, self._g)
+
+    def refresh(self, sds_bvs: Sequence[SD]) -> None:
+        """New parameter values (after an optimizer step): re-pack the forward operands and every transposed / sliced copy the
+        backward GEMMs read, into the same device tensors."""
+        self.sds = [dict(sd) for sd in sds_bvs]
+        self.W.refresh(sds_bvs)
+        ub.repack_all(self.W, sds_bvs)
 
     def set_inputs(self, x0, x1, cond, step, z_unit) -> None:
         self.x0.copy_(x0); self.x1.copy_(x1); self.cond.copy_(cond); self.step.copy_(step); self.z.copy_(z_unit)
