@@ -246,7 +246,7 @@ def unet_case(device, A=7, T=16, B=2, G=2, seed=31):
     import vt_testutil as U
     from vla_touch_b200 import synthetic as syn
     from vla_touch_b200 import unet_train as ut
-    from vla_touch_b200.unet import FILM_ROWS, UnetWeights, build_time_film, xpad_desc
+    from vla_touch_b200.unet import FILM_ROWS, UnetWeights, xpad_desc
     names = ["b_net", "v_net", "s_net"][:G]
     sds = [{k: (bf(v) if v.dim() >= 2 else v.clone()) for k, v in U.net_sd(A, seed, n).items()} for n in names]
     x = syn.det_uniform("bwd.x", (B, T, A), seed, -1.0, 1.0)
@@ -264,10 +264,10 @@ def unet_case(device, A=7, T=16, B=2, G=2, seed=31):
     dfilm = plan.buf("dfilm", (G, B, FILM_ROWS), torch.float32)
     tb = ut.UnetTrainBuffers(plan, W, B, T)
     plan.add(xpad_desc(W, xb, B * T, tb), "xpad")
-    tf = ut.build_time_film_train(plan, W, tbuf, B, cb, film) if hasattr(ut, "build_time_film_train") else build_time_film(plan, W, tbuf, B, cb, film)
+    tf = ut.build_time_film_train(plan, W, tbuf, B, cb, film)
     ut.build_unet_train_forward(plan, W, tb, film)
     grads = ut.build_unet_backward(plan, W, sds, tb, dvs, film, dfilm)
-    extra = ut.build_film_time_backward(plan, W, sds, tf, B, film, dfilm, grads) if hasattr(ut, "build_film_time_backward") else None
+    extra = ut.build_film_time_backward(plan, W, sds, tf, B, film, dfilm, grads)
 
     def check(tol=4e-2):
         errs = {}
@@ -278,8 +278,7 @@ def unet_case(device, A=7, T=16, B=2, G=2, seed=31):
             for k, v in grads.items():
                 got = ut.grad_tensor(v, ref[k].shape)[n].float().cpu()
                 errs[k] = max(errs.get(k, 0.0), _rel(got.reshape(ref[k].shape), ref[k]))
-            if extra is not None:
-                errs["d_cond"] = max(errs.get("d_cond", 0.0), _rel(extra["dcond"][n].float().cpu(), dcond))
+            errs["d_cond"] = max(errs.get("d_cond", 0.0), _rel(extra["dcond"][n].float().cpu(), dcond))
         missing = set(ref) - set(grads)
         bad = {k: v for k, v in errs.items() if not v <= tol}
         assert not bad, (bad,)
