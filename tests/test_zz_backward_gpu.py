@@ -85,3 +85,25 @@ def test_training_step_autograd_contract():
     producer of obs_cond, and the re-packed operand copies after an in-place parameter update."""
     res = bwd_cases.training_step_case(DEV)()
     assert res["first"] <= 3e-2 and res["after_update"] <= 3e-2
+
+
+def test_differentiable_encode_observation_feeds_the_state_encoder():
+    """encode_observation(differentiable=True) equals the native inference path (bf16 gate) and carries the graph of the
+    state encoder, so that get_loss(...).backward() trains it (bridge_train.py:151,315-334)."""
+    import vt_testutil as U
+    c = U.predict_case("predict_cfg2_B3_dark_varstats")        # 2 ViT layers, batch 3
+    ctl = U.make_controller(c, "cuda:0", precise=False)
+    args = (c["state"].to(DEV), c["img1"], c["img2"], c["forces"].to(DEV))
+    ref = ctl.encode_observation(*args)
+    assert not ref.requires_grad
+    cond = ctl.encode_observation(*args, differentiable=True)
+    assert cond.requires_grad and cond.shape == ref.shape
+    assert float((cond - ref).abs().max()) <= 5e-2 * float(ref.abs().max())
+    si = ctl.diffusion_model
+    T, A = c["T"], c["A"]
+    batch = {"obs_cond": cond, "expert_act": torch.zeros(cond.shape[0], T, A, device=DEV), "vla_act": c["vla"].to(DEV)}
+    loss, _ = si.get_loss(batch, DEV)
+    loss.backward()
+    g = [p.grad for p in ctl.state_encoder.parameters()]
+    assert all(x is not None and torch.isfinite(x).all() for x in g) and float(g[0].abs().max()) > 0
+    assert all(p.grad is not None for p in si.net.parameters())
