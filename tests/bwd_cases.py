@@ -370,7 +370,7 @@ def training_step_case(device, A=10, T=16):
         c = cond0.clone().requires_grad_(True)
         ref, *_ = orc.bridge_losses(sd, c, exp, vla, torch.as_tensor(g["step"]), torch.as_tensor(g["z_unit"]))
         (2.0 * ref).backward()
-        assert abs(float(loss) - float(ref)) <= 2e-2 * max(1.0, abs(float(ref)))
+        assert abs(float(loss.detach()) - float(ref.detach())) <= 2e-2 * max(1.0, abs(float(ref.detach())))
         worst = {"d_cond(through the producer of obs_cond)": _rel(pre.weight.grad.float().cpu(), c.grad.t() @ cond0)}
         for n, p in si.net.named_parameters():
             assert p.grad is not None and p.grad.shape == p.shape, n

@@ -13,10 +13,11 @@ Part 1: the DATA gradients (dgrad) of every convolution as implicit GEMMs that r
 Part 2: the WEIGHT gradients as plain row-major GEMMs on the same kernel (K = B*T positions) over K-major operand copies made
 by `tcol_kernel` (transposed im2col), the fused GroupNorm + Mish (+ FiLM) backward `gn_mish_bwd_kernel` working from the raw
 conv output (which is recomputed with the LINEAR epilogue instead of being saved by the forward pass), bias gradients as
-column sums, and `conv_block_backward`, the backward of one whole Conv1dBlock.  Assembling the 12 residual blocks, the FiLM /
-time-MLP linears and the loss derivatives into the full get_loss backward is the next step; `oracle/vt_oracle_bwd.py` is the
-checker all of it is held to.  The plan builders are host logic: verified on the CPU by interpreting the descriptors
-(tests/test_plan_cpu.py) against that oracle; tests/test_zz_backward_gpu.py runs the same plans on the B200.
+column sums, `conv_block_backward` (one whole Conv1dBlock) and `res_block_backward` (one ConditionalResidualBlock1D).
+`unet_train.py` assembles them with the FiLM / time-MLP linears and the loss derivative into the full get_loss backward;
+`oracle/vt_oracle_bwd.py` is the checker all of it is held to.  The plan builders are host logic: verified on the CPU by
+interpreting the descriptors (tests/test_plan_cpu.py) against that oracle; tests/test_zz_backward_gpu.py runs the same plans
+on the B200 (tests/bwd_cases.py holds the cases both share).
 """
 from __future__ import annotations
 
