@@ -14,7 +14,7 @@ def _rel(got, ref):
     return (got - ref).abs().max().item() / max(ref.abs().max().item(), 1e-12)
 
 
-def wgrad_case(kind: str, device, G=2, B=3, C=256, seed=11):
+def wgrad_case(kind: str, device, G=2, B=3, C=256, seed=11, split_k=None):
     """conv_wgrad for 'k5' (Conv1d k5 p2), 'down' (Conv1d k3 s2 p1), 'up' (ConvTranspose1d k4 s2 p1), 'k1in' (1x1 conv on a
     64-channel padded 7-channel input shared by all nets: the first block's residual_conv)."""
     g = torch.Generator().manual_seed(seed)
@@ -34,13 +34,13 @@ def wgrad_case(kind: str, device, G=2, B=3, C=256, seed=11):
     dy.copy_(torch.randn(G, B, Ty, C, generator=g))
     vx, vy = _View(x, Tx, Cx, shared=shared), _View(dy, Ty, C)
     if kind == "k5":
-        dw = ub.conv_wgrad(plan, ctx, B, vy, vx, tap_off=[k - 2 for k in range(5)], t_out=T)
+        dw = ub.conv_wgrad(plan, ctx, B, vy, vx, tap_off=[k - 2 for k in range(5)], t_out=T, split_k=split_k)
     elif kind == "k1in":
         dw = ub.conv_wgrad(plan, ctx, B, vy, vx, tap_off=[0], t_out=T)
     elif kind == "down":
-        dw = ub.conv_wgrad(plan, ctx, B, vy, vx, tap_off=[k - 1 for k in range(3)], stride=2, t_out=Ty)
+        dw = ub.conv_wgrad(plan, ctx, B, vy, vx, tap_off=[k - 1 for k in range(3)], stride=2, t_out=Ty, split_k=split_k)
     else:
-        dw = ub.conv_wgrad(plan, ctx, B, vx, vy, tap_off=[k - 1 for k in range(4)], stride=2, t_out=Tx)
+        dw = ub.conv_wgrad(plan, ctx, B, vx, vy, tap_off=[k - 1 for k in range(4)], stride=2, t_out=Tx, split_k=split_k)
 
     def check(tol=1e-2):
         for n in range(G):

@@ -411,3 +411,20 @@ def test_training_loop_reduces_the_loss(monkeypatch):
     with torch.no_grad():                                    # validation path on the updated weights (fp32 forward program)
         val, _ = si.get_loss(batch, "cpu")
     assert abs(float(val) - losses[2]) < abs(losses[0] - losses[2]) and float(val) < losses[1]
+
+
+@pytest.mark.parametrize("kind", ["k5", "down", "up"])
+def test_split_k_wgrad_descriptors(kind, monkeypatch):
+    """conv_wgrad(split_k=2): batch slices as extra GEMM groups + one column-sum launch give the same weight gradient; and the
+    whole get_loss backward is unchanged with VT_WGRAD_SPLITK=3 (B = 3: one sample per slice; the shared-input convs stay unsplit)."""
+    import bwd_cases
+    plan, check = bwd_cases.wgrad_case(kind, torch.device("cpu"), B=4, split_k=2)
+    assert sum(isinstance(d, nv.ColsumDesc) for d in plan.descs) == 1
+    plan_emu.run(plan)
+    check()
+    if kind == "k5":
+        monkeypatch.setenv("VT_WGRAD_SPLITK", "3")
+        plan, check = bwd_cases.loss_case(torch.device("cpu"), 10, 16)
+        assert sum(isinstance(d, nv.ColsumDesc) and "splitk" in t for d, t in zip(plan.descs, plan.tags)) >= 30
+        plan_emu.run(plan)
+        assert check()["tensors"] == 439

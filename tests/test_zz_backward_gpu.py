@@ -107,3 +107,10 @@ def test_differentiable_encode_observation_feeds_the_state_encoder():
     g = [p.grad for p in ctl.state_encoder.parameters()]
     assert all(x is not None and torch.isfinite(x).all() for x in g) and float(g[0].abs().max()) > 0
     assert all(p.grad is not None for p in si.net.parameters())
+
+
+@pytest.mark.parametrize("kind", ["k5", "down", "up"])
+def test_split_k_wgrad(kind):
+    plan, check = bwd_cases.wgrad_case(kind, DEV, B=4, split_k=2)
+    _run(plan)
+    check()

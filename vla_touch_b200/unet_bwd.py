@@ -21,6 +21,7 @@ on the B200 (tests/bwd_cases.py holds the cases both share).
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -136,7 +137,7 @@ def _tcol(src: _View, B: int, G: int, out: torch.Tensor, *, tap_off: Sequence[in
 
 
 def conv_wgrad(plan, ctx: DgradCtx, B: int, rows_src: _View, cols_src: _View, *, tap_off: Sequence[int], stride: int = 1,
-               t_out: int, tag: str = "conv.wgrad") -> torch.Tensor:
+               t_out: int, tag: str = "conv.wgrad", split_k: Optional[int] = None) -> torch.Tensor:
     """Weight gradient of a convolution as ONE plain row-major GEMM on the forward kernel (K = B * t_out positions):
 
         dW[g][r][tap * c_pad + c] = sum_{b, t < t_out} rows_src[g][b][t][r] * cols_src[g][b][t * stride + tap_off[tap]][c]
@@ -145,22 +146,35 @@ def conv_wgrad(plan, ctx: DgradCtx, B: int, rows_src: _View, cols_src: _View, *,
     ConvTranspose1d(4,2,1):  rows_src = X,                      cols_src = dY (tap_off[k] = k - 1, stride 2)  -> [C_in][k][C_out]
     (conv1d_bwd / convT1d_bwd of oracle/vt_oracle_bwd.py; conditional_unet_1D.py:22-55).  Both operands are first copied
     into K-major (transposed) bf16 buffers by tcol_kernel.  Returns dW fp32 [G][rows][taps * c_pad]: the forward packing of
-    the weight (`_pack_conv`), so `unpack_wgrad` is a view."""
+    the weight (`_pack_conv`), so `unpack_wgrad` is a view.
+
+    split_k = S > 1 (default: env VT_WGRAD_SPLITK, 1): the batch is cut into S slices that run as S x G GEMM groups (S times the
+    tiles: a 256 -> 256 k5 conv has only 5 x G tile pairs for 148 SMs otherwise) and one column-sum launch adds the partial
+    gradients.  Needs B % S == 0 and per-net (not shared) operands; otherwise it silently stays at 1."""
     G = ctx.G
     assert not ctx.mode.precise, "training runs in the bf16 mode"
-    kp = round_up(B * t_out, 64)
+    S = split_k if split_k is not None else int(os.environ.get("VT_WGRAD_SPLITK", "1"))
+    if S < 1 or B % S != 0 or rows_src.shared or cols_src.shared:
+        S = 1
+    Gs, Bs = G * S, B // S                       # split-K: slice s of net g = samples [s Bs, (s+1) Bs) -> group g S + s
+    kp = round_up(Bs * t_out, 64)
     R, c_pad, taps = rows_src.C, cols_src.C, len(tap_off)
     n = taps * c_pad
     bn = 256 if n % 256 == 0 else 128
     n_pad = round_up(n, bn)
     nm = tag + f"#{len(plan)}"
-    rT = plan.buf(nm + ".rowsT", (G, round_up(R, 128), kp), torch.bfloat16)
-    cT = plan.buf(nm + ".colsT", (G, n_pad, kp), torch.bfloat16)
+    rT = plan.buf(nm + ".rowsT", (Gs, round_up(R, 128), kp), torch.bfloat16)
+    cT = plan.buf(nm + ".colsT", (Gs, n_pad, kp), torch.bfloat16)
     dw = plan.buf(nm + ".dw", (G, R, n), torch.float32)
-    plan.add(_tcol(rows_src, B, G, rT, tap_off=[0], stride=1, t_out=t_out, c_pad=R), tag + ".rowsT")
-    plan.add(_tcol(cols_src, B, G, cT, tap_off=list(tap_off), stride=stride, t_out=t_out, c_pad=c_pad), tag + ".colsT")
-    plan.add(linear_desc(a=rT, rows=R, k=kp, a_ld=kp, w=cT, n=n, n_pad=n_pad, w_ld=kp, out=dw, ldc=n, G=G, a_G=G,
+    part = dw if S == 1 else plan.buf(nm + ".dw_part", (Gs, R, n), torch.float32)
+    plan.add(_tcol(rows_src, Bs, Gs, rT, tap_off=[0], stride=1, t_out=t_out, c_pad=R), tag + ".rowsT")
+    plan.add(_tcol(cols_src, Bs, Gs, cT, tap_off=list(tap_off), stride=stride, t_out=t_out, c_pad=c_pad), tag + ".colsT")
+    plan.add(linear_desc(a=rT, rows=R, k=kp, a_ld=kp, w=cT, n=n, n_pad=n_pad, w_ld=kp, out=part, ldc=n, G=Gs, a_G=Gs,
                          a_sG=rT.shape[1] * kp, out_g=R * n, bn=bn), tag + ".gemm")
+    if S > 1:                                    # dW[g] = sum_s part[g S + s]: a column sum over S rows of R n columns
+        d = nv.ColsumDesc()
+        d.x, d.ld, d.x_g, d.G, d.rows, d.C, d.out, d.out_ld = ptr(part), R * n, S * R * n, G, S, R * n, ptr(dw), R * n
+        plan.add(d, tag + ".splitk_sum")
     return dw
 
 
