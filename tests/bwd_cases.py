@@ -387,3 +387,40 @@ def training_step_case(device, A=10, T=16):
         w2 = one_step()
         return dict(first=w1, after_update=w2)
     return check
+
+
+def batch_additivity_case(device, B=256, T=64, A=7, seed=41):
+    """Size-independent property at the BASELINE batch (no oracle needed): the loss is a batch MEAN of per-sample terms and no
+    statistic crosses samples (GroupNorm is per sample), so the gradients of the full batch equal the mean of the gradients of
+    its two halves, and so do the loss values."""
+    from vla_touch_b200 import shapes as shp
+    from vla_touch_b200 import synthetic as syn
+    from vla_touch_b200.params import sub_state_dict
+    from vla_touch_b200.unet_train import LossBackwardProgram
+    full = syn.synth_state_dict(shp.si_net_shapes(A, 256), seed, prefix="net.")
+    sds = [sub_state_dict(full, p) for p in ("b_net.", "v_net.", "s_net.")]
+    g = torch.Generator().manual_seed(seed)
+    x0, x1 = torch.rand(B, T, A, generator=g) * 2 - 1, torch.rand(B, T, A, generator=g) * 2 - 1
+    cond, step, z = torch.randn(B, 256, generator=g), torch.rand(B, generator=g), torch.randn(B, T, A, generator=g)
+    h = B // 2
+
+    def run(lo, hi):
+        lp = LossBackwardProgram(sds, A, hi - lo, T, 0.03, device)
+        lp.set_inputs(x0[lo:hi], x1[lo:hi], cond[lo:hi], step[lo:hi], z[lo:hi])
+        out = lp.run().clone()
+        return out, {k: v.clone() for k, v in lp.grads.items()}, lp.d_cond.clone()
+
+    def check(tol=3e-2):
+        o, gr, dc = run(0, B)
+        oa, ga, dca = run(0, h)
+        ob_, gb, dcb = run(h, B)
+        assert torch.isfinite(o).all()
+        assert float((o - 0.5 * (oa + ob_)).abs().max()) <= 1e-3 * float(o.abs().max())
+        worst = {"d_cond": _rel(dc.float().cpu(), 0.5 * torch.cat((dca, dcb)).float().cpu())}
+        for k in gr:
+            assert torch.isfinite(gr[k]).all(), k
+            worst[k] = _rel(gr[k].float().cpu(), 0.5 * (ga[k] + gb[k]).float().cpu())
+        bad = {k: v for k, v in worst.items() if not v <= tol}
+        assert not bad, bad
+        return dict(worst=max(worst.values()), tensors=len(worst))
+    return check

@@ -428,3 +428,21 @@ def test_split_k_wgrad_descriptors(kind, monkeypatch):
         assert sum(isinstance(d, nv.ColsumDesc) and "splitk" in t for d, t in zip(plan.descs, plan.tags)) >= 30
         plan_emu.run(plan)
         assert check()["tensors"] == 439
+
+
+def test_backward_is_additive_over_the_batch(monkeypatch):
+    """The size-independent property the full-size GPU test uses (tests/bwd_cases.batch_additivity_case), here at batch 4 on the
+    CPU descriptor interpreter."""
+    import bwd_cases
+    from vla_touch_b200.plan import Plan
+
+    class _Interp:
+        def __init__(self, plan):
+            self.plan = plan
+
+        def run(self, first=0, count=-1):
+            plan_emu.run(self.plan, first, count)
+
+    monkeypatch.setattr(Plan, "compile", lambda self: _Interp(self))
+    res = bwd_cases.batch_additivity_case(torch.device("cpu"), B=4, T=16, A=10)()
+    assert res["tensors"] == 439

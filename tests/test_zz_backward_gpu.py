@@ -114,3 +114,9 @@ def test_split_k_wgrad(kind):
     plan, check = bwd_cases.wgrad_case(kind, DEV, B=4, split_k=2)
     _run(plan)
     check()
+
+
+def test_full_size_backward_is_additive_over_the_batch():
+    """BASELINE batch (256 x T 64 x A 7, three nets): gradients of the full batch == mean of the gradients of its halves."""
+    res = bwd_cases.batch_additivity_case(DEV)()
+    assert res["tensors"] == 439
