@@ -57,3 +57,63 @@ def test_gradient_allreduce_world2_gloo():
 def test_allreduce_is_identity_without_process_group():
     g = [torch.ones(3)]
     assert allreduce_gradients(g) == 1 and torch.equal(g[0], torch.ones(3))
+
+
+def _train_worker(rank, world, port, out):
+    """One data-parallel training step as SURVEY 8e describes it: each rank runs get_loss(...).backward() on its own rows
+    (the native program is replaced by the CPU descriptor interpreter), ONE bucketed SUM all-reduce of the gradients, scale by
+    1 / world.  Result on every rank == the gradients of the un-sharded batch."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path[:0] = [here]
+    import bwd_cases
+    import plan_emu
+    import vt_testutil as U
+    from vla_touch_b200 import synthetic as syn
+    from vla_touch_b200.plan import Plan
+
+    class _Interp:
+        def __init__(self, plan):
+            self.plan = plan
+
+        def run(self, first=0, count=-1):
+            plan_emu.run(self.plan, first, count)
+
+    Plan.compile = lambda self: _Interp(self)
+    torch.set_num_threads(2)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    A, T, B = 10, 16, 4
+    g = torch.Generator().manual_seed(7)
+    x0, x1 = torch.rand(B, T, A, generator=g) * 2 - 1, torch.rand(B, T, A, generator=g) * 2 - 1
+    cond, step, z = torch.randn(B, 256, generator=g), torch.rand(B, generator=g), torch.randn(B, T, A, generator=g)
+
+    def grads_of(rows):
+        si = bwd_cases.interpolant(A, T, torch.device("cpu"))
+        si.step_override, si.z_override = step[rows], z[rows]
+        loss, _ = si.get_loss({"obs_cond": cond[rows], "expert_act": x1[rows], "vla_act": x0[rows]}, "cpu")
+        loss.backward()
+        return [p.grad for p in si.net.parameters()], float(loss.detach())
+
+    per = B // world
+    mine, my_loss = grads_of(slice(rank * per, (rank + 1) * per))
+    w = allreduce_gradients(mine, bucket_elems=8 << 20)
+    for t in mine:
+        t.mul_(1.0 / w)
+    ok = w == world
+    if rank == 0:
+        full, full_loss = grads_of(slice(0, B))
+        worst = max(float((a - b).abs().max()) / max(float(b.abs().max()), 1e-12) for a, b in zip(mine, full))
+        ok = ok and worst <= 3e-2
+        out["worst"] = worst
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_data_parallel_training_step_world2_gloo():
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_train_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        res = dict(out)
+        assert res.get(0) is True and res.get(1) is True, res
