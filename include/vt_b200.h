@@ -379,6 +379,32 @@ typedef struct vt_lstm_desc {
   int32_t B, T, H;
 } vt_lstm_desc;
 
+/* Training forward of one nn.LSTM layer from a zero initial state (lstm_step_controller.py:196-204): like vt_lstm_desc, and keeps
+ * the activated gates and the cell state of every step for the backward pass. */
+typedef struct vt_lstm_train_desc {
+  const float* xw;    /* [B][T][4H] input projections W_ih x + b_ih + b_hh */
+  const float* w_hh;  /* W_hh TRANSPOSED: [H][4H] */
+  void* y;            /* [B][T][y_ld] hidden outputs */
+  int32_t y_dtype;
+  int64_t y_ld;
+  float* gates;       /* [B][T][4H] sigmoid(i), sigmoid(f), tanh(g), sigmoid(o) */
+  float* c;           /* [B][T][H] */
+  int32_t B, T, H;
+} vt_lstm_train_desc;
+
+/* Back-propagation through time of one LSTM layer: the sequential part of what torch autograd runs for nn.LSTM in
+ * lstm_train.py:130 (loss.backward()).  Writes the gradients of the pre-activation gates of all steps; W_ih / W_hh / bias
+ * gradients and d x are GEMMs / column sums over them (vt_tcol_desc + vt_gemm_desc, vt_colsum_desc). */
+typedef struct vt_lstm_bwd_desc {
+  const float* gates; /* [B][T][4H] from vt_lstm_train_desc */
+  const float* c;     /* [B][T][H] */
+  const float* dy;    /* [B][T][dy_ld] gradient of the hidden outputs */
+  int64_t dy_ld;
+  const float* w_hh;  /* W_hh as stored by nn.LSTM: [4H][H] */
+  float* dgates;      /* [B][T][4H] */
+  int32_t B, T, H;
+} vt_lstm_bwd_desc;
+
 /* Fused multi-tensor optimizer step of the bridge trainer (bridge_train.py:330-337 + torch_ema update):
  *   g *= grad_scale (1/world after the gradient all-reduce);  AdamW (torch.optim.AdamW semantics, decoupled weight decay,
  *   bias correction with step t);  EMA shadow s -= (1 - ema_decay) (s - p)  when ema != null.
@@ -436,6 +462,8 @@ int vt_program_add_gnbwd(vt_program* p, const vt_gnbwd_desc* d);
 int vt_program_add_colsum(vt_program* p, const vt_colsum_desc* d);
 int vt_program_add_ewise(vt_program* p, const vt_ewise_desc* d);
 int vt_program_add_silossbwd(vt_program* p, const vt_silossbwd_desc* d);
+int vt_program_add_lstm_train(vt_program* p, const vt_lstm_train_desc* d);
+int vt_program_add_lstm_bwd(vt_program* p, const vt_lstm_bwd_desc* d);
 
 /* Launch ops [first, first+count) in order on `stream` (count < 0: to the end). */
 int vt_program_run(vt_program* p, int first, int count, void* stream);

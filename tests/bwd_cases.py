@@ -424,3 +424,44 @@ def batch_additivity_case(device, B=256, T=64, A=7, seed=41):
         assert not bad, bad
         return dict(worst=max(worst.values()), tensors=len(worst))
     return check
+
+
+def lstm_layers_case(device, B=5, T=12, k_in=138, layers=2, seed=51):
+    """lstm_train.lstm_layers_train (training forward + BPTT of the stacked nn.LSTM layers) against torch.nn.LSTM autograd --
+    the module the reference itself trains (lstm_step_controller.py:66-73)."""
+    from vla_touch_b200 import lstm_train as lt
+    from vla_touch_b200.plan import round_up
+    g = torch.Generator().manual_seed(seed)
+    H = 256
+    ref = torch.nn.LSTM(input_size=k_in, hidden_size=H, num_layers=layers, batch_first=True)
+    with torch.no_grad():
+        for p_ in ref.parameters():
+            p_.copy_(torch.randn(p_.shape, generator=g) * (0.06 if p_.dim() == 2 else 0.1))
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    x = bf(torch.randn(B, T, k_in, generator=g))
+    dy = torch.randn(B, T, H, generator=g)
+    plan = Plan(device)
+    kp = round_up(k_in, 64)
+    xb = plan.buf("x", (B, T, kp), torch.bfloat16)
+    xb[:, :, :k_in] = x.to(device)
+    dyb = plan.buf("dy", (B, T, H), torch.float32)
+    dyb.copy_(dy)
+    lays = lt.lstm_layers_train(plan, xb, k_in, sd, B, T, layers)
+    d = dyb
+    for lay in reversed(lays):
+        d = lay.backward(d)
+        if lay is not lays[0]:
+            d = d[:, :, :H] if d.shape[-1] != H else d
+
+    def check(tol=3e-2):
+        xr = x.clone().requires_grad_(True)
+        y, _ = ref(xr)
+        (y * dy).sum().backward()
+        errs = {"y": _rel(lays[-1].y.float().cpu(), y.detach()), "dx": _rel(lays[0].dx[:, :, :k_in].float().cpu(), xr.grad)}
+        for l, lay in enumerate(lays):
+            for k, v in lay.grads.items():
+                errs[f"{k}_l{l}"] = _rel(v.float().cpu(), getattr(ref, f"{k}_l{l}").grad)
+        bad = {k: v for k, v in errs.items() if not v <= tol}
+        assert not bad, (bad, errs)
+        return errs
+    return plan, check

@@ -399,9 +399,49 @@ def emu_silossbwd(plan, d: nv.SilossBwdDesc):
     _flat(plan, d.dvs, torch.float32)[: 3 * N] = ((bvs - tgt) / d.B).reshape(-1)
 
 
+def emu_lstm_train(plan, d: nv.LstmTrainDesc):
+    H, B, T = d.H, d.B, d.T
+    xw = _flat(plan, d.xw, torch.float32)[: B * T * 4 * H].reshape(B, T, 4 * H)
+    w = _flat(plan, d.w_hh, torch.float32)[: 4 * H * H].reshape(H, 4 * H)     # transposed: [H][4H]
+    gates = _flat(plan, d.gates, torch.float32)[: B * T * 4 * H].reshape(B, T, 4 * H)
+    call = _flat(plan, d.c, torch.float32)[: B * T * H].reshape(B, T, H)
+    hh, cc = torch.zeros(B, H), torch.zeros(B, H)
+    rows = torch.arange(B)
+    for t in range(T):
+        i_, f_, g_, o_ = (xw[:, t] + hh @ w).chunk(4, dim=-1)
+        i_, f_, g_, o_ = torch.sigmoid(i_), torch.sigmoid(f_), torch.tanh(g_), torch.sigmoid(o_)
+        cc = f_ * cc + i_ * g_
+        hh = o_ * torch.tanh(cc)
+        gates[:, t] = torch.cat((i_, f_, g_, o_), dim=-1)
+        call[:, t] = cc
+        _store(plan, d.y, d.y_dtype, (rows[:, None] * T + t) * d.y_ld + torch.arange(H)[None, :], hh, 0)
+
+
+def emu_lstm_bwd(plan, d: nv.LstmBwdDesc):
+    H, B, T = d.H, d.B, d.T
+    gates = _flat(plan, d.gates, torch.float32)[: B * T * 4 * H].reshape(B, T, 4 * H)
+    call = _flat(plan, d.c, torch.float32)[: B * T * H].reshape(B, T, H)
+    dyf = _flat(plan, d.dy, torch.float32)
+    w = _flat(plan, d.w_hh, torch.float32)[: 4 * H * H].reshape(4 * H, H)
+    dg_all = _flat(plan, d.dgates, torch.float32)[: B * T * 4 * H].reshape(B, T, 4 * H)
+    rows = torch.arange(B)
+    dh_next, dc_next = torch.zeros(B, H), torch.zeros(B, H)
+    for t in reversed(range(T)):
+        i_, f_, g_, o_ = gates[:, t].chunk(4, dim=-1)
+        tc = torch.tanh(call[:, t])
+        cp = call[:, t - 1] if t > 0 else torch.zeros(B, H)
+        dy = dyf[((rows[:, None] * T + t) * d.dy_ld + torch.arange(H)[None, :]).reshape(-1)].reshape(B, H)
+        dh = dy + dh_next
+        dc = dc_next + dh * o_ * (1 - tc * tc)
+        dg = torch.cat((dc * g_ * i_ * (1 - i_), dc * cp * f_ * (1 - f_), dc * i_ * (1 - g_ * g_), dh * tc * o_ * (1 - o_)), dim=-1)
+        dg_all[:, t] = dg
+        dh_next = dg @ w
+        dc_next = dc * f_
+
+
 _EMU = {nv.QsampleDesc: emu_qsample, nv.SilossDesc: emu_siloss, nv.GemmDesc: emu_gemm, nv.LnDesc: emu_layernorm, nv.AttnDesc: emu_attention, nv.ImgStatsDesc: emu_imgstats,
         nv.PatchifyDesc: emu_patchify, nv.ClsDesc: emu_cls, nv.PackDesc: emu_pack, nv.AffineDesc: emu_affine,
-        nv.TcolDesc: emu_tcol, nv.GnbwdDesc: emu_gnbwd, nv.ColsumDesc: emu_colsum, nv.EwiseDesc: emu_ewise, nv.SilossBwdDesc: emu_silossbwd, nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm, nv.MlpDesc: emu_mlp}
+        nv.TcolDesc: emu_tcol, nv.GnbwdDesc: emu_gnbwd, nv.ColsumDesc: emu_colsum, nv.EwiseDesc: emu_ewise, nv.SilossBwdDesc: emu_silossbwd, nv.LstmTrainDesc: emu_lstm_train, nv.LstmBwdDesc: emu_lstm_bwd, nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm, nv.MlpDesc: emu_mlp}
 
 
 @torch.no_grad()

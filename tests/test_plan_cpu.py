@@ -59,7 +59,8 @@ def test_ctypes_structs_match_the_c_header():
              "vt_sde_desc": nv.SdeDesc, "vt_lstm_desc": nv.LstmDesc, "vt_qsample_desc": nv.QsampleDesc,
              "vt_siloss_desc": nv.SilossDesc, "vt_opt_tensor": nv.OptTensor, "vt_adamw_desc": nv.AdamwDesc,
              "vt_mlp_desc": nv.MlpDesc, "vt_tcol_desc": nv.TcolDesc, "vt_gnbwd_desc": nv.GnbwdDesc,
-             "vt_colsum_desc": nv.ColsumDesc, "vt_ewise_desc": nv.EwiseDesc, "vt_silossbwd_desc": nv.SilossBwdDesc}
+             "vt_colsum_desc": nv.ColsumDesc, "vt_ewise_desc": nv.EwiseDesc, "vt_silossbwd_desc": nv.SilossBwdDesc, "vt_lstm_train_desc": nv.LstmTrainDesc,
+             "vt_lstm_bwd_desc": nv.LstmBwdDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/vt_b200.h"', 'int main(void){']
     probes = []
     for cname, cls in descs.items():
@@ -446,3 +447,13 @@ def test_backward_is_additive_over_the_batch(monkeypatch):
     monkeypatch.setattr(Plan, "compile", lambda self: _Interp(self))
     res = bwd_cases.batch_additivity_case(torch.device("cpu"), B=4, T=16, A=10)()
     assert res["tensors"] == 439
+
+
+def test_lstm_layers_training_plans_match_nn_lstm_autograd():
+    """lstm_train.lstm_layers_train: training forward (gates and cell states kept) + BPTT of the two stacked LSTM layers as plan
+    ops (recurrence kernels + weight-gradient GEMMs + column sums), interpreted on the CPU, against torch.nn.LSTM autograd."""
+    import bwd_cases
+    plan, check = bwd_cases.lstm_layers_case(torch.device("cpu"))
+    plan_emu.run(plan)
+    errs = check()
+    assert len(errs) == 10

@@ -120,3 +120,12 @@ def test_full_size_backward_is_additive_over_the_batch():
     """BASELINE batch (256 x T 64 x A 7, three nets): gradients of the full batch == mean of the gradients of its halves."""
     res = bwd_cases.batch_additivity_case(DEV)()
     assert res["tensors"] == 439
+
+
+@pytest.mark.xfail(strict=False, reason="lstm_seq_train_kernel / lstm_bwd_kernel were written after the round's GPU budget ended: "
+                                        "compiled for sm_100a and checked on the CPU descriptor interpreter, never run on a B200 yet")
+def test_lstm_layers_bptt():
+    """Stacked nn.LSTM layers: training forward + back-propagation through time against torch.nn.LSTM autograd (CPU)."""
+    plan, check = bwd_cases.lstm_layers_case(DEV)
+    _run(plan)
+    check()

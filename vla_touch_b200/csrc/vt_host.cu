@@ -697,6 +697,26 @@ struct LstmOp : Op {
   }
 };
 
+struct LstmTrainOp : Op {
+  vt_lstm_train_desc d;
+  int launch(cudaStream_t s) override {
+    const int blocks = (d.B + vt::LSTM_ROWS - 1) / vt::LSTM_ROWS;
+    vt::lstm_seq_train_kernel<256><<<blocks, 256, 0, s>>>(d.xw, d.w_hh, d.y, d.y_dtype, d.y_ld, d.gates, d.c, d.B, d.T);
+    VT_LAUNCH_CHECK("lstm_seq_train_kernel");
+    return VT_OK;
+  }
+};
+
+struct LstmBwdOp : Op {
+  vt_lstm_bwd_desc d;
+  int launch(cudaStream_t s) override {
+    const int blocks = (d.B + vt::LSTM_ROWS - 1) / vt::LSTM_ROWS;
+    vt::lstm_bwd_kernel<256><<<blocks, 256, 0, s>>>(d.gates, d.c, d.dy, d.dy_ld, d.w_hh, d.dgates, d.B, d.T);
+    VT_LAUNCH_CHECK("lstm_bwd_kernel");
+    return VT_OK;
+  }
+};
+
 }  // namespace
 
 struct vt_program {
@@ -959,6 +979,13 @@ VT_SIMPLE_ADD(vt_program_add_ewise, EwiseOp, vt_ewise_desc,
 VT_SIMPLE_ADD(vt_program_add_silossbwd, SilossBwdOp, vt_silossbwd_desc,
               VT_REQUIRE(d->bvs && d->x0 && d->x1 && d->z_unit && d->tclip && d->dvs && d->B >= 1 && d->n >= 1,
                          "silossbwd: bad descriptor"))
+
+VT_SIMPLE_ADD(vt_program_add_lstm_train, LstmTrainOp, vt_lstm_train_desc,
+              VT_REQUIRE(d->xw && d->w_hh && d->y && d->gates && d->c && d->B >= 1 && d->T >= 1 && d->H == 256 &&
+                             (d->y_dtype == VT_BF16 || d->y_dtype == VT_F32) && d->y_ld >= d->H, "lstm_train: bad descriptor"))
+VT_SIMPLE_ADD(vt_program_add_lstm_bwd, LstmBwdOp, vt_lstm_bwd_desc,
+              VT_REQUIRE(d->gates && d->c && d->dy && d->w_hh && d->dgates && d->B >= 1 && d->T >= 1 && d->H == 256 &&
+                             d->dy_ld >= d->H, "lstm_bwd: bad descriptor"))
 
 VT_SIMPLE_ADD(vt_program_add_qsample, QsampleOp, vt_qsample_desc,
               VT_REQUIRE(d->x0 && d->x1 && d->step && d->z_unit && d->xt && d->tclip && d->B >= 1 && d->n >= 1 && d->A >= 1 &&

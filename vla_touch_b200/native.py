@@ -134,6 +134,16 @@ class SilossBwdDesc(C.Structure):
                 ("dvs", vp)]
 
 
+class LstmTrainDesc(C.Structure):
+    _fields_ = [("xw", vp), ("w_hh", vp), ("y", vp), ("y_dtype", i32), ("y_ld", i64), ("gates", vp), ("c", vp), ("B", i32),
+                ("T", i32), ("H", i32)]
+
+
+class LstmBwdDesc(C.Structure):
+    _fields_ = [("gates", vp), ("c", vp), ("dy", vp), ("dy_ld", i64), ("w_hh", vp), ("dgates", vp), ("B", i32), ("T", i32),
+                ("H", i32)]
+
+
 class OptTensor(C.Structure):
     _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("ema", vp), ("numel", i64)]
 
@@ -149,7 +159,7 @@ EXPORTS = [
     "vt_program_num_ops", "vt_program_num_launches", "vt_program_add_gemm", "vt_program_add_layernorm",
     "vt_program_add_attention", "vt_program_add_mlp", "vt_debug_timestamps", "vt_program_add_imgstats", "vt_program_add_patchify", "vt_program_add_cls",
     "vt_program_add_pack", "vt_program_add_affine", "vt_program_add_tembed", "vt_program_add_sde",
-    "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_add_tcol", "vt_program_add_gnbwd", "vt_program_add_colsum", "vt_program_add_ewise", "vt_program_add_silossbwd", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
+    "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_add_tcol", "vt_program_add_gnbwd", "vt_program_add_colsum", "vt_program_add_ewise", "vt_program_add_silossbwd", "vt_program_add_lstm_train", "vt_program_add_lstm_bwd", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
     "vt_pos_embed_resize", "vt_adamw_ema_step",
 ]
 
@@ -160,7 +170,7 @@ _ADD = {
     SdeDesc: "vt_program_add_sde", LstmDesc: "vt_program_add_lstm", QsampleDesc: "vt_program_add_qsample",
     SilossDesc: "vt_program_add_siloss", TcolDesc: "vt_program_add_tcol", GnbwdDesc: "vt_program_add_gnbwd",
     ColsumDesc: "vt_program_add_colsum", EwiseDesc: "vt_program_add_ewise",
-    SilossBwdDesc: "vt_program_add_silossbwd",
+    SilossBwdDesc: "vt_program_add_silossbwd", LstmTrainDesc: "vt_program_add_lstm_train", LstmBwdDesc: "vt_program_add_lstm_bwd",
 }
 
 _lib: Optional[C.CDLL] = None
