@@ -338,8 +338,10 @@ typedef struct vt_colsum_desc {
 
 /* Strided fp32 elementwise combine over [rows][cols] windows: VT_EW_ADD out = a + b (gradient fan-in where a skip connection
  * and the main path meet, conditional_unet_1D.py:226-240); VT_EW_MISH_BWD out = a * mish'(b) (backward of the Mish in front of
- * the cond_encoder / diffusion_step_encoder linears, :76-80,186-191). */
-enum { VT_EW_ADD = 0, VT_EW_MISH_BWD = 1 };
+ * the cond_encoder / diffusion_step_encoder linears, :76-80,186-191); VT_EW_GELU_BWD out = a * gelu'(b) (force encoder of the LSTM
+ * controller, lstm_step_controller.py:52-58); VT_EW_MUL out = a * b; VT_EW_SCALED_DIFF out = alpha * (a - b) (derivative of
+ * F.mse_loss, lstm_step_controller.py:335). */
+enum { VT_EW_ADD = 0, VT_EW_MISH_BWD = 1, VT_EW_GELU_BWD = 2, VT_EW_MUL = 3, VT_EW_SCALED_DIFF = 4 };
 typedef struct vt_ewise_desc {
   const float* a;
   int64_t a_ld;
@@ -350,7 +352,23 @@ typedef struct vt_ewise_desc {
   int64_t rows;
   int32_t cols;
   int32_t op;
+  float alpha;
 } vt_ewise_desc;
+
+/* Backward of LayerNorm(256) -> GELU of the LSTM controller's output head (lstm_step_controller.py:76-82) from the saved
+ * LayerNorm input z0:  dz0 = d loss / d z0;  d1 = dzn * gelu'(z1) and d1zh = d1 * zh are stored for the column sums that give
+ * d beta and d gamma. */
+typedef struct vt_lngelubwd_desc {
+  const float* z0;      /* [rows][256] */
+  const float* dzn;     /* [rows][256] gradient of the GELU output */
+  const float* gamma;
+  const float* beta;
+  float eps;
+  float* dz0;           /* [rows][256] */
+  float* d1;            /* [rows][256] */
+  float* d1zh;          /* [rows][256] */
+  int32_t rows, D;      /* D == 256 */
+} vt_lngelubwd_desc;
 
 /* Derivative of the summed loss of vt_siloss_desc with respect to the stacked net outputs (the seed of the backward pass):
  *   dvs[0] = (b - (x1 - x0 + gdot z)) / B,  dvs[1] = (v - (x1 - x0)) / B,  dvs[2] = (s + z) / B     (bridge_model.py:183-246) */
@@ -464,6 +482,7 @@ int vt_program_add_ewise(vt_program* p, const vt_ewise_desc* d);
 int vt_program_add_silossbwd(vt_program* p, const vt_silossbwd_desc* d);
 int vt_program_add_lstm_train(vt_program* p, const vt_lstm_train_desc* d);
 int vt_program_add_lstm_bwd(vt_program* p, const vt_lstm_bwd_desc* d);
+int vt_program_add_lngelubwd(vt_program* p, const vt_lngelubwd_desc* d);
 
 /* Launch ops [first, first+count) in order on `stream` (count < 0: to the end). */
 int vt_program_run(vt_program* p, int first, int count, void* stream);

@@ -465,3 +465,49 @@ def lstm_layers_case(device, B=5, T=12, k_in=138, layers=2, seed=51):
         assert not bad, (bad, errs)
         return errs
     return plan, check
+
+
+def lstm_fixture_inputs(A, Fd, T):
+    """The inputs oracle/gen_golden_grads.py::lstm_grads fed to the reference."""
+    from oracle import vt_oracle as orc
+    from vla_touch_b200 import synthetic as syn
+    st = syn.synth_stats_varied(A, 41)
+    return dict(vla_n=orc.normalize_actions(syn.det_uniform("lstm.vla", (3, T, A), 41, -1.0, 1.0), st, "vla"),
+                forces=syn.det_normal("lstm.forces", (3, T, Fd), 41), cond=syn.det_normal("lstm.cond", (3, 256), 41),
+                expert=syn.det_uniform("lstm.exp", (3, T, A), 41, -1.0, 1.0))
+
+
+def lstm_loss_case(device, A=7, Fd=64, T=32):
+    """lstm_train.LstmLossBackwardProgram against the REFERENCE's own TactileLSTMController.get_loss(...).backward() digests
+    (tests/golden/lstm_grads_*.npz, oracle/gen_golden_grads.py) and, tensor by tensor in full, against the explicit BPTT oracle
+    `lstm_loss_backward` (which tests/test_oracle_golden.py holds to those digests at 1e-4)."""
+    import vt_testutil as U
+    from vla_touch_b200 import shapes as shp
+    from vla_touch_b200 import synthetic as syn
+    from vla_touch_b200.lstm_train import LstmLossBackwardProgram
+    gg = U.golden(f"lstm_grads_A{A}_F{Fd}_T{T}")
+    mods = {"force_encoder": syn.synth_state_dict(shp.mlp_shapes([Fd, 128, 128]), 41, "lstm.force_encoder."),
+            "lstm": syn.synth_state_dict(shp.lstm_shapes(128 + A), 41, "lstm.lstm."),
+            "output_head": syn.synth_state_dict(shp.lstm_head_shapes(256, A), 41, "lstm.output_head.")}
+    inputs = lstm_fixture_inputs(A, Fd, T)
+    B = inputs["vla_n"].shape[0]
+    lp = LstmLossBackwardProgram(mods, A, Fd, B, T, device)
+    lp.set_inputs(inputs["vla_n"], inputs["forces"], inputs["cond"], inputs["expert"])
+
+    def check(tol=3e-2):
+        loss_ref, ref, dcond = ob.lstm_loss_backward(mods, inputs["vla_n"], inputs["cond"], inputs["forces"], inputs["expert"])
+        assert abs(lp.loss() - float(loss_ref)) <= 2e-2 * abs(float(loss_ref)), (lp.loss(), float(loss_ref))
+        assert abs(float(loss_ref) - float(gg["loss"])) <= 1e-4 * abs(float(gg["loss"]))
+        worst = {"d_cond": _rel(lp.d_cond.float().cpu(), dcond), "d_cond(reference)": _rel(lp.d_cond.float().cpu(), torch.as_tensor(gg["d_cond"]))}
+        assert sorted(lp.grads) == sorted(ref), sorted(set(lp.grads) ^ set(ref))
+        for k, v in lp.grads.items():
+            worst[k] = _rel(v.float().cpu().reshape(ref[k].shape), ref[k])
+        names = [str(n) for n in gg["names"]]
+        for i, n in enumerate(names):
+            gr = lp.grads[n].float().cpu().flatten().double()
+            scale = max(float(gg["norm"][i]), 1e-12)
+            worst[n + "(reference norm)"] = abs(float(gr.norm()) - scale) / scale
+        bad = {k: v for k, v in worst.items() if not v <= tol}
+        assert not bad, bad
+        return dict(worst=max(worst.values()), tensors=len(lp.grads))
+    return lp.plan, check

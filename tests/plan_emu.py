@@ -384,7 +384,10 @@ def emu_ewise(plan, d: nv.EwiseDesc):
     a, b, out = (_flat(plan, x, torch.float32) for x in (d.a, d.b, d.out))
     r, c = torch.arange(d.rows)[:, None], torch.arange(d.cols)[None, :]
     x, y = a[(r * d.a_ld + c).reshape(-1)], b[(r * d.b_ld + c).reshape(-1)]
-    out[(r * d.out_ld + c).reshape(-1)] = x + y if d.op == nv.EW_ADD else x * _mish_grad(y)
+    gelu_grad = lambda v: 0.5 * (1 + torch.erf(v / 2 ** 0.5)) + v * torch.exp(-0.5 * v * v) / (2 * math.pi) ** 0.5
+    res = {nv.EW_ADD: lambda: x + y, nv.EW_MISH_BWD: lambda: x * _mish_grad(y), nv.EW_GELU_BWD: lambda: x * gelu_grad(y),
+           nv.EW_MUL: lambda: x * y, nv.EW_SCALED_DIFF: lambda: torch.tensor(d.alpha, dtype=torch.float32) * (x - y)}[d.op]()
+    out[(r * d.out_ld + c).reshape(-1)] = res
 
 
 def emu_silossbwd(plan, d: nv.SilossBwdDesc):
@@ -439,9 +442,25 @@ def emu_lstm_bwd(plan, d: nv.LstmBwdDesc):
         dc_next = dc * f_
 
 
+def emu_lngelubwd(plan, d: nv.LnGeluBwdDesc):
+    n, D = d.rows * d.D, d.D
+    z0 = _flat(plan, d.z0, torch.float32)[:n].reshape(d.rows, D)
+    dzn = _flat(plan, d.dzn, torch.float32)[:n].reshape(d.rows, D)
+    g, b = _flat(plan, d.gamma, torch.float32)[:D], _flat(plan, d.beta, torch.float32)[:D]
+    mu = z0.mean(dim=-1, keepdim=True)
+    rstd = torch.rsqrt(z0.var(dim=-1, unbiased=False, keepdim=True) + d.eps)
+    zh = (z0 - mu) * rstd
+    z1 = zh * g + b
+    d1 = dzn * (0.5 * (1 + torch.erf(z1 / 2 ** 0.5)) + z1 * torch.exp(-0.5 * z1 * z1) / (2 * math.pi) ** 0.5)
+    dzh = d1 * g
+    _flat(plan, d.dz0, torch.float32)[:n] = (rstd * (dzh - dzh.mean(dim=-1, keepdim=True) - zh * (dzh * zh).mean(dim=-1, keepdim=True))).reshape(-1)
+    _flat(plan, d.d1, torch.float32)[:n] = d1.reshape(-1)
+    _flat(plan, d.d1zh, torch.float32)[:n] = (d1 * zh).reshape(-1)
+
+
 _EMU = {nv.QsampleDesc: emu_qsample, nv.SilossDesc: emu_siloss, nv.GemmDesc: emu_gemm, nv.LnDesc: emu_layernorm, nv.AttnDesc: emu_attention, nv.ImgStatsDesc: emu_imgstats,
         nv.PatchifyDesc: emu_patchify, nv.ClsDesc: emu_cls, nv.PackDesc: emu_pack, nv.AffineDesc: emu_affine,
-        nv.TcolDesc: emu_tcol, nv.GnbwdDesc: emu_gnbwd, nv.ColsumDesc: emu_colsum, nv.EwiseDesc: emu_ewise, nv.SilossBwdDesc: emu_silossbwd, nv.LstmTrainDesc: emu_lstm_train, nv.LstmBwdDesc: emu_lstm_bwd, nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm, nv.MlpDesc: emu_mlp}
+        nv.TcolDesc: emu_tcol, nv.GnbwdDesc: emu_gnbwd, nv.ColsumDesc: emu_colsum, nv.EwiseDesc: emu_ewise, nv.SilossBwdDesc: emu_silossbwd, nv.LstmTrainDesc: emu_lstm_train, nv.LstmBwdDesc: emu_lstm_bwd, nv.LnGeluBwdDesc: emu_lngelubwd, nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm, nv.MlpDesc: emu_mlp}
 
 
 @torch.no_grad()

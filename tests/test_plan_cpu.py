@@ -60,7 +60,7 @@ def test_ctypes_structs_match_the_c_header():
              "vt_siloss_desc": nv.SilossDesc, "vt_opt_tensor": nv.OptTensor, "vt_adamw_desc": nv.AdamwDesc,
              "vt_mlp_desc": nv.MlpDesc, "vt_tcol_desc": nv.TcolDesc, "vt_gnbwd_desc": nv.GnbwdDesc,
              "vt_colsum_desc": nv.ColsumDesc, "vt_ewise_desc": nv.EwiseDesc, "vt_silossbwd_desc": nv.SilossBwdDesc, "vt_lstm_train_desc": nv.LstmTrainDesc,
-             "vt_lstm_bwd_desc": nv.LstmBwdDesc}
+             "vt_lstm_bwd_desc": nv.LstmBwdDesc, "vt_lngelubwd_desc": nv.LnGeluBwdDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/vt_b200.h"', 'int main(void){']
     probes = []
     for cname, cls in descs.items():
@@ -457,3 +457,14 @@ def test_lstm_layers_training_plans_match_nn_lstm_autograd():
     plan_emu.run(plan)
     errs = check()
     assert len(errs) == 10
+
+
+@pytest.mark.parametrize("A,Fd,T", [(10, 3, 16), (7, 64, 32)])
+def test_lstm_loss_backward_program_reproduces_the_reference_gradients(A, Fd, T):
+    """lstm_train.LstmLossBackwardProgram = TactileLSTMController.get_loss(...).backward() (lstm_step_controller.py:321-337,
+    eval-equivalent: dropout off) as one plan, interpreted on the CPU: loss, d obs_cond and all 18 parameter gradients against the
+    reference's digests (tests/golden/lstm_grads_*.npz) and the explicit BPTT oracle."""
+    import bwd_cases
+    plan, check = bwd_cases.lstm_loss_case(torch.device("cpu"), A, Fd, T)
+    plan_emu.run(plan)
+    assert check()["tensors"] == 18

@@ -129,3 +129,12 @@ def test_lstm_layers_bptt():
     plan, check = bwd_cases.lstm_layers_case(DEV)
     _run(plan)
     check()
+
+
+@pytest.mark.xfail(strict=False, reason="uses lstm_seq_train_kernel / lstm_bwd_kernel / ln_gelu_bwd_kernel and the new ewise ops, all "
+                                        "written after the round's GPU budget ended: never run on a B200 yet")
+@pytest.mark.parametrize("A,Fd,T", [(10, 3, 16), (7, 64, 32)])
+def test_lstm_get_loss_backward_against_the_reference_gradients(A, Fd, T):
+    plan, check = bwd_cases.lstm_loss_case(DEV, A, Fd, T)
+    _run(plan)
+    assert check()["tensors"] == 18

@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include "vt_ptx.cuh"
+#include "vt_elem.cuh"
 
 namespace vt {
 
@@ -233,11 +234,16 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
   }
 }
 
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * expf(-0.5f * x * x) * 0.3989422804014327f;
+}
+
 // Strided fp32 elementwise combine over [rows][cols] windows:  op 0: out = a + b (gradient fan-in at a skip connection),
-// op 1: out = a * mish'(b) (backward of the Mish in front of the FiLM / time-embedding linears).
+// op 1: out = a * mish'(b) (backward of the Mish in front of the FiLM / time-embedding linears), op 2: out = a * gelu'(b),
+// op 3: out = a * b, op 4: out = alpha * (a - b) (derivative of the MSE loss).
 __global__ void __launch_bounds__(256) ewise_kernel(const float* __restrict__ a, long long a_ld, const float* __restrict__ b,
                                                     long long b_ld, float* __restrict__ out, long long out_ld, long long rows,
-                                                    int cols, int op) {
+                                                    int cols, int op, float alpha) {
   const long long total = rows * cols;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(idx % cols);
@@ -246,13 +252,61 @@ __global__ void __launch_bounds__(256) ewise_kernel(const float* __restrict__ a,
     float v;
     if (op == 0) {
       v = x + y;
-    } else {
+    } else if (op == 1) {
       float m, dm;
       mish_and_grad(y, m, dm);
       v = x * dm;
+    } else if (op == 2) {
+      v = x * gelu_erf_grad(y);
+    } else if (op == 3) {
+      v = x * y;
+    } else {
+      v = alpha * (x - y);
     }
     out[r * out_ld + c] = v;
   }
+}
+
+// Backward of LayerNorm(256) -> GELU (the output head of the LSTM controller, lstm_step_controller.py:76-82) from the saved
+// LayerNorm input: one warp per row, 8 columns per lane.
+//   zh = (z0 - mean) rstd;  z1 = zh gamma + beta;  d1 = dzn gelu'(z1);  dzh = d1 gamma
+//   dz0 = rstd (dzh - mean(dzh) - zh mean(dzh zh));  also stores d1 and d1 zh (their column sums are d beta and d gamma)
+__global__ void __launch_bounds__(256) ln_gelu_bwd_kernel(const float* __restrict__ z0, const float* __restrict__ dzn,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                          float* __restrict__ dz0, float* __restrict__ d1_out,
+                                                          float* __restrict__ d1zh_out, int rows) {
+  constexpr int D = 256, PER = D / 32;
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float x[PER], s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    x[i] = z0[row * D + lane + 32 * i];
+    s += x[i];
+  }
+  const float mean = warp_sum(s) * (1.f / D);
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) v += (x[i] - mean) * (x[i] - mean);
+  const float rstd = rsqrtf(warp_sum(v) * (1.f / D) + eps);
+  float zh[PER], dzh[PER], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = lane + 32 * i;
+    zh[i] = (x[i] - mean) * rstd;
+    const float g = gamma[c];
+    const float d1 = dzn[row * D + c] * gelu_erf_grad(zh[i] * g + beta[c]);
+    d1_out[row * D + c] = d1;
+    d1zh_out[row * D + c] = d1 * zh[i];
+    dzh[i] = d1 * g;
+    s1 += dzh[i];
+    s2 += dzh[i] * zh[i];
+  }
+  s1 = warp_sum(s1) * (1.f / D);
+  s2 = warp_sum(s2) * (1.f / D);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) dz0[row * D + lane + 32 * i] = rstd * (dzh[i] - s1 - zh[i] * s2);
 }
 
 // d (L_v + L_s + L_b) / d (net outputs), bridge_model.py:183-218 with the batch mean of get_loss (:240-246), nets stacked as

@@ -669,7 +669,7 @@ struct ColsumOp : Op {
 struct EwiseOp : Op {
   vt_ewise_desc d;
   int launch(cudaStream_t s) override {
-    vt::ewise_kernel<<<grid_for(d.rows * d.cols, 256), 256, 0, s>>>(d.a, d.a_ld, d.b, d.b_ld, d.out, d.out_ld, d.rows, d.cols, d.op);
+    vt::ewise_kernel<<<grid_for(d.rows * d.cols, 256), 256, 0, s>>>(d.a, d.a_ld, d.b, d.b_ld, d.out, d.out_ld, d.rows, d.cols, d.op, d.alpha);
     VT_LAUNCH_CHECK("ewise_kernel");
     return VT_OK;
   }
@@ -693,6 +693,15 @@ struct LstmOp : Op {
     else
       return fail(VT_E_UNSUPPORTED, "lstm: H=%d", d.H);
     VT_LAUNCH_CHECK("lstm_seq_kernel");
+    return VT_OK;
+  }
+};
+
+struct LnGeluBwdOp : Op {
+  vt_lngelubwd_desc d;
+  int launch(cudaStream_t s) override {
+    vt::ln_gelu_bwd_kernel<<<(d.rows + 7) / 8, 256, 0, s>>>(d.z0, d.dzn, d.gamma, d.beta, d.eps, d.dz0, d.d1, d.d1zh, d.rows);
+    VT_LAUNCH_CHECK("ln_gelu_bwd_kernel");
     return VT_OK;
   }
 };
@@ -973,13 +982,16 @@ VT_SIMPLE_ADD(vt_program_add_colsum, ColsumOp, vt_colsum_desc,
 
 VT_SIMPLE_ADD(vt_program_add_ewise, EwiseOp, vt_ewise_desc,
               VT_REQUIRE(d->a && d->b && d->out && d->rows >= 1 && d->cols >= 1 && d->a_ld >= d->cols && d->b_ld >= d->cols &&
-                             d->out_ld >= d->cols && (d->op == VT_EW_ADD || d->op == VT_EW_MISH_BWD),
+                             d->out_ld >= d->cols && d->op >= VT_EW_ADD && d->op <= VT_EW_SCALED_DIFF,
                          "ewise: bad descriptor"))
 
 VT_SIMPLE_ADD(vt_program_add_silossbwd, SilossBwdOp, vt_silossbwd_desc,
               VT_REQUIRE(d->bvs && d->x0 && d->x1 && d->z_unit && d->tclip && d->dvs && d->B >= 1 && d->n >= 1,
                          "silossbwd: bad descriptor"))
 
+VT_SIMPLE_ADD(vt_program_add_lngelubwd, LnGeluBwdOp, vt_lngelubwd_desc,
+              VT_REQUIRE(d->z0 && d->dzn && d->gamma && d->beta && d->dz0 && d->d1 && d->d1zh && d->rows >= 1 && d->D == 256,
+                         "lngelubwd: bad descriptor (D=%d)", d->D))
 VT_SIMPLE_ADD(vt_program_add_lstm_train, LstmTrainOp, vt_lstm_train_desc,
               VT_REQUIRE(d->xw && d->w_hh && d->y && d->gates && d->c && d->B >= 1 && d->T >= 1 && d->H == 256 &&
                              (d->y_dtype == VT_BF16 || d->y_dtype == VT_F32) && d->y_ld >= d->H, "lstm_train: bad descriptor"))

@@ -1,6 +1,7 @@
 """Training plans of the residual-LSTM controller (row a12 of SURVEY 8, lstm_train.py:70-130: get_loss(...).backward()).
 
-First slice: one nn.LSTM layer (lstm_step_controller.py:66-73,196-204) forward-for-training and back-propagation through time.
+`LstmLayerTrain`: one nn.LSTM layer (lstm_step_controller.py:66-73,196-204) forward-for-training and back-propagation through
+time; `LstmLossBackwardProgram`: the whole controller (force encoder, two layers, output head, MSE) forward + backward.
 
     forward   xw = W_ih x + b_ih + b_hh for all steps (one GEMM)  ->  lstm_seq_train_kernel (recurrence; keeps gates and c)
     backward  lstm_bwd_kernel: the sequential part (d gates of every step; dh_{t-1} = d gates_t W_hh)
@@ -8,9 +9,13 @@ First slice: one nn.LSTM layer (lstm_step_controller.py:66-73,196-204) forward-f
                                                                   h_{t-1} is the hidden output read with tap offset -1)
               d b_ih = d b_hh = column sum of d gates;  d x = d gates W_ih   (one GEMM)
 
-`lstm_loss_backward` of oracle/vt_oracle_bwd.py (pinned to the reference's gradient digests) is the checker.  The head
-(Linear, LayerNorm, GELU, Linear), the force encoder and inter-layer dropout are not built yet.  Written after the round's GPU
-budget ended: the two kernels have been compiled for sm_100a and checked on the CPU descriptor interpreter only.
+              head: ln_gelu_bwd_kernel (LayerNorm + GELU backward from the saved LayerNorm input), linears as dgrad / wgrad
+              GEMMs, d obs_cond = sum over time of the head's input gradient (column sum per sample)
+
+`lstm_loss_backward` of oracle/vt_oracle_bwd.py (pinned to the reference's gradient digests) is the checker.  Eval-equivalent
+training: the reference's Dropout(0.1) (between the LSTM layers and in the head) is not applied yet.  Written after the round's
+GPU budget ended: the new kernels (lstm_seq_train, lstm_bwd, ln_gelu_bwd, ewise ops 2-4) have been compiled for sm_100a and
+checked on the CPU descriptor interpreter only; not wired into TactileLSTMController.get_loss yet.
 """
 from __future__ import annotations
 
@@ -34,7 +39,7 @@ class LstmLayerTrain:
     After `backward(plan, dy)`: self.grads = {weight_ih, weight_hh, bias_ih, bias_hh} and self.dx (fp32 [B][T][k_pad])."""
 
     def __init__(self, plan: Plan, x: torch.Tensor, k_in: int, w_ih: torch.Tensor, w_hh: torch.Tensor, b_ih: torch.Tensor,
-                 b_hh: torch.Tensor, B: int, T: int, tag: str = "lstm.l0"):
+                 b_hh: torch.Tensor, B: int, T: int, tag: str = "lstm.l0", y: Optional[torch.Tensor] = None):
         H, dev, f32, bf = H_LSTM, plan.device, torch.float32, torch.bfloat16
         assert w_hh.shape == (4 * H, H) and x.dtype == bf and x.shape[-1] % 64 == 0
         self.plan, self.x, self.k_in, self.k_pad, self.B, self.T, self.tag = plan, x, k_in, x.shape[-1], B, T, tag
@@ -47,7 +52,8 @@ class LstmLayerTrain:
         self.w_hh_t = plan.reg(w_hh.detach().to(dev, f32).t().contiguous())            # [H][4H]  (forward recurrence)
         R = B * T
         self.xw = plan.buf(f"{tag}.xw", (R, 4 * H), f32)
-        self.y = plan.buf(f"{tag}.y", (B, T, H), bf)
+        self.y = y if y is not None else plan.buf(f"{tag}.y", (B, T, H), bf)      # may be the first H columns of a wider buffer
+        self.y_ld = self.y.shape[-1]
         self.gates = plan.buf(f"{tag}.gates", (B, T, 4 * H), f32)
         self.c = plan.buf(f"{tag}.c", (B, T, H), f32)
         self.grads: Dict[str, torch.Tensor] = {}
@@ -58,7 +64,7 @@ class LstmLayerTrain:
         p.add(linear_desc(a=self.x, rows=R, k=self.k_pad, a_ld=self.k_pad, w=self.w_ih, n=4 * H, n_pad=4 * H, w_ld=self.k_pad,
                           out=self.xw, ldc=4 * H, bias=self.b_sum), f"{self.tag}.input_proj")
         d = nv.LstmTrainDesc()
-        d.xw, d.w_hh, d.y, d.y_dtype, d.y_ld = ptr(self.xw), ptr(self.w_hh_t), ptr(self.y), nv.VT_BF16, H
+        d.xw, d.w_hh, d.y, d.y_dtype, d.y_ld = ptr(self.xw), ptr(self.w_hh_t), ptr(self.y), nv.VT_BF16, self.y_ld
         d.gates, d.c, d.B, d.T, d.H = ptr(self.gates), ptr(self.c), self.B, self.T, H
         p.add(d, f"{self.tag}.recurrence(train)")
         return self.y
@@ -77,7 +83,7 @@ class LstmLayerTrain:
         dgv = V(dg.view(1, B, T, 4 * H), T, 4 * H)                                     # fp32 source: tcol converts to bf16
         dw_ih = ub.conv_wgrad(p, ctx, B, dgv, V(self.x.view(1, B, T, self.k_pad), T, self.k_pad), tap_off=[0], t_out=T,
                               tag=f"{tag}.weight_ih.wgrad")
-        dw_hh = ub.conv_wgrad(p, ctx, B, dgv, V(self.y.view(1, B, T, H), T, H), tap_off=[-1], t_out=T,
+        dw_hh = ub.conv_wgrad(p, ctx, B, dgv, V(self.y.view(1, B, T, self.y_ld), T, H), tap_off=[-1], t_out=T,
                               tag=f"{tag}.weight_hh.wgrad")                            # h_{t-1}: zero at t = 0
         db = ub.colsum(p, 1, B, dgv, T, f"{tag}.bias.colsum")
         self.grads = {"weight_ih": dw_ih[0, :, : self.k_in], "weight_hh": dw_hh[0], "bias_ih": db[0], "bias_hh": db[0]}
@@ -90,14 +96,163 @@ class LstmLayerTrain:
 
 
 def lstm_layers_train(plan: Plan, x: torch.Tensor, k_in: int, lstm_sd: Dict[str, torch.Tensor], B: int, T: int,
-                      num_layers: int = 2) -> Sequence[LstmLayerTrain]:
+                      num_layers: int = 2, last_y: Optional[torch.Tensor] = None) -> Sequence[LstmLayerTrain]:
     """The stacked layers of nn.LSTM(num_layers) in eval-equivalent training (no inter-layer dropout yet): forward ops of all
     layers are appended to `plan`; call `.backward(dy)` on them in reverse order."""
     layers = []
     for l in range(num_layers):
         lay = LstmLayerTrain(plan, x, k_in, lstm_sd[f"weight_ih_l{l}"], lstm_sd[f"weight_hh_l{l}"], lstm_sd[f"bias_ih_l{l}"],
-                             lstm_sd[f"bias_hh_l{l}"], B, T, tag=f"lstm.l{l}")
+                             lstm_sd[f"bias_hh_l{l}"], B, T, tag=f"lstm.l{l}", y=last_y if l == num_layers - 1 else None)
         x = lay.forward()
         k_in = H_LSTM
         layers.append(lay)
     return layers
+
+
+# ------------------------------------------------------------------------------------------------
+# the whole controller: force encoder -> LSTM -> output head -> MSE loss, forward + backward as one program
+# ------------------------------------------------------------------------------------------------
+def _lin_w(plan: Plan, w: torch.Tensor, k_pad: int, transpose: bool = False) -> torch.Tensor:
+    """nn.Linear weight [N, K] -> bf16 operand [N][k_pad] (zero padded), or its transpose [K][n_pad64] for the d-input GEMM."""
+    w = w.detach().to(plan.device, torch.float32)
+    if transpose:
+        w = w.t()
+    out = torch.zeros(w.shape[0], k_pad, device=plan.device)
+    out[:, : w.shape[1]] = w
+    return plan.reg(out.to(torch.bfloat16).contiguous())
+
+
+def _vec(plan: Plan, v: torch.Tensor) -> torch.Tensor:
+    return plan.reg(v.detach().to(plan.device, torch.float32).contiguous())
+
+
+def _pack(plan: Plan, src: torch.Tensor, src_ld: int, rows: int, cols: int, out: torch.Tensor, out_ld: int, dst_c0: int, act: int,
+          tag: str, zero_to: int = 0, src_row_div: int = 0) -> None:
+    d = nv.PackDesc()
+    d.src, d.src_ld, d.rows, d.cols, d.act = ptr(src), src_ld, rows, cols, act
+    d.out, d.out_dtype, d.out_ld, d.dst_c0 = ptr(out), nv.VT_BF16 if out.dtype == torch.bfloat16 else nv.VT_F32, out_ld, dst_c0
+    d.out_plane, d.zero_to, d.src_row_div = 0, zero_to, src_row_div
+    plan.add(d, tag)
+
+
+def _ew(plan: Plan, a, a_ld: int, b, b_ld: int, out: torch.Tensor, rows: int, cols: int, op: int, tag: str, alpha: float = 0.0):
+    e = nv.EwiseDesc()
+    e.a, e.a_ld, e.b, e.b_ld, e.out, e.out_ld, e.rows, e.cols, e.op, e.alpha = a, a_ld, b, b_ld, ptr(out), out.shape[-1], rows, cols, op, alpha
+    plan.add(e, tag)
+
+
+class LstmLossBackwardProgram:
+    """TactileLSTMController.get_loss(...) and its backward (lstm_step_controller.py:170-204, 321-337; lstm_train.py:120-130) as
+    one program, in eval-equivalent training (dropout off, like `lstm_loss_backward` of oracle/vt_oracle_bwd.py):
+
+        forces -> Linear(F,128) GELU Linear(128,128) -> cat(., vla_n) -> LSTM x 2 -> cat(., obs_cond) -> Linear(512,256)
+               -> LayerNorm -> GELU -> Linear(256,A) = delta;  out = vla_n + delta;  loss = mean((out - expert)^2)
+
+    Inputs: vla (normalised) [B,T,A], forces [B,T,F], cond [B,256], expert [B,T,A].  Outputs: .loss() (python float),
+    .grads {'force_encoder.0.weight', ..., 'lstm.weight_hh_l1', ..., 'output_head.4.bias'} (18 tensors), .d_cond [B,256]."""
+
+    def __init__(self, mods: Dict[str, Dict[str, torch.Tensor]], A: int, Fd: int, B: int, T: int, device):
+        self.plan = p = Plan(device)
+        H, R, f32, bf = H_LSTM, B * T, torch.float32, torch.bfloat16
+        self.A, self.B, self.T = A, B, T
+        fe, head = mods["force_encoder"], mods["output_head"]
+        V = _View
+        ctx = ub.DgradCtx(1, precise=False)
+        r64 = lambda n: (n + 63) // 64 * 64
+        fpad, apad, kin = r64(Fd), r64(A), H // 2 + A
+        kin_pad = r64(kin)
+        self.vla, self.expert = p.buf("in.vla", (B, T, A), f32), p.buf("in.expert", (B, T, A), f32)
+        self.forces, self.cond = p.buf("in.forces", (B, T, Fd), f32), p.buf("in.cond", (B, H), f32)
+        # ---------------- forward ----------------
+        f_op = p.buf("f_op", (R, fpad), bf)
+        _pack(p, self.forces, Fd, R, Fd, f_op, fpad, 0, nv.ACT_NONE, "lstm.force->operand", zero_to=fpad)
+        a1 = p.buf("fe.a1", (R, H // 2), f32)
+        p.add(linear_desc(a=f_op, rows=R, k=fpad, a_ld=fpad, w=_lin_w(p, fe["0.weight"], fpad), n=H // 2, n_pad=H // 2, w_ld=fpad,
+                          out=a1, ldc=H // 2, bias=_vec(p, fe["0.bias"])), "force_encoder.0")
+        g1 = p.buf("fe.g1", (R, H // 2), bf)
+        _pack(p, a1, H // 2, R, H // 2, g1, H // 2, 0, nv.ACT_GELU, "force_encoder.gelu")
+        lin = p.buf("lstm_in", (B, T, kin_pad), bf)
+        p.add(linear_desc(a=g1, rows=R, k=H // 2, a_ld=H // 2, w=_lin_w(p, fe["2.weight"], H // 2), n=H // 2, n_pad=H // 2,
+                          w_ld=H // 2, out=lin, ldc=kin_pad, bias=_vec(p, fe["2.bias"])), "force_encoder.2 -> lstm_in[:, :128]")
+        _pack(p, self.vla, A, R, A, lin, kin_pad, H // 2, nv.ACT_NONE, "lstm.cat.vla")
+        head_in = p.buf("head_in", (B, T, 2 * H), bf)                                # cat(lstm_out, obs_cond broadcast over T)
+        self.layers = lstm_layers_train(p, lin, kin, mods["lstm"], B, T, 2, last_y=head_in)
+        _pack(p, self.cond, H, R, H, head_in, 2 * H, H, nv.ACT_NONE, "lstm.cat.obs_cond", src_row_div=T)
+        w0 = head["0.weight"]
+        z0 = p.buf("head.z0", (R, H), f32)
+        p.add(linear_desc(a=head_in, rows=R, k=2 * H, a_ld=2 * H, w=_lin_w(p, w0, 2 * H), n=H, n_pad=H, w_ld=2 * H, out=z0, ldc=H,
+                          bias=_vec(p, head["0.bias"])), "output_head.0")
+        zn = p.buf("head.zn", (R, H), bf)
+        ln_w, ln_b = _vec(p, head["1.weight"]), _vec(p, head["1.bias"])
+        d = nv.LnDesc()
+        d.x, d.in_ld, d.in_row_stride, d.rows, d.D, d.gamma, d.beta, d.eps = ptr(z0), H, 1, R, H, ptr(ln_w), ptr(ln_b), 1e-5
+        d.out, d.out_dtype, d.out_ld, d.out_plane, d.act = ptr(zn), nv.VT_BF16, H, 0, nv.ACT_GELU
+        p.add(d, "output_head.layernorm+gelu")
+        self.out = p.buf("out", (R, A), f32)
+        p.add(linear_desc(a=zn, rows=R, k=H, a_ld=H, w=_lin_w(p, head["4.weight"], H), n=A, n_pad=A, w_ld=H, out=self.out, ldc=A,
+                          bias=_vec(p, head["4.bias"]), res=self.vla, ldres=A), "output_head.4 + vla (residual)")
+        # ---------------- loss and its derivative ----------------
+        dout = p.buf("dout", (R, A), f32)
+        _ew(p, ptr(self.out), A, ptr(self.expert), A, dout, R, A, nv.EW_SCALED_DIFF, "mse.bwd", alpha=2.0 / (R * A))
+        sq = p.buf("loss.sq", (R, A), f32)
+        _ew(p, ptr(dout), A, ptr(dout), A, sq, R, A, nv.EW_MUL, "mse.square")
+        self._sq_sum = ub.colsum(p, 1, 1, sq.view(1, 1, R, A), R, "mse.colsum")
+        self.n_forward_ops = len(p)
+        # ---------------- backward ----------------
+        g: Dict[str, torch.Tensor] = {}
+        dv = V(dout.view(1, B, T, A), T, A)
+        g["output_head.4.weight"] = ub.conv_wgrad(p, ctx, B, dv, V(zn.view(1, B, T, H), T, H), tap_off=[0], t_out=T, tag="head.4.wgrad")[0]
+        g["output_head.4.bias"] = ub.colsum(p, 1, B, dv, T, "head.4.dbias")[0]
+        dob = ub.cast_bf16(p, 1, B, dv, T, "dout.bf16", c_pad=apad)
+        dzn = p.buf("head.dzn", (R, H), f32)
+        p.add(linear_desc(a=dob.t, rows=R, k=apad, a_ld=apad, w=_lin_w(p, head["4.weight"], apad, transpose=True), n=H, n_pad=H,
+                          w_ld=apad, out=dzn, ldc=H), "head.4.dgrad")
+        dz0, d1, d1zh = (p.buf(f"head.{n}", (R, H), f32) for n in ("dz0", "d1", "d1zh"))
+        d = nv.LnGeluBwdDesc()
+        d.z0, d.dzn, d.gamma, d.beta, d.eps, d.dz0, d.d1, d.d1zh, d.rows, d.D = ptr(z0), ptr(dzn), ptr(ln_w), ptr(ln_b), 1e-5, ptr(dz0), ptr(d1), ptr(d1zh), R, H
+        p.add(d, "head.layernorm+gelu.bwd")
+        g["output_head.1.weight"] = ub.colsum(p, 1, B, d1zh.view(1, B, T, H), T, "head.ln.dgamma")[0]
+        g["output_head.1.bias"] = ub.colsum(p, 1, B, d1.view(1, B, T, H), T, "head.ln.dbeta")[0]
+        dz0v = V(dz0.view(1, B, T, H), T, H)
+        g["output_head.0.weight"] = ub.conv_wgrad(p, ctx, B, dz0v, V(head_in.view(1, B, T, 2 * H), T, 2 * H), tap_off=[0], t_out=T,
+                                                  tag="head.0.wgrad")[0]
+        g["output_head.0.bias"] = ub.colsum(p, 1, B, dz0v, T, "head.0.dbias")[0]
+        dz0b = ub.cast_bf16(p, 1, B, dz0v, T, "dz0.bf16")
+        dcomb = p.buf("head.dcomb", (R, 2 * H), f32)
+        p.add(linear_desc(a=dz0b.t, rows=R, k=H, a_ld=H, w=_lin_w(p, w0, H, transpose=True), n=2 * H, n_pad=2 * H, w_ld=H, out=dcomb,
+                          ldc=2 * H), "head.0.dgrad")
+        self.d_cond = p.buf("d_cond", (B, H), f32)
+        cs = nv.ColsumDesc()
+        cs.x, cs.ld, cs.x_g, cs.G, cs.rows, cs.C, cs.out, cs.out_ld = ptr(dcomb, H), 2 * H, T * 2 * H, B, T, H, ptr(self.d_cond), H
+        p.add(cs, "d_cond = sum_t dcomb[:, t, H:]")
+        dx1 = self.layers[1].backward(dcomb.view(B, T, 2 * H))                       # reads columns [0, H) with row stride 2H
+        dx0 = self.layers[0].backward(dx1)
+        for l, lay in enumerate(self.layers):
+            for k, v in lay.grads.items():
+                g[f"lstm.{k}_l{l}"] = v
+        dfv = V(dx0.view(1, B, T, kin_pad), T, H // 2)                               # d fenc = first 128 columns of d lstm_in
+        g["force_encoder.2.weight"] = ub.conv_wgrad(p, ctx, B, dfv, V(g1.view(1, B, T, H // 2), T, H // 2), tap_off=[0], t_out=T,
+                                                    tag="fe.2.wgrad")[0]
+        g["force_encoder.2.bias"] = ub.colsum(p, 1, B, dfv, T, "fe.2.dbias")[0]
+        dfb = ub.cast_bf16(p, 1, B, dfv, T, "dfenc.bf16")
+        dg1 = p.buf("fe.dg1", (R, H // 2), f32)
+        p.add(linear_desc(a=dfb.t, rows=R, k=H // 2, a_ld=H // 2, w=_lin_w(p, fe["2.weight"], H // 2, transpose=True), n=H // 2,
+                          n_pad=H // 2, w_ld=H // 2, out=dg1, ldc=H // 2), "fe.2.dgrad")
+        da1 = p.buf("fe.da1", (R, H // 2), f32)
+        _ew(p, ptr(dg1), H // 2, ptr(a1), H // 2, da1, R, H // 2, nv.EW_GELU_BWD, "fe.gelu.bwd")
+        da1v = V(da1.view(1, B, T, H // 2), T, H // 2)
+        g["force_encoder.0.weight"] = ub.conv_wgrad(p, ctx, B, da1v, V(f_op.view(1, B, T, fpad), T, fpad), tap_off=[0], t_out=T,
+                                                    tag="fe.0.wgrad")[0][:, :Fd]
+        g["force_encoder.0.bias"] = ub.colsum(p, 1, B, da1v, T, "fe.0.dbias")[0]
+        self.grads = g
+
+    def set_inputs(self, vla_n, forces, cond, expert) -> None:
+        self.vla.copy_(vla_n); self.forces.copy_(forces); self.cond.copy_(cond); self.expert.copy_(expert)
+
+    def run(self) -> None:
+        self.plan.compile().run()
+
+    def loss(self) -> float:
+        """mean((out - expert)^2) from the squared loss derivative: sum(dout^2) * numel / 4"""
+        n = self.B * self.T * self.A
+        return float(self._sq_sum.sum()) * n / 4.0

@@ -123,10 +123,15 @@ class ColsumDesc(C.Structure):
 
 class EwiseDesc(C.Structure):
     _fields_ = [("a", vp), ("a_ld", i64), ("b", vp), ("b_ld", i64), ("out", vp), ("out_ld", i64), ("rows", i64), ("cols", i32),
-                ("op", i32)]
+                ("op", i32), ("alpha", f32)]
 
 
-EW_ADD, EW_MISH_BWD = 0, 1
+EW_ADD, EW_MISH_BWD, EW_GELU_BWD, EW_MUL, EW_SCALED_DIFF = 0, 1, 2, 3, 4
+
+
+class LnGeluBwdDesc(C.Structure):
+    _fields_ = [("z0", vp), ("dzn", vp), ("gamma", vp), ("beta", vp), ("eps", f32), ("dz0", vp), ("d1", vp), ("d1zh", vp),
+                ("rows", i32), ("D", i32)]
 
 
 class SilossBwdDesc(C.Structure):
@@ -159,7 +164,7 @@ EXPORTS = [
     "vt_program_num_ops", "vt_program_num_launches", "vt_program_add_gemm", "vt_program_add_layernorm",
     "vt_program_add_attention", "vt_program_add_mlp", "vt_debug_timestamps", "vt_program_add_imgstats", "vt_program_add_patchify", "vt_program_add_cls",
     "vt_program_add_pack", "vt_program_add_affine", "vt_program_add_tembed", "vt_program_add_sde",
-    "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_add_tcol", "vt_program_add_gnbwd", "vt_program_add_colsum", "vt_program_add_ewise", "vt_program_add_silossbwd", "vt_program_add_lstm_train", "vt_program_add_lstm_bwd", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
+    "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_add_tcol", "vt_program_add_gnbwd", "vt_program_add_colsum", "vt_program_add_ewise", "vt_program_add_silossbwd", "vt_program_add_lstm_train", "vt_program_add_lstm_bwd", "vt_program_add_lngelubwd", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
     "vt_pos_embed_resize", "vt_adamw_ema_step",
 ]
 
@@ -171,6 +176,7 @@ _ADD = {
     SilossDesc: "vt_program_add_siloss", TcolDesc: "vt_program_add_tcol", GnbwdDesc: "vt_program_add_gnbwd",
     ColsumDesc: "vt_program_add_colsum", EwiseDesc: "vt_program_add_ewise",
     SilossBwdDesc: "vt_program_add_silossbwd", LstmTrainDesc: "vt_program_add_lstm_train", LstmBwdDesc: "vt_program_add_lstm_bwd",
+    LnGeluBwdDesc: "vt_program_add_lngelubwd",
 }
 
 _lib: Optional[C.CDLL] = None
