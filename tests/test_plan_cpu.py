@@ -468,3 +468,58 @@ def test_lstm_loss_backward_program_reproduces_the_reference_gradients(A, Fd, T)
     plan, check = bwd_cases.lstm_loss_case(torch.device("cpu"), A, Fd, T)
     plan_emu.run(plan)
     assert check()["tensors"] == 18
+
+
+def test_lstm_get_loss_backward_through_autograd(monkeypatch):
+    """TactileLSTMController.get_loss(batch, differentiable=True) -> loss.backward() (lstm_train.py:120-130) with the native
+    program replaced by the CPU descriptor interpreter: .grad of the 18 parameters and of obs_cond against the explicit BPTT
+    oracle, before and after an in-place parameter update (operands re-packed into the same tensors)."""
+    import bwd_cases
+    import torch.nn as nn
+    from oracle import vt_oracle_bwd as ob
+    from vla_touch_b200.lstm_step_controller import TactileLSTMController
+    from vla_touch_b200.plan import Plan
+
+    class _Interp:
+        def __init__(self, plan):
+            self.plan = plan
+
+        def run(self, first=0, count=-1):
+            plan_emu.run(self.plan, first, count)
+
+    monkeypatch.setattr(Plan, "compile", lambda self: _Interp(self))
+    A, Fd, T, H = 7, 64, 32, 256
+    lc = object.__new__(TactileLSTMController)            # the parameter containers only: no DinoV2 encoder on a CPU-only box
+    lc.device, lc.state_dim, lc.hidden_dim, lc.force_dim = "cpu", A, H, Fd
+    lc.force_encoder = nn.Sequential(nn.Linear(Fd, H // 2), nn.GELU(), nn.Linear(H // 2, H // 2))
+    lc.lstm = nn.LSTM(input_size=H // 2 + A, hidden_size=H, num_layers=2, batch_first=True, dropout=0.1)
+    lc.output_head = nn.Sequential(nn.Linear(2 * H, H), nn.LayerNorm(H), nn.GELU(), nn.Dropout(0.1), nn.Linear(H, A))
+    lc.trainable_modules = [lc.force_encoder, lc.lstm, lc.output_head]
+    for nm, mod in (("force_encoder", lc.force_encoder), ("lstm", lc.lstm), ("output_head", lc.output_head)):
+        syn.fill_named_(mod.named_parameters(), 41, prefix=f"lstm.{nm}.")
+    inp = bwd_cases.lstm_fixture_inputs(A, Fd, T)
+
+    def one_step():
+        for m in lc.trainable_modules:
+            m.zero_grad()
+        cond = inp["cond"].clone().requires_grad_(True)
+        loss = lc.get_loss({"vla_act": inp["vla_n"], "obs_cond": cond, "forces": inp["forces"], "expert_act": inp["expert"]},
+                           differentiable=True)
+        (3.0 * loss).backward()
+        mods = {"force_encoder": lc.force_encoder.state_dict(), "lstm": lc.lstm.state_dict(), "output_head": lc.output_head.state_dict()}
+        mods = {m: {k: v.detach().clone() for k, v in sd.items()} for m, sd in mods.items()}
+        ref_loss, ref, dcond = ob.lstm_loss_backward(mods, inp["vla_n"], inp["cond"], inp["forces"], inp["expert"])
+        assert abs(float(loss.detach()) - float(ref_loss)) <= 2e-2 * abs(float(ref_loss))
+        worst = float((cond.grad - 3.0 * dcond).abs().max() / (3.0 * dcond).abs().max())
+        for mname, mod in (("force_encoder", lc.force_encoder), ("lstm", lc.lstm), ("output_head", lc.output_head)):
+            for n, p_ in mod.named_parameters():
+                r = 3.0 * ref[f"{mname}.{n}"]
+                worst = max(worst, float((p_.grad - r).abs().max() / r.abs().max()))
+        return worst
+
+    assert one_step() <= 3e-2
+    with torch.no_grad():
+        for m in lc.trainable_modules:
+            for p_ in m.parameters():
+                p_.mul_(1.03)
+    assert one_step() <= 3e-2

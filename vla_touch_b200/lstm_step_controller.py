@@ -255,10 +255,40 @@ class TactileLSTMController:
         self._run(eng, vla_n, obs_cond, force_seq.to(self.device))
         return eng.out.clone()
 
-    @torch.no_grad()
-    def get_loss(self, batch_dict):
-        """MSE(forward, expert_act) (:321-337).  Forward value only: the backward pass is not built yet."""
-        return F.mse_loss(self.forward(batch_dict), batch_dict['expert_act'].to(self.device))
+    def get_loss(self, batch_dict, differentiable: bool = False):
+        """MSE(forward, expert_act) (:321-337).
+
+        Default: the loss VALUE from the inference program (no autograd graph; validation, lstm_train.py:190-215).
+        differentiable=True (the training step, lstm_train.py:120-130): one native program computes the loss and, by an explicit
+        backward (lstm_train.LstmLossBackwardProgram: BPTT recurrence kernel + dgrad / wgrad GEMMs), the gradients of the 18
+        parameters of force_encoder / lstm / output_head and of obs_cond; `loss.backward()` hands them to the nn.Parameters and
+        to the producer of `batch_dict['obs_cond']`.  bf16 operands.  The reference's Dropout(0.1) is NOT applied yet (the
+        gradients are those of the eval-mode network), and this path has only run on the CPU descriptor interpreter so far."""
+        if not differentiable:
+            with torch.no_grad():
+                return F.mse_loss(self.forward(batch_dict), batch_dict['expert_act'].to(self.device))
+        from .lstm_train import LstmLossBackwardProgram
+        vla = batch_dict['vla_act'].to(self.device).float()
+        B, T, A = vla.shape
+        mods_of = lambda: {"force_encoder": self.force_encoder.state_dict(), "lstm": self.lstm.state_dict(),
+                           "output_head": self.output_head.state_dict()}
+        ver = self._version()
+        ent = self._train_programs.get((B, T)) if hasattr(self, "_train_programs") else None
+        if ent is None:
+            if not hasattr(self, "_train_programs"):
+                self._train_programs = {}
+            ent = [LstmLossBackwardProgram(mods_of(), A, batch_dict['forces'].shape[-1], B, T, self.device), ver]
+            self._train_programs[(B, T)] = ent
+        elif ent[1] != ver:
+            ent[0].refresh(mods_of())
+            ent[1] = ver
+        params, names = [], []
+        for mname, mod in (("force_encoder", self.force_encoder), ("lstm", self.lstm), ("output_head", self.output_head)):
+            for n, p_ in mod.named_parameters():
+                params.append(p_)
+                names.append(f"{mname}.{n}")
+        return _LstmLossFn.apply(ent[0], names, vla, batch_dict['forces'].to(self.device).float(),
+                                 batch_dict['expert_act'].to(self.device).float(), batch_dict['obs_cond'].to(self.device).float(), *params)
 
     def save(self, path):
         state_dict = {'stats': self.stats, 'model_args': getattr(self, 'model_args', None),
@@ -284,3 +314,19 @@ def load_lstm_controller(path=None, state_dim=10, force_dim=3, device="cuda", **
     if path:
         controller.load(path)
     return controller
+
+
+class _LstmLossFn(torch.autograd.Function):
+    """Scalar MSE loss whose gradients were computed eagerly by the native program in forward()."""
+
+    @staticmethod
+    def forward(ctx, prog, names, vla, forces, expert, cond, *params):
+        prog.set_inputs(vla, forces, cond, expert)
+        prog.run()
+        ctx.save_for_backward(prog.d_cond.clone(), *[prog.grads[n].clone().reshape(p.shape) for n, p in zip(names, params)])
+        return torch.tensor(prog.loss(), dtype=torch.float32, device=cond.device)
+
+    @staticmethod
+    def backward(ctx, gout):
+        d_cond, *grads = ctx.saved_tensors
+        return (None, None, None, None, None, gout * d_cond) + tuple(gout * g for g in grads)

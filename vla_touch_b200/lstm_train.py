@@ -15,7 +15,7 @@ time; `LstmLossBackwardProgram`: the whole controller (force encoder, two layers
 `lstm_loss_backward` of oracle/vt_oracle_bwd.py (pinned to the reference's gradient digests) is the checker.  Eval-equivalent
 training: the reference's Dropout(0.1) (between the LSTM layers and in the head) is not applied yet.  Written after the round's
 GPU budget ended: the new kernels (lstm_seq_train, lstm_bwd, ln_gelu_bwd, ewise ops 2-4) have been compiled for sm_100a and
-checked on the CPU descriptor interpreter only; not wired into TactileLSTMController.get_loss yet.
+checked on the CPU descriptor interpreter only.  TactileLSTMController.get_loss(batch, differentiable=True) uses it.
 """
 from __future__ import annotations
 
@@ -43,13 +43,9 @@ class LstmLayerTrain:
         H, dev, f32, bf = H_LSTM, plan.device, torch.float32, torch.bfloat16
         assert w_hh.shape == (4 * H, H) and x.dtype == bf and x.shape[-1] % 64 == 0
         self.plan, self.x, self.k_in, self.k_pad, self.B, self.T, self.tag = plan, x, k_in, x.shape[-1], B, T, tag
-        wp = torch.zeros(4 * H, self.k_pad, device=dev)
-        wp[:, :k_in] = w_ih.detach().to(dev, f32)
-        self.w_ih = plan.reg(wp.to(bf).contiguous())                                   # forward operand [4H][k_pad]
-        self.w_ih_t = plan.reg(wp.t().contiguous().to(bf))                             # d x operand     [k_pad][4H]
-        self.b_sum = plan.reg((b_ih + b_hh).detach().to(dev, f32).contiguous())
-        self.w_hh = plan.reg(w_hh.detach().to(dev, f32).contiguous())                  # [4H][H]  (backward recurrence)
-        self.w_hh_t = plan.reg(w_hh.detach().to(dev, f32).t().contiguous())            # [H][4H]  (forward recurrence)
+        packed = self._pack_weights(w_ih, w_hh, b_ih, b_hh)
+        # forward operand [4H][k_pad], d x operand [k_pad][4H], b_ih + b_hh, W_hh [4H][H] (backward) and W_hh^T [H][4H] (forward)
+        self.w_ih, self.w_ih_t, self.b_sum, self.w_hh, self.w_hh_t = (plan.reg(t) for t in packed)
         R = B * T
         self.xw = plan.buf(f"{tag}.xw", (R, 4 * H), f32)
         self.y = y if y is not None else plan.buf(f"{tag}.y", (B, T, H), bf)      # may be the first H columns of a wider buffer
@@ -58,6 +54,19 @@ class LstmLayerTrain:
         self.c = plan.buf(f"{tag}.c", (B, T, H), f32)
         self.grads: Dict[str, torch.Tensor] = {}
         self.dx: Optional[torch.Tensor] = None
+
+    def _pack_weights(self, w_ih, w_hh, b_ih, b_hh):
+        H, dev, f32, bf = H_LSTM, self.plan.device, torch.float32, torch.bfloat16
+        wp = torch.zeros(4 * H, self.k_pad, device=dev)
+        wp[:, : self.k_in] = w_ih.detach().to(dev, f32)
+        whh = w_hh.detach().to(dev, f32)
+        return (wp.to(bf).contiguous(), wp.t().contiguous().to(bf), (b_ih + b_hh).detach().to(dev, f32).contiguous(),
+                whh.contiguous(), whh.t().contiguous())
+
+    def refresh(self, w_ih, w_hh, b_ih, b_hh) -> None:
+        """New parameter values -> the same device tensors (after an optimizer step)."""
+        for dst, src in zip((self.w_ih, self.w_ih_t, self.b_sum, self.w_hh, self.w_hh_t), self._pack_weights(w_ih, w_hh, b_ih, b_hh)):
+            dst.copy_(src)
 
     def forward(self) -> torch.Tensor:
         p, H, R = self.plan, H_LSTM, self.B * self.T
@@ -112,18 +121,38 @@ def lstm_layers_train(plan: Plan, x: torch.Tensor, k_in: int, lstm_sd: Dict[str,
 # ------------------------------------------------------------------------------------------------
 # the whole controller: force encoder -> LSTM -> output head -> MSE loss, forward + backward as one program
 # ------------------------------------------------------------------------------------------------
-def _lin_w(plan: Plan, w: torch.Tensor, k_pad: int, transpose: bool = False) -> torch.Tensor:
-    """nn.Linear weight [N, K] -> bf16 operand [N][k_pad] (zero padded), or its transpose [K][n_pad64] for the d-input GEMM."""
-    w = w.detach().to(plan.device, torch.float32)
-    if transpose:
-        w = w.t()
-    out = torch.zeros(w.shape[0], k_pad, device=plan.device)
-    out[:, : w.shape[1]] = w
-    return plan.reg(out.to(torch.bfloat16).contiguous())
+class _Packer:
+    """Packs parameters into plan-owned operand tensors and remembers how, so that `refresh(mods)` can re-pack new values into
+    the same device tensors.  `get(mods)` selects the raw parameter from {'force_encoder': sd, 'lstm': sd, 'output_head': sd}."""
 
+    def __init__(self, plan: Plan, mods):
+        self.plan, self.mods, self.items = plan, mods, []
 
-def _vec(plan: Plan, v: torch.Tensor) -> torch.Tensor:
-    return plan.reg(v.detach().to(plan.device, torch.float32).contiguous())
+    def _add(self, fn) -> torch.Tensor:
+        t = self.plan.reg(fn(self.mods))
+        self.items.append((t, fn))
+        return t
+
+    def lin(self, get, k_pad: int, transpose: bool = False) -> torch.Tensor:
+        """nn.Linear weight [N, K] -> bf16 operand [N][k_pad] (zero padded); transpose: [K][k_pad >= N] for the d-input GEMM."""
+        dev = self.plan.device
+
+        def fn(mods):
+            w = get(mods).detach().to(dev, torch.float32)
+            if transpose:
+                w = w.t()
+            out = torch.zeros(w.shape[0], k_pad, device=dev)
+            out[:, : w.shape[1]] = w
+            return out.to(torch.bfloat16).contiguous()
+        return self._add(fn)
+
+    def vec(self, get) -> torch.Tensor:
+        dev = self.plan.device
+        return self._add(lambda mods: get(mods).detach().to(dev, torch.float32).contiguous())
+
+    def refresh(self, mods) -> None:
+        for t, fn in self.items:
+            t.copy_(fn(mods))
 
 
 def _pack(plan: Plan, src: torch.Tensor, src_ld: int, rows: int, cols: int, out: torch.Tensor, out_ld: int, dst_c0: int, act: int,
@@ -155,7 +184,8 @@ class LstmLossBackwardProgram:
         self.plan = p = Plan(device)
         H, R, f32, bf = H_LSTM, B * T, torch.float32, torch.bfloat16
         self.A, self.B, self.T = A, B, T
-        fe, head = mods["force_encoder"], mods["output_head"]
+        self.pk = pk = _Packer(p, mods)
+        FE, HD = (lambda k: (lambda m: m["force_encoder"][k])), (lambda k: (lambda m: m["output_head"][k]))
         V = _View
         ctx = ub.DgradCtx(1, precise=False)
         r64 = lambda n: (n + 63) // 64 * 64
@@ -167,30 +197,29 @@ class LstmLossBackwardProgram:
         f_op = p.buf("f_op", (R, fpad), bf)
         _pack(p, self.forces, Fd, R, Fd, f_op, fpad, 0, nv.ACT_NONE, "lstm.force->operand", zero_to=fpad)
         a1 = p.buf("fe.a1", (R, H // 2), f32)
-        p.add(linear_desc(a=f_op, rows=R, k=fpad, a_ld=fpad, w=_lin_w(p, fe["0.weight"], fpad), n=H // 2, n_pad=H // 2, w_ld=fpad,
-                          out=a1, ldc=H // 2, bias=_vec(p, fe["0.bias"])), "force_encoder.0")
+        p.add(linear_desc(a=f_op, rows=R, k=fpad, a_ld=fpad, w=pk.lin(FE("0.weight"), fpad), n=H // 2, n_pad=H // 2, w_ld=fpad,
+                          out=a1, ldc=H // 2, bias=pk.vec(FE("0.bias"))), "force_encoder.0")
         g1 = p.buf("fe.g1", (R, H // 2), bf)
         _pack(p, a1, H // 2, R, H // 2, g1, H // 2, 0, nv.ACT_GELU, "force_encoder.gelu")
         lin = p.buf("lstm_in", (B, T, kin_pad), bf)
-        p.add(linear_desc(a=g1, rows=R, k=H // 2, a_ld=H // 2, w=_lin_w(p, fe["2.weight"], H // 2), n=H // 2, n_pad=H // 2,
-                          w_ld=H // 2, out=lin, ldc=kin_pad, bias=_vec(p, fe["2.bias"])), "force_encoder.2 -> lstm_in[:, :128]")
+        p.add(linear_desc(a=g1, rows=R, k=H // 2, a_ld=H // 2, w=pk.lin(FE("2.weight"), H // 2), n=H // 2, n_pad=H // 2,
+                          w_ld=H // 2, out=lin, ldc=kin_pad, bias=pk.vec(FE("2.bias"))), "force_encoder.2 -> lstm_in[:, :128]")
         _pack(p, self.vla, A, R, A, lin, kin_pad, H // 2, nv.ACT_NONE, "lstm.cat.vla")
         head_in = p.buf("head_in", (B, T, 2 * H), bf)                                # cat(lstm_out, obs_cond broadcast over T)
         self.layers = lstm_layers_train(p, lin, kin, mods["lstm"], B, T, 2, last_y=head_in)
         _pack(p, self.cond, H, R, H, head_in, 2 * H, H, nv.ACT_NONE, "lstm.cat.obs_cond", src_row_div=T)
-        w0 = head["0.weight"]
         z0 = p.buf("head.z0", (R, H), f32)
-        p.add(linear_desc(a=head_in, rows=R, k=2 * H, a_ld=2 * H, w=_lin_w(p, w0, 2 * H), n=H, n_pad=H, w_ld=2 * H, out=z0, ldc=H,
-                          bias=_vec(p, head["0.bias"])), "output_head.0")
+        p.add(linear_desc(a=head_in, rows=R, k=2 * H, a_ld=2 * H, w=pk.lin(HD("0.weight"), 2 * H), n=H, n_pad=H, w_ld=2 * H, out=z0,
+                          ldc=H, bias=pk.vec(HD("0.bias"))), "output_head.0")
         zn = p.buf("head.zn", (R, H), bf)
-        ln_w, ln_b = _vec(p, head["1.weight"]), _vec(p, head["1.bias"])
+        ln_w, ln_b = pk.vec(HD("1.weight")), pk.vec(HD("1.bias"))
         d = nv.LnDesc()
         d.x, d.in_ld, d.in_row_stride, d.rows, d.D, d.gamma, d.beta, d.eps = ptr(z0), H, 1, R, H, ptr(ln_w), ptr(ln_b), 1e-5
         d.out, d.out_dtype, d.out_ld, d.out_plane, d.act = ptr(zn), nv.VT_BF16, H, 0, nv.ACT_GELU
         p.add(d, "output_head.layernorm+gelu")
         self.out = p.buf("out", (R, A), f32)
-        p.add(linear_desc(a=zn, rows=R, k=H, a_ld=H, w=_lin_w(p, head["4.weight"], H), n=A, n_pad=A, w_ld=H, out=self.out, ldc=A,
-                          bias=_vec(p, head["4.bias"]), res=self.vla, ldres=A), "output_head.4 + vla (residual)")
+        p.add(linear_desc(a=zn, rows=R, k=H, a_ld=H, w=pk.lin(HD("4.weight"), H), n=A, n_pad=A, w_ld=H, out=self.out, ldc=A,
+                          bias=pk.vec(HD("4.bias")), res=self.vla, ldres=A), "output_head.4 + vla (residual)")
         # ---------------- loss and its derivative ----------------
         dout = p.buf("dout", (R, A), f32)
         _ew(p, ptr(self.out), A, ptr(self.expert), A, dout, R, A, nv.EW_SCALED_DIFF, "mse.bwd", alpha=2.0 / (R * A))
@@ -205,7 +234,7 @@ class LstmLossBackwardProgram:
         g["output_head.4.bias"] = ub.colsum(p, 1, B, dv, T, "head.4.dbias")[0]
         dob = ub.cast_bf16(p, 1, B, dv, T, "dout.bf16", c_pad=apad)
         dzn = p.buf("head.dzn", (R, H), f32)
-        p.add(linear_desc(a=dob.t, rows=R, k=apad, a_ld=apad, w=_lin_w(p, head["4.weight"], apad, transpose=True), n=H, n_pad=H,
+        p.add(linear_desc(a=dob.t, rows=R, k=apad, a_ld=apad, w=pk.lin(HD("4.weight"), apad, transpose=True), n=H, n_pad=H,
                           w_ld=apad, out=dzn, ldc=H), "head.4.dgrad")
         dz0, d1, d1zh = (p.buf(f"head.{n}", (R, H), f32) for n in ("dz0", "d1", "d1zh"))
         d = nv.LnGeluBwdDesc()
@@ -219,7 +248,7 @@ class LstmLossBackwardProgram:
         g["output_head.0.bias"] = ub.colsum(p, 1, B, dz0v, T, "head.0.dbias")[0]
         dz0b = ub.cast_bf16(p, 1, B, dz0v, T, "dz0.bf16")
         dcomb = p.buf("head.dcomb", (R, 2 * H), f32)
-        p.add(linear_desc(a=dz0b.t, rows=R, k=H, a_ld=H, w=_lin_w(p, w0, H, transpose=True), n=2 * H, n_pad=2 * H, w_ld=H, out=dcomb,
+        p.add(linear_desc(a=dz0b.t, rows=R, k=H, a_ld=H, w=pk.lin(HD("0.weight"), H, transpose=True), n=2 * H, n_pad=2 * H, w_ld=H, out=dcomb,
                           ldc=2 * H), "head.0.dgrad")
         self.d_cond = p.buf("d_cond", (B, H), f32)
         cs = nv.ColsumDesc()
@@ -236,7 +265,7 @@ class LstmLossBackwardProgram:
         g["force_encoder.2.bias"] = ub.colsum(p, 1, B, dfv, T, "fe.2.dbias")[0]
         dfb = ub.cast_bf16(p, 1, B, dfv, T, "dfenc.bf16")
         dg1 = p.buf("fe.dg1", (R, H // 2), f32)
-        p.add(linear_desc(a=dfb.t, rows=R, k=H // 2, a_ld=H // 2, w=_lin_w(p, fe["2.weight"], H // 2, transpose=True), n=H // 2,
+        p.add(linear_desc(a=dfb.t, rows=R, k=H // 2, a_ld=H // 2, w=pk.lin(FE("2.weight"), H // 2, transpose=True), n=H // 2,
                           n_pad=H // 2, w_ld=H // 2, out=dg1, ldc=H // 2), "fe.2.dgrad")
         da1 = p.buf("fe.da1", (R, H // 2), f32)
         _ew(p, ptr(dg1), H // 2, ptr(a1), H // 2, da1, R, H // 2, nv.EW_GELU_BWD, "fe.gelu.bwd")
@@ -245,6 +274,13 @@ class LstmLossBackwardProgram:
                                                     tag="fe.0.wgrad")[0][:, :Fd]
         g["force_encoder.0.bias"] = ub.colsum(p, 1, B, da1v, T, "fe.0.dbias")[0]
         self.grads = g
+
+    def refresh(self, mods) -> None:
+        """New parameter values (after an optimizer step) into the same operand tensors."""
+        self.pk.refresh(mods)
+        for l, lay in enumerate(self.layers):
+            sd = mods["lstm"]
+            lay.refresh(sd[f"weight_ih_l{l}"], sd[f"weight_hh_l{l}"], sd[f"bias_ih_l{l}"], sd[f"bias_hh_l{l}"])
 
     def set_inputs(self, vla_n, forces, cond, expert) -> None:
         self.vla.copy_(vla_n); self.forces.copy_(forces); self.cond.copy_(cond); self.expert.copy_(expert)
