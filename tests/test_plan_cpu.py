@@ -523,3 +523,29 @@ def test_lstm_get_loss_backward_through_autograd(monkeypatch):
             for p_ in m.parameters():
                 p_.mul_(1.03)
     assert one_step() <= 3e-2
+
+
+@pytest.mark.parametrize("A,T,B", [(10, 4, 1), (7, 48, 2)])
+def test_loss_backward_program_edge_shapes(A, T, B):
+    """Smallest horizon (T = 4: one position at the deepest level) with a single row, and the reference's T = 48 variant: every
+    gradient tensor in full against autograd through the forward oracle (bf16 gate 4e-2 of the tensor's scale)."""
+    from vla_touch_b200.unet_train import LossBackwardProgram
+    full = U.net_sd(A, 21)
+    sub = lambda n: {k[len(n):]: v for k, v in full.items() if k.startswith(n)}
+    g = torch.Generator().manual_seed(3)
+    x0, x1 = torch.rand(B, T, A, generator=g) * 2 - 1, torch.rand(B, T, A, generator=g) * 2 - 1
+    cond, step, z = torch.randn(B, 256, generator=g), torch.rand(B, generator=g), torch.randn(B, T, A, generator=g)
+    lp = LossBackwardProgram([sub("b_net."), sub("v_net."), sub("s_net.")], A, B, T, 0.03, "cpu")
+    lp.set_inputs(x0, x1, cond, step, z)
+    plan_emu.run(lp.plan)
+    sd = {k: v.clone().requires_grad_(True) for k, v in full.items()}
+    c = cond.clone().requires_grad_(True)
+    loss, *_ = orc.bridge_losses(sd, c, x1, x0, step, z)
+    loss.backward()
+    assert abs(float(lp.out[0]) - float(loss.detach())) <= 2e-2 * abs(float(loss.detach()))
+    grads = lp.grads
+    for n, p in sd.items():
+        assert float((grads[n].float() - p.grad).abs().max()) <= 4e-2 * float(p.grad.abs().max()), n
+    assert float((lp.d_cond - c.grad).abs().max()) <= 4e-2 * float(c.grad.abs().max())
+    with pytest.raises(ValueError):
+        LossBackwardProgram([sub("b_net."), sub("v_net."), sub("s_net.")], A, B, 6, 0.03, "cpu")      # T must be a multiple of 4
