@@ -141,14 +141,20 @@ class _Packer:
             w = get(mods).detach().to(dev, torch.float32)
             if transpose:
                 w = w.t()
-            out = torch.zeros(w.shape[0], k_pad, device=dev)
-            out[:, : w.shape[1]] = w
+            out = torch.zeros((w.shape[0] + 31) // 32 * 32, k_pad, device=dev)     # rows padded to the narrowest tile width
+            out[: w.shape[0], : w.shape[1]] = w
             return out.to(torch.bfloat16).contiguous()
         return self._add(fn)
 
     def vec(self, get) -> torch.Tensor:
         dev = self.plan.device
-        return self._add(lambda mods: get(mods).detach().to(dev, torch.float32).contiguous())
+
+        def fn(mods):
+            v = get(mods).detach().to(dev, torch.float32).reshape(-1)
+            out = torch.zeros((v.numel() + 255) // 256 * 256, device=dev)          # padded to the widest tile: no masked loads needed
+            out[: v.numel()] = v
+            return out
+        return self._add(fn)
 
     def refresh(self, mods) -> None:
         for t, fn in self.items:
@@ -218,8 +224,11 @@ class LstmLossBackwardProgram:
         d.out, d.out_dtype, d.out_ld, d.out_plane, d.act = ptr(zn), nv.VT_BF16, H, 0, nv.ACT_GELU
         p.add(d, "output_head.layernorm+gelu")
         self.out = p.buf("out", (R, A), f32)
-        p.add(linear_desc(a=zn, rows=R, k=H, a_ld=H, w=pk.lin(HD("4.weight"), H), n=A, n_pad=A, w_ld=H, out=self.out, ldc=A,
-                          bias=pk.vec(HD("4.bias")), res=self.vla, ldres=A), "output_head.4 + vla (residual)")
+        w4 = pk.lin(HD("4.weight"), H)
+        delta = p.buf("head.delta", (R, A), f32)
+        p.add(linear_desc(a=zn, rows=R, k=H, a_ld=H, w=w4, n=A, n_pad=w4.shape[0], w_ld=H, out=delta, ldc=A,
+                          bias=pk.vec(HD("4.bias"))), "output_head.4")
+        _ew(p, ptr(delta), A, ptr(self.vla), A, self.out, R, A, nv.EW_ADD, "out = vla + delta (residual)")
         # ---------------- loss and its derivative ----------------
         dout = p.buf("dout", (R, A), f32)
         _ew(p, ptr(self.out), A, ptr(self.expert), A, dout, R, A, nv.EW_SCALED_DIFF, "mse.bwd", alpha=2.0 / (R * A))
