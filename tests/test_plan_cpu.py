@@ -374,6 +374,15 @@ def test_get_loss_backward_through_autograd(monkeypatch):
     monkeypatch.setattr(Plan, "compile", lambda self: _Interp(self))
     res = bwd_cases.training_step_case(torch.device("cpu"))()
     assert res["first"] <= 3e-2 and res["after_update"] <= 3e-2
+    # the gradients live in the program's buffers: a backward() that comes after a later get_loss() must fail loudly
+    si = bwd_cases.interpolant(10, 16, torch.device("cpu"))
+    batch = {"obs_cond": syn.det_normal("loss.cond", (3, 256), 24), "expert_act": syn.det_uniform("loss.exp", (3, 16, 10), 24, -1.0, 1.0),
+             "vla_act": syn.det_uniform("loss.vla", (3, 16, 10), 24, -1.0, 1.0)}
+    first, _ = si.get_loss(batch, "cpu")
+    second, _ = si.get_loss(batch, "cpu")
+    with pytest.raises(RuntimeError, match="called again before"):
+        first.backward()
+    second.backward()
 
 
 def test_training_loop_reduces_the_loss(monkeypatch):

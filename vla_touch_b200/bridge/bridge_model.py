@@ -192,11 +192,16 @@ class _BridgeLossFn(torch.autograd.Function):
         prog.set_inputs(x0, x1, obs, step, z)
         out = prog.run().clone()
         g = prog.grads
-        ctx.save_for_backward(prog.d_cond.clone(), *[g[n].clone() for n in names])
+        # the gradients stay in the program's own buffers (no 412 MB copy per step); backward() checks they are still current
+        ctx.prog, ctx.run_id = prog, prog.runs
+        ctx.save_for_backward(prog.d_cond, *[g[n] for n in names])
         return out
 
     @staticmethod
     def backward(ctx, gout):
+        if ctx.prog.runs != ctx.run_id:
+            raise RuntimeError("get_loss() was called again before this loss.backward(): the program's gradient buffers now hold "
+                               "the later call's gradients (call backward() before the next get_loss(), as bridge_train.py does)")
         d_cond, *grads = ctx.saved_tensors
         s = gout[0]
-        return (None, None, None, None, None, None, s * d_cond) + tuple(s * g for g in grads)
+        return (None, None, None, None, None, None, s * d_cond) + tuple(torch._foreach_mul(list(grads), s))

@@ -323,10 +323,13 @@ class _LstmLossFn(torch.autograd.Function):
     def forward(ctx, prog, names, vla, forces, expert, cond, *params):
         prog.set_inputs(vla, forces, cond, expert)
         prog.run()
-        ctx.save_for_backward(prog.d_cond.clone(), *[prog.grads[n].clone().reshape(p.shape) for n, p in zip(names, params)])
+        ctx.prog, ctx.run_id = prog, prog.runs
+        ctx.save_for_backward(prog.d_cond, *[prog.grads[n].reshape(p.shape) for n, p in zip(names, params)])
         return torch.tensor(prog.loss(), dtype=torch.float32, device=cond.device)
 
     @staticmethod
     def backward(ctx, gout):
+        if ctx.prog.runs != ctx.run_id:
+            raise RuntimeError("get_loss() was called again before this loss.backward(): the gradient buffers were overwritten")
         d_cond, *grads = ctx.saved_tensors
-        return (None, None, None, None, None, gout * d_cond) + tuple(gout * g for g in grads)
+        return (None, None, None, None, None, gout * d_cond) + tuple(torch._foreach_mul(list(grads), gout))

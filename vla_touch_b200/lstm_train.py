@@ -295,6 +295,7 @@ class LstmLossBackwardProgram:
         self.vla.copy_(vla_n); self.forces.copy_(forces); self.cond.copy_(cond); self.expert.copy_(expert)
 
     def run(self) -> None:
+        self.runs = getattr(self, "runs", 0) + 1
         self.plan.compile().run()
 
     def loss(self) -> float:

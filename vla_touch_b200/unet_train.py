@@ -361,6 +361,7 @@ class LossBackwardProgram:
         """Launch the whole program on the current stream.  graph=True replays it as one CUDA graph (captured on first use;
         the program is static: fixed buffers, weights re-packed in place), which removes the ~300 launch latencies."""
         prog = self.plan.compile()
+        self.runs = getattr(self, "runs", 0) + 1
         if graph:
             if not getattr(self, "_graph_ready", False):
                 prog.graph_build()
