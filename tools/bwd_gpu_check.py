@@ -1,6 +1,6 @@
 """Runs every backward case of tests/bwd_cases.py on the GPU and on the CPU descriptor interpreter op by op (each GPU op
 starts from the interpreter's inputs), prints the per-op deviations, then the comparison with the oracle.
-    python tools/bwd_gpu_check.py > gpurun_out/bwd_check.txt"""
+    python tools/bwd_gpu_check.py [name substrings ...] > gpurun_out/bwd_check.txt      (e.g. `lstm` for the LSTM cases only)"""
 import os
 import sys
 import time
@@ -22,6 +22,8 @@ cases += [("colsum", bwd_cases.colsum_case),
           ("block.film.512ch.T64", lambda d: bwd_cases.block_case(d, True, G=3, B=4, T=64, Ci=256, Co=512, seed=6))]
 cases += [(f"res_block.{ci}->{co}", lambda d, ci=ci, co=co: bwd_cases.res_block_case(d, ci, co))
           for ci, co in ((256, 256), (256, 512), (1024, 512), (7, 256))]
+cases += [("lstm_layers", bwd_cases.lstm_layers_case), ("lstm_loss.A7", lambda d: bwd_cases.lstm_loss_case(d, 7, 64, 32)),
+          ("unet", bwd_cases.unet_case), ("loss.A10", lambda d: bwd_cases.loss_case(d, 10, 16))]
 if len(sys.argv) > 1:
     cases = [c for c in cases if any(a in c[0] for a in sys.argv[1:])]
 ok = True
