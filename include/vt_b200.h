@@ -355,6 +355,19 @@ typedef struct vt_ewise_desc {
   float alpha;
 } vt_ewise_desc;
 
+/* Inverted-dropout mask of nn.Dropout(p) / nn.LSTM(dropout=p) in training mode (lstm_step_controller.py:66-82):
+ * mask[i] = u_i >= p ? 1/(1-p) : 0,  u_i ~ U[0,1) from Philox4x32-10(seed (+ *seed_dev), element i, stream) or from `inject`
+ * (parity tests).  Forward and backward multiply by the stored mask (VT_EW_MUL). */
+typedef struct vt_dropmask_desc {
+  const float* inject;      /* [n] uniforms or null */
+  float p;
+  uint64_t seed;
+  const uint64_t* seed_dev; /* optional: added to seed at run time (a new mask per step without re-encoding the program) */
+  int32_t stream;
+  float* mask;              /* [n] */
+  int64_t n;
+} vt_dropmask_desc;
+
 /* Backward of LayerNorm(256) -> GELU of the LSTM controller's output head (lstm_step_controller.py:76-82) from the saved
  * LayerNorm input z0:  dz0 = d loss / d z0;  d1 = dzn * gelu'(z1) and d1zh = d1 * zh are stored for the column sums that give
  * d beta and d gamma. */
@@ -483,6 +496,7 @@ int vt_program_add_silossbwd(vt_program* p, const vt_silossbwd_desc* d);
 int vt_program_add_lstm_train(vt_program* p, const vt_lstm_train_desc* d);
 int vt_program_add_lstm_bwd(vt_program* p, const vt_lstm_bwd_desc* d);
 int vt_program_add_lngelubwd(vt_program* p, const vt_lngelubwd_desc* d);
+int vt_program_add_dropmask(vt_program* p, const vt_dropmask_desc* d);
 
 /* Launch ops [first, first+count) in order on `stream` (count < 0: to the end). */
 int vt_program_run(vt_program* p, int first, int count, void* stream);

@@ -511,3 +511,59 @@ def lstm_loss_case(device, A=7, Fd=64, T=32):
         assert not bad, bad
         return dict(worst=max(worst.values()), tensors=len(lp.grads))
     return lp.plan, check
+
+
+def lstm_dropout_case(device, A=7, Fd=64, T=32, p_drop=0.1):
+    """LstmLossBackwardProgram(dropout=0.1) with injected uniforms against torch autograd of the same network with the same two
+    inverted-dropout masks (between the LSTM layers, nn.LSTM(dropout=p) semantics, and in the head, nn.Dropout(p))."""
+    import torch.nn.functional as F
+    from vla_touch_b200 import shapes as shp
+    from vla_touch_b200 import synthetic as syn
+    from vla_touch_b200.lstm_train import LstmLossBackwardProgram
+    H = 256
+    mods = {"force_encoder": syn.synth_state_dict(shp.mlp_shapes([Fd, 128, 128]), 41, "lstm.force_encoder."),
+            "lstm": syn.synth_state_dict(shp.lstm_shapes(128 + A), 41, "lstm.lstm."),
+            "output_head": syn.synth_state_dict(shp.lstm_head_shapes(256, A), 41, "lstm.output_head.")}
+    inp = lstm_fixture_inputs(A, Fd, T)
+    B = inp["vla_n"].shape[0]
+    g = torch.Generator().manual_seed(77)
+    u0, u1 = torch.rand(B * T, H, generator=g), torch.rand(B * T, H, generator=g)
+    lp = LstmLossBackwardProgram(mods, A, Fd, B, T, device, dropout=p_drop, inject_uniforms=True)
+    lp.set_inputs(inp["vla_n"], inp["forces"], inp["cond"], inp["expert"])
+    lp.u[0].copy_(u0); lp.u[1].copy_(u1)
+
+    def check(tol=3e-2):
+        P = {m: {k: v.clone().requires_grad_(True) for k, v in sd.items()} for m, sd in mods.items()}
+        fe, ls, hd = P["force_encoder"], P["lstm"], P["output_head"]
+        cond = inp["cond"].clone().requires_grad_(True)
+        m0 = ((u0 >= p_drop).float() / (1 - p_drop)).reshape(B, T, H)
+        m1 = ((u1 >= p_drop).float() / (1 - p_drop)).reshape(B, T, H)
+        fenc = F.linear(F.gelu(F.linear(inp["forces"], fe["0.weight"], fe["0.bias"])), fe["2.weight"], fe["2.bias"])
+        x = torch.cat([fenc, inp["vla_n"]], dim=-1)
+
+        def layer(xin, l):
+            h, c, ys = torch.zeros(B, H), torch.zeros(B, H), []
+            for t in range(T):
+                gt = F.linear(xin[:, t], ls[f"weight_ih_l{l}"], ls[f"bias_ih_l{l}"]) + F.linear(h, ls[f"weight_hh_l{l}"], ls[f"bias_hh_l{l}"])
+                i_, f_, g_, o_ = gt.chunk(4, dim=-1)
+                c = torch.sigmoid(f_) * c + torch.sigmoid(i_) * torch.tanh(g_)
+                h = torch.sigmoid(o_) * torch.tanh(c)
+                ys.append(h)
+            return torch.stack(ys, dim=1)
+        y1 = layer(layer(x, 0) * m0, 1)
+        comb = torch.cat([y1, cond[:, None].expand(B, T, H)], dim=-1)
+        zn = F.gelu(F.layer_norm(F.linear(comb, hd["0.weight"], hd["0.bias"]), (H,), hd["1.weight"], hd["1.bias"], 1e-5)) * m1
+        out = inp["vla_n"] + F.linear(zn, hd["4.weight"], hd["4.bias"])
+        loss = F.mse_loss(out, inp["expert"])
+        loss.backward()
+        assert abs(lp.loss() - float(loss.detach())) <= 2e-2 * abs(float(loss.detach()))
+        keep = float((lp.masks[0] > 0).float().mean())
+        assert abs(keep - (1 - p_drop)) < 0.02 and abs(float(lp.masks[0].max()) - 1 / (1 - p_drop)) < 1e-6
+        worst = {"d_cond": _rel(lp.d_cond.float().cpu(), cond.grad)}
+        for k, v in lp.grads.items():
+            m, key = k.split(".", 1)
+            worst[k] = _rel(v.float().cpu().reshape(P[m][key].shape), P[m][key].grad)
+        bad = {k: v for k, v in worst.items() if not v <= tol}
+        assert not bad, bad
+        return dict(worst=max(worst.values()), tensors=len(lp.grads))
+    return lp.plan, check

@@ -9,7 +9,7 @@ from vla_touch_b200.plan import Plan
 _OUT_FIELD = {nv.GemmDesc: "out", nv.LnDesc: "out", nv.AttnDesc: "ctx", nv.ImgStatsDesc: "flags", nv.PatchifyDesc: "out",
               nv.ClsDesc: "h", nv.PackDesc: "out", nv.AffineDesc: None, nv.TembedDesc: "out", nv.SdeDesc: "x",
               nv.LstmDesc: "y", nv.QsampleDesc: "xt", nv.SilossDesc: "out", nv.TcolDesc: "out", nv.GnbwdDesc: "draw",
-              nv.ColsumDesc: "out", nv.EwiseDesc: "out", nv.SilossBwdDesc: "dvs", nv.LstmTrainDesc: "gates", nv.LstmBwdDesc: "dgates", nv.LnGeluBwdDesc: "dz0"}
+              nv.ColsumDesc: "out", nv.EwiseDesc: "out", nv.SilossBwdDesc: "dvs", nv.LstmTrainDesc: "gates", nv.LstmBwdDesc: "dgates", nv.LnGeluBwdDesc: "dz0", nv.DropmaskDesc: "mask"}
 
 
 def _buffer_of(plan: Plan, address: int):

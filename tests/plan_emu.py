@@ -458,9 +458,16 @@ def emu_lngelubwd(plan, d: nv.LnGeluBwdDesc):
     _flat(plan, d.d1zh, torch.float32)[:n] = (d1 * zh).reshape(-1)
 
 
+def emu_dropmask(plan, d: nv.DropmaskDesc):
+    assert d.inject, "the emulator needs injected uniforms"
+    u = _flat(plan, d.inject, torch.float32)[: d.n]
+    p = torch.tensor(d.p, dtype=torch.float32)
+    _flat(plan, d.mask, torch.float32)[: d.n] = torch.where(u >= p, 1.0 / (1.0 - p), torch.zeros(()))
+
+
 _EMU = {nv.QsampleDesc: emu_qsample, nv.SilossDesc: emu_siloss, nv.GemmDesc: emu_gemm, nv.LnDesc: emu_layernorm, nv.AttnDesc: emu_attention, nv.ImgStatsDesc: emu_imgstats,
         nv.PatchifyDesc: emu_patchify, nv.ClsDesc: emu_cls, nv.PackDesc: emu_pack, nv.AffineDesc: emu_affine,
-        nv.TcolDesc: emu_tcol, nv.GnbwdDesc: emu_gnbwd, nv.ColsumDesc: emu_colsum, nv.EwiseDesc: emu_ewise, nv.SilossBwdDesc: emu_silossbwd, nv.LstmTrainDesc: emu_lstm_train, nv.LstmBwdDesc: emu_lstm_bwd, nv.LnGeluBwdDesc: emu_lngelubwd, nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm, nv.MlpDesc: emu_mlp}
+        nv.TcolDesc: emu_tcol, nv.GnbwdDesc: emu_gnbwd, nv.ColsumDesc: emu_colsum, nv.EwiseDesc: emu_ewise, nv.SilossBwdDesc: emu_silossbwd, nv.LstmTrainDesc: emu_lstm_train, nv.LstmBwdDesc: emu_lstm_bwd, nv.LnGeluBwdDesc: emu_lngelubwd, nv.DropmaskDesc: emu_dropmask, nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm, nv.MlpDesc: emu_mlp}
 
 
 @torch.no_grad()

@@ -60,7 +60,7 @@ def test_ctypes_structs_match_the_c_header():
              "vt_siloss_desc": nv.SilossDesc, "vt_opt_tensor": nv.OptTensor, "vt_adamw_desc": nv.AdamwDesc,
              "vt_mlp_desc": nv.MlpDesc, "vt_tcol_desc": nv.TcolDesc, "vt_gnbwd_desc": nv.GnbwdDesc,
              "vt_colsum_desc": nv.ColsumDesc, "vt_ewise_desc": nv.EwiseDesc, "vt_silossbwd_desc": nv.SilossBwdDesc, "vt_lstm_train_desc": nv.LstmTrainDesc,
-             "vt_lstm_bwd_desc": nv.LstmBwdDesc, "vt_lngelubwd_desc": nv.LnGeluBwdDesc}
+             "vt_lstm_bwd_desc": nv.LstmBwdDesc, "vt_lngelubwd_desc": nv.LnGeluBwdDesc, "vt_dropmask_desc": nv.DropmaskDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/vt_b200.h"', 'int main(void){']
     probes = []
     for cname, cls in descs.items():
@@ -504,6 +504,7 @@ def test_lstm_get_loss_backward_through_autograd(monkeypatch):
     lc.lstm = nn.LSTM(input_size=H // 2 + A, hidden_size=H, num_layers=2, batch_first=True, dropout=0.1)
     lc.output_head = nn.Sequential(nn.Linear(2 * H, H), nn.LayerNorm(H), nn.GELU(), nn.Dropout(0.1), nn.Linear(H, A))
     lc.trainable_modules = [lc.force_encoder, lc.lstm, lc.output_head]
+    lc.eval()                                             # deterministic network (train mode adds Philox dropout masks)
     for nm, mod in (("force_encoder", lc.force_encoder), ("lstm", lc.lstm), ("output_head", lc.output_head)):
         syn.fill_named_(mod.named_parameters(), 41, prefix=f"lstm.{nm}.")
     inp = bwd_cases.lstm_fixture_inputs(A, Fd, T)
@@ -558,3 +559,12 @@ def test_loss_backward_program_edge_shapes(A, T, B):
     assert float((lp.d_cond - c.grad).abs().max()) <= 4e-2 * float(c.grad.abs().max())
     with pytest.raises(ValueError):
         LossBackwardProgram([sub("b_net."), sub("v_net."), sub("s_net.")], A, B, 6, 0.03, "cpu")      # T must be a multiple of 4
+
+
+def test_lstm_training_program_with_dropout():
+    """LstmLossBackwardProgram(dropout=0.1): inverted-dropout masks between the LSTM layers and in the head (training-mode
+    semantics of the reference, lstm_step_controller.py:66-82), injected uniforms, against torch autograd with the same masks."""
+    import bwd_cases
+    plan, check = bwd_cases.lstm_dropout_case(torch.device("cpu"))
+    plan_emu.run(plan)
+    assert check()["tensors"] == 18

@@ -138,3 +138,10 @@ def test_lstm_get_loss_backward_against_the_reference_gradients(A, Fd, T):
     plan, check = bwd_cases.lstm_loss_case(DEV, A, Fd, T)
     _run(plan)
     assert check()["tensors"] == 18
+
+
+@pytest.mark.xfail(strict=False, reason="LSTM training kernels + dropmask_kernel: written after the round's GPU budget ended, never run on a B200")
+def test_lstm_training_with_dropout():
+    plan, check = bwd_cases.lstm_dropout_case(DEV)
+    _run(plan)
+    check()

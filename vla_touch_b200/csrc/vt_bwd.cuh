@@ -309,6 +309,27 @@ __global__ void __launch_bounds__(256) ln_gelu_bwd_kernel(const float* __restric
   for (int i = 0; i < PER; ++i) dz0[row * D + lane + 32 * i] = rstd * (dzh[i] - s1 - zh[i] * s2);
 }
 
+// Inverted-dropout mask (nn.Dropout / the inter-layer dropout of nn.LSTM in training mode, lstm_step_controller.py:66-82):
+// mask[i] = u_i >= p ? 1 / (1 - p) : 0 with u_i ~ U[0, 1) from Philox4x32-10 (seed, element, stream) or, for parity tests,
+// from an injected buffer.  The mask is stored: forward and backward both multiply by it (ewise MUL).
+__global__ void __launch_bounds__(256) dropmask_kernel(const float* __restrict__ inject, float p, unsigned long long seed,
+                                                       const unsigned long long* __restrict__ seed_dev, int stream,
+                                                       float* __restrict__ mask, long long n) {
+  if (seed_dev) seed += *seed_dev;
+  const float keep = 1.f / (1.f - p);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    float u;
+    if (inject) {
+      u = inject[idx];
+    } else {
+      curandStatePhilox4_32_10_t st;
+      curand_init(seed, (unsigned long long)idx, (unsigned long long)stream, &st);
+      u = 1.f - curand_uniform(&st);          // curand_uniform is (0, 1]
+    }
+    mask[idx] = u >= p ? keep : 0.f;
+  }
+}
+
 // d (L_v + L_s + L_b) / d (net outputs), bridge_model.py:183-218 with the batch mean of get_loss (:240-246), nets stacked as
 // [b_net, v_net, s_net]:  d/db = (b - (x1 - x0 + gdot z)) / B,  d/dv = (v - (x1 - x0)) / B,  d/ds = (s + z) / B,  z = d z_unit
 __global__ void __launch_bounds__(256) siloss_bwd_kernel(const float* __restrict__ bvs, const float* __restrict__ x0,

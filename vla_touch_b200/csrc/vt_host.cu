@@ -697,6 +697,16 @@ struct LstmOp : Op {
   }
 };
 
+struct DropmaskOp : Op {
+  vt_dropmask_desc d;
+  int launch(cudaStream_t s) override {
+    vt::dropmask_kernel<<<grid_for(d.n, 256), 256, 0, s>>>(d.inject, d.p, (unsigned long long)d.seed,
+                                                          reinterpret_cast<const unsigned long long*>(d.seed_dev), d.stream, d.mask, d.n);
+    VT_LAUNCH_CHECK("dropmask_kernel");
+    return VT_OK;
+  }
+};
+
 struct LnGeluBwdOp : Op {
   vt_lngelubwd_desc d;
   int launch(cudaStream_t s) override {
@@ -989,6 +999,8 @@ VT_SIMPLE_ADD(vt_program_add_silossbwd, SilossBwdOp, vt_silossbwd_desc,
               VT_REQUIRE(d->bvs && d->x0 && d->x1 && d->z_unit && d->tclip && d->dvs && d->B >= 1 && d->n >= 1,
                          "silossbwd: bad descriptor"))
 
+VT_SIMPLE_ADD(vt_program_add_dropmask, DropmaskOp, vt_dropmask_desc,
+              VT_REQUIRE(d->mask && d->n >= 1 && d->p >= 0.f && d->p < 1.f, "dropmask: bad descriptor (p=%f)", (double)d->p))
 VT_SIMPLE_ADD(vt_program_add_lngelubwd, LnGeluBwdOp, vt_lngelubwd_desc,
               VT_REQUIRE(d->z0 && d->dzn && d->gamma && d->beta && d->dz0 && d->d1 && d->d1zh && d->rows >= 1 && d->D == 256,
                          "lngelubwd: bad descriptor (D=%d)", d->D))

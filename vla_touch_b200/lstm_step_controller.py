@@ -262,8 +262,10 @@ class TactileLSTMController:
         differentiable=True (the training step, lstm_train.py:120-130): one native program computes the loss and, by an explicit
         backward (lstm_train.LstmLossBackwardProgram: BPTT recurrence kernel + dgrad / wgrad GEMMs), the gradients of the 18
         parameters of force_encoder / lstm / output_head and of obs_cond; `loss.backward()` hands them to the nn.Parameters and
-        to the producer of `batch_dict['obs_cond']`.  bf16 operands.  The reference's Dropout(0.1) is NOT applied yet (the
-        gradients are those of the eval-mode network), and this path has only run on the CPU descriptor interpreter so far."""
+        to the producer of `batch_dict['obs_cond']`.  bf16 operands.  In training mode (`controller.train()`) the reference's
+        dropout (0.1 between the LSTM layers and in the head) is applied with in-kernel Philox masks, a new pair every call; in
+        eval mode the gradients are those of the deterministic network.  This path has only run on the CPU descriptor
+        interpreter so far."""
         if not differentiable:
             with torch.no_grad():
                 return F.mse_loss(self.forward(batch_dict), batch_dict['expert_act'].to(self.device))
@@ -273,15 +275,20 @@ class TactileLSTMController:
         mods_of = lambda: {"force_encoder": self.force_encoder.state_dict(), "lstm": self.lstm.state_dict(),
                            "output_head": self.output_head.state_dict()}
         ver = self._version()
-        ent = self._train_programs.get((B, T)) if hasattr(self, "_train_programs") else None
+        # training mode (controller.train(), lstm_train.py:118): the reference's nn.LSTM(dropout=0.1) / nn.Dropout(0.1) are active
+        p_drop = (float(self.lstm.dropout), float(self.output_head[3].p)) if self.lstm.training else (0.0, 0.0)
+        if not hasattr(self, "_train_programs"):
+            self._train_programs, self._drop_seed = {}, 0
+        ent = self._train_programs.get((B, T, p_drop))
         if ent is None:
-            if not hasattr(self, "_train_programs"):
-                self._train_programs = {}
-            ent = [LstmLossBackwardProgram(mods_of(), A, batch_dict['forces'].shape[-1], B, T, self.device), ver]
-            self._train_programs[(B, T)] = ent
+            ent = [LstmLossBackwardProgram(mods_of(), A, batch_dict['forces'].shape[-1], B, T, self.device, dropout=p_drop), ver]
+            self._train_programs[(B, T, p_drop)] = ent
         elif ent[1] != ver:
             ent[0].refresh(mods_of())
             ent[1] = ver
+        if max(p_drop) > 0:
+            self._drop_seed += 1
+            ent[0].seed.fill_(self._drop_seed)                   # fresh Philox masks every step, no re-encoding of the program
         params, names = [], []
         for mname, mod in (("force_encoder", self.force_encoder), ("lstm", self.lstm), ("output_head", self.output_head)):
             for n, p_ in mod.named_parameters():

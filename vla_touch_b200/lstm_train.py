@@ -12,8 +12,9 @@ time; `LstmLossBackwardProgram`: the whole controller (force encoder, two layers
               head: ln_gelu_bwd_kernel (LayerNorm + GELU backward from the saved LayerNorm input), linears as dgrad / wgrad
               GEMMs, d obs_cond = sum over time of the head's input gradient (column sum per sample)
 
-`lstm_loss_backward` of oracle/vt_oracle_bwd.py (pinned to the reference's gradient digests) is the checker.  Eval-equivalent
-training: the reference's Dropout(0.1) (between the LSTM layers and in the head) is not applied yet.  Written after the round's
+`lstm_loss_backward` of oracle/vt_oracle_bwd.py (pinned to the reference's gradient digests) is the checker of the deterministic
+(eval-mode) network; training mode adds the reference's dropout (between the LSTM layers and in the head) as stored Philox masks
+(dropmask_kernel), checked against torch autograd with the same masks.  Written after the round's
 GPU budget ended: the new kernels (lstm_seq_train, lstm_bwd, ln_gelu_bwd, ewise ops 2-4) have been compiled for sm_100a and
 checked on the CPU descriptor interpreter only.  TactileLSTMController.get_loss(batch, differentiable=True) uses it.
 """
@@ -39,7 +40,8 @@ class LstmLayerTrain:
     After `backward(plan, dy)`: self.grads = {weight_ih, weight_hh, bias_ih, bias_hh} and self.dx (fp32 [B][T][k_pad])."""
 
     def __init__(self, plan: Plan, x: torch.Tensor, k_in: int, w_ih: torch.Tensor, w_hh: torch.Tensor, b_ih: torch.Tensor,
-                 b_hh: torch.Tensor, B: int, T: int, tag: str = "lstm.l0", y: Optional[torch.Tensor] = None):
+                 b_hh: torch.Tensor, B: int, T: int, tag: str = "lstm.l0", y: Optional[torch.Tensor] = None,
+                 y_f32: bool = False):
         H, dev, f32, bf = H_LSTM, plan.device, torch.float32, torch.bfloat16
         assert w_hh.shape == (4 * H, H) and x.dtype == bf and x.shape[-1] % 64 == 0
         self.plan, self.x, self.k_in, self.k_pad, self.B, self.T, self.tag = plan, x, k_in, x.shape[-1], B, T, tag
@@ -48,7 +50,8 @@ class LstmLayerTrain:
         self.w_ih, self.w_ih_t, self.b_sum, self.w_hh, self.w_hh_t = (plan.reg(t) for t in packed)
         R = B * T
         self.xw = plan.buf(f"{tag}.xw", (R, 4 * H), f32)
-        self.y = y if y is not None else plan.buf(f"{tag}.y", (B, T, H), bf)      # may be the first H columns of a wider buffer
+        # hidden outputs: bf16 (the next GEMM's operand; may be the first H columns of a wider buffer) or fp32 (when dropout follows)
+        self.y = y if y is not None else plan.buf(f"{tag}.y", (B, T, H), f32 if y_f32 else bf)
         self.y_ld = self.y.shape[-1]
         self.gates = plan.buf(f"{tag}.gates", (B, T, 4 * H), f32)
         self.c = plan.buf(f"{tag}.c", (B, T, H), f32)
@@ -73,7 +76,8 @@ class LstmLayerTrain:
         p.add(linear_desc(a=self.x, rows=R, k=self.k_pad, a_ld=self.k_pad, w=self.w_ih, n=4 * H, n_pad=4 * H, w_ld=self.k_pad,
                           out=self.xw, ldc=4 * H, bias=self.b_sum), f"{self.tag}.input_proj")
         d = nv.LstmTrainDesc()
-        d.xw, d.w_hh, d.y, d.y_dtype, d.y_ld = ptr(self.xw), ptr(self.w_hh_t), ptr(self.y), nv.VT_BF16, self.y_ld
+        d.xw, d.w_hh, d.y, d.y_ld = ptr(self.xw), ptr(self.w_hh_t), ptr(self.y), self.y_ld
+        d.y_dtype = nv.VT_BF16 if self.y.dtype == torch.bfloat16 else nv.VT_F32
         d.gates, d.c, d.B, d.T, d.H = ptr(self.gates), ptr(self.c), self.B, self.T, H
         p.add(d, f"{self.tag}.recurrence(train)")
         return self.y
@@ -186,8 +190,13 @@ class LstmLossBackwardProgram:
     Inputs: vla (normalised) [B,T,A], forces [B,T,F], cond [B,256], expert [B,T,A].  Outputs: .loss() (python float),
     .grads {'force_encoder.0.weight', ..., 'lstm.weight_hh_l1', ..., 'output_head.4.bias'} (18 tensors), .d_cond [B,256]."""
 
-    def __init__(self, mods: Dict[str, Dict[str, torch.Tensor]], A: int, Fd: int, B: int, T: int, device):
+    def __init__(self, mods: Dict[str, Dict[str, torch.Tensor]], A: int, Fd: int, B: int, T: int, device, dropout: float = 0.0,
+                 inject_uniforms: bool = False):
+        """dropout = p > 0 (or a pair (p_lstm, p_head)): training-mode semantics of the reference (nn.LSTM(dropout=p) between the two layers, nn.Dropout(p) in
+        the head): two inverted-dropout masks per step from Philox (seed = self.seed[0], set it per step) or, for parity tests,
+        from the injected uniforms self.u[0] / self.u[1]."""
         self.plan = p = Plan(device)
+        self.p_drop = tuple(float(x) for x in dropout) if isinstance(dropout, (tuple, list)) else (float(dropout), float(dropout))
         H, R, f32, bf = H_LSTM, B * T, torch.float32, torch.bfloat16
         self.A, self.B, self.T = A, B, T
         self.pk = pk = _Packer(p, mods)
@@ -212,17 +221,45 @@ class LstmLossBackwardProgram:
                           w_ld=H // 2, out=lin, ldc=kin_pad, bias=pk.vec(FE("2.bias"))), "force_encoder.2 -> lstm_in[:, :128]")
         _pack(p, self.vla, A, R, A, lin, kin_pad, H // 2, nv.ACT_NONE, "lstm.cat.vla")
         head_in = p.buf("head_in", (B, T, 2 * H), bf)                                # cat(lstm_out, obs_cond broadcast over T)
-        self.layers = lstm_layers_train(p, lin, kin, mods["lstm"], B, T, 2, last_y=head_in)
+        sd = mods["lstm"]
+        lw = lambda l: (sd[f"weight_ih_l{l}"], sd[f"weight_hh_l{l}"], sd[f"bias_ih_l{l}"], sd[f"bias_hh_l{l}"])
+        drop = max(self.p_drop) > 0                                                  # (between the LSTM layers, in the head)
+        self.masks, self.u = [], []
+        if drop:
+            self.seed = p.buf("dropout.seed", (1,), torch.int64)
+            for i, nm in enumerate(("lstm", "head")):
+                m_ = p.buf(f"dropout.mask.{nm}", (R, H), f32)
+                u_ = p.buf(f"dropout.u.{nm}", (R, H), f32) if inject_uniforms else None
+                dm = nv.DropmaskDesc()
+                dm.inject, dm.p, dm.seed, dm.seed_dev, dm.stream, dm.mask, dm.n = ptr(u_), self.p_drop[i], 0, ptr(self.seed), i, ptr(m_), R * H
+                p.add(dm, f"dropout.mask.{nm}")
+                self.masks.append(m_)
+                self.u.append(u_)
+        l0 = LstmLayerTrain(p, lin, kin, *lw(0), B, T, tag="lstm.l0", y_f32=drop)
+        x1 = l0.forward()
+        if drop:                                                                      # nn.LSTM(dropout=p): on layer 0's outputs
+            y0d = p.buf("lstm.l0.y_dropped", (R, H), f32)
+            _ew(p, ptr(l0.y), H, ptr(self.masks[0]), H, y0d, R, H, nv.EW_MUL, "lstm.l0.dropout")
+            x1 = p.buf("lstm.l1.x", (B, T, H), bf)
+            _pack(p, y0d, H, R, H, x1, H, 0, nv.ACT_NONE, "lstm.l0.dropout -> bf16")
+        l1 = LstmLayerTrain(p, x1, H, *lw(1), B, T, tag="lstm.l1", y=head_in)
+        l1.forward()
+        self.layers = [l0, l1]
         _pack(p, self.cond, H, R, H, head_in, 2 * H, H, nv.ACT_NONE, "lstm.cat.obs_cond", src_row_div=T)
         z0 = p.buf("head.z0", (R, H), f32)
         p.add(linear_desc(a=head_in, rows=R, k=2 * H, a_ld=2 * H, w=pk.lin(HD("0.weight"), 2 * H), n=H, n_pad=H, w_ld=2 * H, out=z0,
                           ldc=H, bias=pk.vec(HD("0.bias"))), "output_head.0")
-        zn = p.buf("head.zn", (R, H), bf)
+        zn = p.buf("head.zn", (R, H), bf)                                            # Linear(256, A)'s operand (after dropout)
+        zn_f = p.buf("head.zn_f32", (R, H), f32) if drop else None
         ln_w, ln_b = pk.vec(HD("1.weight")), pk.vec(HD("1.bias"))
         d = nv.LnDesc()
         d.x, d.in_ld, d.in_row_stride, d.rows, d.D, d.gamma, d.beta, d.eps = ptr(z0), H, 1, R, H, ptr(ln_w), ptr(ln_b), 1e-5
-        d.out, d.out_dtype, d.out_ld, d.out_plane, d.act = ptr(zn), nv.VT_BF16, H, 0, nv.ACT_GELU
+        d.out, d.out_dtype, d.out_ld, d.out_plane, d.act = ptr(zn_f if drop else zn), nv.VT_F32 if drop else nv.VT_BF16, H, 0, nv.ACT_GELU
         p.add(d, "output_head.layernorm+gelu")
+        if drop:                                                                      # nn.Dropout(p) of the head
+            znd = p.buf("head.zn_dropped", (R, H), f32)
+            _ew(p, ptr(zn_f), H, ptr(self.masks[1]), H, znd, R, H, nv.EW_MUL, "output_head.dropout")
+            _pack(p, znd, H, R, H, zn, H, 0, nv.ACT_NONE, "output_head.dropout -> bf16")
         self.out = p.buf("out", (R, A), f32)
         w4 = pk.lin(HD("4.weight"), H)
         delta = p.buf("head.delta", (R, A), f32)
@@ -245,6 +282,10 @@ class LstmLossBackwardProgram:
         dzn = p.buf("head.dzn", (R, H), f32)
         p.add(linear_desc(a=dob.t, rows=R, k=apad, a_ld=apad, w=pk.lin(HD("4.weight"), apad, transpose=True), n=H, n_pad=H,
                           w_ld=apad, out=dzn, ldc=H), "head.4.dgrad")
+        if drop:
+            dzn_m = p.buf("head.dzn_masked", (R, H), f32)
+            _ew(p, ptr(dzn), H, ptr(self.masks[1]), H, dzn_m, R, H, nv.EW_MUL, "output_head.dropout.bwd")
+            dzn = dzn_m
         dz0, d1, d1zh = (p.buf(f"head.{n}", (R, H), f32) for n in ("dz0", "d1", "d1zh"))
         d = nv.LnGeluBwdDesc()
         d.z0, d.dzn, d.gamma, d.beta, d.eps, d.dz0, d.d1, d.d1zh, d.rows, d.D = ptr(z0), ptr(dzn), ptr(ln_w), ptr(ln_b), 1e-5, ptr(dz0), ptr(d1), ptr(d1zh), R, H
@@ -264,6 +305,10 @@ class LstmLossBackwardProgram:
         cs.x, cs.ld, cs.x_g, cs.G, cs.rows, cs.C, cs.out, cs.out_ld = ptr(dcomb, H), 2 * H, T * 2 * H, B, T, H, ptr(self.d_cond), H
         p.add(cs, "d_cond = sum_t dcomb[:, t, H:]")
         dx1 = self.layers[1].backward(dcomb.view(B, T, 2 * H))                       # reads columns [0, H) with row stride 2H
+        if drop:
+            dy0 = p.buf("lstm.l0.dy", (B, T, H), f32)
+            _ew(p, ptr(dx1), H, ptr(self.masks[0]), H, dy0, R, H, nv.EW_MUL, "lstm.l0.dropout.bwd")
+            dx1 = dy0
         dx0 = self.layers[0].backward(dx1)
         for l, lay in enumerate(self.layers):
             for k, v in lay.grads.items():

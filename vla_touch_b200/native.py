@@ -149,6 +149,10 @@ class LstmBwdDesc(C.Structure):
                 ("H", i32)]
 
 
+class DropmaskDesc(C.Structure):
+    _fields_ = [("inject", vp), ("p", f32), ("seed", u64), ("seed_dev", vp), ("stream", i32), ("mask", vp), ("n", i64)]
+
+
 class OptTensor(C.Structure):
     _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("ema", vp), ("numel", i64)]
 
@@ -164,7 +168,7 @@ EXPORTS = [
     "vt_program_num_ops", "vt_program_num_launches", "vt_program_add_gemm", "vt_program_add_layernorm",
     "vt_program_add_attention", "vt_program_add_mlp", "vt_debug_timestamps", "vt_program_add_imgstats", "vt_program_add_patchify", "vt_program_add_cls",
     "vt_program_add_pack", "vt_program_add_affine", "vt_program_add_tembed", "vt_program_add_sde",
-    "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_add_tcol", "vt_program_add_gnbwd", "vt_program_add_colsum", "vt_program_add_ewise", "vt_program_add_silossbwd", "vt_program_add_lstm_train", "vt_program_add_lstm_bwd", "vt_program_add_lngelubwd", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
+    "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_add_tcol", "vt_program_add_gnbwd", "vt_program_add_colsum", "vt_program_add_ewise", "vt_program_add_silossbwd", "vt_program_add_lstm_train", "vt_program_add_lstm_bwd", "vt_program_add_lngelubwd", "vt_program_add_dropmask", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
     "vt_pos_embed_resize", "vt_adamw_ema_step",
 ]
 
@@ -176,7 +180,7 @@ _ADD = {
     SilossDesc: "vt_program_add_siloss", TcolDesc: "vt_program_add_tcol", GnbwdDesc: "vt_program_add_gnbwd",
     ColsumDesc: "vt_program_add_colsum", EwiseDesc: "vt_program_add_ewise",
     SilossBwdDesc: "vt_program_add_silossbwd", LstmTrainDesc: "vt_program_add_lstm_train", LstmBwdDesc: "vt_program_add_lstm_bwd",
-    LnGeluBwdDesc: "vt_program_add_lngelubwd",
+    LnGeluBwdDesc: "vt_program_add_lngelubwd", DropmaskDesc: "vt_program_add_dropmask",
 }
 
 _lib: Optional[C.CDLL] = None
