@@ -568,3 +568,41 @@ def test_lstm_training_program_with_dropout():
     plan, check = bwd_cases.lstm_dropout_case(torch.device("cpu"))
     plan_emu.run(plan)
     assert check()["tensors"] == 18
+
+
+def test_native_encoder_training_matches_torch_autograd(monkeypatch):
+    """mlp_train: the 3-layer GELU state encoder (bridge_controller.py:42-48) forward + backward as plan ops behind a
+    torch.autograd.Function, interpreted on the CPU, against torch autograd of the same nn.Sequential -- before and after an
+    in-place parameter update."""
+    import torch.nn as nn
+    from vla_touch_b200 import mlp_train as mt
+    from vla_touch_b200.plan import Plan
+
+    class _Interp:
+        def __init__(self, plan):
+            self.plan = plan
+
+        def run(self, first=0, count=-1):
+            plan_emu.run(self.plan, first, count)
+
+    monkeypatch.setattr(Plan, "compile", lambda self: _Interp(self))
+    g = torch.Generator().manual_seed(5)
+    enc = nn.Sequential(nn.Linear(839, 256), nn.GELU(), nn.Linear(256, 256), nn.GELU(), nn.Linear(256, 256))
+    x = torch.randn(6, 839, generator=g)
+    dout = torch.randn(6, 256, generator=g)
+    cache = {}
+    for step in range(2):
+        enc.zero_grad()
+        out = mt.encoder_forward(enc, cache, x)
+        (out * dout).sum().backward()
+        got = {n: p.grad.clone() for n, p in enc.named_parameters()}
+        enc.zero_grad()
+        ref_out = enc(x)
+        (ref_out * dout).sum().backward()
+        assert float((out - ref_out).detach().abs().max()) <= 2e-2 * float(ref_out.detach().abs().max())
+        for n, p in enc.named_parameters():
+            assert float((got[n] - p.grad).abs().max()) <= 3e-2 * float(p.grad.abs().max()), (step, n)
+        with torch.no_grad():
+            for p in enc.parameters():
+                p.mul_(1.05)
+    assert len(cache) == 1

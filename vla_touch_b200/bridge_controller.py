@@ -167,8 +167,9 @@ class DiffusionController:
         Default: the inference path, one native program (DinoV2 x 2 + the state-encoder GEMMs), no autograd graph.
         differentiable=True (training, bridge_train.py:151,315): the frozen DinoV2 features come from the native kernels and
         the trainable 3-layer state encoder (0.5 MFLOP per sample, < 0.01 % of the step) is applied as the torch module it
-        is, so that `get_loss(...).backward()` reaches its parameters through d loss / d obs_cond; its backward kernels are
-        not built."""
+        is, so that `get_loss(...).backward()` reaches its parameters through d loss / d obs_cond.
+        differentiable="native": the same, with the encoder's forward and backward as native programs behind a
+        torch.autograd.Function (mlp_train.py; CPU-interpreted only so far, hence not the default)."""
         if differentiable:
             with torch.no_grad():
                 f1, f2 = self.encode_images(images_cam1, images_cam2)
@@ -177,7 +178,13 @@ class DiffusionController:
                 if forces is None:
                     raise ValueError("use_force=True but forces is None")
                 st = torch.cat((st, forces.to(self.device).float().reshape(f1.shape[0], -1)), dim=-1)
-            return self.state_encoder(torch.cat((f1, f2, st), dim=-1))
+            x = torch.cat((f1, f2, st), dim=-1)
+            if differentiable == "native":         # forward + backward of the encoder as native programs (mlp_train.py)
+                from .mlp_train import encoder_forward
+                if not hasattr(self, "_enc_train_cache"):
+                    self._enc_train_cache = {}
+                return encoder_forward(self.state_encoder, self._enc_train_cache, x)
+            return self.state_encoder(x)
         with torch.no_grad():
             return self._encode_observation_native(state, images_cam1, images_cam2, forces)
 
