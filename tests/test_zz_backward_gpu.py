@@ -145,3 +145,21 @@ def test_lstm_training_with_dropout():
     plan, check = bwd_cases.lstm_dropout_case(DEV)
     _run(plan)
     check()
+
+
+@pytest.mark.xfail(strict=False, reason="mlp_train uses the ewise gelu' op added after the round's GPU budget ended: never run on a B200")
+def test_native_encoder_training():
+    import torch.nn as nn
+    from vla_touch_b200 import mlp_train as mt
+    g = torch.Generator().manual_seed(5)
+    enc = nn.Sequential(nn.Linear(839, 256), nn.GELU(), nn.Linear(256, 256), nn.GELU(), nn.Linear(256, 256)).to(DEV)
+    x, dout = torch.randn(6, 839, generator=g).to(DEV), torch.randn(6, 256, generator=g).to(DEV)
+    out = mt.encoder_forward(enc, {}, x)
+    (out * dout).sum().backward()
+    got = {n: p.grad.clone() for n, p in enc.named_parameters()}
+    enc.zero_grad()
+    ref = enc(x)
+    (ref * dout).sum().backward()
+    assert float((out - ref).detach().abs().max()) <= 2e-2 * float(ref.detach().abs().max())
+    for n, p in enc.named_parameters():
+        assert float((got[n] - p.grad).abs().max()) <= 3e-2 * float(p.grad.abs().max()), n
