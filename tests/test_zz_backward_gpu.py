@@ -116,6 +116,8 @@ def test_split_k_wgrad(kind):
     check()
 
 
+@pytest.mark.xfail(strict=False, reason="first run of the backward kernels at the BASELINE batch (256 x 64 x 7): written after the "
+                                        "round's GPU budget ended, never run on a B200 at this size")
 def test_full_size_backward_is_additive_over_the_batch():
     """BASELINE batch (256 x T 64 x A 7, three nets): gradients of the full batch == mean of the gradients of its halves."""
     res = bwd_cases.batch_additivity_case(DEV)()
