@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VT_ABI_VERSION 1
+#define VT_ABI_VERSION 2
 
 enum { VT_OK = 0, VT_E_INVALID = -1, VT_E_CUDA = -2, VT_E_UNSUPPORTED = -3, VT_E_NODEVICE = -4 };
 enum { VT_BF16 = 0, VT_F32 = 1, VT_U8 = 2 };
@@ -448,6 +448,15 @@ typedef struct vt_opt_tensor {
   float* v;
   float* ema;       /* may be null */
   int64_t numel;
+  /* Gradient layout.  taps == 0: g is contiguous like p.  taps > 0: p is a convolution weight [rows][c][taps] (nn.Conv1d /
+   * nn.ConvTranspose1d order) and g is the weight-gradient GEMM's output [rows][taps][c_pad] (vt_tcol_desc), i.e.
+   * g index of p[(r * c + ci) * taps + k] = (r * taps + k) * c_pad + ci: the optimizer reads the training program's buffers
+   * in place (no unpack pass, no autograd copy). */
+  int32_t taps, c, c_pad;
+  int32_t reserved;
+  /* optional: the updated weight is also written as the bf16 GEMM operand of the next forward pass, at the same index as the
+   * gradient (the forward packing [rows][taps][c_pad] of unet._pack_conv; contiguous when taps == 0) */
+  void* w_op;
 } vt_opt_tensor;
 typedef struct vt_adamw_desc {
   const vt_opt_tensor* tensors;

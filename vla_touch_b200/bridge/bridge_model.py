@@ -64,6 +64,7 @@ class StochasticInterpolants:
         self.ema.to(device)
         self.device = device
         self._engines.clear()
+        self._loss_programs.clear()      # packed copies of the previous net's weights must not survive a (re)load
 
     def save_model(self, ckpt_path):
         torch.save({"net": self.net.state_dict(), "ema": self.ema.state_dict()}, os.path.join(ckpt_path, "bridge_model.pt"))
@@ -150,26 +151,45 @@ class StochasticInterpolants:
         sd = {k: v.detach() for k, v in self.net.state_dict().items()}
         return [sub_state_dict(sd, "b_net."), sub_state_dict(sd, "v_net."), sub_state_dict(sd, "s_net.")]
 
-    def _get_loss_with_grad(self, obs, x0, x1, step, z, params):
-        B, T, A = x1.shape
+    def _weights_token(self):
+        """Identity + version of the live parameters: a program's packed operand copies are current iff its token matches.
+        (Identity matters: a freshly loaded net has the same version sum as the one it replaces.)"""
+        params = list(self.net.parameters())
+        return (id(self.net), sum(p._version for p in params), getattr(self.ema, "param_writes", 0))
+
+    def train_program(self, B: int, T: int) -> LossBackwardProgram:
+        """The forward + backward program of get_loss for a batch shape (built once, weights re-packed in place)."""
         key = (B, T, "bwd")
-        version = sum(p._version for p in params)
         ent = self._loss_programs.get(key)
         if ent is None:
-            ent = [LossBackwardProgram(self._net_state_dicts(), A, B, T, float(self.d), self.device), version]
+            ent = [LossBackwardProgram(self._net_state_dicts(), self.net.input_dim, B, T, float(self.d), self.device), self._weights_token()]
             self._loss_programs[key] = ent
-        elif ent[1] != version:
-            ent[0].refresh(self._net_state_dicts())
-            ent[1] = version
+        return ent[0]
+
+    def sync_train_program(self, prog: LossBackwardProgram) -> None:
+        """Re-pack the operand copies if the parameters changed since the program last saw them."""
+        for ent in self._loss_programs.values():
+            if ent[0] is prog:
+                tok = self._weights_token()
+                if ent[1] != tok:
+                    prog.refresh(self._net_state_dicts())
+                    ent[1] = tok
+                return
+        raise KeyError("not a program of this model")
+
+    def _get_loss_with_grad(self, obs, x0, x1, step, z, params):
+        B, T, A = x1.shape
+        prog = self.train_program(B, T)
+        self.sync_train_program(prog)
         names = [n for n, _ in self.net.named_parameters()]
-        out = _BridgeLossFn.apply(ent[0], names, x0, x1, step, z, obs.float().flatten(1), *params)
+        out = _BridgeLossFn.apply(prog, names, x0, x1, step, z, obs.float().flatten(1), *params)
         return out[0], {'v_loss': out[1].detach(), 's_loss': out[2].detach(), 'b_loss': out[3].detach()}
 
     def _get_loss_value(self, nobs, prior_action, naction, step, z):
         device = self.device
         B, T, A = naction.shape
         key = (B, T)
-        version = sum(p._version for p in self.net.parameters())
+        version = self._weights_token()
         ent = self._loss_programs.get(key)
         sds = self._net_state_dicts()
         if ent is None:

@@ -24,16 +24,21 @@ from .visual_encoder import DINOv2Encoder, prepare_images
 class DiffusionController:
     def __init__(self, state_dim=10, hidden_dim=256, image_model_path="facebook/dinov2-small", diffusion_steps=10,
                  device="cuda", model_args=None, use_force=True, force_dim=3, *, image_state_dict=None,
-                 precise: bool = False, allow_synthetic_dino: bool = False, image_num_layers: Optional[int] = None):
+                 precise: bool = False, allow_synthetic_dino: bool = False, image_num_layers: Optional[int] = None,
+                 visual: bool = True):
         self.state_dim = state_dim
         self.hidden_dim = hidden_dim
         self.device = device
         self.diffusion_steps = diffusion_steps
         self.precise = precise
-        self.image_encoder = DINOv2Encoder(model_name=image_model_path, device=device, state_dict=image_state_dict,
-                                           precise=precise, allow_synthetic_weights=allow_synthetic_dino,
-                                           num_layers=image_num_layers)
-        self.latent_obs_dim = self.image_encoder.hidden_size
+        if visual:
+            self.image_encoder = DINOv2Encoder(model_name=image_model_path, device=device, state_dict=image_state_dict,
+                                               precise=precise, allow_synthetic_weights=allow_synthetic_dino,
+                                               num_layers=image_num_layers)
+            self.latent_obs_dim = self.image_encoder.hidden_size
+        else:                                   # bridge_controller_no_visual.py:32-33: obs = cat(state, force)
+            self.image_encoder = None
+            self.latent_obs_dim = 0
         self.use_force = use_force
         self.force_dim = force_dim
         self.model_args = model_args
@@ -90,7 +95,7 @@ class DiffusionController:
         ver = (dm.ema.version, self._enc_version())
         if eng is None:
             v_sd, s_sd = dm.ema_state_dicts()
-            eng = BridgeEngine(dino=self.image_encoder.weights(), enc_sd=self.state_encoder.state_dict(), v_sd=v_sd, s_sd=s_sd,
+            eng = BridgeEngine(dino=self.image_encoder.weights() if self.image_encoder is not None else None, enc_sd=self.state_encoder.state_dict(), v_sd=v_sd, s_sd=s_sd,
                                action_dim=dm.net.input_dim, state_dim=self.state_dim, force_dim=self.force_dim,
                                use_force=self.use_force, B=B, T=T, H=H, W=W, img_dtype=img_dtype, layout=layout,
                                diffuse_step=self.diffusion_steps, beta_max=dm.d, device=self.device, precise=self.precise,
@@ -136,7 +141,8 @@ class DiffusionController:
         st["free"][k].record(main)
 
     def _load_inputs(self, eng: BridgeEngine, state, img1, img2, forces):
-        self._upload_images(eng, img1, img2)
+        if self.image_encoder is not None:
+            self._upload_images(eng, img1, img2)
         eng.state.copy_(state.reshape(eng.B, -1), non_blocking=True)
         if self.use_force:
             if forces is None:
@@ -144,6 +150,11 @@ class DiffusionController:
             eng.forces.copy_(forces.reshape(eng.B, -1), non_blocking=True)
 
     def _prep(self, state, images_cam1, images_cam2, T, inject=False):
+        if self.image_encoder is None:          # no-visual ablation: the images, if any are passed, are ignored like the reference does
+            return self._engine(state.shape[0], T, 0, 0, torch.uint8, nv.LAYOUT_BHWC, inject), None, None
+        if images_cam1 is None or images_cam2 is None:
+            raise ValueError("this controller was built with the DinoV2 encoder: images_cam1 / images_cam2 are required "
+                             "(bridge_controller_no_visual.DiffusionController is the image-free variant)")
         img1, layout = prepare_images(images_cam1, self.device, keep_pinned_host=True)
         img2, layout2 = prepare_images(images_cam2, self.device, keep_pinned_host=True)
         if layout != layout2 or img1.shape != img2.shape or img1.dtype != img2.dtype:
@@ -157,28 +168,38 @@ class DiffusionController:
     # ---- reference API ----
     @torch.no_grad()
     def encode_images(self, images_cam1, images_cam2):
-        if images_cam1 is None or images_cam2 is None:
+        if images_cam1 is None or images_cam2 is None or self.image_encoder is None:
             return None
         return self.image_encoder.forward(images_cam1), self.image_encoder.forward(images_cam2)
 
-    def encode_observation(self, state, images_cam1=None, images_cam2=None, forces=None, *, differentiable: bool = False):
+    def _trains_encoder(self) -> bool:
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.state_encoder.parameters())
+
+    def encode_observation(self, state, images_cam1=None, images_cam2=None, forces=None, *, differentiable=None):
         """-> obs_cond [B, hidden_dim] (bridge_controller.py:112-134).
 
-        Default: the inference path, one native program (DinoV2 x 2 + the state-encoder GEMMs), no autograd graph.
-        differentiable=True (training, bridge_train.py:151,315): the frozen DinoV2 features come from the native kernels and
-        the trainable 3-layer state encoder (0.5 MFLOP per sample, < 0.01 % of the step) is applied as the torch module it
-        is, so that `get_loss(...).backward()` reaches its parameters through d loss / d obs_cond.
-        differentiable="native": the same, with the encoder's forward and backward as native programs behind a
-        torch.autograd.Function (mlp_train.py; CPU-interpreted only so far, hence not the default)."""
+        differentiable=None (default) follows torch's grad mode like a plain nn.Module call would: under torch.no_grad() /
+        inference_mode() (predict, validation, deployment) it is the inference path, one native program (DinoV2 x 2 + the
+        state-encoder GEMMs); with autograd enabled and a trainable state encoder (the training loop, bridge_train.py:151)
+        the frozen DinoV2 features come from the native kernels and the 3-layer state encoder (0.5 MFLOP per sample,
+        < 0.01 % of the step) is applied as the torch module it is, so that `get_loss(...).backward()` reaches its
+        parameters through d loss / d obs_cond.  differentiable="native": the same with the encoder's forward and backward
+        as native programs behind a torch.autograd.Function (mlp_train.py)."""
+        if differentiable is None:
+            differentiable = self._trains_encoder()
         if differentiable:
-            with torch.no_grad():
-                f1, f2 = self.encode_images(images_cam1, images_cam2)
-            st = state.to(self.device).float().reshape(f1.shape[0], -1)
+            B = state.shape[0]
+            st = state.to(self.device).float().reshape(B, -1)
             if self.use_force:
                 if forces is None:
                     raise ValueError("use_force=True but forces is None")
-                st = torch.cat((st, forces.to(self.device).float().reshape(f1.shape[0], -1)), dim=-1)
-            x = torch.cat((f1, f2, st), dim=-1)
+                st = torch.cat((st, forces.to(self.device).float().reshape(B, -1)), dim=-1)
+            if self.image_encoder is not None:
+                with torch.no_grad():
+                    f1, f2 = self.encode_images(images_cam1, images_cam2)
+                x = torch.cat((f1, f2, st), dim=-1)
+            else:
+                x = st
             if differentiable == "native":         # forward + backward of the encoder as native programs (mlp_train.py)
                 from .mlp_train import encoder_forward
                 if not hasattr(self, "_enc_train_cache"):

@@ -217,21 +217,68 @@ __global__ void __launch_bounds__(256) gn_colsum_kernel(const float* __restrict_
 }
 
 // out[g][c] = sum_r x[g][r][c] : bias gradient of a convolution without GroupNorm (conv1d_bwd's `dy.sum(dim=(0, 2))`).
-// grid = (ceil(C / 32), G), block = (32, 8)
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long ld, long long x_g, int rows, int C,
-                                                     float* __restrict__ out, int out_ld) {
-  __shared__ float red[8][33];
-  const int c = blockIdx.x * 32 + threadIdx.x, g = blockIdx.y;
-  float s = 0.f;
-  if (c < C)
-    for (int r = threadIdx.y; r < rows; r += 8) s += x[(long long)g * x_g + (long long)r * ld + c];
-  red[threadIdx.y][threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
-    float t = 0.f;
-    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    out[(long long)g * out_ld + c] = t;
+// HBM-bound column reduction: a CLUSTER of COLSUM_SPLIT CTAs shares one (32-column, group) strip, each CTA sums its slice of
+// the rows (32 row lanes x 8 float4 column lanes, 4 independent loads in flight per thread), the partials are combined
+// through distributed shared memory in a fixed order (deterministic, no atomics, no scratch buffer).
+// grid = (ceil(C / 32), G, COLSUM_SPLIT), cluster (1, 1, COLSUM_SPLIT), block = 256.
+constexpr int COLSUM_SPLIT = 8;
+__global__ void __cluster_dims__(1, 1, COLSUM_SPLIT) __launch_bounds__(256)
+    colsum_kernel(const float* __restrict__ x, long long ld, long long x_g, int rows, int C, float* __restrict__ out, int out_ld) {
+  __shared__ float red[32][33];
+  __shared__ float part[32];
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;       // 8 column lanes (4 columns each) x 32 row lanes
+  const int c0 = blockIdx.x * 32 + tx * 4, g = blockIdx.y;
+  const unsigned rank = cluster_ctarank();
+  const int per = (rows + COLSUM_SPLIT - 1) / COLSUM_SPLIT;
+  const int r0 = (int)rank * per, r1 = min(rows, r0 + per);
+  const float* xg = x + (long long)g * x_g;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(xg) & 15) == 0) && (c0 + 4 <= C);
+  if (vec) {
+    int r = r0 + ty;
+    for (; r + 96 < r1; r += 128) {
+      const float4 a = *reinterpret_cast<const float4*>(xg + (long long)r * ld + c0);
+      const float4 b = *reinterpret_cast<const float4*>(xg + (long long)(r + 32) * ld + c0);
+      const float4 c = *reinterpret_cast<const float4*>(xg + (long long)(r + 64) * ld + c0);
+      const float4 d = *reinterpret_cast<const float4*>(xg + (long long)(r + 96) * ld + c0);
+      s.x += (a.x + b.x) + (c.x + d.x);
+      s.y += (a.y + b.y) + (c.y + d.y);
+      s.z += (a.z + b.z) + (c.z + d.z);
+      s.w += (a.w + b.w) + (c.w + d.w);
+    }
+    for (; r < r1; r += 32) {
+      const float4 a = *reinterpret_cast<const float4*>(xg + (long long)r * ld + c0);
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    }
+  } else {
+    for (int r = r0 + ty; r < r1; r += 32) {
+      const float* row = xg + (long long)r * ld;
+      if (c0 < C) s.x += row[c0];
+      if (c0 + 1 < C) s.y += row[c0 + 1];
+      if (c0 + 2 < C) s.z += row[c0 + 2];
+      if (c0 + 3 < C) s.w += row[c0 + 3];
+    }
   }
+  red[ty][tx * 4] = s.x;
+  red[ty][tx * 4 + 1] = s.y;
+  red[ty][tx * 4 + 2] = s.z;
+  red[ty][tx * 4 + 3] = s.w;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x];
+    part[threadIdx.x] = t;
+  }
+  cluster_sync_all();
+  if (rank == 0 && threadIdx.x < 32) {
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    float t = 0.f;
+#pragma unroll
+    for (unsigned k = 0; k < COLSUM_SPLIT; ++k) t += ld_shared_cluster_f32(mapa_shared(smem_u32(&part[threadIdx.x]), k));
+    if (c < C) out[(long long)g * out_ld + c] = t;
+  }
+  cluster_sync_all();   // the partials must stay readable until rank 0 is done
 }
 
 __device__ __forceinline__ float gelu_erf_grad(float x) {

@@ -456,7 +456,9 @@ __global__ void __launch_bounds__(96) siloss_mean_kernel(const float* __restrict
   }
 }
 
-// fused multi-tensor AdamW + EMA (one thread block per chunk of one tensor, 128-bit accesses when aligned)
+// fused multi-tensor AdamW + EMA (one thread block per chunk of one tensor).  The gradient may still be in the layout the
+// weight-gradient GEMM wrote it in ([rows][taps][c_pad], see vt_opt_tensor), and the updated weight can be emitted as the
+// bf16 operand of the next forward pass at the same index, so no unpack / re-pack pass over the parameters exists.
 struct OptTensor {
   float* p;
   const float* g;
@@ -464,6 +466,8 @@ struct OptTensor {
   float* v;
   float* ema;
   long long numel;
+  int taps, c, c_pad, reserved;
+  __nv_bfloat16* w_op;
 };
 __global__ void __launch_bounds__(256) adamw_ema_kernel(const OptTensor* __restrict__ tensors, const long long* __restrict__ chunks,
                                                         int chunk_elems, float lr, float beta1, float beta2, float eps, float wd,
@@ -474,8 +478,16 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(const OptTensor* __restr
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
   const float one_minus_decay = 1.0f - ema_decay;
+  const unsigned ct = (unsigned)(t.c * t.taps);
   for (long long i = off + threadIdx.x; i < end; i += blockDim.x) {
-    const float g = t.g[i] * grad_scale;
+    long long j = i;
+    if (t.taps > 0) {   // p[(r * c + ci) * taps + k]  <->  g[(r * taps + k) * c_pad + ci]
+      const long long r = i / ct;
+      const unsigned rem = (unsigned)(i - r * ct);
+      const unsigned ci = rem / (unsigned)t.taps, k = rem - ci * (unsigned)t.taps;
+      j = (r * t.taps + k) * t.c_pad + ci;
+    }
+    const float g = t.g[j] * grad_scale;
     float p = t.p[i] * (1.0f - lr * wd);
     const float m = beta1 * t.m[i] + (1.0f - beta1) * g;
     const float v = beta2 * t.v[i] + (1.0f - beta2) * g * g;
@@ -484,6 +496,7 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(const OptTensor* __restr
     t.p[i] = p;
     t.m[i] = m;
     t.v[i] = v;
+    if (t.w_op) t.w_op[j] = __float2bfloat16(p);
     if (t.ema) {
       const float s = t.ema[i];
       t.ema[i] = s - one_minus_decay * (s - p);

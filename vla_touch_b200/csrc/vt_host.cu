@@ -659,8 +659,8 @@ struct GnbwdOp : Op {
 struct ColsumOp : Op {
   vt_colsum_desc d;
   int launch(cudaStream_t s) override {
-    vt::colsum_kernel<<<dim3((unsigned)((d.C + 31) / 32), (unsigned)d.G, 1), dim3(32, 8, 1), 0, s>>>(d.x, d.ld, d.x_g, d.rows, d.C,
-                                                                                                  d.out, d.out_ld);
+    vt::colsum_kernel<<<dim3((unsigned)((d.C + 31) / 32), (unsigned)d.G, vt::COLSUM_SPLIT), dim3(256, 1, 1), 0, s>>>(
+        d.x, d.ld, d.x_g, d.rows, d.C, d.out, d.out_ld);
     VT_LAUNCH_CHECK("colsum_kernel");
     return VT_OK;
   }

@@ -198,6 +198,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ra
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
+// 32-bit load from another CTA's shared memory (distributed shared memory, address from mapa_shared)
+__device__ __forceinline__ float ld_shared_cluster_f32(uint32_t cluster_addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+  return v;
+}
 // Arrive on a (possibly remote) barrier of the cluster.  Default semantics (release at CTA scope), as CUTLASS'
 // ClusterBarrier::arrive(cta_id): a cluster-scope release would drain every outstanding global store of the thread
 // first (measured: 10 % of the epilogue's stall samples), and the accumulator hand-off only needs the tcgen05 fence.

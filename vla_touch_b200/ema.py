@@ -22,6 +22,8 @@ class ExponentialMovingAverage:
         self.collected_params: Optional[List[torch.Tensor]] = None
         self._params_refs = [weakref.ref(p) for p in parameters]
         self.version = 0          # bumped whenever the shadow weights change (engines re-pack lazily)
+        self.param_writes = 0     # bumped whenever copy_to / restore overwrite the live parameters (p.data.copy_ does not
+                                  # move the autograd version counters the loss programs watch)
 
     def _get_parameters(self, parameters):
         if parameters is None:
@@ -56,6 +58,7 @@ class ExponentialMovingAverage:
     def copy_to(self, parameters=None) -> None:
         for s, p in zip(self.shadow_params, self._get_parameters(parameters)):
             p.data.copy_(s.data)
+        self.param_writes += 1
 
     def store(self, parameters=None) -> None:
         self.collected_params = [p.clone() for p in self._get_parameters(parameters)]
@@ -66,6 +69,7 @@ class ExponentialMovingAverage:
             raise RuntimeError("This ExponentialMovingAverage has no `store()`ed weights to `restore()`")
         for c, p in zip(self.collected_params, self._get_parameters(parameters)):
             p.data.copy_(c.data)
+        self.param_writes += 1
 
     @contextlib.contextmanager
     def average_parameters(self, parameters=None):

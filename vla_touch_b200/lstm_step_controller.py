@@ -171,9 +171,23 @@ class TactileLSTMController:
     def encode_images(self, images_cam1, images_cam2):
         return self.image_encoder.forward(images_cam1), self.image_encoder.forward(images_cam2)
 
-    @torch.no_grad()
+    def _grad_wanted(self, modules) -> bool:
+        return torch.is_grad_enabled() and any(p.requires_grad for m in modules for p in m.parameters())
+
     def encode_observation(self, state, images_cam1, images_cam2):
-        """obs_encoder(cat(cam1, cam2, state)) (:126-146): DinoV2 program + three tcgen05 GEMMs."""
+        """obs_encoder(cat(cam1, cam2, state)) (:126-146).  Under torch.no_grad() / inference_mode() (deployment, validation): the
+        DinoV2 program + three tcgen05 GEMMs.  With autograd enabled and a trainable obs_encoder (lstm_train.py:70): the frozen
+        DinoV2 features from the native kernels, then the 3-layer encoder as the torch module it is, so that
+        `get_loss(...).backward()` trains it through d loss / d obs_cond."""
+        if self._grad_wanted([self.obs_encoder]):
+            with torch.no_grad():
+                f1, f2 = self.encode_images(images_cam1, images_cam2)
+            st = state.to(self.device).float().reshape(f1.shape[0], -1)
+            return self.obs_encoder(torch.cat((f1, f2, st), dim=-1))
+        with torch.no_grad():
+            return self._encode_observation_native(state, images_cam1, images_cam2)
+
+    def _encode_observation_native(self, state, images_cam1, images_cam2):
         f1, f2 = self.encode_images(images_cam1, images_cam2)
         B = f1.shape[0]
         key = (B,)
@@ -205,7 +219,31 @@ class TactileLSTMController:
 
     @torch.no_grad()
     def encode_force(self, force):
-        raise NotImplementedError("encode_force is fused into forward()/predict() on the B200 path")
+        """force_encoder over [B,T,F] or [B,F] (:148-168): Linear(F,128) GELU Linear(128,128) as two tcgen05 GEMMs."""
+        orig = force.shape
+        f = force.to(self.device).float().reshape(-1, orig[-1])
+        R = f.shape[0]
+        ver = tuple(p._version for p in self.force_encoder.parameters())
+        ent = self._force_engines.get(R) if hasattr(self, "_force_engines") else None
+        if not hasattr(self, "_force_engines"):
+            self._force_engines = {}
+        if ent is None or ent[1] != ver:
+            m = Mode(self.precise)
+            plan = Plan(self.device)
+            W = MlpWeights(self.force_encoder.state_dict(), torch.device(self.device), m, idx=(0, 2))
+            W.register(plan)
+            fpad = W.dims[0][3]
+            fin = plan.buf("in.force", (R, orig[-1]), torch.float32)
+            f_op = plan.buf("f_op", (R, m.ld(fpad)), m.tdt)
+            out = plan.buf("out", (R, self.hidden_dim // 2), torch.float32)
+            plan.add(_pack_desc(fin, orig[-1], R, orig[-1], f_op, 0, m, fpad, 0), "force->operand")
+            build_mlp(plan, W, f_op, R, out, "force_encoder", acts=[nv.ACT_GELU, nv.ACT_NONE])
+            ent = ((plan, fin, out), ver)
+            self._force_engines[R] = ent
+        plan, fin, out = ent[0]
+        fin.copy_(f)
+        plan.compile().run()
+        return out.clone().reshape(*orig[:-1], -1)
 
     def _run(self, eng: LstmEngine, vla_n, obs_cond, forces):
         eng.vla.copy_(vla_n.reshape(eng.B, eng.T, -1))
@@ -255,17 +293,20 @@ class TactileLSTMController:
         self._run(eng, vla_n, obs_cond, force_seq.to(self.device))
         return eng.out.clone()
 
-    def get_loss(self, batch_dict, differentiable: bool = False):
+    def get_loss(self, batch_dict, differentiable=None):
         """MSE(forward, expert_act) (:321-337).
 
-        Default: the loss VALUE from the inference program (no autograd graph; validation, lstm_train.py:190-215).
-        differentiable=True (the training step, lstm_train.py:120-130): one native program computes the loss and, by an explicit
+        differentiable=None (default) follows torch's grad mode: under torch.no_grad() (validation, lstm_train.py:190-215) it is
+        the loss VALUE from the inference program; with autograd enabled and trainable modules (the training step,
+        lstm_train.py:120-130) the returned loss is differentiable: one native program computes the loss and, by an explicit
         backward (lstm_train.LstmLossBackwardProgram: BPTT recurrence kernel + dgrad / wgrad GEMMs), the gradients of the 18
         parameters of force_encoder / lstm / output_head and of obs_cond; `loss.backward()` hands them to the nn.Parameters and
         to the producer of `batch_dict['obs_cond']`.  bf16 operands.  In training mode (`controller.train()`) the reference's
         dropout (0.1 between the LSTM layers and in the head) is applied with in-kernel Philox masks, a new pair every call; in
-        eval mode the gradients are those of the deterministic network.  This path has only run on the CPU descriptor
-        interpreter so far."""
+        eval mode the gradients are those of the deterministic network."""
+        if differentiable is None:
+            differentiable = self._grad_wanted([self.force_encoder, self.lstm, self.output_head]) or \
+                (torch.is_grad_enabled() and batch_dict['obs_cond'].requires_grad)
         if not differentiable:
             with torch.no_grad():
                 return F.mse_loss(self.forward(batch_dict), batch_dict['expert_act'].to(self.device))
@@ -332,7 +373,7 @@ class _LstmLossFn(torch.autograd.Function):
         prog.run()
         ctx.prog, ctx.run_id = prog, prog.runs
         ctx.save_for_backward(prog.d_cond, *[prog.grads[n].reshape(p.shape) for n, p in zip(names, params)])
-        return torch.tensor(prog.loss(), dtype=torch.float32, device=cond.device)
+        return prog.loss_tensor().clone()
 
     @staticmethod
     def backward(ctx, gout):

@@ -343,6 +343,10 @@ class LstmLossBackwardProgram:
         self.runs = getattr(self, "runs", 0) + 1
         self.plan.compile().run()
 
+    def loss_tensor(self) -> torch.Tensor:
+        """The loss as a 0-d device tensor (no host synchronisation: the training loop reads it when it logs)."""
+        return self._sq_sum.sum() * (self.B * self.T * self.A / 4.0)
+
     def loss(self) -> float:
         """mean((out - expert)^2) from the squared loss derivative: sum(dout^2) * numel / 4"""
         n = self.B * self.T * self.A

@@ -17,6 +17,7 @@ ACT_NONE, ACT_GELU, ACT_MISH = 0, 1, 2
 EPI_LINEAR, EPI_GN = 0, 1
 LAYOUT_BHWC, LAYOUT_BCHW = 0, 1
 MAX_TAPS = 8
+ABI_VERSION = 2
 
 i32, i64, f32, u64, vp = C.c_int32, C.c_int64, C.c_float, C.c_uint64, C.c_void_p
 
@@ -154,7 +155,8 @@ class DropmaskDesc(C.Structure):
 
 
 class OptTensor(C.Structure):
-    _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("ema", vp), ("numel", i64)]
+    _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("ema", vp), ("numel", i64),
+                ("taps", i32), ("c", i32), ("c_pad", i32), ("reserved", i32), ("w_op", vp)]
 
 
 class AdamwDesc(C.Structure):
@@ -211,7 +213,7 @@ def lib() -> C.CDLL:
         L.vt_device_info.argtypes = [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
         L.vt_pos_embed_resize.argtypes = [vp, i32, vp, i32, i32, i32, vp]
         L.vt_adamw_ema_step.argtypes = [C.POINTER(AdamwDesc), vp]
-        if L.vt_abi_version() != 1:
+        if L.vt_abi_version() != ABI_VERSION:
             raise NativeError("libvt_b200.so ABI version mismatch; rebuild it")
         _lib = L
     return _lib

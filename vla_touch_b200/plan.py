@@ -37,6 +37,7 @@ class Plan:
         self.bufs: Dict[str, torch.Tensor] = {}
         self._reg: List[torch.Tensor] = []
         self._program: Optional[nv.Program] = None
+        self._arenas: Dict[str, list] = {}      # name -> [flat tensor, elements used, [(offset, numel, op index at allocation)]]
 
     # ---- memory ----
     def reg(self, t: torch.Tensor) -> torch.Tensor:
@@ -46,8 +47,34 @@ class Plan:
         self._reg.append(t)
         return t
 
-    def buf(self, name: str, shape: Sequence[int], dtype: torch.dtype, zero: bool = True) -> torch.Tensor:
+    def set_arena(self, arena: str, numel: int, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        """One contiguous allocation that `buf(..., arena=...)` carves its tensors from, in allocation order (the training
+        programs put every parameter gradient in one arena: the data-parallel all-reduce then runs in place on slices of it)."""
+        t = torch.zeros(numel, dtype=dtype, device=self.device)
+        self._arenas[arena] = [t, 0, []]
+        self._reg.append(t)
+        return t
+
+    def arena(self, arena: str):
+        """(flat tensor, elements used, [(offset, numel, ops in the plan when it was allocated)]) or None."""
+        a = self._arenas.get(arena)
+        return None if a is None else (a[0], a[1], a[2])
+
+    def buf(self, name: str, shape: Sequence[int], dtype: torch.dtype, zero: bool = True, arena: Optional[str] = None) -> torch.Tensor:
         assert name not in self.bufs, name
+        a = self._arenas.get(arena) if arena else None
+        if a is not None and a[0].dtype == dtype:
+            n = 1
+            for d in shape:
+                n *= int(d)
+            off = a[1]
+            if off + n > a[0].numel():
+                raise RuntimeError(f"plan arena '{arena}' is too small for '{name}' ({off} + {n} > {a[0].numel()} elements)")
+            t = a[0][off: off + n].view(tuple(shape))
+            a[2].append((off, n, len(self.descs)))
+            a[1] = off + (n + 63) // 64 * 64           # 256-byte granules: every tensor stays 16-byte (TMA / float4) aligned
+            self.bufs[name] = t
+            return t
         t = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
         self.bufs[name] = t
         self._reg.append(t)

@@ -165,7 +165,7 @@ def conv_wgrad(plan, ctx: DgradCtx, B: int, rows_src: _View, cols_src: _View, *,
     nm = tag + f"#{len(plan)}"
     rT = plan.buf(nm + ".rowsT", (Gs, round_up(R, 128), kp), torch.bfloat16)
     cT = plan.buf(nm + ".colsT", (Gs, n_pad, kp), torch.bfloat16)
-    dw = plan.buf(nm + ".dw", (G, R, n), torch.float32)
+    dw = plan.buf(nm + ".dw", (G, R, n), torch.float32, arena="grads")
     part = dw if S == 1 else plan.buf(nm + ".dw_part", (Gs, R, n), torch.float32)
     plan.add(_tcol(rows_src, Bs, Gs, rT, tap_off=[0], stride=1, t_out=t_out, c_pad=R), tag + ".rowsT")
     plan.add(_tcol(cols_src, Bs, Gs, cT, tap_off=list(tap_off), stride=stride, t_out=t_out, c_pad=c_pad), tag + ".colsT")
@@ -200,7 +200,7 @@ def gn_mish_backward(plan, ctx: DgradCtx, B: int, T: int, C: int, raw: torch.Ten
     nm = tag + f"#{len(plan)}"
     draw = plan.buf(nm + ".draw", (G, B, T, C), torch.bfloat16)
     part = plan.buf(nm + ".part", (G, B, 3, C), torch.float32)
-    dg, db, dbias = (plan.buf(nm + "." + k, (G, C), torch.float32) for k in ("dgamma", "dbeta", "dbias"))
+    dg, db, dbias = (plan.buf(nm + "." + k, (G, C), torch.float32, arena="grads") for k in ("dgamma", "dbeta", "dbias"))
     d = nv.GnbwdDesc()
     dv = as_view(dout, T)
     d.raw, d.dout, d.dout_ld, d.dout_g = ptr(raw), ptr(dv.t, dv.c0), dv.ld, B * T * dv.ld
@@ -259,7 +259,7 @@ def cast_bf16(plan, G: int, B: int, src, T: int, tag: str, c_pad: Optional[int] 
 def colsum(plan, G: int, B: int, x, T: int, tag: str) -> torch.Tensor:
     """fp32 [G][B*T][C] (tensor or channel window) -> [G][C]: the bias gradient of a convolution without GroupNorm."""
     v = as_view(x, T)
-    out = plan.buf(tag + f"#{len(plan)}.out", (G, v.C), torch.float32)
+    out = plan.buf(tag + f"#{len(plan)}.out", (G, v.C), torch.float32, arena="grads")
     d = nv.ColsumDesc()
     d.x, d.ld, d.x_g, d.G, d.rows, d.C, d.out, d.out_ld = ptr(v.t, v.c0), v.ld, B * T * v.ld, G, B * T, v.C, ptr(out), v.C
     plan.add(d, tag)

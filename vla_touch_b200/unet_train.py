@@ -344,6 +344,10 @@ class LossBackwardProgram:
         d.bvs, d.x0, d.x1, d.z_unit, d.tclip, d.d = ptr(tb.out), ptr(self.x0), ptr(self.x1), ptr(self.z), ptr(self.tclip), beta_max
         d.B, d.n, d.dvs = B, T * A, ptr(self.dvs)
         p.add(d, "si_losses.bwd")
+        # every parameter gradient lives in ONE contiguous fp32 arena, in the order the backward produces them: the
+        # data-parallel all-reduce runs in place on slices of it and the optimizer reads it in place (`grad_sources`)
+        n_net = sum(int(v.numel()) for v in self.sds[0].values())
+        p.set_arena("grads", 3 * (n_net + 256 * 1024) + 64 * 2048)
         self._g = build_unet_backward(p, W, self.sds, tb, self.dvs, self.film, self.dfilm)
         self._x = build_film_time_backward(p, W, self.sds, self.tf, B, self.film, self.dfilm, self._g)
 
@@ -383,3 +387,24 @@ class LossBackwardProgram:
     @property
     def d_cond(self) -> torch.Tensor:
         return self._x["dcond"].sum(dim=0)
+
+    def grad_arena(self):
+        """(flat fp32 tensor holding every parameter gradient, [(element offset, numel, op index)] in production order)."""
+        t, used, allocs = self.plan.arena("grads")
+        return t[:used], allocs
+
+    def grad_sources(self) -> Dict[str, Tuple[torch.Tensor, int, int, int]]:
+        """{'b_net.' / 'v_net.' / 's_net.' + reference key: (contiguous gradient buffer of that net, taps, c, c_pad)} in the
+        layout the kernels wrote (vt_opt_tensor: taps == 0 -> same order as the parameter, else [rows][taps][c_pad])."""
+        out = {}
+        for key, (buf, taps) in self._g.items():
+            shape = tuple(self.sds[0][key].shape)
+            for n, pfx in enumerate(self.NETS):
+                b = buf[n]
+                if taps:
+                    out[pfx + key] = (b, taps, shape[1], b.shape[-1] // taps)
+                elif b.dim() == 2 and b.shape[-1] != shape[-1]:      # linear weight whose K dimension is zero padded
+                    out[pfx + key] = (b, 1, shape[1], b.shape[-1])
+                else:
+                    out[pfx + key] = (b, 0, 0, 0)
+        return out
