@@ -1,13 +1,20 @@
 #!/usr/bin/env python
 """Benchmark of the VLA-Touch action-refinement hot path on B200 (contract: see DESIGN.md 'Measurement').
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2|cfg3|cfg1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME] [--only-headline]
 
-metric : refined action-chunks/s (one chunk = one DiffusionController.predict row: 2 camera images + state + tactile
-         + base chunk -> refined [T, A] chunk), whole-job aggregate over N GPUs (weak scaling: `batch` rows per GPU).
-value  : device-resident inputs, K CUDA-graph launches of the whole predict program, CUDA events, max over ranks.
-e2e    : the same metric through the public API (DiffusionController.predict) with pinned HOST inputs, H2D copies and
-         the D2H read of the refined chunks inside the timed region.
+Headline (BASELINE.json `metric`): refined action-chunks/s at batch 256 per GPU = `DiffusionController.predict` rows
+(one chunk = 2 camera images + state + tactile + base chunk -> refined [T, A] chunk), whole-job aggregate over N GPUs.
+  value : device-resident inputs, K CUDA-graph launches of the whole predict program, CUDA events, max over ranks.
+  e2e   : the same metric through the public API with pinned HOST inputs, H2D copies and the D2H read of the result
+          inside the timed region.
+The same JSON line carries, under "workloads", the other BASELINE configs measured by the same process on the same GPUs:
+  cfg2_train : bridge_train.py step (DinoV2 x 2 + state encoder + get_loss forward/backward of 3 U-Nets + NCCL gradient
+               all-reduce + fused AdamW/EMA), batch 256 per GPU                                   (BASELINE configs[1])
+  cfg3       : 50-step sampler, DinoV2-B/14, global batch 1024 (1024 / N rows per GPU: strong scaling)  (configs[2])
+  cfg4_lstm_train : lstm_train.py step, seq_len 128, batch 512 per GPU, NCCL gradient all-reduce        (configs[3])
+  cfg5_latency    : predict() latency p50 per call, global batch 64 (64 / N rows per GPU), host inputs  (configs[4])
+  cfg2_strong     : the headline at GLOBAL batch 256 (256 / N rows per GPU)
 --impl reference : the CPU restatement of the reference (oracle/, "port") on the host cores, bounded sample.
 """
 import argparse
@@ -24,18 +31,33 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (dino variant, hidden, heads, layers, hw, T, A, F, steps, batch per GPU)
     "cfg2": ("facebook/dinov2-small", 384, 6, 12, 224, 64, 7, 64, 10, 256),
-    "cfg3": ("facebook/dinov2-base", 768, 12, 12, 224, 64, 7, 64, 50, 128),
+    "cfg3": ("facebook/dinov2-base", 768, 12, 12, 224, 64, 7, 64, 50, 1024),
     "cfg1": ("facebook/dinov2-small", 384, 6, 12, 384, 16, 10, 3, 10, 1),
+    "cfg5": ("facebook/dinov2-small", 384, 6, 12, 224, 64, 7, 64, 10, 64),
 }
+MODEL_ARGS = {'interpolant_type': 'linear', 'gamma_type': '2^0.5*t(t-1)', 'epsilon_type': '1-t', 'prior_policy': 'vla',
+              'beta_max': 0.03, 'sde_type': 'vs', 'obs_dim': 256, 'obs_horizon': 1, 'net_type': 'unet1D_si',
+              'pretrain': False, 'context_frames': 2}
+
+
+def dino_flops(hidden, layers, hw):
+    n_tok = (hw // 14) ** 2 + 1
+    return 2 * (n_tok - 1) * 588 * hidden + layers * (24 * n_tok * hidden ** 2 + 4 * n_tok ** 2 * hidden)
+
+
+def unet_flops(T):
+    return 0.0115e9 + 0.02008e9 * T
 
 
 def flops_per_chunk(hidden, layers, hw, T, A, F, steps):
     """F = 2 F_dino + F_enc + n * 2 * F_unet(T)."""
-    n_tok = (hw // 14) ** 2 + 1
-    f_dino = 2 * (n_tok - 1) * 588 * hidden + layers * (24 * n_tok * hidden ** 2 + 4 * n_tok ** 2 * hidden)
     f_enc = 2 * ((2 * hidden + A + F) * 256 + 2 * 256 ** 2)
-    f_unet = 0.0115e9 + 0.02008e9 * T
-    return 2 * f_dino + f_enc + steps * 2 * f_unet
+    return 2 * dino_flops(hidden, layers, hw) + f_enc + steps * 2 * unet_flops(T)
+
+
+def flops_per_train_sample(hidden, layers, hw, T):
+    """2 DinoV2 forwards + 3 U-Net forwards + 3 U-Net backwards (2 x forward) = 2 F_dino + 9 F_unet."""
+    return 2 * dino_flops(hidden, layers, hw) + 9 * unet_flops(T)
 
 
 def synth_weights(hidden, layers, A, F, seed=7):
@@ -77,18 +99,14 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def run_reference(args, wl):
-    """--impl reference: the oracle port of the reference CPU path, all host threads, bounded sample per step."""
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference
+# ----------------------------------------------------------------------------------------------------------------------
+def _oracle_predict_fn(wl, Bs):
     import torch
     from oracle import vt_oracle as orc
     from vla_touch_b200 import synthetic as syn
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
     name, hidden, heads, layers, hw, T, A, F, steps, batch = wl
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
-    Bs = args.ref_batch
     dino, enc, net = synth_weights(hidden, layers, A, F)
     sub = lambda p: {k[len(p):]: v for k, v in net.items() if k.startswith(p)}
     v_sd, s_sd = sub("v_net."), sub("s_net.")
@@ -100,6 +118,21 @@ def run_reference(args, wl):
         with torch.no_grad():
             return orc.predict(dino, enc, v_sd, s_sd, stats, heads, inp["state"], inp["vla_actions"], inp["images_cam1"][:, None],
                                inp["images_cam2"][:, None], inp["forces"], steps, 0.03, noise)
+    return step
+
+
+def run_reference(args, wl):
+    """--impl reference: the oracle port of the reference CPU path, all host threads, bounded sample per step
+    (B = 32 rows per predict() call)."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name, hidden, heads, layers, hw, T, A, F, steps, batch = wl
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    Bs = args.ref_batch
+    step = _oracle_predict_fn(wl, Bs)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -118,31 +151,24 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(wl, seconds=15.0):
+def cpu_baseline(wl, seconds=15.0, Bs=8):
     import torch
-    from oracle import vt_oracle as orc
-    from vla_touch_b200 import synthetic as syn
-    name, hidden, heads, layers, hw, T, A, F, steps, batch = wl
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    Bs = 4
-    dino, enc, net = synth_weights(hidden, layers, A, F)
-    sub = lambda p: {k[len(p):]: v for k, v in net.items() if k.startswith(p)}
-    inp = syn.synth_predict_inputs(Bs, T, A, F, hw, 1234)
-    noise = syn.det_normal("bench.noise", (steps, Bs, T, A), 1)
-    f = lambda: orc.predict(dino, enc, sub("v_net."), sub("s_net."), syn.synth_stats(A), heads, inp["state"], inp["vla_actions"],
-                            inp["images_cam1"][:, None], inp["images_cam2"][:, None], inp["forces"], steps, 0.03, noise)
-    with torch.no_grad():
+    f = _oracle_predict_fn(wl, Bs)
+    f()
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
         f()
-        n, t0 = 0, time.perf_counter()
-        while time.perf_counter() - t0 < seconds:
-            f()
-            n += 1
+        n += 1
     dt = time.perf_counter() - t0
     return {"value": Bs * n / dt, "unit": "chunks/s", "cores": cores, "kind": "port",
             "sample": f"{n} predict() calls of {Bs} rows in {dt:.1f}s (oracle/vt_oracle.py restatement, torch CPU fp32, {cores} threads)"}
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------------
 def gemm_flops(d):
     """FLOPs of one tensor-core launch: an implicit GEMM, or the fused ViT MLP (two GEMMs rows x D x 4D)."""
     if hasattr(d, "w2"):                       # MlpDesc
@@ -150,59 +176,79 @@ def gemm_flops(d):
     return 2.0 * d.G * d.M * d.N * d.taps * d.kc * d.passes
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=0, help="rows per GPU (default: the workload's)")
-    ap.add_argument("--ref-batch", type=int, default=4)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
-    wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
-        args.steps = min(args.steps, 5)
-        return run_reference(args, wl)
-
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"      # the version banner goes to stdout and would precede the JSON line
-    import torch
-    import torch.distributed as dist
+def op_kind(d):
+    """Kernel family of a program op (the grouping the `roofline` block ranks by time share)."""
     from vla_touch_b200 import native as nv
+    if isinstance(d, nv.GemmDesc):
+        return "gemm_tc_kernel<GroupNorm+Mish+FiLM epilogue> (U-Net k5 convs)" if d.epi == nv.EPI_GN else \
+            ("gemm_tc_kernel<linear epilogue> (U-Net 1x1 / strided convs, FiLM)" if d.taps > 1 or d.t_box != 128 or d.G > 1
+             else "gemm_tc_kernel<linear epilogue> (ViT / encoder linears)")
+    if isinstance(d, nv.MlpDesc):
+        return "mlp_fused_kernel (ViT fc1+GELU+fc2)"
+    if isinstance(d, nv.AttnDesc):
+        return "attn_row_kernel (ViT attention)"
+    if hasattr(nv, "UnetPersistDesc") and isinstance(d, nv.UnetPersistDesc):
+        return "unet_persist_kernel (whole U-Net evaluation)"
+    return type(d).__name__.replace("Desc", "").lower() + "_kernel"
+
+
+class Ctx:
+    """Per-process benchmark context: rank / world, timing helpers."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank, self.world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = f"cuda:{self.local}"
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, n):
+        """ms for n calls: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks."""
+        torch = self.torch
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        ev0.record()
+        for _ in range(n):
+            fn()
+        ev1.record()
+        self.barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms)
+
+
+def make_controller(cx, wl, steps=None):
     from vla_touch_b200 import synthetic as syn
     from vla_touch_b200.bridge_controller import DiffusionController
-
-    name, hidden, heads, layers, hw, T, A, F, steps, batch = wl
-    batch = args.batch or batch
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    # stdout carries exactly ONE JSON line: NCCL writes its version banner to fd 1 when the first communicator is created,
-    # so fd 1 points at stderr until the line is printed
-    sys.stdout.flush()
-    saved_stdout = os.dup(1)
-    os.dup2(2, 1)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    nv.require_b200()
-    dev = f"cuda:{local}"
-
-    # ---- controller with seeded synthetic weights (no network: no checkpoints) ----
+    name, hidden, heads, layers, hw, T, A, F, n_steps, batch = wl
     dino_sd, enc_sd, net_sd = synth_weights(hidden, layers, A, F)
-    model_args = {'interpolant_type': 'linear', 'gamma_type': '2^0.5*t(t-1)', 'epsilon_type': '1-t', 'prior_policy': 'vla',
-                  'beta_max': 0.03, 'sde_type': 'vs', 'action_dim': A, 'obs_dim': 256, 'obs_horizon': 1, 'net_type': 'unet1D_si',
-                  'pretrain': False, 'context_frames': 2, 'horizon': T}
-    ctl = DiffusionController(state_dim=A, hidden_dim=256, image_model_path=name, diffusion_steps=steps, device=dev,
-                              model_args=model_args, use_force=True, force_dim=F, image_state_dict=dino_sd)
+    ctl = DiffusionController(state_dim=A, hidden_dim=256, image_model_path=name, diffusion_steps=steps or n_steps, device=cx.dev,
+                              model_args=dict(MODEL_ARGS, action_dim=A, horizon=T), use_force=True, force_dim=F,
+                              image_state_dict=dino_sd)
     ctl.state_encoder.load_state_dict(enc_sd)
     ctl.diffusion_model.net.load_state_dict(net_sd)
     ctl.diffusion_model.ema = type(ctl.diffusion_model.ema)(ctl.diffusion_model.net.parameters(), decay=0.75)
-    ctl.stats = {k: v.to(dev) for k, v in syn.synth_stats(A).items()}
+    ctl.stats = {k: v.to(cx.dev) for k, v in syn.synth_stats(A).items()}
+    return ctl
 
-    inp = syn.synth_predict_inputs(batch, T, A, F, hw, 1234 + rank)
+
+def predict_harness(cx, wl, batch):
+    """(controller, engine, api_step, h2d bytes, d2h bytes) for predict() on `batch` rows with pinned host inputs."""
+    torch = cx.torch
+    from vla_touch_b200 import synthetic as syn
+    name, hidden, heads, layers, hw, T, A, F, steps, _ = wl
+    ctl = make_controller(cx, wl)
+    inp = syn.synth_predict_inputs(batch, T, A, F, hw, 1234 + cx.rank)
     host = {k: v.pin_memory() for k, v in inp.items()}
     host["images_cam1"] = inp["images_cam1"][:, None].contiguous().pin_memory()   # deployment layout [B,1,H,W,3] uint8
     host["images_cam2"] = inp["images_cam2"][:, None].contiguous().pin_memory()
@@ -213,134 +259,401 @@ def main():
         out = ctl.predict(host["state"], host["vla_actions"], host["images_cam1"], host["images_cam2"], host["forces"])
         out_host.copy_(out, non_blocking=True)
 
-    # first call builds the engine, the FiLM time tables and the CUDA graph
-    api_step()
+    api_step()                      # builds the engine, the FiLM time tables and the CUDA graph
     torch.cuda.synchronize()
     eng = next(iter(ctl._engines.values()))
-    launches = eng.num_launches()
+    return ctl, eng, api_step, h2d, out_host.numel() * 4
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    def timed(fn, n):
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        ev0.record()
-        for _ in range(n):
-            fn()
-        ev1.record()
-        barrier()
-        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms)
-
-    # ---- value: device-resident inputs, graph replays ----
-    for _ in range(args.warmup):
+def bench_predict(cx, wl, batch, steps, warmup):
+    ctl, eng, api_step, h2d, d2h = predict_harness(cx, wl, batch)
+    for _ in range(warmup):
         eng.run_predict(graph=True)
-    sampler = ClockSampler(local)
-    sampler.start()
-    ms = timed(lambda: eng.run_predict(graph=True), args.steps)
-    sampler.stop_flag = True
-    value = world * batch * args.steps / (ms * 1e-3)
-    # ---- e2e: public API, pinned host inputs, H2D + D2H inside the timed region ----
-    for _ in range(args.warmup):
+    ms = cx.timed(lambda: eng.run_predict(graph=True), steps)
+    for _ in range(warmup):
         api_step()
-    ms_e2e = timed(api_step, args.steps)
-    e2e = world * batch * args.steps / (ms_e2e * 1e-3)
+    ms_e2e = cx.timed(api_step, steps)
+    return dict(ctl=ctl, eng=eng, ms=ms, ms_e2e=ms_e2e, h2d=h2d, d2h=d2h, launches=eng.num_launches())
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
 
-    # ---- roofline of the dominant kernel: the GEMM launch with the most FLOPs, timed alone on this stream ----
-    peaks = {}
+def peaks():
     try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return p, "MEASURED_PEAKS.json"
     except Exception:
-        pass
-    peak_tf = peaks.get("bf16_tflops", 1590.0)
-    peak_src = "MEASURED_PEAKS.json bf16_tflops (burst, kernel timed alone)" if peaks else "fallback 1590 (B200_PROFILING.md)"
+        return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def roofline_block(cx, eng, wl, workload, value, world):
+    """The kernel family with the largest share of the step (each op of the program timed alone, back to back), its achieved
+    algorithmic TFLOP/s against the burst bf16 peak, plus the fused ViT MLP / attention kernels and the whole step."""
+    torch = cx.torch
+    from vla_touch_b200 import native as nv
+    name, hidden, heads, layers, hw, T, A, F, steps, batch = wl
+    pk, pk_src = peaks()
+    peak_tf = pk["bf16_tflops"]
     prog = eng.plan.compile()
     a0, b1 = eng.predict_range()
-    gemms = [(gemm_flops(d), i) for i, d in enumerate(eng.plan.descs) if isinstance(d, (nv.GemmDesc, nv.MlpDesc)) and a0 <= i < b1]
-    total_gemm_flops = sum(f for f, _ in gemms)
-    fl, idx = max(gemms)
-    for _ in range(5):
-        prog.run(idx, 1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    reps = 50
-    ev0.record()
-    for _ in range(reps):
-        prog.run(idx, 1)
-    ev1.record()
-    torch.cuda.synchronize()
-    k_ms = ev0.elapsed_time(ev1) / reps
-    achieved = fl / (k_ms * 1e-3) / 1e12
-    # DRAM traffic of that launch from the committed ncu --set full capture (profiles/ncu_traffic.json, bytes per launch)
-    traffic, traffic_src = None, None
-    try:
-        table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        for key, rec in table.get(args.workload, {}).items():
-            if eng.plan.tags[idx].endswith(key):
-                traffic, traffic_src = rec["dram_bytes"], rec["source"]
-    except Exception:
-        pass
-    # the attention kernel of one ViT layer, timed the same way (BASELINE metric: DinoV2 attention TFLOP/s vs peak)
-    attn = None
-    att_ops = [i for i, d in enumerate(eng.plan.descs) if isinstance(d, nv.AttnDesc) and a0 <= i < b1]
-    if att_ops:
-        ai = att_ops[-1]
-        d = eng.plan.descs[ai]
-        for _ in range(5):
-            prog.run(ai, 1)
+    kinds = {}
+    reps = 3
+    for i in range(a0, b1):
+        d = eng.plan.descs[i]
+        prog.run(i, 1)
         torch.cuda.synchronize()
         ev0.record()
         for _ in range(reps):
-            prog.run(ai, 1)
+            prog.run(i, 1)
         ev1.record()
         torch.cuda.synchronize()
-        a_ms = ev0.elapsed_time(ev1) / reps
-        a_fl = 4.0 * d.tokens * d.tokens * 64 * d.heads * d.images
-        a_exp = float(d.tokens) * d.tokens * d.heads * d.images
-        attn = {"kernel": f"attention [{eng.plan.tags[ai]}]", "ms_per_launch": a_ms, "flops_per_launch": a_fl,
-                "achieved": a_fl / (a_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "frac_of_tensor_peak": a_fl / (a_ms * 1e-3) / 1e12 / peak_tf,
-                "exp_per_launch": a_exp,
-                "note": "head_dim 64: one exponential per 256 tensor FLOPs; at 16 MUFU ex2 / clock / SM the softmax alone "
-                        "needs 2x the cycles of the two MMAs, so the tensor pipe cannot exceed ~50 % in this kernel"}
+        us = ev0.elapsed_time(ev1) * 1e3 / reps
+        k = kinds.setdefault(op_kind(d), {"us": 0.0, "flops": 0.0, "launches": 0})
+        k["us"] += us
+        k["launches"] += 1
+        if isinstance(d, (nv.GemmDesc, nv.MlpDesc)) or (hasattr(nv, "UnetPersistDesc") and isinstance(d, nv.UnetPersistDesc)):
+            k["flops"] += getattr(d, "algo_flops", None) or gemm_flops(d)
+        elif isinstance(d, nv.AttnDesc):
+            k["flops"] += 4.0 * d.tokens * d.tokens * 64 * d.heads * d.images
+    total_us = sum(k["us"] for k in kinds.values())
+    ranked = sorted(kinds.items(), key=lambda kv: -kv[1]["us"])
+    dom_name, dom = ranked[0]
+    ach = dom["flops"] / (dom["us"] * 1e-6) / 1e12 if dom["us"] else 0.0
+    traffic, traffic_src = None, None
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        rec = table.get(workload, {}).get(dom_name.split(" ")[0])
+        if rec:
+            traffic, traffic_src = rec["dram_bytes"], rec["source"]
+    except Exception:
+        pass
     f_chunk = flops_per_chunk(hidden, layers, hw, T, A, F, eng.n_steps)
     step_tf = value / world * f_chunk / 1e12
-    roofline = {"bound": "tensor",
-                "kernel": f"{'mlp_fused_kernel' if isinstance(eng.plan.descs[idx], nv.MlpDesc) else 'gemm_tc_kernel'} [{eng.plan.tags[idx]}]", "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": peak_src, "flops_per_launch": fl, "ms_per_launch": k_ms, "attention": attn,
-                "whole_step": {"algorithmic_tflops_per_gpu": step_tf, "frac_of_sustained": step_tf / peaks.get("bf16_tflops_sustained", 1400.0),
-                               "gflop_per_chunk": f_chunk / 1e9, "executed_gemm_gflop_per_chunk": total_gemm_flops / batch / 1e9}}
+    by_kind = [{"kernel": n, "share_of_step": k["us"] / total_us, "launches": k["launches"], "us_per_launch": k["us"] / k["launches"],
+                "achieved_tflops": (k["flops"] / (k["us"] * 1e-6) / 1e12) if k["flops"] else None,
+                "frac_of_peak": (k["flops"] / (k["us"] * 1e-6) / 1e12 / peak_tf) if k["flops"] else None} for n, k in ranked[:6]]
+    return {"bound": "tensor", "kernel": dom_name, "selected_by": "largest share of the step's summed per-op times",
+            "share_of_step": dom["us"] / total_us, "launches_per_step": dom["launches"],
+            "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+            "flops_per_launch": dom["flops"] / dom["launches"], "ms_per_launch": dom["us"] / dom["launches"] * 1e-3,
+            "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": f"{pk_src} bf16_tflops (burst: ops timed alone, back to back)",
+            "by_kernel": by_kind,
+            "whole_step": {"algorithmic_tflops_per_gpu": step_tf, "frac_of_sustained": step_tf / pk.get("bf16_tflops_sustained", 1400.0),
+                           "gflop_per_chunk": f_chunk / 1e9}}
+
+
+def synth_train_batch(cx, wl, batch, device):
+    """A ControllerDataset-style minibatch (controller_dataset.py:142-236): ctx = 2 context frames; only the LAST context image is
+    read by the trainer (bridge_train.py:143-144), so the image tensors carry that frame alone, uint8 [B,1,H,W,3]."""
+    torch = cx.torch
+    from vla_touch_b200 import synthetic as syn
+    name, hidden, heads, layers, hw, T, A, F, steps, _ = wl
+    s = 4321 + cx.rank
+    b = {"states": syn.det_normal("tr.states", (batch, 2 + T, A), s), "forces": syn.det_normal("tr.forces", (batch, 2 + T, F), s),
+         "vla_actions": syn.det_uniform("tr.vla", (batch, T, A), s, -1.0, 1.0),
+         "images_cam1": syn.synth_images_u8("tr.cam1", batch, hw, s)[:, None].contiguous(),
+         "images_cam2": syn.synth_images_u8("tr.cam2", batch, hw, s)[:, None].contiguous()}
+    b["expert_actions"] = (b["vla_actions"] + 0.1 * syn.det_normal("tr.delta", (batch, T, A), s)).clamp(-1, 1)
+    if device == "pinned":
+        return {k: v.pin_memory() for k, v in b.items()}
+    return {k: v.to(device) for k, v in b.items()}
+
+
+def bench_train(cx, wl, batch, steps, warmup):
+    """bridge_train.py:296-342 at `batch` rows per GPU through vla_touch_b200.trainer.DiffusionControllerTrainer."""
+    torch, dist = cx.torch, cx.dist
+    from vla_touch_b200 import synthetic as syn
+    from vla_touch_b200.trainer import DiffusionControllerTrainer
+    name, hidden, heads, layers, hw, T, A, F, _, _ = wl
+    ctl = make_controller(cx, wl)
+    tr = DiffusionControllerTrainer(ctl, syn.synth_stats(A), device=cx.dev)
+    dev_batch = synth_train_batch(cx, wl, batch, cx.dev)
+    host_batch = synth_train_batch(cx, wl, batch, "pinned")
+    loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
+    losses = []
+
+    def dev_step():
+        losses.append(tr.train_step(dict(dev_batch))["loss"])
+
+    def api_step():
+        out = tr.train_step(dict(host_batch))          # H2D of the minibatch inside (images, states, forces, chunks)
+        loss_host.copy_(torch.stack([out["loss"], out["v_loss"], out["s_loss"], out["b_loss"]]), non_blocking=True)
+
+    for _ in range(max(warmup, 2)):
+        dev_step()
+    torch.cuda.synchronize()
+    l0 = float(losses[0])
+    ms = cx.timed(dev_step, steps)
+    l1 = float(losses[-1])
+    for _ in range(2):
+        api_step()
+    ms_e2e = cx.timed(api_step, steps)
+    prog = tr._prog
+    arena, _ = prog.grad_arena()
+    ar_ms = None
+    if cx.world > 1:                                   # the collective alone (not overlapped), for its share of the step
+        for _ in range(2):
+            dist.all_reduce(arena)
+        ar_ms = cx.timed(lambda: dist.all_reduce(arena), 5) / 5
+    if tr.timing:
+        print("train_step host ms per phase (accumulated):", {k: round(v, 1) for k, v in tr.timing.items()}, file=sys.stderr)
+    f_s = flops_per_train_sample(hidden, layers, hw, T)
+    pk, _ = peaks()
+    sps = cx.world * batch * steps / (ms * 1e-3)
+    h2d = sum(v.numel() * v.element_size() for v in host_batch.values())
+    return {"metric": "training samples/sec (bridge_train.py step)", "value": sps, "unit": "samples/s", "ms_per_step": ms / steps,
+            "batch_per_gpu": batch, "global_batch": batch * cx.world, "scaling": "weak", "dtype": "bf16",
+            "e2e": {"value": cx.world * batch * steps / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e / steps,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16},
+            "step": "encode_observation (DinoV2 x2 no_grad + state encoder with grad) -> get_loss forward+backward (b/v/s U-Nets, "
+                    "one native program) -> gradient all-reduce -> fused AdamW + EMA + cosine LR",
+            "gpu_launches_per_step": prog.plan.compile().num_launches() + 2 * 160 + 1,
+            "grad_elements": int(arena.numel()), "buckets": len(tr._buckets),
+            "collective": None if cx.world == 1 else {
+                "op": "NCCL all-reduce (SUM) of the fp32 gradient arena, in place, per bucket on a side stream during backward",
+                "ranks": cx.world, "bytes": int(arena.numel()) * 4, "ms_alone": ar_ms, "share_of_step_if_exposed": ar_ms / (ms / steps)},
+            "loss_first": l0, "loss_last": l1,
+            "roofline": {"bound": "tensor", "gflop_per_sample": f_s / 1e9, "achieved_tflops_per_gpu": sps / cx.world * f_s / 1e12,
+                         "frac_of_sustained": sps / cx.world * f_s / 1e12 / pk.get("bf16_tflops_sustained", 1400.0)}}
+
+
+def make_lstm_controller(cx, wl):
+    from vla_touch_b200 import shapes as shp
+    from vla_touch_b200 import synthetic as syn
+    from vla_touch_b200.lstm_step_controller import TactileLSTMController
+    name, hidden, heads, layers, hw, T, A, F, _, _ = wl
+    dino_sd, _, _ = synth_weights(hidden, layers, A, F)
+    lc = TactileLSTMController(state_dim=A, hidden_dim=256, num_layers=2, dropout=0.1, image_model_path=name, device=cx.dev,
+                               force_dim=F, use_force=True, image_state_dict=dino_sd)
+    for nm, mod in (("obs_encoder", lc.obs_encoder), ("force_encoder", lc.force_encoder), ("lstm", lc.lstm), ("output_head", lc.output_head)):
+        syn.fill_named_(mod.named_parameters(), 41, prefix=f"lstm.{nm}.")
+    return lc
+
+
+def bench_lstm_train(cx, wl, batch, T, steps, warmup):
+    """lstm_train.py:122-139 (BASELINE configs[3]: seq_len 128, batch 512 per GPU) through trainer.LSTMControllerTrainer."""
+    torch, dist = cx.torch, cx.dist
+    from vla_touch_b200 import synthetic as syn
+    from vla_touch_b200.trainer import LSTMControllerTrainer
+    name, hidden, heads, layers, hw, _, A, F, _, _ = wl
+    lc = make_lstm_controller(cx, wl)
+    tr = LSTMControllerTrainer(lc, syn.synth_stats(A), device=cx.dev)
+    s = 777 + cx.rank
+    b = {"states": syn.det_normal("lt.states", (batch, 2 + T, A), s), "forces": syn.det_normal("lt.forces", (batch, 2 + T, F), s),
+         "vla_actions": syn.det_uniform("lt.vla", (batch, T, A), s, -1.0, 1.0),
+         "images_cam1": syn.synth_images_u8("lt.cam1", batch, hw, s)[:, None].contiguous(),
+         "images_cam2": syn.synth_images_u8("lt.cam2", batch, hw, s)[:, None].contiguous()}
+    b["expert_actions"] = (b["vla_actions"] + 0.1 * syn.det_normal("lt.delta", (batch, T, A), s)).clamp(-1, 1)
+    dev_batch = {k: v.to(cx.dev) for k, v in b.items()}
+    host_batch = {k: v.pin_memory() for k, v in b.items()}
+    losses = []
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def dev_step():
+        losses.append(tr.train_step(dict(dev_batch)))
+
+    def api_step():
+        loss_host.copy_(tr.train_step(dict(host_batch)), non_blocking=True)
+
+    for _ in range(max(warmup, 2)):
+        dev_step()
+    torch.cuda.synchronize()
+    ms = cx.timed(dev_step, steps)
+    for _ in range(2):
+        api_step()
+    ms_e2e = cx.timed(api_step, steps)
+    # the recurrent part alone: the forward + backward program of the last get_loss call
+    prog = next(iter(lc._train_programs.values()))[0]
+    native = prog.plan.compile()
+    for _ in range(2):
+        native.run()
+    ms_prog = cx.timed(lambda: native.run(), 5) / 5
+    # deployment tick (lstm_step_controller.py:232-286): T = 1 step per control tick, state carried on the device
+    cond = torch.zeros(1, 256, device=cx.dev)
+    vla1, f1 = torch.zeros(1, A, device=cx.dev), torch.zeros(1, F, device=cx.dev)
+    with torch.no_grad():
+        lc.eval()
+        lc.predict(cond, vla1, f1, initialize=True)
+        torch.cuda.synchronize()
+        lat = []
+        for _ in range(50):
+            t0 = time.perf_counter()
+            lc.predict(cond, vla1, f1)
+            torch.cuda.synchronize()
+            lat.append((time.perf_counter() - t0) * 1e3)
+    lat.sort()
+    sps = cx.world * batch * steps / (ms * 1e-3)
+    n_par = sum(p.numel() for m in lc.trainable_modules for p in m.parameters())
+    return {"metric": "training sequences/sec (lstm_train.py step)", "value": sps, "unit": "sequences/s", "ms_per_step": ms / steps,
+            "seq_len": T, "batch_per_gpu": batch, "global_batch": batch * cx.world, "scaling": "weak", "dtype": "bf16",
+            "e2e": {"value": cx.world * batch * steps / (ms_e2e * 1e-3), "unit": "sequences/s", "ms_per_step": ms_e2e / steps,
+                    "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host_batch.values()), "d2h_bytes_per_step": 4},
+            "lstm_forward_backward_program_ms": ms_prog, "lstm_steps_per_s": batch * T / (ms_prog * 1e-3),
+            "collective": None if cx.world == 1 else {"op": "NCCL all-reduce (SUM) of the flat fp32 gradient buffer", "ranks": cx.world,
+                                                      "bytes": n_par * 4},
+            "predict_tick_ms_p50": lat[len(lat) // 2], "loss_first": float(losses[0]), "loss_last": float(losses[-1])}
+
+
+def bench_latency(cx, wl, batch, calls):
+    """BASELINE configs[4]: RDT stub (random chunks) + refine, p50 latency of one predict() call with host inputs (wall clock around
+    the call + synchronize, per rank; the reported p50 is the max over ranks)."""
+    torch = cx.torch
+    ctl, eng, api_step, h2d, d2h = predict_harness(cx, wl, batch)
+    for _ in range(3):
+        api_step()
+    torch.cuda.synchronize()
+    lat = []
+    for _ in range(calls):
+        cx.barrier()
+        t0 = time.perf_counter()
+        api_step()
+        torch.cuda.synchronize()
+        lat.append((time.perf_counter() - t0) * 1e3)
+    lat.sort()
+    p = torch.tensor([lat[len(lat) // 2], lat[int(len(lat) * 0.9)]], device=cx.dev)
+    if cx.world > 1:
+        cx.dist.all_reduce(p, op=cx.dist.ReduceOp.MAX)
+    return {"metric": "predict() latency per call, p50", "value": float(p[0]), "unit": "ms", "p90_ms": float(p[1]), "higher_is_better": False,
+            "batch_per_gpu": batch, "global_batch": batch * cx.world, "calls": calls, "chunks_per_s": cx.world * batch / (float(p[0]) * 1e-3),
+            "h2d_bytes_per_call": h2d, "d2h_bytes_per_call": d2h}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg1", "cfg2_train", "cfg4", "cfg5"])
+    ap.add_argument("--batch", type=int, default=0, help="rows per GPU (default: the workload's)")
+    ap.add_argument("--ref-batch", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only-headline", action="store_true", help="skip the secondary workloads (cfg2_train, cfg3, cfg4, cfg5)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
+    base = "cfg2" if args.workload in ("cfg2_train", "cfg4") else args.workload
+    wl = WORKLOADS[base]
+    if args.impl == "reference":
+        args.steps = min(args.steps, 4)
+        return run_reference(args, wl)
+
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # the version banner goes to stdout and would precede the JSON line
+    # stdout carries exactly ONE JSON line: NCCL writes its version banner to fd 1 when the first communicator is created,
+    # so fd 1 points at stderr until the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    cx = Ctx(args)
+    from vla_touch_b200 import native as nv
+    nv.require_b200()
+    torch, world, rank = cx.torch, cx.world, cx.rank
+    name, hidden, heads, layers, hw, T, A, F, steps, batch = wl
+    if args.workload in ("cfg3", "cfg5"):
+        batch = max(1, batch // world)          # global batch fixed by BASELINE: strong scaling
+    batch = args.batch or batch
+    strong = args.workload in ("cfg3", "cfg5")
+
+    def emit(line):
+        if rank == 0:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            cx.dist.destroy_process_group()
+
+    sampler = ClockSampler(cx.local)
+    sampler.start()
+    # ---- single secondary workloads selected explicitly ----
+    if args.workload == "cfg2_train":
+        r = bench_train(cx, wl, batch, args.steps, args.warmup)
+        sampler.stop_flag = True
+        r.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None,
+                  "data": "synthetic", "config": {"workload": "cfg2_train: bridge_train.py step, dinov2-small 224x224 x2 cams, T=64, A=7, F=64"},
+                  "clocks": sampler.summary(), "gpu_launches": r["gpu_launches_per_step"] * args.steps})
+        return emit(r)
+    if args.workload == "cfg4":
+        r = bench_lstm_train(cx, wl, args.batch or 512, 128, args.steps, args.warmup)
+        sampler.stop_flag = True
+        r.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None,
+                  "data": "synthetic", "config": {"workload": "cfg4: lstm_train.py step, seq_len 128, dinov2-small 224x224 x2 cams, A=7, F=64"},
+                  "clocks": sampler.summary()})
+        return emit(r)
+    if args.workload == "cfg5":
+        r = bench_latency(cx, wl, batch, max(args.steps, 20))
+        sampler.stop_flag = True
+        r.update({"n_gpus": world, "steps": max(args.steps, 20), "warmup": 3, "vs_baseline": None, "data": "synthetic", "scaling": "strong",
+                  "dtype": "bf16", "config": {"workload": "cfg5: random base chunks + predict(), global batch 64"}, "clocks": sampler.summary()})
+        return emit(r)
+
+    # ---- headline: predict ----
+    res = bench_predict(cx, wl, batch, args.steps, args.warmup)
+    sampler.stop_flag = True
+    eng, ms, ms_e2e = res["eng"], res["ms"], res["ms_e2e"]
+    value = world * batch * args.steps / (ms * 1e-3)
+    e2e = world * batch * args.steps / (ms_e2e * 1e-3)
     line = {
         "metric": "refined action-chunks/sec", "value": value, "unit": "chunks/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload}: DiffusionController.predict, {name} ({layers} layers), {hw}x{hw} uint8 x2 cams, "
                                f"T={T}, A={A}, F={F}, {eng.n_steps} SDE steps, batch {batch}/GPU",
-                   "batch_per_gpu": batch, "global_batch": batch * world, "parallelism": f"dp{world} (no collective)",
+                   "batch_per_gpu": batch, "global_batch": batch * world, "parallelism": f"dp{world} (no collective on the inference path)",
                    "l2": "no flush: per-step working set (activations ~1.3 GB at batch 256) exceeds the 126 MB L2",
                    "weights": "seeded synthetic (no network)", "noise": "in-kernel Philox"},
-        "e2e": {"value": e2e, "unit": "chunks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_host.numel() * 4,
+        "e2e": {"value": e2e, "unit": "chunks/s", "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"],
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches * args.steps, "launches_per_step": launches,
-        "clocks": sampler.summary(), "roofline": roofline,
+        "gpu_launches": res["launches"] * args.steps, "launches_per_step": res["launches"],
+        "clocks": sampler.summary(),
     }
-    if not args.no_cpu_baseline and world == 1:
+    if rank == 0:
+        line["roofline"] = roofline_block(cx, eng, wl, args.workload, value, world)
+    cx.barrier()
+    del res, eng
+    torch.cuda.empty_cache()
+    # ---- the other BASELINE configs, same process, same GPUs ----
+    if not args.only_headline and args.workload == "cfg2":
+        k = max(3, min(args.steps, 8))
+        extra = {}
+
+        def attempt(key, fn):
+            try:
+                extra[key] = fn()
+            except Exception as e:               # a secondary workload must not take the headline down with it
+                extra[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+
+        attempt("cfg2_train", lambda: bench_train(cx, wl, 256, k, 3))
+        attempt("cfg4_lstm_train", lambda: bench_lstm_train(cx, wl, 512, 128, k, 3))
+        wl3 = WORKLOADS["cfg3"]
+
+        def cfg3():
+            b3 = max(1, wl3[9] // world)
+            r3 = bench_predict(cx, wl3, b3, 3, 3)
+            v = world * b3 * 3 / (r3["ms"] * 1e-3)
+            f3 = flops_per_chunk(wl3[1], wl3[3], wl3[4], wl3[5], wl3[6], wl3[7], wl3[8])
+            pk, _ = peaks()
+            return {"metric": "refined action-chunks/sec", "value": v, "unit": "chunks/s", "ms_per_step": r3["ms"] / 3, "scaling": "strong",
+                    "batch_per_gpu": b3, "global_batch": b3 * world, "sde_steps": 50, "model": wl3[0],
+                    "e2e": {"value": world * b3 * 3 / (r3["ms_e2e"] * 1e-3), "unit": "chunks/s", "h2d_bytes_per_step": r3["h2d"],
+                            "d2h_bytes_per_step": r3["d2h"]},
+                    "gflop_per_chunk": f3 / 1e9, "algorithmic_tflops_per_gpu": v / world * f3 / 1e12,
+                    "frac_of_sustained": v / world * f3 / 1e12 / pk.get("bf16_tflops_sustained", 1400.0)}
+        attempt("cfg3", cfg3)
+        attempt("cfg5_latency", lambda: bench_latency(cx, WORKLOADS["cfg5"], max(1, 64 // world), 20))
+        if world > 1:
+            def strong_headline():
+                bs = max(1, 256 // world)
+                r = bench_predict(cx, wl, bs, k, 3)
+                return {"metric": "refined action-chunks/sec", "value": world * bs * k / (r["ms"] * 1e-3), "unit": "chunks/s",
+                        "ms_per_step": r["ms"] / k, "scaling": "strong", "batch_per_gpu": bs, "global_batch": bs * world,
+                        "e2e": {"value": world * bs * k / (r["ms_e2e"] * 1e-3), "unit": "chunks/s"}}
+            attempt("cfg2_strong", strong_headline)
+        line["workloads"] = extra
+    if not args.no_cpu_baseline and world == 1 and rank == 0:
         line["cpu_baseline"] = cpu_baseline(wl)
-    sys.stdout.flush()
-    os.dup2(saved_stdout, 1)
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    emit(line)
 
 
 if __name__ == "__main__":

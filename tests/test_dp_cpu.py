@@ -117,3 +117,64 @@ def test_data_parallel_training_step_world2_gloo():
         mp.spawn(_train_worker, args=(world, _free_port(), out), nprocs=world, join=True)
         res = dict(out)
         assert res.get(0) is True and res.get(1) is True, res
+
+
+def test_gradient_arena_buckets_are_complete_when_their_op_index_is_reached():
+    """The trainer launches the all-reduce of a bucket of the gradient arena as soon as the backward program has executed the
+    bucket's `ready` op count (optim.arena_buckets).  Claim checked here on the CPU descriptor interpreter: after ops [0, ready)
+    every element of the bucket already holds its final value (no later op writes into it), the buckets tile the arena, and all
+    438 parameter gradients live inside it."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path[:0] = [here]
+    import plan_emu
+    from vla_touch_b200 import shapes as shp
+    from vla_touch_b200 import synthetic as syn
+    from vla_touch_b200.optim import arena_buckets
+    from vla_touch_b200.params import sub_state_dict
+    from vla_touch_b200.unet_train import LossBackwardProgram
+    A, B, T = 7, 2, 8
+    full = syn.synth_state_dict(shp.si_net_shapes(A, 256), 21, prefix="net.")
+    lp = LossBackwardProgram([sub_state_dict(full, p) for p in ("b_net.", "v_net.", "s_net.")], A, B, T, 0.03, "cpu")
+    g = torch.Generator().manual_seed(3)
+    lp.set_inputs(torch.rand(B, T, A, generator=g) * 2 - 1, torch.rand(B, T, A, generator=g) * 2 - 1, torch.randn(B, 256, generator=g),
+                  torch.rand(B, generator=g), torch.randn(B, T, A, generator=g))
+    arena, allocs = lp.grad_arena()
+    buckets = arena_buckets(allocs, arena.numel(), bucket_elems=12 << 20)
+    assert len(buckets) >= 4 and buckets[0][0] == 0 and buckets[-1][1] == arena.numel() and buckets[-1][2] is None
+    assert all(a[1] == b[0] for a, b in zip(buckets, buckets[1:]))
+    ready = [b[2] for b in buckets[:-1]]
+    assert ready == sorted(ready) and all(0 < r < len(lp.plan) for r in ready)
+    base, end = arena.data_ptr(), arena.data_ptr() + arena.numel() * 4
+    src = lp.grad_sources()
+    assert len(src) == 438 and all(base <= t.data_ptr() < end and t.is_contiguous() for t, _, _, _ in src.values())
+    snaps, op0 = [], 0
+    for a, b, r in buckets:
+        r = len(lp.plan) if r is None else r
+        plan_emu.run(lp.plan, op0, r - op0)
+        op0 = r
+        snaps.append(arena[a:b].clone())
+    assert float(arena.abs().max()) > 0
+    for (a, b, _), snap in zip(buckets, snaps):
+        assert torch.equal(arena[a:b], snap)
+
+
+def _arena_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vla_touch_b200.optim import allreduce_arena, arena_buckets
+    arena = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    allocs = [(i * 100, 100, i) for i in range(10)]
+    works = [allreduce_arena(arena[a:b]) for a, b, _ in arena_buckets(allocs, 1000, bucket_elems=250)]
+    for w in works:
+        w.wait()
+    out[rank] = bool(torch.equal(arena, torch.arange(1000, dtype=torch.float32) * 3))
+    dist.destroy_process_group()
+
+
+def test_arena_allreduce_in_place_world2_gloo():
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_arena_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}

@@ -29,7 +29,7 @@ class StochasticInterpolants:
         self.step_override: Optional[torch.Tensor] = None     # get_loss: injected U(0,1) draws [B]
         self.z_override: Optional[torch.Tensor] = None        # get_loss: injected N(0,1) draws [B,T,A]
         self._loss_programs: Dict[tuple, list] = {}
-        self._seed = 0
+        self._seed = int(torch.initial_seed()) & 0x7FFFFFFF       # Philox base seed follows torch.manual_seed
         if model_args:
             self.load_model_args(model_args)
 
@@ -172,7 +172,7 @@ class StochasticInterpolants:
             if ent[0] is prog:
                 tok = self._weights_token()
                 if ent[1] != tok:
-                    prog.refresh(self._net_state_dicts())
+                    prog.refresh_graphed(self._net_state_dicts())
                     ent[1] = tok
                 return
         raise KeyError("not a program of this model")

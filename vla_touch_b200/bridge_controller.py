@@ -57,7 +57,7 @@ class DiffusionController:
         self._engines: Dict[tuple, BridgeEngine] = {}
         self._versions: Dict[tuple, tuple] = {}
         self.noise_override: Optional[torch.Tensor] = None   # [n_steps,B,T,A] injected N(0,1) draws (parity tests)
-        self._seed = 0
+        self._seed = int(torch.initial_seed()) & 0x7FFFFFFF       # Philox base seed follows torch.manual_seed (new stream per call)
         self.to(device)
 
     # ---- module-ish plumbing ----

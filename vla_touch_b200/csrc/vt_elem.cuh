@@ -374,7 +374,9 @@ __global__ void __launch_bounds__(256) sde_step_kernel(float* __restrict__ x, co
       z = noise[idx];
     } else {
       curandStatePhilox4_32_10_t st;
-      curand_init(seed, (unsigned long long)idx, (unsigned long long)step, &st);
+      // one whole Philox counter block (4 outputs) per step: curand_normal consumes two outputs (Box-Muller), so an offset
+      // of `step` alone would let consecutive steps of the same element share a uniform
+      curand_init(seed, (unsigned long long)idx, 4ull * (unsigned long long)step, &st);
       z = curand_normal(&st);
     }
     const float sv = __fmul_rn(s[idx], ginv);                                  // s = s * gamma_inv

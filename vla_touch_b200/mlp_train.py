@@ -4,7 +4,7 @@ TactileLSTMController.obs_encoder (lstm_step_controller.py:40-46), Sequential(Li
 Forward keeps the GELU inputs; backward (from d loss / d obs_cond, which the diffusion / LSTM training program produces) is
 dgrad / wgrad GEMMs on gemm_tc_kernel (the batch is the K dimension of the weight gradients), `a * gelu'(b)` and column sums.
 `MlpTrainFn` exposes it to torch autograd: forward() runs the forward range of the program, backward() the backward range.
-Written after the round's GPU budget ended: checked on the CPU descriptor interpreter only.
+GPU-checked by tests/test_zz_backward_gpu.py::test_native_encoder_training.
 """
 from __future__ import annotations
 
@@ -71,6 +71,7 @@ class MlpTrainProgram:
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         self.x.copy_(x)
+        self.runs = getattr(self, "runs", 0) + 1
         self.plan.compile().run(0, self.n_forward_ops)
         return self.out
 
@@ -86,10 +87,15 @@ class MlpTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, prog: MlpTrainProgram, names: Sequence[str], x, *params):
         ctx.prog, ctx.names = prog, names
-        return prog.forward(x).clone()
+        out = prog.forward(x).clone()
+        ctx.run_id = prog.runs
+        return out
 
     @staticmethod
     def backward(ctx, gout):
+        if ctx.prog.runs != ctx.run_id:
+            raise RuntimeError("the encoder was evaluated again (same batch size) before this backward(): its saved activations "
+                               "were overwritten -- call backward() first, or evaluate the second batch under torch.no_grad()")
         g = ctx.prog.backward(gout.contiguous())
         return (None, None, None) + tuple(g[n].clone() for n in ctx.names)
 

@@ -21,12 +21,17 @@ from . import native as nv
 CHUNK = 65536
 
 
-def _bump_version(p: torch.Tensor) -> None:
+def _bump_versions(params: Sequence[torch.Tensor]) -> None:
+    """Advance the autograd version counters of tensors a native kernel has written in place (one call for all of them)."""
     try:
-        torch._C._autograd._unsafe_set_version_counter(p, p._version + 1)
+        torch._C._autograd._unsafe_set_version_counter(tuple(params), tuple(p._version + 1 for p in params))
     except Exception:
         with torch.no_grad():
-            p.add_(0)
+            torch._foreach_add_(list(params), 0)
+
+
+def _bump_version(p: torch.Tensor) -> None:
+    _bump_versions((p,))
 
 
 class FusedAdamWEMA:
@@ -157,8 +162,7 @@ class FusedAdamWEMA:
         d.bias_corr1, d.bias_corr2 = 1 - self.betas[0] ** t, 1 - self.betas[1] ** t
         d.ema_decay, d.grad_scale = ema_decay, grad_scale
         nv.check(nv.lib().vt_adamw_ema_step(C.byref(d), C.c_void_p(nv.current_stream_ptr())))
-        for p in self.params:          # the kernel wrote the parameters in place: bump their version counters so that
-            _bump_version(p)           # engines holding packed copies (BridgeEngine, LossProgram) re-pack lazily
+        _bump_versions(self.params)    # the kernel wrote the parameters in place: engines holding packed copies re-pack lazily
 
 
 def bucket_plan(numels: Sequence[int], bucket_elems: int = 32 << 20) -> List[List[int]]:

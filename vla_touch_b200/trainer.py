@@ -44,6 +44,8 @@ class DiffusionControllerTrainer:
         self._prog = None
         self._comm = None
         self.timing: Dict[str, float] = {}
+        import os
+        self._timing_on = os.environ.get("VT_TRAIN_TIMING") == "1"
 
     # ---- bridge_train.py:105-164 ----
     def _prepare_batch_for_diffusion(self, batch):
@@ -78,12 +80,23 @@ class DiffusionControllerTrainer:
             self._prog = prog
         return prog
 
+    def _tick(self, name: str, t0: float) -> float:
+        """Developer timing (env VT_TRAIN_TIMING=1): host wall-clock per phase, accumulated in self.timing."""
+        import time
+        t1 = time.perf_counter()
+        if self._timing_on:
+            self.timing[name] = self.timing.get(name, 0.0) + (t1 - t0) * 1e3
+        return t1
+
     def train_step(self, batch) -> Dict[str, torch.Tensor]:
         """bridge_train.py:296-342 for one minibatch; returns {'loss', 'v_loss', 's_loss', 'b_loss'} as device tensors."""
+        import time
         import torch.distributed as dist
+        t = time.perf_counter()
         self.controller.train()
         dm = self.controller.diffusion_model
         bd = self._prepare_batch_for_diffusion(batch)
+        t = self._tick("prepare_batch", t)
         obs = bd['obs_cond']
         x1, x0 = bd['expert_act'].float(), bd['vla_act'].float()
         B, T, A = x1.shape
@@ -91,7 +104,9 @@ class DiffusionControllerTrainer:
         self.optimizer.zero_grad()
         step = dm.step_override if dm.step_override is not None else torch.rand(B, device=self.device)
         z = dm.z_override if dm.z_override is not None else torch.randn_like(x1)
+        t = self._tick("ensure+zero_grad+rng", t)
         dm.sync_train_program(prog)
+        t = self._tick("sync_train_program", t)
         prog.set_inputs(x0, x1, obs.detach().float().flatten(1), step, z)
         world = _world(self.group)
         if world == 1:
@@ -115,6 +130,7 @@ class DiffusionControllerTrainer:
                     works.append(dist.all_reduce(self._arena[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
             if op0 < len(prog.plan):
                 native.run(op0, len(prog.plan) - op0)
+        t = self._tick("program", t)
         out = prog.out.clone()
         if obs.requires_grad:                               # d loss / d obs_cond -> state encoder (torch autograd, 0.33 M parameters)
             obs.backward(prog.d_cond.view_as(obs))
@@ -123,7 +139,9 @@ class DiffusionControllerTrainer:
             works.append(dist.all_reduce(self.optimizer.grad_flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
             for w in works:
                 w.wait()
+        t = self._tick("encoder backward + collective wait", t)
         self.optimizer.step(grad_scale=1.0 / world)         # AdamW + EMA + cosine LR, one launch
+        self._tick("optimizer", t)
         return {'loss': out[0], 'v_loss': out[1], 's_loss': out[2], 'b_loss': out[3]}
 
 

@@ -67,12 +67,12 @@ def repack_all(ctx, sds: Sequence[dict]) -> None:
 def pack_dgrad_conv(ws: Sequence[torch.Tensor], taps_k: Sequence[int], cout_pad: int, mode: Mode) -> torch.Tensor:
     """Forward Conv1d weights [C_out, C_in, K] of G nets -> dgrad B operand [G][round128(C_in)][len(taps_k) * cout_pad]:
     row ci holds, tap by tap (in the order of taps_k), W[:, ci, k] over the output channels (the GEMM's K dimension)."""
-    return _pack_conv([w.permute(1, 0, 2)[:, :, list(taps_k)] for w in ws], cout_pad, mode)
+    return _pack_conv([torch.stack([w.permute(1, 0, 2)[:, :, k] for k in taps_k], dim=-1) for w in ws], cout_pad, mode)
 
 
 def pack_dgrad_convT(ws: Sequence[torch.Tensor], taps_k: Sequence[int], cout_pad: int, mode: Mode) -> torch.Tensor:
     """ConvTranspose1d weights [C_in, C_out, K] are already [n = C_in][channel = C_out][tap]."""
-    return _pack_conv([w[:, :, list(taps_k)] for w in ws], cout_pad, mode)
+    return _pack_conv([torch.stack([w[:, :, k] for k in taps_k], dim=-1) for w in ws], cout_pad, mode)
 
 
 def conv_dgrad(plan, ctx: DgradCtx, B: int, dy: _View, dx: _View, ws: Sequence[torch.Tensor], pad: int, tag: str = "",

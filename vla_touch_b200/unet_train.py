@@ -358,6 +358,24 @@ class LossBackwardProgram:
         self.W.refresh(sds_bvs)
         ub.repack_all(self.W, sds_bvs)
 
+    def refresh_graphed(self, sds_bvs: Sequence[SD]) -> None:
+        """`refresh` replayed as one CUDA graph.  The re-pack is ~2000 tiny tensor ops (permute / pad / cast per parameter and
+        operand copy): ~20 ms of host time per training step when issued one by one, with the GPU idle in between.  The
+        parameters are updated in place by the optimizer, so the whole re-pack is a static sequence between fixed addresses: it
+        is captured once (the intermediates live in the graph's private pool) and replayed per step; re-captured if a parameter
+        tensor was replaced."""
+        ptrs = tuple(v.data_ptr() for sd in sds_bvs for v in sd.values())
+        if getattr(self, "_refresh_ptrs", None) != ptrs or self.plan.device.type != "cuda":
+            self.refresh(sds_bvs)
+            if self.plan.device.type == "cuda":
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.refresh(sds_bvs)
+                self._refresh_graph, self._refresh_ptrs = g, ptrs
+            return
+        self._refresh_graph.replay()
+
     def set_inputs(self, x0, x1, cond, step, z_unit) -> None:
         self.x0.copy_(x0); self.x1.copy_(x1); self.cond.copy_(cond); self.step.copy_(step); self.z.copy_(z_unit)
 
