@@ -187,8 +187,8 @@ def op_kind(d):
         return "mlp_fused_kernel (ViT fc1+GELU+fc2)"
     if isinstance(d, nv.AttnDesc):
         return "attn_row_kernel (ViT attention)"
-    if hasattr(nv, "UnetPersistDesc") and isinstance(d, nv.UnetPersistDesc):
-        return "unet_persist_kernel (whole U-Net evaluation)"
+    if isinstance(d, nv.PersistDesc):
+        return "unet_persist_kernel (sde_vs: all steps x [v_net + s_net evaluation, Euler-Maruyama update], one launch)"
     return type(d).__name__.replace("Desc", "").lower() + "_kernel"
 
 
@@ -310,8 +310,10 @@ def roofline_block(cx, eng, wl, workload, value, world):
         k = kinds.setdefault(op_kind(d), {"us": 0.0, "flops": 0.0, "launches": 0})
         k["us"] += us
         k["launches"] += 1
-        if isinstance(d, (nv.GemmDesc, nv.MlpDesc)) or (hasattr(nv, "UnetPersistDesc") and isinstance(d, nv.UnetPersistDesc)):
-            k["flops"] += getattr(d, "algo_flops", None) or gemm_flops(d)
+        if isinstance(d, nv.PersistDesc):
+            k["flops"] += d.algo_flops
+        elif isinstance(d, (nv.GemmDesc, nv.MlpDesc)):
+            k["flops"] += gemm_flops(d)
         elif isinstance(d, nv.AttnDesc):
             k["flops"] += 4.0 * d.tokens * d.tokens * 64 * d.heads * d.images
     total_us = sum(k["us"] for k in kinds.values())

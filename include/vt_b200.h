@@ -468,6 +468,31 @@ typedef struct vt_adamw_desc {
   float grad_scale;
 } vt_adamw_desc;
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Persistent multi-layer launch: a whole U-Net evaluation (DiffusionConditionalUnet1D.forward, conditional_unet_1D.py:194-247)
+ * or the whole sampling loop of sde_vs (bridge/bridge_model.py:343-385: n_steps x [evaluation of v_net and s_net,
+ * Euler-Maruyama update]) as ONE kernel launch instead of 36 (+1) launches per evaluation.  The layers are the same
+ * vt_gemm_desc records the multi-launch form uses; `deps` tells which earlier layers produce a layer's A operand / residual.
+ * One CTA pair per TPC walks a static tile schedule; tiles are ordered by per-(layer, net, sample block) counters in global
+ * memory (nothing in the U-Net crosses samples), see csrc/vt_persist.cuh.  bf16 operands; GroupNorm layers bn = 256, linear
+ * layers bn = 256 or 32; every tile holds whole samples (t_box == positions per sample).
+ * ------------------------------------------------------------------------------------------------------------ */
+#define VT_PERSIST_MAX_DEPS 4
+#define VT_PERSIST_MAX_LAYERS 37
+typedef struct vt_persist_desc {
+  const vt_gemm_desc* gemms;  /* HOST array: the layers of ONE evaluation, execution order */
+  int32_t n_gemms;
+  const vt_sde_desc* sde;     /* HOST, optional: the update closing every step (x, v, s, noise, d, seed, xpad; its per-step scalars
+                                 come from sde_coef); referred to in `deps` as layer index n_gemms */
+  const int32_t* deps;        /* HOST [n_gemms + (sde ? 1 : 0)][VT_PERSIST_MAX_DEPS]: producing layer indices, -1 = unused */
+  const int32_t* dep_lag;     /* same shape: 1 = the producer's output of the PREVIOUS step (0 otherwise) */
+  int32_t n_steps;            /* >= 1; 1 = a single evaluation */
+  int64_t film_t_step;        /* elements between consecutive steps' rows of the layers' film_t tables */
+  const float* sde_coef;      /* HOST [n_steps][5]: ginv, dgg, eps, dt, nscale of each step */
+  int64_t noise_step;         /* elements between consecutive steps of sde->noise */
+  int32_t sde_T;              /* positions per sample of x */
+} vt_persist_desc;
+
 typedef struct vt_program vt_program;
 
 const char* vt_last_error(void);
@@ -506,6 +531,7 @@ int vt_program_add_lstm_train(vt_program* p, const vt_lstm_train_desc* d);
 int vt_program_add_lstm_bwd(vt_program* p, const vt_lstm_bwd_desc* d);
 int vt_program_add_lngelubwd(vt_program* p, const vt_lngelubwd_desc* d);
 int vt_program_add_dropmask(vt_program* p, const vt_dropmask_desc* d);
+int vt_program_add_persist(vt_program* p, const vt_persist_desc* d);
 
 /* Launch ops [first, first+count) in order on `stream` (count < 0: to the end). */
 int vt_program_run(vt_program* p, int first, int count, void* stream);

@@ -465,7 +465,26 @@ def emu_dropmask(plan, d: nv.DropmaskDesc):
     _flat(plan, d.mask, torch.float32)[: d.n] = torch.where(u >= p, 1.0 / (1.0 - p), torch.zeros(()))
 
 
-_EMU = {nv.QsampleDesc: emu_qsample, nv.SilossDesc: emu_siloss, nv.GemmDesc: emu_gemm, nv.LnDesc: emu_layernorm, nv.AttnDesc: emu_attention, nv.ImgStatsDesc: emu_imgstats,
+def emu_persist(plan, d: nv.PersistDesc):
+    """The persistent multi-layer launch = its layers in order, step by step (film_t / noise rows and the Euler-Maruyama scalars of
+    the step substituted exactly as the kernel does)."""
+    clone = lambda st: type(st).from_buffer_copy(st)
+    for step in range(d.n_steps):
+        for g in d.layers:
+            if g.film_t and d.film_t_step:
+                g = clone(g)
+                g.film_t = g.film_t + 4 * step * d.film_t_step
+            emu_gemm(plan, g)
+        if d.py_sde is not None:
+            s = clone(d.py_sde)
+            s.ginv, s.dgg, s.eps, s.dt, s.nscale = (float(x) for x in d.coef[step])
+            s.step = step
+            if s.noise:
+                s.noise = s.noise + 4 * step * d.noise_step
+            emu_sde(plan, s)
+
+
+_EMU = {nv.PersistDesc: emu_persist, nv.QsampleDesc: emu_qsample, nv.SilossDesc: emu_siloss, nv.GemmDesc: emu_gemm, nv.LnDesc: emu_layernorm, nv.AttnDesc: emu_attention, nv.ImgStatsDesc: emu_imgstats,
         nv.PatchifyDesc: emu_patchify, nv.ClsDesc: emu_cls, nv.PackDesc: emu_pack, nv.AffineDesc: emu_affine,
         nv.TcolDesc: emu_tcol, nv.GnbwdDesc: emu_gnbwd, nv.ColsumDesc: emu_colsum, nv.EwiseDesc: emu_ewise, nv.SilossBwdDesc: emu_silossbwd, nv.LstmTrainDesc: emu_lstm_train, nv.LstmBwdDesc: emu_lstm_bwd, nv.LnGeluBwdDesc: emu_lngelubwd, nv.DropmaskDesc: emu_dropmask, nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm, nv.MlpDesc: emu_mlp}
 

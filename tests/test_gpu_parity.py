@@ -117,6 +117,30 @@ def test_sample_with_recorded_noise(A, T, n, precise):
     assert torch.equal(out2, out)                      # step-by-step == one-shot, and deterministic
 
 
+@pytest.mark.parametrize("A,T,B,n", [(7, 64, 40, 4), (10, 36, 60, 3), (7, 64, 256, 2), (10, 16, 1, 10)])
+def test_persistent_sampler_equals_the_multi_launch_form(A, T, B, n, monkeypatch):
+    """The whole sde_vs loop as ONE persistent launch (csrc/vt_persist.cuh: tiles ordered by per-sample-block counters) against
+    the same layers replayed one kernel each: bit-identical states.  Shapes: a ragged last sample block (40 = 16 + 16 + 8), tiles
+    that straddle sample blocks (T = 36: 6 / 14 / 28 samples per tile at the three levels), the BASELINE batch, a single row."""
+    x0 = syn.det_uniform("ps.x0", (B, T, A), 5, -1.0, 1.0).to(DEV)
+    cond = syn.det_normal("ps.cond", (B, 256), 5).to(DEV)
+    noise = syn.det_normal("ps.noise", (n, B, T, A), 5).to(DEV)
+    outs = []
+    for persist in ("1", "0"):
+        monkeypatch.setenv("VT_PERSIST", persist)
+        si = _interpolant(A, T, False)
+        si.noise_override = noise
+        out = si.sample(x_prior=x0, cond=cond, diffuse_step=n)
+        eng = next(iter(si._engines.values()))
+        assert eng.persistent == (persist == "1")
+        assert eng.plan.compile().num_launches(*eng.sampler_range[:1], eng.sampler_range[1] - eng.sampler_range[0]) == (1 if persist == "1" else 37 * eng.n_steps)
+        outs.append(out.clone())
+        out_again = si.sample(x_prior=x0, cond=cond, diffuse_step=n)     # counters are reset per launch
+        assert torch.equal(out_again, out)
+    assert torch.isfinite(outs[0]).all() and float((outs[0] - x0).abs().max()) > 0
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("A,T", [(10, 16), (7, 64)])
 def test_sample_beta0_is_noise_free(A, T):
     g = U.golden(f"sde_A{A}_T{T}_n10_beta0")

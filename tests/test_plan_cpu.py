@@ -141,7 +141,7 @@ def test_predict_plan_reproduces_the_reference_golden(tag, precise):
     plan_emu.run(eng.setup)
     a0, a1 = eng.ranges["dino"][0], eng.ranges["normalize"][1]
     plan_emu.run(eng.plan, a0, a1 - a0)
-    b0, b1 = eng.step_ranges[0][0], eng.ranges["denormalize"][1]
+    b0, b1 = eng.sampler_range[0], eng.ranges["denormalize"][1]      # bf16: the persistent descriptor, interpreted layer by layer
     plan_emu.run(eng.plan, b0, b1 - b0)
     g = c["gold"]
     scale = float(g["out"].abs().max())

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libvt_b200.so")
 SOURCES = ["vt_host.cu"]
-DEPS = ["vt_host.cu", "vt_gemm.cuh", "vt_attn.cuh", "vt_mlp.cuh", "vt_elem.cuh", "vt_lstm.cuh", "vt_bwd.cuh", "vt_ptx.cuh",
+DEPS = ["vt_host.cu", "vt_persist.cuh", "vt_gemm.cuh", "vt_attn.cuh", "vt_mlp.cuh", "vt_elem.cuh", "vt_lstm.cuh", "vt_bwd.cuh", "vt_ptx.cuh",
         os.path.join("..", "..", "include", "vt_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -23,12 +23,13 @@ def stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, debug_knobs: bool = False) -> str:
+    """debug_knobs: compile the developer knobs / timestamps of csrc/vt_gemm.cuh in (VT_GEMM_DEBUG env variable; tools/ only)."""
     if not force and not stale():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc] + NVCC_FLAGS + (["-DVT_DEBUG_KNOBS=1"] if debug_knobs else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(os.path.join(HERE, "lib", "build.log"), "w") as f:
@@ -41,4 +42,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv or "--debug-knobs" in sys.argv, verbose="-v" in sys.argv, debug_knobs="--debug-knobs" in sys.argv))

@@ -29,14 +29,21 @@ constexpr int GEMM_MAX_TAPS = 8;
 
 enum : int { ACT_NONE = 0, ACT_GELU = 1, ACT_MISH = 2 };
 
-// Developer instrumentation (VT_GEMM_DEBUG bit 128): warp 2 of CTA 0 records clock64() at the phase boundaries of its
-// epilogue into this buffer (read back with vt_debug_timestamps).
+// Developer instrumentation.  Release builds (VT_DEBUG_KNOBS == 0, the default) compile every knob and timestamp out of the
+// kernels; `python -m vla_touch_b200.build --debug-knobs` builds a library in which the env variable VT_GEMM_DEBUG selects:
+// 1 skip TMA loads + MMAs, 2 skip the epilogue body, 4 skip TMA loads only, 8 skip MMAs only, 16 no epilogue stores,
+// 32 no TMEM loads / no transposition, 128 / 256 clock64() stamps of one epilogue warp / the MMA thread of CTA 0 (read back with
+// vt_debug_timestamps; tools/gemm_debug.py, tools/epi_trace.py).
+#ifndef VT_DEBUG_KNOBS
+#define VT_DEBUG_KNOBS 0
+#endif
+constexpr bool kDbg = VT_DEBUG_KNOBS != 0;
 constexpr int VT_DBG_TS = 2048;
 __device__ long long vt_dbg_ts[VT_DBG_TS];
 __device__ int vt_dbg_n;
 // The entry counter lives in a register of the recording thread (`n`): a stamp is two fire-and-forget stores.
 __device__ __forceinline__ void dbg_stamp(bool on, int& n, int tag) {
-  if (on && n + 1 < VT_DBG_TS) {
+  if (kDbg && on && n + 1 < VT_DBG_TS) {
     vt_dbg_ts[n] = tag;
     vt_dbg_ts[n + 1] = clock64();
     n += 2;
@@ -49,10 +56,7 @@ enum : int { EPI_LINEAR = 0, EPI_GN = 1 };
 struct GemmArgs {
   CUtensorMap tmA;  // 5-D (C, P, T, B, G), box (KE, 1, Tbox, Bbox, 1), SWIZZLE_128B
   CUtensorMap tmB;  // 2-D (Ktot, G*n_pad), box (KE, BN), SWIZZLE_128B
-  CUtensorMap tmO;  // 3-D (N, M, G) over the output, box (128 B, 32 rows, 1), SWIZZLE_128B; valid when tma_out
-  int debug;        // developer knob (env VT_GEMM_DEBUG): 1 skip TMA loads + MMAs, 2 skip the epilogue body, 4 skip TMA
-                    // loads only, 8 skip MMAs only
-  int tma_out;      // 1: the epilogue stages 32-row x 128-byte boxes in shared memory and drains them with TMA stores
+  int debug;        // developer knobs (VT_DEBUG_KNOBS builds only, see above)
   // ---- tiles ----
   int n_tiles, m_tiles, total_tiles;  // tile id = (g * m_tiles + m_tile) * n_tiles + n_tile
   // ---- K loop: k-block i -> (pass, tap, cb) ----
@@ -122,13 +126,8 @@ __host__ __device__ constexpr int GEMM_SCRATCH_FLOATS(int BN, int MODE) {
                    : GEMM_COLV_FLOATS(BN, MODE) + 2 * (128 + 64) * 4 * 2 + GEMM_FILM_SAMPLES * 2 * BN;
 }
 
-// 8 epilogue warps x 2 boxes of 32 rows x 128 B when the TMA-store epilogue is compiled in.  Measured on B200: the
-// main loop is bound by the TMA -> MMA -> commit round trip divided by the ring depth, so the 64 KB buy more as two
-// extra operand stages than as output staging; the direct-store epilogue is kept as the default.
-#ifndef VT_GEMM_TMA_STORE
-#define VT_GEMM_TMA_STORE 0
-#endif
-constexpr int GEMM_OUT_STAGE_BYTES = VT_GEMM_TMA_STORE ? 8 * 2 * 4096 : 0;
+// (A TMA-store epilogue -- 32-row x 128-byte boxes staged in shared memory -- was measured on B200 and dropped: the main loop
+// is bound by the TMA -> MMA -> commit round trip divided by the ring depth, so 64 KB buy more as two extra operand stages.)
 // Per-warp 32 x 32 fp32 transposition buffer of the coalescing epilogue (8 epilogue warps x 4 KB).
 __host__ __device__ constexpr int GEMM_XPOSE_BYTES(int BN, int MODE, int EW = 8) { return (MODE == 0 && BN >= 128) ? EW * 4096 : 0; }
 
@@ -137,7 +136,7 @@ __host__ __device__ constexpr int GEMM_XPOSE_BYTES(int BN, int MODE, int EW = 8)
 // time of one atom at BN=128, so a stage carries KA atoms (2 x 4 UMMA instructions per barrier round).
 template <int BN, int STAGES, int MODE, int KA, int CTAS = 1, int EW = 8>
 constexpr int gemm_smem_bytes() {
-  return 1024 /*align slack*/ + STAGES * KA * (GEMM_A_STAGE_BYTES + (BN / CTAS) * 128) + GEMM_OUT_STAGE_BYTES +
+  return 1024 /*align slack*/ + STAGES * KA * (GEMM_A_STAGE_BYTES + (BN / CTAS) * 128) +
          GEMM_XPOSE_BYTES(BN, MODE, EW) + 256 /*barriers*/ + GEMM_SCRATCH_FLOATS(BN, MODE) * 4;
 }
 
@@ -190,43 +189,6 @@ __device__ __forceinline__ void store_split8(TOut* outp, long long plane, const 
   store_chunk8<TOut>(outp, y);
 }
 
-// Per-warp output staging.  Direct epilogue stores (one 16-byte piece of 32 different rows per instruction) keep the
-// L1TEX unit busy for 32 cycles each and were the measured bottleneck of the ViT GEMMs; instead every warp writes its
-// 32 rows x 128 bytes into a swizzled shared-memory box (conflict-free) and one lane issues a TMA store of the box.
-struct OutStage {
-  uint32_t base;   // shared address of this warp's box 0 (box 1 at +4096), 1024-byte aligned
-  uint32_t count;  // boxes staged so far (persists across tiles)
-};
-__device__ __forceinline__ uint32_t stage_begin(OutStage& st, int lane) {
-  if (st.count >= 2) {  // the box used two stores ago must have been read out
-    if (lane == 0) bulk_wait_read<1>();
-    __syncwarp();
-  }
-  return st.base + (st.count & 1) * 4096;
-}
-template <typename TOut>
-__device__ __forceinline__ void stage_put8(uint32_t box, int lane, int col, const float* y) {  // col: multiple of 8 inside the box
-  const uint32_t row = box + lane * 128;
-  const int sw = lane & 7;
-  if constexpr (sizeof(TOut) == 2) {
-    st_shared_v4(row + (((col >> 3) ^ sw) << 4), pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
-                 pack_bf16x2(y[6], y[7]));
-  } else {
-    const int u = col >> 2;
-    st_shared_v4(row + ((u ^ sw) << 4), __float_as_uint(y[0]), __float_as_uint(y[1]), __float_as_uint(y[2]), __float_as_uint(y[3]));
-    st_shared_v4(row + (((u + 1) ^ sw) << 4), __float_as_uint(y[4]), __float_as_uint(y[5]), __float_as_uint(y[6]), __float_as_uint(y[7]));
-  }
-}
-__device__ __forceinline__ void stage_end(OutStage& st, const CUtensorMap* tm, uint32_t box, int lane, int col0, int row0, int g) {
-  fence_proxy_async_smem();
-  __syncwarp();
-  if (lane == 0) {
-    tma_store_3d(tm, box, col0, row0, g);
-    bulk_commit();
-  }
-  st.count++;
-}
-
 // Per-tile state shared by the epilogue flavours.
 struct EpiTile {
   int n0, g, r;            // first column, group, tile row (== TMEM lane)
@@ -243,17 +205,13 @@ struct EpiTile {
 // ------------------------------------------------------------------------------------------------------------
 template <int BN, typename TOut, bool PRECISE>
 __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile& t, const float* colv, uint64_t* acc_full,
-                                                uint32_t acc_parity, OutStage& st, int c_begin, int c_end) {
+                                                uint32_t acc_parity, int c_begin, int c_end) {
   // kernel parameters used inside the column loops, pinned in registers (the struct lives in the constant bank and is
   // otherwise re-read after every asm "memory" clobber)
-  const int N = a.N, act = a.act, dbg = a.debug;
-  const bool tma = a.tma_out != 0, vec = a.vec != 0;
+  const int N = a.N, act = a.act, dbg = kDbg ? a.debug : 0;
+  const bool vec = a.vec != 0;
   const long long oplane = a.out_plane;
 
-  constexpr int CG = 128 / sizeof(TOut);   // columns per staged box
-  const int lane = threadIdx.x & 31;
-  const int row0 = (int)(t.grow - lane);   // first logical row of this warp
-  uint32_t box = 0;
   TOut* outp = reinterpret_cast<TOut*>(a.out) + (long long)t.g * a.out_g +
                ((long long)t.q * a.out_q + (long long)t.rem * a.out_r + a.out_off) * a.ldc + t.n0;
   const long long res_row = (long long)t.q * a.res_q + (long long)t.rem * a.res_r + a.res_off;
@@ -281,7 +239,6 @@ __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile
 #pragma unroll
     for (int i = 0; i < 8; ++i) rc[i] = rb[i];
     if (c + 32 < c_end) fetch(c + 32);
-    if (tma && (c % CG) == 0 && !(dbg & 16)) box = stage_begin(st, lane);
     tmem_ld_wait();
     if (t.valid) {
 #pragma unroll
@@ -305,11 +262,6 @@ __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc += y[j];
           if (acc == 123.456f) outp[cc] = TOut(acc);   // keeps the math alive without producing output traffic
-        } else if (tma) {
-          const float4 r0 = rc[j8 / 4], r1 = rc[j8 / 4 + 1];
-          y[0] += r0.x; y[1] += r0.y; y[2] += r0.z; y[3] += r0.w;
-          y[4] += r1.x; y[5] += r1.y; y[6] += r1.z; y[7] += r1.w;
-          stage_put8<TOut>(box, lane, cc % CG, y);
         } else if (vec && t.n0 + cc + 8 <= N) {
           const float4 r0 = rc[j8 / 4], r1 = rc[j8 / 4 + 1];
           y[0] += r0.x; y[1] += r0.y; y[2] += r0.z; y[3] += r0.w;
@@ -333,8 +285,6 @@ __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile
         }
       }
     }
-    if (tma && !(dbg & 16) && (((c + 32) % CG) == 0 || c + 32 >= c_end))
-      stage_end(st, &a.tmO, box, lane, t.n0 + (c / CG) * CG, row0, t.g);
   }
 }
 
@@ -370,7 +320,7 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, EpiTile& t,
   constexpr int NV = NC / 4;              // float4 pieces per lane row
   const int lane = threadIdx.x & 31;
   const int sr = lane / LPR, cg = lane % LPR;
-  const int dbg = a.debug;
+  const int dbg = kDbg ? a.debug : 0;
   const int wrow0 = (int)t.grow - lane;             // first logical row of this warp
   const int trow0 = t.r - lane;                     // ... and its row inside the tile
   const int rdiv = a.row_div, oq = (int)a.out_q, orr = (int)a.out_r, ooff0 = (int)a.out_off;
@@ -638,7 +588,7 @@ __device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, EpiTile& t, 
     for (int i = 0; i < 4; ++i) rr[i] = resp ? *reinterpret_cast<const uint4*>(resp + ch * 32 + i * 8) : make_uint4(0u, 0u, 0u, 0u);
   };
   fetch_res(0);
-  const bool ts_on = (a.debug & 128) && blockIdx.x == 0 && threadIdx.x == 64;
+  const bool ts_on = kDbg && (a.debug & 128) && blockIdx.x == 0 && threadIdx.x == 64;
   dbg_stamp(ts_on, t.dbg_n, 20);
 
   mbar_wait(acc_full, acc_parity);
@@ -749,7 +699,7 @@ __device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, EpiTile& t, 
         w.y = pack_bf16x2(y[4 * q + 1].x, y[4 * q + 1].y);
         w.z = pack_bf16x2(y[4 * q + 2].x, y[4 * q + 2].y);
         w.w = pack_bf16x2(y[4 * q + 3].x, y[4 * q + 3].y);
-        if (a.debug & 16) {   // developer knob: no store traffic (timing only)
+        if (kDbg && (a.debug & 16)) {   // developer knob: no store traffic (timing only)
           if (w.x == 0x12345678u) *reinterpret_cast<uint4*>(outp + c0 + 8 * q) = w;
         } else {
           *reinterpret_cast<uint4*>(outp + c0 + 8 * q) = w;
@@ -763,23 +713,18 @@ __device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, EpiTile& t, 
 template <int BN, typename TOut, bool PRECISE>
 __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t, const float* colv, float2* gn_part,
                                             float2* gn_stat, int et, int bar_id, uint64_t* acc_full, uint32_t acc_parity,
-                                            OutStage& st, int cb) {
+                                            int cb) {
   // `cb`: first tile column of the half this warpgroup handles (0 or BN / 2); colv / TMEM / output columns are tile-relative
-  const bool tma = a.tma_out != 0;
   const long long oplane = a.out_plane, rplane = a.res_plane;
   const int filmC = a.film_C;
 
   static_assert(BN == 128 || BN == 256, "GN epilogue: whole 32/64-channel groups per tile");
   constexpr int NCH = BN / 64;  // 32-column chunks per half tile (2 or 4): whole 32- / 64-channel groups
-  constexpr int CG = 128 / sizeof(TOut);
-  const int row0 = (int)(t.grow - (threadIdx.x & 31));
-  uint32_t box = 0;
   TOut* outp = reinterpret_cast<TOut*>(a.out) + (long long)t.g * a.out_g +
                ((long long)t.q * a.out_q + (long long)t.rem * a.out_r + a.out_off) * a.ldc + t.n0 + cb;
   const long long res_row = (long long)t.q * a.res_q + (long long)t.rem * a.res_r + a.res_off;
   const TOut* resp = a.res ? reinterpret_cast<const TOut*>(a.res) + (long long)t.g * a.res_g + res_row * a.ldres + t.n0 + cb : nullptr;
   const float* filmp = a.film_c ? a.film_c + (long long)t.g * a.film_g + (long long)t.q * a.film_ld + a.film_off + t.n0 + cb : nullptr;
-  const int lane = threadIdx.x & 31;
 
   mbar_wait(acc_full, acc_parity);
   tc_fence_after();
@@ -818,7 +763,6 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
       mu = (ch == k) ? mean[k] : mu;
       rs = (ch == k) ? rstd[k] : rs;
     }
-    if (tma && ((ch * 32) % CG) == 0) box = stage_begin(st, lane);
     tmem_ld_wait();
     if (t.valid) {
 #pragma unroll
@@ -852,11 +796,9 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
             for (int j = 0; j < 8; ++j) y[j] += rl[j];
           }
         }
-        if (tma) stage_put8<TOut>(box, lane, cc % CG, y);
-        else store_split8<TOut>(outp + cc, oplane, y);
+        store_split8<TOut>(outp + cc, oplane, y);
       }
     }
-    if (tma && (((ch + 1) * 32) % CG) == 0) stage_end(st, &a.tmO, box, lane, t.n0 + cb + ((ch * 32) / CG) * CG, row0, t.g);
   }
 }
 
@@ -877,15 +819,14 @@ __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __gr
   static_assert(CTAS == 1 || (CTAS == 2 && sizeof(TIn) == 2 && BN % 32 == 0), "CTA pairs: bf16 operands");
 
   extern __shared__ uint8_t smem_raw[];
-  const bool ts_mma = (a.debug & 256) && blockIdx.x == 0 && threadIdx.x == 32;   // developer instrumentation: MMA thread of CTA 0
+  const bool ts_mma = kDbg && (a.debug & 256) && blockIdx.x == 0 && threadIdx.x == 32;   // developer instrumentation: MMA thread of CTA 0
   int ts_n = 0;
   dbg_stamp(ts_mma, ts_n, 30);
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  uint8_t* sOut = sB + STAGES * B_STAGE_BYTES;   // per-warp output staging boxes (1024-byte aligned)
-  uint8_t* sX = sOut + GEMM_OUT_STAGE_BYTES;      // per-warp transposition buffers of the coalescing epilogue
+  uint8_t* sX = sB + STAGES * B_STAGE_BYTES;      // per-warp transposition buffers of the coalescing epilogue
   uint64_t* full = reinterpret_cast<uint64_t*>(sX + GEMM_XPOSE_BYTES(BN, MODE, EW));
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;   // [2]
@@ -903,7 +844,6 @@ __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __gr
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.tmA);
     tma_prefetch_desc(&a.tmB);
-    if (a.tma_out) tma_prefetch_desc(&a.tmO);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -936,7 +876,7 @@ __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __gr
   // dependent launch).  Only the producer thread runs ahead: the WEIGHT tiles of its first stages do not depend on the
   // predecessor, so their HBM round trip is started before the wait.
   int pre_atoms = 0;
-  if (warp == 0 && lane == 0 && a.passes == 1 && (a.debug & 5) == 0 && worker < a.total_tiles) {
+  if (warp == 0 && lane == 0 && a.passes == 1 && !(kDbg && (a.debug & 5)) && worker < a.total_tiles) {
     const int per_pass = a.taps * a.cblocks;          // == nk
     const int pre_stages = (per_pass + KA - 1) / KA < STAGES ? (per_pass + KA - 1) / KA : STAGES;
     const int n_tile0 = worker % a.n_tiles, g0 = (worker / a.n_tiles) / a.m_tiles;
@@ -965,7 +905,7 @@ __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __gr
       uint32_t ph = 0;   // ring position kept incrementally: no divisions in this loop
       int n_tile = worker % a.n_tiles, rest = worker / a.n_tiles;
       const int dn = n_workers % a.n_tiles, dr = n_workers / a.n_tiles;
-      const bool no_tma = (a.debug & 5) != 0;
+      const bool no_tma = kDbg && (a.debug & 5) != 0;
       int at = 0, n_at = 0;   // atoms issued into / planned for the current stage
       int atom_seq = 0;       // atoms handled so far (the first pre_atoms already have their stage opened and B in flight)
       for (int tile = worker; tile < a.total_tiles; tile += n_workers) {
@@ -1027,7 +967,7 @@ __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __gr
     if (lane == 0 && rank == 0) {
       uint32_t lt = 0, ph = 0;
       int s = 0;
-      const bool no_mma = (a.debug & 9) != 0;
+      const bool no_mma = kDbg && (a.debug & 9) != 0;
       for (int tile = worker; tile < a.total_tiles; tile += n_workers, ++lt) {
         const uint32_t acc = lt & 1;
         mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);  // the epilogues have drained this accumulator
@@ -1084,15 +1024,12 @@ __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __gr
     EpiTile t;
     t.r = quarter * 32 + lane;
     t.dbg_n = 0;
-    OutStage st;
-    st.base = smem_u32(sOut) + (warp - 2) * 8192;
-    st.count = 0;
     uint32_t lt = 0;
     const bool fast = GEMM_XPOSE_BYTES(BN, MODE, EW) > 0 && a.fast != 0;
     const int et256 = threadIdx.x - 64;
     for (int tile = worker; tile < a.total_tiles; tile += n_workers, ++lt) {
       const uint32_t acc = lt & 1;
-      dbg_stamp((a.debug & 128) && blockIdx.x == 0 && threadIdx.x == 64, t.dbg_n, 19);
+      dbg_stamp(kDbg && (a.debug & 128) && blockIdx.x == 0 && threadIdx.x == 64, t.dbg_n, 19);
       const int n_tile = tile % a.n_tiles;
       const int rest = tile / a.n_tiles;
       const int m_tile = (rest % a.m_tiles) * CTAS + rank;
@@ -1148,23 +1085,23 @@ __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __gr
       t.taddr = tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
       const uint32_t parity = (lt >> 1) & 1;
       if (c_begin < c_end) {
-        if (a.debug & 2) {
+        if (kDbg && (a.debug & 2)) {
           mbar_wait(&acc_full[acc], parity);
           tc_fence_after();
         } else if constexpr (MODE == EPI_LINEAR) {
           if constexpr (GEMM_XPOSE_BYTES(BN, MODE, EW) > 0) {
             if (fast) epilogue_linear_fast<BN, TOut, PRECISE>(a, t, smem_u32(sX) + (warp - 2) * 4096, &acc_full[acc], parity, c_begin, c_end);
-            else epilogue_linear<BN, TOut, PRECISE>(a, t, colv, &acc_full[acc], parity, st, c_begin, c_end);
+            else epilogue_linear<BN, TOut, PRECISE>(a, t, colv, &acc_full[acc], parity, c_begin, c_end);
           } else {
-            epilogue_linear<BN, TOut, PRECISE>(a, t, colv, &acc_full[acc], parity, st, c_begin, c_end);
+            epilogue_linear<BN, TOut, PRECISE>(a, t, colv, &acc_full[acc], parity, c_begin, c_end);
           }
         } else if constexpr (GN_FAST) {
-          if (a.out_plane == 0 && a.res_plane == 0 && !a.tma_out)
+          if (a.out_plane == 0 && a.res_plane == 0)
             epilogue_gn_fast<BN>(a, t, colv, film_staged ? films : nullptr, gn_part, gn_stat, et, 2 + half, &acc_full[acc], parity, c_begin);
           else
-            epilogue_gn<BN, TOut, PRECISE>(a, t, colv, gn_part, gn_stat, et, 2 + half, &acc_full[acc], parity, st, c_begin);
+            epilogue_gn<BN, TOut, PRECISE>(a, t, colv, gn_part, gn_stat, et, 2 + half, &acc_full[acc], parity, c_begin);
         } else {
-          epilogue_gn<BN, TOut, PRECISE>(a, t, colv, gn_part, gn_stat, et, 2 + half, &acc_full[acc], parity, st, c_begin);
+          epilogue_gn<BN, TOut, PRECISE>(a, t, colv, gn_part, gn_stat, et, 2 + half, &acc_full[acc], parity, c_begin);
         }
       }
       tc_fence_before();
@@ -1173,7 +1110,6 @@ __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __gr
         if constexpr (CTAS == 2) mbar_arrive_remote(mapa_shared(smem_u32(&acc_empty[acc]), 0)); else mbar_arrive(&acc_empty[acc]);
       }
     }
-    if (a.tma_out && lane == 0) bulk_wait_all();   // staged boxes must be drained before the CTA exits
   }
 
   dbg_stamp(ts_mma, ts_n, 35);

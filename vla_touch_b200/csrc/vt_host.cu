@@ -15,6 +15,7 @@
 #include "vt_mlp.cuh"
 #include "vt_elem.cuh"
 #include "vt_gemm.cuh"
+#include "vt_persist.cuh"
 #include "vt_lstm.cuh"
 #include "vt_bwd.cuh"
 
@@ -245,7 +246,9 @@ struct GemmOp : Op {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
+int fill_gemm_args(const vt_gemm_desc& d, int ctas, vt::GemmArgs* out);
+
+int validate_gemm(const vt_gemm_desc& d) {
   VT_REQUIRE(d.in_dtype == VT_BF16 || d.in_dtype == VT_F32, "gemm: in_dtype %d", d.in_dtype);
   VT_REQUIRE(d.out_dtype == VT_BF16 || d.out_dtype == VT_F32, "gemm: out_dtype %d", d.out_dtype);
   const int es = d.in_dtype == VT_BF16 ? 2 : 4;
@@ -263,6 +266,12 @@ int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
   VT_REQUIRE(d.w_ld >= d.taps * d.kc, "gemm: w_ld=%d < taps*kc=%d", d.w_ld, d.taps * d.kc);
   VT_REQUIRE(d.a_P >= 1 && d.a_T >= 1 && d.a_B >= 1 && d.a_C >= 1, "gemm: bad A extents");
   VT_REQUIRE(d.row_div >= 1, "gemm: row_div=%d", d.row_div);
+  return VT_OK;
+}
+
+int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
+  int rc0 = validate_gemm(d);
+  if (rc0) return rc0;
   // CTA pairs whenever the shape has at least two row tiles (env VT_GEMM_PAIR=0 keeps the single-CTA kernels: A/B runs)
   const int m_tiles_1 = (d.M + d.t_box * d.b_box - 1) / (d.t_box * d.b_box);
   const bool pair_enabled = !(getenv("VT_GEMM_PAIR") && atoi(getenv("VT_GEMM_PAIR")) == 0);
@@ -271,10 +280,22 @@ int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
   if (d.epi == VT_EPI_GN && d.bn == 256) pair = true;   // the 256-wide GroupNorm epilogue exists as a pair kernel only
   GemmVariant* var = gemm_variant(d.in_dtype, d.bn, d.epi, d.out_dtype, pair);
   if (!var) return fail(VT_E_UNSUPPORTED, "gemm: no kernel for in=%d bn=%d epi=%d out=%d", d.in_dtype, d.bn, d.epi, d.out_dtype);
-
-  vt::GemmArgs& a = op->args;
-  memset(&a, 0, sizeof(a));
   op->var = var;
+  int rc = fill_gemm_args(d, var->ctas, &op->args);
+  if (rc) return rc;
+  const int workers = sm_count() / var->ctas;
+  const long long total = op->args.total_tiles;
+  op->grid = dim3((unsigned)(total < workers ? total : workers) * var->ctas, 1u, 1u);   // persistent: one CTA per SM
+  return VT_OK;
+}
+
+// Kernel arguments of one implicit GEMM for tiles of `ctas` x 128 rows (2 = CTA pairs: the B tensor map's box holds half the
+// tile's columns).  Shared by gemm_tc_kernel and the persistent multi-layer kernel.
+int fill_gemm_args(const vt_gemm_desc& d, int ctas, vt::GemmArgs* out) {
+  const int es = d.in_dtype == VT_BF16 ? 2 : 4;
+  const int KE = 128 / es;
+  vt::GemmArgs& a = *out;
+  memset(&a, 0, sizeof(a));
   const int rows_valid = d.t_box * d.b_box;
   const int t_out = d.M / d.a_B;
   if (d.b_box == 1 && d.a_B == 1) {  // one sample: tiles step along its positions
@@ -296,12 +317,12 @@ int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
   {
     const uint64_t dims[2] = {(uint64_t)d.w_ld, (uint64_t)d.G * d.n_pad};
     const uint64_t st[1] = {(uint64_t)d.w_ld * es};
-    const uint32_t box[2] = {(uint32_t)KE, (uint32_t)(d.bn / var->ctas)};   // a pair splits the tile's N rows of B
+    const uint32_t box[2] = {(uint32_t)KE, (uint32_t)(d.bn / ctas)};   // a pair splits the tile's N rows of B
     int rc = make_tmap(&a.tmB, d.in_dtype, 2, d.w, dims, st, box);
     if (rc) return rc;
   }
   {
-    const char* dbg = getenv("VT_GEMM_DEBUG");
+    const char* dbg = VT_DEBUG_KNOBS ? getenv("VT_GEMM_DEBUG") : nullptr;
     a.debug = dbg ? atoi(dbg) : 0;
   }
   a.passes = d.passes;
@@ -385,34 +406,14 @@ int build_gemm(const vt_gemm_desc& d, GemmOp* op) {
   }
   const int m_tiles = (d.M + rows_valid - 1) / rows_valid;
   const int n_tiles = (d.N + d.bn - 1) / d.bn;
-  // TMA-store epilogue: full 128-row tiles, output rows linear in the logical row (row = out_r * m + out_off), no hi|lo planes
-  {
-    const int cg = 128 / oes;
-    const bool linear_rows = d.out_q == d.out_r * (int64_t)d.row_div && d.out_r >= 1;
-    if (VT_GEMM_TMA_STORE && vec && d.out_plane == 0 && rows_valid == 128 && linear_rows && (d.bn % cg == 0 || n_tiles == 1) && d.N >= 8) {
-      const uint64_t dims[3] = {(uint64_t)d.N, (uint64_t)d.M, (uint64_t)d.G};
-      const uint64_t row_bytes = (uint64_t)d.out_r * d.ldc * oes;
-      const uint64_t g_bytes = d.G > 1 ? (uint64_t)d.out_g * oes : row_bytes * (uint64_t)d.M;
-      const uint64_t st[2] = {row_bytes, g_bytes};
-      const uint32_t box[3] = {(uint32_t)cg, 32u, 1u};
-      const char* base = reinterpret_cast<const char*>(d.out) + (int64_t)d.out_off * d.ldc * oes;
-      if (aligned16(base) && g_bytes < (1ull << 40)) {
-        int rc = make_tmap(&a.tmO, d.out_dtype, 3, base, dims, st, box);
-        if (rc) return rc;
-        a.tma_out = 1;
-      }
-    }
-  }
   // work units: one 128-row tile per CTA, or two vertically adjacent tiles per CTA pair (a missing second tile is all
   // out-of-bounds: zero-filled by TMA, masked in the epilogue)
-  const int m_units = (m_tiles + var->ctas - 1) / var->ctas;
+  const int m_units = (m_tiles + ctas - 1) / ctas;
   const long long total = (long long)m_units * n_tiles * d.G;
   VT_REQUIRE(total < (1ll << 31), "gemm: too many tiles");
   a.n_tiles = n_tiles;
   a.m_tiles = m_units;
   a.total_tiles = (int)total;
-  const int workers = sm_count() / var->ctas;
-  op->grid = dim3((unsigned)(total < workers ? total : workers) * var->ctas, 1u, 1u);   // persistent: one CTA per SM
   return VT_OK;
 }
 
@@ -736,6 +737,148 @@ struct LstmBwdOp : Op {
   }
 };
 
+// ---- persistent multi-layer launch ----
+struct PersistOp : Op {
+  vt::PersistArgs args;
+  dim3 grid;
+  void* dev_mem = nullptr;      // counters | expected | coefficients, one allocation
+  size_t counter_bytes = 0;
+  ~PersistOp() override {
+    if (dev_mem) cudaFree(dev_mem);
+  }
+  int launches() const override { return 1; }
+  int launch(cudaStream_t s) override {
+    static bool attr_set = false;
+    if (!attr_set) {
+      VT_CUDA(cudaFuncSetAttribute(vt::unet_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vt::PERSIST_SMEM_BYTES));
+      attr_set = true;
+    }
+    VT_CUDA(cudaMemsetAsync(args.done, 0, counter_bytes, s));
+    cudaError_t e = launch_ex(vt::unet_persist_kernel, grid, dim3(vt::PERSIST_THREADS, 1, 1), (size_t)vt::PERSIST_SMEM_BYTES, s, true, false, args);
+    if (e != cudaSuccess) return fail(VT_E_CUDA, "unet_persist_kernel launch: %s", cudaGetErrorString(e));
+    VT_LAUNCH_CHECK("unet_persist_kernel");
+    return VT_OK;
+  }
+};
+
+int build_persist(const vt_persist_desc& d, PersistOp* op) {
+  static_assert(VT_PERSIST_MAX_DEPS == vt::PERSIST_MAX_DEPS && VT_PERSIST_MAX_LAYERS + 1 == vt::PERSIST_MAX_LAYERS, "header constants");
+  static_assert(sizeof(vt::PersistArgs) <= 32764, "kernel parameter space");
+  VT_REQUIRE(d.gemms && d.deps && d.dep_lag && d.n_gemms >= 1 && d.n_gemms <= VT_PERSIST_MAX_LAYERS && d.n_steps >= 1,
+             "persist: bad descriptor (n_gemms=%d, n_steps=%d)", d.n_gemms, d.n_steps);
+  VT_REQUIRE(!d.sde || (d.sde_coef && d.sde_T >= 1), "persist: the Euler-Maruyama update needs sde_coef and sde_T");
+  vt::PersistArgs& P = op->args;
+  memset(&P, 0, sizeof(P));
+  const int n_layers = d.n_gemms + (d.sde ? 1 : 0);
+  const int B = d.gemms[0].a_B;
+  int sbs = 1;
+  for (int l = 0; l < d.n_gemms; ++l) {
+    const vt_gemm_desc& g = d.gemms[l];
+    int rc = validate_gemm(g);
+    if (rc) return rc;
+    VT_REQUIRE(g.in_dtype == VT_BF16 && g.passes == 1, "persist: layer %d: bf16 operands only", l);
+    VT_REQUIRE(g.a_B == B && g.M % B == 0 && g.t_box == g.M / B, "persist: layer %d: tiles must hold whole samples of the same batch", l);
+    if (g.epi == VT_EPI_GN) VT_REQUIRE(g.bn == 256 && g.out_dtype == VT_BF16, "persist: layer %d: GroupNorm layers need bn = 256, bf16 out", l);
+    else VT_REQUIRE(g.bn == 256 || g.bn == 32, "persist: layer %d: bn = %d (256 or 32)", l, g.bn);
+    if (2 * g.b_box > sbs) sbs = 2 * g.b_box;
+  }
+  const int n_sb = (B + sbs - 1) / sbs;
+  std::vector<unsigned> expected;
+  int tile_base = 0, cnt_off = 0, max_tiles = 1;
+  for (int l = 0; l < n_layers; ++l) {
+    vt::PersistLayer& L = P.layers[l];
+    L.exp_off = (int)expected.size();
+    L.cnt_off = cnt_off;
+    L.tile_base = tile_base;
+    if (l < d.n_gemms) {
+      const vt_gemm_desc& g = d.gemms[l];
+      int rc = fill_gemm_args(g, 2, &L.g);
+      if (rc) return rc;
+      L.kind = 0;
+      L.mode = g.epi;
+      L.bn = g.bn;
+      L.out_f32 = g.out_dtype == VT_F32;
+      L.idesc = vt::umma_idesc(vt::UMMA_FMT_BF16, (uint32_t)g.bn, 0, 0, 256);
+      L.G = g.G;
+      L.spu = 2 * g.b_box;
+      L.n_tiles_total = L.g.total_tiles;
+      L.film_t_step = g.film_t ? d.film_t_step : 0;
+      for (int sb = 0; sb < n_sb; ++sb) {
+        int units = 0;
+        for (int u = 0; u < L.g.m_tiles; ++u) {
+          const int s0 = u * L.spu, s1 = (s0 + L.spu < B ? s0 + L.spu : B) - 1;
+          if (s0 < B && s0 / sbs <= sb && sb <= s1 / sbs) ++units;
+        }
+        expected.push_back(16u * (unsigned)units * (unsigned)L.g.n_tiles);
+      }
+    } else {
+      L.kind = 1;
+      L.G = 1;
+      L.spu = sbs;
+      L.n_tiles_total = n_sb;
+      for (int sb = 0; sb < n_sb; ++sb) expected.push_back(16u);
+    }
+    cnt_off += L.G * n_sb;
+    tile_base += L.n_tiles_total;
+    if (L.n_tiles_total > max_tiles) max_tiles = L.n_tiles_total;
+    int nd = 0;
+    for (int k = 0; k < VT_PERSIST_MAX_DEPS; ++k) {
+      const int dep = d.deps[l * VT_PERSIST_MAX_DEPS + k];
+      if (dep < 0) continue;
+      const int lag = d.dep_lag[l * VT_PERSIST_MAX_DEPS + k];
+      VT_REQUIRE(dep < n_layers && (lag == 0 || lag == 1), "persist: layer %d depends on layer %d (lag %d)", l, dep, lag);
+      VT_REQUIRE(lag == 1 || dep < l, "persist: layer %d depends on the later layer %d of the same step", l, dep);
+      L.dep[nd] = dep;
+      L.dep_lag[nd] = lag;
+      ++nd;
+    }
+    L.n_dep = nd;
+  }
+  P.n_layers = n_layers;
+  P.n_steps = d.n_steps;
+  P.tiles_per_step = tile_base;
+  P.n_sb = n_sb;
+  P.sbs = sbs;
+  P.B = B;
+  VT_REQUIRE((long long)tile_base * d.n_steps < (1ll << 31), "persist: too many tiles");
+  if (d.sde) {
+    const vt_sde_desc& s = *d.sde;
+    VT_REQUIRE(s.x && s.v && s.s && s.A >= 1 && s.rows == B * d.sde_T, "persist: bad Euler-Maruyama descriptor");
+    VT_REQUIRE(s.s == s.v + (long long)s.rows * s.A, "persist: v and s must be consecutive groups of the nets' output");
+    vt::PersistSde& S = P.sde;
+    S.x = s.x; S.v = s.v; S.s = s.s; S.noise = s.noise; S.noise_step = d.noise_step;
+    S.A = s.A; S.T = d.sde_T; S.d = s.d; S.seed = s.seed;
+    S.seed_dev = reinterpret_cast<const unsigned long long*>(s.seed_dev);
+    S.xpad = s.xpad; S.xpad_dtype = s.xpad_dtype; S.xpad_ld = s.xpad_ld; S.xpad_plane = s.xpad_plane;
+  }
+  // device tables: counters | expected | coefficients
+  const size_t cnt_bytes = ((size_t)cnt_off * 4 + 255) / 256 * 256;
+  const size_t exp_bytes = (expected.size() * 4 + 255) / 256 * 256;
+  const size_t coef_bytes = (size_t)d.n_steps * sizeof(vt::PersistCoef);
+  VT_CUDA(cudaMalloc(&op->dev_mem, cnt_bytes + exp_bytes + coef_bytes));
+  char* base = reinterpret_cast<char*>(op->dev_mem);
+  P.done = reinterpret_cast<unsigned*>(base);
+  P.expected = reinterpret_cast<const unsigned*>(base + cnt_bytes);
+  P.coef = reinterpret_cast<const vt::PersistCoef*>(base + cnt_bytes + exp_bytes);
+  op->counter_bytes = cnt_bytes;
+  VT_CUDA(cudaMemcpy(base + cnt_bytes, expected.data(), expected.size() * 4, cudaMemcpyHostToDevice));
+  std::vector<vt::PersistCoef> coef((size_t)d.n_steps);
+  for (int k = 0; k < d.n_steps; ++k) {
+    vt::PersistCoef c;
+    memset(&c, 0, sizeof(c));
+    if (d.sde_coef) {
+      c.ginv = d.sde_coef[5 * k]; c.dgg = d.sde_coef[5 * k + 1]; c.eps = d.sde_coef[5 * k + 2];
+      c.dt = d.sde_coef[5 * k + 3]; c.nscale = d.sde_coef[5 * k + 4];
+    }
+    coef[(size_t)k] = c;
+  }
+  VT_CUDA(cudaMemcpy(base + cnt_bytes + exp_bytes, coef.data(), coef_bytes, cudaMemcpyHostToDevice));
+  const int workers_max = sm_count() / 2;
+  const int workers = max_tiles < workers_max ? max_tiles : workers_max;
+  op->grid = dim3((unsigned)workers * 2u, 1u, 1u);
+  return VT_OK;
+}
+
 }  // namespace
 
 struct vt_program {
@@ -805,6 +948,15 @@ int vt_program_add_gemm(vt_program* p, const vt_gemm_desc* d) {
   return VT_OK;
 }
 
+int vt_program_add_persist(vt_program* p, const vt_persist_desc* d) {
+  if (!p || !d) return fail(VT_E_INVALID, "null argument");
+  std::unique_ptr<PersistOp> op(new PersistOp());
+  int rc = build_persist(*d, op.get());
+  if (rc) return rc;
+  p->ops.push_back(std::move(op));
+  return VT_OK;
+}
+
 // developer instrumentation: copy out (and reset) the epilogue timestamps recorded under VT_GEMM_DEBUG bit 128
 int vt_debug_timestamps(long long* out, int max_entries) {
   int n = 0;
@@ -868,7 +1020,7 @@ int vt_program_add_mlp(vt_program* p, const vt_mlp_desc* d) {
   e.vec = 1;
   e.fast = 1;
   {
-    const char* dbg = getenv("VT_GEMM_DEBUG");
+    const char* dbg = VT_DEBUG_KNOBS ? getenv("VT_GEMM_DEBUG") : nullptr;
     e.debug = dbg ? (atoi(dbg) & 128) : 0;
   }
   a.m_tiles = (d->rows + 127) / 128;

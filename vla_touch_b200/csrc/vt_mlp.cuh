@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const __grid_
     const uint32_t yfree_l = mapa_shared(smem_u32(y_free), 0);
     uint32_t ts = 0, cs = 0;
     int dbg_n = 0;
-    const bool ts_on = (a.epi.debug & 128) && blockIdx.x == 0 && threadIdx.x == 64;
+    const bool ts_on = kDbg && (a.epi.debug & 128) && blockIdx.x == 0 && threadIdx.x == 64;
     for (int unit = worker; unit < a.n_pairs; unit += n_workers, ++ts) {
       {
         // The residual rows this thread will read in the Y epilogue (twelve chunks = ~25 us from now) are requested from

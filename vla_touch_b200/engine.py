@@ -14,12 +14,14 @@ whole sequence is replayed as a single CUDA graph launch.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
 
 from . import native as nv
 from .dino import DinoProgram, DinoWeights, native_pos_resize
+from .persist import Collector, make_desc
 from .plan import Plan, linear_desc, ptr, round_up
 from .schedule import sde_coefficients, sde_schedule
 from .unet import (FILM_ROWS, Mode, UnetBuffers, UnetWeights, build_cond_film, build_time_film, build_unet_eval)
@@ -166,22 +168,29 @@ class BridgeEngine:
         from .unet import xpad_desc
         p.add(xpad_desc(self.unet, self.x, B * T, self.bufs), "x_prior->xpad")
         self.ranges["xprior"] = (start, len(p))
+        self._ts = ts
+        # The sampling loop.  bf16 mode: ONE persistent kernel launch for all steps (csrc/vt_persist.cuh; the op list of one
+        # evaluation + the Euler-Maruyama update, repeated n_steps times inside the kernel, ordered by per-sample-block
+        # counters instead of kernel boundaries).  fp32 (split-tf32) mode, VT_PERSIST=0, or stepping through the trajectory
+        # (`run_steps(k, 1)`): the multi-launch form, 36 implicit-GEMM launches + one update kernel per step.
+        self.persistent = (not precise) and os.environ.get("VT_PERSIST", "1") != "0"
         self.step_ranges: List[tuple] = []
-        self._sde_ops: List[int] = []
-        for k in range(self.n_steps):
+        self._step_plan: Optional[Plan] = None
+        if self.persistent:
             start = len(p)
-            build_unet_eval(p, self.unet, self.bufs, self.film_c, ptr(self.film_t, k * FILM_ROWS), self.n_steps * FILM_ROWS,
-                            tag=f"step{k}")
-            ginv, dgg, eps, nscale = sde_coefficients(ts[k], self.delta_t)
-            d = nv.SdeDesc()
-            d.x, d.v, d.s = ptr(self.x), ptr(self.bufs.out), ptr(self.bufs.out, B * T * A)
-            d.noise = ptr(self.noise, k * B * T * A) if inject_noise else None
-            d.rows, d.A = B * T, A
-            d.ginv, d.dgg, d.eps, d.dt, d.nscale, d.d = ginv, dgg, eps, self.delta_t, nscale, self.beta_max
-            d.seed, d.seed_dev, d.step = 0, ptr(self.seed), k
-            d.xpad, d.xpad_dtype, d.xpad_ld, d.xpad_plane = ptr(self.bufs.xpad), m.dt, m.ld(self.unet.cin0), m.plane(self.unet.cin0)
-            self._sde_ops.append(p.add(d, f"step{k}.euler_maruyama"))
-            self.step_ranges.append((start, len(p)))
+            col = Collector()
+            build_unet_eval(col, self.unet, self.bufs, self.film_c, ptr(self.film_t, 0), self.n_steps * FILM_ROWS, tag="unet")
+            coef = []
+            for k in range(self.n_steps):
+                ginv, dgg, eps, nscale = sde_coefficients(ts[k], self.delta_t)
+                coef.append((ginv, dgg, eps, self.delta_t, nscale))
+            d = self._sde_desc(0)
+            p.add(make_desc(p._reg, col.descs, sde=d, n_steps=self.n_steps, film_t_step=FILM_ROWS, coef=coef, noise_step=B * T * A,
+                            sde_T=T, tags=col.tags), f"sde_vs: {self.n_steps} x [v_net + s_net evaluation, Euler-Maruyama] (persistent)")
+            self.sampler_range = (start, len(p))
+        else:
+            self._build_steps(p)
+            self.sampler_range = (self.step_ranges[0][0], self.step_ranges[-1][1])
         start = len(p)
         p.add(_affine_desc(self.x, self.out, self.stats["action_mins"], self.stats["action_maxs"], B * T, A, 1),
               "denormalize_actions(expert)")
@@ -197,6 +206,40 @@ class BridgeEngine:
         self._setup_done = False
         self._graphs: Dict[tuple, object] = {}
         self._noise_mode: Optional[bool] = None
+
+    def _sde_desc(self, k: int) -> nv.SdeDesc:
+        B, T, A, m = self.B, self.T, self.A, self.mode
+        ginv, dgg, eps, nscale = sde_coefficients(self._ts[k], self.delta_t)
+        d = nv.SdeDesc()
+        d.x, d.v, d.s = ptr(self.x), ptr(self.bufs.out), ptr(self.bufs.out, B * T * A)
+        d.noise = ptr(self.noise, k * B * T * A) if self.inject_noise else None
+        d.rows, d.A = B * T, A
+        d.ginv, d.dgg, d.eps, d.dt, d.nscale, d.d = ginv, dgg, eps, self.delta_t, nscale, self.beta_max
+        d.seed, d.seed_dev, d.step = 0, ptr(self.seed), k
+        d.xpad, d.xpad_dtype, d.xpad_ld, d.xpad_plane = ptr(self.bufs.xpad), m.dt, m.ld(self.unet.cin0), m.plane(self.unet.cin0)
+        return d
+
+    def _build_steps(self, p: Plan) -> None:
+        """The multi-launch form of the sampling loop appended to plan `p`: per step 36 launches + the update kernel."""
+        self.step_ranges = []
+        for k in range(self.n_steps):
+            start = len(p)
+            build_unet_eval(p, self.unet, self.bufs, self.film_c, ptr(self.film_t, k * FILM_ROWS), self.n_steps * FILM_ROWS,
+                            tag=f"step{k}")
+            p.add(self._sde_desc(k), f"step{k}.euler_maruyama")
+            self.step_ranges.append((start, len(p)))
+
+    def _steps_plan(self) -> Plan:
+        """Multi-launch steps for callers that need the state after every step (sample(recod_traj=True)); built on first use,
+        shares every buffer with the main plan."""
+        if not self.persistent:
+            return self.plan
+        if self._step_plan is None:
+            sp = Plan(self.device)
+            sp._reg = self.plan._reg            # same tensors: addresses resolve identically
+            self._build_steps(sp)
+            self._step_plan = sp
+        return self._step_plan
 
     # ---- weight refresh (same device addresses: programs and graphs stay valid) ----
     def refresh_unet(self, v_sd: SD, s_sd: SD) -> None:
@@ -231,7 +274,11 @@ class BridgeEngine:
     def run_steps(self, first: int = 0, count: Optional[int] = None):
         self._ensure_setup()
         last = self.n_steps if count is None else first + count
-        self._run(self.step_ranges[first][0], self.step_ranges[last - 1][1])
+        if self.persistent and first == 0 and last == self.n_steps:
+            self._run(*self.sampler_range)
+            return
+        sp = self._steps_plan()
+        sp.compile().run(self.step_ranges[first][0], self.step_ranges[last - 1][1] - self.step_ranges[first][0])
 
     def predict_range(self) -> tuple:
         a = self.ranges["dino"][0]
@@ -242,7 +289,7 @@ class BridgeEngine:
         self._ensure_setup()
         prog = self.plan.compile()
         a0, a1 = self.ranges["dino"][0], self.ranges["normalize"][1]
-        b0, b1 = self.step_ranges[0][0], self.ranges["denormalize"][1]
+        b0, b1 = self.sampler_range[0], self.ranges["denormalize"][1]
         if not graph:
             prog.run(a0, a1 - a0)
             prog.run(b0, b1 - b0)

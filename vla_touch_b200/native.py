@@ -159,6 +159,16 @@ class OptTensor(C.Structure):
                 ("taps", i32), ("c", i32), ("c_pad", i32), ("reserved", i32), ("w_op", vp)]
 
 
+PERSIST_MAX_DEPS, PERSIST_MAX_LAYERS = 4, 37
+
+
+class PersistDesc(C.Structure):
+    """vt_persist_desc.  The host arrays it points to are kept alive as Python attributes of the instance (`_keep`); `layers`,
+    `sde`, `coef` mirror them for inspection and for the CPU plan interpreter."""
+    _fields_ = [("gemms", vp), ("n_gemms", i32), ("sde", vp), ("deps", vp), ("dep_lag", vp), ("n_steps", i32),
+                ("film_t_step", i64), ("sde_coef", vp), ("noise_step", i64), ("sde_T", i32)]
+
+
 class AdamwDesc(C.Structure):
     _fields_ = [("tensors", vp), ("chunks", vp), ("n_chunks", i32), ("chunk_elems", i32), ("lr", f32), ("beta1", f32),
                 ("beta2", f32), ("eps", f32), ("weight_decay", f32), ("bias_corr1", f32), ("bias_corr2", f32),
@@ -170,7 +180,7 @@ EXPORTS = [
     "vt_program_num_ops", "vt_program_num_launches", "vt_program_add_gemm", "vt_program_add_layernorm",
     "vt_program_add_attention", "vt_program_add_mlp", "vt_debug_timestamps", "vt_program_add_imgstats", "vt_program_add_patchify", "vt_program_add_cls",
     "vt_program_add_pack", "vt_program_add_affine", "vt_program_add_tembed", "vt_program_add_sde",
-    "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_add_tcol", "vt_program_add_gnbwd", "vt_program_add_colsum", "vt_program_add_ewise", "vt_program_add_silossbwd", "vt_program_add_lstm_train", "vt_program_add_lstm_bwd", "vt_program_add_lngelubwd", "vt_program_add_dropmask", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
+    "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_add_tcol", "vt_program_add_gnbwd", "vt_program_add_colsum", "vt_program_add_ewise", "vt_program_add_silossbwd", "vt_program_add_lstm_train", "vt_program_add_lstm_bwd", "vt_program_add_lngelubwd", "vt_program_add_dropmask", "vt_program_add_persist", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
     "vt_pos_embed_resize", "vt_adamw_ema_step",
 ]
 
@@ -182,7 +192,7 @@ _ADD = {
     SilossDesc: "vt_program_add_siloss", TcolDesc: "vt_program_add_tcol", GnbwdDesc: "vt_program_add_gnbwd",
     ColsumDesc: "vt_program_add_colsum", EwiseDesc: "vt_program_add_ewise",
     SilossBwdDesc: "vt_program_add_silossbwd", LstmTrainDesc: "vt_program_add_lstm_train", LstmBwdDesc: "vt_program_add_lstm_bwd",
-    LnGeluBwdDesc: "vt_program_add_lngelubwd", DropmaskDesc: "vt_program_add_dropmask",
+    LnGeluBwdDesc: "vt_program_add_lngelubwd", DropmaskDesc: "vt_program_add_dropmask", PersistDesc: "vt_program_add_persist",
 }
 
 _lib: Optional[C.CDLL] = None
