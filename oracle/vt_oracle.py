@@ -347,6 +347,24 @@ def sde_vs(v_sd: SD, s_sd: SD, x_initial: torch.Tensor, cond: torch.Tensor, diff
     return (x, traj) if return_traj else x
 
 
+def sde_bs(b_sd: SD, s_sd: SD, x_initial: torch.Tensor, cond: torch.Tensor, diffuse_step: int = 10,
+           beta_max: float = 0.03, noise: Optional[torch.Tensor] = None, quant=None):
+    """StochasticInterpolants.sample with sde_type='bs' -> sde_bs (forward direction, score_weight=1), bridge_model.py:281-332:
+    the drift comes straight from b_net instead of v_net - dot_gamma gamma eps s."""
+    n_steps, delta_t, ts = sde_schedule(diffuse_step)
+    B = x_initial.shape[0]
+    x = x_initial
+    for k in range(n_steps):
+        t = ts[k].expand(B)
+        ginv, _, eps, noise_scale = sde_coefficients(t, delta_t, beta_max)
+        b = unet_forward(b_sd, x, t, cond, quant=quant)
+        s = unet_forward(s_sd, x, t, cond, quant=quant) * ginv[:, None, None]
+        z = torch.randn_like(x) if noise is None else noise[k]
+        new_x = x + (b + 1.0 * eps[0] * s) * delta_t
+        x = new_x + noise_scale[0] * (beta_max * z)
+    return x
+
+
 def predict(dino_sd: SD, enc_sd: SD, v_sd: SD, s_sd: SD, stats, num_heads: int, state, vla_actions, img1, img2,
             forces, diffuse_step: int = 10, beta_max: float = 0.03, noise=None, quant=None):
     """DiffusionController.predict  bridge_controller.py:149-182 (v_sd/s_sd = EMA weights, :267)"""

@@ -141,6 +141,22 @@ def test_persistent_sampler_equals_the_multi_launch_form(A, T, B, n, monkeypatch
     assert torch.equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("precise", MODES)
+def test_sample_sde_bs_with_recorded_noise(precise):
+    """sde_type='bs' (bridge_model.py:271-273, 281-332): b_net + s_net, golden from the reference itself."""
+    A, T = 7, 64
+    g = U.golden(f"sde_bs_A{A}_T{T}_n10")
+    si = _interpolant(A, T, precise)
+    si.sde_type = 'bs'
+    x0 = syn.det_uniform("sde.x0", (2, T, A), 23, -1.0, 1.0).to(DEV)
+    cond = syn.det_normal("sde.cond", (2, 256), 23).to(DEV)
+    si.noise_override = g["noise"].to(DEV)
+    out, traj = si.sample(x_prior=x0, cond=cond, diffuse_step=10, recod_traj=True)
+    check(traj[1], g["x1"], precise, "first step (bs)")
+    check(out, g["out"], precise, "sample (bs)")
+    assert torch.equal(si.sample(x_prior=x0, cond=cond, diffuse_step=10), out)
+
+
 @pytest.mark.parametrize("A,T", [(10, 16), (7, 64)])
 def test_sample_beta0_is_noise_free(A, T):
     g = U.golden(f"sde_A{A}_T{T}_n10_beta0")

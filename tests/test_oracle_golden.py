@@ -81,6 +81,19 @@ def test_sde_vs_beta0(A, T):
     torch.testing.assert_close(out, g["out"], rtol=0, atol=5e-5)
 
 
+def test_sde_bs_recorded_noise():
+    """sde_type='bs' (bridge_model.py:271-273,281-332): b_net drives the drift; fixture from the reference itself
+    (oracle/gen_golden_extra.py), EMA weights."""
+    A, T = 7, 64
+    g = U.golden(f"sde_bs_A{A}_T{T}_n10")
+    x0 = syn.det_uniform("sde.x0", (2, T, A), 23, -1.0, 1.0)
+    cond = syn.det_normal("sde.cond", (2, 256), 23)
+    out = orc.sde_bs(U.net_sd(A, 1021, "b_net"), U.net_sd(A, 1021, "s_net"), x0, cond, 10, 0.03, g["noise"])
+    torch.testing.assert_close(out, g["out"], rtol=0, atol=5e-5)
+    bad = orc.sde_vs(U.net_sd(A, 1021, "v_net"), U.net_sd(A, 1021, "s_net"), x0, cond, 10, 0.03, g["noise"])
+    assert (bad - g["out"]).abs().max() > 1e-3
+
+
 def test_sde_schedule_step_count_quirk():
     # n = int(1/float(1/diffuse_step)) differs from diffuse_step for some values (SURVEY 8 a7)
     for ds, n in ((10, 10), (50, 50), (93, 92), (99, 98)):

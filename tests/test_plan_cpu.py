@@ -92,8 +92,10 @@ def test_schedule_matches_oracle_and_reference_quirks():
     assert sch.sde_schedule(93)[0] == 92
     with pytest.raises(NotImplementedError):
         sch.check_model_args({"gamma_type": "(2t(t-1))^0.5"})
+    sch.check_model_args({"sde_type": "bs"})                   # sde_bs (bridge_model.py:281-332) = the 'vs' update with b_net as drift
+    assert sch.sde_coefficients(sch.sde_schedule(10)[2][3], 0.1, "bs")[1] == 0.0
     with pytest.raises(NotImplementedError):
-        sch.check_model_args({"sde_type": "bs"})
+        sch.check_model_args({"sde_type": "xs"})
 
 
 @pytest.mark.parametrize("precise,A,T,tol", [(True, 7, 64, 5e-5), (True, 10, 48, 5e-5), (False, 10, 16, 8e-2)])
@@ -606,3 +608,104 @@ def test_native_encoder_training_matches_torch_autograd(monkeypatch):
             for p in enc.parameters():
                 p.mul_(1.05)
     assert len(cache) == 1
+
+
+def test_checkpoint_files_have_the_reference_structure(tmp_path):
+    """controller.pt / bridge_model.pt / tactile_controller.pt written by vla_touch_b200 have exactly the key paths, order, shapes
+    and dtypes of the files the reference writes (bridge_controller.py:203-244, bridge_model.py:435-447,
+    lstm_step_controller.py:351-379; manifest recorded from the reference by oracle/gen_golden_extra.py), incl. the `ema` dict
+    (decay, num_updates, shadow_params in net.parameters() order, collected_params)."""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from oracle.gen_golden_extra import manifest
+    from vla_touch_b200.bridge_controller import DiffusionController
+    from vla_touch_b200.lstm_step_controller import TactileLSTMController
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "ckpt_manifest.json")))
+    A, Fd, T = gold["A"], gold["F"], gold["T"]
+    ma = {'interpolant_type': 'linear', 'gamma_type': '2^0.5*t(t-1)', 'epsilon_type': '1-t', 'prior_policy': 'vla', 'beta_max': 0.03,
+          'sde_type': 'bs', 'action_dim': A, 'obs_dim': 256, 'obs_horizon': 1, 'net_type': 'unet1D_si', 'pretrain': False,
+          'context_frames': 2, 'horizon': T}
+    dino = U.dino_sd(384, 1, 1)
+    ctl = DiffusionController(state_dim=A, hidden_dim=256, diffusion_steps=10, device="cpu", model_args=ma, use_force=True, force_dim=Fd,
+                              image_state_dict=dino)
+    ctl.stats = {k: v.numpy() for k, v in syn.synth_stats(A).items()}
+    ctl.save(str(tmp_path))
+    lc = TactileLSTMController(state_dim=A, hidden_dim=256, num_layers=2, dropout=0.1, device="cpu", force_dim=Fd, image_state_dict=dino)
+    lc.stats = {k: torch.as_tensor(v) for k, v in ctl.stats.items()}
+    lc.save(str(tmp_path))
+    for f, want in gold["files"].items():
+        got = manifest(torch.load(os.path.join(str(tmp_path), f), map_location="cpu", weights_only=False))
+        strip = lambda m: [[a, b, c, d] for a, b, c, d in m]
+        assert len(got) == len(want), (f, len(got), len(want))
+        for g_, w_ in zip(strip(got), want):
+            assert g_ == w_, (f, g_, w_)
+    # and they load back (round trip through the files)
+    ctl2 = DiffusionController(state_dim=A, hidden_dim=256, diffusion_steps=10, device="cpu", model_args=ma, use_force=True, force_dim=Fd,
+                               image_state_dict=dino)
+    ctl2.load(str(tmp_path))
+    for a, b in zip(ctl.diffusion_model.net.parameters(), ctl2.diffusion_model.net.parameters()):
+        assert torch.equal(a, b)
+    assert ctl2.diffusion_model.ema.num_updates == ctl.diffusion_model.ema.num_updates
+    lc2 = TactileLSTMController(state_dim=A, hidden_dim=256, num_layers=2, dropout=0.1, device="cpu", force_dim=Fd, image_state_dict=dino)
+    lc2.load(str(tmp_path))
+    for a, b in zip(lc.lstm.parameters(), lc2.lstm.parameters()):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference tree (build container only)")
+def test_checkpoints_interchange_with_the_reference_classes(tmp_path):
+    """Files SAVED BY THE IMPORTED REFERENCE load into the drop-in classes with identical tensors, and files saved by the drop-in
+    classes load into the reference classes (bridge_controller.py:203-244, bridge_model.py:421-447, lstm_step_controller.py:351-379)."""
+    from oracle.ref_shims import import_reference
+    from vla_touch_b200.bridge_controller import DiffusionController
+    from vla_touch_b200.lstm_step_controller import TactileLSTMController
+    import contextlib, io
+    ref = import_reference(num_dino_layers=1)
+    A, Fd, T = 7, 64, 16
+    ma = {'interpolant_type': 'linear', 'gamma_type': '2^0.5*t(t-1)', 'epsilon_type': '1-t', 'prior_policy': 'vla', 'beta_max': 0.03,
+          'sde_type': 'vs', 'action_dim': A, 'obs_dim': 256, 'obs_horizon': 1, 'net_type': 'unet1D_si', 'pretrain': False,
+          'context_frames': 2, 'horizon': T}
+    with contextlib.redirect_stdout(io.StringIO()):
+        rc = ref.bridge_controller.DiffusionController(state_dim=A, hidden_dim=256, image_model_path="facebook/dinov2-small",
+                                                       diffusion_steps=10, device="cpu", model_args=dict(ma), use_force=True, force_dim=Fd)
+        rl = ref.lstm_step_controller.TactileLSTMController(state_dim=A, hidden_dim=256, num_layers=2, dropout=0.1, device="cpu", force_dim=Fd)
+    syn.fill_named_(rc.diffusion_model.net.named_parameters(), 5, prefix="net.")
+    syn.fill_named_(rc.state_encoder.named_parameters(), 5, prefix="enc.")
+    rc.diffusion_model.ema.update()                       # shadow != live, num_updates = 1
+    rc.stats = {k: v.numpy() for k, v in syn.synth_stats_varied(A, 2).items()}
+    rl.stats = {k: torch.as_tensor(v) for k, v in rc.stats.items()}
+    d_ref = tmp_path / "ref"; d_ref.mkdir()
+    rc.save(str(d_ref)); rl.save(str(d_ref))
+    dino = U.dino_sd(384, 1, 1)
+    ours = DiffusionController(state_dim=A, hidden_dim=256, diffusion_steps=10, device="cpu", model_args=dict(ma), use_force=True,
+                               force_dim=Fd, image_state_dict=dino)
+    _cuda = torch.Tensor.cuda
+    ours.load(str(d_ref))
+    for (n, a), b in zip(rc.diffusion_model.net.named_parameters(), ours.diffusion_model.net.parameters()):
+        assert torch.equal(a, b), n
+    for a, b in zip(rc.diffusion_model.ema.shadow_params, ours.diffusion_model.ema.shadow_params):
+        assert torch.equal(a, b)
+    assert ours.diffusion_model.ema.num_updates == 1 and ours.diffusion_model.ema.decay == rc.diffusion_model.ema.decay
+    for a, b in zip(rc.state_encoder.parameters(), ours.state_encoder.parameters()):
+        assert torch.equal(a, b)
+    for k, v in rc.stats.items():
+        assert torch.equal(ours.stats[k].cpu(), torch.as_tensor(v, dtype=torch.float32))
+    lo = TactileLSTMController(state_dim=A, hidden_dim=256, num_layers=2, dropout=0.1, device="cpu", force_dim=Fd, image_state_dict=dino)
+    lo.load(str(d_ref))
+    for mod in ("obs_encoder", "force_encoder", "lstm", "output_head"):
+        for (n, a), b in zip(getattr(rl, mod).named_parameters(), getattr(lo, mod).parameters()):
+            assert torch.equal(a, b), (mod, n)
+    # the other direction: our files into the reference's state dicts (its own load() hard-codes .cuda(), bridge_controller.py:241)
+    d_ours = tmp_path / "ours"; d_ours.mkdir()
+    with torch.no_grad():
+        for p_ in ours.diffusion_model.net.parameters():
+            p_.mul_(1.01)
+    ours.save(str(d_ours)); lo.save(str(d_ours))
+    ck = torch.load(str(d_ours / "controller.pt"), map_location="cpu", weights_only=False)
+    rc.state_encoder.load_state_dict(ck['state_encoder']); rc.force_decoder.load_state_dict(ck['force_decoder'])
+    rc.diffusion_model.load_model({**ck['model_args'], 'ckpt_path': str(d_ours), 'pretrain': True}, "cpu")
+    for a, b in zip(rc.diffusion_model.net.parameters(), ours.diffusion_model.net.parameters()):
+        assert torch.equal(a, b)
+    ck = torch.load(str(d_ours / "tactile_controller.pt"), map_location="cpu", weights_only=False)
+    for mod in ("obs_encoder", "force_encoder", "lstm", "output_head"):
+        getattr(rl, mod).load_state_dict(ck['modules'][mod])

@@ -79,7 +79,8 @@ class StochasticInterpolants:
     def ema_state_dicts(self):
         names = [n for n, _ in self.net.named_parameters()]
         full = {n: s for n, s in zip(names, self.ema.shadow_params)}
-        return sub_state_dict(full, "v_net."), sub_state_dict(full, "s_net.")
+        drift = "b_net." if self.sde_type == 'bs' else "v_net."          # sde_bs integrates b_net directly (:271-273)
+        return sub_state_dict(full, drift), sub_state_dict(full, "s_net.")
 
     def _engine(self, B: int, T: int, diffuse_step: int, inject: bool) -> BridgeEngine:
         key = (B, T, diffuse_step, inject)
@@ -89,7 +90,7 @@ class StochasticInterpolants:
             eng = BridgeEngine(dino=None, enc_sd=None, v_sd=v_sd, s_sd=s_sd, action_dim=self.net.input_dim,
                                state_dim=self.net.input_dim, force_dim=0, use_force=False, B=B, T=T, diffuse_step=diffuse_step,
                                beta_max=self.d, device=self.device, precise=self.precise, hidden_dim=self.net.global_cond_dim,
-                               inject_noise=inject)
+                               inject_noise=inject, sde_type=self.sde_type)
             self._engines[key] = eng
             self._engine_version[key] = self.ema.version
         elif self._engine_version[key] != self.ema.version:
@@ -100,7 +101,7 @@ class StochasticInterpolants:
     @torch.no_grad()
     def sample(self, x_prior, cond, diffuse_step=10, recod_traj=False):
         """x_prior [B,T,A] (normalised), cond [B,obs_dim] -> x_target [B,T,A] (and the trajectory list)."""
-        if self.sde_type != 'vs':
+        if self.sde_type not in ('vs', 'bs'):
             raise NotImplementedError
         B, T, A = x_prior.shape
         inject = self.noise_override is not None

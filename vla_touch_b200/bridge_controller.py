@@ -99,7 +99,7 @@ class DiffusionController:
                                action_dim=dm.net.input_dim, state_dim=self.state_dim, force_dim=self.force_dim,
                                use_force=self.use_force, B=B, T=T, H=H, W=W, img_dtype=img_dtype, layout=layout,
                                diffuse_step=self.diffusion_steps, beta_max=dm.d, device=self.device, precise=self.precise,
-                               hidden_dim=self.hidden_dim, inject_noise=inject)
+                               hidden_dim=self.hidden_dim, inject_noise=inject, sde_type=dm.sde_type)
             self._engines[key] = eng
             self._versions[key] = ver
         elif self._versions[key] != ver:

@@ -204,30 +204,48 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) unet_persist_kernel(const 
             const int n_tile = tile % a.n_tiles, rest = tile / a.n_tiles;
             const int unit = rest % a.m_tiles, g = rest / a.m_tiles;
             const int m_tile = unit * 2 + rank;
-            persist_wait(P, L, step, g, unit);
-            fence_proxy_async_global();
             const int b_base = m_tile * a.m_b_step, t_base = m_tile * a.m_t_step, g_a = g * a.a_g_mul;
             const int g_b = g * a.n_pad + n_tile * L.bn + rank * b_rows;
-            int left = nk, at = 0, n_at = 0, kb = 0;
-            for (int tp = 0; tp < a.taps; ++tp) {
-              const int tap_p = a.tap_p[tp], tap_t = t_base + a.tap_t[tp];
-              for (int cb = 0; cb < a.cblocks; ++cb, kb += KE) {
-                if (at == 0) {
-                  n_at = left < KA ? left : KA;
-                  mbar_wait(&empty[s], ph ^ 1);
-                  if (rank == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)n_at * stage_tx);
+            const int n_stages = (nk + KA - 1) / KA;
+            // The weight tiles depend on nothing: the first ring-full of stages is opened and its B halves are requested BEFORE
+            // the wait for the producers of the A operand, so their L2 round trip overlaps the dependency latency.
+            const int pre = n_stages < STAGES ? n_stages : STAGES;
+            const int s0 = s;
+            for (int q = 0; q < pre; ++q) {
+              const int n_at = (nk - q * KA) < KA ? (nk - q * KA) : KA;
+              mbar_wait(&empty[s], ph ^ 1);
+              if (rank == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)n_at * stage_tx);
+              const uint32_t fb = mapa_shared(smem_u32(&full[s]), 0);
+              for (int at = 0; at < n_at; ++at)
+                tma_load_2d_pair(sB + s * B_STAGE_BYTES + at * B_ATOM_SLOT, &a.tmB, fb, (q * KA + at) * KE, g_b);
+              if (++s == STAGES) {
+                s = 0;
+                ph ^= 1;
+              }
+            }
+            persist_wait(P, L, step, g, unit);
+            fence_proxy_async_global();
+            for (int q = 0; q < n_stages; ++q) {
+              const int n_at = (nk - q * KA) < KA ? (nk - q * KA) : KA;
+              int slot;
+              if (q < pre) {
+                slot = s0 + q >= STAGES ? s0 + q - STAGES : s0 + q;
+              } else {
+                slot = s;
+                mbar_wait(&empty[s], ph ^ 1);
+                if (rank == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)n_at * stage_tx);
+                if (++s == STAGES) {
+                  s = 0;
+                  ph ^= 1;
                 }
-                const uint32_t fb = mapa_shared(smem_u32(&full[s]), 0);
-                tma_load_5d_pair(sA + s * A_STAGE_BYTES + at * A_ATOM_BYTES, &a.tmA, fb, a.a_c0 + cb * KE, tap_p, tap_t, b_base, g_a);
-                tma_load_2d_pair(sB + s * B_STAGE_BYTES + at * B_ATOM_SLOT, &a.tmB, fb, kb, g_b);
-                --left;
-                if (++at == n_at) {
-                  at = 0;
-                  if (++s == STAGES) {
-                    s = 0;
-                    ph ^= 1;
-                  }
-                }
+              }
+              const uint32_t fb = mapa_shared(smem_u32(&full[slot]), 0);
+              for (int at = 0; at < n_at; ++at) {
+                const int i = q * KA + at;
+                const int tp = i / a.cblocks, cb = i - tp * a.cblocks;
+                tma_load_5d_pair(sA + slot * A_STAGE_BYTES + at * A_ATOM_BYTES, &a.tmA, fb, a.a_c0 + cb * KE, a.tap_p[tp],
+                                 t_base + a.tap_t[tp], b_base, g_a);
+                if (q >= pre) tma_load_2d_pair(sB + slot * B_STAGE_BYTES + at * B_ATOM_SLOT, &a.tmB, fb, i * KE, g_b);
               }
             }
           }

@@ -79,8 +79,7 @@ class ExponentialMovingAverage:
         try:
             yield
         finally:
-            self.restore(parameters)
-            self.collected_params = None
+            self.restore(parameters)         # torch_ema keeps `collected_params` afterwards (it is part of state_dict())
 
     def to(self, device=None, dtype=None) -> None:
         self.shadow_params = [p.to(device=device, dtype=dtype) if p.is_floating_point() else p.to(device=device)

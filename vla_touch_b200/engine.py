@@ -96,7 +96,11 @@ class BridgeEngine:
                  force_dim: int, use_force: bool, B: int, T: int, H: int = 0, W: int = 0,
                  img_dtype: torch.dtype = torch.uint8, layout: int = nv.LAYOUT_BHWC, diffuse_step: int = 10,
                  beta_max: float = 0.03, device="cuda", precise: bool = False, resize=native_pos_resize,
-                 hidden_dim: int = 256, inject_noise: bool = False):
+                 hidden_dim: int = 256, inject_noise: bool = False, sde_type: str = "vs"):
+        """v_sd: the drift net -- v_net for sde_type 'vs' (sde_vs, bridge_model.py:334-387), b_net for 'bs' (sde_bs, :281-332)."""
+        if sde_type not in ("vs", "bs"):
+            raise NotImplementedError(f"sde_type={sde_type!r}")
+        self.sde_type = sde_type
         self.device = torch.device(device)
         self.mode = m = Mode(precise)
         self.B, self.T, self.A = B, T, action_dim
@@ -182,7 +186,7 @@ class BridgeEngine:
             build_unet_eval(col, self.unet, self.bufs, self.film_c, ptr(self.film_t, 0), self.n_steps * FILM_ROWS, tag="unet")
             coef = []
             for k in range(self.n_steps):
-                ginv, dgg, eps, nscale = sde_coefficients(ts[k], self.delta_t)
+                ginv, dgg, eps, nscale = sde_coefficients(ts[k], self.delta_t, self.sde_type)
                 coef.append((ginv, dgg, eps, self.delta_t, nscale))
             d = self._sde_desc(0)
             p.add(make_desc(p._reg, col.descs, sde=d, n_steps=self.n_steps, film_t_step=FILM_ROWS, coef=coef, noise_step=B * T * A,
@@ -209,7 +213,7 @@ class BridgeEngine:
 
     def _sde_desc(self, k: int) -> nv.SdeDesc:
         B, T, A, m = self.B, self.T, self.A, self.mode
-        ginv, dgg, eps, nscale = sde_coefficients(self._ts[k], self.delta_t)
+        ginv, dgg, eps, nscale = sde_coefficients(self._ts[k], self.delta_t, self.sde_type)
         d = nv.SdeDesc()
         d.x, d.v, d.s = ptr(self.x), ptr(self.bufs.out), ptr(self.bufs.out, B * T * A)
         d.noise = ptr(self.noise, k * B * T * A) if self.inject_noise else None

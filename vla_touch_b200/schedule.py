@@ -21,8 +21,8 @@ def check_model_args(model_args: dict) -> None:
         got = model_args.get(key, want)
         if got != want:
             raise NotImplementedError(f"{key}={got!r}: only {want!r} is implemented on the B200 path")
-    if model_args.get("sde_type", "vs") != "vs":
-        raise NotImplementedError(f"sde_type={model_args.get('sde_type')!r}: only 'vs' is implemented on the B200 path")
+    if model_args.get("sde_type", "vs") not in ("vs", "bs"):
+        raise NotImplementedError(f"sde_type={model_args.get('sde_type')!r}: 'vs' and 'bs' are implemented (bridge_model.py:268-275)")
     if model_args.get("net_type", "unet1D_si") != "unet1D_si":
         raise NotImplementedError(f"net_type={model_args.get('net_type')!r}")
 
@@ -39,11 +39,13 @@ def sde_schedule(diffuse_step: int) -> Tuple[int, float, List[torch.Tensor]]:
     return n_steps, delta_t, ts
 
 
-def sde_coefficients(t: torch.Tensor, delta_t: float) -> Tuple[float, float, float, float]:
-    """(gamma_inv, dot_gamma*gamma, epsilon, delta_t*sqrt(2 epsilon)) at time t (fp32, reference operation order)."""
+def sde_coefficients(t: torch.Tensor, delta_t: float, sde_type: str = "vs") -> Tuple[float, float, float, float]:
+    """(gamma_inv, dot_gamma*gamma, epsilon, delta_t*sqrt(2 epsilon)) at time t (fp32, reference operation order).
+    sde_type 'bs' (sde_bs, bridge_model.py:281-332): the drift net's output is used as it is, i.e. the dot_gamma*gamma
+    coefficient of the velocity form (b = v - dot_gamma gamma eps s, :369) is zero."""
     gamma = 1.4142 * t * (1 - t)
     dgamma = 1.4142 * (1 - 2 * t)
     ginv = torch.clamp(1 / (1.4142 * t * (1 - t) + 1e-4), 0.0, GAMMA_INV_MAX)
     eps = (1 - t) * 1.0
     nscale = delta_t * torch.sqrt(2 * eps)
-    return float(ginv), float(dgamma * gamma), float(eps), float(nscale)
+    return float(ginv), (0.0 if sde_type == "bs" else float(dgamma * gamma)), float(eps), float(nscale)
