@@ -408,6 +408,11 @@ typedef struct vt_lstm_desc {
   int64_t y_ld;
   int64_t y_plane;    /* >0 (f32): tf32 hi/lo split of y */
   int32_t B, T, H;
+  /* Tensor-core recurrence (csrc/vt_lstm_tc.cuh: a cluster of 8 CTAs per 128 batch rows keeps W_hh in shared memory for all T steps,
+   * tcgen05 MMA per step).  Used when all three are set and B >= 16; the fp32 parity mode and single control ticks leave them null. */
+  const void* w_hh_tc; /* bf16 [4H][H], row = unit * 4 + gate (W_hh rows regrouped per hidden unit) */
+  void* h_tc;          /* bf16 [B][T][H] scratch: h of every step */
+  int32_t zero_init;   /* 1: the state h / c is zero on entry (whole-sequence passes); required by the tensor-core path */
 } vt_lstm_desc;
 
 /* Training forward of one nn.LSTM layer from a zero initial state (lstm_step_controller.py:196-204): like vt_lstm_desc, and keeps
@@ -421,6 +426,8 @@ typedef struct vt_lstm_train_desc {
   float* gates;       /* [B][T][4H] sigmoid(i), sigmoid(f), tanh(g), sigmoid(o) */
   float* c;           /* [B][T][H] */
   int32_t B, T, H;
+  const void* w_hh_tc; /* see vt_lstm_desc: both set and B >= 16 -> tensor-core recurrence */
+  void* h_tc;
 } vt_lstm_train_desc;
 
 /* Back-propagation through time of one LSTM layer: the sequential part of what torch autograd runs for nn.LSTM in
@@ -434,6 +441,8 @@ typedef struct vt_lstm_bwd_desc {
   const float* w_hh;  /* W_hh as stored by nn.LSTM: [4H][H] */
   float* dgates;      /* [B][T][4H] */
   int32_t B, T, H;
+  const void* w_hh_t_tc; /* bf16 W_hh TRANSPOSED [H][4H]; with dg_tc set and B >= 16 -> tensor-core BPTT (csrc/vt_lstm_tc.cuh) */
+  void* dg_tc;           /* bf16 [B][T][4H] scratch: d gates, the recurrence's A operand */
 } vt_lstm_bwd_desc;
 
 /* Fused multi-tensor optimizer step of the bridge trainer (bridge_train.py:330-337 + torch_ema update):

@@ -273,7 +273,10 @@ def test_lstm_controller(A, Fd, T, precise):
     vla_n = normalize_actions(vla, lc.stats, 'vla')
     batch = {"vla_act": vla_n, "obs_cond": cond, "forces": forces, "expert_act": expert}
     check(lc.forward(batch), g["fwd"], precise, "forward")
-    assert abs(float(lc.get_loss(batch)) - float(g["loss"])) <= (1e-4 if precise else 5e-2 * float(g["loss"]))
+    with torch.no_grad():                        # validation semantics (lstm_train.py:190-215): the loss value of the inference program
+        assert abs(float(lc.get_loss(batch)) - float(g["loss"])) <= (1e-4 if precise else 5e-2 * float(g["loss"]))
+    loss = lc.get_loss(batch)                    # grad mode on: the differentiable loss of the (bf16) training program
+    assert loss.requires_grad and abs(float(loss.detach()) - float(g["loss"])) <= 5e-2 * float(g["loss"])
     check(lc.predict_sequence(cond, vla, forces), g["seq"], precise, "predict_sequence")
     # stateful single-step deployment path (:232-286): T ticks carrying (h, c)
     steps = [lc.predict(cond, vla_n[:, t], forces[:, t], initialize=(t == 0)) for t in range(T)]

@@ -279,3 +279,39 @@ def test_no_visual_controller_predicts_and_trains():
     assert out.shape == (B, T, A) and torch.isfinite(out).all()
     cond_t = ctl.encode_observation(state.to(DEV), None, None, forces.to(DEV))
     assert cond_t.requires_grad and cond_t.shape == (B, 256)
+
+
+@pytest.mark.parametrize("B,T", [(40, 24), (256, 8)])
+def test_lstm_tensor_core_recurrence_equals_the_cuda_core_kernels(B, T, monkeypatch):
+    """csrc/vt_lstm_tc.cuh (cluster of 8 CTAs per 128 rows, W_hh resident in shared memory, tcgen05 MMA per step) against the
+    CUDA-core recurrence kernels of csrc/vt_lstm.cuh on the same program: loss, every one of the 18 parameter gradients and
+    d obs_cond of get_loss forward + BPTT, and the inference forward.  Ragged row block (40 of 128) and two clusters (256 rows).
+    The kernels differ in operand precision (bf16 h / d gates on the tensor cores) and in the MUFU tanh: gate 2e-2 of scale."""
+    from vla_touch_b200 import shapes as shp
+    from vla_touch_b200 import synthetic as syn
+    from vla_touch_b200.lstm_step_controller import LstmEngine
+    from vla_touch_b200.lstm_train import LstmLossBackwardProgram
+    A, Fd = 7, 64
+    mods = {"force_encoder": syn.synth_state_dict(shp.mlp_shapes([Fd, 128, 128]), 41, "lstm.force_encoder."),
+            "lstm": syn.synth_state_dict(shp.lstm_shapes(128 + A), 41, "lstm.lstm."),
+            "output_head": syn.synth_state_dict(shp.lstm_head_shapes(256, A), 41, "lstm.output_head.")}
+    vla, f = syn.det_uniform("lt.vla", (B, T, A), 1, -1.0, 1.0), syn.det_normal("lt.f", (B, T, Fd), 1)
+    cond, exp = syn.det_normal("lt.cond", (B, 256), 1), syn.det_uniform("lt.exp", (B, T, A), 1, -1.0, 1.0)
+    res = {}
+    for tc in ("1", "0"):
+        monkeypatch.setenv("VT_LSTM_TC", tc)
+        lp = LstmLossBackwardProgram(mods, A, Fd, B, T, DEV)
+        lp.set_inputs(vla, f, cond, exp)
+        lp.run()
+        torch.cuda.synchronize()
+        eng = LstmEngine(mods, A, Fd, 256, 2, B, T, DEV, False, False)
+        eng.vla.copy_(vla); eng.forces.copy_(f); eng.cond.copy_(cond)
+        eng.run()
+        torch.cuda.synchronize()
+        res[tc] = (lp.loss(), {k: v.detach().float().clone() for k, v in lp.grads.items()}, lp.d_cond.clone(), eng.out.clone())
+    (l1, g1, d1, o1), (l0, g0, d0, o0) = res["1"], res["0"]
+    rel = lambda a, b: float((a - b).abs().max()) / max(float(b.abs().max()), 1e-12)
+    assert abs(l1 - l0) <= 2e-2 * abs(l0)
+    assert rel(o1, o0) <= 2e-2 and rel(d1, d0) <= 2e-2
+    worst = {k: rel(g1[k], g0[k]) for k in g0}
+    assert len(worst) == 18 and max(worst.values()) <= 2e-2, worst

@@ -17,6 +17,7 @@
 #include "vt_gemm.cuh"
 #include "vt_persist.cuh"
 #include "vt_lstm.cuh"
+#include "vt_lstm_tc.cuh"
 #include "vt_bwd.cuh"
 
 namespace {
@@ -685,9 +686,58 @@ struct SilossBwdOp : Op {
   }
 };
 
+// tensor-core recurrence (vt_lstm_tc.cuh): shared by the inference and the training forward
+constexpr int LSTM_TC_MIN_BATCH = 16;
+int build_lstm_tc(vt::LstmTcArgs* a, const void* w_hh_tc, void* h_tc, const float* xw, void* y, int y_dtype, long long y_ld,
+                  float* gates, float* c_all, float* h_out, float* c_out, int B, int T) {
+  const int H = vt::LTC_H;
+  memset(a, 0, sizeof(*a));
+  {
+    const uint64_t dims[2] = {(uint64_t)H, (uint64_t)4 * H};
+    const uint64_t st[1] = {(uint64_t)H * 2};
+    const uint32_t box[2] = {64u, 128u};
+    int rc = make_tmap(&a->tmW, VT_BF16, 2, w_hh_tc, dims, st, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)H, (uint64_t)T, (uint64_t)B};
+    const uint64_t st[2] = {(uint64_t)H * 2, (uint64_t)T * H * 2};
+    const uint32_t box[3] = {64u, 1u, 128u};
+    int rc = make_tmap(&a->tmH, VT_BF16, 3, h_tc, dims, st, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)4 * H, (uint64_t)T, (uint64_t)B};
+    const uint64_t st[2] = {(uint64_t)4 * H * 4, (uint64_t)T * 4 * H * 4};
+    const uint32_t box[3] = {32u, 1u, 128u};
+    int rc = make_tmap(&a->tmX, VT_F32, 3, xw, dims, st, box);
+    if (rc) return rc;
+  }
+  VT_REQUIRE(!y || (y_ld % 8 == 0 && aligned16(y)), "lstm (tensor-core path): y rows must be 16-byte aligned");
+  a->hbuf = reinterpret_cast<__nv_bfloat16*>(h_tc);
+  a->y = y; a->y_dtype = y_dtype == VT_BF16 ? 0 : 1; a->y_ld = y_ld;
+  a->gates = gates; a->c_all = c_all; a->h_out = h_out; a->c_out = c_out;
+  a->B = B; a->T = T;
+  return VT_OK;
+}
+int launch_lstm_tc(const vt::LstmTcArgs& a, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VT_CUDA(cudaFuncSetAttribute(vt::lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vt::LTC_FWD_SMEM));
+    attr_set = true;
+  }
+  const unsigned grid = (unsigned)((a.B + vt::LTC_ROWS - 1) / vt::LTC_ROWS) * vt::LTC_CLUSTER;
+  vt::lstm_tc_kernel<<<grid, vt::LTC_THREADS, vt::LTC_FWD_SMEM, s>>>(a);
+  VT_LAUNCH_CHECK("lstm_tc_kernel");
+  return VT_OK;
+}
+
 struct LstmOp : Op {
   vt_lstm_desc d;
+  vt::LstmTcArgs tc;
+  bool use_tc = false;
   int launch(cudaStream_t s) override {
+    if (use_tc) return launch_lstm_tc(tc, s);
     const int blocks = (d.B + vt::LSTM_ROWS - 1) / vt::LSTM_ROWS;
     if (d.H == 256)
       vt::lstm_seq_kernel<256><<<blocks, 256, 0, s>>>(d.xw, d.w_hh, d.h, d.c, d.y, d.y_dtype, d.y_ld, d.y_plane, d.B, d.T);
@@ -719,7 +769,10 @@ struct LnGeluBwdOp : Op {
 
 struct LstmTrainOp : Op {
   vt_lstm_train_desc d;
+  vt::LstmTcArgs tc;
+  bool use_tc = false;
   int launch(cudaStream_t s) override {
+    if (use_tc) return launch_lstm_tc(tc, s);
     const int blocks = (d.B + vt::LSTM_ROWS - 1) / vt::LSTM_ROWS;
     vt::lstm_seq_train_kernel<256><<<blocks, 256, 0, s>>>(d.xw, d.w_hh, d.y, d.y_dtype, d.y_ld, d.gates, d.c, d.B, d.T);
     VT_LAUNCH_CHECK("lstm_seq_train_kernel");
@@ -729,7 +782,20 @@ struct LstmTrainOp : Op {
 
 struct LstmBwdOp : Op {
   vt_lstm_bwd_desc d;
+  vt::LstmBwdTcArgs tc;
+  bool use_tc = false;
   int launch(cudaStream_t s) override {
+    if (use_tc) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        VT_CUDA(cudaFuncSetAttribute(vt::lstm_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vt::LTC_BWD_SMEM));
+        attr_set = true;
+      }
+      const unsigned grid = (unsigned)((d.B + vt::LTC_ROWS - 1) / vt::LTC_ROWS) * vt::LTC_CLUSTER;
+      vt::lstm_bwd_tc_kernel<<<grid, vt::LTC_THREADS, vt::LTC_BWD_SMEM, s>>>(tc);
+      VT_LAUNCH_CHECK("lstm_bwd_tc_kernel");
+      return VT_OK;
+    }
     const int blocks = (d.B + vt::LSTM_ROWS - 1) / vt::LSTM_ROWS;
     vt::lstm_bwd_kernel<256><<<blocks, 256, 0, s>>>(d.gates, d.c, d.dy, d.dy_ld, d.w_hh, d.dgates, d.B, d.T);
     VT_LAUNCH_CHECK("lstm_bwd_kernel");
@@ -1124,8 +1190,19 @@ VT_SIMPLE_ADD(vt_program_add_tembed, TembedOp, vt_tembed_desc,
               VT_REQUIRE(d->t && d->out && d->rows >= 1 && d->dim >= 4 && d->dim % 2 == 0, "tembed: bad descriptor"))
 VT_SIMPLE_ADD(vt_program_add_sde, SdeOp, vt_sde_desc,
               VT_REQUIRE(d->x && d->v && d->s && d->rows >= 1 && d->A >= 1, "sde: bad descriptor"))
-VT_SIMPLE_ADD(vt_program_add_lstm, LstmOp, vt_lstm_desc,
-              VT_REQUIRE(d->xw && d->w_hh && d->h && d->c && d->y && d->B >= 1 && d->T >= 1 && d->H == 256, "lstm: bad descriptor"))
+int vt_program_add_lstm(vt_program* p, const vt_lstm_desc* d) {
+  if (!p || !d) return fail(VT_E_INVALID, "null argument");
+  VT_REQUIRE(d->xw && d->w_hh && d->h && d->c && d->y && d->B >= 1 && d->T >= 1 && d->H == 256, "lstm: bad descriptor");
+  std::unique_ptr<LstmOp> op(new LstmOp());
+  op->d = *d;
+  if (d->w_hh_tc && d->h_tc && d->zero_init && d->B >= LSTM_TC_MIN_BATCH && d->y_plane == 0) {
+    int rc = build_lstm_tc(&op->tc, d->w_hh_tc, d->h_tc, d->xw, d->y, d->y_dtype, d->y_ld, nullptr, nullptr, d->h, d->c, d->B, d->T);
+    if (rc) return rc;
+    op->use_tc = true;
+  }
+  p->ops.push_back(std::move(op));
+  return VT_OK;
+}
 
 VT_SIMPLE_ADD(vt_program_add_tcol, TcolOp, vt_tcol_desc,
               VT_REQUIRE(d->src && d->out && (d->src_dtype == VT_BF16 || d->src_dtype == VT_F32) && d->G >= 1 && d->B >= 1 &&
@@ -1156,12 +1233,52 @@ VT_SIMPLE_ADD(vt_program_add_dropmask, DropmaskOp, vt_dropmask_desc,
 VT_SIMPLE_ADD(vt_program_add_lngelubwd, LnGeluBwdOp, vt_lngelubwd_desc,
               VT_REQUIRE(d->z0 && d->dzn && d->gamma && d->beta && d->dz0 && d->d1 && d->d1zh && d->rows >= 1 && d->D == 256,
                          "lngelubwd: bad descriptor (D=%d)", d->D))
-VT_SIMPLE_ADD(vt_program_add_lstm_train, LstmTrainOp, vt_lstm_train_desc,
-              VT_REQUIRE(d->xw && d->w_hh && d->y && d->gates && d->c && d->B >= 1 && d->T >= 1 && d->H == 256 &&
-                             (d->y_dtype == VT_BF16 || d->y_dtype == VT_F32) && d->y_ld >= d->H, "lstm_train: bad descriptor"))
-VT_SIMPLE_ADD(vt_program_add_lstm_bwd, LstmBwdOp, vt_lstm_bwd_desc,
-              VT_REQUIRE(d->gates && d->c && d->dy && d->w_hh && d->dgates && d->B >= 1 && d->T >= 1 && d->H == 256 &&
-                             d->dy_ld >= d->H, "lstm_bwd: bad descriptor"))
+int vt_program_add_lstm_train(vt_program* p, const vt_lstm_train_desc* d) {
+  if (!p || !d) return fail(VT_E_INVALID, "null argument");
+  VT_REQUIRE(d->xw && d->w_hh && d->y && d->gates && d->c && d->B >= 1 && d->T >= 1 && d->H == 256 &&
+                 (d->y_dtype == VT_BF16 || d->y_dtype == VT_F32) && d->y_ld >= d->H, "lstm_train: bad descriptor");
+  std::unique_ptr<LstmTrainOp> op(new LstmTrainOp());
+  op->d = *d;
+  if (d->w_hh_tc && d->h_tc && d->B >= LSTM_TC_MIN_BATCH) {
+    int rc = build_lstm_tc(&op->tc, d->w_hh_tc, d->h_tc, d->xw, d->y, d->y_dtype, d->y_ld, d->gates, d->c, nullptr, nullptr, d->B, d->T);
+    if (rc) return rc;
+    op->use_tc = true;
+  }
+  p->ops.push_back(std::move(op));
+  return VT_OK;
+}
+int vt_program_add_lstm_bwd(vt_program* p, const vt_lstm_bwd_desc* d) {
+  if (!p || !d) return fail(VT_E_INVALID, "null argument");
+  VT_REQUIRE(d->gates && d->c && d->dy && d->w_hh && d->dgates && d->B >= 1 && d->T >= 1 && d->H == 256 && d->dy_ld >= d->H,
+             "lstm_bwd: bad descriptor");
+  std::unique_ptr<LstmBwdOp> op(new LstmBwdOp());
+  op->d = *d;
+  if (d->w_hh_t_tc && d->dg_tc && d->B >= LSTM_TC_MIN_BATCH && d->dy_ld % 4 == 0 && aligned16(d->dy)) {
+    const int H = vt::LTC_H;
+    vt::LstmBwdTcArgs& a = op->tc;
+    memset(&a, 0, sizeof(a));
+    {
+      const uint64_t dims[2] = {(uint64_t)4 * H, (uint64_t)H};
+      const uint64_t st[1] = {(uint64_t)4 * H * 2};
+      const uint32_t box[2] = {64u, (uint32_t)vt::LTC_U};
+      int rc = make_tmap(&a.tmW, VT_BF16, 2, d->w_hh_t_tc, dims, st, box);
+      if (rc) return rc;
+    }
+    {
+      const uint64_t dims[3] = {(uint64_t)4 * H, (uint64_t)d->T, (uint64_t)d->B};
+      const uint64_t st[2] = {(uint64_t)4 * H * 2, (uint64_t)d->T * 4 * H * 2};
+      const uint32_t box[3] = {64u, 1u, 128u};
+      int rc = make_tmap(&a.tmD, VT_BF16, 3, d->dg_tc, dims, st, box);
+      if (rc) return rc;
+    }
+    a.gates = d->gates; a.c_all = d->c; a.dy = d->dy; a.dy_ld = d->dy_ld; a.dgates = d->dgates;
+    a.dgb = reinterpret_cast<__nv_bfloat16*>(d->dg_tc);
+    a.B = d->B; a.T = d->T;
+    op->use_tc = true;
+  }
+  p->ops.push_back(std::move(op));
+  return VT_OK;
+}
 
 VT_SIMPLE_ADD(vt_program_add_qsample, QsampleOp, vt_qsample_desc,
               VT_REQUIRE(d->x0 && d->x1 && d->step && d->z_unit && d->xt && d->tclip && d->B >= 1 && d->n >= 1 && d->A >= 1 &&

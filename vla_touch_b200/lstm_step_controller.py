@@ -6,6 +6,7 @@ recurrence itself is one launch per layer of the LSTM_SEQ kernel (csrc/vt_lstm.c
 T=1 launch per control tick with the (h, c) state kept on the device (`predict`, :232-286)."""
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -45,7 +46,7 @@ class LstmEngine:
         lstm = mods["lstm"]
         kin = H // 2 + A
         self.kin_pad = round_up(kin, 64)
-        self.w_ih, self.b_sum, self.w_hh_t = [], [], []
+        self.w_ih, self.b_sum, self.w_hh_t, self.w_hh_tc = [], [], [], []
         for l in range(L):
             w = lstm[f"weight_ih_l{l}"].detach().to(dev, f32)
             kp = self.kin_pad if l == 0 else H
@@ -54,6 +55,9 @@ class LstmEngine:
             self.w_ih.append(p.reg(m.pack_w(wp)))
             self.b_sum.append(p.reg((lstm[f"bias_ih_l{l}"] + lstm[f"bias_hh_l{l}"]).detach().to(dev, f32).contiguous()))
             self.w_hh_t.append(p.reg(lstm[f"weight_hh_l{l}"].detach().to(dev, f32).t().contiguous()))
+            # tensor-core recurrence (csrc/vt_lstm_tc.cuh): W_hh rows regrouped per hidden unit (row = unit * 4 + gate), bf16
+            self.w_hh_tc.append(None if precise else p.reg(
+                lstm[f"weight_hh_l{l}"].detach().to(dev, f32).view(4, H, H).permute(1, 0, 2).reshape(4 * H, H).to(torch.bfloat16).contiguous()))
         head = mods["output_head"]
         self.head0 = MlpWeights({"0.weight": head["0.weight"], "0.bias": head["0.bias"]}, dev, m, idx=(0,))
         self.head0.register(p)
@@ -84,6 +88,8 @@ class LstmEngine:
             d.xw, d.w_hh, d.h, d.c = ptr(xw), ptr(self.w_hh_t[l]), ptr(self.h, l * B * H), ptr(self.c, l * B * H)
             d.y, d.y_dtype, d.y_ld, d.B, d.T, d.H = ptr(y), m.dt, m.ld(yk), B, T, H
             d.y_plane = m.plane(yk)
+            if not precise and T > 1 and os.environ.get("VT_LSTM_TC", "1") != "0":        # whole-sequence passes start from a zero state (forward / predict_sequence, :196-204, 288-319)
+                d.w_hh_tc, d.h_tc, d.zero_init = ptr(self.w_hh_tc[l]), ptr(p.buf(f"h_tc{l}", (B, T, H), torch.bfloat16)), 1
             p.add(d, f"lstm.l{l}.recurrence")
             y_prev, y_ld, y_k = y, m.ld(yk), yk
         d = _pack_desc(self.cond, H, R, H, head_in, 0, m, 2 * H, H)

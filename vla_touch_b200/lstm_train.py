@@ -20,6 +20,7 @@ checked on the CPU descriptor interpreter only.  TactileLSTMController.get_loss(
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Sequence
 
 import torch
@@ -47,7 +48,8 @@ class LstmLayerTrain:
         self.plan, self.x, self.k_in, self.k_pad, self.B, self.T, self.tag = plan, x, k_in, x.shape[-1], B, T, tag
         packed = self._pack_weights(w_ih, w_hh, b_ih, b_hh)
         # forward operand [4H][k_pad], d x operand [k_pad][4H], b_ih + b_hh, W_hh [4H][H] (backward) and W_hh^T [H][4H] (forward)
-        self.w_ih, self.w_ih_t, self.b_sum, self.w_hh, self.w_hh_t = (plan.reg(t) for t in packed)
+        self.w_ih, self.w_ih_t, self.b_sum, self.w_hh, self.w_hh_t, self.w_hh_tc, self.w_hh_t_tc = (plan.reg(t) for t in packed)
+        self.h_tc = plan.buf(f"{tag}.h_tc", (B, T, H), bf)                 # tensor-core recurrence: its bf16 copy of h (vt_lstm_tc.cuh)
         R = B * T
         self.xw = plan.buf(f"{tag}.xw", (R, 4 * H), f32)
         # hidden outputs: bf16 (the next GEMM's operand; may be the first H columns of a wider buffer) or fp32 (when dropout follows)
@@ -64,11 +66,14 @@ class LstmLayerTrain:
         wp[:, : self.k_in] = w_ih.detach().to(dev, f32)
         whh = w_hh.detach().to(dev, f32)
         return (wp.to(bf).contiguous(), wp.t().contiguous().to(bf), (b_ih + b_hh).detach().to(dev, f32).contiguous(),
-                whh.contiguous(), whh.t().contiguous())
+                whh.contiguous(), whh.t().contiguous(),
+                whh.view(4, H, H).permute(1, 0, 2).reshape(4 * H, H).to(bf).contiguous(),      # rows regrouped per unit: unit * 4 + gate
+                whh.t().contiguous().to(bf))                                                    # W_hh^T [H][4H]
 
     def refresh(self, w_ih, w_hh, b_ih, b_hh) -> None:
         """New parameter values -> the same device tensors (after an optimizer step)."""
-        for dst, src in zip((self.w_ih, self.w_ih_t, self.b_sum, self.w_hh, self.w_hh_t), self._pack_weights(w_ih, w_hh, b_ih, b_hh)):
+        for dst, src in zip((self.w_ih, self.w_ih_t, self.b_sum, self.w_hh, self.w_hh_t, self.w_hh_tc, self.w_hh_t_tc),
+                            self._pack_weights(w_ih, w_hh, b_ih, b_hh)):
             dst.copy_(src)
 
     def forward(self) -> torch.Tensor:
@@ -79,6 +84,8 @@ class LstmLayerTrain:
         d.xw, d.w_hh, d.y, d.y_ld = ptr(self.xw), ptr(self.w_hh_t), ptr(self.y), self.y_ld
         d.y_dtype = nv.VT_BF16 if self.y.dtype == torch.bfloat16 else nv.VT_F32
         d.gates, d.c, d.B, d.T, d.H = ptr(self.gates), ptr(self.c), self.B, self.T, H
+        if os.environ.get("VT_LSTM_TC", "1") != "0":
+            d.w_hh_tc, d.h_tc = ptr(self.w_hh_tc), ptr(self.h_tc)
         p.add(d, f"{self.tag}.recurrence(train)")
         return self.y
 
@@ -90,6 +97,8 @@ class LstmLayerTrain:
         d = nv.LstmBwdDesc()
         d.gates, d.c, d.dy, d.dy_ld, d.w_hh, d.dgates = ptr(self.gates), ptr(self.c), ptr(dy), dy.shape[-1], ptr(self.w_hh), ptr(dg)
         d.B, d.T, d.H = B, T, H
+        if os.environ.get("VT_LSTM_TC", "1") != "0":
+            d.w_hh_t_tc, d.dg_tc = ptr(self.w_hh_t_tc), ptr(p.buf(f"{tag}.dgates_bf16", (B, T, 4 * H), torch.bfloat16))
         p.add(d, f"{tag}.bptt")
         ctx = ub.DgradCtx(1, precise=False)
         V = _View

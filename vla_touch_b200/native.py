@@ -92,7 +92,7 @@ class SdeDesc(C.Structure):
 
 class LstmDesc(C.Structure):
     _fields_ = [("xw", vp), ("w_hh", vp), ("h", vp), ("c", vp), ("y", vp), ("y_dtype", i32), ("y_ld", i64),
-                ("y_plane", i64), ("B", i32), ("T", i32), ("H", i32)]
+                ("y_plane", i64), ("B", i32), ("T", i32), ("H", i32), ("w_hh_tc", vp), ("h_tc", vp), ("zero_init", i32)]
 
 
 class QsampleDesc(C.Structure):
@@ -142,12 +142,12 @@ class SilossBwdDesc(C.Structure):
 
 class LstmTrainDesc(C.Structure):
     _fields_ = [("xw", vp), ("w_hh", vp), ("y", vp), ("y_dtype", i32), ("y_ld", i64), ("gates", vp), ("c", vp), ("B", i32),
-                ("T", i32), ("H", i32)]
+                ("T", i32), ("H", i32), ("w_hh_tc", vp), ("h_tc", vp)]
 
 
 class LstmBwdDesc(C.Structure):
     _fields_ = [("gates", vp), ("c", vp), ("dy", vp), ("dy_ld", i64), ("w_hh", vp), ("dgates", vp), ("B", i32), ("T", i32),
-                ("H", i32)]
+                ("H", i32), ("w_hh_t_tc", vp), ("dg_tc", vp)]
 
 
 class DropmaskDesc(C.Structure):
