@@ -1,5 +1,6 @@
 """Developer tool (GPU box): replay selected ops of the predict program once each inside a cudaProfiler range, for
-   ncu --profile-from-start off --set full ... python tools/ncu_ops.py <op index> [<op index> ...]"""
+   ncu --profile-from-start off --set full ... python tools/ncu_ops.py <op index | tag substring> [...]
+   `step` replays the whole predict program once (eager, op by op) instead: the launch list of one step."""
 import os
 import sys
 
@@ -35,9 +36,15 @@ def make(workload="cfg2", batch=None):
 
 
 if __name__ == "__main__":
-    ops = [int(x) for x in sys.argv[1:]]
     ctl, eng = make()
     prog = eng.plan.compile()
+    if sys.argv[1:] == ["step"]:
+        a0, b1 = eng.predict_range()
+        ops = list(range(a0, b1))
+    else:
+        ops = []
+        for x in sys.argv[1:]:
+            ops.append(int(x) if x.isdigit() else next(i for i, t in enumerate(eng.plan.tags) if x in t))
     for i in ops:
         prog.run(i, 1)
     torch.cuda.synchronize()
