@@ -802,6 +802,52 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
   }
 }
 
+// FiLM scale / shift of every sample of a GroupNorm tile (per-sample cond part + per-step time part) -> shared memory
+// [samples][2][BN].  128-bit loads; every thread first issues ALL its global loads (up to 2 x 4 float4), then adds and stores: a
+// plain load / store loop lets the compiler assume the shared-memory stores alias the following loads, which serialises one L2
+// round trip per element (measured: the top stall reason of the epilogue warps, 16 dependent round trips per tile).
+template <int BN>
+__device__ __forceinline__ void stage_film(const GemmArgs& a, float* films, const float* ft, int g, int n0, int m_tile, int nsamp,
+                                           int tid, int nthreads) {
+  const long long smp0 = (long long)m_tile * nsamp;
+  const long long n_samples = a.M_total / a.gn_rows;
+  const float* fc = a.film_c + (long long)g * a.film_g + a.film_off + n0;
+  const int n4 = nsamp * 2 * BN / 4;
+  constexpr int MAXV = GEMM_FILM_SAMPLES * 2 * BN / 4 / 256;   // float4 pieces per thread with 256 staging threads
+  float4 vc[MAXV], vt[MAXV];
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int i = (tid + k * nthreads) * 4;
+    vc[k] = vt[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid + k * nthreads < n4) {
+      const int c = i % BN, which = (i / BN) & 1, smp = i / (2 * BN);
+      if (smp0 + smp < n_samples) {
+        vc[k] = __ldg(reinterpret_cast<const float4*>(fc + (smp0 + smp) * a.film_ld + which * a.film_C + c));
+        if (ft) vt[k] = __ldg(reinterpret_cast<const float4*>(ft + which * a.film_C + c));
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int i4 = tid + k * nthreads;
+    if (i4 < n4)
+      *reinterpret_cast<float4*>(films + i4 * 4) = make_float4(vc[k].x + vt[k].x, vc[k].y + vt[k].y, vc[k].z + vt[k].z, vc[k].w + vt[k].w);
+  }
+  for (int i4 = tid + MAXV * nthreads; i4 < n4; i4 += nthreads) {   // (fewer than 256 staging threads)
+    const int i = i4 * 4;
+    const int c = i % BN, which = (i / BN) & 1, smp = i / (2 * BN);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (smp0 + smp < n_samples) {
+      v = __ldg(reinterpret_cast<const float4*>(fc + (smp0 + smp) * a.film_ld + which * a.film_C + c));
+      if (ft) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(ft + which * a.film_C + c));
+        v = make_float4(v.x + w.x, v.y + w.y, v.z + w.z, v.w + w.w);
+      }
+    }
+    *reinterpret_cast<float4*>(films + i4 * 4) = v;
+  }
+}
+
 template <typename TIn, int BN, int MODE, typename TOut, int STAGES, bool PRECISE, int KA, int CTAS, int EW>
 __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __grid_constant__ GemmArgs a) {
   static_assert(EW == 8 || (EW == 12 && MODE == EPI_LINEAR), "epilogue warps: 8, or 12 for the LINEAR epilogue");
@@ -1042,18 +1088,25 @@ __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __gr
         // barrier of the tile in between, so only the write -> read edge needs a barrier.  GroupNorm (one set): all
         // readers of the previous tile must be done first.
         if (MODE == EPI_GN) named_bar_sync(1, 32 * EW);
+        // (all global loads of a thread are issued before its first shared-memory store, see stage_film)
         const long long gcol = (long long)t.g * a.n_pad + t.n0;
         for (int c = et256; c < BN; c += 32 * EW) {
-          colv[c] = a.bias ? a.bias[gcol + c] : 0.f;
           if (MODE == EPI_LINEAR) {
-            colv[BN + c] = (a.colscale && (t.n0 + c) < a.N) ? a.colscale[t.n0 + c] : 1.f;
+            const float b_ = a.bias ? __ldg(a.bias + gcol + c) : 0.f;
+            const float s_ = (a.colscale && (t.n0 + c) < a.N) ? __ldg(a.colscale + t.n0 + c) : 1.f;
+            colv[c] = b_;
+            colv[BN + c] = s_;
           } else {
-            colv[BN + c] = a.gn_gamma[gcol + c];
-            colv[2 * BN + c] = a.gn_beta[gcol + c];
             const bool f = a.film_t != nullptr;
             const long long fo = (long long)t.g * a.film_tg + a.film_off + t.n0 + c;
-            colv[3 * BN + c] = f ? a.film_t[fo] : 0.f;
-            colv[4 * BN + c] = f ? a.film_t[fo + a.film_C] : 0.f;
+            const float b_ = a.bias ? __ldg(a.bias + gcol + c) : 0.f;
+            const float g_ = __ldg(a.gn_gamma + gcol + c), e_ = __ldg(a.gn_beta + gcol + c);
+            const float f0 = f ? __ldg(a.film_t + fo) : 0.f, f1 = f ? __ldg(a.film_t + fo + a.film_C) : 0.f;
+            colv[c] = b_;
+            colv[BN + c] = g_;
+            colv[2 * BN + c] = e_;
+            colv[3 * BN + c] = f0;
+            colv[4 * BN + c] = f1;
           }
         }
         if constexpr (GN_FAST) {
@@ -1061,19 +1114,8 @@ __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __gr
           const int nsamp = a.rows_valid / a.gn_rows;
           if (a.film_c && nsamp <= GEMM_FILM_SAMPLES) {
             film_staged = true;
-            const long long smp0 = (long long)m_tile * nsamp;
-            const long long n_samples = a.M_total / a.gn_rows;
-            const float* fc = a.film_c + (long long)t.g * a.film_g + a.film_off + t.n0;
-            const float* ft = a.film_t ? a.film_t + (long long)t.g * a.film_tg + a.film_off + t.n0 : nullptr;
-            for (int i = et256; i < nsamp * 2 * BN; i += 32 * EW) {
-              const int c = i % BN, which = (i / BN) & 1, smp = i / (2 * BN);
-              float v = 0.f;
-              if (smp0 + smp < n_samples) {
-                v = fc[(smp0 + smp) * a.film_ld + which * a.film_C + c];
-                if (ft) v += ft[which * a.film_C + c];
-              }
-              films[i] = v;
-            }
+            stage_film<BN>(a, films, a.film_t ? a.film_t + (long long)t.g * a.film_tg + a.film_off + t.n0 : nullptr, t.g, t.n0, m_tile, nsamp,
+                           et256, 32 * EW);
           }
         }
         named_bar_sync(1, 32 * EW);

@@ -390,8 +390,9 @@ int fill_gemm_args(const vt_gemm_desc& d, int ctas, vt::GemmArgs* out) {
     VT_REQUIRE(d.row_div == d.t_box, "gemm: GroupNorm epilogue needs row_div == t_box");
     VT_REQUIRE(vec, "gemm: GroupNorm epilogue needs 16-byte aligned rows");
     VT_REQUIRE(d.b_box <= 32, "gemm: GroupNorm epilogue supports at most 32 samples per tile");
-    if (d.film_c) VT_REQUIRE(d.film_ld % 4 == 0 && d.film_off % 4 == 0 && d.film_C % 4 == 0 && d.film_g % 4 == 0 && aligned16(d.film_c),
-                             "gemm: FiLM table must be 16-byte aligned");
+    if (d.film_c) VT_REQUIRE(d.film_ld % 4 == 0 && d.film_off % 4 == 0 && d.film_C % 4 == 0 && d.film_g % 4 == 0 && aligned16(d.film_c) &&
+                                 (!d.film_t || (aligned16(d.film_t) && d.film_tg % 4 == 0)),
+                             "gemm: FiLM tables must be 16-byte aligned");
     a.gn_gamma = d.gn_gamma;
     a.gn_beta = d.gn_beta;
     a.gn_gs_log2 = d.gn_group_ch == 32 ? 5 : 6;
@@ -869,6 +870,7 @@ int build_persist(const vt_persist_desc& d, PersistOp* op) {
       L.spu = 2 * g.b_box;
       L.n_tiles_total = L.g.total_tiles;
       L.film_t_step = g.film_t ? d.film_t_step : 0;
+      VT_REQUIRE(L.film_t_step % 4 == 0, "persist: film_t_step must be a multiple of 4 elements");
       for (int sb = 0; sb < n_sb; ++sb) {
         int units = 0;
         for (int u = 0; u < L.g.m_tiles; ++u) {

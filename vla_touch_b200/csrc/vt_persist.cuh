@@ -368,37 +368,36 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) unet_persist_kernel(const 
           float* colv = scratch + (L.mode == EPI_LINEAR ? (int)acc * 2 * L.bn : 0);
           bool film_staged = false;
           if (!fast_lin) {
+            // Per-column vectors and the per-sample FiLM table of this tile -> shared memory.  All global loads of a thread are
+            // issued before its first shared-memory store: written as a plain load / store loop the compiler must assume that the
+            // stores alias the next loads and serialises one L2 round trip per element (ncu: the top stall of the epilogue warps).
             const long long gcol = (long long)t.g * a.n_pad + t.n0;
-            for (int c = et256; c < L.bn; c += 256) {
-              colv[c] = a.bias ? a.bias[gcol + c] : 0.f;
+            if (et256 < L.bn) {
+              const int c = et256;
               if (L.mode == EPI_LINEAR) {
-                colv[L.bn + c] = (a.colscale && (t.n0 + c) < a.N) ? a.colscale[t.n0 + c] : 1.f;
+                const float b_ = a.bias ? __ldg(a.bias + gcol + c) : 0.f;
+                const float s_ = (a.colscale && (t.n0 + c) < a.N) ? __ldg(a.colscale + t.n0 + c) : 1.f;
+                colv[c] = b_;
+                colv[L.bn + c] = s_;
               } else {
-                colv[BN + c] = a.gn_gamma[gcol + c];
-                colv[2 * BN + c] = a.gn_beta[gcol + c];
                 const bool f = a.film_t != nullptr;
                 const long long fo = (long long)t.g * a.film_tg + (long long)step * L.film_t_step + a.film_off + t.n0 + c;
-                colv[3 * BN + c] = f ? a.film_t[fo] : 0.f;
-                colv[4 * BN + c] = f ? a.film_t[fo + a.film_C] : 0.f;
+                const float b_ = a.bias ? __ldg(a.bias + gcol + c) : 0.f;
+                const float g_ = __ldg(a.gn_gamma + gcol + c), e_ = __ldg(a.gn_beta + gcol + c);
+                const float f0 = f ? __ldg(a.film_t + fo) : 0.f, f1 = f ? __ldg(a.film_t + fo + a.film_C) : 0.f;
+                colv[c] = b_;
+                colv[BN + c] = g_;
+                colv[2 * BN + c] = e_;
+                colv[3 * BN + c] = f0;
+                colv[4 * BN + c] = f1;
               }
             }
             if (L.mode == EPI_GN) {
               const int nsamp = a.rows_valid / a.gn_rows;
               if (a.film_c && nsamp <= GEMM_FILM_SAMPLES && a.out_plane == 0 && a.res_plane == 0) {
                 film_staged = true;
-                const long long smp0 = (long long)m_tile * nsamp;
-                const long long n_samples = a.M_total / a.gn_rows;
-                const float* fc = a.film_c + (long long)t.g * a.film_g + a.film_off + t.n0;
-                const float* ft = a.film_t ? a.film_t + (long long)t.g * a.film_tg + (long long)step * L.film_t_step + a.film_off + t.n0 : nullptr;
-                for (int i = et256; i < nsamp * 2 * BN; i += 256) {
-                  const int c = i % BN, which = (i / BN) & 1, smp = i / (2 * BN);
-                  float v = 0.f;
-                  if (smp0 + smp < n_samples) {
-                    v = fc[(smp0 + smp) * a.film_ld + which * a.film_C + c];
-                    if (ft) v += ft[which * a.film_C + c];
-                  }
-                  films[i] = v;
-                }
+                stage_film<BN>(a, films, a.film_t ? a.film_t + (long long)t.g * a.film_tg + (long long)step * L.film_t_step + a.film_off + t.n0 : nullptr,
+                               t.g, t.n0, m_tile, nsamp, et256, 256);
               }
             }
             named_bar_sync(1, 256);
