@@ -262,6 +262,13 @@ def predict_harness(cx, wl, batch):
     api_step()                      # builds the engine, the FiLM time tables and the CUDA graph
     torch.cuda.synchronize()
     eng = next(iter(ctl._engines.values()))
+    keys = ("state", "forces", "vla_actions", "images_cam1", "images_cam2")
+    land = {k: torch.empty_like(host[k], device=cx.dev) for k in keys}
+
+    def h2d_only():                 # the step's host->device traffic alone (what the e2e number adds on top of `value`)
+        for k in keys:
+            land[k].copy_(host[k], non_blocking=True)
+    api_step.h2d_only = h2d_only
     return ctl, eng, api_step, h2d, out_host.numel() * 4
 
 
@@ -273,7 +280,8 @@ def bench_predict(cx, wl, batch, steps, warmup):
     for _ in range(warmup):
         api_step()
     ms_e2e = cx.timed(api_step, steps)
-    return dict(ctl=ctl, eng=eng, ms=ms, ms_e2e=ms_e2e, h2d=h2d, d2h=d2h, launches=eng.num_launches())
+    ms_h2d = cx.timed(api_step.h2d_only, steps)
+    return dict(ctl=ctl, eng=eng, ms=ms, ms_e2e=ms_e2e, ms_h2d=ms_h2d, h2d=h2d, d2h=d2h, launches=eng.num_launches())
 
 
 def peaks():
@@ -604,7 +612,11 @@ def main():
                    "l2": "no flush: per-step working set (activations ~1.3 GB at batch 256) exceeds the 126 MB L2",
                    "weights": "seeded synthetic (no network)", "noise": "in-kernel Philox"},
         "e2e": {"value": e2e, "unit": "chunks/s", "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"],
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                # the upload alone, all ranks at once, max over ranks: with N GPUs behind shared host memory / PCIe switches this is
+                # what grows with N and what the e2e figure loses against `value` (the upload of call i+1 overlaps the kernels of
+                # call i only while it is shorter than the step)
+                "h2d_ms_alone": res["ms_h2d"] / args.steps, "h2d_gbs_per_gpu": res["h2d"] / (res["ms_h2d"] / args.steps * 1e-3) / 1e9},
         "gpu_launches": res["launches"] * args.steps, "launches_per_step": res["launches"],
         "clocks": sampler.summary(),
     }

@@ -301,6 +301,33 @@ typedef struct vt_tcol_desc {
   int64_t out_g;        /* elements between groups of out */
 } vt_tcol_desc;
 
+/* Weight gradient of a convolution / linear layer straight from the channels-last activations (no transposed operand copy):
+ *   out[g][r][tap * c_pad + c] = sum_{b < B, t < t_out} rows[g][b][t + rows_t (phase rows_p)][r] * cols[g][b][t + tap_t[tap] (phase tap_p[tap])][c]
+ * Both operands are bf16 [G][B][positions][ld] tensors whose positions are stored as (tq, phase) pairs like vt_gemm_desc's A operand
+ * (position = tq * P + phase; a stride-2 convolution reads one phase); positions outside [0, T) read as zero.  The contraction runs
+ * over positions with the operands in the tensor cores' MN-major form (csrc/vt_wgrad.cuh).  t_out must divide 64.
+ *   Conv1d(k, s, p):         rows = dY, cols = X  (tap k at position offset k - p, stride s)  ->  [C_out][k][C_in]
+ *   ConvTranspose1d(4,2,1):  rows = X,  cols = dY (tap k at offset k - 1, stride 2)           ->  [C_in][k][C_out] */
+typedef struct vt_wgrad_desc {
+  const void* rows;        /* first channel of the window */
+  int32_t rows_C;          /* channels visible from `rows` (reads beyond are zero) */
+  int32_t rows_P, rows_T;  /* phases, tq extent per sample */
+  int64_t rows_ld, rows_sB, rows_sG;
+  int32_t rows_p, rows_t;
+  const void* cols;
+  int32_t cols_C, cols_P, cols_T;
+  int64_t cols_ld, cols_sB, cols_sG;
+  int32_t taps;
+  int32_t tap_p[VT_MAX_TAPS];
+  int32_t tap_t[VT_MAX_TAPS];
+  int32_t c_pad;           /* columns per tap, multiple of 64 */
+  int32_t G, B, t_out;
+  int32_t R;               /* output rows (channels of `rows`) */
+  float* out;              /* fp32 [G][R][ldc] */
+  int32_t ldc;
+  int64_t out_g;
+} vt_wgrad_desc;
+
 /* GroupNorm + Mish (+ FiLM) backward from the raw conv output (bias included), per net g and sample b:
  *   xh = (raw - mean) * rstd over each (sample, group);  y = xh * gamma + beta;  m = mish(y)
  *   film != null (forward out = scale * m + shift):  dm = dout * scale,  dfilm[b][film_off + c] = sum_t dout * m,
@@ -541,6 +568,7 @@ int vt_program_add_lstm_bwd(vt_program* p, const vt_lstm_bwd_desc* d);
 int vt_program_add_lngelubwd(vt_program* p, const vt_lngelubwd_desc* d);
 int vt_program_add_dropmask(vt_program* p, const vt_dropmask_desc* d);
 int vt_program_add_persist(vt_program* p, const vt_persist_desc* d);
+int vt_program_add_wgrad(vt_program* p, const vt_wgrad_desc* d);
 
 /* Launch ops [first, first+count) in order on `stream` (count < 0: to the end). */
 int vt_program_run(vt_program* p, int first, int count, void* stream);

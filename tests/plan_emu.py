@@ -465,6 +465,34 @@ def emu_dropmask(plan, d: nv.DropmaskDesc):
     _flat(plan, d.mask, torch.float32)[: d.n] = torch.where(u >= p, 1.0 / (1.0 - p), torch.zeros(()))
 
 
+def emu_wgrad(plan, d: nv.WgradDesc):
+    """out[g][r][tap * c_pad + c] = sum_{b,t} rows[g][b][t + rows_t (phase rows_p)][r] * cols[g][b][t + tap_t (phase tap_p)][c]"""
+    bf = torch.bfloat16
+    rows, cols = _flat(plan, d.rows, bf), _flat(plan, d.cols, bf)
+    out = _flat(plan, d.out, torch.float32)
+    b = torch.arange(d.B)[:, None]
+    t = torch.arange(d.t_out)[None, :]
+
+    def gather(flat, g, sG, sB, ld, P, T, p, dt, c0, C, C_vis):
+        tq = t + dt
+        ok = (tq >= 0) & (tq < T)
+        base = g * sG + b * sB + (tq.clamp(0, T - 1) * P + p) * ld                     # [B, t_out]
+        ch = c0 + torch.arange(C)
+        vis = ch < C_vis
+        idx = base[:, :, None] + ch.clamp(max=C_vis - 1)[None, None, :]
+        v = flat[idx.reshape(-1)].reshape(d.B, d.t_out, C).float()
+        return v * (ok[:, :, None] & vis[None, None, :])
+
+    for g in range(d.G):
+        X = gather(rows, g, d.rows_sG, d.rows_sB, d.rows_ld, d.rows_P, d.rows_T, d.rows_p, d.rows_t, 0, d.R, d.rows_C).reshape(-1, d.R)
+        for tap in range(d.taps):
+            Y = gather(cols, g, d.cols_sG, d.cols_sB, d.cols_ld, d.cols_P, d.cols_T, d.tap_p[tap], d.tap_t[tap], 0, d.c_pad, d.cols_C).reshape(-1, d.c_pad)
+            blk = X.t() @ Y                                                            # [R, c_pad]
+            rr = torch.arange(d.R)[:, None]
+            cc = tap * d.c_pad + torch.arange(d.c_pad)[None, :]
+            out[(g * d.out_g + rr * d.ldc + cc).reshape(-1)] = blk.reshape(-1)
+
+
 def emu_persist(plan, d: nv.PersistDesc):
     """The persistent multi-layer launch = its layers in order, step by step (film_t / noise rows and the Euler-Maruyama scalars of
     the step substituted exactly as the kernel does)."""
@@ -484,7 +512,7 @@ def emu_persist(plan, d: nv.PersistDesc):
             emu_sde(plan, s)
 
 
-_EMU = {nv.PersistDesc: emu_persist, nv.QsampleDesc: emu_qsample, nv.SilossDesc: emu_siloss, nv.GemmDesc: emu_gemm, nv.LnDesc: emu_layernorm, nv.AttnDesc: emu_attention, nv.ImgStatsDesc: emu_imgstats,
+_EMU = {nv.WgradDesc: emu_wgrad, nv.PersistDesc: emu_persist, nv.QsampleDesc: emu_qsample, nv.SilossDesc: emu_siloss, nv.GemmDesc: emu_gemm, nv.LnDesc: emu_layernorm, nv.AttnDesc: emu_attention, nv.ImgStatsDesc: emu_imgstats,
         nv.PatchifyDesc: emu_patchify, nv.ClsDesc: emu_cls, nv.PackDesc: emu_pack, nv.AffineDesc: emu_affine,
         nv.TcolDesc: emu_tcol, nv.GnbwdDesc: emu_gnbwd, nv.ColsumDesc: emu_colsum, nv.EwiseDesc: emu_ewise, nv.SilossBwdDesc: emu_silossbwd, nv.LstmTrainDesc: emu_lstm_train, nv.LstmBwdDesc: emu_lstm_bwd, nv.LnGeluBwdDesc: emu_lngelubwd, nv.DropmaskDesc: emu_dropmask, nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm, nv.MlpDesc: emu_mlp}
 

@@ -281,6 +281,33 @@ __global__ void __cluster_dims__(1, 1, COLSUM_SPLIT) __launch_bounds__(256)
   cluster_sync_all();   // the partials must stay readable until rank 0 is done
 }
 
+// The same reduction for FEW rows and many columns (the split-K partial sums of a weight gradient: rows = slices, C = the whole
+// gradient): one thread per 4 columns, rows summed in order (deterministic), 128-bit accesses.
+__global__ void __launch_bounds__(256) colsum_fewrows_kernel(const float* __restrict__ x, long long ld, long long x_g, int rows, long long C,
+                                                             float* __restrict__ out, long long out_ld) {
+  const int g = blockIdx.y;
+  const float* xg = x + (long long)g * x_g;
+  float* og = out + (long long)g * out_ld;
+  const bool vec = ((ld & 3) == 0) && ((C & 3) == 0) && ((reinterpret_cast<uintptr_t>(xg) & 15) == 0) && ((reinterpret_cast<uintptr_t>(og) & 15) == 0);
+  if (vec) {
+    const long long n4 = C >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      float4 s = *reinterpret_cast<const float4*>(xg + 4 * i);
+      for (int r = 1; r < rows; ++r) {
+        const float4 v = *reinterpret_cast<const float4*>(xg + (long long)r * ld + 4 * i);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      *reinterpret_cast<float4*>(og + 4 * i) = s;
+    }
+  } else {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < C; i += (long long)gridDim.x * blockDim.x) {
+      float s = 0.f;
+      for (int r = 0; r < rows; ++r) s += xg[(long long)r * ld + i];
+      og[i] = s;
+    }
+  }
+}
+
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * expf(-0.5f * x * x) * 0.3989422804014327f;
 }

@@ -16,6 +16,7 @@
 #include "vt_elem.cuh"
 #include "vt_gemm.cuh"
 #include "vt_persist.cuh"
+#include "vt_wgrad.cuh"
 #include "vt_lstm.cuh"
 #include "vt_lstm_tc.cuh"
 #include "vt_bwd.cuh"
@@ -662,6 +663,12 @@ struct GnbwdOp : Op {
 struct ColsumOp : Op {
   vt_colsum_desc d;
   int launch(cudaStream_t s) override {
+    if (d.rows <= 32 && d.C >= 4096) {   // few rows, many columns (split-K partial sums): elementwise over the columns
+      vt::colsum_fewrows_kernel<<<dim3((unsigned)grid_for((long long)d.C / 4, 256), (unsigned)d.G, 1), 256, 0, s>>>(d.x, d.ld, d.x_g, d.rows, d.C,
+                                                                                                                 d.out, d.out_ld);
+      VT_LAUNCH_CHECK("colsum_fewrows_kernel");
+      return VT_OK;
+    }
     vt::colsum_kernel<<<dim3((unsigned)((d.C + 31) / 32), (unsigned)d.G, vt::COLSUM_SPLIT), dim3(256, 1, 1), 0, s>>>(
         d.x, d.ld, d.x_g, d.rows, d.C, d.out, d.out_ld);
     VT_LAUNCH_CHECK("colsum_kernel");
@@ -803,6 +810,86 @@ struct LstmBwdOp : Op {
     return VT_OK;
   }
 };
+
+// ---- weight gradients with MN-major operands ----
+struct WgradOp : Op {
+  vt::WgradArgs args;
+  dim3 grid;
+  int launch(cudaStream_t s) override {
+    static bool attr_set = false;
+    if (!attr_set) {
+      VT_CUDA(cudaFuncSetAttribute(vt::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vt::WG_SMEM_BYTES));
+      attr_set = true;
+    }
+    cudaError_t e = launch_ex(vt::wgrad_tc_kernel, grid, dim3(vt::WG_THREADS, 1, 1), (size_t)vt::WG_SMEM_BYTES, s, true, true, args);
+    if (e != cudaSuccess) return fail(VT_E_CUDA, "wgrad_tc_kernel launch: %s", cudaGetErrorString(e));
+    VT_LAUNCH_CHECK("wgrad_tc_kernel");
+    return VT_OK;
+  }
+};
+
+int build_wgrad(const vt_wgrad_desc& d, WgradOp* op) {
+  VT_REQUIRE(d.rows && d.cols && d.out && d.G >= 1 && d.B >= 1 && d.R >= 1, "wgrad: bad descriptor");
+  VT_REQUIRE(d.t_out >= 1 && d.t_out <= 64 && 64 % d.t_out == 0, "wgrad: t_out=%d must divide 64", d.t_out);
+  VT_REQUIRE(d.taps >= 1 && d.taps <= VT_MAX_TAPS && d.c_pad >= 64 && d.c_pad % 64 == 0, "wgrad: taps=%d c_pad=%d", d.taps, d.c_pad);
+  VT_REQUIRE(d.rows_P >= 1 && d.cols_P >= 1 && d.rows_T >= 1 && d.cols_T >= 1 && d.rows_C >= 1 && d.cols_C >= 1, "wgrad: bad operand extents");
+  VT_REQUIRE(d.ldc >= d.taps * d.c_pad || d.ldc >= 1, "wgrad: ldc");
+  vt::WgradArgs& a = op->args;
+  memset(&a, 0, sizeof(a));
+  const uint32_t b_box = (uint32_t)(64 / d.t_out);
+  {
+    const uint64_t dims[5] = {(uint64_t)d.rows_C, (uint64_t)d.rows_P, (uint64_t)d.rows_T, (uint64_t)d.B, (uint64_t)d.G};
+    const uint64_t st[4] = {(uint64_t)d.rows_ld * 2, (uint64_t)d.rows_ld * d.rows_P * 2, (uint64_t)d.rows_sB * 2,
+                            (uint64_t)(d.G > 1 ? d.rows_sG : d.rows_sB * d.B) * 2};
+    const uint32_t box[5] = {64u, 1u, (uint32_t)d.t_out, b_box, 1u};
+    int rc = make_tmap(&a.tmR, VT_BF16, 5, d.rows, dims, st, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[5] = {(uint64_t)d.cols_C, (uint64_t)d.cols_P, (uint64_t)d.cols_T, (uint64_t)d.B, (uint64_t)d.G};
+    const uint64_t st[4] = {(uint64_t)d.cols_ld * 2, (uint64_t)d.cols_ld * d.cols_P * 2, (uint64_t)d.cols_sB * 2,
+                            (uint64_t)(d.G > 1 ? d.cols_sG : d.cols_sB * d.B) * 2};
+    const uint32_t box[5] = {64u, 1u, (uint32_t)d.t_out, b_box, 1u};
+    int rc = make_tmap(&a.tmC, VT_BF16, 5, d.cols, dims, st, box);
+    if (rc) return rc;
+  }
+  a.rows_p = d.rows_p;
+  a.rows_t = d.rows_t;
+  a.taps = d.taps;
+  a.c_pad = d.c_pad;
+  for (int i = 0; i < d.taps; ++i) {
+    VT_REQUIRE(d.tap_p[i] >= 0 && d.tap_p[i] < d.cols_P, "wgrad: tap %d phase %d", i, d.tap_p[i]);
+    a.tap_p[i] = d.tap_p[i];
+    a.tap_t[i] = d.tap_t[i];
+  }
+  VT_REQUIRE(d.rows_p >= 0 && d.rows_p < d.rows_P, "wgrad: rows phase %d", d.rows_p);
+  a.k_tiles = (d.B + (int)b_box - 1) / (int)b_box;
+  a.k_t_step = 0;
+  a.k_b_step = (int)b_box;
+  a.box_bytes = 64 * 128;
+  const int N = d.taps * d.c_pad;
+  a.m_units = (d.R + 255) / 256;
+  a.n_tiles = (N + 255) / 256;
+  const long long total = (long long)a.m_units * a.n_tiles * d.G;
+  VT_REQUIRE(total < (1ll << 31), "wgrad: too many tiles");
+  a.total_tiles = (int)total;
+  vt::GemmArgs& e = a.epi;
+  e.rows_valid = 128;
+  e.n_pad = a.n_tiles * 256;
+  e.M_total = d.R;
+  e.N = N;
+  e.row_div = 1;
+  e.out_q = 1;
+  e.out_g = d.out_g;
+  e.ldc = d.ldc;
+  e.out = d.out;
+  e.act = VT_ACT_NONE;
+  e.vec = (aligned16(d.out) && d.ldc % 4 == 0 && d.out_g % 4 == 0) ? 1 : 0;
+  e.fast = (e.vec && N % 256 == 0 && ((long long)d.R + 1) * d.ldc < (1ll << 31)) ? 1 : 0;
+  const int workers = sm_count() / 2;
+  op->grid = dim3((unsigned)(total < workers ? total : workers) * 2u, 1u, 1u);
+  return VT_OK;
+}
 
 // ---- persistent multi-layer launch ----
 struct PersistOp : Op {
@@ -1020,6 +1107,15 @@ int vt_program_add_persist(vt_program* p, const vt_persist_desc* d) {
   if (!p || !d) return fail(VT_E_INVALID, "null argument");
   std::unique_ptr<PersistOp> op(new PersistOp());
   int rc = build_persist(*d, op.get());
+  if (rc) return rc;
+  p->ops.push_back(std::move(op));
+  return VT_OK;
+}
+
+int vt_program_add_wgrad(vt_program* p, const vt_wgrad_desc* d) {
+  if (!p || !d) return fail(VT_E_INVALID, "null argument");
+  std::unique_ptr<WgradOp> op(new WgradOp());
+  int rc = build_wgrad(*d, op.get());
   if (rc) return rc;
   p->ops.push_back(std::move(op));
   return VT_OK;

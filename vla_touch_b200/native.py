@@ -111,6 +111,13 @@ class TcolDesc(C.Structure):
                 ("k_ld", i64), ("out_g", i64)]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [("rows", vp), ("rows_C", i32), ("rows_P", i32), ("rows_T", i32), ("rows_ld", i64), ("rows_sB", i64), ("rows_sG", i64),
+                ("rows_p", i32), ("rows_t", i32), ("cols", vp), ("cols_C", i32), ("cols_P", i32), ("cols_T", i32), ("cols_ld", i64),
+                ("cols_sB", i64), ("cols_sG", i64), ("taps", i32), ("tap_p", i32 * MAX_TAPS), ("tap_t", i32 * MAX_TAPS), ("c_pad", i32),
+                ("G", i32), ("B", i32), ("t_out", i32), ("R", i32), ("out", vp), ("ldc", i32), ("out_g", i64)]
+
+
 class GnbwdDesc(C.Structure):
     _fields_ = [("raw", vp), ("dout", vp), ("dout_ld", i64), ("dout_g", i64), ("gamma", vp), ("beta", vp), ("p_ld", i32),
                 ("film", vp), ("dfilm", vp), ("film_g", i64), ("film_ld", i32), ("film_off", i32), ("draw", vp), ("part", vp),
@@ -180,7 +187,7 @@ EXPORTS = [
     "vt_program_num_ops", "vt_program_num_launches", "vt_program_add_gemm", "vt_program_add_layernorm",
     "vt_program_add_attention", "vt_program_add_mlp", "vt_debug_timestamps", "vt_program_add_imgstats", "vt_program_add_patchify", "vt_program_add_cls",
     "vt_program_add_pack", "vt_program_add_affine", "vt_program_add_tembed", "vt_program_add_sde",
-    "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_add_tcol", "vt_program_add_gnbwd", "vt_program_add_colsum", "vt_program_add_ewise", "vt_program_add_silossbwd", "vt_program_add_lstm_train", "vt_program_add_lstm_bwd", "vt_program_add_lngelubwd", "vt_program_add_dropmask", "vt_program_add_persist", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
+    "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_add_tcol", "vt_program_add_gnbwd", "vt_program_add_colsum", "vt_program_add_ewise", "vt_program_add_silossbwd", "vt_program_add_lstm_train", "vt_program_add_lstm_bwd", "vt_program_add_lngelubwd", "vt_program_add_dropmask", "vt_program_add_persist", "vt_program_add_wgrad", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
     "vt_pos_embed_resize", "vt_adamw_ema_step",
 ]
 
@@ -193,6 +200,7 @@ _ADD = {
     ColsumDesc: "vt_program_add_colsum", EwiseDesc: "vt_program_add_ewise",
     SilossBwdDesc: "vt_program_add_silossbwd", LstmTrainDesc: "vt_program_add_lstm_train", LstmBwdDesc: "vt_program_add_lstm_bwd",
     LnGeluBwdDesc: "vt_program_add_lngelubwd", DropmaskDesc: "vt_program_add_dropmask", PersistDesc: "vt_program_add_persist",
+    WgradDesc: "vt_program_add_wgrad",
 }
 
 _lib: Optional[C.CDLL] = None

@@ -153,13 +153,47 @@ def conv_wgrad(plan, ctx: DgradCtx, B: int, rows_src: _View, cols_src: _View, *,
     gradients.  Needs B % S == 0 and per-net (not shared) operands; otherwise it silently stays at 1."""
     G = ctx.G
     assert not ctx.mode.precise, "training runs in the bf16 mode"
+    R, c_pad, taps = rows_src.C, cols_src.C, len(tap_off)
+    n = taps * c_pad
+    # MN-major path (csrc/vt_wgrad.cuh): both operands are read by TMA straight from the channels-last activations -- no
+    # transposed copies.  Needs bf16 per-net operands, 64-column tap blocks and a K tile of whole samples (t_out | 64).
+    direct = (os.environ.get("VT_WGRAD_DIRECT", "1") != "0" and rows_src.t.dtype == torch.bfloat16 and cols_src.t.dtype == torch.bfloat16
+              and not rows_src.shared and not cols_src.shared and 64 % t_out == 0 and c_pad % 64 == 0 and stride in (1, 2)
+              and (stride == 1 or cols_src.T % 2 == 0))
+    if direct:
+        S = split_k if split_k is not None else int(os.environ.get("VT_WGRAD_SPLITK", "0"))
+        if S <= 0:      # automatic: enough tiles for the 74 CTA pairs, at least 256 positions per slice
+            tiles = G * ((R + 255) // 256) * ((n + 255) // 256)
+            S = 1
+            while tiles * S < 64 and S < 16 and B % (2 * S) == 0 and (B // (2 * S)) * t_out >= 256:
+                S *= 2
+        if B % S != 0:
+            S = 1
+        Gs, Bs = G * S, B // S
+        nm = tag + f"#{len(plan)}"
+        dw = plan.buf(nm + ".dw", (G, R, n), torch.float32, arena="grads")
+        part = dw if S == 1 else plan.buf(nm + ".dw_part", (Gs, R, n), torch.float32)
+        d = nv.WgradDesc()
+        d.rows, d.rows_C, d.rows_P, d.rows_T = ptr(rows_src.t, rows_src.c0), rows_src.ld - rows_src.c0, 1, rows_src.T
+        d.rows_ld, d.rows_sB, d.rows_sG, d.rows_p, d.rows_t = rows_src.ld, rows_src.T * rows_src.ld, Bs * rows_src.T * rows_src.ld, 0, 0
+        d.cols, d.cols_C, d.cols_P, d.cols_T = ptr(cols_src.t, cols_src.c0), cols_src.ld - cols_src.c0, stride, cols_src.T // stride
+        d.cols_ld, d.cols_sB, d.cols_sG = cols_src.ld, cols_src.T * cols_src.ld, Bs * cols_src.T * cols_src.ld
+        d.taps, d.c_pad = taps, c_pad
+        for i, o in enumerate(tap_off):
+            d.tap_p[i] = o % stride
+            d.tap_t[i] = (o - o % stride) // stride
+        d.G, d.B, d.t_out, d.R, d.out, d.ldc, d.out_g = Gs, Bs, t_out, R, ptr(part), n, R * n
+        plan.add(d, tag + ".gemm(MN-major)")
+        if S > 1:
+            c = nv.ColsumDesc()
+            c.x, c.ld, c.x_g, c.G, c.rows, c.C, c.out, c.out_ld = ptr(part), R * n, S * R * n, G, S, R * n, ptr(dw), R * n
+            plan.add(c, tag + ".splitk_sum")
+        return dw
     S = split_k if split_k is not None else int(os.environ.get("VT_WGRAD_SPLITK", "1"))
     if S < 1 or B % S != 0 or rows_src.shared or cols_src.shared:
         S = 1
     Gs, Bs = G * S, B // S                       # split-K: slice s of net g = samples [s Bs, (s+1) Bs) -> group g S + s
     kp = round_up(Bs * t_out, 64)
-    R, c_pad, taps = rows_src.C, cols_src.C, len(tap_off)
-    n = taps * c_pad
     bn = 256 if n % 256 == 0 else 128
     n_pad = round_up(n, bn)
     nm = tag + f"#{len(plan)}"
