@@ -548,6 +548,10 @@ int vt_program_add_attention(vt_program* p, const vt_attn_desc* d);
 int vt_program_add_mlp(vt_program* p, const vt_mlp_desc* d);
 /* developer instrumentation (VT_GEMM_DEBUG bit 128): (tag, clock64) pairs of one epilogue warp; returns the entry count */
 int vt_debug_timestamps(long long* out, int max_entries);
+/* developer instrumentation (debug-knobs builds, VT_GEMM_DEBUG bit 512): timeline of the persistent multi-layer kernel.
+   out: [workers][tiles][slots] clock64 stamps, cal: [workers][4] = (clock64, globaltimer) at kernel entry and exit;
+   dims receives {workers, tiles, slots}.  Returns 0, or -1 when the library was built without the instrumentation. */
+int vt_debug_persist_trace(long long* out, long long* cal, int32_t* dims);
 int vt_program_add_imgstats(vt_program* p, const vt_imgstats_desc* d);
 int vt_program_add_patchify(vt_program* p, const vt_patchify_desc* d);
 int vt_program_add_cls(vt_program* p, const vt_cls_desc* d);

@@ -24,21 +24,28 @@ def stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, debug_knobs: bool = False) -> str:
-    """debug_knobs: compile the developer knobs / timestamps of csrc/vt_gemm.cuh in (VT_GEMM_DEBUG env variable; tools/ only)."""
+    """debug_knobs: compile the developer knobs / timestamps of csrc/vt_gemm.cuh in (VT_GEMM_DEBUG env variable; tools/ only) --
+    into a SEPARATE file, lib/libvt_b200_dbg.so (selected with VT_LIB=...), so that the release library is never replaced."""
+    if debug_knobs:
+        return _compile(OUT.replace("libvt_b200.so", "libvt_b200_dbg.so"), ["-DVT_DEBUG_KNOBS=1"], verbose, "build_dbg.log")
     if not force and not stale():
         return OUT
+    return _compile(OUT, [], verbose, "build.log")
+
+
+def _compile(out: str, extra, verbose: bool, logname: str) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-DVT_DEBUG_KNOBS=1"] if debug_knobs else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
-    with open(os.path.join(HERE, "lib", "build.log"), "w") as f:
+    with open(os.path.join(HERE, "lib", logname), "w") as f:
         f.write(" ".join(cmd) + "\n" + log)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + log[-4000:])
     if verbose:
         print(log)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

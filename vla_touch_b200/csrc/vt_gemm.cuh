@@ -41,6 +41,24 @@ constexpr bool kDbg = VT_DEBUG_KNOBS != 0;
 constexpr int VT_DBG_TS = 2048;
 __device__ long long vt_dbg_ts[VT_DBG_TS];
 __device__ int vt_dbg_n;
+// Persistent-kernel timeline (VT_GEMM_DEBUG bit 512, tools/persist_trace.py): per worker and local tile PTRACE_SLOTS clock64()
+// stamps by the leader CTA's TMA thread, MMA thread and first epilogue thread; vt_ptrace_cal holds (clock64, globaltimer)
+// pairs per worker at kernel entry and exit to put the SM clocks on one time base.
+constexpr int PTRACE_SLOTS = 12, PTRACE_TILES = 256, PTRACE_WORKERS = 80;
+#if VT_DEBUG_KNOBS
+__device__ long long vt_ptrace[PTRACE_WORKERS * PTRACE_TILES * PTRACE_SLOTS];
+__device__ long long vt_ptrace_cal[PTRACE_WORKERS * 4];
+#endif
+__device__ __forceinline__ void ptrace(long long* base, int slot) {
+#if VT_DEBUG_KNOBS
+  if (base) base[slot] = clock64();
+#endif
+}
+__device__ __forceinline__ void ptrace_val(long long* base, int slot, long long v) {
+#if VT_DEBUG_KNOBS
+  if (base) base[slot] = v;
+#endif
+}
 // The entry counter lives in a register of the recording thread (`n`): a stamp is two fire-and-forget stores.
 __device__ __forceinline__ void dbg_stamp(bool on, int& n, int tag) {
   if (kDbg && on && n + 1 < VT_DBG_TS) {
@@ -195,6 +213,7 @@ struct EpiTile {
   long long grow;          // logical row
   bool valid;
   int dbg_n;               // developer instrumentation: timestamps recorded so far (see dbg_stamp)
+  long long* tr;           // developer instrumentation: this tile's row of the persistent kernel's timeline (null = off)
   int q, rem;
   uint32_t taddr;          // TMEM address of this thread's lane, column 0 of the accumulator
 };
@@ -226,6 +245,7 @@ __device__ __forceinline__ void epilogue_linear(const GemmArgs& a, const EpiTile
   fetch(c_begin);
   mbar_wait(acc_full, acc_parity);
   tc_fence_after();
+  ptrace(t.tr, 7);
 #pragma unroll 1
   for (int c = c_begin; c < c_end; c += 32) {
     uint32_t v[32];
@@ -371,6 +391,7 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, EpiTile& t,
   fetch(c_begin);
   mbar_wait(acc_full, acc_parity);
   tc_fence_after();
+  ptrace(t.tr, 7);
   dbg_stamp(ts_on, t.dbg_n, 2);
 #pragma unroll 1
   for (int c = c_begin; c < c_end; c += 32) {
@@ -593,6 +614,7 @@ __device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, EpiTile& t, 
 
   mbar_wait(acc_full, acc_parity);
   tc_fence_after();
+  ptrace(t.tr, 7);
   dbg_stamp(ts_on, t.dbg_n, 21);
   // ---- pass 1: per-row sums of (acc + bias) over every 32-column chunk ----
   float s1[NCH], s2[NCH];
@@ -617,6 +639,7 @@ __device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, EpiTile& t, 
   dbg_stamp(ts_on, t.dbg_n, 22);
   gn_sample_totals<NCH>(a, t, s1, s2, gn_part, gn_stat, et, bar_id);
   dbg_stamp(ts_on, t.dbg_n, 23);
+  ptrace(t.tr, 8);
   const float cnt = (float)(a.gn_rows << a.gn_gs_log2);
   float rstd[NCH], nmr[NCH];   // 1/std and -mean/std of the row's sample, per chunk (group)
 #pragma unroll
@@ -728,6 +751,7 @@ __device__ __forceinline__ void epilogue_gn(const GemmArgs& a, const EpiTile& t,
 
   mbar_wait(acc_full, acc_parity);
   tc_fence_after();
+  ptrace(t.tr, 7);
   float s1[NCH], s2[NCH];
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
@@ -1070,6 +1094,7 @@ __global__ void __launch_bounds__(GEMM_THREADS(EW), 1) gemm_tc_kernel(const __gr
     EpiTile t;
     t.r = quarter * 32 + lane;
     t.dbg_n = 0;
+    t.tr = nullptr;
     uint32_t lt = 0;
     const bool fast = GEMM_XPOSE_BYTES(BN, MODE, EW) > 0 && a.fast != 0;
     const int et256 = threadIdx.x - 64;

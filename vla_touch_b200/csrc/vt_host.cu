@@ -1132,6 +1132,23 @@ int vt_debug_timestamps(long long* out, int max_entries) {
   return n;
 }
 
+int vt_debug_persist_trace(long long* out, long long* cal, int32_t* dims) {
+  if (dims) {
+    dims[0] = vt::PTRACE_WORKERS;
+    dims[1] = vt::PTRACE_TILES;
+    dims[2] = vt::PTRACE_SLOTS;
+  }
+#if VT_DEBUG_KNOBS
+  if (out && cudaMemcpyFromSymbol(out, vt::vt_ptrace, sizeof(vt::vt_ptrace)) != cudaSuccess) return -1;
+  if (cal && cudaMemcpyFromSymbol(cal, vt::vt_ptrace_cal, sizeof(vt::vt_ptrace_cal)) != cudaSuccess) return -1;
+  static std::vector<long long> zeros(sizeof(vt::vt_ptrace) / sizeof(long long), 0);
+  cudaMemcpyToSymbol(vt::vt_ptrace, zeros.data(), sizeof(vt::vt_ptrace));
+  return 0;
+#else
+  return -1;
+#endif
+}
+
 int vt_program_add_mlp(vt_program* p, const vt_mlp_desc* d) {
   if (!p || !d) return fail(VT_E_INVALID, "null argument");
   VT_REQUIRE(d->xn && d->w1 && d->b1 && d->w2 && d->b2 && d->h && d->rows >= 1, "mlp: bad descriptor");

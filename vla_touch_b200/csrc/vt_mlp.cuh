@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const __grid_
       // ---- Y + b2, * ls2, + residual -> h (coalescing epilogue; this warpgroup takes 192 of the 384 columns) ----
       EpiTile t;
       t.dbg_n = dbg_n;
+      t.tr = nullptr;
       t.r = r;
       t.g = 0;
       t.n0 = 0;

@@ -32,7 +32,14 @@ constexpr int PERSIST_MAX_DEPS = 4;
 constexpr int PERSIST_STAGES = 3;
 constexpr int PERSIST_KA = 2;
 constexpr int PERSIST_BN_MAX = 256;
-constexpr int PERSIST_THREADS = GEMM_THREADS(8);
+// Warpgroup 0 = {TMA producer, MMA issuer, two idle warps}, warpgroups 1-2 = the eight epilogue warps.  With 10 warps two of the
+// four SM sub-partitions host three warps and ptxas caps every thread at 168 registers, which the GroupNorm epilogue exceeds
+// (its spill reloads were 39 % of the stall samples of its inner loop, profiles/r02_persist_epilogue_stalls.txt); with whole
+// warpgroups per role `setmaxnreg` moves the registers warpgroup 0 does not need to the epilogue warps.
+constexpr int PERSIST_THREADS = 128 + 256;
+constexpr int PERSIST_EPI_T0 = 128;          // first epilogue thread
+constexpr int PERSIST_REGS_CTRL = 56, PERSIST_REGS_EPI = 224;
+static_assert(PERSIST_REGS_CTRL * 128 + PERSIST_REGS_EPI * 256 <= 65536, "register file");
 // operand ring (A 16 KB + B up to 16 KB per atom) + barriers + the GroupNorm epilogue's scratch (the transposition buffers of
 // the linear epilogue alias it: 8 warps x 4 KB)
 constexpr int PERSIST_SCRATCH_FLOATS = GEMM_SCRATCH_FLOATS(PERSIST_BN_MAX, EPI_GN);
@@ -185,12 +192,27 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) unet_persist_kernel(const 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything before this line overlaps the predecessor's tail (programmatic dependent launch)
+  long long* tr_base = nullptr;   // developer instrumentation (debug-knobs builds, VT_GEMM_DEBUG bit 512): see vt_gemm.cuh ptrace
+#if VT_DEBUG_KNOBS
+  if ((P.layers[0].g.debug & 512) && rank == 0 && worker < PTRACE_WORKERS) {
+    tr_base = vt_ptrace + (size_t)worker * PTRACE_TILES * PTRACE_SLOTS;
+    if (threadIdx.x == 0) {
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      vt_ptrace_cal[worker * 4 + 0] = clock64();
+      vt_ptrace_cal[worker * 4 + 1] = (long long)gt;
+    }
+  }
+#endif
+  auto tr_row = [&](uint32_t lt) -> long long* { return (tr_base && lt < (uint32_t)PTRACE_TILES) ? tr_base + lt * PTRACE_SLOTS : nullptr; };
 
-  if (warp == 0) {
+  if (warp < 4) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PERSIST_REGS_CTRL));
+   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int s = 0;
-      uint32_t ph = 0;
+      uint32_t ph = 0, lt = 0;
       for (int step = 0; step < P.n_steps; ++step) {
         for (int l = 0; l < P.n_layers; ++l) {
           const PersistLayer& L = P.layers[l];
@@ -200,7 +222,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) unet_persist_kernel(const 
           const int b_rows = L.bn >> 1;
           const uint32_t stage_tx = 2u * (uint32_t)(a.a_box_bytes + b_rows * 128);   // both CTAs, per atom
           for (int tile = persist_first_tile(step * P.tiles_per_step + L.tile_base, worker, n_workers); tile < L.n_tiles_total;
-               tile += n_workers) {
+               tile += n_workers, ++lt) {
             const int n_tile = tile % a.n_tiles, rest = tile / a.n_tiles;
             const int unit = rest % a.m_tiles, g = rest / a.m_tiles;
             const int m_tile = unit * 2 + rank;
@@ -223,7 +245,9 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) unet_persist_kernel(const 
                 ph ^= 1;
               }
             }
+            ptrace(tr_row(lt), 1);
             persist_wait(P, L, step, g, unit);
+            ptrace(tr_row(lt), 2);
             fence_proxy_async_global();
             for (int q = 0; q < n_stages; ++q) {
               const int n_at = (nk - q * KA) < KA ? (nk - q * KA) : KA;
@@ -252,7 +276,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) unet_persist_kernel(const 
         }
       }
     }
-  } else if (warp == 1) {
+   } else if (warp == 1) {
     // ------------------------------ UMMA issuer (leader CTA only) ------------------------------
     if (lane == 0 && rank == 0) {
       uint32_t lt = 0, ph = 0;
@@ -268,11 +292,13 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) unet_persist_kernel(const 
             const uint32_t acc = lt & 1;
             mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);
             tc_fence_after();
+            ptrace(tr_row(lt), 3);
             const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
             for (int i = 0; i < nk; i += KA) {
               const int n_at = (nk - i) < KA ? (nk - i) : KA;
               mbar_wait(&full[s], ph);
               tc_fence_after();
+              if (i == 0) ptrace(tr_row(lt), 4);
 #pragma unroll
               for (int at = 0; at < KA; ++at) {
                 if (at >= n_at) break;
@@ -288,25 +314,29 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) unet_persist_kernel(const 
               }
             }
             umma_commit_pair(&acc_full[acc], 3);
+            ptrace(tr_row(lt), 5);
           }
         }
       }
     }
+   }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PERSIST_REGS_EPI));
     // ------------------------------ epilogue warps ------------------------------
     constexpr int BN = PERSIST_BN_MAX;
-    const int half = (warp - 2) >> 2;
-    const int et = (threadIdx.x - 64) & 127;
-    const int et256 = threadIdx.x - 64;
+    const int half = (warp - 4) >> 2;
+    const int et = (threadIdx.x - PERSIST_EPI_T0) & 127;
+    const int et256 = threadIdx.x - PERSIST_EPI_T0;
     const int quarter = warp & 3;
     constexpr int CVG = GEMM_COLV_FLOATS(BN, EPI_GN);
     float2* gn_part = reinterpret_cast<float2*>(scratch + CVG) + half * (128 + 64) * 4;
     float2* gn_stat = gn_part + 128 * 4;
     float* films = scratch + CVG + 2 * (128 + 64) * 4 * 2;
-    const uint32_t xbuf = smem_u32(scratch) + (warp - 2) * 4096;
+    const uint32_t xbuf = smem_u32(scratch) + (warp - 4) * 4096;
     EpiTile t;
     t.r = quarter * 32 + lane;
     t.dbg_n = 0;
+    t.tr = nullptr;
     uint32_t lt = 0;
     for (int step = 0; step < P.n_steps; ++step) {
       for (int l = 0; l < P.n_layers; ++l) {
@@ -359,6 +389,11 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) unet_persist_kernel(const 
           const int m_tile = unit * 2 + rank;
           t.g = rest / a.m_tiles;
           t.n0 = n_tile * L.bn;
+#if VT_DEBUG_KNOBS
+          t.tr = threadIdx.x == PERSIST_EPI_T0 ? tr_row(lt) : nullptr;
+          ptrace_val(t.tr, 0, ((long long)step << 40) | ((long long)l << 20) | tile);
+          ptrace(t.tr, 6);
+#endif
           // the residual rows come from another pair's epilogue: acquire before the first read (the A operand's producers were
           // acquired by the TMA thread; this warp's own acquire also covers them)
           if (lane == 0) persist_wait(P, L, step, t.g, unit);
@@ -423,6 +458,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) unet_persist_kernel(const 
             if (L.out_f32) epilogue_linear<32, float, false>(a, t, colv, &acc_full[acc], parity, 0, 32);
             else epilogue_linear<32, bf, false>(a, t, colv, &acc_full[acc], parity, 0, 32);
           }
+          ptrace(t.tr, 9);
           tc_fence_before();
           fence_proxy_async_global();   // this tile's rows are A operands (TMA) of the consumer layers
           __syncwarp();
@@ -430,11 +466,20 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) unet_persist_kernel(const 
             mbar_arrive_remote(mapa_shared(smem_u32(&acc_empty[acc]), 0));
             persist_signal(P, L, t.g, unit);
           }
+          ptrace(t.tr, 10);
         }
       }
     }
   }
 
+#if VT_DEBUG_KNOBS
+  if (tr_base && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    vt_ptrace_cal[worker * 4 + 2] = clock64();
+    vt_ptrace_cal[worker * 4 + 3] = (long long)gt;
+  }
+#endif
   tc_fence_before();
   cluster_sync_all();   // the peer may still signal / read this CTA
   if (warp == 1) tmem_dealloc_pair(tmem_base, TMEM_COLS);

@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     EpiTile t;
     t.r = quarter * 32 + lane;
     t.dbg_n = 0;
+    t.tr = nullptr;
     uint32_t lt = 0;
     for (int tile = worker; tile < a.total_tiles; tile += n_workers, ++lt) {
       const uint32_t acc = lt & 1;

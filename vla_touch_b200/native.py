@@ -10,7 +10,8 @@ import os
 from typing import List, Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvt_b200.so")
+# VT_LIB: developer override (tools/ only), e.g. the instrumented build `python -m vla_touch_b200.build --debug-knobs` writes
+LIB_PATH = os.environ.get("VT_LIB") or os.path.join(_HERE, "lib", "libvt_b200.so")
 
 VT_BF16, VT_F32, VT_U8 = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_MISH = 0, 1, 2
@@ -185,7 +186,7 @@ class AdamwDesc(C.Structure):
 EXPORTS = [
     "vt_last_error", "vt_abi_version", "vt_device_info", "vt_program_create", "vt_program_destroy",
     "vt_program_num_ops", "vt_program_num_launches", "vt_program_add_gemm", "vt_program_add_layernorm",
-    "vt_program_add_attention", "vt_program_add_mlp", "vt_debug_timestamps", "vt_program_add_imgstats", "vt_program_add_patchify", "vt_program_add_cls",
+    "vt_program_add_attention", "vt_program_add_mlp", "vt_debug_timestamps", "vt_debug_persist_trace", "vt_program_add_imgstats", "vt_program_add_patchify", "vt_program_add_cls",
     "vt_program_add_pack", "vt_program_add_affine", "vt_program_add_tembed", "vt_program_add_sde",
     "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_add_tcol", "vt_program_add_gnbwd", "vt_program_add_colsum", "vt_program_add_ewise", "vt_program_add_silossbwd", "vt_program_add_lstm_train", "vt_program_add_lstm_bwd", "vt_program_add_lngelubwd", "vt_program_add_dropmask", "vt_program_add_persist", "vt_program_add_wgrad", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
     "vt_pos_embed_resize", "vt_adamw_ema_step",
