@@ -61,7 +61,8 @@ class ExponentialMovingAverage:
         self.param_writes += 1
 
     def store(self, parameters=None) -> None:
-        self.collected_params = [p.clone() for p in self._get_parameters(parameters)]
+        # detached: a clone that carries a grad_fn cannot be deep-copied by load_state_dict / saved in a checkpoint
+        self.collected_params = [p.detach().clone() for p in self._get_parameters(parameters)]
 
     @torch.no_grad()
     def restore(self, parameters=None) -> None:
