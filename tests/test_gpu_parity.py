@@ -353,13 +353,17 @@ def test_fused_adamw_ema_matches_torch():
     assert ema_new.num_updates == 5
 
 
-@pytest.mark.parametrize("tokens", [256, 257, 264, 272, 130, 730])
-def test_attention_kernels_against_fp32_softmax(tokens):
-    """attn_row_kernel (256..272 tokens: whole key range in TMEM, tail query rows on the CUDA cores) and the flash-style
-    attn_tc_kernel (any other count) against softmax(Q K^T / 8) V computed in fp32 from the same bf16 qkv rows (HF:199-235)."""
+@pytest.mark.parametrize("tokens,images,pp", [(256, 3, 0), (257, 3, 0), (257, 3, 1), (257, 80, 0), (257, 80, 1), (264, 3, 0), (272, 3, 0),
+                                              (130, 3, 0), (730, 3, 0)])
+def test_attention_kernels_against_fp32_softmax(tokens, images, pp, monkeypatch):
+    """attn_pp_kernel (257 tokens: both query tiles of a unit in flight, P in tensor memory, the 257th key and query row on the
+    CUDA cores; 80 images = several units per persistent CTA, both buffer sets), attn_row_kernel (256..272 tokens otherwise)
+    and the flash-style attn_tc_kernel (any other count) against softmax(Q K^T / 8) V computed in fp32 from the same bf16 qkv rows
+    (HF:199-235)."""
     from vla_touch_b200 import native as nv
     from vla_touch_b200.plan import Plan, ptr
-    images, heads = 3, 6
+    heads = 6
+    monkeypatch.setenv("VT_ATTN_PP", "1" if pp else "0")
     D = heads * 64
     g = torch.Generator().manual_seed(tokens)
     qkv32 = torch.randn(images * tokens, 3 * D, generator=g) * 1.5

@@ -16,6 +16,7 @@
 #include "vt_elem.cuh"
 #include "vt_gemm.cuh"
 #include "vt_persist.cuh"
+#include "vt_attn_pp.cuh"
 #include "vt_wgrad.cuh"
 #include "vt_lstm.cuh"
 #include "vt_lstm_tc.cuh"
@@ -425,13 +426,25 @@ struct AttnOp : Op {
   vt::AttnArgs args;
   vt::AttnRowArgs rargs;
   bool row_kernel = false;   // whole key range resident in TMEM (256..272 tokens): attn_row_kernel
+  bool pp_kernel = false;    // 257 tokens: attn_pp_kernel (both query tiles of a unit in flight, P in tensor memory)
   vt_attn_desc d;
   dim3 grid;
   int tail_first = -1;   // first query row handled by attn_tail_kernel, or -1
   static bool attr_set;
   int launches() const override { return (d.in_dtype == VT_BF16 && !row_kernel && tail_first >= 0 && grid.x > 0) ? 2 : 1; }
   int launch(cudaStream_t s) override {
-    if (d.in_dtype == VT_BF16 && row_kernel) {
+    if (d.in_dtype == VT_BF16 && row_kernel && pp_kernel) {
+      static bool pp_attr_set = false;
+      if (!pp_attr_set) {
+        VT_CUDA(cudaFuncSetAttribute(vt::attn_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vt::APP_SMEM_BYTES));
+        pp_attr_set = true;
+      }
+      {
+        cudaError_t e = launch_ex(vt::attn_pp_kernel, grid, dim3(vt::APP_THREADS, 1, 1), (size_t)vt::APP_SMEM_BYTES, s, false, true, rargs);
+        if (e != cudaSuccess) return fail(VT_E_CUDA, "attn_pp_kernel launch: %s", cudaGetErrorString(e));
+      }
+      VT_LAUNCH_CHECK("attn_pp_kernel");
+    } else if (d.in_dtype == VT_BF16 && row_kernel) {
       static bool row_attr_set = false;
       if (!row_attr_set) {
         VT_CUDA(cudaFuncSetAttribute(vt::attn_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vt::ATR_SMEM_BYTES));
@@ -1260,6 +1273,8 @@ int vt_program_add_attention(vt_program* p, const vt_attn_desc* d) {
       r.units = d->images * d->heads;
       r.scale_log2 = op->args.scale_log2;
       op->row_kernel = true;
+      const char* pp = getenv("VT_ATTN_PP");
+      op->pp_kernel = d->tokens == 257 && pp && atoi(pp) != 0;   // opt-in until it beats attn_row_kernel (profiles/r02_experiments.txt)
       const int sms = sm_count();
       op->grid = dim3((unsigned)(r.units < sms ? r.units : sms), 1u, 1u);
     }

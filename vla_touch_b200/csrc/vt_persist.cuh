@@ -39,7 +39,7 @@ constexpr int PERSIST_BN_MAX = 256;
 constexpr int PERSIST_THREADS = 128 + 256;
 constexpr int PERSIST_EPI_T0 = 128;          // first epilogue thread
 constexpr int PERSIST_REGS_CTRL = 56, PERSIST_REGS_EPI = 224;
-static_assert(PERSIST_REGS_CTRL * 128 + PERSIST_REGS_EPI * 256 <= 65536, "register file");
+static_assert(PERSIST_REGS_CTRL * 128 + PERSIST_REGS_EPI * 256 <= 168 * PERSIST_THREADS, "setmaxnreg can only redistribute the registers the launch allocated (168 per thread at 12 warps)");
 // operand ring (A 16 KB + B up to 16 KB per atom) + barriers + the GroupNorm epilogue's scratch (the transposition buffers of
 // the linear epilogue alias it: 8 warps x 4 KB)
 constexpr int PERSIST_SCRATCH_FLOATS = GEMM_SCRATCH_FLOATS(PERSIST_BN_MAX, EPI_GN);
