@@ -6,6 +6,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 os.environ.setdefault("VT_LIB", os.path.join(ROOT, "vla_touch_b200", "lib", "libvt_b200_dbg.so"))
+os.environ["VT_ATTN_PP"] = "1"
 sys.path.insert(0, ROOT)
 import torch
 
@@ -52,6 +53,6 @@ for t, sl, tag in ev[: int(sys.argv[1]) if len(sys.argv) > 1 else 260]:
     elif sl == 2:
         label = f"S issued g{tag - 20}" if tag < 30 else f"PV g{(tag - 30) // 10} c{(tag - 30) % 10}"
     else:
-        label = {50: "tail: K seen", 51: "tail: scores", 52: "tail: done", 60: "TMA: buf 0 free", 61: "TMA: buf 1 free"}.get(tag, str(tag))
+        label = {50: "tail: K seen", 51: "tail: scores", 52: "tail: done", 60: "TMA: K issued (g0)", 61: "TMA: V issued (g0)"}.get(tag, str(tag))
     print(f"{t - t0:8d}  " + "                          " * sl + f"{label:10s} +{t - last[sl]:5d}")
     last[sl] = t
