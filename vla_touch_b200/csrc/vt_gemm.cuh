@@ -573,16 +573,18 @@ __device__ __forceinline__ void gn_sample_totals(const GemmArgs& a, const EpiTil
   }
 }
 
-// Mish on two lanes: x * n / (n + 2), n = e^x (e^x + 2); two MUFU (ex2, rcp) per element, the rest packed f32x2.
+// Mish on two lanes: x tanh(softplus(x)) = x n / (n + 2) = x - 2 x / (n + 2) with n = e^x (e^x + 2); two MUFU (ex2, rcp) per
+// element, five packed f32x2 operations per pair.  No clamp is needed in this form: e^x = inf gives 1 / inf = 0 and the result x,
+// e^x = 0 gives x - x = 0; for very negative x the cancellation leaves an absolute error of ~|x| 2^-23, far below a bf16 ulp of
+// anything the value is added to.
 __device__ __forceinline__ float2 mish2(float2 x) {
-  const float2 xe = fmul2(make_float2(fminf(x.x, 20.f), fminf(x.y, 20.f)), make_float2(1.4426950408889634f, 1.4426950408889634f));
+  const float2 xe = fmul2(x, make_float2(1.4426950408889634f, 1.4426950408889634f));
   const float2 e = make_float2(ex2_approx(xe.x), ex2_approx(xe.y));
-  const float2 n = ffma2(e, e, fadd2(e, e));
-  const float2 d = fadd2(n, make_float2(2.f, 2.f));
+  const float2 d = ffma2(e, fadd2(e, make_float2(2.f, 2.f)), make_float2(2.f, 2.f));   // n + 2
   float2 r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
-  return fmul2(x, fmul2(n, r));
+  return ffma2(fmul2(x, make_float2(-2.f, -2.f)), r, x);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -603,10 +605,18 @@ __device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, EpiTile& t, 
   const bf* resp = (a.res && t.valid) ? reinterpret_cast<const bf*>(a.res) + (long long)t.g * a.res_g + res_row * a.ldres + t.n0 + cb : nullptr;
   const float* filmp = (a.film_c && !films) ? a.film_c + (long long)t.g * a.film_g + (long long)t.q * a.film_ld + a.film_off + t.n0 + cb : nullptr;
   const float* fs = films ? films + (t.valid ? (t.r / a.gn_rows) : 0) * 2 * BN + cb : nullptr;   // this row's sample
+  // 32-byte accesses when rows and chunk offsets allow (chunks are 64 bytes apart): half the L1 wavefronts of the row-per-lane pattern
+  const bool out32 = ((reinterpret_cast<uintptr_t>(outp) | (uintptr_t)((long long)a.ldc * 2)) & 31) == 0;
+  const bool res32 = resp && ((reinterpret_cast<uintptr_t>(resp) | (uintptr_t)((long long)a.ldres * 2)) & 31) == 0;
   uint4 rr[4];
   auto fetch_res = [&](int ch) {
+    if (res32) {
+      ld_global_v8(resp + ch * 32, rr[0], rr[1]);
+      ld_global_v8(resp + ch * 32 + 16, rr[2], rr[3]);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) rr[i] = resp ? *reinterpret_cast<const uint4*>(resp + ch * 32 + i * 8) : make_uint4(0u, 0u, 0u, 0u);
+      for (int i = 0; i < 4; ++i) rr[i] = resp ? *reinterpret_cast<const uint4*>(resp + ch * 32 + i * 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
   };
   fetch_res(0);
   const bool ts_on = kDbg && (a.debug & 128) && blockIdx.x == 0 && threadIdx.x == 64;
@@ -618,23 +628,30 @@ __device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, EpiTile& t, 
   dbg_stamp(ts_on, t.dbg_n, 21);
   // ---- pass 1: per-row sums of (acc + bias) over every 32-column chunk ----
   float s1[NCH], s2[NCH];
+  static_assert(NCH % 2 == 0, "pass 1 reads two chunks per TMEM round trip");
 #pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) {
-    uint32_t v[32];
-    tmem_ld32(t.taddr + cb + ch * 32, v);
+  for (int c2 = 0; c2 < NCH; c2 += 2) {
+    uint32_t va[32], vb[32];                 // both loads in flight: one exposed TMEM latency per 64 columns instead of two
+    tmem_ld32(t.taddr + cb + c2 * 32, va);
+    tmem_ld32(t.taddr + cb + c2 * 32 + 32, vb);
     tmem_ld_wait();
-    float2 a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b4 = *reinterpret_cast<const float4*>(colv + cb + ch * 32 + j);
-      const float2 x0 = fadd2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(b4.x, b4.y));
-      const float2 x1 = fadd2(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), make_float2(b4.z, b4.w));
-      a1 = fadd2(a1, fadd2(x0, x1));
-      a2 = ffma2(x0, x0, a2);
-      a2 = ffma2(x1, x1, a2);
+    for (int u = 0; u < 2; ++u) {
+      const int ch = c2 + u;
+      const uint32_t(&v)[32] = u ? vb : va;
+      float2 a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(colv + cb + ch * 32 + j);
+        const float2 x0 = fadd2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(b4.x, b4.y));
+        const float2 x1 = fadd2(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), make_float2(b4.z, b4.w));
+        a1 = fadd2(a1, fadd2(x0, x1));
+        a2 = ffma2(x0, x0, a2);
+        a2 = ffma2(x1, x1, a2);
+      }
+      s1[ch] = t.valid ? a1.x + a1.y : 0.f;
+      s2[ch] = t.valid ? a2.x + a2.y : 0.f;
     }
-    s1[ch] = t.valid ? a1.x + a1.y : 0.f;
-    s2[ch] = t.valid ? a2.x + a2.y : 0.f;
   }
   dbg_stamp(ts_on, t.dbg_n, 22);
   gn_sample_totals<NCH>(a, t, s1, s2, gn_part, gn_stat, et, bar_id);
@@ -649,10 +666,12 @@ __device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, EpiTile& t, 
     nmr[ch] = -mean * rstd[ch];
   }
   // ---- pass 2: normalise, affine, Mish, FiLM, residual, store ----
+  // The accumulator chunk is only read by the first phase (v -> y), so the NEXT chunk's tcgen05.ld is issued right after it and its
+  // latency (~400 cycles, and the scoreboard wait for the stores that still read the previous values) hides under the Mish phase.
+  uint32_t v[32];
+  tmem_ld32(t.taddr + cb, v);
 #pragma unroll 1
   for (int ch = 0; ch < NCH; ++ch) {
-    uint32_t v[32];
-    tmem_ld32(t.taddr + cb + ch * 32, v);
     float rs = rstd[0], nm = nmr[0];
 #pragma unroll
     for (int k = 1; k < NCH; ++k) {
@@ -665,11 +684,11 @@ __device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, EpiTile& t, 
     for (int i = 0; i < 4; ++i) rc[i] = rr[i];
     tmem_ld_wait();
     if (ch + 1 < NCH) fetch_res(ch + 1);   // after the wait: tcgen05.wait::ld also waits for global loads issued before it
-    if (t.valid) {
+    const int c0 = ch * 32;
+    float2 y[16];
+    {
       // The whole 32-column chunk moves through the phases together (16 independent pairs per phase): the Mish chain
       // (ex2 -> fma -> add -> rcp -> mul) has ~150 cycles of latency and only two warps share a scheduler.
-      const int c0 = ch * 32;
-      float2 y[16];
 #pragma unroll
       for (int h = 0; h < 8; ++h) {
         const float4 b4 = *reinterpret_cast<const float4*>(colv + cb + c0 + 4 * h);
@@ -680,6 +699,9 @@ __device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, EpiTile& t, 
         y[2 * h] = ffma2(ffma2(x0, rs2, nm2), make_float2(g4.x, g4.y), make_float2(e4.x, e4.y));
         y[2 * h + 1] = ffma2(ffma2(x1, rs2, nm2), make_float2(g4.z, g4.w), make_float2(e4.z, e4.w));
       }
+    }
+    if (ch + 1 < NCH) tmem_ld32(t.taddr + cb + (ch + 1) * 32, v);
+    if (t.valid) {
 #pragma unroll
       for (int p = 0; p < 16; ++p) y[p] = mish2(y[p]);
       if (fs) {
@@ -715,18 +737,22 @@ __device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, EpiTile& t, 
           for (int h = 0; h < 4; ++h) y[4 * q + h] = fadd2(y[4 * q + h], __bfloat1622float2(h2[h]));
         }
       }
+      uint4 w[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        uint4 w;
-        w.x = pack_bf16x2(y[4 * q].x, y[4 * q].y);
-        w.y = pack_bf16x2(y[4 * q + 1].x, y[4 * q + 1].y);
-        w.z = pack_bf16x2(y[4 * q + 2].x, y[4 * q + 2].y);
-        w.w = pack_bf16x2(y[4 * q + 3].x, y[4 * q + 3].y);
-        if (kDbg && (a.debug & 16)) {   // developer knob: no store traffic (timing only)
-          if (w.x == 0x12345678u) *reinterpret_cast<uint4*>(outp + c0 + 8 * q) = w;
-        } else {
-          *reinterpret_cast<uint4*>(outp + c0 + 8 * q) = w;
-        }
+        w[q].x = pack_bf16x2(y[4 * q].x, y[4 * q].y);
+        w[q].y = pack_bf16x2(y[4 * q + 1].x, y[4 * q + 1].y);
+        w[q].z = pack_bf16x2(y[4 * q + 2].x, y[4 * q + 2].y);
+        w[q].w = pack_bf16x2(y[4 * q + 3].x, y[4 * q + 3].y);
+      }
+      if (kDbg && (a.debug & 16)) {   // developer knob: no store traffic (timing only)
+        if (w[0].x == 0x12345678u) *reinterpret_cast<uint4*>(outp + c0) = w[0];
+      } else if (out32) {
+        st_global_v8(outp + c0, w[0], w[1]);
+        st_global_v8(outp + c0 + 16, w[2], w[3]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(outp + c0 + 8 * q) = w[q];
       }
     }
     dbg_stamp(ts_on, t.dbg_n, 24);

@@ -394,6 +394,19 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
   return d;
 }
+// 256-bit global accesses (sm_100: LDG / STG .E.ENL2.256; 32-byte aligned).  A warp whose lanes address 32 different rows pays one
+// L1 wavefront per lane and instruction whatever the access width, so a 32-byte access moves twice the bytes of a 16-byte one
+// per wavefront: the row-per-lane epilogues after tcgen05.ld (32x32b) are bound by exactly that.
+__device__ __forceinline__ void ld_global_v8(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void st_global_v8(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
 __device__ __forceinline__ float4 ld_shared_v4f(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
