@@ -583,6 +583,12 @@ int vt_program_graph_launch(vt_program* p, void* stream);
 /* immediate launch of the fused AdamW + EMA step */
 int vt_adamw_ema_step(const vt_adamw_desc* d, void* stream);
 
+/* pad_and_resize_for_siglip (scripts/utils_eef.py:44-77; called at scripts/franka_inference_eef.py:329-330): n uint8 frames
+   [h][w][c] on the device -> [target][target][c], zero-padded to a centred square and down-scaled like
+   cv2.resize(..., interpolation=cv2.INTER_AREA) -- bit-identical to OpenCV (integer-factor and fractional-factor paths).
+   Up-scaling (max(h, w) < target) returns VT_E_INVALID. */
+int vt_pad_resize_area(const uint8_t* src_dev, int32_t n, int32_t h, int32_t w, int32_t c, uint8_t* dst_dev, int32_t target, void* stream);
+
 /* bicubic (A=-0.75, align_corners=False) resize of the patch position embeddings, HF:57-95: src [s*s][D] -> dst [nh*nw][D] */
 int vt_pos_embed_resize(const float* src_dev, int32_t s, float* dst_dev, int32_t nh, int32_t nw, int32_t D, void* stream);
 

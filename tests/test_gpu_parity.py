@@ -5,10 +5,15 @@ Tolerances are the north-star gates: bf16 path  max|err| <= 5e-2 * max|ref| (rel
                                                 ||err||_2 <= 5e-2 ||ref||_2
                                      fp32 path  max|err| <= 1e-3 absolute     (3-pass split-tf32 tensor-core GEMMs)
 """
+import os
+import sys
+
 import pytest
 import torch
 
 import vt_testutil as U
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 from oracle import vt_oracle as orc
 from vla_touch_b200 import shapes as shp
 from vla_touch_b200 import synthetic as syn
@@ -463,3 +468,34 @@ def test_fused_mlp_matches_reference_math(rows):
     assert torch.isfinite(got).all()
     err = (got - ref).abs().max().item()
     assert err <= 2e-2 * ref.abs().max().item(), (rows, err, ref.abs().max().item())
+
+
+def test_pad_and_resize_for_siglip_is_bit_identical_to_cv2():
+    """image_ops.pad_and_resize_for_siglip (csrc/vt_resize.cuh) against the reference function's own outputs (cv2 INTER_AREA,
+    tests/golden/resize_*.npz): every down-scaling path, numpy / CPU-tensor / CUDA-tensor inputs, a batch, the deployment frame size."""
+    import hashlib
+    import numpy as np
+    from vla_touch_b200.image_ops import pad_and_resize_for_siglip
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gen_golden_resize as gg
+    g = np.load(os.path.join(ROOT, "tests", "golden", "resize_small.npz"))
+    for name, h, w, t in gg.CASES:
+        got = pad_and_resize_for_siglip(g[f"{name}_in"], t)
+        assert got.is_cuda and got.dtype == torch.uint8 and tuple(got.shape) == (t, t, 3)
+        assert np.array_equal(got.cpu().numpy(), g[f"{name}_out"]), name
+    d = np.load(os.path.join(ROOT, "tests", "golden", "resize_digests.npz"))
+    frames = []
+    for name, h, w, t, seed in gg.BIG:
+        f = gg.frame(h, w, seed)
+        got = pad_and_resize_for_siglip(torch.from_numpy(f).cuda(), t)
+        assert np.array_equal(np.frombuffer(hashlib.sha256(got.cpu().numpy().tobytes()).digest(), dtype=np.uint8), d[name]), name
+        frames.append((f, got))
+    f0, want0 = frames[0]
+    batch = pad_and_resize_for_siglip(np.stack([f0, f0[::-1].copy()]), 384)            # [N, H, W, C]
+    assert tuple(batch.shape) == (2, 384, 384, 3) and torch.equal(batch[0], want0)
+    assert torch.equal(batch[1], pad_and_resize_for_siglip(f0[::-1].copy(), 384))
+    assert pad_and_resize_for_siglip(None) is None
+    with pytest.raises(NotImplementedError):
+        pad_and_resize_for_siglip(np.zeros((100, 120, 3), np.uint8), 384)
+    with pytest.raises(TypeError):
+        pad_and_resize_for_siglip(np.zeros((500, 500, 3), np.float32), 384)

@@ -1,5 +1,8 @@
 """Pins the oracle restatement (oracle/vt_oracle.py) to outputs of the UNMODIFIED reference
 (tests/golden/*.npz, produced by oracle/gen_golden.py).  CPU only."""
+import os
+import sys
+
 import pytest
 import torch
 
@@ -7,6 +10,8 @@ from oracle import vt_oracle as orc
 from vla_touch_b200 import shapes as shp
 from vla_touch_b200 import synthetic as syn
 import vt_testutil as U
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 TOL = dict(rtol=0, atol=3e-6)
 
@@ -263,3 +268,22 @@ def test_explicit_lstm_bptt_matches_reference_digests(A, Fd, T):
         assert abs(float(gr.norm()) - float(gg["norm"][i])) <= 1e-3 * scale, n
         k = min(8, gr.numel())
         assert float((gr[:k] - gg["head"][i][:k].double()).abs().max()) <= 1e-3 * scale, n
+
+
+# ---- pad_and_resize_for_siglip (scripts/utils_eef.py:44-77): the numpy restatement of cv2 INTER_AREA against cv2's own outputs ----
+def test_resize_oracle_reproduces_cv2_goldens():
+    import hashlib
+    import numpy as np
+    from oracle import resize_oracle as ro
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gen_golden_resize as gg
+    g = np.load(os.path.join(ROOT, "tests", "golden", "resize_small.npz"))
+    for name, h, w, t in gg.CASES:
+        got = ro.pad_and_resize_for_siglip(g[f"{name}_in"], t)
+        assert got.shape == (t, t, 3) and got.dtype == np.uint8
+        assert np.array_equal(got, g[f"{name}_out"]), name                      # bit-exact: byte work
+    d = np.load(os.path.join(ROOT, "tests", "golden", "resize_digests.npz"))
+    for name, h, w, t, seed in gg.BIG:
+        got = ro.pad_and_resize_for_siglip(gg.frame(h, w, seed), t)
+        assert np.array_equal(np.frombuffer(hashlib.sha256(got.tobytes()).digest(), dtype=np.uint8), d[name]), name
+    assert ro.pad_and_resize_for_siglip(None) is None

@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
+#include <cmath>
 #include <memory>
 #include <string>
 #include <vector>
@@ -17,6 +19,7 @@
 #include "vt_gemm.cuh"
 #include "vt_persist.cuh"
 #include "vt_attn_pp.cuh"
+#include "vt_resize.cuh"
 #include "vt_wgrad.cuh"
 #include "vt_lstm.cuh"
 #include "vt_lstm_tc.cuh"
@@ -1468,6 +1471,85 @@ int vt_adamw_ema_step(const vt_adamw_desc* d, void* stream) {
       reinterpret_cast<const vt::OptTensor*>(d->tensors), reinterpret_cast<const long long*>(d->chunks), d->chunk_elems, d->lr,
       d->beta1, d->beta2, d->eps, d->weight_decay, d->bias_corr1, d->bias_corr2, d->ema_decay, d->grad_scale);
   VT_LAUNCH_CHECK("adamw_ema_kernel");
+  return VT_OK;
+}
+
+// ---- pad_and_resize_for_siglip (scripts/utils_eef.py:44-77) ----
+namespace {
+struct ResizeTab {
+  int side = 0, target = 0;
+  int* off = nullptr;
+  int* si = nullptr;
+  float* alpha = nullptr;
+};
+std::vector<ResizeTab> g_resize_tabs;   // one per (canvas side, target) seen; a handful in practice
+
+// OpenCV computeResizeAreaTab (imgproc/resize.cpp), double arithmetic, weights stored as float
+int resize_area_tab(int side, int target, ResizeTab* out) {
+  for (const ResizeTab& t : g_resize_tabs)
+    if (t.side == side && t.target == target) {
+      *out = t;
+      return VT_OK;
+    }
+  const double scale = (double)side / target;
+  std::vector<int> off(target + 1, 0), si;
+  std::vector<float> al;
+  for (int dx = 0; dx < target; ++dx) {
+    off[dx] = (int)si.size();
+    const double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+    const double cell = std::min(scale, side - fsx1);
+    int sx1 = (int)std::ceil(fsx1), sx2 = (int)std::floor(fsx2);
+    sx2 = std::min(sx2, side - 1);
+    sx1 = std::min(sx1, sx2);
+    if (sx1 - fsx1 > 1e-3) {
+      si.push_back(sx1 - 1);
+      al.push_back((float)((sx1 - fsx1) / cell));
+    }
+    for (int sx = sx1; sx < sx2; ++sx) {
+      si.push_back(sx);
+      al.push_back((float)(1.0 / cell));
+    }
+    if (fsx2 - sx2 > 1e-3) {
+      si.push_back(sx2);
+      al.push_back((float)(std::min(std::min(fsx2 - sx2, 1.0), cell) / cell));
+    }
+  }
+  off[target] = (int)si.size();
+  ResizeTab t;
+  t.side = side;
+  t.target = target;
+  VT_CUDA(cudaMalloc(&t.off, off.size() * sizeof(int)));
+  VT_CUDA(cudaMalloc(&t.si, si.size() * sizeof(int)));
+  VT_CUDA(cudaMalloc(&t.alpha, al.size() * sizeof(float)));
+  VT_CUDA(cudaMemcpy(t.off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
+  VT_CUDA(cudaMemcpy(t.si, si.data(), si.size() * sizeof(int), cudaMemcpyHostToDevice));
+  VT_CUDA(cudaMemcpy(t.alpha, al.data(), al.size() * sizeof(float), cudaMemcpyHostToDevice));
+  g_resize_tabs.push_back(t);
+  *out = t;
+  return VT_OK;
+}
+}  // namespace
+
+int vt_pad_resize_area(const uint8_t* src_dev, int32_t n, int32_t h, int32_t w, int32_t c, uint8_t* dst_dev, int32_t target, void* stream) {
+  VT_REQUIRE(src_dev && dst_dev && n >= 1 && h >= 1 && w >= 1 && c >= 1 && c <= 4 && target >= 1, "pad_resize_area: bad arguments");
+  const int side = h > w ? h : w;
+  VT_REQUIRE(side >= target, "pad_resize_area: up-scaling (canvas %d < target %d) is a different INTER_AREA code path and is not built", side, target);
+  vt::ResizeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.src = src_dev; a.dst = dst_dev; a.n = n; a.h = h; a.w = w; a.c = c; a.target = target;
+  a.side = side; a.pad_y = (side - h) / 2; a.pad_x = (side - w) / 2;
+  if (side % target == 0) {
+    a.iscale = side / target;
+    a.inv_area = 1.f / (float)(a.iscale * a.iscale);
+  } else {
+    ResizeTab t;
+    int rc = resize_area_tab(side, target, &t);
+    if (rc) return rc;
+    a.tab_off = t.off; a.tab_si = t.si; a.tab_alpha = t.alpha;
+  }
+  const long long total = (long long)n * target * target * c;
+  vt::pad_resize_area_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  VT_LAUNCH_CHECK("pad_resize_area_kernel");
   return VT_OK;
 }
 
