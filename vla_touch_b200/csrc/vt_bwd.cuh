@@ -203,17 +203,249 @@ __global__ void __launch_bounds__(256) gn_mish_bwd_kernel(const GnBwdArgs a) {
   }
 }
 
+// Shared-memory-resident version (C in {128, 256, 512}, T * C * 8 bytes <= 128 KB: every shape of the U-Net at T <= 64).
+// gn_mish_bwd_kernel re-reads the sample's tile from L1 / L2 in four sweeps with one dependent load per thread and position and
+// evaluates Mish twice with expf: 0.85 TB/s of its 10 bytes per element, 28 % of the training program.  Here the CTA (512 threads)
+// loads the raw and d out tiles ONCE with all its 128-bit loads in flight, keeps them in shared memory, overwrites them in place
+// with x_hat and d a in sweep 3, so Mish (ex2 + rcp on MUFU) is evaluated once per element, and splits the T positions of a
+// channel over 512 / C threads.  Same outputs as gn_mish_bwd_kernel (different summation order over T).
+constexpr int GNBS_THREADS = 512;
+
+// d mish / dx and mish on two lanes: packed f32x2 arithmetic, one ex2 and ONE rcp per lane (1 / ((1 + e)(n + 2)) gives both
+// 1 / (n + 2) and 1 / (1 + e) by a multiplication)
+__device__ __forceinline__ void mish_and_grad2(float2 x, float2& m, float2& dm) {
+  const float2 one = make_float2(1.f, 1.f), two = make_float2(2.f, 2.f);
+  const float2 xe = fmul2(make_float2(fminf(x.x, 20.f), fminf(x.y, 20.f)), make_float2(1.4426950408889634f, 1.4426950408889634f));
+  const float2 e = make_float2(ex2_approx(xe.x), ex2_approx(xe.y));
+  const float2 e1 = fadd2(e, one);                 // 1 + e
+  const float2 n = fmul2(e, fadd2(e, two));        // e (e + 2)
+  const float2 n2 = fadd2(n, two);                 // n + 2
+  const float2 den = fmul2(e1, n2);
+  float2 r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(den.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(den.y));
+  const float2 tsp = fmul2(n, fmul2(r, e1));       // n / (n + 2)
+  const float2 sig = fmul2(e, fmul2(r, n2));       // e / (1 + e)
+  m = fmul2(x, tsp);
+  // dm = tsp + x (1 - tsp^2) sig
+  const float2 omt = ffma2(make_float2(-tsp.x, -tsp.y), tsp, one);
+  dm = ffma2(fmul2(x, omt), sig, tsp);
+}
+
+// Thread = one channel PAIR (packed f32x2 arithmetic, 8-byte shared-memory accesses) and every PARTS-th position; C is a template
+// parameter so that the tile addressing is strength-reduced (the first version spent 128 instructions per element, most of them
+// integer address arithmetic and loop control: 57 % issue utilisation at 0.8 TB/s).
+template <int C>
+__global__ void __launch_bounds__(GNBS_THREADS, 1) gn_mish_bwd_smem_kernel(const GnBwdArgs a) {
+  extern __shared__ float gnb_smem[];
+  constexpr int CP = C / 2;                     // channel pairs
+  constexpr int PARTS = GNBS_THREADS / CP;      // threads per channel pair: 2 (C = 512), 4 (256), 8 (128)
+  const int T = a.T, Cg = C / a.groups;
+  float* s_raw = gnb_smem;              // [T][C]  raw conv output, later x_hat
+  float* s_do = s_raw + T * C;          // [T][C]  d out, later d a = d out * scale * mish'
+  float* s_red = s_do + T * C;          // [4][PARTS][C] partial sums of the threads that share a channel pair
+  float* s_ch = s_red + 4 * PARTS * C;  // [2][C] per-channel totals
+  float* s_grp = s_ch + 2 * C;          // [4][64] mean, E[x^2] / rstd, m1, m2 per group
+  const int g = blockIdx.x / a.B, b = blockIdx.x % a.B;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long sample = ((long long)g * a.B + b) * T;
+  const float* raw = a.raw + sample * C;
+  const float* dout = a.dout + (long long)g * a.dout_g + (long long)b * T * a.dout_ld;
+  const float inv_n = 1.f / (float)(Cg * T);
+  const int c = 2 * (tid % CP), part = tid / CP;
+  const int rows = T / PARTS;                   // positions of this thread: part, part + PARTS, ...
+
+  // ---- the two tiles -> shared memory (one tile at a time: 16 x 128-bit loads in flight per thread) ----
+  {
+    const int n4 = T * C / 4;
+    constexpr int c4 = C / 4;
+    constexpr int MAXV = 64 * 512 / 4 / GNBS_THREADS;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const float* src = which ? dout : raw;
+      const long long ld = which ? a.dout_ld : (long long)C;
+      float4* dst = reinterpret_cast<float4*>(which ? s_do : s_raw);
+      float4 v[MAXV];
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) {
+        const int i = tid + k * GNBS_THREADS;
+        if (i < n4) {
+          const int t = i / c4, cc = (i - t * c4) * 4;
+          v[k] = *reinterpret_cast<const float4*>(src + (long long)t * ld + cc);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) {
+        const int i = tid + k * GNBS_THREADS;
+        if (i < n4) dst[i] = v[k];
+      }
+    }
+  }
+  __syncthreads();
+  float2* raw2 = reinterpret_cast<float2*>(s_raw + part * C + c);   // this thread's column pair, first position; stride PARTS * C
+  float2* do2 = reinterpret_cast<float2*>(s_do + part * C + c);
+  constexpr int ST2 = PARTS * C / 2;                                // ... in float2 units
+  auto put = [&](int slot, float2 v) { *reinterpret_cast<float2*>(s_red + (slot * PARTS + part) * C + c) = v; };
+  // totals over the channel's threads -> s_ch[slot][.] (n_slots <= 2 at a time), then per-group totals by one warp per group
+  auto channel_totals = [&](int n_slots, int first_slot) {
+    __syncthreads();
+    if (tid < C) {
+      for (int sl = 0; sl < n_slots; ++sl) {
+        float v = 0.f;
+#pragma unroll
+        for (int p = 0; p < PARTS; ++p) v += s_red[((first_slot + sl) * PARTS + p) * C + tid];
+        s_ch[sl * C + tid] = v;
+      }
+    }
+    __syncthreads();
+  };
+  auto group_totals = [&](float* out0, float* out1, float scale) {
+    if (warp < a.groups) {
+      float v0 = 0.f, v1 = 0.f;
+      for (int i = lane; i < Cg; i += 32) {
+        v0 += s_ch[warp * Cg + i];
+        v1 += s_ch[C + warp * Cg + i];
+      }
+      v0 = warp_sum(v0);
+      v1 = warp_sum(v1);
+      if (lane == 0) {
+        out0[warp] = v0 * scale;
+        out1[warp] = v1 * scale;
+      }
+    }
+    __syncthreads();
+  };
+  // sweeps 1 + 2 in one pass: group mean and variance from sum / sum of squares in fp32, exactly what the forward GroupNorm
+  // epilogue normalises with (vt_gemm.cuh epilogue_gn_fast), so x_hat here equals the forward's
+  {
+    float2 s = make_float2(0.f, 0.f), q = make_float2(0.f, 0.f);
+#pragma unroll 4
+    for (int i = 0; i < rows; ++i) {
+      const float2 x = raw2[i * ST2];
+      s = fadd2(s, x);
+      q = ffma2(x, x, q);
+    }
+    put(0, s);
+    put(1, q);
+    channel_totals(2, 0);
+    group_totals(s_grp, s_grp + 64, inv_n);
+  }
+  const int gi = c / Cg;                         // both channels of the pair are in the same group (Cg is even)
+  const float mu = s_grp[gi];
+  const float rs = rsqrtf(fmaxf(s_grp[64 + gi] - mu * mu, 0.f) + a.eps);
+  const float2 mu2 = make_float2(mu, mu), rs2 = make_float2(rs, rs);
+  const float2 gam = *reinterpret_cast<const float2*>(a.gamma + (long long)g * a.p_ld + c);
+  const float2 bet = *reinterpret_cast<const float2*>(a.beta + (long long)g * a.p_ld + c);
+  const float2 scl = a.film ? *reinterpret_cast<const float2*>(a.film + (long long)g * a.film_g + (long long)b * a.film_ld + a.film_off + c)
+                            : make_float2(1.f, 1.f);
+  // sweep 3: x_hat and d a in place; per-channel sums of d a, d a * x_hat and the FiLM gradients
+  {
+    float2 s_da = make_float2(0.f, 0.f), s_dax = s_da, f_sc = s_da, f_sh = s_da;
+    const float2 nmr = make_float2(-mu * rs, -mu * rs);
+#pragma unroll 2
+    for (int i = 0; i < rows; ++i) {
+      const float2 xh = ffma2(raw2[i * ST2], rs2, nmr);
+      const float2 go = do2[i * ST2];
+      float2 m, dm;
+      mish_and_grad2(ffma2(xh, gam, bet), m, dm);
+      const float2 da = fmul2(fmul2(go, scl), dm);
+      raw2[i * ST2] = xh;
+      do2[i * ST2] = da;
+      s_da = fadd2(s_da, da);
+      s_dax = ffma2(da, xh, s_dax);
+      f_sc = ffma2(go, m, f_sc);
+      f_sh = fadd2(f_sh, go);
+    }
+    put(0, s_da);
+    put(1, s_dax);
+    put(2, f_sc);
+    put(3, f_sh);
+    __syncthreads();
+    if (tid < C) {
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+      for (int p = 0; p < PARTS; ++p) {
+        t0 += s_red[(0 * PARTS + p) * C + tid];
+        t1 += s_red[(1 * PARTS + p) * C + tid];
+        t2 += s_red[(2 * PARTS + p) * C + tid];
+        t3 += s_red[(3 * PARTS + p) * C + tid];
+      }
+      if (a.dfilm) {
+        float* df = a.dfilm + (long long)g * a.film_g + (long long)b * a.film_ld + a.film_off;
+        df[tid] = t2;
+        df[C + tid] = t3;
+      }
+      float* p = a.part + ((long long)g * a.B + b) * 3 * C;
+      p[tid] = t1;           // d gamma contribution: sum d a * x_hat
+      p[C + tid] = t0;       // d beta contribution: sum d a
+      const float gm = a.gamma[(long long)g * a.p_ld + tid];
+      s_ch[tid] = gm * t0;
+      s_ch[C + tid] = gm * t1;
+    }
+    __syncthreads();
+    group_totals(s_grp + 128, s_grp + 192, inv_n);
+  }
+  // sweep 4: d raw = rstd * (d a * gamma - mean_g(d xh) - x_hat * mean_g(d xh * x_hat));  d bias = sum_t d raw
+  {
+    const float m1 = s_grp[128 + gi], m2 = s_grp[192 + gi];
+    const float2 nm1 = make_float2(-m1, -m1), nm2 = make_float2(-m2, -m2);
+    float2 s_dr = make_float2(0.f, 0.f);
+    __nv_bfloat16* dr_out = a.draw + (sample + part) * C + c;
+#pragma unroll 4
+    for (int i = 0; i < rows; ++i) {
+      const float2 t0 = ffma2(do2[i * ST2], gam, nm1);
+      const float2 dr = fmul2(rs2, ffma2(raw2[i * ST2], nm2, t0));
+      s_dr = fadd2(s_dr, dr);
+      *reinterpret_cast<uint32_t*>(dr_out + (long long)i * PARTS * C) = pack_bf16x2(dr.x, dr.y);
+    }
+    put(0, s_dr);          // slot 0 was last read before the group_totals barrier above
+    __syncthreads();
+    if (tid < C) {
+      float v = 0.f;
+#pragma unroll
+      for (int p = 0; p < PARTS; ++p) v += s_red[p * C + tid];
+      a.part[((long long)g * a.B + b) * 3 * C + 2 * C + tid] = v;
+    }
+  }
+}
+__host__ __device__ constexpr size_t gnbs_smem_bytes(int T, int C) {
+  return (size_t)(2 * T * C + 4 * (GNBS_THREADS / (C / 2)) * C + 2 * C + 256) * sizeof(float);
+}
+
 // out_k[g][c] = sum_b part[g][b][k][c], k = 0..2 -> (d gamma, d beta, d bias), each [G][p_ld]
+// One CTA per 32 columns of a (g, k) row block: 32 column lanes x 8 sample lanes, four independent loads in flight per thread, the
+// eight partials combined through shared memory in a fixed order (deterministic).  (The first version gave every thread one column
+// and the whole serial chain of B dependent L2 loads, on a grid of G * 3 * C / 256 = 18 CTAs: ~75 us per call, more than the
+// GroupNorm backward kernel it follows.)
 __global__ void __launch_bounds__(256) gn_colsum_kernel(const float* __restrict__ part, int G, int B, int C, float* dgamma,
                                                         float* dbeta, float* dbias, int p_ld) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= G * 3 * C) return;
-  const int c = idx % C, k = (idx / C) % 3, g = idx / (3 * C);
-  const float* p = part + (long long)g * B * 3 * C + (long long)k * C + c;
-  float s = 0.f;
-  for (int b = 0; b < B; ++b) s += p[(long long)b * 3 * C];
-  float* o = k == 0 ? dgamma : (k == 1 ? dbeta : dbias);
-  if (o) o[(long long)g * p_ld + c] = s;
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int strips = (C + 31) / 32;
+  const int strip = blockIdx.x % strips, k = (blockIdx.x / strips) % 3, g = blockIdx.x / (3 * strips);
+  const int c = strip * 32 + tx;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < C) {
+    const float* p = part + (long long)g * B * 3 * C + (long long)k * C + c;
+    const long long st = 3LL * C;
+    int b = ty;
+    for (; b + 24 < B; b += 32) {
+      s0 += p[(long long)b * st];
+      s1 += p[(long long)(b + 8) * st];
+      s2 += p[(long long)(b + 16) * st];
+      s3 += p[(long long)(b + 24) * st];
+    }
+    for (; b < B; b += 8) s0 += p[(long long)b * st];
+  }
+  red[ty][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][tx];
+    float* o = k == 0 ? dgamma : (k == 1 ? dbeta : dbias);
+    if (o) o[(long long)g * p_ld + c] = s;
+  }
 }
 
 // out[g][c] = sum_r x[g][r][c] : bias gradient of a convolution without GroupNorm (conv1d_bwd's `dy.sum(dim=(0, 2))`).

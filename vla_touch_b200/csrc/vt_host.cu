@@ -668,9 +668,30 @@ struct GnbwdOp : Op {
     a.film = d.film; a.film_g = d.film_g; a.film_ld = d.film_ld; a.film_off = d.film_off; a.dfilm = d.dfilm;
     a.draw = reinterpret_cast<__nv_bfloat16*>(d.draw); a.part = d.part;
     a.G = d.G; a.B = d.B; a.T = d.T; a.C = d.C; a.groups = d.groups; a.eps = d.eps;
-    vt::gn_mish_bwd_kernel<<<d.G * d.B, 256, 0, s>>>(a);
-    VT_LAUNCH_CHECK("gn_mish_bwd_kernel");
-    vt::gn_colsum_kernel<<<(d.G * 3 * d.C + 255) / 256, 256, 0, s>>>(d.part, d.G, d.B, d.C, d.dgamma, d.dbeta, d.dbias, d.p_ld);
+    const size_t smem = vt::gnbs_smem_bytes(d.T, d.C);
+    const char* env = getenv("VT_GNBWD_SMEM");
+    const int parts = d.C >= 2 ? vt::GNBS_THREADS / (d.C / 2) : 1;
+    const bool fits = (d.C == 128 || d.C == 256 || d.C == 512) && d.T % parts == 0 && smem <= 200 * 1024 && d.groups <= vt::GNBS_THREADS / 32 &&
+                      (d.C / d.groups) % 2 == 0 && d.dout_ld % 4 == 0 && d.p_ld % 2 == 0 && aligned16(d.raw) && aligned16(d.dout) && d.dout_g % 4 == 0 &&
+                      (!d.film || (d.film_g % 2 == 0 && d.film_ld % 2 == 0 && d.film_off % 2 == 0 && ((uintptr_t)d.film & 7) == 0)) &&
+                      ((uintptr_t)d.gamma & 7) == 0 && ((uintptr_t)d.beta & 7) == 0 && !(env && atoi(env) == 0);
+    if (fits) {   // shared-memory-resident kernel: the sample's tiles are read from HBM once
+      static bool attr_set = false;
+      if (!attr_set) {
+        VT_CUDA(cudaFuncSetAttribute(vt::gn_mish_bwd_smem_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        VT_CUDA(cudaFuncSetAttribute(vt::gn_mish_bwd_smem_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        VT_CUDA(cudaFuncSetAttribute(vt::gn_mish_bwd_smem_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+      }
+      if (d.C == 128) vt::gn_mish_bwd_smem_kernel<128><<<d.G * d.B, vt::GNBS_THREADS, smem, s>>>(a);
+      else if (d.C == 256) vt::gn_mish_bwd_smem_kernel<256><<<d.G * d.B, vt::GNBS_THREADS, smem, s>>>(a);
+      else vt::gn_mish_bwd_smem_kernel<512><<<d.G * d.B, vt::GNBS_THREADS, smem, s>>>(a);
+      VT_LAUNCH_CHECK("gn_mish_bwd_smem_kernel");
+    } else {
+      vt::gn_mish_bwd_kernel<<<d.G * d.B, 256, 0, s>>>(a);
+      VT_LAUNCH_CHECK("gn_mish_bwd_kernel");
+    }
+    vt::gn_colsum_kernel<<<d.G * 3 * ((d.C + 31) / 32), 256, 0, s>>>(d.part, d.G, d.B, d.C, d.dgamma, d.dbeta, d.dbias, d.p_ld);
     VT_LAUNCH_CHECK("gn_colsum_kernel");
     return VT_OK;
   }
