@@ -152,6 +152,13 @@ class StochasticInterpolants:
         sd = {k: v.detach() for k, v in self.net.state_dict().items()}
         return [sub_state_dict(sd, "b_net."), sub_state_dict(sd, "v_net."), sub_state_dict(sd, "s_net.")]
 
+    def _net_param_dicts(self):
+        """{key: Parameter} of b_net / v_net / s_net in the order of `_net_state_dicts` (only parameters: the nets have no buffers)"""
+        out = []
+        for name in ("b_net", "v_net", "s_net"):
+            out.append({k: p for k, p in getattr(self.net, name).named_parameters()})
+        return out
+
     def _weights_token(self):
         """Identity + version of the live parameters: a program's packed operand copies are current iff its token matches.
         (Identity matters: a freshly loaded net has the same version sum as the one it replaces.)"""
@@ -173,8 +180,17 @@ class StochasticInterpolants:
             if ent[0] is prog:
                 tok = self._weights_token()
                 if ent[1] != tok:
-                    prog.refresh_graphed(self._net_state_dicts())
-                    ent[1] = tok
+                    if getattr(prog, "_gather", None) is None and not getattr(prog, "_gather_tried", False):
+                        # first re-pack: build and verify the gather maps; the parameters move into one contiguous arena
+                        # (p.data becomes a view of it)
+                        prog._gather_tried = True
+                        if os.environ.get("VT_GATHER_REPACK", "1") != "0":
+                            prog.setup_gather(self._net_param_dicts(), self._net_state_dicts())
+                    if getattr(prog, "_gather", None) is not None:
+                        prog.refresh_gather()
+                    else:
+                        prog.refresh_graphed(self._net_state_dicts())
+                    ent[1] = self._weights_token()
                 return
         raise KeyError("not a program of this model")
 

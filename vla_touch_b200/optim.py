@@ -110,6 +110,7 @@ class FusedAdamWEMA:
         self._chunks = torch.tensor(chunks, dtype=torch.int64).to(self._dev)
         self.n_chunks = len(chunks)
         self._shadow_ptrs = [s.data_ptr() if s is not None else 0 for s in self._shadow]
+        self._param_ptrs = [p.data_ptr() for p in self.params]
 
     def set_grad_sources(self, grad_sources: dict) -> None:
         """Point the records at another program's gradient buffers (a new batch shape built a new training program)."""
@@ -141,6 +142,8 @@ class FusedAdamWEMA:
     @torch.no_grad()
     def step(self, grad_scale: float = 1.0) -> None:
         self.gather_grads()                                 # a backward pass may have re-bound .grad
+        if [p.data_ptr() for p in self.params] != self._param_ptrs:      # p.data was re-pointed (parameter arena of the re-pack)
+            self._build_records()
         if self.ema is not None:                            # ema.load_state_dict() / ema.to() replace the shadow tensors
             cur = self._shadows()
             if [s.data_ptr() if s is not None else 0 for s in cur] != self._shadow_ptrs:

@@ -46,8 +46,12 @@ class Mode:
     def plane(self, C: int) -> int:
         return C if self.precise else 0
 
+    TRACE = False     # unet_train.GatherRepack: run the packing functions on index-valued tensors (no cast to the operand dtype)
+
     def pack_w(self, w: torch.Tensor) -> torch.Tensor:
         """[..., K] fp32 (already zero padded) -> operand dtype; precise: [..., hi K | lo K]."""
+        if Mode.TRACE:
+            return w.float().contiguous()
         if not self.precise:
             return w.to(torch.bfloat16).contiguous()
         hi = tf32_round(w.float())

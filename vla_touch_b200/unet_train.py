@@ -23,9 +23,14 @@ import torch
 from . import native as nv
 from . import unet_bwd as ub
 from .plan import Plan, linear_desc, ptr
-from .unet import DOWN_DIMS, DSED, FILM_ROWS, UnetWeights, _View, _conv, _tembed, block_names
+from .unet import DOWN_DIMS, DSED, FILM_ROWS, Mode, UnetWeights, _View, _conv, _tembed, block_names
 
 SD = Dict[str, torch.Tensor]
+
+
+def _operand_dtype():
+    """bf16, or fp32 while the packing functions are traced with index-valued tensors (GatherRepack)"""
+    return torch.float32 if Mode.TRACE else torch.bfloat16
 K5 = [(0, dt) for dt in (-2, -1, 0, 1, 2)]
 K1 = [(0, 0)]
 
@@ -269,7 +274,7 @@ def build_film_time_backward(plan: Plan, W: UnetWeights, sds: Sequence[SD], tf: 
         grads[pfx + "cond_encoder.1.bias"] = (dbf[:, off: off + 2 * co], 0)
     # d Mish(gf) = d film @ W_full
     pack_wt = lambda sds_: torch.stack([torch.cat([sd[pfx + "cond_encoder.1.weight"].detach().to(dev).float()
-                                                   for pfx, _, _ in block_names()]).t() for sd in sds_]).to(torch.bfloat16).contiguous()
+                                                   for pfx, _, _ in block_names()]).t() for sd in sds_]).to(_operand_dtype()).contiguous()
     wt = plan.reg(pack_wt(sds))                                                                       # [G][512][11264]
     dfb = ub.cast_bf16(plan, G, B, dfilm, 1, f"{tag}.dfilm.bf16")
     dmgf = plan.buf(f"{tag}.dmgf", (G, B, kd), torch.float32)
@@ -283,7 +288,7 @@ def build_film_time_backward(plan: Plan, W: UnetWeights, sds: Sequence[SD], tf: 
                                                               tag=f"{tag}.time_mlp.1.wgrad"), 0)
     grads["diffusion_step_encoder.3.bias"] = (ub.colsum(plan, G, B, dtemb, 1, f"{tag}.time_mlp.1.dbias"), 0)
     pack_w3t = lambda sds_: torch.stack([sd["diffusion_step_encoder.3.weight"].detach().to(dev).float().t()
-                                         for sd in sds_]).to(torch.bfloat16).contiguous()
+                                         for sd in sds_]).to(_operand_dtype()).contiguous()
     w3t = plan.reg(pack_w3t(sds))
     if not hasattr(W, "repack"):
         W.repack = []
@@ -357,6 +362,104 @@ class LossBackwardProgram:
         self.sds = [dict(sd) for sd in sds_bvs]
         self.W.refresh(sds_bvs)
         ub.repack_all(self.W, sds_bvs)
+
+    # ---- re-pack by gather maps ----
+    def setup_gather(self, params_bvs: Sequence[Dict[str, torch.nn.Parameter]], sds_bvs: Sequence[SD]) -> bool:
+        """Replace the ~2000 tiny tensor ops of `refresh` (6.5 ms of device time per training step even as a CUDA graph) by one
+        gather per operand tensor.  Every packed operand (forward weights, the transposed / tap-sliced dgrad copies, stacked FiLM
+        matrices, bias / gamma vectors) is a fixed rearrangement of parameter elements plus zero padding, so it is described by an
+        index map -- obtained by running the very same packing functions on index-valued tensors -- into ONE contiguous fp32 arena
+        that the parameters are re-pointed into (`p.data` becomes a view; values, Parameter objects and state_dict keys are
+        unchanged).  A bf16 mirror of the arena (one cast per step) feeds the bf16 operands.  The maps are verified against the
+        tensor-op re-pack before they are used; returns False (and changes nothing) if the verification fails."""
+        if self.plan.device.type != "cuda" or self.W.mode.precise or getattr(self, "_gather", None) is not None:
+            return getattr(self, "_gather", None) is not None
+        dev = self.plan.device
+        self.refresh(sds_bvs)                               # operands = the current parameter values: what the maps are verified against
+        plist = [p for ps in params_bvs for p in ps.values()]
+        if any(p.dtype != torch.float32 or not p.is_contiguous() or p.device != dev for p in plist):
+            return False
+        offs, total = [], 0
+        for p in plist:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        zero_slot = total
+        arena = torch.zeros(total + 4, dtype=torch.float32, device=dev)
+        # index-valued stand-ins: parameter id + 1 and element offset + 1 (both exact in fp32), 0 = padding
+        fake_id, fake_off, i = [], [], 0
+        for g, ps in enumerate(params_bvs):
+            fid, fof = {}, {}
+            for k, p in ps.items():
+                fid[k] = torch.full(p.shape, float(i + 1), dtype=torch.float32, device=dev)
+                fof[k] = (torch.arange(p.numel(), dtype=torch.float32, device=dev) + 1.0).view(p.shape)
+                i += 1
+            fake_id.append(fid)
+            fake_off.append(fof)
+        off_t = torch.tensor(offs, dtype=torch.int64, device=dev)
+        numel_t = torch.tensor([p.numel() for p in plist], dtype=torch.int64, device=dev)
+        dests = [(k, t) for k, t in self.W.t.items()] + [(f"tracked{j}", d) for j, (d, _) in enumerate(getattr(self.W, "repack", []))]
+
+        def traced(fake):
+            Mode.TRACE = True
+            try:
+                out = list(self.W._pack(fake).values()) + [fn(fake) for _, fn in getattr(self.W, "repack", [])]
+            finally:
+                Mode.TRACE = False
+            return out
+        ids, ofs = traced(fake_id), traced(fake_off)
+        maps = []
+        for (name, dest), mi, mo in zip(dests, ids, ofs):
+            if tuple(mi.shape) != tuple(dest.shape):
+                return False
+            mi_f, mo_f = mi.reshape(-1), mo.reshape(-1)
+            mi = mi_f.round().long()
+            mo = mo_f.round().long()
+            if int(mi.max()) == 0:
+                continue                                    # independent of the parameters (zero vectors)
+            # a pure rearrangement: integer ids in range, offsets inside the parameter, padding exactly where the id is 0
+            sel = mi > 0
+            lim = numel_t[(mi - 1).clamp(0, len(plist) - 1)]
+            if (bool(((mi_f - mi).abs() > 1e-3).any()) or bool(((mo_f - mo).abs() > 1e-3).any()) or int(mi.min()) < 0 or int(mi.max()) > len(plist)
+                    or bool((sel & ((mo < 1) | (mo > lim))).any()) or bool(((~sel) & (mo != 0)).any())):
+                return False
+            idx = torch.where(mi > 0, off_t[(mi - 1).clamp_min(0)] + mo - 1, torch.full_like(mi, zero_slot))
+            maps.append((dest, idx.to(torch.int32)))
+        # move the parameters into the arena, verify the maps against the tensor-op re-pack, then switch over
+        with torch.no_grad():
+            for p, o in zip(plist, offs):
+                arena[o: o + p.numel()].copy_(p.detach().reshape(-1))
+        arena_bf = arena.to(torch.bfloat16)
+        for dest, idx in maps:
+            src = arena_bf if dest.dtype == torch.bfloat16 else arena
+            if dest.dtype not in (torch.bfloat16, torch.float32):
+                return False
+            got = torch.index_select(src, 0, idx).view(dest.shape)
+            if not torch.equal(got, dest):
+                return False
+        with torch.no_grad():
+            for p, o in zip(plist, offs):
+                p.data = arena[o: o + p.numel()].view(p.shape)
+        self._gather = (arena, arena_bf, maps)
+        self._gather_graph = None
+        return True
+
+    def refresh_gather(self) -> None:
+        """One cast of the parameter arena + one gather per operand tensor, replayed as a CUDA graph."""
+        arena, arena_bf, maps = self._gather
+
+        def run():
+            arena_bf.copy_(arena)
+            for dest, idx in maps:
+                torch.index_select(arena_bf if dest.dtype == torch.bfloat16 else arena, 0, idx, out=dest.view(-1))
+        if self._gather_graph is None:
+            run()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run()
+            self._gather_graph = g
+            return
+        self._gather_graph.replay()
 
     def refresh_graphed(self, sds_bvs: Sequence[SD]) -> None:
         """`refresh` replayed as one CUDA graph.  The re-pack is ~2000 tiny tensor ops (permute / pad / cast per parameter and
