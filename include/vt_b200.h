@@ -583,6 +583,12 @@ int vt_program_graph_launch(vt_program* p, void* stream);
 /* immediate launch of the fused AdamW + EMA step */
 int vt_adamw_ema_step(const vt_adamw_desc* d, void* stream);
 
+/* Operand re-pack after an optimizer step (no reference counterpart: torch re-reads nn.Parameters, here every GEMM reads a packed
+   bf16 copy): dst[i] = arena[map[i]] for all records in one launch.  recs_dev: device array of {void* dst; const int32_t* map;
+   int64_t n; int32_t bf16; int32_t pad} (n a multiple of 8 per 16-byte aligned dst, or any n with a scalar tail); chunks_dev:
+   (record, first element) pairs, 8192 elements per chunk. */
+int vt_gather_repack(const void* recs_dev, const int64_t* chunks_dev, int32_t n_chunks, const float* arena_dev, void* stream);
+
 /* pad_and_resize_for_siglip (scripts/utils_eef.py:44-77; called at scripts/franka_inference_eef.py:329-330): n uint8 frames
    [h][w][c] on the device -> [target][target][c], zero-padded to a centred square and down-scaled like
    cv2.resize(..., interpolation=cv2.INTER_AREA) -- bit-identical to OpenCV (integer-factor and fractional-factor paths).

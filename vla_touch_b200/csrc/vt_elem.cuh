@@ -506,6 +506,49 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(const OptTensor* __restr
   }
 }
 
+// Operand re-pack after an optimizer step (unet_train.LossBackwardProgram.setup_gather): every packed GEMM operand is a fixed
+// rearrangement of parameter elements, dst[i] = arena[map[i]] (map points at a zero slot for padding).  One launch for all
+// operands: chunk -> (record, offset); a thread converts 8 consecutive destination elements (32-byte map load, 16-byte store).
+struct GatherRec {
+  void* dst;
+  const int* map;
+  long long n;
+  int bf16;        // 1: destination is bf16, 0: fp32
+  int pad;
+};
+constexpr int GATHER_CHUNK = 8192;
+__global__ void __launch_bounds__(256) gather_repack_kernel(const GatherRec* __restrict__ recs, const long long* __restrict__ chunks,
+                                                            const float* __restrict__ arena) {
+  const GatherRec r = recs[chunks[2 * blockIdx.x]];
+  const long long off = chunks[2 * blockIdx.x + 1];
+  const long long end = min(off + (long long)GATHER_CHUNK, r.n);
+  for (long long i = off + 8LL * threadIdx.x; i < end; i += 8LL * blockDim.x) {
+    if (i + 8 <= end) {
+      const int4 m0 = *reinterpret_cast<const int4*>(r.map + i), m1 = *reinterpret_cast<const int4*>(r.map + i + 4);
+      const float v0 = arena[m0.x], v1 = arena[m0.y], v2 = arena[m0.z], v3 = arena[m0.w];
+      const float v4 = arena[m1.x], v5 = arena[m1.y], v6 = arena[m1.z], v7 = arena[m1.w];
+      if (r.bf16) {
+        uint4 w;
+        w.x = pack_bf16x2(v0, v1);
+        w.y = pack_bf16x2(v2, v3);
+        w.z = pack_bf16x2(v4, v5);
+        w.w = pack_bf16x2(v6, v7);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(r.dst) + i) = w;
+      } else {
+        float* d = reinterpret_cast<float*>(r.dst) + i;
+        *reinterpret_cast<float4*>(d) = make_float4(v0, v1, v2, v3);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(v4, v5, v6, v7);
+      }
+    } else {
+      for (long long j = i; j < end; ++j) {
+        const float v = arena[r.map[j]];
+        if (r.bf16) reinterpret_cast<__nv_bfloat16*>(r.dst)[j] = __float2bfloat16(v);
+        else reinterpret_cast<float*>(r.dst)[j] = v;
+      }
+    }
+  }
+}
+
 // bicubic resize (A = -0.75, align_corners = False) of the patch position embeddings, HF:57-95
 __device__ __forceinline__ void cubic_coeffs(float t, float* w) {
   const float A = -0.75f;

@@ -1495,6 +1495,14 @@ int vt_adamw_ema_step(const vt_adamw_desc* d, void* stream) {
   return VT_OK;
 }
 
+int vt_gather_repack(const void* recs_dev, const int64_t* chunks_dev, int32_t n_chunks, const float* arena_dev, void* stream) {
+  VT_REQUIRE(recs_dev && chunks_dev && arena_dev && n_chunks >= 1, "gather_repack: bad arguments");
+  vt::gather_repack_kernel<<<n_chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const vt::GatherRec*>(recs_dev), reinterpret_cast<const long long*>(chunks_dev), arena_dev);
+  VT_LAUNCH_CHECK("gather_repack_kernel");
+  return VT_OK;
+}
+
 // ---- pad_and_resize_for_siglip (scripts/utils_eef.py:44-77) ----
 namespace {
 struct ResizeTab {

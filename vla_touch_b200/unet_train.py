@@ -439,27 +439,17 @@ class LossBackwardProgram:
         with torch.no_grad():
             for p, o in zip(plist, offs):
                 p.data = arena[o: o + p.numel()].view(p.shape)
-        self._gather = (arena, arena_bf, maps)
-        self._gather_graph = None
+        # one native launch for all operands: records {dst, map, n, bf16} + (record, offset) chunks of 8192 elements
+        import struct
+        recs = b"".join(struct.pack("<QQqii", d.data_ptr(), idx.data_ptr(), d.numel(), 1 if d.dtype == torch.bfloat16 else 0, 0) for d, idx in maps)
+        chunks = [(i, off) for i, (d, _) in enumerate(maps) for off in range(0, d.numel(), 8192)]
+        self._gather = (arena, maps, torch.frombuffer(bytearray(recs), dtype=torch.uint8).to(dev), torch.tensor(chunks, dtype=torch.int64, device=dev), len(chunks))
         return True
 
     def refresh_gather(self) -> None:
-        """One cast of the parameter arena + one gather per operand tensor, replayed as a CUDA graph."""
-        arena, arena_bf, maps = self._gather
-
-        def run():
-            arena_bf.copy_(arena)
-            for dest, idx in maps:
-                torch.index_select(arena_bf if dest.dtype == torch.bfloat16 else arena, 0, idx, out=dest.view(-1))
-        if self._gather_graph is None:
-            run()
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                run()
-            self._gather_graph = g
-            return
-        self._gather_graph.replay()
+        """dst[i] = arena[map[i]] for every packed operand, one kernel launch (csrc/vt_elem.cuh gather_repack_kernel)."""
+        arena, _, recs, chunks, n_chunks = self._gather
+        nv.check(nv.lib().vt_gather_repack(recs.data_ptr(), chunks.data_ptr(), n_chunks, arena.data_ptr(), nv.current_stream_ptr()))
 
     def refresh_graphed(self, sds_bvs: Sequence[SD]) -> None:
         """`refresh` replayed as one CUDA graph.  The re-pack is ~2000 tiny tensor ops (permute / pad / cast per parameter and
