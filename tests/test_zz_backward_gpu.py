@@ -315,3 +315,50 @@ def test_lstm_tensor_core_recurrence_equals_the_cuda_core_kernels(B, T, monkeypa
     assert rel(o1, o0) <= 2e-2 and rel(d1, d0) <= 2e-2
     worst = {k: rel(g1[k], g0[k]) for k in g0}
     assert len(worst) == 18 and max(worst.values()) <= 2e-2, worst
+
+
+def test_gather_repack_equals_the_tensor_op_repack(monkeypatch):
+    """After an optimizer step the packed GEMM operands are rebuilt by ONE gather launch over index maps (unet_train.setup_gather,
+    csrc gather_repack_kernel).  Every operand must equal what the packing functions produce from the new parameter values, bit for
+    bit; the parameters must still be the same Parameter objects with the same values; a parameter that leaves the arena
+    (p.data replaced) switches the program back to the tensor-op re-pack."""
+    import vt_testutil as U
+    c = U.predict_case("predict_cfg2_B3_dark_varstats")
+    ctl = U.make_controller(c, "cuda:0", precise=False)
+    si = ctl.diffusion_model
+    B, T, A = 3, c["T"], c["A"]
+    cond = torch.randn(B, 256, device=DEV)
+    batch = {"obs_cond": cond, "expert_act": torch.zeros(B, T, A, device=DEV), "vla_act": c["vla"].to(DEV)}
+    params = list(si.net.parameters())
+    before = [p.detach().clone() for p in params]
+    loss, _ = si.get_loss(batch, DEV)
+    loss.backward()
+    with torch.no_grad():                                    # "optimizer step": in-place update bumps the version counters
+        for p in params:
+            p.add_(0.01 * torch.randn_like(p))
+    want = [p.detach().clone() for p in params]
+    loss2, _ = si.get_loss(batch, DEV)                       # first re-pack: sets the gather up (verified against the tensor ops)
+    prog = si.train_program(B, T)
+    assert getattr(prog, "_gather", None) is not None and prog.gather_valid()
+    assert all(p is q for p, q in zip(params, si.net.parameters()))
+    assert all(torch.equal(p.detach(), w) for p, w in zip(params, want)) and not torch.equal(want[0], before[0])
+    with torch.no_grad():
+        for p in params:
+            p.mul_(1.0 + 0.05 * torch.rand_like(p))
+    loss3, _ = si.get_loss(batch, DEV)                       # second re-pack: the gather launch alone
+    sds = si._net_state_dicts()
+    fresh = prog.W._pack(sds)
+    for k, t in prog.W.t.items():
+        assert torch.equal(t, fresh[k]), k
+    for dest, fn in prog.W.repack:
+        assert torch.equal(dest, fn(sds))
+    assert torch.isfinite(loss3) and float(loss3) != float(loss2)
+    with torch.no_grad():                                    # a parameter leaves the arena
+        params[5].data = params[5].data.clone()
+        params[5].add_(0.5)
+    assert not prog.gather_valid()
+    loss4, _ = si.get_loss(batch, DEV)
+    assert getattr(prog, "_gather", None) is None
+    fresh = prog.W._pack(si._net_state_dicts())
+    for k, t in prog.W.t.items():
+        assert torch.equal(t, fresh[k]), k

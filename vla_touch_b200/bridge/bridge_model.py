@@ -186,6 +186,8 @@ class StochasticInterpolants:
                         prog._gather_tried = True
                         if os.environ.get("VT_GATHER_REPACK", "1") != "0":
                             prog.setup_gather(self._net_param_dicts(), self._net_state_dicts())
+                    if getattr(prog, "_gather", None) is not None and not prog.gather_valid():
+                        prog._gather = None                 # parameters were moved out of the arena: tensor-op re-pack from now on
                     if getattr(prog, "_gather", None) is not None:
                         prog.refresh_gather()
                     else:

@@ -444,7 +444,13 @@ class LossBackwardProgram:
         recs = b"".join(struct.pack("<QQqii", d.data_ptr(), idx.data_ptr(), d.numel(), 1 if d.dtype == torch.bfloat16 else 0, 0) for d, idx in maps)
         chunks = [(i, off) for i, (d, _) in enumerate(maps) for off in range(0, d.numel(), 8192)]
         self._gather = (arena, maps, torch.frombuffer(bytearray(recs), dtype=torch.uint8).to(dev), torch.tensor(chunks, dtype=torch.int64, device=dev), len(chunks))
+        self._gather_probe = [(p, arena.data_ptr() + 4 * o) for p, o in zip(plist, offs)]
         return True
+
+    def gather_valid(self) -> bool:
+        """False once a parameter no longer lives in the arena (`net.to(...)`, a replaced `p.data`): the caller falls back to the
+        tensor-op re-pack and may set the gather up again."""
+        return getattr(self, "_gather", None) is not None and all(p.data_ptr() == ptr_ for p, ptr_ in self._gather_probe)
 
     def refresh_gather(self) -> None:
         """dst[i] = arena[map[i]] for every packed operand, one kernel launch (csrc/vt_elem.cuh gather_repack_kernel)."""
