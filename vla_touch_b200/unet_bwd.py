@@ -189,7 +189,13 @@ def conv_wgrad(plan, ctx: DgradCtx, B: int, rows_src: _View, cols_src: _View, *,
             c.x, c.ld, c.x_g, c.G, c.rows, c.C, c.out, c.out_ld = ptr(part), R * n, S * R * n, G, S, R * n, ptr(dw), R * n
             plan.add(c, tag + ".splitk_sum")
         return dw
-    S = split_k if split_k is not None else int(os.environ.get("VT_WGRAD_SPLITK", "1"))
+    S = split_k if split_k is not None else int(os.environ.get("VT_WGRAD_SPLITK", "0"))
+    if S <= 0:          # automatic (as on the MN-major path): enough tiles for the 74 CTA pairs, at least 256 positions per slice
+        bn_ = 256 if n % 256 == 0 else 128
+        tiles = G * ((R + 255) // 256) * ((n + bn_ - 1) // bn_)
+        S = 1
+        while tiles * S < 64 and S < 16 and B % (2 * S) == 0 and (B // (2 * S)) * t_out >= 256:
+            S *= 2
     if S < 1 or B % S != 0 or rows_src.shared or cols_src.shared:
         S = 1
     Gs, Bs = G * S, B // S                       # split-K: slice s of net g = samples [s Bs, (s+1) Bs) -> group g S + s
