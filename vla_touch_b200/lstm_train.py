@@ -97,20 +97,25 @@ class LstmLayerTrain:
         d = nv.LstmBwdDesc()
         d.gates, d.c, d.dy, d.dy_ld, d.w_hh, d.dgates = ptr(self.gates), ptr(self.c), ptr(dy), dy.shape[-1], ptr(self.w_hh), ptr(dg)
         d.B, d.T, d.H = B, T, H
+        dg_bf = None
         if os.environ.get("VT_LSTM_TC", "1") != "0":
-            d.w_hh_t_tc, d.dg_tc = ptr(self.w_hh_t_tc), ptr(p.buf(f"{tag}.dgates_bf16", (B, T, 4 * H), torch.bfloat16))
+            dg_bf = p.buf(f"{tag}.dgates_bf16", (B, T, 4 * H), torch.bfloat16)      # the tensor-core BPTT kernel's bf16 copy of d gates
+            d.w_hh_t_tc, d.dg_tc = ptr(self.w_hh_t_tc), ptr(dg_bf)
         p.add(d, f"{tag}.bptt")
         ctx = ub.DgradCtx(1, precise=False)
         V = _View
         dgv = V(dg.view(1, B, T, 4 * H), T, 4 * H)                                     # fp32 source: tcol converts to bf16
+        memo: dict = {}                                                                # both weight gradients read the same d gates^T
         dw_ih = ub.conv_wgrad(p, ctx, B, dgv, V(self.x.view(1, B, T, self.k_pad), T, self.k_pad), tap_off=[0], t_out=T,
-                              tag=f"{tag}.weight_ih.wgrad")
+                              tag=f"{tag}.weight_ih.wgrad", rows_t_memo=memo)
         dw_hh = ub.conv_wgrad(p, ctx, B, dgv, V(self.y.view(1, B, T, self.y_ld), T, H), tap_off=[-1], t_out=T,
-                              tag=f"{tag}.weight_hh.wgrad")                            # h_{t-1}: zero at t = 0
+                              tag=f"{tag}.weight_hh.wgrad", rows_t_memo=memo)          # h_{t-1}: zero at t = 0
         db = ub.colsum(p, 1, B, dgv, T, f"{tag}.bias.colsum")
         self.grads = {"weight_ih": dw_ih[0, :, : self.k_in], "weight_hh": dw_hh[0], "bias_ih": db[0], "bias_hh": db[0]}
         if need_dx:
-            dgb = ub.cast_bf16(p, 1, B, dgv, T, f"{tag}.dgates.bf16")
+            # the tensor-core BPTT kernel (host: B >= 16, 16-byte aligned dy rows) already wrote d gates as bf16
+            tc_bptt = dg_bf is not None and p.device.type == "cuda" and B >= 16 and dy.shape[-1] % 4 == 0
+            dgb = V(dg_bf.view(1, B, T, 4 * H), T, 4 * H) if tc_bptt else ub.cast_bf16(p, 1, B, dgv, T, f"{tag}.dgates.bf16")
             self.dx = p.buf(f"{tag}.dx", (B, T, self.k_pad), torch.float32)
             p.add(linear_desc(a=dgb.t, rows=R, k=4 * H, a_ld=4 * H, w=self.w_ih_t, n=self.k_pad, n_pad=self.k_pad,
                               w_ld=4 * H, out=self.dx, ldc=self.k_pad), f"{tag}.dx")

@@ -137,7 +137,7 @@ def _tcol(src: _View, B: int, G: int, out: torch.Tensor, *, tap_off: Sequence[in
 
 
 def conv_wgrad(plan, ctx: DgradCtx, B: int, rows_src: _View, cols_src: _View, *, tap_off: Sequence[int], stride: int = 1,
-               t_out: int, tag: str = "conv.wgrad", split_k: Optional[int] = None) -> torch.Tensor:
+               t_out: int, tag: str = "conv.wgrad", split_k: Optional[int] = None, rows_t_memo: Optional[dict] = None) -> torch.Tensor:
     """Weight gradient of a convolution as ONE plain row-major GEMM on the forward kernel (K = B * t_out positions):
 
         dW[g][r][tap * c_pad + c] = sum_{b, t < t_out} rows_src[g][b][t][r] * cols_src[g][b][t * stride + tap_off[tap]][c]
@@ -203,11 +203,20 @@ def conv_wgrad(plan, ctx: DgradCtx, B: int, rows_src: _View, cols_src: _View, *,
     bn = 256 if n % 256 == 0 else 128
     n_pad = round_up(n, bn)
     nm = tag + f"#{len(plan)}"
-    rT = plan.buf(nm + ".rowsT", (Gs, round_up(R, 128), kp), torch.bfloat16)
+    # rows_t_memo (opt-in, caller's promise that rows_src is not rewritten between the calls that share the dict): consecutive
+    # weight gradients with the SAME rows operand (d gates of an LSTM layer feeds d W_ih and d W_hh) share one transposed copy
+    key = (ptr(rows_src.t, rows_src.c0), rows_src.ld, rows_src.T, Bs, Gs, t_out, R, kp)
+    rT = rows_t_memo.get(key) if rows_t_memo is not None else None
+    new_rows = rT is None
+    if new_rows:
+        rT = plan.buf(nm + ".rowsT", (Gs, round_up(R, 128), kp), torch.bfloat16)
+        if rows_t_memo is not None:
+            rows_t_memo[key] = rT
     cT = plan.buf(nm + ".colsT", (Gs, n_pad, kp), torch.bfloat16)
     dw = plan.buf(nm + ".dw", (G, R, n), torch.float32, arena="grads")
     part = dw if S == 1 else plan.buf(nm + ".dw_part", (Gs, R, n), torch.float32)
-    plan.add(_tcol(rows_src, Bs, Gs, rT, tap_off=[0], stride=1, t_out=t_out, c_pad=R), tag + ".rowsT")
+    if new_rows:
+        plan.add(_tcol(rows_src, Bs, Gs, rT, tap_off=[0], stride=1, t_out=t_out, c_pad=R), tag + ".rowsT")
     plan.add(_tcol(cols_src, Bs, Gs, cT, tap_off=list(tap_off), stride=stride, t_out=t_out, c_pad=c_pad), tag + ".colsT")
     plan.add(linear_desc(a=rT, rows=R, k=kp, a_ld=kp, w=cT, n=n, n_pad=n_pad, w_ld=kp, out=part, ldc=n, G=Gs, a_G=Gs,
                          a_sG=rT.shape[1] * kp, out_g=R * n, bn=bn), tag + ".gemm")
