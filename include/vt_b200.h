@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VT_ABI_VERSION 2
+#define VT_ABI_VERSION 3
 
 enum { VT_OK = 0, VT_E_INVALID = -1, VT_E_CUDA = -2, VT_E_UNSUPPORTED = -3, VT_E_NODEVICE = -4 };
 enum { VT_BF16 = 0, VT_F32 = 1, VT_U8 = 2 };
@@ -151,6 +151,13 @@ typedef struct vt_mlp_desc {
   float* h;         /* fp32 [rows][ld_h] residual stream, updated in place */
   int64_t ld_h;
   int32_t rows, D;
+  /* optional (ln_out != NULL): LayerNorm(h_new) * ln_gamma + ln_beta as bf16 -- the NEXT block's norm1 (HF:367-372), written by the
+     CTA that produced the rows; ln_out may alias xn (a tile's xn rows are dead once its last fc1 MMA has been issued) */
+  const float* ln_gamma;
+  const float* ln_beta;
+  void* ln_out;     /* bf16 [rows][ln_ld] */
+  int64_t ln_ld;
+  float ln_eps;
 } vt_mlp_desc;
 
 /* visual_encoder.py:66-81,95-106: batch-global predicates max>1 and mean<0.5, evaluated on the device. */

@@ -156,7 +156,13 @@ def emu_mlp(plan, d: nv.MlpDesc):
         y = y * _flat(plan, d.ls2, torch.float32)[:D]
     hf = _flat(plan, d.h, torch.float32)
     idx = (r[:, None] * d.ld_h + torch.arange(D)[None, :]).reshape(-1)
-    hf[idx] = (y + hf[idx].reshape(d.rows, D)).reshape(-1)
+    hn = y + hf[idx].reshape(d.rows, D)
+    hf[idx] = hn.reshape(-1)
+    if d.ln_out:                                   # the next block's norm1, written by the same kernel
+        g, b = _flat(plan, d.ln_gamma, torch.float32)[:D], _flat(plan, d.ln_beta, torch.float32)[:D]
+        yn = F.layer_norm(hn, (D,), g, b, d.ln_eps).to(torch.bfloat16)
+        of = _flat(plan, d.ln_out, torch.bfloat16)
+        of[(r[:, None] * d.ln_ld + torch.arange(D)[None, :]).reshape(-1)] = yn.reshape(-1)
 
 
 def emu_imgstats(plan, d: nv.ImgStatsDesc):

@@ -449,16 +449,23 @@ def test_fused_mlp_matches_reference_math(rows):
     b1, b2 = torch.randn(4 * D, generator=g) * 0.1, torch.randn(D, generator=g) * 0.1
     ls2 = torch.rand(D, generator=g) + 0.5
     h0 = torch.randn(rows, D, generator=g)
+    h0[:, 7] += 40.0                                  # an outlier channel, as the DinoV2 residual stream has
+    h0 += torch.randn(rows, 1, generator=g) * 3.0     # and rows whose mean is not small against their spread
+    lg, lb = torch.rand(D, generator=g) + 0.5, torch.randn(D, generator=g) * 0.1
     plan = Plan(torch.device(DEV))
     xn = plan.buf("xn", (rows, D), torch.bfloat16)
+    ln = plan.buf("ln", (rows, D), torch.bfloat16)
+    ln.fill_(-7.0)
     h = plan.buf("h", (rows, D), torch.float32)
     xn.copy_(xn32)
     h.copy_(h0)
-    t = {k: plan.reg(v.to(DEV).contiguous()) for k, v in dict(w1=w1, w2=w2, b1=b1, b2=b2, ls2=ls2).items()}
+    t = {k: plan.reg(v.to(DEV).contiguous()) for k, v in dict(w1=w1, w2=w2, b1=b1, b2=b2, ls2=ls2, lg=lg, lb=lb).items()}
     d = nv.MlpDesc()
     d.xn, d.ld_x, d.w1, d.w1_ld, d.b1 = ptr(xn), D, ptr(t["w1"]), D, ptr(t["b1"])
     d.w2, d.w2_ld, d.b2, d.ls2 = ptr(t["w2"]), 4 * D, ptr(t["b2"]), ptr(t["ls2"])
     d.h, d.ld_h, d.rows, d.D = ptr(h), D, rows, D
+    # the next block's norm1 of the updated rows, from the same kernel (HF:367-372)
+    d.ln_gamma, d.ln_beta, d.ln_out, d.ln_ld, d.ln_eps = ptr(t["lg"]), ptr(t["lb"]), ptr(ln), D, 1e-6
     plan.add(d, "mlp")
     plan.compile().run(0, 1)
     torch.cuda.synchronize()
@@ -468,6 +475,10 @@ def test_fused_mlp_matches_reference_math(rows):
     assert torch.isfinite(got).all()
     err = (got - ref).abs().max().item()
     assert err <= 2e-2 * ref.abs().max().item(), (rows, err, ref.abs().max().item())
+    # LayerNorm of the rows the kernel actually wrote (fp32 statistics), rounded to bf16: one bf16 ulp of the normalised value
+    want = torch.nn.functional.layer_norm(got, (D,), lg, lb, 1e-6)
+    lerr = (ln.float().cpu() - want).abs()
+    assert (lerr <= 2.0 ** -7 * want.abs() + 1e-3).all(), (rows, lerr.max().item())
 
 
 def test_pad_and_resize_for_siglip_is_bit_identical_to_cv2():

@@ -330,9 +330,11 @@ __device__ __forceinline__ float2 gelu_fast2(float2 x) {   // same fit as gelu_f
   return ffma2(hx, th, hx);
 }
 
-template <int BN, typename TOut, bool PRECISE, int ACT, bool HAS_RES>
+// STATS: st[2i] / st[2i + 1] accumulate the sum / sum of squares of the values this lane stores for its i-th row (the
+// fused MLP kernel turns them into the next LayerNorm's row statistics); rows that do not exist accumulate garbage.
+template <int BN, typename TOut, bool PRECISE, int ACT, bool HAS_RES, bool STATS = false>
 __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, EpiTile& t, uint32_t xbuf, uint64_t* acc_full,
-                                                  uint32_t acc_parity, int c_begin, int c_end) {
+                                                  uint32_t acc_parity, int c_begin, int c_end, float* st = nullptr) {
   constexpr int NC = 16 / sizeof(TOut);   // columns per lane after the transpose
   constexpr int LPR = 32 / NC;            // lanes per row segment (8 / 4)
   constexpr int RPI = 32 / LPR;           // rows per warp-wide access (4 / 8)
@@ -456,6 +458,11 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, EpiTile& t,
           y1 = fmul2(z1, make_float2(sc[h].z, sc[h].w));
         }
         y[h] = make_float4(y0.x, y0.y, y1.x, y1.y);
+        if constexpr (STATS) {
+          const float2 s2 = fadd2(y0, y1), q2 = ffma2(y0, y0, fmul2(y1, y1));
+          st[2 * i] += s2.x + s2.y;
+          st[2 * i + 1] += q2.x + q2.y;
+        }
       }
       if (dbg & 16) {   // developer knob: keep the math alive, produce no store traffic
         if (y[0].x == 123.456f) outp[ooff[i] + c] = TOut(y[0].y);

@@ -1243,6 +1243,18 @@ int vt_program_add_mlp(vt_program* p, const vt_mlp_desc* d) {
   }
   a.m_tiles = (d->rows + 127) / 128;
   a.n_pairs = (a.m_tiles + 1) / 2;
+  if (d->ln_out) {
+    VT_REQUIRE(d->ln_gamma && d->ln_beta && d->ln_ld >= d->D && d->ln_ld % 4 == 0 && aligned16(d->ln_out) && aligned16(d->ln_gamma) &&
+                   aligned16(d->ln_beta) && d->ld_h % 4 == 0,
+               "mlp: fused LayerNorm output needs 16-byte aligned rows / vectors");
+    a.ln_gamma = d->ln_gamma;
+    a.ln_beta = d->ln_beta;
+    a.ln_out = reinterpret_cast<__nv_bfloat16*>(d->ln_out);
+    a.ln_ld = d->ln_ld;
+    a.ln_eps = d->ln_eps;
+    const char* ldbg = VT_DEBUG_KNOBS ? getenv("VT_MLP_LN_DEBUG") : nullptr;
+    a.ln_debug = ldbg ? atoi(ldbg) : 0;
+  }
   const int workers = sm_count() / 2;
   op->grid = dim3((unsigned)(a.n_pairs < workers ? a.n_pairs : workers) * 2u, 1u, 1u);
   p->ops.push_back(std::move(op));

@@ -13,14 +13,17 @@
 //   Y + b2, * ls2, + residual -> h through the coalescing epilogue of the GEMM kernel (vt_gemm.cuh).
 // Each CTA stages only HALF of every weight tile (64 of W1_j's 128 rows, 2 x 96 of W2's 384 rows): the 2.36 MB of
 // weights stream through a pair once per 256 rows, 28 bytes per clock per SM.
-//   warp 0  TMA producer      warp 1  MMA issuer (leader CTA)      warps 2-9  epilogue (quarter = warp & 3, half = (warp-2)/4)
+//   warp 0  TMA producer      warp 1  MMA issuer (leader CTA)      warps 4-11  epilogue (quarter = warp & 3, half = (warp-4)/4)
+//   warps 2-3  LayerNorm of the finished rows (the next block's norm1), off the critical path.
+// 12 warps: every thread keeps the 168-register budget the epilogue needs (no setmaxnreg).
 #pragma once
 #include "vt_gemm.cuh"
 
 namespace vt {
 
 constexpr int MLP_D = 384, MLP_H = 1536, MLP_CH = 128, MLP_NCH = MLP_H / MLP_CH;   // 12 hidden chunks
-constexpr int MLP_THREADS = 320;
+constexpr int MLP_THREADS = 384;
+constexpr int MLP_LN_W0 = 2, MLP_LN_WARPS = 2, MLP_EPI_W0 = 4;   // first LayerNorm warp, their number, first epilogue warp
 constexpr int MLP_X_BYTES = 6 * 16384;          // six K atoms of 128 rows x 128 B
 constexpr int MLP_H_BYTES = 2 * 16384;          // H chunk as two K atoms (also the epilogue's transposition scratch)
 constexpr int MLP_W1_SLOT = 64 * 128;           // 64 rows x 128 B (this CTA's half of a W1 chunk atom)
@@ -43,6 +46,13 @@ struct MlpArgs {
   GemmArgs epi;       // output side: out = res = h (fp32, ld D), bias = b2, colscale = ls2, M_total = rows, rows_valid = 128 ...
   int m_tiles;        // 128-row tiles
   int n_pairs;        // ceil(m_tiles / 2) work units
+  // optional: LayerNorm of the updated rows (the NEXT block's norm1, HF:367-372) written as bf16 by the CTA that produced them
+  const float* ln_gamma;   // [D] or null
+  const float* ln_beta;
+  __nv_bfloat16* ln_out;   // [rows][ln_ld]
+  long long ln_ld;
+  float ln_eps;
+  int ln_debug;            // developer knobs (VT_DEBUG_KNOBS builds): 1 no stores, 2 no loads, 4 handshake only
 };
 
 __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const __grid_constant__ MlpArgs a) {
@@ -66,7 +76,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const __grid_
   uint64_t* h_sfree = bars + 21;           // both: MMA2(j) has read the shared-memory H_j
   uint64_t* y_full = bars + 22;            // both: MMA2(11) complete
   uint64_t* y_free = bars + 23;            // leader: every epilogue warp of the pair has read Y
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* ln_go = bars + 24;             // own CTA: the eight epilogue warps have stored their columns of the tile's rows
+  uint64_t* st_free = bars + 25;           // own CTA: the LayerNorm warps have read the row statistics out of the H scratch
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -95,6 +107,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const __grid_
       mbar_init(h_sfree, 1);
       mbar_init(y_full, 1);
       mbar_init(y_free, 16);
+      mbar_init(ln_go, 8);
+      mbar_init(st_free, MLP_LN_WARPS);
       fence_barrier_init();
     }
     __syncwarp();
@@ -207,9 +221,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const __grid_
         umma_commit_pair(y_full, 3);
       }
     }
-  } else {
+  } else if (warp >= MLP_EPI_W0) {
     // ------------------------------ epilogue warps ------------------------------
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int quarter = warp & 3, half = (warp - MLP_EPI_W0) >> 2;
     const int r = quarter * 32 + lane;                       // row of the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const int sw = r & 7;
@@ -219,7 +233,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const __grid_
     const uint32_t yfree_l = mapa_shared(smem_u32(y_free), 0);
     uint32_t ts = 0, cs = 0;
     int dbg_n = 0;
-    const bool ts_on = kDbg && (a.epi.debug & 128) && blockIdx.x == 0 && threadIdx.x == 64;
+    const bool ts_on = kDbg && (a.epi.debug & 128) && blockIdx.x == 0 && threadIdx.x == 32 * MLP_EPI_W0;
     for (int unit = worker; unit < a.n_pairs; unit += n_workers, ++ts) {
       {
         // The residual rows this thread will read in the Y epilogue (twelve chunks = ~25 us from now) are requested from
@@ -254,6 +268,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const __grid_
         }
         dbg_stamp(ts_on, dbg_n, 13);
         mbar_wait(h_sfree, (cs & 1) ^ 1);     // MMA2 of the previous chunk has read the shared-memory H
+        if (j == 0 && ts > 0 && a.ln_out) mbar_wait(st_free, (ts - 1) & 1);   // ... and the LayerNorm warps the statistics in it
         dbg_stamp(ts_on, dbg_n, 14);
 #pragma unroll
         for (int p = 0; p < 8; ++p) st_shared_v4(h_row + ((p ^ sw) << 4), pk[4 * p], pk[4 * p + 1], pk[4 * p + 2], pk[4 * p + 3]);
@@ -276,11 +291,109 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const __grid_
       t.taddr = tmem_Y + lane_off;
       // the last chunk's shared-memory H (which the scratch aliases) has been consumed once y_full completes; the wait is
       // inside the epilogue.  epilogue_linear_t<.., ACT_NONE, true>: y = (acc + b2) * ls2 + h
-      epilogue_linear_t<MLP_D, float, false, ACT_NONE, true>(a.epi, t, xbuf, y_full, ts & 1, half * 192, half * 192 + 192);
-      dbg_n = t.dbg_n;
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(yfree_l);
+      if (!a.ln_out) {
+        epilogue_linear_t<MLP_D, float, false, ACT_NONE, true>(a.epi, t, xbuf, y_full, ts & 1, half * 192, half * 192 + 192);
+        dbg_n = t.dbg_n;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(yfree_l);
+      } else {
+        // ... and the statistics of the next block's LayerNorm1 over the stored values.  After the transposition lane
+        // (sr, cg) holds columns cg*4.. of rows i*4 + sr (i < 8) of every 32-column chunk: sums and sums of squares ride
+        // along in 16 registers, are completed over the 8 lanes of a row segment by shuffles and left in the top 256 B of the
+        // warp's scratch for the LayerNorm warps (no barrier between epilogue warps: the two column halves stay decoupled).
+        float st[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) st[i] = 0.f;
+        epilogue_linear_t<MLP_D, float, false, ACT_NONE, true, true>(a.epi, t, xbuf, y_full, ts & 1, half * 192, half * 192 + 192, st);
+        dbg_n = t.dbg_n;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(yfree_l);
+        const int sr = lane >> 3, cg = lane & 7;
+#pragma unroll
+        for (int m = 1; m < 8; m <<= 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) st[i] += __shfl_xor_sync(0xffffffffu, st[i], m);
+        }
+        if (cg == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) st_shared_v2f(xbuf + 3072 + (i * 4 + sr) * 8, st[2 * i], st[2 * i + 1]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ln_go);   // release: the tile's rows (global) and partial statistics (shared) are written
+      }
+    }
+  } else {
+    // ------------------------------ LayerNorm warps ------------------------------
+    // The next block's norm1 (HF:367-372) of the 128 rows this CTA has just written, while the epilogue warps are already in
+    // the next tile: one warp per row, 64 rows per warp, eight rows in flight from L2; lane l combines the two column halves'
+    // sums of rows 2l, 2l + 1 into (mean, rstd) and hands them out by shuffle.
+    // Replaces a standalone kernel that re-reads the whole fp32 residual stream from HBM (46 us per layer at batch 512).
+    // The SM is issue-bound on the epilogue warps' GELU: every instruction spent here costs; three earlier forms of this
+    // (tail on the epilogue warps, statistics + tail on them, full two-pass LayerNorm on these warps) all cost 46 us.
+    if (a.ln_out) {
+      const int w2 = warp - MLP_LN_W0;
+      const float* hp = reinterpret_cast<const float*>(a.epi.out);
+      float4 g[3], b[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        g[i] = __ldg(reinterpret_cast<const float4*>(a.ln_gamma) + lane + 32 * i);
+        b[i] = __ldg(reinterpret_cast<const float4*>(a.ln_beta) + lane + 32 * i);
+      }
+      const int ldbg = kDbg ? a.ln_debug : 0;
+      uint32_t ts = 0;
+      for (int unit = worker; unit < a.n_pairs; unit += n_workers, ++ts) {
+        const int lrow0 = w2 * (128 / MLP_LN_WARPS);
+        const long long row0 = (long long)(unit * 2 + rank) * 128 + lrow0;
+        mbar_wait_relaxed(ln_go, ts & 1);
+        float2 mr_e[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int lrow = lrow0 + 2 * lane + e;
+          const uint32_t at = smem_u32(sH) + (lrow >> 5) * 4096 + 3072 + (lrow & 31) * 8;
+          const float2 p0 = ld_shared_v2f(at), p1 = ld_shared_v2f(at + 16384);
+          const float mean = (p0.x + p1.x) * (1.0f / MLP_D);
+          const float var = fmaxf((p0.y + p1.y) * (1.0f / MLP_D) - mean * mean, 0.f);
+          const float rstd = rsqrtf(var + a.ln_eps);
+          mr_e[e] = make_float2(rstd, -mean * rstd);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(st_free);
+#pragma unroll 1
+        for (int r8 = (ldbg & 4) ? 1 << 20 : 0; r8 < 128 / MLP_LN_WARPS; r8 += 8) {
+          float4 v[8][3];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const long long row = row0 + r8 + u;
+            const float4* xr = reinterpret_cast<const float4*>(hp + row * a.epi.ldc);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+              v[u][i] = (row < a.epi.M_total && !(ldbg & 2)) ? __ldcg(xr + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const long long row = row0 + r8 + u;
+            const float rs = __shfl_sync(0xffffffffu, mr_e[u & 1].x, (r8 + u) >> 1);
+            const float nm = __shfl_sync(0xffffffffu, mr_e[u & 1].y, (r8 + u) >> 1);
+            const float2 rs2 = make_float2(rs, rs), nm2 = make_float2(nm, nm);
+            if (row < a.epi.M_total && !((ldbg & 1) && rs != 123.456f)) {
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                // (v - mean) * rstd * g + b  with packed fp32 pairs: t = v * rstd - mean * rstd, then t * g + b
+                const float2 t0 = ffma2(make_float2(v[u][i].x, v[u][i].y), rs2, nm2);
+                const float2 t1 = ffma2(make_float2(v[u][i].z, v[u][i].w), rs2, nm2);
+                const float2 y0 = ffma2(t0, make_float2(g[i].x, g[i].y), make_float2(b[i].x, b[i].y));
+                const float2 y1 = ffma2(t1, make_float2(g[i].z, g[i].w), make_float2(b[i].z, b[i].w));
+                uint2 pk;
+                pk.x = pack_bf16x2(y0.x, y0.y);
+                pk.y = pack_bf16x2(y1.x, y1.y);
+                *reinterpret_cast<uint2*>(a.ln_out + row * a.ln_ld + 4 * (lane + 32 * i)) = pk;
+              }
+            }
+          }
+        }
+      }
     }
   }
 

@@ -64,6 +64,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if ((++spins & 0x3FF) == 0 && (clock64() - t0) > 4000000000LL) __trap();
   }
 }
+// The same for warps that are off the critical path and share their scheduler with warps that are on it: sleep between polls.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(256);
+    if ((++spins & 0x3FF) == 0 && (clock64() - t0) > 4000000000LL) __trap();
+  }
+}
 
 // ------------------------------------------------------------------------------------------
 // Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
@@ -414,6 +424,14 @@ __device__ __forceinline__ float4 ld_shared_v4f(uint32_t addr) {
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_shared_v2f(uint32_t addr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ float2 ld_shared_v2f(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

@@ -161,9 +161,13 @@ class DinoProgram:
         lin = dict(rows=M, passes=m.passes)
         # DinoV2-S in bf16 on the GPU: fc1 + GELU + fc2 + LayerScale + residual as ONE kernel (hidden activation stays on chip)
         fused_mlp = (not m.precise and D == 384 and plan.device.type == "cuda" and os.environ.get("VT_FUSED_MLP", "1") != "0")
+        # ... and the NEXT block's norm1 comes out of the same kernel (the CTA re-reads the rows it has just written from L2), so only
+        # the first block runs a standalone norm1
+        fused_ln1 = fused_mlp and os.environ.get("VT_FUSED_LN1", "1") != "0"
         for i in range(W.layers):
             L = f"{tag}.l{i}."
-            ln(0, M, 1, T_[f"{i}.ln1.w"], T_[f"{i}.ln1.b"], xn, m.dt, m.ld(D), m.plane(D), 0, L + "norm1")
+            if i == 0 or not fused_ln1:
+                ln(0, M, 1, T_[f"{i}.ln1.w"], T_[f"{i}.ln1.b"], xn, m.dt, m.ld(D), m.plane(D), 0, L + "norm1")
             plan.add(linear_desc(a=xn, k=D, a_ld=m.ld(D), w=T_[f"{i}.qkv.w"], n=3 * D, n_pad=3 * D,
                                  w_ld=T_[f"{i}.qkv.w"].shape[-1], out=qkv, ldc=3 * D, bias=T_[f"{i}.qkv.b"],
                                  a_plane=m.plane(D), w_plane=D if m.precise else 0, **lin), L + "qkv")
@@ -181,7 +185,10 @@ class DinoProgram:
                 d.w1, d.w1_ld, d.b1 = ptr(T_[f"{i}.fc1.w"]), T_[f"{i}.fc1.w"].shape[-1], ptr(T_[f"{i}.fc1.b"])
                 d.w2, d.w2_ld, d.b2 = ptr(T_[f"{i}.fc2.w"]), T_[f"{i}.fc2.w"].shape[-1], ptr(T_[f"{i}.fc2.b"])
                 d.ls2, d.h, d.ld_h, d.rows, d.D = ptr(T_[f"{i}.ls2"]), ptr(h), D, M, D
-                plan.add(d, L + "mlp(fc1+gelu+fc2+ls2+res)")
+                if fused_ln1 and i + 1 < W.layers:
+                    d.ln_gamma, d.ln_beta = ptr(T_[f"{i + 1}.ln1.w"]), ptr(T_[f"{i + 1}.ln1.b"])
+                    d.ln_out, d.ln_ld, d.ln_eps = ptr(xn), m.ld(D), 1e-6
+                plan.add(d, L + ("mlp(fc1+gelu+fc2+ls2+res)+next.norm1" if d.ln_out else "mlp(fc1+gelu+fc2+ls2+res)"))
                 continue
             plan.add(linear_desc(a=xn, k=D, a_ld=m.ld(D), w=T_[f"{i}.fc1.w"], n=4 * D, n_pad=4 * D,
                                  w_ld=T_[f"{i}.fc1.w"].shape[-1], out=hid, ldc=m.ld(4 * D), bias=T_[f"{i}.fc1.b"],

@@ -18,7 +18,7 @@ ACT_NONE, ACT_GELU, ACT_MISH = 0, 1, 2
 EPI_LINEAR, EPI_GN = 0, 1
 LAYOUT_BHWC, LAYOUT_BCHW = 0, 1
 MAX_TAPS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 i32, i64, f32, u64, vp = C.c_int32, C.c_int64, C.c_float, C.c_uint64, C.c_void_p
 
@@ -53,7 +53,8 @@ class AttnDesc(C.Structure):
 
 class MlpDesc(C.Structure):
     _fields_ = [("xn", vp), ("ld_x", i64), ("w1", vp), ("w1_ld", i64), ("b1", vp), ("w2", vp), ("w2_ld", i64), ("b2", vp),
-                ("ls2", vp), ("h", vp), ("ld_h", i64), ("rows", i32), ("D", i32)]
+                ("ls2", vp), ("h", vp), ("ld_h", i64), ("rows", i32), ("D", i32),
+                ("ln_gamma", vp), ("ln_beta", vp), ("ln_out", vp), ("ln_ld", i64), ("ln_eps", C.c_float)]
 
 
 class ImgStatsDesc(C.Structure):
