@@ -173,6 +173,8 @@ def gemm_flops(d):
     """FLOPs of one tensor-core launch: an implicit GEMM, or the fused ViT MLP (two GEMMs rows x D x 4D)."""
     if hasattr(d, "w2"):                       # MlpDesc
         return 2.0 * 2.0 * d.rows * d.D * 4 * d.D
+    if hasattr(d, "colscale") and hasattr(d, "ln_out"):   # RowprojDesc: rows x D x D
+        return 2.0 * d.rows * d.D * d.D
     return 2.0 * d.G * d.M * d.N * d.taps * d.kc * d.passes
 
 
@@ -185,6 +187,8 @@ def op_kind(d):
              else "gemm_tc_kernel<linear epilogue> (ViT / encoder linears)")
     if isinstance(d, nv.MlpDesc):
         return "mlp_fused_kernel (ViT fc1+GELU+fc2)"
+    if isinstance(d, nv.RowprojDesc):
+        return "rowproj_kernel (ViT attention out-projection + norm2)"
     if isinstance(d, nv.AttnDesc):
         return "attn_row_kernel (ViT attention)"
     if isinstance(d, nv.PersistDesc):
@@ -320,7 +324,7 @@ def roofline_block(cx, eng, wl, workload, value, world):
         k["launches"] += 1
         if isinstance(d, nv.PersistDesc):
             k["flops"] += d.algo_flops
-        elif isinstance(d, (nv.GemmDesc, nv.MlpDesc)):
+        elif isinstance(d, (nv.GemmDesc, nv.MlpDesc, nv.RowprojDesc)):
             k["flops"] += gemm_flops(d)
         elif isinstance(d, nv.AttnDesc):
             k["flops"] += 4.0 * d.tokens * d.tokens * 64 * d.heads * d.images

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VT_ABI_VERSION 3
+#define VT_ABI_VERSION 4
 
 enum { VT_OK = 0, VT_E_INVALID = -1, VT_E_CUDA = -2, VT_E_UNSUPPORTED = -3, VT_E_NODEVICE = -4 };
 enum { VT_BF16 = 0, VT_F32 = 1, VT_U8 = 2 };
@@ -159,6 +159,26 @@ typedef struct vt_mlp_desc {
   int64_t ln_ld;
   float ln_eps;
 } vt_mlp_desc;
+
+/* Attention output projection of a DinoV2-S block with whole 384-wide rows per CTA (HF Dinov2SelfOutput + layer_scale1 + residual,
+ * HF:238-251,374-378):  h += colscale * (x W^T + bias);  optionally the block's norm2 (HF:380-381) of the updated rows as bf16 from
+ * the same kernel.  D must be 384.  Means exactly what a GEMM descriptor with bias, colscale, res = out = h followed by a LayerNorm descriptor means. */
+typedef struct vt_rowproj_desc {
+  const void* x;         /* bf16 [rows][ld_x]: attention context */
+  int64_t ld_x;
+  const void* w;         /* bf16 [D][w_ld], K contiguous (nn.Linear weight) */
+  int64_t w_ld;
+  const float* bias;     /* [D] */
+  const float* colscale; /* [D] LayerScale, or NULL */
+  float* h;              /* fp32 [rows][ld_h] residual stream, updated in place */
+  int64_t ld_h;
+  int32_t rows, D;
+  const float* ln_gamma; /* optional (ln_out != NULL): LayerNorm(h_new) * ln_gamma + ln_beta as bf16 */
+  const float* ln_beta;
+  void* ln_out;          /* bf16 [rows][ln_ld] */
+  int64_t ln_ld;
+  float ln_eps;
+} vt_rowproj_desc;
 
 /* visual_encoder.py:66-81,95-106: batch-global predicates max>1 and mean<0.5, evaluated on the device. */
 typedef struct vt_imgstats_desc {
@@ -553,6 +573,7 @@ int vt_program_add_gemm(vt_program* p, const vt_gemm_desc* d);
 int vt_program_add_layernorm(vt_program* p, const vt_ln_desc* d);
 int vt_program_add_attention(vt_program* p, const vt_attn_desc* d);
 int vt_program_add_mlp(vt_program* p, const vt_mlp_desc* d);
+int vt_program_add_rowproj(vt_program* p, const vt_rowproj_desc* d);
 /* developer instrumentation (VT_GEMM_DEBUG bit 128): (tag, clock64) pairs of one epilogue warp; returns the entry count */
 int vt_debug_timestamps(long long* out, int max_entries);
 /* developer instrumentation (debug-knobs builds, VT_GEMM_DEBUG bit 512): timeline of the persistent multi-layer kernel.

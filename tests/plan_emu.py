@@ -165,6 +165,27 @@ def emu_mlp(plan, d: nv.MlpDesc):
         of[(r[:, None] * d.ln_ld + torch.arange(D)[None, :]).reshape(-1)] = yn.reshape(-1)
 
 
+def emu_rowproj(plan, d: nv.RowprojDesc):
+    """h += colscale * (x W^T + bias), then (optionally) LayerNorm of the updated rows as bf16: what the attn_out GEMM descriptor
+    followed by the norm2 LayerNorm descriptor compute."""
+    D = d.D
+    r = torch.arange(d.rows)
+    x = _flat(plan, d.x, torch.bfloat16)[(r[:, None] * d.ld_x + torch.arange(D)[None, :]).reshape(-1)].reshape(d.rows, D).float()
+    w = _flat(plan, d.w, torch.bfloat16)[(torch.arange(D)[:, None] * d.w_ld + torch.arange(D)[None, :]).reshape(-1)].reshape(D, D).float()
+    y = x @ w.t() + _flat(plan, d.bias, torch.float32)[:D]
+    if d.colscale:
+        y = y * _flat(plan, d.colscale, torch.float32)[:D]
+    hf = _flat(plan, d.h, torch.float32)
+    idx = (r[:, None] * d.ld_h + torch.arange(D)[None, :]).reshape(-1)
+    hn = y + hf[idx].reshape(d.rows, D)
+    hf[idx] = hn.reshape(-1)
+    if d.ln_out:
+        g, b = _flat(plan, d.ln_gamma, torch.float32)[:D], _flat(plan, d.ln_beta, torch.float32)[:D]
+        yn = F.layer_norm(hn, (D,), g, b, d.ln_eps).to(torch.bfloat16)
+        of = _flat(plan, d.ln_out, torch.bfloat16)
+        of[(r[:, None] * d.ln_ld + torch.arange(D)[None, :]).reshape(-1)] = yn.reshape(-1)
+
+
 def emu_imgstats(plan, d: nv.ImgStatsDesc):
     img = _flat(plan, d.img, TORCH_DT[d.dtype])[: d.count]
     mx = float(img.max())
@@ -520,7 +541,7 @@ def emu_persist(plan, d: nv.PersistDesc):
 
 _EMU = {nv.WgradDesc: emu_wgrad, nv.PersistDesc: emu_persist, nv.QsampleDesc: emu_qsample, nv.SilossDesc: emu_siloss, nv.GemmDesc: emu_gemm, nv.LnDesc: emu_layernorm, nv.AttnDesc: emu_attention, nv.ImgStatsDesc: emu_imgstats,
         nv.PatchifyDesc: emu_patchify, nv.ClsDesc: emu_cls, nv.PackDesc: emu_pack, nv.AffineDesc: emu_affine,
-        nv.TcolDesc: emu_tcol, nv.GnbwdDesc: emu_gnbwd, nv.ColsumDesc: emu_colsum, nv.EwiseDesc: emu_ewise, nv.SilossBwdDesc: emu_silossbwd, nv.LstmTrainDesc: emu_lstm_train, nv.LstmBwdDesc: emu_lstm_bwd, nv.LnGeluBwdDesc: emu_lngelubwd, nv.DropmaskDesc: emu_dropmask, nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm, nv.MlpDesc: emu_mlp}
+        nv.TcolDesc: emu_tcol, nv.GnbwdDesc: emu_gnbwd, nv.ColsumDesc: emu_colsum, nv.EwiseDesc: emu_ewise, nv.SilossBwdDesc: emu_silossbwd, nv.LstmTrainDesc: emu_lstm_train, nv.LstmBwdDesc: emu_lstm_bwd, nv.LnGeluBwdDesc: emu_lngelubwd, nv.DropmaskDesc: emu_dropmask, nv.TembedDesc: emu_tembed, nv.SdeDesc: emu_sde, nv.LstmDesc: emu_lstm, nv.MlpDesc: emu_mlp, nv.RowprojDesc: emu_rowproj}
 
 
 @torch.no_grad()

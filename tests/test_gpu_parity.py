@@ -481,6 +481,52 @@ def test_fused_mlp_matches_reference_math(rows):
     assert (lerr <= 2.0 ** -7 * want.abs() + 1e-3).all(), (rows, lerr.max().item())
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows", [128, 257, 4 * 257, 150 * 257])
+def test_rowproj_matches_reference_math(rows):
+    """rowproj_kernel (attention output projection + LayerScale + residual with whole rows per CTA, and the block's norm2 from
+    the same kernel; HF:238-251,374-381) against the same math in fp32 on the bf16-rounded operands."""
+    from vla_touch_b200 import native as nv
+    from vla_touch_b200.plan import Plan, ptr
+    D = 384
+    g = torch.Generator().manual_seed(rows)
+    ctx32 = torch.randn(rows, D, generator=g)
+    w = (torch.randn(D, D, generator=g) / D ** 0.5).bfloat16()
+    b, ls = torch.randn(D, generator=g) * 0.1, torch.rand(D, generator=g) + 0.5
+    h0 = torch.randn(rows, D, generator=g)
+    h0[:, 7] += 40.0                                  # an outlier channel, as the DinoV2 residual stream has
+    h0 += torch.randn(rows, 1, generator=g) * 3.0     # and rows whose mean is not small against their spread
+    lg, lb = torch.rand(D, generator=g) + 0.5, torch.randn(D, generator=g) * 0.1
+    for with_ln in (True, False):
+        plan = Plan(torch.device(DEV))
+        ctx = plan.buf("ctx", (rows, D), torch.bfloat16)
+        h = plan.buf("h", (rows, D), torch.float32)
+        ln = plan.buf("ln", (rows, D), torch.bfloat16)
+        ctx.copy_(ctx32)
+        h.copy_(h0)
+        ln.fill_(-7.0)
+        t = {k: plan.reg(v.to(DEV).contiguous()) for k, v in dict(w=w, b=b, ls=ls, lg=lg, lb=lb).items()}
+        d = nv.RowprojDesc()
+        d.x, d.ld_x, d.w, d.w_ld, d.bias, d.colscale = ptr(ctx), D, ptr(t["w"]), D, ptr(t["b"]), ptr(t["ls"])
+        d.h, d.ld_h, d.rows, d.D = ptr(h), D, rows, D
+        if with_ln:
+            d.ln_gamma, d.ln_beta, d.ln_out, d.ln_ld, d.ln_eps = ptr(t["lg"]), ptr(t["lb"]), ptr(ln), D, 1e-6
+        plan.add(d, "rowproj")
+        plan.compile().run(0, 1)
+        torch.cuda.synchronize()
+        ref = h0 + ls * (ctx.float().cpu() @ w.float().t() + b)
+        got = h.cpu()
+        assert torch.isfinite(got).all()
+        err = (got - ref).abs().max().item()
+        assert err <= 2e-3 * ref.abs().max().item(), (rows, err, ref.abs().max().item())     # fp32 accumulation of bf16 products
+        if with_ln:
+            want = torch.nn.functional.layer_norm(got, (D,), lg, lb, 1e-6)
+            lerr = (ln.float().cpu() - want).abs()
+            assert (lerr <= 2.0 ** -7 * want.abs() + 1e-3).all(), (rows, lerr.max().item())
+        else:
+            assert (ln == -7.0).all()
+
+
 def test_pad_and_resize_for_siglip_is_bit_identical_to_cv2():
     """image_ops.pad_and_resize_for_siglip (csrc/vt_resize.cuh) against the reference function's own outputs (cv2 INTER_AREA,
     tests/golden/resize_*.npz): every down-scaling path, numpy / CPU-tensor / CUDA-tensor inputs, a batch, the deployment frame size."""

@@ -58,7 +58,7 @@ def test_ctypes_structs_match_the_c_header():
              "vt_pack_desc": nv.PackDesc, "vt_affine_desc": nv.AffineDesc, "vt_tembed_desc": nv.TembedDesc,
              "vt_sde_desc": nv.SdeDesc, "vt_lstm_desc": nv.LstmDesc, "vt_qsample_desc": nv.QsampleDesc,
              "vt_siloss_desc": nv.SilossDesc, "vt_opt_tensor": nv.OptTensor, "vt_adamw_desc": nv.AdamwDesc,
-             "vt_mlp_desc": nv.MlpDesc, "vt_tcol_desc": nv.TcolDesc, "vt_gnbwd_desc": nv.GnbwdDesc,
+             "vt_mlp_desc": nv.MlpDesc, "vt_rowproj_desc": nv.RowprojDesc, "vt_tcol_desc": nv.TcolDesc, "vt_gnbwd_desc": nv.GnbwdDesc,
              "vt_colsum_desc": nv.ColsumDesc, "vt_ewise_desc": nv.EwiseDesc, "vt_silossbwd_desc": nv.SilossBwdDesc, "vt_lstm_train_desc": nv.LstmTrainDesc,
              "vt_lstm_bwd_desc": nv.LstmBwdDesc, "vt_lngelubwd_desc": nv.LnGeluBwdDesc, "vt_dropmask_desc": nv.DropmaskDesc,
              "vt_persist_desc": nv.PersistDesc, "vt_wgrad_desc": nv.WgradDesc}
@@ -261,6 +261,44 @@ def test_fused_mlp_descriptor_equals_the_two_gemm_descriptors():
         plan_emu.run(plan)
         outs.append(h.clone())
     assert torch.equal(outs[0], outs[1])
+
+
+def test_rowproj_descriptor_equals_the_gemm_and_layernorm_descriptors():
+    """vt_rowproj_desc (one whole-row kernel on the GPU) means exactly what the attention output projection GEMM descriptor
+    (bias, LayerScale, residual) followed by the norm2 LayerNorm descriptor mean (HF:238-251,374-381)."""
+    from vla_touch_b200.plan import Plan, linear_desc, pack_linear_weight, ptr
+    D, rows = 384, 150
+    g = torch.Generator().manual_seed(7)
+    w = torch.randn(D, D, generator=g) / D ** 0.5
+    outs = []
+    for fused in (True, False):
+        plan = Plan(torch.device("cpu"))
+        ctx = plan.buf("ctx", (rows, D), torch.bfloat16)
+        xn = plan.buf("xn", (rows, D), torch.bfloat16)
+        h = plan.buf("h", (rows, D), torch.float32)
+        gg = torch.Generator().manual_seed(8)
+        ctx.copy_(torch.randn(rows, D, generator=gg))
+        h.copy_(torch.randn(rows, D, generator=gg) * 3)
+        wp, n1, k1 = pack_linear_weight(w, torch.bfloat16)
+        t = {k: plan.reg(v) for k, v in dict(w=wp, b=torch.linspace(-1, 1, D), ls=torch.linspace(0.5, 1.5, D),
+                                             lg=torch.linspace(0.8, 1.2, D), lb=torch.linspace(-0.1, 0.1, D)).items()}
+        if fused:
+            d = nv.RowprojDesc()
+            d.x, d.ld_x, d.w, d.w_ld, d.bias, d.colscale = ptr(ctx), D, ptr(t["w"]), k1, ptr(t["b"]), ptr(t["ls"])
+            d.h, d.ld_h, d.rows, d.D = ptr(h), D, rows, D
+            d.ln_gamma, d.ln_beta, d.ln_out, d.ln_ld, d.ln_eps = ptr(t["lg"]), ptr(t["lb"]), ptr(xn), D, 1e-6
+            plan.add(d, "rowproj")
+        else:
+            plan.add(linear_desc(a=ctx, rows=rows, k=k1, a_ld=D, w=t["w"], n=D, n_pad=n1, w_ld=k1, out=h, ldc=D, bias=t["b"],
+                                 colscale=t["ls"], res=h, ldres=D), "attn_out")
+            d = nv.LnDesc()
+            d.x, d.in_ld, d.in_row_stride, d.rows, d.D = ptr(h), D, 1, rows, D
+            d.gamma, d.beta, d.eps = ptr(t["lg"]), ptr(t["lb"]), 1e-6
+            d.out, d.out_dtype, d.out_ld, d.out_plane, d.act = ptr(xn), nv.VT_BF16, D, 0, nv.ACT_NONE
+            plan.add(d, "norm2")
+        plan_emu.run(plan)
+        outs.append((h.clone(), xn.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
 def test_dgrad_descriptors_reproduce_the_explicit_backward():

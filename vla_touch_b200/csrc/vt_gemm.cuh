@@ -380,6 +380,9 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, EpiTile& t,
   };
   const bool ts_on = (dbg & 128) && blockIdx.x == 0 && threadIdx.x == 64;
   dbg_stamp(ts_on, t.dbg_n, 1);
+  // STATS: the rows are read back from L2 by the LayerNorm warps within one tile time; without the hint 60 % of them have been
+  // written back and evicted by then (ncu: +121 MB dram__bytes_read per launch at batch 512)
+  const uint64_t st_policy = STATS ? l2_policy_evict_last() : 0ull;
   if constexpr (HAS_RES) {
     // Row `lane` of this warp's 32 rows: ask for its residual columns in L2 now (one bulk prefetch per lane), so that the
     // per-chunk loads below are L2 hits; the first chunk's loads are issued before the accumulator is ready.
@@ -468,7 +471,8 @@ __device__ __forceinline__ void epilogue_linear_t(const GemmArgs& a, EpiTile& t,
         if (y[0].x == 123.456f) outp[ooff[i] + c] = TOut(y[0].y);
       } else if ((vmask >> i) & 1) {
         if constexpr (sizeof(TOut) == 4) {
-          *reinterpret_cast<float4*>(outp + ooff[i] + c) = y[0];
+          if constexpr (STATS) st_global_v4f_hint(reinterpret_cast<float*>(outp + ooff[i] + c), y[0], st_policy);   // read back soon
+          else *reinterpret_cast<float4*>(outp + ooff[i] + c) = y[0];
         } else {
           uint4 w;
           w.x = pack_bf16x2(y[0].x, y[0].y);

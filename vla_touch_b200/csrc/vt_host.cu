@@ -15,6 +15,7 @@
 #include "../../include/vt_b200.h"
 #include "vt_attn.cuh"
 #include "vt_mlp.cuh"
+#include "vt_rowproj.cuh"
 #include "vt_elem.cuh"
 #include "vt_gemm.cuh"
 #include "vt_persist.cuh"
@@ -502,6 +503,23 @@ struct MlpOp : Op {
     cudaError_t e = launch_ex(vt::mlp_fused_kernel, grid, dim3(vt::MLP_THREADS, 1, 1), (size_t)vt::MLP_SMEM_BYTES, s, true, true, args);
     if (e != cudaSuccess) return fail(VT_E_CUDA, "mlp_fused_kernel launch: %s", cudaGetErrorString(e));
     VT_LAUNCH_CHECK("mlp_fused_kernel");
+    return VT_OK;
+  }
+};
+
+// ---- whole-row output projection + LayerNorm ----
+struct RowprojOp : Op {
+  vt::RowprojArgs args;
+  dim3 grid;
+  int launch(cudaStream_t s) override {
+    static bool attr_set = false;
+    if (!attr_set) {
+      VT_CUDA(cudaFuncSetAttribute(vt::rowproj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vt::RP_SMEM_BYTES));
+      attr_set = true;
+    }
+    cudaError_t e = launch_ex(vt::rowproj_kernel, grid, dim3(vt::RP_THREADS, 1, 1), (size_t)vt::RP_SMEM_BYTES, s, true, true, args);
+    if (e != cudaSuccess) return fail(VT_E_CUDA, "rowproj_kernel launch: %s", cudaGetErrorString(e));
+    VT_LAUNCH_CHECK("rowproj_kernel");
     return VT_OK;
   }
 };
@@ -1254,6 +1272,66 @@ int vt_program_add_mlp(vt_program* p, const vt_mlp_desc* d) {
     a.ln_eps = d->ln_eps;
     const char* ldbg = VT_DEBUG_KNOBS ? getenv("VT_MLP_LN_DEBUG") : nullptr;
     a.ln_debug = ldbg ? atoi(ldbg) : 0;
+  }
+  const int workers = sm_count() / 2;
+  op->grid = dim3((unsigned)(a.n_pairs < workers ? a.n_pairs : workers) * 2u, 1u, 1u);
+  p->ops.push_back(std::move(op));
+  return VT_OK;
+}
+
+int vt_program_add_rowproj(vt_program* p, const vt_rowproj_desc* d) {
+  if (!p || !d) return fail(VT_E_INVALID, "null argument");
+  VT_REQUIRE(d->x && d->w && d->bias && d->h && d->rows >= 1, "rowproj: bad descriptor");
+  VT_REQUIRE(d->D == vt::RP_D, "rowproj: the kernel is built for D = %d (got %d)", vt::RP_D, d->D);
+  VT_REQUIRE(d->ld_x >= d->D && d->ld_x % 8 == 0 && d->w_ld >= d->D && d->w_ld % 8 == 0, "rowproj: leading dimensions");
+  VT_REQUIRE(d->ld_h >= d->D && d->ld_h % 4 == 0 && aligned16(d->h) && aligned16(d->bias) && (!d->colscale || aligned16(d->colscale)),
+             "rowproj: fp32 operands must be 16-byte aligned");
+  VT_REQUIRE((long long)d->rows * d->ld_h < (1ll << 31), "rowproj: residual stream too large for 32-bit offsets");
+  std::unique_ptr<RowprojOp> op(new RowprojOp());
+  vt::RowprojArgs& a = op->args;
+  memset(&a, 0, sizeof(a));
+  {
+    const uint64_t dims[2] = {(uint64_t)d->D, (uint64_t)d->rows};
+    const uint64_t st[1] = {(uint64_t)d->ld_x * 2};
+    const uint32_t box[2] = {64u, 128u};
+    int rc = make_tmap(&a.tmX, VT_BF16, 2, d->x, dims, st, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)d->D, (uint64_t)d->D};
+    const uint64_t st[1] = {(uint64_t)d->w_ld * 2};
+    const uint32_t box[2] = {64u, 32u};
+    int rc = make_tmap(&a.tmW, VT_BF16, 2, d->w, dims, st, box);
+    if (rc) return rc;
+  }
+  vt::GemmArgs& e = a.epi;
+  e.M_total = d->rows;
+  e.N = d->D;
+  e.n_pad = d->D;
+  e.rows_valid = 128;
+  e.row_div = 1;
+  e.out_q = 1;
+  e.res_q = 1;
+  e.ldc = (int)d->ld_h;
+  e.ldres = (int)d->ld_h;
+  e.out = d->h;
+  e.res = d->h;
+  e.bias = d->bias;
+  e.colscale = d->colscale;
+  e.act = VT_ACT_NONE;
+  e.vec = 1;
+  e.fast = 1;
+  a.m_tiles = (d->rows + 127) / 128;
+  a.n_pairs = (a.m_tiles + 1) / 2;
+  if (d->ln_out) {
+    VT_REQUIRE(d->ln_gamma && d->ln_beta && d->ln_ld >= d->D && d->ln_ld % 4 == 0 && aligned16(d->ln_out) && aligned16(d->ln_gamma) &&
+                   aligned16(d->ln_beta),
+               "rowproj: fused LayerNorm output needs 16-byte aligned rows / vectors");
+    a.ln_gamma = d->ln_gamma;
+    a.ln_beta = d->ln_beta;
+    a.ln_out = reinterpret_cast<__nv_bfloat16*>(d->ln_out);
+    a.ln_ld = d->ln_ld;
+    a.ln_eps = d->ln_eps;
   }
   const int workers = sm_count() / 2;
   op->grid = dim3((unsigned)(a.n_pairs < workers ? a.n_pairs : workers) * 2u, 1u, 1u);

@@ -55,6 +55,82 @@ struct MlpArgs {
   int ln_debug;            // developer knobs (VT_DEBUG_KNOBS builds): 1 no stores, 2 no loads, 4 handshake only
 };
 
+
+// ---- LayerNorm of finished 384-wide rows by a warp that is off the critical path (shared with vt_rowproj.cuh) ----
+// (sum, sum of squares) of the two column halves of a row -> (rstd, -mean * rstd)
+__device__ __forceinline__ float2 ln_finish_stats(float2 p0, float2 p1, float eps) {
+  const float mean = (p0.x + p1.x) * (1.0f / 384.0f);
+  const float var = fmaxf((p0.y + p1.y) * (1.0f / 384.0f) - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  return make_float2(rstd, -mean * rstd);
+}
+// NROWS consecutive rows from `row0`.  NROWS = 64: lane l holds the statistics of rows 2l (mr0) and 2l + 1 (mr1); NROWS = 32:
+// of row l (mr0).  One warp per row, eight rows in flight from L2, (v * rstd - mean * rstd) * g + b in packed fp32 pairs, bf16
+// out: ~35 instructions per row.  HOLD_GB keeps gamma / beta in 24 registers instead of re-reading them from L1.
+template <int NROWS, bool HOLD_GB>
+__device__ __forceinline__ void ln_warp_rows(const float* hp, long long ldh, long long m_total, long long row0, float2 mr0, float2 mr1,
+                                             const float* gamma, const float* beta, __nv_bfloat16* out, long long ldo, int lane,
+                                             int ldbg) {
+  static_assert(NROWS == 64 || NROWS == 32, "statistics layout");
+  float4 g[3], b[3];
+  if constexpr (HOLD_GB) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+      b[i] = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+    }
+  }
+#pragma unroll 1
+  for (int r8 = (ldbg & 4) ? 1 << 20 : 0; r8 < NROWS; r8 += 8) {
+    float4 v[8][3];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const long long row = row0 + r8 + u;
+      const float4* xr = reinterpret_cast<const float4*>(hp + row * ldh);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) v[u][i] = (row < m_total && !(ldbg & 2)) ? __ldcg(xr + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const long long row = row0 + r8 + u;
+      const int owner = NROWS == 64 ? (r8 + u) >> 1 : r8 + u;
+      const float rs = __shfl_sync(0xffffffffu, (NROWS == 64 && (u & 1)) ? mr1.x : mr0.x, owner);
+      const float nm = __shfl_sync(0xffffffffu, (NROWS == 64 && (u & 1)) ? mr1.y : mr0.y, owner);
+      const float2 rs2 = make_float2(rs, rs), nm2 = make_float2(nm, nm);
+      if (row < m_total && !((ldbg & 1) && rs != 123.456f)) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          if constexpr (!HOLD_GB) {
+            g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+            b[i] = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+          }
+          const float2 t0 = ffma2(make_float2(v[u][i].x, v[u][i].y), rs2, nm2);
+          const float2 t1 = ffma2(make_float2(v[u][i].z, v[u][i].w), rs2, nm2);
+          const float2 y0 = ffma2(t0, make_float2(g[i].x, g[i].y), make_float2(b[i].x, b[i].y));
+          const float2 y1 = ffma2(t1, make_float2(g[i].z, g[i].w), make_float2(b[i].z, b[i].w));
+          uint2 pk;
+          pk.x = pack_bf16x2(y0.x, y0.y);
+          pk.y = pack_bf16x2(y1.x, y1.y);
+          *reinterpret_cast<uint2*>(out + row * ldo + 4 * (lane + 32 * i)) = pk;
+        }
+      }
+    }
+  }
+}
+// Epilogue side: st[2i] / st[2i + 1] (sum, sum of squares of this lane's four columns of row i*4 + sr, all chunks) are completed
+// over the 8 lanes of a row segment; lanes cg == 0 leave the 32 rows' partials at `dst` (256 B of shared memory).
+__device__ __forceinline__ void ln_store_partials(float (&st)[16], uint32_t dst, int lane) {
+#pragma unroll
+  for (int m = 1; m < 8; m <<= 1) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) st[i] += __shfl_xor_sync(0xffffffffu, st[i], m);
+  }
+  if ((lane & 7) == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) st_shared_v2f(dst + (i * 4 + (lane >> 3)) * 8, st[2 * i], st[2 * i + 1]);
+  }
+}
+
 __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const __grid_constant__ MlpArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -310,16 +386,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(yfree_l);
-        const int sr = lane >> 3, cg = lane & 7;
-#pragma unroll
-        for (int m = 1; m < 8; m <<= 1) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) st[i] += __shfl_xor_sync(0xffffffffu, st[i], m);
-        }
-        if (cg == 0) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) st_shared_v2f(xbuf + 3072 + (i * 4 + sr) * 8, st[2 * i], st[2 * i + 1]);
-        }
+        ln_store_partials(st, xbuf + 3072, lane);
         __syncwarp();
         if (lane == 0) mbar_arrive(ln_go);   // release: the tile's rows (global) and partial statistics (shared) are written
       }
@@ -334,65 +401,19 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const __grid_
     // (tail on the epilogue warps, statistics + tail on them, full two-pass LayerNorm on these warps) all cost 46 us.
     if (a.ln_out) {
       const int w2 = warp - MLP_LN_W0;
-      const float* hp = reinterpret_cast<const float*>(a.epi.out);
-      float4 g[3], b[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        g[i] = __ldg(reinterpret_cast<const float4*>(a.ln_gamma) + lane + 32 * i);
-        b[i] = __ldg(reinterpret_cast<const float4*>(a.ln_beta) + lane + 32 * i);
-      }
+      static_assert(MLP_LN_WARPS == 2, "ln_warp_rows<64>: 64 rows per LayerNorm warp");
       const int ldbg = kDbg ? a.ln_debug : 0;
       uint32_t ts = 0;
       for (int unit = worker; unit < a.n_pairs; unit += n_workers, ++ts) {
-        const int lrow0 = w2 * (128 / MLP_LN_WARPS);
-        const long long row0 = (long long)(unit * 2 + rank) * 128 + lrow0;
+        const int lrow = w2 * 64 + 2 * lane;     // this lane finishes the statistics of tile rows lrow, lrow + 1
+        const uint32_t at = smem_u32(sH) + (lrow >> 5) * 4096 + 3072 + (lrow & 31) * 8;
         mbar_wait_relaxed(ln_go, ts & 1);
-        float2 mr_e[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int lrow = lrow0 + 2 * lane + e;
-          const uint32_t at = smem_u32(sH) + (lrow >> 5) * 4096 + 3072 + (lrow & 31) * 8;
-          const float2 p0 = ld_shared_v2f(at), p1 = ld_shared_v2f(at + 16384);
-          const float mean = (p0.x + p1.x) * (1.0f / MLP_D);
-          const float var = fmaxf((p0.y + p1.y) * (1.0f / MLP_D) - mean * mean, 0.f);
-          const float rstd = rsqrtf(var + a.ln_eps);
-          mr_e[e] = make_float2(rstd, -mean * rstd);
-        }
+        const float2 mr0 = ln_finish_stats(ld_shared_v2f(at), ld_shared_v2f(at + 16384), a.ln_eps);
+        const float2 mr1 = ln_finish_stats(ld_shared_v2f(at + 8), ld_shared_v2f(at + 16384 + 8), a.ln_eps);
         __syncwarp();
         if (lane == 0) mbar_arrive(st_free);
-#pragma unroll 1
-        for (int r8 = (ldbg & 4) ? 1 << 20 : 0; r8 < 128 / MLP_LN_WARPS; r8 += 8) {
-          float4 v[8][3];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const long long row = row0 + r8 + u;
-            const float4* xr = reinterpret_cast<const float4*>(hp + row * a.epi.ldc);
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-              v[u][i] = (row < a.epi.M_total && !(ldbg & 2)) ? __ldcg(xr + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const long long row = row0 + r8 + u;
-            const float rs = __shfl_sync(0xffffffffu, mr_e[u & 1].x, (r8 + u) >> 1);
-            const float nm = __shfl_sync(0xffffffffu, mr_e[u & 1].y, (r8 + u) >> 1);
-            const float2 rs2 = make_float2(rs, rs), nm2 = make_float2(nm, nm);
-            if (row < a.epi.M_total && !((ldbg & 1) && rs != 123.456f)) {
-#pragma unroll
-              for (int i = 0; i < 3; ++i) {
-                // (v - mean) * rstd * g + b  with packed fp32 pairs: t = v * rstd - mean * rstd, then t * g + b
-                const float2 t0 = ffma2(make_float2(v[u][i].x, v[u][i].y), rs2, nm2);
-                const float2 t1 = ffma2(make_float2(v[u][i].z, v[u][i].w), rs2, nm2);
-                const float2 y0 = ffma2(t0, make_float2(g[i].x, g[i].y), make_float2(b[i].x, b[i].y));
-                const float2 y1 = ffma2(t1, make_float2(g[i].z, g[i].w), make_float2(b[i].z, b[i].w));
-                uint2 pk;
-                pk.x = pack_bf16x2(y0.x, y0.y);
-                pk.y = pack_bf16x2(y1.x, y1.y);
-                *reinterpret_cast<uint2*>(a.ln_out + row * a.ln_ld + 4 * (lane + 32 * i)) = pk;
-              }
-            }
-          }
-        }
+        ln_warp_rows<64, true>(reinterpret_cast<const float*>(a.epi.out), a.epi.ldc, a.epi.M_total, (long long)(unit * 2 + rank) * 128 + w2 * 64,
+                       mr0, mr1, a.ln_gamma, a.ln_beta, a.ln_out, a.ln_ld, lane, ldbg);
       }
     }
   }

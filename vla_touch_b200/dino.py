@@ -164,6 +164,8 @@ class DinoProgram:
         # ... and the NEXT block's norm1 comes out of the same kernel (the CTA re-reads the rows it has just written from L2), so only
         # the first block runs a standalone norm1
         fused_ln1 = fused_mlp and os.environ.get("VT_FUSED_LN1", "1") != "0"
+        # ... and norm2 out of the attention output projection: rowproj_kernel owns whole 384-wide rows (csrc/vt_rowproj.cuh)
+        fused_ln2 = fused_mlp and os.environ.get("VT_FUSED_LN2", "1") != "0"
         for i in range(W.layers):
             L = f"{tag}.l{i}."
             if i == 0 or not fused_ln1:
@@ -175,10 +177,18 @@ class DinoProgram:
             d.qkv, d.ctx, d.in_dtype, d.images, d.tokens, d.heads = ptr(qkv), ptr(ctx), m.dt, images, N, W.heads
             d.ctx_ld, d.ctx_plane = m.ld(D), m.plane(D)
             plan.add(d, L + "attention")
-            plan.add(linear_desc(a=ctx, k=D, a_ld=m.ld(D), w=T_[f"{i}.o.w"], n=D, n_pad=D, w_ld=T_[f"{i}.o.w"].shape[-1],
-                                 out=h, ldc=D, bias=T_[f"{i}.o.b"], colscale=T_[f"{i}.ls1"], res=h, ldres=D,
-                                 a_plane=m.plane(D), w_plane=D if m.precise else 0, **lin), L + "attn_out+ls1+res")
-            ln(0, M, 1, T_[f"{i}.ln2.w"], T_[f"{i}.ln2.b"], xn, m.dt, m.ld(D), m.plane(D), 0, L + "norm2")
+            if fused_ln2:
+                d = nv.RowprojDesc()
+                d.x, d.ld_x, d.w, d.w_ld = ptr(ctx), m.ld(D), ptr(T_[f"{i}.o.w"]), T_[f"{i}.o.w"].shape[-1]
+                d.bias, d.colscale, d.h, d.ld_h, d.rows, d.D = ptr(T_[f"{i}.o.b"]), ptr(T_[f"{i}.ls1"]), ptr(h), D, M, D
+                d.ln_gamma, d.ln_beta = ptr(T_[f"{i}.ln2.w"]), ptr(T_[f"{i}.ln2.b"])
+                d.ln_out, d.ln_ld, d.ln_eps = ptr(xn), m.ld(D), 1e-6
+                plan.add(d, L + "attn_out+ls1+res+norm2")
+            else:
+                plan.add(linear_desc(a=ctx, k=D, a_ld=m.ld(D), w=T_[f"{i}.o.w"], n=D, n_pad=D, w_ld=T_[f"{i}.o.w"].shape[-1],
+                                     out=h, ldc=D, bias=T_[f"{i}.o.b"], colscale=T_[f"{i}.ls1"], res=h, ldres=D,
+                                     a_plane=m.plane(D), w_plane=D if m.precise else 0, **lin), L + "attn_out+ls1+res")
+                ln(0, M, 1, T_[f"{i}.ln2.w"], T_[f"{i}.ln2.b"], xn, m.dt, m.ld(D), m.plane(D), 0, L + "norm2")
             if fused_mlp:
                 d = nv.MlpDesc()
                 d.xn, d.ld_x = ptr(xn), m.ld(D)

@@ -18,7 +18,7 @@ ACT_NONE, ACT_GELU, ACT_MISH = 0, 1, 2
 EPI_LINEAR, EPI_GN = 0, 1
 LAYOUT_BHWC, LAYOUT_BCHW = 0, 1
 MAX_TAPS = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 i32, i64, f32, u64, vp = C.c_int32, C.c_int64, C.c_float, C.c_uint64, C.c_void_p
 
@@ -55,6 +55,11 @@ class MlpDesc(C.Structure):
     _fields_ = [("xn", vp), ("ld_x", i64), ("w1", vp), ("w1_ld", i64), ("b1", vp), ("w2", vp), ("w2_ld", i64), ("b2", vp),
                 ("ls2", vp), ("h", vp), ("ld_h", i64), ("rows", i32), ("D", i32),
                 ("ln_gamma", vp), ("ln_beta", vp), ("ln_out", vp), ("ln_ld", i64), ("ln_eps", C.c_float)]
+
+
+class RowprojDesc(C.Structure):
+    _fields_ = [("x", vp), ("ld_x", i64), ("w", vp), ("w_ld", i64), ("bias", vp), ("colscale", vp), ("h", vp), ("ld_h", i64),
+                ("rows", i32), ("D", i32), ("ln_gamma", vp), ("ln_beta", vp), ("ln_out", vp), ("ln_ld", i64), ("ln_eps", C.c_float)]
 
 
 class ImgStatsDesc(C.Structure):
@@ -187,14 +192,14 @@ class AdamwDesc(C.Structure):
 EXPORTS = [
     "vt_last_error", "vt_abi_version", "vt_device_info", "vt_program_create", "vt_program_destroy",
     "vt_program_num_ops", "vt_program_num_launches", "vt_program_add_gemm", "vt_program_add_layernorm",
-    "vt_program_add_attention", "vt_program_add_mlp", "vt_debug_timestamps", "vt_debug_persist_trace", "vt_pad_resize_area", "vt_gather_repack", "vt_program_add_imgstats", "vt_program_add_patchify", "vt_program_add_cls",
+    "vt_program_add_attention", "vt_program_add_mlp", "vt_program_add_rowproj", "vt_debug_timestamps", "vt_debug_persist_trace", "vt_pad_resize_area", "vt_gather_repack", "vt_program_add_imgstats", "vt_program_add_patchify", "vt_program_add_cls",
     "vt_program_add_pack", "vt_program_add_affine", "vt_program_add_tembed", "vt_program_add_sde",
     "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_add_tcol", "vt_program_add_gnbwd", "vt_program_add_colsum", "vt_program_add_ewise", "vt_program_add_silossbwd", "vt_program_add_lstm_train", "vt_program_add_lstm_bwd", "vt_program_add_lngelubwd", "vt_program_add_dropmask", "vt_program_add_persist", "vt_program_add_wgrad", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
     "vt_pos_embed_resize", "vt_adamw_ema_step",
 ]
 
 _ADD = {
-    GemmDesc: "vt_program_add_gemm", LnDesc: "vt_program_add_layernorm", AttnDesc: "vt_program_add_attention", MlpDesc: "vt_program_add_mlp",
+    GemmDesc: "vt_program_add_gemm", LnDesc: "vt_program_add_layernorm", AttnDesc: "vt_program_add_attention", MlpDesc: "vt_program_add_mlp", RowprojDesc: "vt_program_add_rowproj",
     ImgStatsDesc: "vt_program_add_imgstats", PatchifyDesc: "vt_program_add_patchify", ClsDesc: "vt_program_add_cls",
     PackDesc: "vt_program_add_pack", AffineDesc: "vt_program_add_affine", TembedDesc: "vt_program_add_tembed",
     SdeDesc: "vt_program_add_sde", LstmDesc: "vt_program_add_lstm", QsampleDesc: "vt_program_add_qsample",
