@@ -58,3 +58,7 @@ def build(mode):
 
 for mode in ("gemm", "gemm+ln", "rowproj", "rowproj+ln"):
     print(f"{mode:14s} {timed(*build(mode)):8.1f} us")
+if "dbg" in os.environ.get("VT_LIB", ""):     # knock-outs of the LayerNorm warps (debug library)
+    for name, k in (("no stores", 1), ("no loads", 2), ("no loads, no stores", 3), ("handshake only", 4)):
+        os.environ["VT_MLP_LN_DEBUG"] = str(k)
+        print(f"  rowproj+ln, {name:20s} {timed(*build('rowproj+ln')):8.1f} us")

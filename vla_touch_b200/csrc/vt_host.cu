@@ -1327,6 +1327,8 @@ int vt_program_add_rowproj(vt_program* p, const vt_rowproj_desc* d) {
     VT_REQUIRE(d->ln_gamma && d->ln_beta && d->ln_ld >= d->D && d->ln_ld % 4 == 0 && aligned16(d->ln_out) && aligned16(d->ln_gamma) &&
                    aligned16(d->ln_beta),
                "rowproj: fused LayerNorm output needs 16-byte aligned rows / vectors");
+    const char* ldbg = VT_DEBUG_KNOBS ? getenv("VT_MLP_LN_DEBUG") : nullptr;
+    a.ln_debug = ldbg ? atoi(ldbg) : 0;
     a.ln_gamma = d->ln_gamma;
     a.ln_beta = d->ln_beta;
     a.ln_out = reinterpret_cast<__nv_bfloat16*>(d->ln_out);

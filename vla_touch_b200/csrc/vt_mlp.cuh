@@ -72,6 +72,7 @@ __device__ __forceinline__ void ln_warp_rows(const float* hp, long long ldh, lon
                                              const float* gamma, const float* beta, __nv_bfloat16* out, long long ldo, int lane,
                                              int ldbg) {
   static_assert(NROWS == 64 || NROWS == 32, "statistics layout");
+  const uint64_t pol = l2_policy_evict_first();
   float4 g[3], b[3];
   if constexpr (HOLD_GB) {
 #pragma unroll
@@ -88,7 +89,8 @@ __device__ __forceinline__ void ln_warp_rows(const float* hp, long long ldh, lon
       const long long row = row0 + r8 + u;
       const float4* xr = reinterpret_cast<const float4*>(hp + row * ldh);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) v[u][i] = (row < m_total && !(ldbg & 2)) ? __ldcg(xr + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 3; ++i)   // last use of the fp32 row in this kernel: first in line for eviction
+        v[u][i] = (row < m_total && !(ldbg & 2)) ? ld_global_v4f_hint(xr + lane + 32 * i, pol) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {

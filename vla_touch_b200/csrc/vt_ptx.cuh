@@ -440,9 +440,10 @@ __device__ __forceinline__ void st_global_v4f_hint(float* ptr, float4 v, uint64_
   asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy)
                : "memory");
 }
+// (.cg: past L1 -- the reader is not the thread that wrote the line)
 __device__ __forceinline__ float4 ld_global_v4f_hint(const float4* ptr, uint64_t policy) {
   float4 v;
-  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(policy) : "memory");
+  asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(policy) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_shared_v2f(uint32_t addr, float a, float b) {

@@ -51,6 +51,7 @@ struct RowprojArgs {
   __nv_bfloat16* ln_out;   // [rows][ln_ld]
   long long ln_ld;
   float ln_eps;
+  int ln_debug;            // developer knobs (VT_DEBUG_KNOBS builds): 1 no stores, 2 no loads, 4 handshake only
 };
 
 __global__ void __launch_bounds__(RP_THREADS, 1) rowproj_kernel(const __grid_constant__ RowprojArgs a) {
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) rowproj_kernel(const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(st_free);
         ln_warp_rows<32, false>(reinterpret_cast<const float*>(a.epi.out), a.epi.ldc, a.epi.M_total,
-                                (long long)(unit * 2 + rank) * 128 + w4 * 32, mr, mr, a.ln_gamma, a.ln_beta, a.ln_out, a.ln_ld, lane, 0);
+                                (long long)(unit * 2 + rank) * 128 + w4 * 32, mr, mr, a.ln_gamma, a.ln_beta, a.ln_out, a.ln_ld, lane, kDbg ? a.ln_debug : 0);
       }
     }
   }
