@@ -431,6 +431,87 @@ def bench_train(cx, wl, batch, steps, warmup):
                          "frac_of_sustained": sps / cx.world * f_s / 1e12 / pk.get("bf16_tflops_sustained", 1400.0)}}
 
 
+def bench_train_cached(cx, wl, batch, steps, warmup, episodes=4, frames=168):
+    """The same training step fed from the HBM-resident episode store with the DinoV2 feature cache (SURVEY.md 8f N2;
+    vla_touch_b200/episode_store.py): per step the host sends `batch` sample numbers, vt_batch_gather assembles the collated,
+    normalised minibatch + cached features of both cameras, and the frozen encoder no longer runs.  Episodes follow the reference's
+    HDF5 schema (A = 10 pose dims, 3 force dims, 64 x 10 VLA chunks, 224 x 224 uint8 frames), written as .vtep shards to a
+    temporary directory, `episodes` x `frames` frames per rank."""
+    import shutil
+    import tempfile
+    import numpy as np
+    torch = cx.torch
+    from vla_touch_b200 import controller_dataset as cd
+    from vla_touch_b200 import episode_store as es
+    from vla_touch_b200.synthetic import synth_episode
+    from vla_touch_b200.trainer import DiffusionControllerTrainer
+    name, hidden, heads, layers, hw, T, _, _, n_steps, _ = wl
+    wl10 = (name, hidden, heads, layers, hw, T, 10, 3, n_steps, batch)
+    td = tempfile.mkdtemp(prefix="vtep_")
+    try:
+        for e in range(episodes):
+            es.write_episode_shard(synth_episode(1000 * cx.rank + e, frames, hw, still_frames=2), os.path.join(td, f"episode_{e}.vtep"))
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):          # the dataset prints progress like the reference's does
+            ds = cd.ControllerDataset(td, context_frames=2, horizon=T, use_images=True, image_size=hw)
+        ctl = make_controller(cx, wl10)
+        t0 = time.perf_counter()
+        store = ds.device_store(cx.dev, image_encoder=ctl.image_encoder, feature_chunk=128)
+        torch.cuda.synchronize()
+        fill_s = time.perf_counter() - t0
+    finally:
+        shutil.rmtree(td, ignore_errors=True)
+    tr = DiffusionControllerTrainer(ctl, ds.stats, device=cx.dev)
+    sampler = cd.EpisodeBatchSampler(len(ds), batch, 0, 1, seed=cx.rank)      # every rank owns its own episodes here
+    epoch = [0]
+    losses = []
+
+    def next_indices():
+        sampler.set_epoch(epoch[0])
+        epoch[0] += 1
+        return next(iter(sampler))
+
+    fixed = torch.from_numpy(next_indices()).to(cx.dev)
+
+    def dev_step():
+        losses.append(tr.train_step(store.gather(fixed))["loss"])
+
+    loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
+
+    def api_step():
+        out = tr.train_step(store.gather(next_indices()))     # host -> device: the sample numbers
+        loss_host.copy_(torch.stack([out["loss"], out["v_loss"], out["s_loss"], out["b_loss"]]), non_blocking=True)
+
+    for _ in range(max(warmup, 2)):
+        dev_step()
+    torch.cuda.synchronize()
+    ms = cx.timed(dev_step, steps)
+    for _ in range(2):
+        api_step()
+    ms_e2e = cx.timed(api_step, steps)
+    reps = 50
+    ms_gather = cx.timed(lambda: store.gather(fixed), reps) / reps
+    L, A, H = 2 + T, store.A, T
+    per_sample = 4 * (L * A + 2 * H * A + L * store.Fd + L * store.Dd + 2 * store.D)          # fp32 elements read from the store
+    per_sample_out = per_sample + 4 * 2 * H * A + 4 * H * A                                  # + expert_actions copy, two normalised chunks
+    pk, _ = peaks()
+    gbs = batch * (per_sample + per_sample_out) / (ms_gather * 1e-3) / 1e9
+    sps = cx.world * batch * steps / (ms * 1e-3)
+    f_s = 9 * unet_flops(T)
+    return {"metric": "training samples/sec (bridge_train.py step fed from the HBM episode store, DinoV2 features cached)",
+            "value": sps, "unit": "samples/s", "ms_per_step": ms / steps, "batch_per_gpu": batch, "global_batch": batch * cx.world,
+            "scaling": "weak", "dtype": "bf16",
+            "e2e": {"value": cx.world * batch * steps / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e / steps,
+                    "h2d_bytes_per_step": batch * 8, "d2h_bytes_per_step": 16},
+            "store": {"episodes": episodes, "frames": store.frames, "samples": len(store), "A": A, "force_dim": store.Fd,
+                      "fill_seconds_incl_feature_cache": fill_s, "feature_cache_bytes": int(store.feats.numel()) * 4},
+            "gather_kernel": {"ms": ms_gather, "algorithmic_bytes": batch * (per_sample + per_sample_out), "achieved_gbs": gbs,
+                              "peak_gbs": pk.get("hbm_gbs"), "note": "launch-latency-bound at this size (10 MB per minibatch)"},
+            "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
+            "roofline": {"bound": "tensor", "gflop_per_sample": f_s / 1e9, "achieved_tflops_per_gpu": sps / cx.world * f_s / 1e12,
+                         "frac_of_sustained": sps / cx.world * f_s / 1e12 / pk.get("bf16_tflops_sustained", 1400.0)}}
+
+
 def make_lstm_controller(cx, wl):
     from vla_touch_b200 import shapes as shp
     from vla_touch_b200 import synthetic as syn
@@ -538,14 +619,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg1", "cfg2_train", "cfg4", "cfg5"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg1", "cfg2_train", "cfg2_train_cached", "cfg4", "cfg5"])
     ap.add_argument("--batch", type=int, default=0, help="rows per GPU (default: the workload's)")
     ap.add_argument("--ref-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only-headline", action="store_true", help="skip the secondary workloads (cfg2_train, cfg3, cfg4, cfg5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
-    base = "cfg2" if args.workload in ("cfg2_train", "cfg4") else args.workload
+    base = "cfg2" if args.workload in ("cfg2_train", "cfg2_train_cached", "cfg4") else args.workload
     wl = WORKLOADS[base]
     if args.impl == "reference":
         args.steps = min(args.steps, 4)
@@ -585,6 +666,13 @@ def main():
         r.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None,
                   "data": "synthetic", "config": {"workload": "cfg2_train: bridge_train.py step, dinov2-small 224x224 x2 cams, T=64, A=7, F=64"},
                   "clocks": sampler.summary(), "gpu_launches": r["gpu_launches_per_step"] * args.steps})
+        return emit(r)
+    if args.workload == "cfg2_train_cached":
+        r = bench_train_cached(cx, wl, batch, args.steps, args.warmup)
+        sampler.stop_flag = True
+        r.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None,
+                  "data": "synthetic", "config": {"workload": "cfg2_train_cached: bridge_train.py step from the HBM episode store, T=64, A=10, F=3, DinoV2-S features of 2 x 224x224 cameras cached"},
+                  "clocks": sampler.summary()})
         return emit(r)
     if args.workload == "cfg4":
         r = bench_lstm_train(cx, wl, args.batch or 512, 128, args.steps, args.warmup)
@@ -643,6 +731,7 @@ def main():
             torch.cuda.empty_cache()
 
         attempt("cfg2_train", lambda: bench_train(cx, wl, 256, k, 3))
+        attempt("cfg2_train_cached", lambda: bench_train_cached(cx, wl, 256, k, 3))
         attempt("cfg4_lstm_train", lambda: bench_lstm_train(cx, wl, 512, 128, k, 3))
         wl3 = WORKLOADS["cfg3"]
 

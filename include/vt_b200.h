@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VT_ABI_VERSION 4
+#define VT_ABI_VERSION 5
 
 enum { VT_OK = 0, VT_E_INVALID = -1, VT_E_CUDA = -2, VT_E_UNSUPPORTED = -3, VT_E_NODEVICE = -4 };
 enum { VT_BF16 = 0, VT_F32 = 1, VT_U8 = 2 };
@@ -622,6 +622,42 @@ int vt_gather_repack(const void* recs_dev, const int64_t* chunks_dev, int32_t n_
    cv2.resize(..., interpolation=cv2.INTER_AREA) -- bit-identical to OpenCV (integer-factor and fractional-factor paths).
    Up-scaling (max(h, w) < target) returns VT_E_INVALID. */
 int vt_pad_resize_area(const uint8_t* src_dev, int32_t n, int32_t h, int32_t w, int32_t c, uint8_t* dst_dev, int32_t target, void* stream);
+
+/* Minibatch assembly from the HBM-resident episode store: replaces ControllerDataset.__getitem__
+   (controller_dataset.py:101-170), the DataLoader's collate + host->device copy (controller_dataset.py:467-476,
+   bridge_train.py:304-307) and the action normalisation of _prepare_batch_for_diffusion (bridge_train.py:120-145) for B samples
+   in one launch.  All episode streams are concatenated over frames in device memory; `start[b]` is the global frame index of
+   sample b's first context frame.  Output values are bit-identical to the reference's fp32 tensors. */
+typedef struct vt_batch_gather_desc {
+  const float* qpos;            /* [frames][A]  fp32(converted_ee_pose_with_gripper), scripts/utils_eef.py:80-90 */
+  const float* grip_scaled;     /* [frames]     fp32(gripper / 255), divided in the source precision (controller_dataset.py:124) */
+  const float* vla;             /* [frames][vla_T][A] vla_action as stored */
+  const float* vla_last_scaled; /* [frames][vla_T]    fp32(vla_action[..., -1] / 255) (controller_dataset.py:130) */
+  const float* forces;          /* [frames][Fd] gelsight_force/forces */
+  const float* disps;           /* [frames][Dd] gelsight_force/displacement flattened (63*2), or NULL */
+  const float* feats;           /* [frames][2 cameras][2 branches][D] cached DINOv2Encoder.forward features (branch 0: images
+                                   passed un-normalised, 1: ImageNet-normalised, visual_encoder.py:95-106), or NULL */
+  const double* frame_mean;     /* [frames][2] mean pixel value in [0, 1] per frame and camera (required with feats) */
+  const int64_t* start;         /* [B] */
+  int32_t B, A, vla_T, Fd, Dd, D;
+  int32_t context_frames, horizon;
+  float* states;                /* out [B][context_frames + horizon][A], may be NULL (like every output below) */
+  float* expert_actions;        /* out [B][horizon][A] */
+  float* vla_actions;           /* out [B][horizon][A] */
+  float* forces_out;            /* out [B][context_frames + horizon][Fd] */
+  float* disps_out;             /* out [B][context_frames + horizon][Dd] */
+  float* feat_cam1;             /* out [B][D]: features of the last context frame (bridge_train.py:142-145); required with feats */
+  float* feat_cam2;
+  int32_t* branch;              /* out [2]: branch chosen per camera from the batch mean (visual_encoder.py:100), may be NULL */
+  const float* action_mins;     /* [A] fp32 stats; NULL = no normalised outputs */
+  const float* action_maxs;
+  const float* vla_mins;
+  const float* vla_maxs;
+  float pad;                    /* padding_factor of normalize_actions (controller_dataset.py:303), 1.4 */
+  float* expert_n;              /* out [B][horizon][A] = normalize_actions(expert_actions, stats, 'expert') */
+  float* vla_n;                 /* out [B][horizon][A] = normalize_actions(vla_actions, stats, 'vla') */
+} vt_batch_gather_desc;
+int vt_batch_gather(const vt_batch_gather_desc* d, void* stream);
 
 /* bicubic (A=-0.75, align_corners=False) resize of the patch position embeddings, HF:57-95: src [s*s][D] -> dst [nh*nw][D] */
 int vt_pos_embed_resize(const float* src_dev, int32_t s, float* dst_dev, int32_t nh, int32_t nw, int32_t D, void* stream);

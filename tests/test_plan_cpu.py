@@ -61,7 +61,7 @@ def test_ctypes_structs_match_the_c_header():
              "vt_mlp_desc": nv.MlpDesc, "vt_rowproj_desc": nv.RowprojDesc, "vt_tcol_desc": nv.TcolDesc, "vt_gnbwd_desc": nv.GnbwdDesc,
              "vt_colsum_desc": nv.ColsumDesc, "vt_ewise_desc": nv.EwiseDesc, "vt_silossbwd_desc": nv.SilossBwdDesc, "vt_lstm_train_desc": nv.LstmTrainDesc,
              "vt_lstm_bwd_desc": nv.LstmBwdDesc, "vt_lngelubwd_desc": nv.LnGeluBwdDesc, "vt_dropmask_desc": nv.DropmaskDesc,
-             "vt_persist_desc": nv.PersistDesc, "vt_wgrad_desc": nv.WgradDesc}
+             "vt_persist_desc": nv.PersistDesc, "vt_wgrad_desc": nv.WgradDesc, "vt_batch_gather_desc": nv.BatchGatherDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/vt_b200.h"', 'int main(void){']
     probes = []
     for cname, cls in descs.items():

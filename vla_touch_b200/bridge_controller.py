@@ -175,8 +175,11 @@ class DiffusionController:
     def _trains_encoder(self) -> bool:
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.state_encoder.parameters())
 
-    def encode_observation(self, state, images_cam1=None, images_cam2=None, forces=None, *, differentiable=None):
+    def encode_observation(self, state, images_cam1=None, images_cam2=None, forces=None, *, differentiable=None, image_features=None):
         """-> obs_cond [B, hidden_dim] (bridge_controller.py:112-134).
+
+        image_features=(f1, f2): the frozen encoder's outputs for this batch, already computed (the DinoV2 feature cache of
+        episode_store.DeviceEpisodeStore); the images are then not needed and the state encoder runs as the torch module.
 
         differentiable=None (default) follows torch's grad mode like a plain nn.Module call would: under torch.no_grad() /
         inference_mode() (predict, validation, deployment) it is the inference path, one native program (DinoV2 x 2 + the
@@ -187,14 +190,19 @@ class DiffusionController:
         as native programs behind a torch.autograd.Function (mlp_train.py)."""
         if differentiable is None:
             differentiable = self._trains_encoder()
-        if differentiable:
+        if image_features is not None and self.image_encoder is None:
+            raise ValueError("image_features passed to a controller without an image encoder")
+        if differentiable or image_features is not None:
             B = state.shape[0]
             st = state.to(self.device).float().reshape(B, -1)
             if self.use_force:
                 if forces is None:
                     raise ValueError("use_force=True but forces is None")
                 st = torch.cat((st, forces.to(self.device).float().reshape(B, -1)), dim=-1)
-            if self.image_encoder is not None:
+            if image_features is not None:
+                f1, f2 = image_features
+                x = torch.cat((f1.to(self.device).float(), f2.to(self.device).float(), st), dim=-1)
+            elif self.image_encoder is not None:
                 with torch.no_grad():
                     f1, f2 = self.encode_images(images_cam1, images_cam2)
                 x = torch.cat((f1, f2, st), dim=-1)

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libvt_b200.so")
 SOURCES = ["vt_host.cu"]
-DEPS = ["vt_host.cu", "vt_wgrad.cuh", "vt_persist.cuh", "vt_attn_pp.cuh", "vt_resize.cuh", "vt_lstm_tc.cuh", "vt_gemm.cuh", "vt_attn.cuh", "vt_mlp.cuh", "vt_rowproj.cuh", "vt_elem.cuh", "vt_lstm.cuh", "vt_bwd.cuh", "vt_ptx.cuh",
+DEPS = ["vt_host.cu", "vt_wgrad.cuh", "vt_persist.cuh", "vt_attn_pp.cuh", "vt_resize.cuh", "vt_dataset.cuh", "vt_lstm_tc.cuh", "vt_gemm.cuh", "vt_attn.cuh", "vt_mlp.cuh", "vt_rowproj.cuh", "vt_elem.cuh", "vt_lstm.cuh", "vt_bwd.cuh", "vt_ptx.cuh",
         os.path.join("..", "..", "include", "vt_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

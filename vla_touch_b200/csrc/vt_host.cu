@@ -21,6 +21,7 @@
 #include "vt_persist.cuh"
 #include "vt_attn_pp.cuh"
 #include "vt_resize.cuh"
+#include "vt_dataset.cuh"
 #include "vt_wgrad.cuh"
 #include "vt_lstm.cuh"
 #include "vt_lstm_tc.cuh"
@@ -1671,6 +1672,19 @@ int vt_pad_resize_area(const uint8_t* src_dev, int32_t n, int32_t h, int32_t w, 
   const long long total = (long long)n * target * target * c;
   vt::pad_resize_area_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   VT_LAUNCH_CHECK("pad_resize_area_kernel");
+  return VT_OK;
+}
+
+int vt_batch_gather(const vt_batch_gather_desc* d, void* stream) {
+  VT_REQUIRE(d && d->qpos && d->grip_scaled && d->vla && d->vla_last_scaled && d->start, "batch_gather: missing store arrays");
+  VT_REQUIRE(d->B >= 1 && d->A >= 1 && d->context_frames >= 1 && d->horizon >= 1 && d->horizon <= d->vla_T,
+             "batch_gather: bad shape (B %d, A %d, context %d, horizon %d, chunk length %d)", d->B, d->A, d->context_frames, d->horizon, d->vla_T);
+  VT_REQUIRE(!d->forces_out || (d->forces && d->Fd >= 1), "batch_gather: forces requested but the store has none");
+  VT_REQUIRE(!d->disps_out || (d->disps && d->Dd >= 1), "batch_gather: displacements requested but the store has none");
+  VT_REQUIRE(!d->feats || (d->frame_mean && d->feat_cam1 && d->feat_cam2 && d->D >= 1), "batch_gather: feature cache needs frame_mean, feat_cam1, feat_cam2");
+  VT_REQUIRE(!(d->expert_n || d->vla_n) || (d->action_mins && d->action_maxs && d->vla_mins && d->vla_maxs), "batch_gather: normalised outputs need the four stats vectors");
+  vt::batch_gather_kernel<<<d->B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*d);
+  VT_LAUNCH_CHECK("batch_gather_kernel");
   return VT_OK;
 }
 

@@ -98,7 +98,9 @@ class DinoProgram:
     """images (n_calls tensors of [B,H,W,3] uint8/float or [B,3,H,W] float) -> features fp32 [n_calls][B][D]."""
 
     def __init__(self, plan: Plan, W: DinoWeights, n_calls: int, B: int, H: int, Wd: int, img_dtype: torch.dtype,
-                 layout: int, resize: Callable = native_pos_resize, tag: str = "dino"):
+                 layout: int, resize: Callable = native_pos_resize, tag: str = "dino", host_flags: bool = False):
+        """host_flags: no IMGSTATS ops -- the caller writes `self.flags` ([divide by 255, ImageNet-normalise] per call) itself
+        (episode_store.DeviceEpisodeStore caches features for both outcomes of the batch-global predicate)."""
         if H < PATCH or Wd < PATCH:
             raise ValueError(f"image size {H}x{Wd} is smaller than one {PATCH}x{PATCH} patch")
         # like Conv2d(k14, s14), trailing rows/columns that do not fill a patch are ignored (384 -> 27 patches)
@@ -131,7 +133,8 @@ class DinoProgram:
             d = nv.ImgStatsDesc()
             d.img, d.dtype, d.count = ptr(self.img[c]), nv.VT_U8 if img_dtype == torch.uint8 else nv.VT_F32, self.img[c].numel()
             d.partial, d.flags = ptr(scratch, c * 3 * 1024), ptr(self.flags, c * 4)
-            plan.add(d, f"{tag}.imgstats{c}")
+            if not host_flags:
+                plan.add(d, f"{tag}.imgstats{c}")
             d = nv.PatchifyDesc()
             d.img, d.dtype, d.layout = ptr(self.img[c]), nv.VT_U8 if img_dtype == torch.uint8 else nv.VT_F32, layout
             d.images, d.H, d.W, d.patch, d.flags = B, H, Wd, PATCH, ptr(self.flags, c * 4)

@@ -18,7 +18,7 @@ ACT_NONE, ACT_GELU, ACT_MISH = 0, 1, 2
 EPI_LINEAR, EPI_GN = 0, 1
 LAYOUT_BHWC, LAYOUT_BCHW = 0, 1
 MAX_TAPS = 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 i32, i64, f32, u64, vp = C.c_int32, C.c_int64, C.c_float, C.c_uint64, C.c_void_p
 
@@ -189,13 +189,21 @@ class AdamwDesc(C.Structure):
                 ("ema_decay", f32), ("grad_scale", f32)]
 
 
+class BatchGatherDesc(C.Structure):
+    _fields_ = [("qpos", vp), ("grip_scaled", vp), ("vla", vp), ("vla_last_scaled", vp), ("forces", vp), ("disps", vp), ("feats", vp),
+                ("frame_mean", vp), ("start", vp), ("B", i32), ("A", i32), ("vla_T", i32), ("Fd", i32), ("Dd", i32), ("D", i32),
+                ("context_frames", i32), ("horizon", i32), ("states", vp), ("expert_actions", vp), ("vla_actions", vp),
+                ("forces_out", vp), ("disps_out", vp), ("feat_cam1", vp), ("feat_cam2", vp), ("branch", vp),
+                ("action_mins", vp), ("action_maxs", vp), ("vla_mins", vp), ("vla_maxs", vp), ("pad", f32), ("expert_n", vp), ("vla_n", vp)]
+
+
 EXPORTS = [
     "vt_last_error", "vt_abi_version", "vt_device_info", "vt_program_create", "vt_program_destroy",
     "vt_program_num_ops", "vt_program_num_launches", "vt_program_add_gemm", "vt_program_add_layernorm",
     "vt_program_add_attention", "vt_program_add_mlp", "vt_program_add_rowproj", "vt_debug_timestamps", "vt_debug_persist_trace", "vt_pad_resize_area", "vt_gather_repack", "vt_program_add_imgstats", "vt_program_add_patchify", "vt_program_add_cls",
     "vt_program_add_pack", "vt_program_add_affine", "vt_program_add_tembed", "vt_program_add_sde",
     "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_add_tcol", "vt_program_add_gnbwd", "vt_program_add_colsum", "vt_program_add_ewise", "vt_program_add_silossbwd", "vt_program_add_lstm_train", "vt_program_add_lstm_bwd", "vt_program_add_lngelubwd", "vt_program_add_dropmask", "vt_program_add_persist", "vt_program_add_wgrad", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
-    "vt_pos_embed_resize", "vt_adamw_ema_step",
+    "vt_pos_embed_resize", "vt_adamw_ema_step", "vt_batch_gather",
 ]
 
 _ADD = {
@@ -240,6 +248,7 @@ def lib() -> C.CDLL:
         L.vt_adamw_ema_step.argtypes = [C.POINTER(AdamwDesc), vp]
         L.vt_pad_resize_area.argtypes = [vp, i32, i32, i32, i32, vp, i32, vp]
         L.vt_gather_repack.argtypes = [vp, vp, i32, vp, vp]
+        L.vt_batch_gather.argtypes = [C.POINTER(BatchGatherDesc), vp]
         if L.vt_abi_version() != ABI_VERSION:
             raise NativeError("libvt_b200.so ABI version mismatch; rebuild it")
         _lib = L

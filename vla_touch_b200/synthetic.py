@@ -111,3 +111,32 @@ def synth_stats_varied(action_dim: int, seed: int = 0) -> Dict[str, torch.Tensor
         "action_mins": a_lo, "action_maxs": a_hi, "action_range": a_hi - a_lo,
         "vla_mins": v_lo, "vla_maxs": v_hi, "vla_range": v_hi - v_lo,
     }
+
+
+def synth_episode(seed: int, n_frames: int, image_size: int = 28, vla_T: int = 64, still_frames: int = 3, moving: bool = True,
+                  dark: bool = False, images: bool = True) -> Dict[str, object]:
+    """One episode with the reference's HDF5 schema (data/create_controller_dataset_episode.py:179-188) as a nested dict of numpy
+    arrays: the end effector stands still for `still_frames` frames (the dataset skips those, controller_dataset.py:80-92), then
+    random-walks; gripper in [0, 255]; `moving=False` gives an episode the dataset must skip entirely."""
+    g = np.random.default_rng([seed, n_frames])
+    step = g.normal(0.0, 0.02, (n_frames, 3))
+    step[:still_frames + 1] = 0.0
+    if not moving:
+        step[:] = 0.0
+    pos = np.array([0.4, 0.0, 0.3]) + np.cumsum(step, axis=0)
+    quat = g.normal(0.0, 1.0, (n_frames, 4))
+    quat[:still_frames + 1] = quat[0]
+    if not moving:
+        quat[:] = quat[0]
+    quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    epi = {
+        "ee_poses": np.concatenate((pos, quat), axis=1),
+        "gripper_pos": np.floor(g.uniform(0.0, 256.0, n_frames)),
+        "vla_action": np.concatenate((g.normal(0.0, 0.5, (n_frames, vla_T, 9)), g.uniform(0.0, 255.0, (n_frames, vla_T, 1))), axis=2).astype(np.float32),
+        "gelsight_force": {"forces": g.normal(0.0, 1.0, (n_frames, 3)), "displacement": g.normal(0.0, 2.0, (n_frames, 63, 2))},
+    }
+    if images:
+        lo, hi = (0, 100) if dark else (96, 256)
+        epi["camera1_resized"] = g.integers(lo, hi, (n_frames, image_size, image_size, 3), dtype=np.uint8)
+        epi["camera2_resized"] = g.integers(lo, hi, (n_frames, image_size, image_size, 3), dtype=np.uint8)
+    return epi

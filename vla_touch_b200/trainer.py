@@ -52,12 +52,16 @@ class DiffusionControllerTrainer:
         ctx = self.controller.model_args.get('context_frames', 2)
         states, forces = batch['states'], batch['forces']
         current_state, current_forces = states[:, ctx - 1], forces[:, ctx - 1]
-        vla_n = normalize_actions(batch['vla_actions'].to(self.device), self.stats, 'vla')
-        exp_n = normalize_actions(batch['expert_actions'].to(self.device), self.stats, 'expert')
+        if 'vla_act' in batch and 'expert_act' in batch:     # DeviceEpisodeStore.gather: normalised by the gather kernel already
+            vla_n, exp_n = batch['vla_act'], batch['expert_act']
+        else:
+            vla_n = normalize_actions(batch['vla_actions'].to(self.device), self.stats, 'vla')
+            exp_n = normalize_actions(batch['expert_actions'].to(self.device), self.stats, 'expert')
         cam1, cam2 = batch.get('images_cam1'), batch.get('images_cam2')
         if cam1 is not None and cam2 is not None:
             cam1, cam2 = cam1[:, -1], cam2[:, -1]
-        obs_cond = self.controller.encode_observation(current_state, cam1, cam2, current_forces)
+        feats = (batch['feat_cam1'], batch['feat_cam2']) if 'feat_cam1' in batch else None   # cached frozen-encoder features
+        obs_cond = self.controller.encode_observation(current_state, cam1, cam2, current_forces, image_features=feats)
         return {'obs_cond': obs_cond, 'expert_act': exp_n, 'vla_act': vla_n, 'forces': forces[:, ctx:], 'current_force': current_forces}
 
     def _ensure(self, B: int, T: int):
