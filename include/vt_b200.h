@@ -659,6 +659,15 @@ typedef struct vt_batch_gather_desc {
 } vt_batch_gather_desc;
 int vt_batch_gather(const vt_batch_gather_desc* d, void* stream);
 
+/* RDT policy.step -> controller.predict hand-off: replaces RoboticDiffusionTransformerModel._unformat_action_to_joint
+   + `.to(torch.float32)` (scripts/franka_model_eef.py:199-222,312) and the deployment loop's `vla_tensor[:, :, -1] /= 255` + slice
+   (scripts/franka_inference_eef.py:546,552-554).  action_dev: [B][N][S] unified action vectors (VT_BF16 or VT_F32) as the policy
+   wrote them; idx_dev [A] positions of the robot's dims in the unified vector; scale_dev [A] (1,...,1,255).
+   raw_dev   out [B][N][A] fp32 = what policy.step returns (may be NULL);
+   chunk_dev out [B][T_exec][A] fp32 = the tensor predict() receives: last dim / last_div, first T_exec rows (may be NULL). */
+int vt_chunk_handoff(const void* action_dev, int32_t dtype, int32_t B, int32_t N, int32_t S, const int32_t* idx_dev, const float* scale_dev,
+                     int32_t A, float last_div, float* raw_dev, float* chunk_dev, int32_t T_exec, void* stream);
+
 /* bicubic (A=-0.75, align_corners=False) resize of the patch position embeddings, HF:57-95: src [s*s][D] -> dst [nh*nw][D] */
 int vt_pos_embed_resize(const float* src_dev, int32_t s, float* dst_dev, int32_t nh, int32_t nw, int32_t D, void* stream);
 

@@ -99,8 +99,9 @@ def main():
         for k, v in batch.items():
             if not k.startswith("images"):
                 out[f"{tag}.batch5.{k}"] = v.numpy()
-        out[f"{tag}.norm.expert"] = ref.normalize_actions(batch["expert_actions"], ds.stats, "expert").numpy()
-        out[f"{tag}.norm.vla"] = ref.normalize_actions(batch["vla_actions"], ds.stats, "vla").numpy()
+        stats32 = {k: torch.tensor(v, dtype=torch.float32) for k, v in ds.stats.items()}      # as the trainer holds them, bridge_train.py:74
+        out[f"{tag}.norm.expert"] = ref.normalize_actions(batch["expert_actions"], stats32, "expert").numpy()
+        out[f"{tag}.norm.vla"] = ref.normalize_actions(batch["vla_actions"], stats32, "vla").numpy()
     np.random.seed(7)
     dm = ref.ControllerDataModule(td, batch_size=4, num_workers=0, context_frames=2, horizon=8, use_images=False, image_size=IMAGE, val_ratio=0.3)
     out["dm.train_files"] = np.array([os.path.basename(p) for p in dm.train_dataset.file_paths])

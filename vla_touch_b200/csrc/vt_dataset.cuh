@@ -14,6 +14,7 @@
 // to the reference's tensors: the two /255 columns are pre-divided on the host in the source precision when the store is built
 // (the reference divides in float64 / float32 BEFORE the fp32 cast), the normalisation repeats affine_kernel's operation order.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -118,6 +119,36 @@ __global__ void __launch_bounds__(256) batch_gather_kernel(const vt_batch_gather
     } else {
       for (int i = tid; i < n; i += 256) o[i] = s[i];
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// RDT -> controller hand-off.  Reference, four tensor ops and a host round trip apart
+// (scripts/franka_model_eef.py:199-222,312: `action[:, :, AGILEX_STATE_INDICES] * [1,..,1,255]` in the policy's dtype, `.to(float32)`;
+// scripts/franka_inference_eef.py:186,546,552-554: `.cpu().numpy()` copy for the buffer, `vla_tensor[:, :, -1] /= 255`, slice
+// `[:, :act_chunk_execute_step]` into controller.predict): one launch on the policy's own stream reads the unified action vector
+// where the policy left it and writes both fp32 tensors.  Same roundings as the reference: the product is rounded to the policy's
+// dtype (bf16 RN) before the fp32 widening, the division is an IEEE fp32 division.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) chunk_handoff_kernel(const void* __restrict__ action, int dtype, int B, int N, int S,
+                                                            const int32_t* __restrict__ idx, const float* __restrict__ scale, int A,
+                                                            float last_div, float* __restrict__ raw, float* __restrict__ chunk, int T_exec) {
+  const long long total = (long long)B * N * A;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int a = (int)(i % A);
+    const long long bn = i / A;
+    const int n = (int)(bn % N);
+    const long long b = bn / N;
+    const long long src = bn * S + idx[a];
+    float v;
+    if (dtype == VT_BF16) {
+      const float x = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(action)[src]);
+      v = __bfloat162float(__float2bfloat16_rn(__fmul_rn(x, scale[a])));     // bf16 * bf16 -> bf16 (torch computes in fp32, rounds once)
+    } else {
+      v = __fmul_rn(reinterpret_cast<const float*>(action)[src], scale[a]);
+    }
+    if (raw) raw[i] = v;
+    if (chunk && n < T_exec) chunk[(b * T_exec + n) * A + a] = (a == A - 1) ? __fdiv_rn(v, last_div) : v;
   }
 }
 

@@ -1688,6 +1688,18 @@ int vt_batch_gather(const vt_batch_gather_desc* d, void* stream) {
   return VT_OK;
 }
 
+int vt_chunk_handoff(const void* action_dev, int32_t dtype, int32_t B, int32_t N, int32_t S, const int32_t* idx_dev, const float* scale_dev,
+                     int32_t A, float last_div, float* raw_dev, float* chunk_dev, int32_t T_exec, void* stream) {
+  VT_REQUIRE(action_dev && idx_dev && scale_dev && (raw_dev || chunk_dev), "chunk_handoff: missing pointers");
+  VT_REQUIRE(dtype == VT_BF16 || dtype == VT_F32, "chunk_handoff: the action vector must be bf16 or fp32");
+  VT_REQUIRE(B >= 1 && N >= 1 && A >= 1 && S >= A && T_exec >= 0 && T_exec <= N, "chunk_handoff: bad shape (B %d, N %d, S %d, A %d, T_exec %d)", B, N, S, A, T_exec);
+  VT_REQUIRE(last_div != 0.f, "chunk_handoff: last_div is zero");
+  vt::chunk_handoff_kernel<<<grid_for((long long)B * N * A, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      action_dev, dtype, B, N, S, idx_dev, scale_dev, A, last_div, raw_dev, chunk_dev, T_exec);
+  VT_LAUNCH_CHECK("chunk_handoff_kernel");
+  return VT_OK;
+}
+
 int vt_pos_embed_resize(const float* src_dev, int32_t s, float* dst_dev, int32_t nh, int32_t nw, int32_t D, void* stream) {
   VT_REQUIRE(src_dev && dst_dev && s >= 1 && nh >= 1 && nw >= 1 && D >= 1, "pos_embed_resize: bad arguments");
   vt::pos_resize_kernel<<<grid_for((long long)nh * nw * D, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(

@@ -203,7 +203,7 @@ EXPORTS = [
     "vt_program_add_attention", "vt_program_add_mlp", "vt_program_add_rowproj", "vt_debug_timestamps", "vt_debug_persist_trace", "vt_pad_resize_area", "vt_gather_repack", "vt_program_add_imgstats", "vt_program_add_patchify", "vt_program_add_cls",
     "vt_program_add_pack", "vt_program_add_affine", "vt_program_add_tembed", "vt_program_add_sde",
     "vt_program_add_lstm", "vt_program_add_qsample", "vt_program_add_siloss", "vt_program_add_tcol", "vt_program_add_gnbwd", "vt_program_add_colsum", "vt_program_add_ewise", "vt_program_add_silossbwd", "vt_program_add_lstm_train", "vt_program_add_lstm_bwd", "vt_program_add_lngelubwd", "vt_program_add_dropmask", "vt_program_add_persist", "vt_program_add_wgrad", "vt_program_run", "vt_program_graph_build", "vt_program_graph_launch",
-    "vt_pos_embed_resize", "vt_adamw_ema_step", "vt_batch_gather",
+    "vt_pos_embed_resize", "vt_adamw_ema_step", "vt_batch_gather", "vt_chunk_handoff",
 ]
 
 _ADD = {
@@ -249,6 +249,7 @@ def lib() -> C.CDLL:
         L.vt_pad_resize_area.argtypes = [vp, i32, i32, i32, i32, vp, i32, vp]
         L.vt_gather_repack.argtypes = [vp, vp, i32, vp, vp]
         L.vt_batch_gather.argtypes = [C.POINTER(BatchGatherDesc), vp]
+        L.vt_chunk_handoff.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, f32, vp, vp, i32, vp]
         if L.vt_abi_version() != ABI_VERSION:
             raise NativeError("libvt_b200.so ABI version mismatch; rebuild it")
         _lib = L
