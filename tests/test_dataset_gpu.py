@@ -137,3 +137,35 @@ def test_training_step_from_the_store_equals_the_step_from_images(big_dir):
         assert float((pa - pb).abs().max()) <= 1e-5 * max(1.0, float(pb.abs().max())), n
     for pa, pb in zip(ctl_a.state_encoder.parameters(), ctl_b.state_encoder.parameters()):
         assert float((pa - pb).abs().max()) <= 1e-5
+
+
+def test_feature_cache_file_round_trip(big_dir, tmp_path):
+    ds = cd.ControllerDataset(big_dir, use_images=True, image_size=224, **CASES["h64c1"])
+    enc = _encoder()
+    a = ds.device_store(DEV, image_encoder=enc, feature_chunk=64)
+    path = a.save_feature_cache(str(tmp_path / "cache"), encoder_tag="synthetic-s2-seed4")
+    b = ds.device_store(DEV)
+    assert b.feats is None and "feat_cam1" not in b.gather([0])
+    with pytest.raises(ValueError):
+        b.load_feature_cache(path, encoder_tag="another encoder")
+    b.load_feature_cache(path, encoder_tag="synthetic-s2-seed4")
+    ga, gb = a.gather(np.arange(len(ds))), b.gather(np.arange(len(ds)))
+    for k in ("feat_cam1", "feat_cam2", "branch", "states", "vla_act"):
+        assert torch.equal(ga[k], gb[k]), k
+    other = cd.ControllerDataset(big_dir, file_paths=ds.file_paths[:2], **CASES["h64c1"]).device_store(DEV)
+    with pytest.raises(ValueError):
+        other.load_feature_cache(path, encoder_tag="synthetic-s2-seed4")
+
+
+def test_lstm_trainer_step_from_the_store(big_dir):
+    """lstm_train.py:57-82,122-139 fed from the store: forces[:, ctx-1:-1], cached features into obs_encoder, loss finite and falling."""
+    import vt_testutil as U
+    from vla_touch_b200.lstm_step_controller import TactileLSTMController
+    from vla_touch_b200.trainer import LSTMControllerTrainer
+    ds = cd.ControllerDataset(big_dir, use_images=True, image_size=224, **CASES["h16s3"])
+    lc = TactileLSTMController(state_dim=10, hidden_dim=256, device=DEV, force_dim=3, use_force=True, image_state_dict=U.dino_sd(384, 2, 4))
+    store = ds.device_store(DEV, image_encoder=lc.image_encoder, feature_chunk=32)
+    tr = LSTMControllerTrainer(lc, ds.stats, learning_rate=1e-3, device=DEV)
+    idx = np.arange(12)
+    losses = [float(tr.train_step(store.gather(idx))) for _ in range(6)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses

@@ -289,6 +289,29 @@ class DeviceEpisodeStore:
         self._feat_parts.append(feats)
         self._mean_parts.append(means)
 
+    def save_feature_cache(self, path: str, encoder_tag: str = "") -> str:
+        """Writes the feature cache (features, per-frame means, frame count per episode, a caller-chosen tag naming the encoder
+        weights) so that a later run can skip the DinoV2 pass: `DeviceEpisodeStore(ds)` + `load_feature_cache(path)`."""
+        if self.feats is None:
+            raise ValueError("this store holds no feature cache")
+        ends = self.episode_offset[1:] + [self.frames]
+        np.savez(path, feats=self.feats.cpu().numpy(), frame_mean=self.frame_mean.cpu().numpy(),
+                 episode_frames=np.array([e - o for o, e in zip(self.episode_offset, ends)], dtype=np.int64), tag=np.array(encoder_tag))
+        return path if path.endswith(".npz") else path + ".npz"
+
+    def load_feature_cache(self, path: str, encoder_tag: str = "") -> None:
+        """Rejects a cache whose episode layout or encoder tag differs from this store's (a stale cache must not train silently)."""
+        z = np.load(path)
+        ends = self.episode_offset[1:] + [self.frames]
+        mine = np.array([e - o for o, e in zip(self.episode_offset, ends)], dtype=np.int64)
+        if not np.array_equal(z["episode_frames"], mine) or z["feats"].shape[0] != self.frames:
+            raise ValueError(f"{path}: feature cache was written for a different set of episodes")
+        if str(z["tag"]) != encoder_tag:
+            raise ValueError(f"{path}: feature cache was written for encoder '{z['tag']}', not '{encoder_tag}'")
+        self.feats = torch.from_numpy(z["feats"]).to(self.device).contiguous()
+        self.frame_mean = torch.from_numpy(z["frame_mean"]).to(self.device).contiguous()
+        self.D = self.feats.shape[-1]
+
     # -- stats ----------------------------------------------------------------------------------------------------
     def set_stats(self, stats: Optional[Dict]) -> None:
         if stats is None:

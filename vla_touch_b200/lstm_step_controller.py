@@ -180,14 +180,18 @@ class TactileLSTMController:
     def _grad_wanted(self, modules) -> bool:
         return torch.is_grad_enabled() and any(p.requires_grad for m in modules for p in m.parameters())
 
-    def encode_observation(self, state, images_cam1, images_cam2):
-        """obs_encoder(cat(cam1, cam2, state)) (:126-146).  Under torch.no_grad() / inference_mode() (deployment, validation): the
+    def encode_observation(self, state, images_cam1=None, images_cam2=None, *, image_features=None):
+        """obs_encoder(cat(cam1, cam2, state)) (:126-146).  image_features=(f1, f2): the frozen encoder's outputs, already computed
+        (the DinoV2 feature cache of episode_store.DeviceEpisodeStore) -- the images are then not needed.  Under torch.no_grad() / inference_mode() (deployment, validation): the
         DinoV2 program + three tcgen05 GEMMs.  With autograd enabled and a trainable obs_encoder (lstm_train.py:70): the frozen
         DinoV2 features from the native kernels, then the 3-layer encoder as the torch module it is, so that
         `get_loss(...).backward()` trains it through d loss / d obs_cond."""
-        if self._grad_wanted([self.obs_encoder]):
-            with torch.no_grad():
-                f1, f2 = self.encode_images(images_cam1, images_cam2)
+        if image_features is not None or self._grad_wanted([self.obs_encoder]):
+            if image_features is not None:
+                f1, f2 = (f.to(self.device).float() for f in image_features)
+            else:
+                with torch.no_grad():
+                    f1, f2 = self.encode_images(images_cam1, images_cam2)
             st = state.to(self.device).float().reshape(f1.shape[0], -1)
             return self.obs_encoder(torch.cat((f1, f2, st), dim=-1))
         with torch.no_grad():

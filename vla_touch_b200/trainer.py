@@ -162,11 +162,15 @@ class LSTMControllerTrainer:
         c = self.controller
         current_state = batch['states'][:, context_frames - 1]
         forces = batch['forces'][:, context_frames - 1:-1] if c.use_force else None
-        vla_n = normalize_actions(batch['vla_actions'].to(self.device), c.stats, 'vla')
-        exp_n = normalize_actions(batch['expert_actions'].to(self.device), c.stats, 'expert')
+        if 'vla_act' in batch and 'expert_act' in batch:     # DeviceEpisodeStore.gather: normalised by the gather kernel already
+            vla_n, exp_n = batch['vla_act'], batch['expert_act']
+        else:
+            vla_n = normalize_actions(batch['vla_actions'].to(self.device), c.stats, 'vla')
+            exp_n = normalize_actions(batch['expert_actions'].to(self.device), c.stats, 'expert')
         cam1 = batch['images_cam1'][:, -1] if 'images_cam1' in batch else None
         cam2 = batch['images_cam2'][:, -1] if 'images_cam2' in batch else None
-        obs_cond = c.encode_observation(current_state, cam1, cam2)
+        feats = (batch['feat_cam1'], batch['feat_cam2']) if 'feat_cam1' in batch else None   # cached frozen-encoder features
+        obs_cond = c.encode_observation(current_state, cam1, cam2, image_features=feats)
         return {'obs_cond': obs_cond, 'expert_act': exp_n, 'vla_act': vla_n, 'forces': forces}
 
     def train_step(self, batch) -> torch.Tensor:
