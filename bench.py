@@ -589,6 +589,70 @@ def bench_lstm_train(cx, wl, batch, T, steps, warmup):
             "predict_tick_ms_p50": lat[len(lat) // 2], "loss_first": float(losses[0]), "loss_last": float(losses[-1])}
 
 
+def bench_lstm_train_cached(cx, wl, batch, T, steps, warmup, episodes=4):
+    """lstm_train.py:122-139 fed from the HBM episode store with the DinoV2 feature cache: per step the host sends
+    `batch` sample numbers; obs_encoder consumes the cached features, the frozen encoder does not run.  Synthetic episodes in the
+    reference's schema with `T`-step VLA chunks (A = 10, 3 force dims), `episodes` x (T + 2 + batch / episodes + 8) frames."""
+    import contextlib
+    import shutil
+    import tempfile
+    torch = cx.torch
+    from vla_touch_b200 import controller_dataset as cd
+    from vla_touch_b200 import episode_store as es
+    from vla_touch_b200.synthetic import synth_episode
+    from vla_touch_b200.trainer import LSTMControllerTrainer
+    name, hidden, heads, layers, hw, _, _, _, n_steps, _ = wl
+    wl10 = (name, hidden, heads, layers, hw, T, 10, 3, n_steps, batch)
+    frames = T + 2 + -(-batch // episodes) + 8
+    td = tempfile.mkdtemp(prefix="vtep_")
+    try:
+        for e in range(episodes):
+            es.write_episode_shard(synth_episode(2000 * (cx.rank + 1) + e, frames, hw, vla_T=T, still_frames=2), os.path.join(td, f"episode_{e}.vtep"))
+        with contextlib.redirect_stdout(sys.stderr):
+            ds = cd.ControllerDataset(td, context_frames=2, horizon=T, use_images=True, image_size=hw)
+        lc = make_lstm_controller(cx, wl10)
+        t0 = time.perf_counter()
+        store = ds.device_store(cx.dev, image_encoder=lc.image_encoder, feature_chunk=128)
+        torch.cuda.synchronize()
+        fill_s = time.perf_counter() - t0
+    finally:
+        shutil.rmtree(td, ignore_errors=True)
+    tr = LSTMControllerTrainer(lc, ds.stats, device=cx.dev)
+    sampler = cd.EpisodeBatchSampler(len(ds), batch, 0, 1, seed=cx.rank)
+    epoch = [0]
+
+    def next_indices():
+        sampler.set_epoch(epoch[0])
+        epoch[0] += 1
+        return next(iter(sampler))
+
+    fixed = torch.from_numpy(next_indices()).to(cx.dev)
+    losses = []
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def dev_step():
+        losses.append(tr.train_step(store.gather(fixed, with_displacements=False)))
+
+    def api_step():
+        loss_host.copy_(tr.train_step(store.gather(next_indices(), with_displacements=False)), non_blocking=True)
+
+    for _ in range(max(warmup, 2)):
+        dev_step()
+    torch.cuda.synchronize()
+    ms = cx.timed(dev_step, steps)
+    for _ in range(2):
+        api_step()
+    ms_e2e = cx.timed(api_step, steps)
+    sps = cx.world * batch * steps / (ms * 1e-3)
+    return {"metric": "training sequences/sec (lstm_train.py step fed from the HBM episode store, DinoV2 features cached)", "value": sps,
+            "unit": "sequences/s", "ms_per_step": ms / steps, "seq_len": T, "batch_per_gpu": batch, "global_batch": batch * cx.world,
+            "scaling": "weak", "dtype": "bf16",
+            "e2e": {"value": cx.world * batch * steps / (ms_e2e * 1e-3), "unit": "sequences/s", "ms_per_step": ms_e2e / steps,
+                    "h2d_bytes_per_step": batch * 8, "d2h_bytes_per_step": 4},
+            "store": {"episodes": episodes, "frames": store.frames, "samples": len(store), "fill_seconds_incl_feature_cache": fill_s},
+            "loss_first": float(losses[0]), "loss_last": float(losses[-1])}
+
+
 def bench_latency(cx, wl, batch, calls):
     """BASELINE configs[4]: RDT stub (random chunks) + refine, p50 latency of one predict() call with host inputs (wall clock around
     the call + synchronize, per rank; the reported p50 is the max over ranks)."""
@@ -619,14 +683,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg1", "cfg2_train", "cfg2_train_cached", "cfg4", "cfg5"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg1", "cfg2_train", "cfg2_train_cached", "cfg4", "cfg4_cached", "cfg5"])
     ap.add_argument("--batch", type=int, default=0, help="rows per GPU (default: the workload's)")
     ap.add_argument("--ref-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only-headline", action="store_true", help="skip the secondary workloads (cfg2_train, cfg3, cfg4, cfg5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
-    base = "cfg2" if args.workload in ("cfg2_train", "cfg2_train_cached", "cfg4") else args.workload
+    base = "cfg2" if args.workload in ("cfg2_train", "cfg2_train_cached", "cfg4", "cfg4_cached") else args.workload
     wl = WORKLOADS[base]
     if args.impl == "reference":
         args.steps = min(args.steps, 4)
@@ -672,6 +736,13 @@ def main():
         sampler.stop_flag = True
         r.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None,
                   "data": "synthetic", "config": {"workload": "cfg2_train_cached: bridge_train.py step from the HBM episode store, T=64, A=10, F=3, DinoV2-S features of 2 x 224x224 cameras cached"},
+                  "clocks": sampler.summary()})
+        return emit(r)
+    if args.workload == "cfg4_cached":
+        r = bench_lstm_train_cached(cx, wl, args.batch or 512, 128, args.steps, args.warmup)
+        sampler.stop_flag = True
+        r.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None,
+                  "data": "synthetic", "config": {"workload": "cfg4_cached: lstm_train.py step from the HBM episode store, seq_len 128, A=10, F=3, DinoV2-S features of 2 x 224x224 cameras cached"},
                   "clocks": sampler.summary()})
         return emit(r)
     if args.workload == "cfg4":
@@ -732,6 +803,7 @@ def main():
 
         attempt("cfg2_train", lambda: bench_train(cx, wl, 256, k, 3))
         attempt("cfg2_train_cached", lambda: bench_train_cached(cx, wl, 256, k, 3))
+        attempt("cfg4_lstm_train_cached", lambda: bench_lstm_train_cached(cx, wl, 512, 128, k, 3))
         attempt("cfg4_lstm_train", lambda: bench_lstm_train(cx, wl, 512, 128, k, 3))
         wl3 = WORKLOADS["cfg3"]
 
