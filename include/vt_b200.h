@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VT_ABI_VERSION 5
+#define VT_ABI_VERSION 6
 
 enum { VT_OK = 0, VT_E_INVALID = -1, VT_E_CUDA = -2, VT_E_UNSUPPORTED = -3, VT_E_NODEVICE = -4 };
 enum { VT_BF16 = 0, VT_F32 = 1, VT_U8 = 2 };
@@ -107,6 +107,12 @@ typedef struct vt_gemm_desc {
   int64_t film_g;         /* elements between groups of film_c */
   int64_t film_tg;        /* elements between groups of film_t */
   int32_t film_ld, film_C, film_off;
+  float* raw_out;         /* VT_EPI_GN with bf16 in / out, bn 256 (training forward): ALSO store conv + bias, the value GroupNorm
+                             sees, as fp32 at raw_out[g * raw_g + m * raw_ld + n] (m = logical row).  It is what the backward of
+                             GroupNorm + Mish reads (autograd keeps this tensor for conditional_unet_1D.py:48-52), so the backward
+                             program needs no recomputation of the convolution.  NULL = not stored.  (ABI v6) */
+  int64_t raw_g;
+  int32_t raw_ld;
 } vt_gemm_desc;
 
 /* LayerNorm over the last dim (HF:354,359,449; lstm_step_controller.py:76-82).  Row r of the output is computed

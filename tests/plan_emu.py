@@ -93,6 +93,8 @@ def emu_gemm(plan: Plan, d: nv.GemmDesc):
             gamma = _flat(plan, d.gn_gamma, torch.float32)[g * d.n_pad: g * d.n_pad + N]
             beta = _flat(plan, d.gn_beta, torch.float32)[g * d.n_pad: g * d.n_pad + N]
             assert d.row_div == d.t_box == t_out
+            if d.raw_out:                                               # training forward: conv + bias as GroupNorm sees it
+                _store(plan, d.raw_out, nv.VT_F32, g * d.raw_g + m[:, None] * d.raw_ld + ncol[None, :], x, 0)
             xs = x.reshape(d.a_B, t_out, N).permute(0, 2, 1)          # [B, C, T]
             xs = F.group_norm(xs, N // d.gn_group_ch, gamma, beta, d.gn_eps)
             xs = F.mish(xs).permute(0, 2, 1).reshape(M, N)

@@ -362,3 +362,31 @@ def test_gather_repack_equals_the_tensor_op_repack(monkeypatch):
     fresh = prog.W._pack(si._net_state_dicts())
     for k, t in prog.W.t.items():
         assert torch.equal(t, fresh[k]), k
+
+
+def test_saved_raw_conv_outputs_equal_the_recomputed_ones(monkeypatch):
+    """vt_gemm_desc.raw_out (ABI v6): the training forward's GroupNorm epilogue also stores conv + bias as fp32, so the backward needs
+    no recomputation GEMM.  The stored values are the same accumulators + bias the recompute produced: every gradient, d obs_cond
+    and the losses are bit-identical between the two forms of the program, and the new form has 25 GEMM ops fewer."""
+    from vla_touch_b200 import shapes as shp
+    from vla_touch_b200 import synthetic as syn
+    from vla_touch_b200.params import sub_state_dict
+    from vla_touch_b200.unet_train import LossBackwardProgram
+    A, T, B = 7, 32, 5
+    full = syn.synth_state_dict(shp.si_net_shapes(A, 256), 77, prefix="net.")
+    sds = [sub_state_dict(full, p) for p in ("b_net.", "v_net.", "s_net.")]
+    g = torch.Generator().manual_seed(77)
+    inputs = (torch.rand(B, T, A, generator=g) * 2 - 1, torch.rand(B, T, A, generator=g) * 2 - 1, torch.randn(B, 256, generator=g),
+              torch.rand(B, generator=g), torch.randn(B, T, A, generator=g))
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("VT_TRAIN_RECOMPUTE", mode)
+        lp = LossBackwardProgram(sds, A, B, T, 0.03, DEV)
+        lp.set_inputs(*inputs)
+        out = lp.run().clone()
+        res[mode] = (out, {k: v.clone() for k, v in lp.grads.items()}, lp.d_cond.clone(), len(lp.plan))
+    (o1, g1, d1, n1), (o0, g0, d0, n0) = res["1"], res["0"]
+    assert n1 - n0 == 25 * 1, (n1, n0)                      # 12 blocks x 2 + final_conv.0, one grouped GEMM each
+    assert torch.equal(o1, o0) and torch.equal(d1, d0)
+    for k in g1:
+        assert torch.equal(g1[k], g0[k]), k

@@ -119,6 +119,9 @@ struct GemmArgs {
   long long film_g;     // group stride of film_c (elements)
   long long film_tg;    // group stride of film_t (elements)
   int film_ld, film_C, film_off;
+  float* raw;          // EPI_GN fast path: fp32 copy of acc + bias at raw[g * raw_g + logical row * raw_ld + n], or null
+  long long raw_g;
+  int raw_ld;
 };
 
 template <typename TIn>
@@ -616,6 +619,7 @@ __device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, EpiTile& t, 
   const bf* resp = (a.res && t.valid) ? reinterpret_cast<const bf*>(a.res) + (long long)t.g * a.res_g + res_row * a.ldres + t.n0 + cb : nullptr;
   const float* filmp = (a.film_c && !films) ? a.film_c + (long long)t.g * a.film_g + (long long)t.q * a.film_ld + a.film_off + t.n0 + cb : nullptr;
   const float* fs = films ? films + (t.valid ? (t.r / a.gn_rows) : 0) * 2 * BN + cb : nullptr;   // this row's sample
+  float* rawp = (a.raw && t.valid) ? a.raw + (long long)t.g * a.raw_g + ((long long)t.q * a.row_div + t.rem) * a.raw_ld + t.n0 + cb : nullptr;
   // 32-byte accesses when rows and chunk offsets allow (chunks are 64 bytes apart): half the L1 wavefronts of the row-per-lane pattern
   const bool out32 = ((reinterpret_cast<uintptr_t>(outp) | (uintptr_t)((long long)a.ldc * 2)) & 31) == 0;
   const bool res32 = resp && ((reinterpret_cast<uintptr_t>(resp) | (uintptr_t)((long long)a.ldres * 2)) & 31) == 0;
@@ -707,6 +711,7 @@ __device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, EpiTile& t, 
         const float4 e4 = *reinterpret_cast<const float4*>(colv + 2 * BN + cb + c0 + 4 * h);
         const float2 x0 = fadd2(make_float2(__uint_as_float(v[4 * h]), __uint_as_float(v[4 * h + 1])), make_float2(b4.x, b4.y));
         const float2 x1 = fadd2(make_float2(__uint_as_float(v[4 * h + 2]), __uint_as_float(v[4 * h + 3])), make_float2(b4.z, b4.w));
+        if (rawp) *reinterpret_cast<float4*>(rawp + c0 + 4 * h) = make_float4(x0.x, x0.y, x1.x, x1.y);   // training: what GroupNorm sees
         y[2 * h] = ffma2(ffma2(x0, rs2, nm2), make_float2(g4.x, g4.y), make_float2(e4.x, e4.y));
         y[2 * h + 1] = ffma2(ffma2(x1, rs2, nm2), make_float2(g4.z, g4.w), make_float2(e4.z, e4.w));
       }

@@ -18,7 +18,7 @@ ACT_NONE, ACT_GELU, ACT_MISH = 0, 1, 2
 EPI_LINEAR, EPI_GN = 0, 1
 LAYOUT_BHWC, LAYOUT_BCHW = 0, 1
 MAX_TAPS = 8
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 i32, i64, f32, u64, vp = C.c_int32, C.c_int64, C.c_float, C.c_uint64, C.c_void_p
 
@@ -37,6 +37,7 @@ class GemmDesc(C.Structure):
         ("res_g", i64), ("res_q", i64), ("res_r", i64), ("res_off", i64), ("res_plane", i64),
         ("gn_gamma", vp), ("gn_beta", vp), ("gn_group_ch", i32), ("gn_eps", f32),
         ("film_c", vp), ("film_t", vp), ("film_g", i64), ("film_tg", i64), ("film_ld", i32), ("film_C", i32), ("film_off", i32),
+        ("raw_out", vp), ("raw_g", i64), ("raw_ld", i32),
     ]
 
 

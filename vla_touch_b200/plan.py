@@ -124,7 +124,7 @@ def gemm_desc(*, a, in_dtype, a_C, a_T, a_B=1, a_P=1, a_G=1, a_ld, a_sB=0, a_sG=
               out_off=0, out_plane=0, epi=nv.EPI_LINEAR, act=nv.ACT_NONE, bias=None, colscale=None, res=None, ldres=0,
               res_g=0, res_q=0, res_r=0, res_off=0, res_plane=0, gn_gamma=None, gn_beta=None, gn_group_ch=0, gn_eps=1e-5,
               film_c=None, film_t=None, film_g=0, film_tg=0, film_ld=0, film_C=0, film_off=0, passes=1, a_plane=0,
-              w_plane=0) -> nv.GemmDesc:
+              w_plane=0, raw_out=None, raw_g=0, raw_ld=0) -> nv.GemmDesc:
     d = nv.GemmDesc()
     d.a, d.in_dtype, d.a_C, d.a_P, d.a_T, d.a_B, d.a_G = a, in_dtype, a_C, a_P, a_T, a_B, a_G
     d.a_ld, d.a_sB, d.a_sG, d.a_c0, d.kc = a_ld, a_sB if a_sB else a_ld * a_T * a_P, a_sG, a_c0, kc
@@ -141,6 +141,7 @@ def gemm_desc(*, a, in_dtype, a_C, a_T, a_B=1, a_P=1, a_G=1, a_ld, a_sB=0, a_sG=
     d.gn_gamma, d.gn_beta, d.gn_group_ch, d.gn_eps = gn_gamma, gn_beta, gn_group_ch, gn_eps
     d.film_c, d.film_t, d.film_g, d.film_tg = film_c, film_t, film_g, film_tg
     d.film_ld, d.film_C, d.film_off = film_ld, film_C, film_off
+    d.raw_out, d.raw_g, d.raw_ld = raw_out, raw_g, raw_ld
     return d
 
 

@@ -215,8 +215,10 @@ class _View:
 
 def _conv(plan: Plan, W: UnetWeights, B: int, src: _View, dst: _View, w: torch.Tensor, bias: torch.Tensor, *, taps,
           cin_pad: int, n: int, t_out: int, phases: int = 1, gn=None, film=None, res: Optional[_View] = None,
-          out_rows=None, bn: int = 128, out_f32: Optional[torch.Tensor] = None, tag: str = "") -> None:
-    """One grouped implicit-GEMM convolution.  src/dst are channel windows of [G][B][T][ld] buffers."""
+          out_rows=None, bn: int = 128, out_f32: Optional[torch.Tensor] = None, raw: Optional[torch.Tensor] = None,
+          tag: str = "") -> None:
+    """One grouped implicit-GEMM convolution.  src/dst are channel windows of [G][B][T][ld] buffers.
+    raw (GroupNorm convs of the training forward): fp32 [G][B][t_out][n] receiving conv + bias, the input of GroupNorm."""
     m, G = W.mode, W.G
     t_in_q = src.T // phases
     if bn == 128 and not m.precise and n % 256 == 0 and not (gn is not None and os.environ.get("VT_GN_BN") == "128"):
@@ -252,6 +254,9 @@ def _conv(plan: Plan, W: UnetWeights, B: int, src: _View, dst: _View, w: torch.T
         if res is not None:
             kw.update(res=ptr(res.t, res.c0), ldres=res.ld, res_g=B * res.T * res.ld, res_q=t_out, res_r=1, res_off=0,
                       res_plane=m.plane(res.ctot))
+        if raw is not None:
+            assert raw.dtype == torch.float32 and tuple(raw.shape) == (G, B, t_out, n)
+            kw.update(raw_out=ptr(raw), raw_g=B * t_out * n, raw_ld=n)
     plan.add(gemm_desc(**kw), tag)
 
 

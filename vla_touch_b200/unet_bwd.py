@@ -265,25 +265,27 @@ def gn_mish_backward(plan, ctx: DgradCtx, B: int, T: int, C: int, raw: torch.Ten
 
 def conv_block_backward(plan, ctx: DgradCtx, B: int, x: _View, ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor],
                         gammas: Sequence[torch.Tensor], betas: Sequence[torch.Tensor], dout: torch.Tensor, dx: _View, *,
-                        film=None, res: Optional[_View] = None, tag: str = "block"):
+                        film=None, res: Optional[_View] = None, raw: Optional[torch.Tensor] = None, tag: str = "block"):
     """Backward of Conv1dBlock = Conv1d(k, padding k//2) -> GroupNorm(8) -> Mish [-> FiLM] (conditional_unet_1D.py:40-55,
-    97-102) for G nets: the raw conv output is RECOMPUTED with the forward kernel (LINEAR epilogue, fp32) instead of being
-    saved by the forward pass, then  gn_mish_backward -> conv_wgrad -> conv_dgrad.
+    97-102) for G nets.  raw = fp32 [G][B][T][C_out] conv + bias saved by the training forward (vt_gemm_desc.raw_out); None: it is
+    RECOMPUTED here with the forward kernel (LINEAR epilogue, fp32) -- bit-identical, one more GEMM.  Then gn_mish_backward ->
+    conv_wgrad -> conv_dgrad.
     x: bf16 [G][B][T][C_in] view (block input), dout fp32 [G][B][T][C_out], dx: bf16 or fp32 view receiving d x (+ res).
     Returns dict(dw [G][C_out][k * cin_pad], dbias, dgamma, dbeta [G][C_out])."""
     co, ci, K = ws[0].shape
     m, T = ctx.mode, x.T
     dev = plan.device
-    pw = lambda w: _pack_conv([t.to(dev) for t in w], x.C, m)
-    wf = track(ctx, plan.reg(pw(ws)), ws, pw)
-    pb = lambda v: _pack_vec([t.to(dev) for t in v], wf.shape[1])
     pc = lambda v: _pack_vec([t.to(dev) for t in v], co)
-    bf = track(ctx, plan.reg(pb(bs)), bs, pb)
     gm = track(ctx, plan.reg(pc(gammas)), gammas, pc)
     bt = track(ctx, plan.reg(pc(betas)), betas, pc)
-    raw = plan.buf(tag + f"#{len(plan)}.raw", (ctx.G, B, T, co), torch.float32)
-    _conv(plan, ctx, B, x, None, wf, bf, taps=[(0, k - K // 2) for k in range(K)], cin_pad=x.C, n=co, t_out=T, out_f32=raw,
-          tag=tag + ".conv_raw(recompute)")
+    if raw is None:
+        pw = lambda w: _pack_conv([t.to(dev) for t in w], x.C, m)
+        wf = track(ctx, plan.reg(pw(ws)), ws, pw)
+        pb = lambda v: _pack_vec([t.to(dev) for t in v], wf.shape[1])
+        bf = track(ctx, plan.reg(pb(bs)), bs, pb)
+        raw = plan.buf(tag + f"#{len(plan)}.raw", (ctx.G, B, T, co), torch.float32)
+        _conv(plan, ctx, B, x, None, wf, bf, taps=[(0, k - K // 2) for k in range(K)], cin_pad=x.C, n=co, t_out=T, out_f32=raw,
+              tag=tag + ".conv_raw(recompute)")
     draw, dg, db, dbias = gn_mish_backward(plan, ctx, B, T, co, raw, dout, gm, bt, film=film, tag=tag + ".gn+mish.bwd")
     vy = _View(draw, T, co)
     dw = conv_wgrad(plan, ctx, B, vy, x, tap_off=[k - K // 2 for k in range(K)], t_out=T, tag=tag + ".wgrad")
@@ -316,7 +318,7 @@ def colsum(plan, G: int, B: int, x, T: int, tag: str) -> torch.Tensor:
 
 
 def res_block_backward(plan, ctx: DgradCtx, B: int, sds: Sequence[dict], pfx: str, x: _View, y1: _View, dout: torch.Tensor,
-                       dx: _View, film, tag: str = "") -> dict:
+                       dx: _View, film, raws=(None, None), tag: str = "") -> dict:
     """Backward of ConditionalResidualBlock1D (conditional_unet_1D.py:58-105; `_res_block_bwd` of the oracle) for G nets.
 
     sds: the nets' state dicts, pfx the block's key prefix; x: bf16 view of the block input, y1: bf16 view of the FiLM output
@@ -332,7 +334,8 @@ def res_block_backward(plan, ctx: DgradCtx, B: int, sds: Sequence[dict], pfx: st
     # blocks[1]: Conv1d -> GN -> Mish, no FiLM; its d x is d y1 (fp32: it is the d out of blocks[0]'s elementwise backward)
     dy1 = plan.buf(tag + f"#{len(plan)}.dy1", (ctx.G, B, T, co), torch.float32)
     b1 = conv_block_backward(plan, ctx, B, y1, g("blocks.1.block.0.weight"), g("blocks.1.block.0.bias"),
-                             g("blocks.1.block.1.weight"), g("blocks.1.block.1.bias"), dout, _View(dy1, T, co), tag=tag + "blocks.1")
+                             g("blocks.1.block.1.weight"), g("blocks.1.block.1.bias"), dout, _View(dy1, T, co), raw=raws[1],
+                             tag=tag + "blocks.1")
     # residual path: d x += dout (identity) or W_r^T dout (1x1 conv)
     res = dout
     if pfx + "residual_conv.weight" in sds[0]:
@@ -345,7 +348,7 @@ def res_block_backward(plan, ctx: DgradCtx, B: int, sds: Sequence[dict], pfx: st
         out["residual_conv.weight"] = (conv_wgrad(plan, ctx, B, dob, x, tap_off=[0], t_out=T, tag=tag + "residual_conv.wgrad"), 1)
         out["residual_conv.bias"] = colsum(plan, ctx.G, B, dout, T, tag + "residual_conv.dbias")
     b0 = conv_block_backward(plan, ctx, B, x, g("blocks.0.block.0.weight"), g("blocks.0.block.0.bias"),
-                             g("blocks.0.block.1.weight"), g("blocks.0.block.1.bias"), dy1, dx, film=film, res=res,
+                             g("blocks.0.block.1.weight"), g("blocks.0.block.1.bias"), dy1, dx, film=film, res=res, raw=raws[0],
                              tag=tag + "blocks.0")
     for i, b in ((0, b0), (1, b1)):
         K = sds[0][pfx + f"blocks.{i}.block.0.weight"].shape[-1]

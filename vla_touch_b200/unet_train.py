@@ -4,7 +4,9 @@ bridge/networks/conditional_unet_1D.py:194-247) as ONE plan for the G = 3 nets (
 
 Forward: the same fused kernels as inference (implicit-GEMM conv + GroupNorm + Mish + FiLM + residual in the epilogue), but
 every block writes its own buffers, because the backward reads each block's input and FiLM output again.  The raw conv outputs
-are NOT stored: the backward recomputes them (unet_bwd.conv_block_backward).
+(conv + bias, what GroupNorm sees) are stored as fp32 by the forward GEMM's GroupNorm epilogue itself (vt_gemm_desc.raw_out), as
+autograd would keep them; VT_TRAIN_RECOMPUTE=1 restores the older form in which the backward recomputes them
+(unet_bwd.conv_block_backward without `raw`).
 
 Backward, in reverse execution order (`unet_backward` of oracle/vt_oracle_bwd.py is the checker):
   final 1x1 conv, final Conv1dBlock, then per level: ConvTranspose1d (up) / 12 x ConditionalResidualBlock1D / Conv1d stride 2
@@ -16,6 +18,7 @@ Gradient activations are fp32 where an elementwise backward consumes them and ar
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -36,14 +39,17 @@ K1 = [(0, 0)]
 
 
 class _Block:
-    def __init__(self, pfx: str, x: _View, y1: _View, out: _View, r: Optional[_View]):
+    def __init__(self, pfx: str, x: _View, y1: _View, out: _View, r: Optional[_View], raw0=None, raw1=None):
         self.pfx, self.x, self.y1, self.out, self.r = pfx, x, y1, out, r
+        self.raw0, self.raw1 = raw0, raw1          # fp32 [G][B][T][C_out]: conv + bias of blocks[0] / blocks[1] (None: recomputed)
 
 
 class UnetTrainBuffers:
     """Activations of one training forward of G nets on (B, T): one buffer per block output / FiLM output."""
 
-    def __init__(self, plan: Plan, W: UnetWeights, B: int, T: int, tag: str = "tr"):
+    def __init__(self, plan: Plan, W: UnetWeights, B: int, T: int, tag: str = "tr", save_raw: Optional[bool] = None):
+        if save_raw is None:
+            save_raw = os.environ.get("VT_TRAIN_RECOMPUTE") != "1"
         if T % 4 != 0 or T > 128 or T < 4:
             raise ValueError(f"horizon T={T} must be a multiple of 4 in [4, 128]")
         if W.mode.precise:
@@ -76,7 +82,9 @@ class UnetTrainBuffers:
         for i, ((pfx, _, co), (x, out)) in enumerate(zip(block_names(), chain)):
             y1 = V(mk(f"U{i}", out.T, co), out.T, co)
             r = V(mk(f"R{i}", out.T, co), out.T, co) if pfx + "r.w" in W.t else None
-            self.blocks.append(_Block(pfx, x, y1, out, r))
+            raws = [plan.buf(f"{tag}.raw{i}.{j}", (G, B, out.T, co), torch.float32, zero=False) if save_raw else None for j in (0, 1)]
+            self.blocks.append(_Block(pfx, x, y1, out, r, *raws))
+        self.rawF = plan.buf(f"{tag}.rawF", (G, B, T0, d0), torch.float32, zero=False) if save_raw else None
 
 
 def build_unet_train_forward(plan: Plan, W: UnetWeights, tb: UnetTrainBuffers, film: torch.Tensor, tag: str = "fwd") -> None:
@@ -90,14 +98,15 @@ def build_unet_train_forward(plan: Plan, W: UnetWeights, tb: UnetTrainBuffers, f
         b = tb.blocks[k]
         pfx, co, t = b.pfx, b.out.C, b.out.T
         _conv(plan, W, B, b.x, b.y1, T_[pfx + "c0.w"], T_[pfx + "c0.b"], taps=K5, cin_pad=b.x.C, n=co, t_out=t,
-              gn=(T_[pfx + "g0.w"], T_[pfx + "g0.b"]), film=(film, None, 0, W.film_off[pfx]), tag=f"{tag}.{pfx}conv0+gn+mish+film")
+              gn=(T_[pfx + "g0.w"], T_[pfx + "g0.b"]), film=(film, None, 0, W.film_off[pfx]), raw=b.raw0,
+              tag=f"{tag}.{pfx}conv0+gn+mish+film")
         res = b.x
         if b.r is not None:
             _conv(plan, W, B, b.x, b.r, T_[pfx + "r.w"], T_[pfx + "r.b"], taps=K1, cin_pad=b.x.C, n=co, t_out=t,
                   tag=f"{tag}.{pfx}residual_conv")
             res = b.r
         _conv(plan, W, B, b.y1, b.out, T_[pfx + "c1.w"], T_[pfx + "c1.b"], taps=K5, cin_pad=co, n=co, t_out=t,
-              gn=(T_[pfx + "g1.w"], T_[pfx + "g1.b"]), res=res, tag=f"{tag}.{pfx}conv1+gn+mish+res")
+              gn=(T_[pfx + "g1.w"], T_[pfx + "g1.b"]), res=res, raw=b.raw1, tag=f"{tag}.{pfx}conv1+gn+mish+res")
 
     def up(U: int, src: _View, dst: _View, t_in: int, c: int) -> None:
         for ph, taps in ((0, [(0, 0), (0, -1)]), (1, [(0, 1), (0, 0)])):
@@ -114,7 +123,7 @@ def build_unet_train_forward(plan: Plan, W: UnetWeights, tb: UnetTrainBuffers, f
     crb(10); crb(11)
     up(1, tb.A11, tb.F0, T1, d0)
     _conv(plan, W, B, tb.F0, tb.F1, T_["final0.w"], T_["final0.b"], taps=K5, cin_pad=d0, n=d0, t_out=T0,
-          gn=(T_["final0.gw"], T_["final0.gb"]), tag=f"{tag}.final_conv.0+gn+mish")
+          gn=(T_["final0.gw"], T_["final0.gb"]), raw=tb.rawF, tag=f"{tag}.final_conv.0+gn+mish")
     _conv(plan, W, B, tb.F1, None, T_["final1.w"], T_["final1.b"], taps=K1, cin_pad=d0, n=W.A, t_out=T0, bn=32,
           out_f32=tb.out, tag=f"{tag}.final_conv.1")
 
@@ -145,7 +154,7 @@ def build_unet_backward(plan: Plan, W: UnetWeights, sds: Sequence[SD], tb: UnetT
     dF0 = f32("dF0", T0, d0)
     b = ub.conv_block_backward(plan, W, B, tb.F0, g("final_conv.0.block.0.weight"), g("final_conv.0.block.0.bias"),
                                g("final_conv.0.block.1.weight"), g("final_conv.0.block.1.bias"), dF1, V(dF0, T0, d0),
-                               tag=f"{tag}.final_conv.0")
+                               raw=tb.rawF, tag=f"{tag}.final_conv.0")
     grads.update({"final_conv.0.block.0.weight": (b["dw"], 5), "final_conv.0.block.0.bias": (b["dbias"], 0),
                   "final_conv.0.block.1.weight": (b["dgamma"], 0), "final_conv.0.block.1.bias": (b["dbeta"], 0)})
 
@@ -168,7 +177,8 @@ def build_unet_backward(plan: Plan, W: UnetWeights, sds: Sequence[SD], tb: UnetT
     def crb_bwd(k: int, dout, dx: Optional[_View]) -> None:
         blk = tb.blocks[k]
         pfx = blk.pfx
-        out = ub.res_block_backward(plan, W, B, sds, pfx, blk.x, blk.y1, dout, dx, (film, dfilm, W.film_off[pfx]), tag=f"{tag}.{pfx}")
+        out = ub.res_block_backward(plan, W, B, sds, pfx, blk.x, blk.y1, dout, dx, (film, dfilm, W.film_off[pfx]), raws=(blk.raw0, blk.raw1),
+                                    tag=f"{tag}.{pfx}")
         for key, v in out.items():
             grads[pfx + key] = v if isinstance(v, tuple) else (v, 0)
 
