@@ -4,7 +4,7 @@
     compute-sanitizer --tool racecheck python tools/sanitize.py > gpurun_out/sanitizer_racecheck.log
 
 gemm_tc_kernel (linear + GroupNorm epilogues, CTA pairs), mlp_fused_kernel, attn_row_kernel, unet_persist_kernel (whole sampler),
-wgrad_tc_kernel, lstm_tc_kernel / lstm_bwd_tc_kernel -- through the public API at the smallest shapes that reach each kernel."""
+wgrad_tc_kernel, lstm_tc_kernel / lstm_bwd_tc_kernel, batch_gather_kernel, chunk_handoff_kernel -- through the public API at the smallest shapes that reach each kernel."""
 import os
 import sys
 
@@ -42,6 +42,24 @@ def main():
     lp.run()
     torch.cuda.synchronize()
     print("LSTM forward + BPTT (lstm_tc, lstm_bwd_tc):", lp.loss())
+    # episode store (batch_gather_kernel, feature cache through a 2-layer DinoV2) and the RDT hand-off (chunk_handoff_kernel)
+    import tempfile
+    import numpy as np
+    from vla_touch_b200 import controller_dataset as cd
+    from vla_touch_b200 import episode_store as es
+    from vla_touch_b200.rdt_handoff import handoff_action_chunk
+    from vla_touch_b200.synthetic import synth_episode
+    with tempfile.TemporaryDirectory() as td:
+        for e in range(2):
+            es.write_episode_shard(synth_episode(e, 30, 224, still_frames=1), os.path.join(td, f"episode_{e}.vtep"))
+        ds = cd.ControllerDataset(td, horizon=8, use_images=True, image_size=224)
+        store = ds.device_store(dev, image_encoder=ctl.image_encoder, feature_chunk=16)
+    got = store.gather(np.arange(len(ds)))
+    torch.cuda.synchronize()
+    print("episode store gather (batch_gather_kernel):", len(ds), "samples, branch", got["branch"].tolist(), float(got["vla_act"].abs().max()))
+    raw, chunk = handoff_action_chunk(torch.randn(2, 64, 128, device=dev).bfloat16(), 32)
+    torch.cuda.synchronize()
+    print("RDT hand-off (chunk_handoff_kernel):", tuple(raw.shape), tuple(chunk.shape))
 
 
 if __name__ == "__main__":

@@ -704,6 +704,7 @@ __device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, EpiTile& t, 
     {
       // The whole 32-column chunk moves through the phases together (16 independent pairs per phase): the Mish chain
       // (ex2 -> fma -> add -> rcp -> mul) has ~150 cycles of latency and only two warps share a scheduler.
+      uint4 xprev = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
       for (int h = 0; h < 8; ++h) {
         const float4 b4 = *reinterpret_cast<const float4*>(colv + cb + c0 + 4 * h);
@@ -711,7 +712,10 @@ __device__ __forceinline__ void epilogue_gn_fast(const GemmArgs& a, EpiTile& t, 
         const float4 e4 = *reinterpret_cast<const float4*>(colv + 2 * BN + cb + c0 + 4 * h);
         const float2 x0 = fadd2(make_float2(__uint_as_float(v[4 * h]), __uint_as_float(v[4 * h + 1])), make_float2(b4.x, b4.y));
         const float2 x1 = fadd2(make_float2(__uint_as_float(v[4 * h + 2]), __uint_as_float(v[4 * h + 3])), make_float2(b4.z, b4.w));
-        if (rawp) *reinterpret_cast<float4*>(rawp + c0 + 4 * h) = make_float4(x0.x, x0.y, x1.x, x1.y);   // training: what GroupNorm sees
+        if (rawp) {   // training: conv + bias as GroupNorm sees it, 32 bytes per store (rows are 32-byte aligned, checked on the host)
+          if (h & 1) st_global_v8(rawp + c0 + 4 * (h - 1), xprev, make_uint4(__float_as_uint(x0.x), __float_as_uint(x0.y), __float_as_uint(x1.x), __float_as_uint(x1.y)));
+          else xprev = make_uint4(__float_as_uint(x0.x), __float_as_uint(x0.y), __float_as_uint(x1.x), __float_as_uint(x1.y));
+        }
         y[2 * h] = ffma2(ffma2(x0, rs2, nm2), make_float2(g4.x, g4.y), make_float2(e4.x, e4.y));
         y[2 * h + 1] = ffma2(ffma2(x1, rs2, nm2), make_float2(g4.z, g4.w), make_float2(e4.z, e4.w));
       }

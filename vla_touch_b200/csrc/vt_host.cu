@@ -415,7 +415,7 @@ int fill_gemm_args(const vt_gemm_desc& d, int ctas, vt::GemmArgs* out) {
     if (d.raw_out) {
       VT_REQUIRE(d.in_dtype == VT_BF16 && d.out_dtype == VT_BF16 && d.bn == 256 && d.out_plane == 0 && d.res_plane == 0,
                  "gemm: raw_out is written by the bf16 GroupNorm epilogue at bn = 256 only");
-      VT_REQUIRE(d.raw_ld >= d.N && d.raw_ld % 4 == 0 && d.raw_g % 4 == 0 && aligned16(d.raw_out), "gemm: raw_out rows must be 16-byte aligned");
+      VT_REQUIRE(d.raw_ld >= d.N && d.raw_ld % 8 == 0 && d.raw_g % 8 == 0 && ((uintptr_t)d.raw_out & 31) == 0, "gemm: raw_out rows must be 32-byte aligned");
       a.raw = d.raw_out;
       a.raw_g = d.raw_g;
       a.raw_ld = d.raw_ld;
