@@ -471,38 +471,69 @@ struct OptTensor {
   int taps, c, c_pad, reserved;
   __nv_bfloat16* w_op;
 };
+struct AdamScalars {
+  float lr_wd, beta1, beta2, omb1, omb2, step_size, inv_sqrt_bc2, eps, one_minus_decay, grad_scale;
+};
+// one element of torch.optim.AdamW (decoupled weight decay first) + the torch_ema shadow update; same operation order in the scalar
+// and the 128-bit paths below
+__device__ __forceinline__ void adamw_one(const AdamScalars& c, float g, float& p, float& m, float& v, float* s) {
+  g *= c.grad_scale;
+  p *= c.lr_wd;
+  m = c.beta1 * m + c.omb1 * g;
+  v = c.beta2 * v + c.omb2 * g * g;
+  const float denom = sqrtf(v) * c.inv_sqrt_bc2 + c.eps;
+  p -= c.step_size * (m / denom);
+  if (s) *s = *s - c.one_minus_decay * (*s - p);
+}
 __global__ void __launch_bounds__(256) adamw_ema_kernel(const OptTensor* __restrict__ tensors, const long long* __restrict__ chunks,
                                                         int chunk_elems, float lr, float beta1, float beta2, float eps, float wd,
                                                         float bc1, float bc2, float ema_decay, float grad_scale) {
   const OptTensor t = tensors[chunks[2 * blockIdx.x]];
   const long long off = chunks[2 * blockIdx.x + 1];
   const long long end = min(off + (long long)chunk_elems, t.numel);
-  const float step_size = lr / bc1;
-  const float inv_sqrt_bc2 = rsqrtf(bc2);
-  const float one_minus_decay = 1.0f - ema_decay;
+  AdamScalars c;
+  c.lr_wd = 1.0f - lr * wd; c.beta1 = beta1; c.beta2 = beta2; c.omb1 = 1.0f - beta1; c.omb2 = 1.0f - beta2;
+  c.step_size = lr / bc1; c.inv_sqrt_bc2 = rsqrtf(bc2); c.eps = eps; c.one_minus_decay = 1.0f - ema_decay; c.grad_scale = grad_scale;
   const unsigned ct = (unsigned)(t.c * t.taps);
-  for (long long i = off + threadIdx.x; i < end; i += blockDim.x) {
-    long long j = i;
-    if (t.taps > 0) {   // p[(r * c + ci) * taps + k]  <->  g[(r * taps + k) * c_pad + ci]
-      const long long r = i / ct;
-      const unsigned rem = (unsigned)(i - r * ct);
-      const unsigned ci = rem / (unsigned)t.taps, k = rem - ci * (unsigned)t.taps;
-      j = (r * t.taps + k) * t.c_pad + ci;
+  auto gidx = [&](long long i) -> long long {   // p[(r * c + ci) * taps + k]  <->  g[(r * taps + k) * c_pad + ci]
+    if (t.taps <= 0) return i;
+    const long long r = i / ct;
+    const unsigned rem = (unsigned)(i - r * ct);
+    const unsigned ci = rem / (unsigned)t.taps, k = rem - ci * (unsigned)t.taps;
+    return (r * t.taps + k) * t.c_pad + ci;
+  };
+  // 128-bit path: four consecutive parameter elements per thread (p, m, v, shadow as float4; the gradient too when it shares the
+  // parameter's layout, four gathers when it sits in the weight-gradient GEMM's layout) -- 36 B per parameter of HBM traffic
+  const uintptr_t al = (uintptr_t)t.p | (uintptr_t)t.m | (uintptr_t)t.v | (uintptr_t)t.ema | (t.taps <= 0 ? (uintptr_t)t.g : 0);
+  if (((t.numel | off) & 3) == 0 && (al & 15) == 0 && !t.w_op) {
+    for (long long i = off + 4LL * threadIdx.x; i < end; i += 4LL * blockDim.x) {
+      float4 p = *reinterpret_cast<const float4*>(t.p + i), m = *reinterpret_cast<const float4*>(t.m + i);
+      float4 v = *reinterpret_cast<const float4*>(t.v + i);
+      float4 s = t.ema ? *reinterpret_cast<const float4*>(t.ema + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 g;
+      if (t.taps <= 0) g = *reinterpret_cast<const float4*>(t.g + i);
+      else g = make_float4(t.g[gidx(i)], t.g[gidx(i + 1)], t.g[gidx(i + 2)], t.g[gidx(i + 3)]);
+      adamw_one(c, g.x, p.x, m.x, v.x, t.ema ? &s.x : nullptr);
+      adamw_one(c, g.y, p.y, m.y, v.y, t.ema ? &s.y : nullptr);
+      adamw_one(c, g.z, p.z, m.z, v.z, t.ema ? &s.z : nullptr);
+      adamw_one(c, g.w, p.w, m.w, v.w, t.ema ? &s.w : nullptr);
+      *reinterpret_cast<float4*>(t.p + i) = p;
+      *reinterpret_cast<float4*>(t.m + i) = m;
+      *reinterpret_cast<float4*>(t.v + i) = v;
+      if (t.ema) *reinterpret_cast<float4*>(t.ema + i) = s;
     }
-    const float g = t.g[j] * grad_scale;
-    float p = t.p[i] * (1.0f - lr * wd);
-    const float m = beta1 * t.m[i] + (1.0f - beta1) * g;
-    const float v = beta2 * t.v[i] + (1.0f - beta2) * g * g;
-    const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
-    p -= step_size * (m / denom);
+    return;
+  }
+  for (long long i = off + threadIdx.x; i < end; i += blockDim.x) {
+    const long long j = gidx(i);
+    float p = t.p[i], m = t.m[i], v = t.v[i];
+    float s = t.ema ? t.ema[i] : 0.f;
+    adamw_one(c, t.g[j], p, m, v, t.ema ? &s : nullptr);
     t.p[i] = p;
     t.m[i] = m;
     t.v[i] = v;
     if (t.w_op) t.w_op[j] = __float2bfloat16(p);
-    if (t.ema) {
-      const float s = t.ema[i];
-      t.ema[i] = s - one_minus_decay * (s - p);
-    }
+    if (t.ema) t.ema[i] = s;
   }
 }
 
