@@ -16,8 +16,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from vla_touch_b200.synthetic import synth_episode  # noqa: E402
 
-# (episode number, frames, still frames, moving, dark) -- episode_10 / episode_2 check the natural sort, episode_5 is skipped
-EPISODES = [(2, 40, 3, True, False), (10, 31, 0, True, False), (5, 25, 0, False, False), (7, 90, 6, True, True), (1, 22, 2, True, False)]
+# (episode number, frames, still frames, moving, dark) -- episode_10 / episode_2 check the natural sort, episode_5 never moves and is
+# skipped, episode_3 is shorter than context + horizon: it yields no sample but still counts in the statistics
+EPISODES = [(2, 40, 3, True, False), (10, 31, 0, True, False), (5, 25, 0, False, False), (7, 90, 6, True, True), (1, 22, 2, True, False),
+            (3, 9, 0, True, False)]
 CASES = {"h8": dict(context_frames=2, horizon=8, stride=1), "h16s3": dict(context_frames=2, horizon=16, stride=3),
          "h64c1": dict(context_frames=1, horizon=64, stride=2)}
 IMAGE = 28

@@ -61,6 +61,8 @@ def test_dataset_reproduces_the_reference(shard_dir, tag):
     assert stems(ds.file_paths) == stems(GOLD[f"{tag}.files"])                       # natural sort: 1, 2, 5, 7, 10
     assert np.array_equal(np.array(ds.episode_indices, dtype=np.int64), GOLD[f"{tag}.episode_indices"])
     assert len(ds) == len(GOLD[f"{tag}.episode_indices"])
+    used = {stems(ds.file_paths)[fi] for fi, _ in ds.episode_indices}
+    assert "episode_5" not in used and "episode_3" not in used         # never moves / shorter than context + horizon: no samples
     for k, v in ds.stats.items():
         g = GOLD[f"{tag}.stats.{k}"]
         assert v.dtype == g.dtype and np.array_equal(v, g), k
