@@ -12,7 +12,7 @@ from __future__ import annotations
 import fnmatch
 import os
 import re
-from typing import Iterator, List, Optional
+from typing import Iterator, List
 
 import numpy as np
 import torch

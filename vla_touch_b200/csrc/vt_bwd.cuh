@@ -235,8 +235,10 @@ __device__ __forceinline__ void mish_and_grad2(float2 x, float2& m, float2& dm) 
 // Thread = one channel PAIR (packed f32x2 arithmetic, 8-byte shared-memory accesses) and every PARTS-th position; C is a template
 // parameter so that the tile addressing is strength-reduced (the first version spent 128 instructions per element, most of them
 // integer address arithmetic and loop control: 57 % issue utilisation at 0.8 TB/s).
-template <int C>
-__global__ void __launch_bounds__(GNBS_THREADS, 1) gn_mish_bwd_smem_kernel(const GnBwdArgs a) {
+// MINB = 2: two CTAs per SM (<= 64 registers per thread) for the shapes whose tiles take <= 100 KB of shared memory, so that one CTA's
+// loads overlap the other's arithmetic; the 128 KB shapes stay at one CTA per SM.
+template <int C, int MINB = 1>
+__global__ void __launch_bounds__(GNBS_THREADS, MINB) gn_mish_bwd_smem_kernel(const GnBwdArgs a) {
   extern __shared__ float gnb_smem[];
   constexpr int CP = C / 2;                     // channel pairs
   constexpr int PARTS = GNBS_THREADS / CP;      // threads per channel pair: 2 (C = 512), 4 (256), 8 (128)
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(GNBS_THREADS, 1) gn_mish_bwd_smem_kernel(const
   {
     const int n4 = T * C / 4;
     constexpr int c4 = C / 4;
-    constexpr int MAXV = 64 * 512 / 4 / GNBS_THREADS;
+    constexpr int MAXV = MINB == 2 ? 8 : 64 * 512 / 4 / GNBS_THREADS;   // MINB = 2: tiles of <= 12 800 elements (<= 100 KB for both)
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       const float* src = which ? dout : raw;

@@ -712,7 +712,20 @@ struct GnbwdOp : Op {
         VT_CUDA(cudaFuncSetAttribute(vt::gn_mish_bwd_smem_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
       }
-      if (d.C == 128) vt::gn_mish_bwd_smem_kernel<128><<<d.G * d.B, vt::GNBS_THREADS, smem, s>>>(a);
+      const char* e2 = getenv("VT_GNBWD_2CTA");
+      const bool two = smem <= 100 * 1024 && !(e2 && atoi(e2) == 0);   // two CTAs per SM when the tiles allow it
+      if (two) {
+        static bool attr2_set = false;
+        if (!attr2_set) {
+          VT_CUDA(cudaFuncSetAttribute(vt::gn_mish_bwd_smem_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+          VT_CUDA(cudaFuncSetAttribute(vt::gn_mish_bwd_smem_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+          VT_CUDA(cudaFuncSetAttribute(vt::gn_mish_bwd_smem_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+          attr2_set = true;
+        }
+        if (d.C == 128) vt::gn_mish_bwd_smem_kernel<128, 2><<<d.G * d.B, vt::GNBS_THREADS, smem, s>>>(a);
+        else if (d.C == 256) vt::gn_mish_bwd_smem_kernel<256, 2><<<d.G * d.B, vt::GNBS_THREADS, smem, s>>>(a);
+        else vt::gn_mish_bwd_smem_kernel<512, 2><<<d.G * d.B, vt::GNBS_THREADS, smem, s>>>(a);
+      } else if (d.C == 128) vt::gn_mish_bwd_smem_kernel<128><<<d.G * d.B, vt::GNBS_THREADS, smem, s>>>(a);
       else if (d.C == 256) vt::gn_mish_bwd_smem_kernel<256><<<d.G * d.B, vt::GNBS_THREADS, smem, s>>>(a);
       else vt::gn_mish_bwd_smem_kernel<512><<<d.G * d.B, vt::GNBS_THREADS, smem, s>>>(a);
       VT_LAUNCH_CHECK("gn_mish_bwd_smem_kernel");

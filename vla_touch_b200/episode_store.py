@@ -24,7 +24,7 @@ from __future__ import annotations
 import ctypes
 import json
 import os
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
