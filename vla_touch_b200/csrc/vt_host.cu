@@ -606,6 +606,13 @@ struct PackOp : Op {
   vt_pack_desc d;
   int launch(cudaStream_t s) override {
     const int width = d.zero_to > d.cols ? d.zero_to : d.cols;
+    __nv_bfloat16* out16 = reinterpret_cast<__nv_bfloat16*>(d.out) + d.dst_c0;
+    if (d.act == VT_ACT_NONE && d.out_dtype == VT_BF16 && d.src_row_div <= 1 && width == d.cols && d.cols % 8 == 0 && d.src_ld % 4 == 0 &&
+        d.out_ld % 8 == 0 && aligned16(d.src) && aligned16(out16)) {
+      vt::pack_cast8_kernel<<<grid_for((long long)d.rows * (d.cols / 8), 256), 256, 0, s>>>(d.src, d.src_ld, d.rows, d.cols / 8, out16, d.out_ld);
+      VT_LAUNCH_CHECK("pack_cast8_kernel");
+      return VT_OK;
+    }
     vt::pack_kernel<<<grid_for((long long)d.rows * width, 256), 256, 0, s>>>(d.src, d.src_ld, d.rows, d.cols, d.act, d.out,
                                                                              d.out_dtype, d.out_ld, d.dst_c0, d.out_plane,
                                                                              d.zero_to, d.src_row_div);
