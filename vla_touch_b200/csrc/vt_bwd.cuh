@@ -237,11 +237,12 @@ __device__ __forceinline__ void mish_and_grad2(float2 x, float2& m, float2& dm) 
 // integer address arithmetic and loop control: 57 % issue utilisation at 0.8 TB/s).
 // MINB = 2: two CTAs per SM (<= 64 registers per thread) for the shapes whose tiles take <= 100 KB of shared memory, so that one CTA's
 // loads overlap the other's arithmetic; the 128 KB shapes stay at one CTA per SM.
-template <int C, int MINB = 1>
-__global__ void __launch_bounds__(GNBS_THREADS, MINB) gn_mish_bwd_smem_kernel(const GnBwdArgs a) {
+// THREADS = 1024 (64 registers): the 128 KB shapes, which cannot share an SM, run with twice the warps per sample instead.
+template <int C, int MINB = 1, int THREADS = GNBS_THREADS>
+__global__ void __launch_bounds__(THREADS, MINB) gn_mish_bwd_smem_kernel(const GnBwdArgs a) {
   extern __shared__ float gnb_smem[];
   constexpr int CP = C / 2;                     // channel pairs
-  constexpr int PARTS = GNBS_THREADS / CP;      // threads per channel pair: 2 (C = 512), 4 (256), 8 (128)
+  constexpr int PARTS = THREADS / CP;           // threads per channel pair at 512 threads: 2 (C = 512), 4 (256), 8 (128)
   const int T = a.T, Cg = C / a.groups;
   float* s_raw = gnb_smem;              // [T][C]  raw conv output, later x_hat
   float* s_do = s_raw + T * C;          // [T][C]  d out, later d a = d out * scale * mish'
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(GNBS_THREADS, MINB) gn_mish_bwd_smem_kernel(co
   {
     const int n4 = T * C / 4;
     constexpr int c4 = C / 4;
-    constexpr int MAXV = MINB == 2 ? 8 : 64 * 512 / 4 / GNBS_THREADS;   // MINB = 2: tiles of <= 12 800 elements (<= 100 KB for both)
+    constexpr int MAXV = MINB == 2 ? 8 : 64 * 512 / 4 / THREADS;   // MINB = 2: tiles of <= 12 800 elements (<= 100 KB for both)
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       const float* src = which ? dout : raw;
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(GNBS_THREADS, MINB) gn_mish_bwd_smem_kernel(co
       float4 v[MAXV];
 #pragma unroll
       for (int k = 0; k < MAXV; ++k) {
-        const int i = tid + k * GNBS_THREADS;
+        const int i = tid + k * THREADS;
         if (i < n4) {
           const int t = i / c4, cc = (i - t * c4) * 4;
           v[k] = *reinterpret_cast<const float4*>(src + (long long)t * ld + cc);
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(GNBS_THREADS, MINB) gn_mish_bwd_smem_kernel(co
       }
 #pragma unroll
       for (int k = 0; k < MAXV; ++k) {
-        const int i = tid + k * GNBS_THREADS;
+        const int i = tid + k * THREADS;
         if (i < n4) dst[i] = v[k];
       }
     }
@@ -410,8 +411,8 @@ __global__ void __launch_bounds__(GNBS_THREADS, MINB) gn_mish_bwd_smem_kernel(co
     }
   }
 }
-__host__ __device__ constexpr size_t gnbs_smem_bytes(int T, int C) {
-  return (size_t)(2 * T * C + 4 * (GNBS_THREADS / (C / 2)) * C + 2 * C + 256) * sizeof(float);
+__host__ __device__ constexpr size_t gnbs_smem_bytes(int T, int C, int threads = GNBS_THREADS) {
+  return (size_t)(2 * T * C + 4 * (threads / (C / 2)) * C + 2 * C + 256) * sizeof(float);
 }
 
 // out_k[g][c] = sum_b part[g][b][k][c], k = 0..2 -> (d gamma, d beta, d bias), each [G][p_ld]

@@ -732,6 +732,18 @@ struct GnbwdOp : Op {
         if (d.C == 128) vt::gn_mish_bwd_smem_kernel<128, 2><<<d.G * d.B, vt::GNBS_THREADS, smem, s>>>(a);
         else if (d.C == 256) vt::gn_mish_bwd_smem_kernel<256, 2><<<d.G * d.B, vt::GNBS_THREADS, smem, s>>>(a);
         else vt::gn_mish_bwd_smem_kernel<512, 2><<<d.G * d.B, vt::GNBS_THREADS, smem, s>>>(a);
+      } else if (const char* e3 = getenv("VT_GNBWD_1024"); d.C >= 256 && d.T % (1024 / (d.C / 2)) == 0 && vt::gnbs_smem_bytes(d.T, d.C, 1024) <= 200 * 1024 &&
+                 !(e3 && atoi(e3) == 0)) {
+        // the shapes that own an SM alone: 1024 threads (twice the warps per sample) at 64 registers
+        static bool attr3_set = false;
+        if (!attr3_set) {
+          VT_CUDA(cudaFuncSetAttribute(vt::gn_mish_bwd_smem_kernel<256, 1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+          VT_CUDA(cudaFuncSetAttribute(vt::gn_mish_bwd_smem_kernel<512, 1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+          attr3_set = true;
+        }
+        const size_t smem3 = vt::gnbs_smem_bytes(d.T, d.C, 1024);
+        if (d.C == 256) vt::gn_mish_bwd_smem_kernel<256, 1, 1024><<<d.G * d.B, 1024, smem3, s>>>(a);
+        else vt::gn_mish_bwd_smem_kernel<512, 1, 1024><<<d.G * d.B, 1024, smem3, s>>>(a);
       } else if (d.C == 128) vt::gn_mish_bwd_smem_kernel<128><<<d.G * d.B, vt::GNBS_THREADS, smem, s>>>(a);
       else if (d.C == 256) vt::gn_mish_bwd_smem_kernel<256><<<d.G * d.B, vt::GNBS_THREADS, smem, s>>>(a);
       else vt::gn_mish_bwd_smem_kernel<512><<<d.G * d.B, vt::GNBS_THREADS, smem, s>>>(a);
