@@ -169,3 +169,20 @@ def test_lstm_trainer_step_from_the_store(big_dir):
     idx = np.arange(12)
     losses = [float(tr.train_step(store.gather(idx))) for _ in range(6)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+def test_pinned_camera_batches_give_the_same_features():
+    """visual_encoder.forward_two_cameras: pinned host batches (the DataLoader's pin_memory=True) take the side-stream upload path;
+    features must equal the plain two-call path bit for bit, for the 5-D uint8 and the float layouts."""
+    from vla_touch_b200.visual_encoder import forward_two_cameras
+    enc = _encoder()
+    g = torch.Generator().manual_seed(3)
+    u8 = [torch.randint(90, 256, (6, 1, 224, 224, 3), generator=g, dtype=torch.uint8) for _ in range(2)]
+    f32 = [t[:, 0].float() / 255.0 for t in u8]
+    for a, b in (u8, f32):
+        want = (enc.forward(a.to(DEV)), enc.forward(b.to(DEV)))
+        for _ in range(2):                                  # twice: the second call reuses the side stream and freed blocks
+            got = forward_two_cameras(enc, a.pin_memory(), b.pin_memory())
+            assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+        plain = forward_two_cameras(enc, a, b)              # pageable host tensors: the plain path
+        assert torch.equal(plain[0], want[0]) and torch.equal(plain[1], want[1])

@@ -18,7 +18,7 @@ from . import native as nv
 from .bridge.bridge_model import StochasticInterpolants
 from .controller_dataset import denormalize_actions, normalize_actions  # noqa: F401  (re-exported like the reference)
 from .engine import BridgeEngine
-from .visual_encoder import DINOv2Encoder, prepare_images
+from .visual_encoder import DINOv2Encoder, forward_two_cameras, prepare_images
 
 
 class DiffusionController:
@@ -170,7 +170,7 @@ class DiffusionController:
     def encode_images(self, images_cam1, images_cam2):
         if images_cam1 is None or images_cam2 is None or self.image_encoder is None:
             return None
-        return self.image_encoder.forward(images_cam1), self.image_encoder.forward(images_cam2)
+        return forward_two_cameras(self.image_encoder, images_cam1, images_cam2)
 
     def _trains_encoder(self) -> bool:
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.state_encoder.parameters())

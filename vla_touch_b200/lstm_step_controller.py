@@ -18,7 +18,7 @@ from .controller_dataset import denormalize_actions, normalize_actions
 from .engine import MlpWeights, _affine_desc, _pack_desc, build_mlp
 from .plan import Plan, linear_desc, ptr, round_up
 from .unet import Mode
-from .visual_encoder import DINOv2Encoder
+from .visual_encoder import DINOv2Encoder, forward_two_cameras
 
 SD = Dict[str, torch.Tensor]
 
@@ -175,7 +175,7 @@ class TactileLSTMController:
 
     @torch.no_grad()
     def encode_images(self, images_cam1, images_cam2):
-        return self.image_encoder.forward(images_cam1), self.image_encoder.forward(images_cam2)
+        return forward_two_cameras(self.image_encoder, images_cam1, images_cam2)
 
     def _grad_wanted(self, modules) -> bool:
         return torch.is_grad_enabled() and any(p.requires_grad for m in modules for p in m.parameters())

@@ -65,6 +65,36 @@ def prepare_images(images, device, keep_pinned_host: bool = False):
     return images.to(device, non_blocking=True).contiguous(), layout
 
 
+_side_streams: Dict[str, "torch.cuda.Stream"] = {}
+
+
+def forward_two_cameras(enc: "DINOv2Encoder", images_cam1, images_cam2):
+    """(enc.forward(cam1), enc.forward(cam2)) as the reference's encode_images calls them (bridge_controller.py:99-110).  When both
+    batches are pinned host tensors (a DataLoader with pin_memory=True, controller_dataset.py:451-459) the second camera's
+    host -> device copy runs on a side stream behind the first one's and overlaps the first camera's ViT forward; the values
+    and the order of the two forward calls on the caller's stream are unchanged."""
+    pinned = lambda t: torch.is_tensor(t) and t.device.type == "cpu" and t.is_pinned()
+    if not (pinned(images_cam1) and pinned(images_cam2)) or not torch.cuda.is_available():
+        return enc.forward(images_cam1), enc.forward(images_cam2)
+    dev = torch.device(enc.device)
+    main = torch.cuda.current_stream(dev)
+    side = _side_streams.get(str(dev))
+    if side is None:
+        side = _side_streams[str(dev)] = torch.cuda.Stream(device=dev)
+    d1 = images_cam1.to(dev, non_blocking=True)
+    up1 = torch.cuda.Event()
+    up1.record(main)
+    side.wait_event(up1)                        # one copy at a time on the link: camera 2 follows camera 1
+    with torch.cuda.stream(side):
+        d2 = images_cam2.to(dev, non_blocking=True)
+        up2 = torch.cuda.Event()
+        up2.record(side)
+    f1 = enc.forward(d1)
+    main.wait_event(up2)
+    d2.record_stream(main)                      # allocated on the side stream, consumed on the caller's
+    return f1, enc.forward(d2)
+
+
 class DINOv2Encoder:
     def __init__(self, model_name="facebook/dinov2-small", device="cuda", state_dict=None, precise: bool = False,
                  allow_synthetic_weights: bool = False, num_layers: Optional[int] = None):
