@@ -365,3 +365,11 @@ class DeviceEpisodeStore:
         nv.check(nv.lib().vt_batch_gather(ctypes.byref(d), nv.current_stream_ptr()))
         self._keep = (start, d)
         return out
+
+
+if __name__ == "__main__":      # python -m vla_touch_b200.episode_store <dir with *.h5> <dir for *.vtep> [--no-images]
+    import sys
+    if len(sys.argv) < 3:
+        raise SystemExit("usage: python -m vla_touch_b200.episode_store SRC_DIR DST_DIR [--no-images]")
+    done = convert_directory(sys.argv[1], sys.argv[2], with_images="--no-images" not in sys.argv)
+    print(f"wrote {len(done)} shards under {sys.argv[2]}")
