@@ -152,3 +152,31 @@ def test_device_store_needs_the_gpu(shard_dir):
     ds = cd.ControllerDataset(shard_dir, **CASES["h8"])
     with pytest.raises(nv.NativeError):
         ds.device_store()
+
+
+def test_dataset_reads_hdf5_episodes_through_h5py(tmp_path, monkeypatch):
+    """The `.h5` route (open_episode -> h5py.File) with the stand-in h5py the fixture generator uses for the reference (h5py is not in
+    this image): same items, index mapping and statistics as the reference got from the very same `File` objects."""
+    import types
+    from oracle import gen_golden_dataset as gen
+    gen.make_store()
+    fake = types.ModuleType("h5py")
+    fake.File = gen._File
+    monkeypatch.setitem(sys.modules, "h5py", fake)
+    for name in gen._STORE:
+        open(tmp_path / name, "wb").close()
+    ds = cd.ControllerDataset(str(tmp_path), use_images=True, image_size=IMAGE, **CASES["h16s3"])
+    assert stems(ds.file_paths) == stems(GOLD["h16s3.files"]) and all(p.endswith(".h5") for p in ds.file_paths)
+    assert np.array_equal(np.array(ds.episode_indices, dtype=np.int64), GOLD["h16s3.episode_indices"])
+    for k, v in ds.stats.items():
+        assert np.array_equal(v, GOLD[f"h16s3.stats.{k}"]), k
+    for i in GOLD["h16s3.picks"]:
+        for k, v in ds[int(i)].items():
+            g = GOLD[f"h16s3.item{i}.{k}"]
+            assert np.array_equal((v[:, ::9, ::9] if k.startswith("images") else v).numpy(), g), (i, k)
+    # and the converter: .h5 -> .vtep shards that read back identically
+    out = es.convert_directory(str(tmp_path), str(tmp_path / "shards"))
+    assert len(out) == len(gen._STORE)
+    ds2 = cd.ControllerDataset(str(tmp_path / "shards"), use_images=False, **CASES["h16s3"])
+    assert ds2.episode_indices == ds.episode_indices
+    assert torch.equal(ds2[3]["states"], ds[3]["states"]) and torch.equal(ds2[3]["vla_actions"], ds[3]["vla_actions"])

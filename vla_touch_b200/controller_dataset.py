@@ -199,7 +199,9 @@ class EpisodeBatchSampler:
 
 class ControllerDataModule:
     """Train / validation split by FILES with numpy's global RNG (controller_dataset.py:428-443): seed numpy the same way and the
-    split is the reference's.  Statistics come from the training files (:446)."""
+    split is the reference's.  `stats` comes from the training files (:446).  (The reference builds both datasets over ALL files first
+    and then swaps their file lists, :431-443, so its `train_dataset.stats` attribute -- which nothing reads -- still holds the all-files
+    statistics; here each dataset is built on its own files.)"""
 
     def __init__(self, data_dir, batch_size=32, num_workers=4, context_frames=2, horizon=8, use_images=True, image_size=384,
                  val_ratio=0.1, stride=1):
