@@ -107,7 +107,7 @@ def test_feature_cache_equals_the_encoder_on_the_batch(big_dir):
                 assert br == want_branch
             err = float((got[key] - ref).abs().max())
             worst = max(worst, err)
-            assert err <= 1e-3 * float(ref.abs().max()), (name, cam, err)
+            assert err == 0.0, (name, cam, err)           # per-image results do not depend on the batch they were computed in
     print(f"feature cache vs encoder on the batch: worst |diff| {worst:.3g}")
 
 
