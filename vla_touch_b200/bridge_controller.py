@@ -233,17 +233,19 @@ class DiffusionController:
             raise RuntimeError("controller.stats is not set (load a checkpoint or assign the normalisation stats)")
         B, T, A = vla_actions.shape
         inject = self.noise_override is not None
-        eng, img1, img2 = self._prep(state, images_cam1, images_cam2, T, inject)
-        self._load_inputs(eng, state, img1, img2, forces)
-        eng.vla.copy_(vla_actions, non_blocking=True)
-        eng.set_stats(self.stats)
-        if inject:
-            eng.noise.copy_(self.noise_override)
-        else:
-            self._seed += 1
-            eng.seed.fill_(self._seed)
-        eng.run_predict(graph=True)
-        return eng.out.clone()
+        with nv.nvtx_range("vt.predict.inputs"):
+            eng, img1, img2 = self._prep(state, images_cam1, images_cam2, T, inject)
+            self._load_inputs(eng, state, img1, img2, forces)
+            eng.vla.copy_(vla_actions, non_blocking=True)
+            eng.set_stats(self.stats)
+            if inject:
+                eng.noise.copy_(self.noise_override)
+            else:
+                self._seed += 1
+                eng.seed.fill_(self._seed)
+        with nv.nvtx_range("vt.predict.program"):
+            eng.run_predict(graph=True)
+            return eng.out.clone()
 
     def get_reconstruction_loss(self, batch_data):
         target_force = batch_data['current_force'].to(self.device)

@@ -275,6 +275,29 @@ def require_b200() -> None:
         raise NativeError(f"vla_touch_b200 needs an sm_100a (B200) device, found compute capability {ma}.{mi}")
 
 
+class nvtx_range:
+    """`with nvtx_range("vt.predict"):` -- an NVTX range around a host-side phase when VT_NVTX=1 (ncu --nvtx / any NVTX-aware profiler
+    can then filter the launches of one phase); a no-op otherwise (the reference has no tracing of its own)."""
+    _on = None
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if nvtx_range._on is None:
+            nvtx_range._on = os.environ.get("VT_NVTX") == "1"
+        if nvtx_range._on:
+            import torch
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if nvtx_range._on:
+            import torch
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def current_stream_ptr() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream

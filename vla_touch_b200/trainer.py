@@ -21,6 +21,7 @@ from typing import Dict, Optional
 import torch
 
 from .controller_dataset import normalize_actions
+from .native import nvtx_range
 from .optim import FusedAdamWEMA, arena_buckets
 
 
@@ -100,7 +101,8 @@ class DiffusionControllerTrainer:
         t = time.perf_counter()
         self.controller.train()
         dm = self.controller.diffusion_model
-        bd = self._prepare_batch_for_diffusion(batch)
+        with nvtx_range("vt.train.prepare_batch"):
+            bd = self._prepare_batch_for_diffusion(batch)
         t = self._tick("prepare_batch", t)
         obs = bd['obs_cond']
         x1, x0 = bd['expert_act'].float(), bd['vla_act'].float()
@@ -145,7 +147,8 @@ class DiffusionControllerTrainer:
             for w in works:
                 w.wait()
         t = self._tick("encoder backward + collective wait", t)
-        self.optimizer.step(grad_scale=1.0 / world)         # AdamW + EMA + cosine LR, one launch
+        with nvtx_range("vt.train.optimizer"):
+            self.optimizer.step(grad_scale=1.0 / world)     # AdamW + EMA + cosine LR, one launch
         self._tick("optimizer", t)
         return {'loss': out[0], 'v_loss': out[1], 's_loss': out[2], 'b_loss': out[3]}
 
