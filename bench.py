@@ -505,6 +505,9 @@ def bench_train_cached(cx, wl, batch, steps, warmup, episodes=4, frames=168):
                     "h2d_bytes_per_step": batch * 8, "d2h_bytes_per_step": 16},
             "store": {"episodes": episodes, "frames": store.frames, "samples": len(store), "A": A, "force_dim": store.Fd,
                       "fill_seconds_incl_feature_cache": fill_s, "feature_cache_bytes": int(store.feats.numel()) * 4},
+            "collective": None if cx.world == 1 else {
+                "op": "NCCL all-reduce (SUM) of the fp32 gradient arena, in place, per bucket on a side stream during backward",
+                "ranks": cx.world, "bytes": int(tr._prog.grad_arena()[0].numel()) * 4},
             "gather_kernel": {"ms": ms_gather, "algorithmic_bytes": batch * (per_sample + per_sample_out), "achieved_gbs": gbs,
                               "peak_gbs": pk.get("hbm_gbs"), "note": "launch-latency-bound at this size (10 MB per minibatch)"},
             "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
